@@ -1,0 +1,125 @@
+/* lqgk.h -- C ABI of liblqgk.so: B200 (sm_100a) kernels for the LQG inverse-optimal-control likelihood.
+ *
+ * Drop-in boundary for ONE hot path of RothkopfLab/lqg.  The reference has no FFI of its own (pure
+ * Python/JAX); these entry points are what an XLA-FFI custom call (or ctypes / torch harness) binds in
+ * place of the reference functions cited per entry.  All paths below are relative to the reference repo.
+ *
+ * Conventions
+ *  - All buffers are caller-owned DEVICE memory.  No allocation, no host synchronisation and no use of the
+ *    default stream inside; kernels are enqueued on `stream` (a cudaStream_t passed as void*).
+ *  - Return 0 (LQGK_OK) or a negative LQGK_E_* code; never throws.  Re-entrant; no mutable globals.
+ *  - Matrices are row-major.  Every matrix has a leading parameter-sample axis and a time axis described by
+ *    element strides: sample_stride 0 = shared by all samples, time_stride 0 = time-invariant
+ *    (the reference stacks T copies: lqg/utils.py:6-35).
+ *  - `_f32` / `_f64` select the I/O element type of matrices, gains, log-likelihoods and gradients.  The
+ *    per-sample recursions always run in FP64 and the per-trial recursions in FP32 (precision).
+ *  - Observations are FP32, time-major x_tm[T+1][N][d] (use lqgk_pack_obs_* once per dataset).
+ *  - Dimension tuple (x, b, u, y, d) = (dynamics state, belief state, control, observation, observed-by-
+ *    experimenter dims) must be one of the compiled instantiations (lqgk_dims_supported), else
+ *    LQGK_E_UNSUPPORTED.
+ */
+#ifndef LQGK_H_
+#define LQGK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LQGK_OK 0
+#define LQGK_E_INVALID (-1)      /* null pointer / non-positive dimension / misaligned buffer          */
+#define LQGK_E_UNSUPPORTED (-2)  /* dimension tuple not instantiated, or time-varying spec in the VJP  */
+#define LQGK_E_WORKSPACE (-3)    /* workspace too small for even one 32-sample chunk                   */
+#define LQGK_E_CUDA (-4)         /* a CUDA runtime call failed (see cudaGetLastError)                  */
+
+typedef struct {
+  int32_t S; /* parameter samples (systems) in this call                              */
+  int32_t N; /* trials per system                                                     */
+  int32_t T; /* time steps; observations have T+1 rows (lqg/system.py:233) */
+  int32_t x, b, u, y, d;
+} LqgkDims;
+
+typedef struct {
+  const void* ptr;       /* NULL = absent (zeros / default)          */
+  int64_t sample_stride; /* elements between samples, 0 = shared     */
+  int64_t time_stride;   /* elements between time steps, 0 = const   */
+} LqgkMat;
+
+/* One LQG specification, mirrors lqg/spec.py:5-19 (LQGSpec).  For the dynamics side only A,B,F,V,W are read. */
+typedef struct {
+  LqgkMat A, B, F, V, W, Q, R;
+  LqgkMat Qf;          /* absent -> Q at the last time step (lqg/utils.py:30)          */
+  LqgkMat q, r, P, qf; /* affine terms, gains API only (zeros in every reference model) */
+} LqgkSpec;
+
+typedef struct {
+  void* ptr;             /* NULL = gradient not wanted */
+  int64_t sample_stride; /* elements between samples   */
+} LqgkMatGrad;
+
+/* Cotangents of a time-invariant spec (sum over time steps). */
+typedef struct {
+  LqgkMatGrad A, B, F, V, W, Q, R, Qf;
+} LqgkSpecGrad;
+
+/* ---- gains -------------------------------------------------------------------------------------------
+ * lqgk_lqr_backward_*: replaces lqg/control/lqr.py:16-42  lqr.backward(spec, eps) -> Gains(L, l, H).
+ *   Outputs L[S][T][u][b], l[S][T][u] (may be NULL), H[S][T][u][u] (may be NULL; the shifted Ht).
+ * lqgk_kf_forward_*:   replaces lqg/belief/kf.py:6-21     kf.forward(spec, Sigma0) -> K.
+ *   sigma0: [b][b] per sample (time_stride ignored); absent -> V[0] V[0]^T (lqg/system.py:158-161).
+ *   Output K[S][T][b][y].
+ * `d` in dims is ignored by the gains entry points (set it to any supported value, e.g. min(x, 2)).    */
+int lqgk_lqr_backward_f32(const LqgkDims* dims, const LqgkSpec* actor, double eps, float* L_out, float* l_out,
+                          float* H_out, void* workspace, size_t workspace_bytes, void* stream);
+int lqgk_lqr_backward_f64(const LqgkDims* dims, const LqgkSpec* actor, double eps, double* L_out, double* l_out,
+                          double* H_out, void* workspace, size_t workspace_bytes, void* stream);
+int lqgk_kf_forward_f32(const LqgkDims* dims, const LqgkSpec* actor, const LqgkMat* sigma0, float* K_out,
+                        void* workspace, size_t workspace_bytes, void* stream);
+int lqgk_kf_forward_f64(const LqgkDims* dims, const LqgkSpec* actor, const LqgkMat* sigma0, double* K_out,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- likelihood ---------------------------------------------------------------------------------------
+ * lqgk_loglik_fwd_*: replaces lqg/system.py:142-248  System.log_likelihood(x) (= conditional_moments +
+ *   numpyro MultivariateNormal(...).to_event(1).log_prob).  Output ll[S][N].
+ * lqgk_loglik_vjp_*: forward + reverse-mode adjoint in one call (what jax.value_and_grad of the above
+ *   computes in the reference, lqg/infer/models.py:34,61,130).  ll_bar[S][N] are the cotangents of ll
+ *   (NULL = all ones).  Time-invariant specs only.  Gradients of absent/defaulted inputs flow to their
+ *   source (Qf absent -> Q; sigma0 absent -> actor V).                                                   */
+int lqgk_loglik_fwd_f32(const LqgkDims* dims, const LqgkSpec* actor, const LqgkSpec* dynamics,
+                        const LqgkMat* sigma0, const float* x_tm, float* ll_out, void* workspace,
+                        size_t workspace_bytes, void* stream);
+int lqgk_loglik_fwd_f64(const LqgkDims* dims, const LqgkSpec* actor, const LqgkSpec* dynamics,
+                        const LqgkMat* sigma0, const float* x_tm, double* ll_out, void* workspace,
+                        size_t workspace_bytes, void* stream);
+int lqgk_loglik_vjp_f32(const LqgkDims* dims, const LqgkSpec* actor, const LqgkSpec* dynamics,
+                        const LqgkMat* sigma0, const float* x_tm, const float* ll_bar, float* ll_out,
+                        const LqgkSpecGrad* actor_grad, const LqgkSpecGrad* dynamics_grad,
+                        const LqgkMatGrad* sigma0_grad, void* workspace, size_t workspace_bytes, void* stream);
+int lqgk_loglik_vjp_f64(const LqgkDims* dims, const LqgkSpec* actor, const LqgkSpec* dynamics,
+                        const LqgkMat* sigma0, const float* x_tm, const double* ll_bar, double* ll_out,
+                        const LqgkSpecGrad* actor_grad, const LqgkSpecGrad* dynamics_grad,
+                        const LqgkMatGrad* sigma0_grad, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- helpers ------------------------------------------------------------------------------------------ */
+/* x[N][T+1][d] (f32 or f64, trial-major as in the reference) -> x_tm[T+1][N][d] float. */
+int lqgk_pack_obs_f32(int32_t N, int32_t T1, int32_t d, const float* x, float* x_tm, void* stream);
+int lqgk_pack_obs_f64(int32_t N, int32_t T1, int32_t d, const double* x, float* x_tm, void* stream);
+
+#define LQGK_MODE_GAINS 0
+#define LQGK_MODE_FWD 1
+#define LQGK_MODE_VJP 2
+/* Bytes of workspace that let `mode` process min(S, max_chunk) samples per internal chunk (max_chunk <= 0:
+ * all S at once).  Any size >= lqgk_workspace_bytes(dims, mode, 32) is accepted; larger = fewer chunks.   */
+size_t lqgk_workspace_bytes(const LqgkDims* dims, int mode, int32_t max_chunk);
+int lqgk_dims_supported(const LqgkDims* dims);
+const char* lqgk_strerror(int code);
+const char* lqgk_version(void);
+/* Number of kernel launches issued by the calling thread's last entry-point call (for bench accounting). */
+int lqgk_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LQGK_H_ */

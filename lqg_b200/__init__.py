@@ -1,0 +1,3 @@
+"""lqg_b200 -- B200-native (sm_100a) implementation of the LQG inverse-optimal-control likelihood path of
+RothkopfLab/lqg, behind the reference's Python API.  See DESIGN.md."""
+__version__ = "0.1.0"

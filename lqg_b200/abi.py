@@ -1,0 +1,228 @@
+"""ctypes binding of the C ABI declared in ``include/lqgk.h``.
+
+Thin and mechanical: builds the ``LqgkDims / LqgkSpec / LqgkMat`` structs from torch tensors (pointer +
+strides, no copies) and calls the entry points.  The product path loads ``liblqgk.so`` (CUDA, sm_100a) through
+:func:`load_library`; there is no CPU fallback -- a missing library raises.  ``tests/`` additionally point
+:class:`Library` at ``tests/emul/liblqgk_emul.so`` (the kernels' step functions compiled for the host) to check
+the math without a GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "liblqgk.so")
+
+MODE_GAINS, MODE_FWD, MODE_VJP = 0, 1, 2
+ACTOR_KEYS = ("A", "B", "F", "V", "W", "Q", "R")
+DYN_KEYS = ("A", "B", "F", "V", "W")
+
+
+class LqgkDims(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("S", "N", "T", "x", "b", "u", "y", "d")]
+
+
+class LqgkMat(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("sample_stride", C.c_int64), ("time_stride", C.c_int64)]
+
+
+class LqgkSpec(C.Structure):
+    _fields_ = [(k, LqgkMat) for k in ("A", "B", "F", "V", "W", "Q", "R", "Qf", "q", "r", "P", "qf")]
+
+
+class LqgkMatGrad(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("sample_stride", C.c_int64)]
+
+
+class LqgkSpecGrad(C.Structure):
+    _fields_ = [(k, LqgkMatGrad) for k in ("A", "B", "F", "V", "W", "Q", "R", "Qf")]
+
+
+class LqgkError(RuntimeError):
+    pass
+
+
+def _mat(t: Optional[torch.Tensor], S: int, T: int, trailing: int = 2) -> LqgkMat:
+    """Describe ``t`` of shape ``([S|1], [T|1], *trailing dims)`` (leading dims optional) without copying."""
+    if t is None:
+        return LqgkMat(None, 0, 0)
+    lead = t.dim() - trailing
+    if lead < 0 or lead > 2:
+        raise ValueError(f"matrix with shape {tuple(t.shape)} has too many/few leading dims")
+    core = t.shape[lead:]
+    exp_stride, n = [], 1
+    for sz in reversed(core):
+        exp_stride.append(n)
+        n *= sz
+    if list(t.stride()[lead:]) != list(reversed(exp_stride)) and n > 1:
+        raise ValueError("trailing matrix dims must be row-major contiguous")
+    ss = ts = 0
+    if lead == 2:
+        if t.shape[0] not in (1, S) or t.shape[1] not in (1, T):
+            raise ValueError(f"leading dims {tuple(t.shape[:2])} do not match (S={S}, T={T})")
+        ss = t.stride(0) if t.shape[0] == S and S > 1 else 0
+        ts = t.stride(1) if t.shape[1] == T and T > 1 else 0
+    elif lead == 1:
+        # a single leading dim is the sample axis (time-invariant per-sample matrices)
+        if t.shape[0] not in (1, S):
+            raise ValueError(f"leading dim {t.shape[0]} does not match S={S}")
+        ss = t.stride(0) if t.shape[0] == S and S > 1 else 0
+    return LqgkMat(t.data_ptr(), ss, ts)
+
+
+class Library:
+    """One loaded implementation of the C ABI."""
+
+    def __init__(self, path: str):
+        if not os.path.exists(path):
+            raise LqgkError(
+                f"{path} not found: the CUDA library is not built (run `python -c 'import __graft_entry__ as g; "
+                f"g.build()'`).  lqg_b200 has no CPU fallback.")
+        self.path = path
+        self.lib = C.CDLL(path)
+        self.lib.lqgk_version.restype = C.c_char_p
+        if hasattr(self.lib, "lqgk_workspace_bytes"):
+            self.lib.lqgk_workspace_bytes.restype = C.c_size_t
+            self.lib.lqgk_workspace_bytes.argtypes = [C.POINTER(LqgkDims), C.c_int, C.c_int32]
+            self.lib.lqgk_strerror.restype = C.c_char_p
+
+    # -- helpers
+    def version(self) -> str:
+        return self.lib.lqgk_version().decode()
+
+    def strerror(self, code: int) -> str:
+        if hasattr(self.lib, "lqgk_strerror"):
+            return self.lib.lqgk_strerror(code).decode()
+        return {-1: "invalid argument", -2: "unsupported dims / time-varying VJP", -3: "workspace too small",
+                -4: "CUDA error"}.get(code, f"error {code}")
+
+    def _check(self, code: int, what: str):
+        if code != 0:
+            raise LqgkError(f"{what} failed: {self.strerror(code)} ({code})")
+
+    def workspace_bytes(self, dims: LqgkDims, mode: int, max_chunk: int = 0) -> int:
+        if not hasattr(self.lib, "lqgk_workspace_bytes"):
+            return 0
+        return int(self.lib.lqgk_workspace_bytes(C.byref(dims), mode, max_chunk))
+
+    @staticmethod
+    def _suffix(dtype) -> str:
+        return {torch.float32: "f32", torch.float64: "f64"}[dtype]
+
+    @staticmethod
+    def _spec(mats: Dict[str, torch.Tensor], S: int, T: int, keys) -> LqgkSpec:
+        sp = LqgkSpec()
+        for k in keys:
+            setattr(sp, k, _mat(mats.get(k), S, T))
+        for k in ("Qf",):
+            setattr(sp, k, _mat(mats.get(k), S, 1))
+        for k, tr in (("q", 1), ("r", 1), ("P", 2), ("qf", 1)):
+            setattr(sp, k, _mat(mats.get(k), S, T if k != "qf" else 1, trailing=tr))
+        return sp
+
+    @staticmethod
+    def _ws(ws: Optional[torch.Tensor]):
+        return (ws.data_ptr(), ws.numel() * ws.element_size()) if ws is not None else (None, 0)
+
+    # -- entry points
+    def lqr_backward(self, dims, actor, eps=1e-8, want_l=True, want_H=True, ws=None, stream=0):
+        dt, dev = actor["A"].dtype, actor["A"].device
+        S, T = dims.S, dims.T
+        L = torch.empty((S, T, dims.u, dims.b), dtype=dt, device=dev)
+        l = torch.empty((S, T, dims.u), dtype=dt, device=dev) if want_l else None
+        H = torch.empty((S, T, dims.u, dims.u), dtype=dt, device=dev) if want_H else None
+        sp = self._spec(actor, S, T, ACTOR_KEYS)
+        p, n = self._ws(ws)
+        fn = getattr(self.lib, "lqgk_lqr_backward_" + self._suffix(dt))
+        self._check(fn(C.byref(dims), C.byref(sp), C.c_double(eps), C.c_void_p(L.data_ptr()),
+                       C.c_void_p(l.data_ptr() if want_l else None), C.c_void_p(H.data_ptr() if want_H else None),
+                       C.c_void_p(p), C.c_size_t(n), C.c_void_p(stream)), "lqgk_lqr_backward")
+        return L, l, H
+
+    def kf_forward(self, dims, actor, sigma0=None, ws=None, stream=0):
+        dt, dev = actor["A"].dtype, actor["A"].device
+        S, T = dims.S, dims.T
+        K = torch.empty((S, T, dims.b, dims.y), dtype=dt, device=dev)
+        sp = self._spec(actor, S, T, ACTOR_KEYS)
+        s0 = _mat(sigma0, S, 1) if sigma0 is not None else None
+        p, n = self._ws(ws)
+        fn = getattr(self.lib, "lqgk_kf_forward_" + self._suffix(dt))
+        self._check(fn(C.byref(dims), C.byref(sp), C.byref(s0) if s0 is not None else None,
+                       C.c_void_p(K.data_ptr()), C.c_void_p(p), C.c_size_t(n), C.c_void_p(stream)), "lqgk_kf_forward")
+        return K
+
+    def loglik_fwd(self, dims, actor, dyn, x_tm, sigma0=None, ws=None, stream=0):
+        dt, dev = actor["A"].dtype, actor["A"].device
+        S, T = dims.S, dims.T
+        assert x_tm.dtype == torch.float32 and x_tm.is_contiguous() and tuple(x_tm.shape) == (T + 1, dims.N, dims.d)
+        ll = torch.empty((S, dims.N), dtype=dt, device=dev)
+        sa, sd = self._spec(actor, S, T, ACTOR_KEYS), self._spec(dyn, S, T, DYN_KEYS)
+        s0 = _mat(sigma0, S, 1) if sigma0 is not None else None
+        p, n = self._ws(ws)
+        fn = getattr(self.lib, "lqgk_loglik_fwd_" + self._suffix(dt))
+        self._check(fn(C.byref(dims), C.byref(sa), C.byref(sd), C.byref(s0) if s0 is not None else None,
+                       C.c_void_p(x_tm.data_ptr()), C.c_void_p(ll.data_ptr()), C.c_void_p(p), C.c_size_t(n),
+                       C.c_void_p(stream)), "lqgk_loglik_fwd")
+        return ll
+
+    def loglik_vjp(self, dims, actor, dyn, x_tm, ll_bar=None, sigma0=None, want_actor=ACTOR_KEYS, want_dyn=DYN_KEYS,
+                   want_qf=False, ws=None, stream=0):
+        """Returns ll[S,N], grads_actor{name: [S,r,c]}, grads_dyn{...}, grad_sigma0 or None."""
+        dt, dev = actor["A"].dtype, actor["A"].device
+        S, T = dims.S, dims.T
+        assert x_tm.dtype == torch.float32 and x_tm.is_contiguous() and tuple(x_tm.shape) == (T + 1, dims.N, dims.d)
+        ll = torch.empty((S, dims.N), dtype=dt, device=dev)
+        sa, sd = self._spec(actor, S, T, ACTOR_KEYS), self._spec(dyn, S, T, DYN_KEYS)
+        s0 = _mat(sigma0, S, 1) if sigma0 is not None else None
+        shp_a = dict(A=(dims.b, dims.b), B=(dims.b, dims.u), F=(dims.y, dims.b), V=(dims.b, dims.b),
+                     W=(dims.y, dims.y), Q=(dims.b, dims.b), R=(dims.u, dims.u), Qf=(dims.b, dims.b))
+        shp_d = dict(A=(dims.x, dims.x), B=(dims.x, dims.u), F=(dims.y, dims.x), V=(dims.x, dims.x), W=(dims.y, dims.y))
+        ga, gd = LqgkSpecGrad(), LqgkSpecGrad()
+        out_a, out_d = {}, {}
+        for k in list(want_actor) + (["Qf"] if want_qf else []):
+            out_a[k] = torch.empty((S,) + shp_a[k], dtype=dt, device=dev)
+            setattr(ga, k, LqgkMatGrad(out_a[k].data_ptr(), out_a[k].stride(0)))
+        for k in want_dyn:
+            out_d[k] = torch.empty((S,) + shp_d[k], dtype=dt, device=dev)
+            setattr(gd, k, LqgkMatGrad(out_d[k].data_ptr(), out_d[k].stride(0)))
+        gs0, out_s0 = None, None
+        if sigma0 is not None:
+            out_s0 = torch.empty((S, dims.b, dims.b), dtype=dt, device=dev)
+            gs0 = LqgkMatGrad(out_s0.data_ptr(), out_s0.stride(0))
+        if ll_bar is not None:
+            ll_bar = ll_bar.to(dt).expand(S, dims.N).contiguous()
+        p, n = self._ws(ws)
+        fn = getattr(self.lib, "lqgk_loglik_vjp_" + self._suffix(dt))
+        self._check(fn(C.byref(dims), C.byref(sa), C.byref(sd), C.byref(s0) if s0 is not None else None,
+                       C.c_void_p(x_tm.data_ptr()), C.c_void_p(ll_bar.data_ptr() if ll_bar is not None else None),
+                       C.c_void_p(ll.data_ptr()), C.byref(ga), C.byref(gd), C.byref(gs0) if gs0 is not None else None,
+                       C.c_void_p(p), C.c_size_t(n), C.c_void_p(stream)), "lqgk_loglik_vjp")
+        return ll, out_a, out_d, out_s0
+
+    def pack_obs(self, x: torch.Tensor, stream=0) -> torch.Tensor:
+        """x[N, T+1, d] (f32/f64) -> time-major float32 x_tm[T+1, N, d] on the same device."""
+        N, T1, d = x.shape
+        x = x.contiguous()
+        out = torch.empty((T1, N, d), dtype=torch.float32, device=x.device)
+        fn = getattr(self.lib, "lqgk_pack_obs_" + self._suffix(x.dtype))
+        self._check(fn(C.c_int32(N), C.c_int32(T1), C.c_int32(d), C.c_void_p(x.data_ptr()),
+                       C.c_void_p(out.data_ptr()), C.c_void_p(stream)), "lqgk_pack_obs")
+        return out
+
+    def last_launch_count(self) -> int:
+        return int(self.lib.lqgk_last_launch_count())
+
+
+_LIB: Optional[Library] = None
+
+
+def load_library() -> Library:
+    """The product library (CUDA).  Raises if it has not been built -- there is no fallback."""
+    global _LIB
+    if _LIB is None:
+        _LIB = Library(LIB_PATH)
+    return _LIB

@@ -1,0 +1,152 @@
+// lqgk_api.cu -- extern "C" entry points of liblqgk.so (see include/lqgk.h): validation, dimension dispatch,
+// workspace planning, chunking over parameter samples and the kernel launch sequence.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+
+#include "../../include/lqgk.h"
+#include "lqgk_dims.h"
+#include "lqgk_run.cuh"
+
+using namespace lqgk;
+
+namespace lqgk {
+thread_local int g_launches = 0;
+}
+
+namespace {
+
+int validate(const Call& c) {
+  if (!c.dims || !c.act) return LQGK_E_INVALID;
+  const LqgkDims& d = *c.dims;
+  if (d.S <= 0 || d.T <= 0 || d.x <= 0 || d.b <= 0 || d.u <= 0 || d.y <= 0) return LQGK_E_INVALID;
+  if (!c.act->A.ptr || !c.act->B.ptr) return LQGK_E_INVALID;
+  if (c.mode != LQGK_MODE_GAINS) {
+    if (d.N <= 0 || d.d <= 0 || d.d > d.x) return LQGK_E_INVALID;
+    if (!c.dyn || !c.x_tm || !c.ll_out) return LQGK_E_INVALID;
+    const LqgkMat* need[] = {&c.act->F, &c.act->V, &c.act->W, &c.act->Q, &c.act->R, &c.dyn->A, &c.dyn->B, &c.dyn->F, &c.dyn->V, &c.dyn->W};
+    for (auto m : need)
+      if (!m->ptr) return LQGK_E_INVALID;
+    if (((uintptr_t)c.x_tm % 16) != 0) return LQGK_E_INVALID;
+  }
+  return LQGK_OK;
+}
+
+template <class T>
+int dispatch(const Call& c) {
+  g_launches = 0;
+  int rc = validate(c);
+  if (rc) return rc;
+  const LqgkDims& d = *c.dims;
+#define LQGK_CASE(X, B, U, Y, DD)                                                                       \
+  if (d.x == X && d.b == B && d.u == U && d.y == Y && (d.d == DD || c.mode == LQGK_MODE_GAINS))         \
+    return std::is_same<T, float>::value ? Runner<X, B, U, Y, DD>::run_f32(c) : Runner<X, B, U, Y, DD>::run_f64(c);
+  LQGK_FOR_EACH_DIMS(LQGK_CASE)
+#undef LQGK_CASE
+  return LQGK_E_UNSUPPORTED;
+}
+
+template <class T>
+int pack_obs(int32_t N, int32_t T1, int32_t d, const T* x, float* x_tm, void* stream) {
+  g_launches = 0;
+  if (N <= 0 || T1 <= 0 || d <= 0 || !x || !x_tm) return LQGK_E_INVALID;
+  size_t total = (size_t)N * T1 * d;
+  k_pack_obs<T><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(N, T1, d, x, x_tm);
+  LQGK_LAUNCH_CHECK();
+  return LQGK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lqgk_lqr_backward_f32(const LqgkDims* dims, const LqgkSpec* actor, double eps, float* L_out, float* l_out, float* H_out,
+                          void* ws, size_t ws_bytes, void* stream) {
+  Call c{dims, actor, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, L_out, l_out, H_out, nullptr, eps, LQGK_MODE_GAINS, ws, ws_bytes, (cudaStream_t)stream};
+  if (!L_out) return LQGK_E_INVALID;
+  return dispatch<float>(c);
+}
+int lqgk_lqr_backward_f64(const LqgkDims* dims, const LqgkSpec* actor, double eps, double* L_out, double* l_out, double* H_out,
+                          void* ws, size_t ws_bytes, void* stream) {
+  Call c{dims, actor, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, L_out, l_out, H_out, nullptr, eps, LQGK_MODE_GAINS, ws, ws_bytes, (cudaStream_t)stream};
+  if (!L_out) return LQGK_E_INVALID;
+  return dispatch<double>(c);
+}
+int lqgk_kf_forward_f32(const LqgkDims* dims, const LqgkSpec* actor, const LqgkMat* sigma0, float* K_out, void* ws,
+                        size_t ws_bytes, void* stream) {
+  Call c{dims, actor, nullptr, sigma0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, K_out, 1e-8, LQGK_MODE_GAINS, ws, ws_bytes, (cudaStream_t)stream};
+  if (!K_out) return LQGK_E_INVALID;
+  return dispatch<float>(c);
+}
+int lqgk_kf_forward_f64(const LqgkDims* dims, const LqgkSpec* actor, const LqgkMat* sigma0, double* K_out, void* ws,
+                        size_t ws_bytes, void* stream) {
+  Call c{dims, actor, nullptr, sigma0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, K_out, 1e-8, LQGK_MODE_GAINS, ws, ws_bytes, (cudaStream_t)stream};
+  if (!K_out) return LQGK_E_INVALID;
+  return dispatch<double>(c);
+}
+int lqgk_loglik_fwd_f32(const LqgkDims* dims, const LqgkSpec* actor, const LqgkSpec* dynamics, const LqgkMat* sigma0,
+                        const float* x_tm, float* ll_out, void* ws, size_t ws_bytes, void* stream) {
+  Call c{dims, actor, dynamics, sigma0, x_tm, nullptr, ll_out, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 1e-8, LQGK_MODE_FWD, ws, ws_bytes, (cudaStream_t)stream};
+  return dispatch<float>(c);
+}
+int lqgk_loglik_fwd_f64(const LqgkDims* dims, const LqgkSpec* actor, const LqgkSpec* dynamics, const LqgkMat* sigma0,
+                        const float* x_tm, double* ll_out, void* ws, size_t ws_bytes, void* stream) {
+  Call c{dims, actor, dynamics, sigma0, x_tm, nullptr, ll_out, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 1e-8, LQGK_MODE_FWD, ws, ws_bytes, (cudaStream_t)stream};
+  return dispatch<double>(c);
+}
+int lqgk_loglik_vjp_f32(const LqgkDims* dims, const LqgkSpec* actor, const LqgkSpec* dynamics, const LqgkMat* sigma0,
+                        const float* x_tm, const float* ll_bar, float* ll_out, const LqgkSpecGrad* ga, const LqgkSpecGrad* gd,
+                        const LqgkMatGrad* gs, void* ws, size_t ws_bytes, void* stream) {
+  Call c{dims, actor, dynamics, sigma0, x_tm, ll_bar, ll_out, ga, gd, gs, nullptr, nullptr, nullptr, nullptr, 1e-8, LQGK_MODE_VJP, ws, ws_bytes, (cudaStream_t)stream};
+  return dispatch<float>(c);
+}
+int lqgk_loglik_vjp_f64(const LqgkDims* dims, const LqgkSpec* actor, const LqgkSpec* dynamics, const LqgkMat* sigma0,
+                        const float* x_tm, const double* ll_bar, double* ll_out, const LqgkSpecGrad* ga, const LqgkSpecGrad* gd,
+                        const LqgkMatGrad* gs, void* ws, size_t ws_bytes, void* stream) {
+  Call c{dims, actor, dynamics, sigma0, x_tm, ll_bar, ll_out, ga, gd, gs, nullptr, nullptr, nullptr, nullptr, 1e-8, LQGK_MODE_VJP, ws, ws_bytes, (cudaStream_t)stream};
+  return dispatch<double>(c);
+}
+
+int lqgk_pack_obs_f32(int32_t N, int32_t T1, int32_t d, const float* x, float* x_tm, void* stream) {
+  return pack_obs<float>(N, T1, d, x, x_tm, stream);
+}
+int lqgk_pack_obs_f64(int32_t N, int32_t T1, int32_t d, const double* x, float* x_tm, void* stream) {
+  return pack_obs<double>(N, T1, d, x, x_tm, stream);
+}
+
+size_t lqgk_workspace_bytes(const LqgkDims* dims, int mode, int32_t max_chunk) {
+  if (!dims) return 0;
+  const LqgkDims& d = *dims;
+#define LQGK_CASE(X, B, U, Y, DD)                                                              \
+  if (d.x == X && d.b == B && d.u == U && d.y == Y && (d.d == DD || mode == LQGK_MODE_GAINS)) \
+    return Runner<X, B, U, Y, DD>::plan_bytes(d, mode, max_chunk);
+  LQGK_FOR_EACH_DIMS(LQGK_CASE)
+#undef LQGK_CASE
+  return 0;
+}
+
+int lqgk_dims_supported(const LqgkDims* dims) {
+  if (!dims) return 0;
+  const LqgkDims& d = *dims;
+#define LQGK_CASE(X, B, U, Y, DD) \
+  if (d.x == X && d.b == B && d.u == U && d.y == Y && d.d == DD) return 1;
+  LQGK_FOR_EACH_DIMS(LQGK_CASE)
+#undef LQGK_CASE
+  return 0;
+}
+
+const char* lqgk_strerror(int code) {
+  switch (code) {
+    case LQGK_OK: return "ok";
+    case LQGK_E_INVALID: return "invalid argument (null pointer, non-positive dimension or misaligned buffer)";
+    case LQGK_E_UNSUPPORTED: return "unsupported: dimension tuple not compiled in, or time-varying spec passed to the VJP";
+    case LQGK_E_WORKSPACE: return "workspace too small for one 32-sample chunk (see lqgk_workspace_bytes)";
+    case LQGK_E_CUDA: return "CUDA runtime error";
+    default: return "unknown error";
+  }
+}
+const char* lqgk_version(void) { return "lqgk 0.1.0 (sm_100a)"; }
+int lqgk_last_launch_count(void) { return g_launches; }
+
+}  // extern "C"

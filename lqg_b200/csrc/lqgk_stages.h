@@ -1,0 +1,187 @@
+// lqgk_stages.h -- whole-sweep bodies of the per-sample (FP64) stages, one call per parameter sample.
+//
+// On the GPU each body is executed by one thread (lane = sample, 32 samples per warp-CTA) with the derived
+// constants and cotangent accumulators in shared memory (view stride 32); tests/emul runs the same bodies on
+// the CPU with stride-1 local arrays.  Workspace arrays are sample-minor: row (t * E + e) of W lives at
+// W.p[(t * E + e) * W.stride], so a warp's accesses are coalesced.
+#pragma once
+#include "lqgk_core.h"
+
+namespace lqgk {
+
+template <class KC, class G, class Lc>
+LQGK_HD void load_consts(const G& g, Lc&& l, int nseg) {
+  for (int i = 0; i < nseg; ++i) {
+    int go, lo, len;
+    KC::seg(i, go, lo, len);
+    for (int e = 0; e < len; ++e) l(lo + e) = g(go + e);
+  }
+}
+template <class KC, class G, class La>
+LQGK_HD void flush_acc(G&& g, const La& l, int nseg) {
+  for (int i = 0; i < nseg; ++i) {
+    int go, lo, len;
+    KC::seg(i, go, lo, len);
+    for (int e = 0; e < len; ++e) g(go + e) += l(lo + e);
+  }
+}
+template <int M, class W>
+LQGK_HD void store_sym(W&& w, size_t off, const double* C) {
+  LQGK_UNROLL for (int i = 0; i < M; ++i) LQGK_UNROLL for (int j = 0; j <= i; ++j) w(off + i * (i + 1) / 2 + j) = C[i * M + j];
+}
+template <int M, class W>
+LQGK_HD void load_sym_ws(const W& w, size_t off, double* C) {
+  LQGK_UNROLL for (int i = 0; i < M; ++i) LQGK_UNROLL for (int j = 0; j <= i; ++j) {
+    double a = w(off + i * (i + 1) / 2 + j);
+    C[i * M + j] = a;
+    C[j * M + i] = a;
+  }
+}
+
+// gcst: this sample's global constant block (stride = chunk size); tstride: elements between consecutive
+// time steps of that block (0 = time-invariant).  lc: local (shared-memory) copy used by the step functions.
+struct GCst {
+  const double* p;
+  size_t stride;
+  size_t tstride;
+  LQGK_HD WView at(int t) const { return WView{const_cast<double*>(p) + (size_t)t * tstride, stride}; }
+};
+
+// ---------------------------------------------------------------------------------------------- LQR fwd
+template <class DM, bool AFFINE>
+LQGK_HD void lqr_fwd_body(const GCst& g, WView lc, int T, double eps, WView Lw, bool save_S, WView Sw, WView lw, WView Hw) {
+  constexpr int B = DM::B, U = DM::U;
+  using C = LqrC<DM>;
+  const int nseg = AFFINE ? C::NSEG_AFF : C::NSEG;
+  load_consts<C>(g.at(g.tstride ? T - 1 : 0), lc, nseg);
+  double S[B * B], s[B];
+  load_sym<B>(lc, C::Qf, S);
+  if (AFFINE) { LQGK_UNROLL for (int i = 0; i < B; ++i) s[i] = lc(C::qf + i); }
+  for (int t = T - 1; t >= 0; --t) {
+    if (g.tstride && t != T - 1) load_consts<C>(g.at(t), lc, nseg);
+    if (save_S) store_sym<B>(Sw, (size_t)t * DM::ES, S);
+    double L[U * B], l[U], Ht[U * U], shift;
+    LqrFwd<DM, AFFINE>::step(lc, eps, S, s, L, l, Ht, shift);
+    LQGK_UNROLL for (int i = 0; i < U * B; ++i) Lw((size_t)t * DM::EL + i) = L[i];
+    if (AFFINE) {
+      LQGK_UNROLL for (int i = 0; i < U; ++i) lw((size_t)t * U + i) = l[i];
+      LQGK_UNROLL for (int i = 0; i < U * U; ++i) Hw((size_t)t * U * U + i) = Ht[i];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- KF fwd
+template <class DM>
+LQGK_HD void kf_fwd_body(const GCst& g, WView lc, int T, WView Kw, bool save_P, WView Pw) {
+  constexpr int B = DM::B, Y = DM::Y;
+  using C = KfC<DM>;
+  load_consts<C>(g.at(0), lc, C::NSEG);
+  double P[B * B];
+  load_sym<B>(lc, C::Sig0, P);
+  for (int t = 0; t < T; ++t) {
+    if (g.tstride && t != 0) load_consts<C>(g.at(t), lc, C::NSEG);
+    if (save_P) store_sym<B>(Pw, (size_t)t * DM::EP, P);
+    double K[B * Y];
+    KfFwd<DM>::step(lc, P, K);
+    LQGK_UNROLL for (int i = 0; i < B * Y; ++i) Kw((size_t)t * DM::EK + i) = K[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- COV fwd
+// Sink: put(idx, v) stores one float of the current step's record; commit(t) publishes the record.
+template <class DM, class Sink>
+LQGK_HD void cov_fwd_body(const GCst& g, WView lc, int T, WView Lw, WView Kw, bool save_C, WView Cw, Sink&& sink) {
+  constexpr int B = DM::B, U = DM::U, Y = DM::Y, R = DM::R;
+  using C = CovC<DM>;
+  load_consts<C>(g.at(0), lc, C::NSEG);
+  double Cm[R * R], L[U * B], K[B * Y];
+  LQGK_UNROLL for (int i = 0; i < B * Y; ++i) K[i] = Kw(i);
+  CovFwd<DM>::init(lc, K, Cm);
+  for (int t = 0; t < T; ++t) {
+    if (g.tstride && t != 0) load_consts<C>(g.at(t), lc, C::NSEG);
+    LQGK_UNROLL for (int i = 0; i < U * B; ++i) L[i] = Lw((size_t)t * DM::EL + i);
+    LQGK_UNROLL for (int i = 0; i < B * Y; ++i) K[i] = Kw((size_t)t * DM::EK + i);
+    if (save_C) store_sym<R>(Cw, (size_t)t * DM::EC, Cm);
+    CovFwd<DM>::step(lc, L, K, Cm, [&](int idx, float v) { sink.put(idx, v); });
+    sink.commit(t);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- COV rev
+// Source: fetch(t) makes the float sums of step t available; get(idx) reads one.
+template <class DM, class Source>
+LQGK_HD void cov_rev_body(const GCst& g, WView lc, WView la, int T, double sw, WView Lw, WView Kw, WView Cw,
+                          Source&& src, WView Lbw, WView Kbw, WView gacc) {
+  constexpr int B = DM::B, U = DM::U, Y = DM::Y, R = DM::R;
+  using C = CovC<DM>;
+  load_consts<C>(g.at(0), lc, C::NSEG);
+  for (int e = 0; e < C::n; ++e) la(e) = 0.0;
+  auto acc = [&](int e) -> double& { return la(e); };
+  double Cb[R * R], L[U * B], K[B * Y], Lb[U * B], Kb[B * Y];
+  LQGK_UNROLL for (int i = 0; i < R * R; ++i) Cb[i] = 0.0;
+  for (int t = T - 1; t >= 0; --t) {
+    double Cm[R * R];
+    LQGK_UNROLL for (int i = 0; i < U * B; ++i) L[i] = Lw((size_t)t * DM::EL + i);
+    LQGK_UNROLL for (int i = 0; i < B * Y; ++i) K[i] = Kw((size_t)t * DM::EK + i);
+    load_sym_ws<R>(Cw, (size_t)t * DM::EC, Cm);
+    src.fetch(t);
+    CovRev<DM>::step(lc, acc, L, K, Cm, [&](int idx) { return src.get(idx); }, sw, Cb, Lb, Kb);
+    if (t == 0) CovRev<DM>::init_bar(lc, acc, L, K, Cb, Lb, Kb);
+    LQGK_UNROLL for (int i = 0; i < U * B; ++i) Lbw((size_t)t * DM::EL + i) = Lb[i];
+    LQGK_UNROLL for (int i = 0; i < B * Y; ++i) Kbw((size_t)t * DM::EK + i) = Kb[i];
+  }
+  flush_acc<C>(gacc, la, C::NSEG);
+}
+
+// ---------------------------------------------------------------------------------------------- KF rev
+template <class DM>
+LQGK_HD void kf_rev_body(const GCst& g, WView lc, WView la, int T, WView Pw, WView Kbw, WView gacc) {
+  constexpr int B = DM::B, Y = DM::Y;
+  using C = KfC<DM>;
+  load_consts<C>(g.at(0), lc, C::NSEG);
+  for (int e = 0; e < C::n; ++e) la(e) = 0.0;
+  auto acc = [&](int e) -> double& { return la(e); };
+  double Pnb[B * B];
+  LQGK_UNROLL for (int i = 0; i < B * B; ++i) Pnb[i] = 0.0;
+  for (int t = T - 1; t >= 0; --t) {
+    double P[B * B], Kb[B * Y];
+    load_sym_ws<B>(Pw, (size_t)t * DM::EP, P);
+    LQGK_UNROLL for (int i = 0; i < B * Y; ++i) Kb[i] = Kbw((size_t)t * DM::EK + i);
+    KfRev<DM>::step(lc, acc, P, Kb, Pnb);
+  }
+  KfRev<DM>::finish(acc, Pnb);
+  flush_acc<C>(gacc, la, C::NSEG);
+}
+
+// ---------------------------------------------------------------------------------------------- LQR rev
+template <class DM>
+LQGK_HD void lqr_rev_body(const GCst& g, WView lc, WView la, int T, double eps, WView Lw, WView Sw, WView Lbw, WView gacc) {
+  constexpr int B = DM::B, U = DM::U;
+  using C = LqrC<DM>;
+  load_consts<C>(g.at(0), lc, C::NSEG);
+  for (int e = 0; e < C::n; ++e) la(e) = 0.0;
+  auto acc = [&](int e) -> double& { return la(e); };
+  double Sn[B * B];
+  LQGK_UNROLL for (int i = 0; i < B * B; ++i) Sn[i] = 0.0;
+  for (int t = 0; t < T; ++t) {
+    double S[B * B], L[U * B], Lb[U * B];
+    load_sym_ws<B>(Sw, (size_t)t * DM::ES, S);
+    LQGK_UNROLL for (int i = 0; i < U * B; ++i) { L[i] = Lw((size_t)t * DM::EL + i); Lb[i] = Lbw((size_t)t * DM::EL + i); }
+    // eigen-shift recomputed from S_{t+1} (lqr.py:27-28); zero in every well-posed model
+    double shift;
+    {
+      double Bm[B * U], SB[B * U], H[U * U];
+      load_mat<B, U>(lc, C::Ba, Bm);
+      mm<B, B, U>(S, Bm, SB);
+      load_sym<U>(lc, C::R, H);
+      mm_tn_sym<U, B, true>(Bm, SB, H);
+      shift = eps - lambda_min<U>(H);
+      shift = shift > 0.0 ? shift : 0.0;
+    }
+    LqrRev<DM>::step(lc, acc, S, L, Lb, shift, Sn);
+  }
+  LqrRev<DM>::finish(acc, Sn);
+  flush_acc<C>(gacc, la, C::NSEG);
+}
+
+}  // namespace lqgk

@@ -1,0 +1,65 @@
+"""GPU parity tests proper: the CUDA library, called through the C ABI, against the float64 oracle.
+
+Tolerances are the north star's: gains and log-likelihood rtol 1e-4, gradients rtol 1e-3 (vs float64)."""
+import numpy as np
+import pytest
+import torch
+
+from lqg_b200 import abi
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    assert torch.cuda.is_available()
+    return abi.load_library()
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.mark.parametrize("name,d", [("bounded", 2), ("subjective", 2), ("relobs", 2), ("bounded2", 4), ("relobs2", 4),
+                                    ("subjective2", 4), ("pointmass", 2)])
+def test_gains_match_oracle(lib, dev, name, d):
+    case = H.Case(name, S=3, T=300, N=2, d=d, want_grad=False)
+    H.check_gains(lib, dev, case, torch.float64, rtol=1e-9)
+    H.check_gains(lib, dev, case, torch.float32, rtol=1e-4)
+
+
+@pytest.mark.parametrize("name,d,N", [("bounded", 2, 20), ("subjective", 2, 33), ("relobs", 2, 7), ("bounded2", 4, 64),
+                                      ("relobs2", 4, 20), ("subjective2", 4, 100), ("pointmass", 2, 50)])
+def test_loglik_and_gradients_match_oracle(lib, dev, name, d, N):
+    case = H.Case(name, S=3, T=200, N=N, d=d, weights=True)
+    H.check_fwd(lib, dev, case, torch.float32)
+    H.check_fwd(lib, dev, case, torch.float64)
+    H.check_vjp(lib, dev, case, torch.float32)
+    H.check_vjp(lib, dev, case, torch.float64)
+
+
+def test_many_samples_multiple_warps_and_chunks(lib, dev):
+    case = H.Case("subjective2", S=70, T=60, N=12)
+    H.check_vjp(lib, dev, case, torch.float32)                  # one chunk, 3 warps, padded
+    H.check_vjp(lib, dev, case, torch.float32, max_chunk=32)    # three chunks
+    H.check_fwd(lib, dev, case, torch.float32, max_chunk=32)
+
+
+def test_more_trials_than_one_pass(lib, dev):
+    case = H.Case("bounded", S=2, T=50, N=150)
+    H.check_vjp(lib, dev, case, torch.float32)
+
+
+def test_config_c1_shape(lib, dev):
+    """BASELINE config 1: BoundedActor 1-D, T=500, 20 trials (reference tests/infer_test.py:19-26 shape)."""
+    case = H.Case("bounded", S=1, T=500, N=20, seed=123)
+    H.check_vjp(lib, dev, case, torch.float32)
+    assert -1.3e3 < case.ll.mean() < -0.9e3
+
+
+def test_config_c2_horizon(lib, dev):
+    """BASELINE config 2 shape: SubjectiveActor 2-D, T=1200, 20 trials, 6 conditions (sigma_target varies)."""
+    case = H.Case("subjective2", S=6, T=1200, N=20, seed=5)
+    H.check_vjp(lib, dev, case, torch.float32)
