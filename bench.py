@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- headline metric of BASELINE.json: trial log-lik+grad evals/sec on B200, with roofline fractions,
+next to the reference algorithm on the host CPU.
+
+Workload (config c3 of BASELINE.json): SubjectiveActor 2-D tracking, N=100 trials x T=1200, a sweep of
+S parameter samples PER GPU (default 16,384; weak scaling: N GPUs evaluate N*S samples; 8 GPUs x 8,192 = the
+65,536-sample target).  One "step" = one log-likelihood + parameter-gradient evaluation of all S samples
+(S*100 trial evals).  Data are synthetic (float64 restatement of System.simulate, NumPy PCG64 seed 7); parameter
+samples are theta_true * exp(0.25 z), z ~ N(0, I_6), seed 11 + rank.
+
+  value : device-resident (base matrices + observations already in HBM), CUDA events, max over ranks.
+  e2e   : through the public API (lqg_b200.tracking.SubjectiveActor(...).log_likelihood(x).sum().backward()) with
+          theta in pinned HOST memory every step: H2D of theta + observations, model construction, fused
+          forward+adjoint, D2H of ll[S] and grad[S,6].
+  roofline : dominant kernel, algorithmic FLOPs (SURVEY 8d convention) / its live CUDA-event time, against the
+          FP32 FMA peak measured in this run by an FFMA-saturating micro-kernel (MEASURED_PEAKS.json has no FP32
+          figure); HBM fraction reported beside it.
+  cpu_baseline : the oracle's torch-float64 port of the reference algorithm (autodiff through the three scans),
+          all host threads, on a bounded sample (64 samples x 100 trials x T=1200).
+
+`--impl reference` runs only that CPU port (the real JAX reference is not installable in this image).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+PARAM_NAMES = ("action_cost", "action_variability", "subj_noise", "subj_vel_noise", "sigma_target", "sigma_cursor")
+THETA_TRUE = (1.0, 0.5, 1.0, 0.5, 19.9, 6.0)
+DIMS = dict(x=4, b=6, u=2, y=4, d=4)
+
+
+# ----------------------------------------------------------------------------------------------- flop model
+def mm(m, k, n):
+    return 2 * m * k * n
+
+
+def algorithmic_flops(x, b, u, y, d, N, T):
+    """Forward flops of one system evaluation, SURVEY 8(d) convention (dense algebra of the reference recursions).
+    Returns (per-sample-per-step, per-trial-per-step, forward total).  fwd+grad = 3x forward by convention."""
+    n, m = x + b, x + y
+    lqr = (2 * mm(u, b, b) + mm(u, b, u) + mm(u, b, 1) + 10 * u ** 3 + (2 * u ** 3) // 3 + 2 * u * u * b + 2 * u * u
+           + 2 * mm(b, b, b) + mm(b, u, u) + 3 * mm(b, u, b) + 4 * b * b + mm(b, b, 1) + 3 * mm(b, u, 1) + mm(u, u, 1) + 4 * b)
+    kf = (3 * mm(b, b, b) + b * b + mm(y, b, b) + mm(y, b, y) + mm(y, y, y) + y * y + 2 * y ** 3 + mm(b, b, y) + mm(b, y, y)
+          + mm(b, y, b) + b + mm(b, b, b))
+    joint = (mm(x, u, b) + 2 * (mm(b, y, x) + mm(b, x, x)) + 2 * mm(b, u, b) + mm(b, y, b) + mm(b, b, b) + mm(y, x, u)
+             + mm(y, b, u) + y * u + mm(b, y, u) + 3 * b * b + mm(b, y, y))
+    cov = 2 * mm(n, n, n) + mm(n, m, n) + 2 * (d ** 3 // 3) + 2 * n * d * d + mm(n, d, n) + 2 * n * n + d
+    trial = 2 * n * n + 2 * n * d + n + d * d + 4 * d
+    per_sample = lqr + kf + joint + cov
+    return per_sample, trial, T * (per_sample + N * trial)
+
+
+# ----------------------------------------------------------------------------------------------- helpers
+def make_data(N, T, seed=7):
+    from oracle import lqg_np as O
+    kw = dict(zip(PARAM_NAMES, THETA_TRUE))
+    sa, sd = O.make_system(O.subjective_actor_mats(dim=2, **kw), T)
+    return O.simulate(sa, sd, N, np.random.default_rng(seed)).astype(np.float32)
+
+
+def make_theta(S, seed):
+    rng = np.random.default_rng(seed)
+    return (np.asarray(THETA_TRUE)[None] * np.exp(0.25 * rng.standard_normal((S, len(THETA_TRUE))))).astype(np.float32)
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons of one GPU during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [c.strip() for c in r.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+                for nm, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_port_eval(S, N, T, X, seed=3):
+    """One fwd+grad evaluation of S samples with the oracle's torch-float64 port on all host threads.  Returns seconds."""
+    from oracle import lqg_torch as OT
+    torch.set_num_threads(os.cpu_count() or 1)
+    th = torch.tensor(make_theta(S, seed), dtype=torch.float64, requires_grad=True)
+    Xt = torch.tensor(X, dtype=torch.float64)
+    t0 = time.perf_counter()
+    a, d = OT.subjective_actor(dim=2, **{n: th[:, i] for i, n in enumerate(PARAM_NAMES)})
+    ll = OT.log_likelihood(a, d, Xt)
+    ll.sum().backward()
+    assert torch.isfinite(th.grad).all()
+    return time.perf_counter() - t0
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    N, T, S = args.trials, args.T, args.cpu_samples
+    X = make_data(N, T)
+    times = []
+    for i in range(args.warmup + args.steps):
+        dt = cpu_port_eval(S, N, T, X, seed=3 + i)
+        if i >= args.warmup:
+            times.append(dt)
+    sec = float(np.mean(times))
+    val = S * N / sec
+    cores = os.cpu_count() or 1
+    line = {"impl": "reference", "metric": "trial log-lik+grad evals/sec", "value": val, "unit": "trial-evals/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, S_per_gpu=S, note="CPU port of the reference algorithm (oracle/lqg_torch.py); "
+                                      "the JAX reference is not installable in this image"),
+            "cpu_baseline": {"value": val, "unit": "trial-evals/s", "cores": cores, "kind": "port",
+                             "sample": f"{S} parameter samples x {N} trials x T={T}, fwd+grad by torch autograd, float64"},
+            "e2e": {"value": val, "unit": "trial-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, S_per_gpu, note=None):
+    cfg = {"workload": "c3: SubjectiveActor dim=2 (x=4,b=6,u=2,y=4,d=4), parameter-sample sweep, log-lik + gradient",
+           "samples_per_gpu": S_per_gpu, "trials": args.trials, "T": args.T, "params": len(PARAM_NAMES),
+           "sharding": "parameter samples across GPUs (no data-path collective); one NCCL all-reduce of [sum ll, sum grad]",
+           "cache": "per-step workspace traffic (tens of GB) >> 126 MB L2; no explicit flush needed"}
+    if note:
+        cfg["note"] = note
+    return cfg
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch.distributed as dist
+
+    from lqg_b200 import abi, runtime
+    from lqg_b200.tracking import SubjectiveActor
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = abi.load_library()
+    S, N, T = args.samples, args.trials, args.T
+    X = make_data(N, T)
+    theta_np = make_theta(S, 11 + rank)
+    P = theta_np.shape[1]
+
+    # ---------------- device-resident leg
+    theta = torch.tensor(theta_np, device=dev)
+    model = SubjectiveActor(dim=2, T=T, device=dev, **{n: theta[:, i] for i, n in enumerate(PARAM_NAMES)})
+    x_dev = torch.tensor(X, device=dev)
+    x_tm = lib.pack_obs(x_dev, stream=torch.cuda.current_stream().cuda_stream)
+    dims = abi.LqgkDims(S, N, T, DIMS["x"], DIMS["b"], DIMS["u"], DIMS["y"], DIMS["d"])
+    act = {k: runtime._row_major(getattr(model.actor, k)[:, 0]) for k in abi.ACTOR_KEYS}
+    dyn = {k: runtime._row_major(getattr(model.dynamics, k)[:, 0]) for k in abi.DYN_KEYS}
+    ws = runtime.workspace(dev, lib.workspace_bytes(dims, abi.MODE_VJP, args.chunk))
+    red = torch.zeros(1 + 12, device=dev)
+
+    def step_resident():
+        st = torch.cuda.current_stream().cuda_stream
+        ll, ga, gd, _ = lib.loglik_vjp(dims, act, dyn, x_tm, ws=ws, stream=st)
+        if world > 1:
+            red[0] = ll.sum()
+            for i, g in enumerate(list(ga.values()) + list(gd.values())):
+                red[1 + i] = g.sum()
+            dist.all_reduce(red)          # the path's one collective: [sum ll, sum grad] over NVLink
+        return ll
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        ll = step_resident()
+    barrier()
+    launches_per_step = lib.last_launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    lib.profile_enable(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        ll = step_resident()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    prof = lib.profile_read()
+    lib.profile_enable(False)
+    clocks = sampler.stop()
+    assert torch.isfinite(ll).all(), "non-finite log-likelihood in the timed region"
+    t_ms = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = float(t_ms.item())
+    ms_per_step = ms / args.steps
+    value = world * S * N / (ms_per_step * 1e-3)
+
+    # ---------------- end-to-end leg through the public API, host buffers
+    theta_host = torch.tensor(theta_np).pin_memory()
+    x_host = torch.tensor(X).pin_memory()
+    out_host = torch.empty((S, 1 + P), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        th = theta_host.to(dev, non_blocking=True).requires_grad_()
+        xd = x_host.to(dev, non_blocking=True)
+        m = SubjectiveActor(dim=2, T=T, device=dev, **{n: th[:, i] for i, n in enumerate(PARAM_NAMES)})
+        lls = m.log_likelihood(xd).sum(-1)
+        lls.sum().backward()
+        out = torch.cat([lls.detach()[:, None], th.grad], 1)
+        if world > 1:
+            red[:1 + P] = out.sum(0)
+            dist.all_reduce(red)
+        out_host.copy_(out, non_blocking=True)
+        return out
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step_e2e()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    t_e = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t_e.item()) / args.steps
+    e2e_val = world * S * N / (e2e_ms * 1e-3)
+    assert np.isfinite(out_host.numpy()).all()
+
+    if rank == 0:
+        # ---------------- roofline of the dominant kernel + whole step
+        per_sample, per_trial, fwd = algorithmic_flops(DIMS["x"], DIMS["b"], DIMS["u"], DIMS["y"], DIMS["d"], N, T)
+        step_flops = 3.0 * fwd * S                                 # fwd+grad = 3x forward (SURVEY 8d convention)
+        # attribution of the "fwd+grad = 3x forward" convention to the kernels: forward kernels 1x, adjoints 2x
+        lqr_f, kf_f = [T * v for v in split_sample_flops()[:2]]
+        cov_f = T * per_sample - lqr_f - kf_f
+        kind_flops = {"lqr_fwd": lqr_f, "kf_fwd": kf_f, "cov_fwd": cov_f, "trial_fwd": T * N * per_trial,
+                      "lqr_rev": 2 * lqr_f, "kf_rev": 2 * kf_f, "cov_rev": 2 * cov_f, "trial_rev": 2 * T * N * per_trial}
+        fp32_peak = lib.peak_fma(False, dev)
+        fp64_peak = lib.peak_fma(True, dev)
+        kernels = {}
+        for k, (kms, cnt) in prof.items():
+            if cnt == 0:
+                continue
+            per_step_ms = kms / args.steps
+            entry = {"ms_per_step": per_step_ms, "launches_per_step": cnt / args.steps, "share": per_step_ms / ms_per_step}
+            if k in kind_flops:
+                entry["algorithmic_tflops"] = kind_flops[k] * S / (per_step_ms * 1e-3) / 1e12
+            kernels[k] = entry
+        dom = max((k for k in kernels if k in kind_flops), key=lambda k: kernels[k]["ms_per_step"])
+        dom_launches = max(1.0, kernels[dom]["launches_per_step"])
+        achieved = kernels[dom]["algorithmic_tflops"]
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        ws_bytes = step_hbm_bytes(S, N, T)
+        roofline = {"bound": "fp32", "kernel": "k_" + dom, "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                    "frac": achieved / fp32_peak, "traffic": None,
+                    "algorithmic_flops_per_launch": kind_flops[dom] * S / dom_launches,
+                    "launch_ms": kernels[dom]["ms_per_step"] / dom_launches,
+                    "peak_source": "FFMA micro-kernel measured in this run (lqgk_peak_fma); nominal 74.5 TFLOP/s",
+                    "fp64_peak_tflops_measured": fp64_peak,
+                    "step": {"achieved": step_flops / (ms_per_step * 1e-3) / 1e12, "frac": step_flops / (ms_per_step * 1e-3) / 1e12 / fp32_peak,
+                             "algorithmic_flops": step_flops},
+                    "hbm": {"achieved_gbs": ws_bytes / (ms_per_step * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                            "frac": ws_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
+                            "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
+                            "bytes_per_step_workspace_model": ws_bytes}}
+        # ---------------- CPU baseline (bounded sample) on this box's host cores
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            sec = cpu_port_eval(args.cpu_samples, N, T, X)
+            cpu = {"value": args.cpu_samples * N / sec, "unit": "trial-evals/s", "cores": os.cpu_count() or 1, "kind": "port",
+                   "sample": f"{args.cpu_samples} parameter samples x {N} trials x T={T}, one fwd+grad eval by torch-float64 "
+                             f"autograd over the oracle's restatement of the reference scans ({sec:.1f} s)"}
+        line = {"metric": "trial log-lik+grad evals/sec", "value": value, "unit": "trial-evals/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64 per-sample recursions + f32 per-trial recursions (f32 I/O)",
+                "data": "synthetic", "config": workload_config(args, S),
+                "trial_steps_per_sec": value * T,
+                "e2e": {"value": e2e_val, "unit": "trial-evals/s", "ms_per_step": e2e_ms,
+                        "h2d_bytes_per_step": int(theta_host.numel() * 4 + x_host.numel() * 4),
+                        "d2h_bytes_per_step": int(out_host.numel() * 4)},
+                "gpu_launches": int(launches_per_step * args.steps),
+                "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def split_sample_flops():
+    """(lqr, kf) per-step forward flops for the c3 dims."""
+    x, b, u, y = DIMS["x"], DIMS["b"], DIMS["u"], DIMS["y"]
+    lqr = (2 * mm(u, b, b) + mm(u, b, u) + mm(u, b, 1) + 10 * u ** 3 + (2 * u ** 3) // 3 + 2 * u * u * b + 2 * u * u
+           + 2 * mm(b, b, b) + mm(b, u, u) + 3 * mm(b, u, b) + 4 * b * b + mm(b, b, 1) + 3 * mm(b, u, 1) + mm(u, u, 1) + 4 * b)
+    kf = (3 * mm(b, b, b) + b * b + mm(y, b, b) + mm(y, b, y) + mm(y, y, y) + y * y + 2 * y ** 3 + mm(b, b, y) + mm(b, y, y)
+          + mm(b, y, b) + b + mm(b, b, b))
+    return lqr, kf
+
+
+def step_hbm_bytes(S, N, T):
+    """Model of the workspace bytes one fwd+grad step writes and reads back."""
+    n, r, d, u, b, y = 10, 6, 4, 2, 6, 4
+    tri = lambda k: k * (k + 1) // 2
+    rec, sums = 136, 136
+    dbl = (u * b + b * y) * 2 + tri(b) * 2 + tri(r)        # L,K,Lbar,Kbar + Sric,Pkf + Cs   (doubles per step)
+    per_step = dbl * 8 * 2 + rec * 4 * 3 + sums * 4 * 2 + r * N * 4 * 2
+    return float(S) * T * per_step
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--samples", type=int, default=16384, help="parameter samples per GPU per step")
+    ap.add_argument("--trials", type=int, default=100)
+    ap.add_argument("--T", type=int, default=1200)
+    ap.add_argument("--chunk", type=int, default=0, help="max samples per internal workspace chunk (0 = as many as fit)")
+    ap.add_argument("--cpu-samples", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

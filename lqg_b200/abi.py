@@ -216,6 +216,39 @@ class Library:
     def last_launch_count(self) -> int:
         return int(self.lib.lqgk_last_launch_count())
 
+    PROFILE_KINDS = ("pack", "lqr_fwd", "kf_fwd", "cov_fwd", "trial_fwd", "misc", "trial_rev", "cov_rev", "kf_rev",
+                     "lqr_rev", "unpack")
+
+    def profile_enable(self, on: bool):
+        self._check(self.lib.lqgk_profile_enable(C.c_int(1 if on else 0)), "lqgk_profile_enable")
+
+    def profile_read(self):
+        """{kind: (milliseconds, launches)} accumulated since the last read (synchronises on the recorded events)."""
+        n = len(self.PROFILE_KINDS)
+        ms = (C.c_float * n)()
+        cnt = (C.c_int32 * n)()
+        rc = self.lib.lqgk_profile_read(ms, cnt, C.c_int(n))
+        if rc < 0:
+            self._check(rc, "lqgk_profile_read")
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.PROFILE_KINDS)}
+
+    def peak_fma(self, fp64: bool, device, iters=4096, reps=5) -> float:
+        """Measured CUDA-core FMA peak in TFLOP/s (best of `reps`), CUDA events on the current stream."""
+        sink = torch.zeros(8, dtype=torch.float64, device=device)
+        st = torch.cuda.current_stream(device).cuda_stream
+        flop = C.c_double(0.0)
+        best = 0.0
+        for r in range(reps + 1):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self._check(self.lib.lqgk_peak_fma(C.c_int(1 if fp64 else 0), C.c_int(iters), C.c_void_p(sink.data_ptr()),
+                                               C.c_void_p(st), C.byref(flop)), "lqgk_peak_fma")
+            e1.record()
+            e1.synchronize()
+            if r > 0:
+                best = max(best, flop.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        return best
+
 
 _LIB: Optional[Library] = None
 

@@ -13,6 +13,7 @@ using namespace lqgk;
 
 namespace lqgk {
 thread_local int g_launches = 0;
+thread_local Profiler g_prof;
 }
 
 namespace {
@@ -59,6 +60,23 @@ int pack_obs(int32_t N, int32_t T1, int32_t d, const T* x, float* x_tm, void* st
 
 }  // namespace
 
+// FMA-saturating micro-kernels: the measured FP32 / FP64 CUDA-core peaks used as roofline denominators.
+template <class T>
+__global__ void k_peak_fma(int iters, T* sink) {
+  T a[8];
+  for (int i = 0; i < 8; ++i) a[i] = (T)(threadIdx.x + i) * (T)1e-3;
+  const T m = (T)0.999, c = (T)1e-4;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = a[i] * m + c;
+    }
+  }
+  T s = 0;
+  for (int i = 0; i < 8; ++i) s += a[i];
+  if (s == (T)123456.789) sink[0] = s;
+}
 extern "C" {
 
 int lqgk_lqr_backward_f32(const LqgkDims* dims, const LqgkSpec* actor, double eps, float* L_out, float* l_out, float* H_out,
@@ -146,6 +164,35 @@ const char* lqgk_strerror(int code) {
     default: return "unknown error";
   }
 }
+int lqgk_profile_enable(int on) {
+  g_prof.on = on != 0;
+  g_prof.used = 0;
+  return LQGK_OK;
+}
+int lqgk_profile_read(float* ms_by_kind, int32_t* launches_by_kind, int nkinds) {
+  if (!ms_by_kind || nkinds <= 0) return LQGK_E_INVALID;
+  for (int i = 0; i < nkinds; ++i) { ms_by_kind[i] = 0.f; if (launches_by_kind) launches_by_kind[i] = 0; }
+  for (size_t i = 0; i + 1 < g_prof.used; i += 2) {
+    if (cudaEventSynchronize(g_prof.ev[i + 1]) != cudaSuccess) return LQGK_E_CUDA;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_prof.ev[i], g_prof.ev[i + 1]) != cudaSuccess) return LQGK_E_CUDA;
+    int k = g_prof.kinds[i / 2];
+    if (k < nkinds) { ms_by_kind[k] += ms; if (launches_by_kind) launches_by_kind[k] += 1; }
+  }
+  g_prof.used = 0;
+  return PK_COUNT;
+}
+
+int lqgk_peak_fma(int fp64, int iters, void* sink, void* stream, double* flop_out) {
+  if (!sink || iters <= 0) return LQGK_E_INVALID;
+  const int blocks = 148 * 8, threads = 256;
+  if (fp64) k_peak_fma<double><<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, (double*)sink);
+  else k_peak_fma<float><<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, (float*)sink);
+  if (cudaPeekAtLastError() != cudaSuccess) return LQGK_E_CUDA;
+  if (flop_out) *flop_out = 2.0 * 64.0 * (double)iters * blocks * threads;
+  return LQGK_OK;
+}
+
 const char* lqgk_version(void) { return "lqgk 0.1.0 (sm_100a)"; }
 int lqgk_last_launch_count(void) { return g_launches; }
 

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "../../include/lqgk.h"
 #include "lqgk_kernels.cuh"
@@ -11,6 +12,39 @@
 namespace lqgk {
 
 extern thread_local int g_launches;
+
+// Optional per-kernel timing (bench.py): CUDA events recorded on the launching stream around every launch.
+enum ProfKind { PK_PACK = 0, PK_LQR_FWD, PK_KF_FWD, PK_COV_FWD, PK_TRIAL_FWD, PK_MISC, PK_TRIAL_REV, PK_COV_REV, PK_KF_REV,
+                PK_LQR_REV, PK_UNPACK, PK_COUNT };
+struct Profiler {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;   // pairs (start, stop)
+  std::vector<int> kinds;
+  size_t used = 0;
+};
+extern thread_local Profiler g_prof;
+struct ProfScope {
+  cudaStream_t st;
+  bool active;
+  ProfScope(int kind, cudaStream_t s) : st(s), active(g_prof.on) {
+    if (!active) return;
+    if (g_prof.used + 2 > g_prof.ev.size()) {
+      cudaEvent_t a, b;
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      g_prof.ev.push_back(a);
+      g_prof.ev.push_back(b);
+    }
+    g_prof.kinds.resize(g_prof.ev.size() / 2);
+    g_prof.kinds[g_prof.used / 2] = kind;
+    cudaEventRecord(g_prof.ev[g_prof.used], st);
+  }
+  ~ProfScope() {
+    if (!active) return;
+    cudaEventRecord(g_prof.ev[g_prof.used + 1], st);
+    g_prof.used += 2;
+  }
+};
 
 #define LQGK_LAUNCH_CHECK()                              \
   do {                                                   \
@@ -98,6 +132,7 @@ int launch_trial_fwd(cudaStream_t st, const float* rec, const float* x_tm, int n
   size_t smem = trial_smem_bytes<DM>();
   int rc = set_smem<DM>((const void*)k_trial_fwd<DM, RT>, smem);
   if (rc) return rc;
+  ProfScope ps_(PK_TRIAL_FWD, st);
   k_trial_fwd<DM, RT><<<(n + TRIAL_WARPS - 1) / TRIAL_WARPS, 32 * TRIAL_WARPS, smem, st>>>(rec, x_tm, n, N, T, ll, hist);
   LQGK_LAUNCH_CHECK();
   return LQGK_OK;
@@ -108,6 +143,7 @@ int launch_trial_rev(cudaStream_t st, const float* rec, const float* x_tm, const
   size_t smem = trial_smem_bytes<DM>();
   int rc = set_smem<DM>((const void*)k_trial_rev<DM, RT>, smem);
   if (rc) return rc;
+  ProfScope ps_(PK_TRIAL_REV, st);
   k_trial_rev<DM, RT><<<(n + TRIAL_WARPS - 1) / TRIAL_WARPS, 32 * TRIAL_WARPS, smem, st>>>(rec, x_tm, hist, w, n, N, T, sums);
   LQGK_LAUNCH_CHECK();
   return LQGK_OK;
@@ -162,12 +198,14 @@ int run(const Call& c) {
     const int nblk = npad / 32;
     {
       dim3 grid((npad + 127) / 128, tv ? Tn : 1);
+      ProfScope ps_(PK_PACK, st);
       k_pack<T><<<grid, 128, 0, st>>>(pa, (int)s0, n, npad, D(p.cst), Sc, tstride, tv ? Tn : 1);
       LQGK_LAUNCH_CHECK();
     }
     if (c.mode == LQGK_MODE_GAINS) {
       if (c.L_out) {
         size_t smem = sizeof(double) * 32 * LqrC<DM>::n_affine;
+        ProfScope ps_(PK_LQR_FWD, st);
         k_lqr_fwd<DM, true><<<nblk, 32, smem, st>>>(D(p.cst), Sc, tstride, Tn, c.eps, D(p.L), 0, nullptr, D(p.l), D(p.H));
         LQGK_LAUNCH_CHECK();
         auto store = [&](size_t off, int E, void* out) -> int {
@@ -184,6 +222,7 @@ int run(const Call& c) {
       }
       if (c.K_out) {
         size_t smem = sizeof(double) * 32 * KfC<DM>::n;
+        ProfScope ps_(PK_KF_FWD, st);
         k_kf_fwd<DM><<<nblk, 32, smem, st>>>(D(p.cst), Sc, tstride, Tn, D(p.K), 0, nullptr);
         LQGK_LAUNCH_CHECK();
         size_t total = (size_t)n * Tn * DM::EK;
@@ -196,17 +235,20 @@ int run(const Call& c) {
     int rc;
     {
       size_t smem = sizeof(double) * 32 * LqrC<DM>::n;
+      ProfScope ps_(PK_LQR_FWD, st);
       k_lqr_fwd<DM, false><<<nblk, 32, smem, st>>>(D(p.cst), Sc, tstride, Tn, c.eps, D(p.L), vjp, vjp ? D(p.Sric) : nullptr, nullptr, nullptr);
       LQGK_LAUNCH_CHECK();
     }
     {
       size_t smem = sizeof(double) * 32 * KfC<DM>::n;
+      ProfScope ps_(PK_KF_FWD, st);
       k_kf_fwd<DM><<<nblk, 32, smem, st>>>(D(p.cst), Sc, tstride, Tn, D(p.K), vjp, vjp ? D(p.Pkf) : nullptr);
       LQGK_LAUNCH_CHECK();
     }
     {
       size_t smem = sizeof(double) * 32 * CovC<DM>::n + sizeof(float) * 32 * SmemRecSink<DM>::RS;
       if ((rc = set_smem<DM>((const void*)k_cov_fwd<DM>, smem))) return rc;
+      ProfScope ps_(PK_COV_FWD, st);
       k_cov_fwd<DM><<<nblk, 32, smem, st>>>(D(p.cst), Sc, tstride, Tn, D(p.L), D(p.K), vjp, vjp ? D(p.Cs) : nullptr, F(p.rec));
       LQGK_LAUNCH_CHECK();
     }
@@ -218,6 +260,7 @@ int run(const Call& c) {
     if (rc) return rc;
     {
       size_t total = (size_t)n * N;
+      ProfScope ps_(PK_MISC, st);
       k_store_ll<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(D(p.ll), total, (T*)c.ll_out + s0 * N);
       LQGK_LAUNCH_CHECK();
     }
@@ -245,18 +288,21 @@ int run(const Call& c) {
     {
       size_t smem = sizeof(double) * 32 * 2 * CovC<DM>::n + sizeof(float) * 32 * SmemSumSrc<DM>::RS;
       if ((rc = set_smem<DM>((const void*)k_cov_rev<DM>, smem))) return rc;
+      ProfScope ps_(PK_COV_REV, st);
       k_cov_rev<DM><<<nblk, 32, smem, st>>>(D(p.cst), Sc, Tn, N, F(p.w), D(p.L), D(p.K), D(p.Cs), F(p.sums), D(p.Lbar), D(p.Kbar), D(p.acc));
       LQGK_LAUNCH_CHECK();
     }
     {
       size_t smem = sizeof(double) * 32 * 2 * KfC<DM>::n;
       if ((rc = set_smem<DM>((const void*)k_kf_rev<DM>, smem))) return rc;
+      ProfScope ps_(PK_KF_REV, st);
       k_kf_rev<DM><<<nblk, 32, smem, st>>>(D(p.cst), Sc, Tn, D(p.Pkf), D(p.Kbar), D(p.acc));
       LQGK_LAUNCH_CHECK();
     }
     {
       size_t smem = sizeof(double) * 32 * 2 * LqrC<DM>::n;
       if ((rc = set_smem<DM>((const void*)k_lqr_rev<DM>, smem))) return rc;
+      ProfScope ps_(PK_LQR_REV, st);
       k_lqr_rev<DM><<<nblk, 32, smem, st>>>(D(p.cst), Sc, Tn, c.eps, D(p.L), D(p.Sric), D(p.Lbar), D(p.acc));
       LQGK_LAUNCH_CHECK();
     }
@@ -267,6 +313,7 @@ int run(const Call& c) {
       if (c.gdyn) ua.gdyn = *c.gdyn;
       if (c.gsig0) ua.gsigma0 = *c.gsig0;
       ua.x = DM::X; ua.b = DM::B; ua.u = DM::U; ua.y = DM::Y;
+      ProfScope ps_(PK_UNPACK, st);
       k_unpack<T><<<(n + 63) / 64, 64, 0, st>>>(ua, (int)s0, n, D(p.acc), D(p.cst), Sc);
       LQGK_LAUNCH_CHECK();
     }

@@ -1,0 +1,254 @@
+"""Host-side glue between the torch-facing API (``lqg_b200.system`` etc.) and the C ABI (``lqg_b200.abi``).
+
+* canonicalises ``LQGSpec`` tensors to the ``(S, T, r, c)`` views the ABI describes by strides (no copies for
+  stride-0 time axes / shared samples);
+* owns one cached device workspace per GPU, sized by :data:`WORKSPACE_FRACTION` of free memory (the library
+  chunks over parameter samples inside that budget);
+* wraps the fused forward+adjoint entry point in a ``torch.autograd.Function`` (the reference gets its
+  gradient from ``jax.value_and_grad``; here the CUDA adjoint is the ``backward``).
+
+There is no CPU path: every function raises if the tensors are not on a CUDA device or the library is missing.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from lqg_b200 import abi
+from lqg_b200.dims import SUPPORTED_DIMS
+from lqg_b200.spec import LQGSpec
+
+WORKSPACE_FRACTION = 0.6          # of currently free device memory, upper bound for the cached workspace
+WORKSPACE_MAX_BYTES = 96 << 30
+_WS: Dict[int, torch.Tensor] = {}
+
+ACT_KEYS = abi.ACTOR_KEYS
+DYN_KEYS = abi.DYN_KEYS
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"lqg_b200: {what} must live on a CUDA device (got {t.device}); there is no CPU fallback. "
+                           f"Move the model/data to 'cuda' (B200, sm_100a).")
+
+
+def workspace(device: torch.device, need: int) -> torch.Tensor:
+    """Cached uint8 workspace on `device`, at least min(need, budget) bytes."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    cur = _WS.get(idx)
+    if cur is not None and cur.numel() >= need:
+        return cur
+    free, _total = torch.cuda.mem_get_info(idx)
+    have = cur.numel() if cur is not None else 0
+    budget = min(int((free + have) * WORKSPACE_FRACTION), WORKSPACE_MAX_BYTES)
+    size = min(need, budget)
+    if cur is not None and cur.numel() >= size:
+        return cur
+    _WS.pop(idx, None)
+    del cur
+    _WS[idx] = torch.empty(size, dtype=torch.uint8, device=torch.device("cuda", idx))
+    return _WS[idx]
+
+
+def release_workspace():
+    _WS.clear()
+
+
+def spec_batch(spec: LQGSpec) -> Tuple[int, int]:
+    """(S, T) of a spec whose arrays are (T, r, c) or (S, T, r, c)."""
+    A = spec.A
+    if A.dim() == 3:
+        return 1, A.shape[0]
+    if A.dim() == 4:
+        return A.shape[0], A.shape[1]
+    raise ValueError(f"spec arrays must be (T, r, c) or (S, T, r, c); got {tuple(A.shape)}")
+
+
+def _as4(M: torch.Tensor) -> torch.Tensor:
+    return M if M.dim() == 4 else M.unsqueeze(0)
+
+
+def _row_major(M: torch.Tensor) -> torch.Tensor:
+    """Make the trailing matrix dims row-major contiguous without materialising stride-0 leading axes."""
+    r, c = M.shape[-2:]
+    if M.stride(-1) == 1 and (M.stride(-2) == c or r == 1):
+        return M
+    lead = M.shape[:-2]
+    # collapse expanded (stride-0) leading dims before copying, then expand again
+    idx = tuple(slice(0, 1) if (M.stride(i) == 0 and M.shape[i] > 1) else slice(None) for i in range(len(lead)))
+    return M[idx].contiguous().expand(*lead, r, c)
+
+
+def spec_mats(spec: LQGSpec, keys) -> Dict[str, torch.Tensor]:
+    return {k: _row_major(_as4(getattr(spec, k))) for k in keys}
+
+
+def is_time_invariant(M4: torch.Tensor) -> bool:
+    return M4.shape[1] == 1 or M4.stride(1) == 0
+
+
+def dims_of(actor: LQGSpec, dynamics: LQGSpec, N: int, d: int) -> abi.LqgkDims:
+    Sa, T = spec_batch(actor)
+    Sd, Td = spec_batch(dynamics)
+    if T != Td:
+        raise ValueError("actor and dynamics specs have different numbers of time steps")
+    if Sa != Sd and 1 not in (Sa, Sd):
+        raise ValueError("actor and dynamics specs have incompatible sample axes")
+    S = max(Sa, Sd)
+    x, b = dynamics.A.shape[-1], actor.A.shape[-1]
+    u, y = dynamics.B.shape[-1], dynamics.F.shape[-2]
+    return abi.LqgkDims(S, N, T, x, b, u, y, d)
+
+
+def check_supported(dims: abi.LqgkDims, gains_only=False):
+    tup = (dims.x, dims.b, dims.u, dims.y, dims.d)
+    if gains_only:
+        if not any(t[:4] == tup[:4] for t in SUPPORTED_DIMS):
+            raise NotImplementedError(f"lqg_b200: no kernels compiled for (x,b,u,y)={tup[:4]}; add a line to csrc/lqgk_dims.h")
+    elif tup not in SUPPORTED_DIMS:
+        raise NotImplementedError(f"lqg_b200: no kernels compiled for (x,b,u,y,d)={tup}; supported: {SUPPORTED_DIMS}. "
+                                  f"Add a line to lqg_b200/csrc/lqgk_dims.h and rebuild.")
+
+
+def _stream(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def lqr_backward(spec: LQGSpec, eps: float = 1e-8):
+    """CUDA backward Riccati sweep.  Returns L, l, H shaped like the reference ((T,u,b) or (S,T,u,b))."""
+    _require_cuda(spec.A, "spec")
+    lib = abi.load_library()
+    S, T = spec_batch(spec)
+    b, u, y = spec.A.shape[-1], spec.B.shape[-1], spec.F.shape[-2]
+    dims = abi.LqgkDims(S, 1, T, next((t[0] for t in SUPPORTED_DIMS if t[1:4] == (b, u, y)), b), b, u, y, 1)
+    dims.d = next((t[4] for t in SUPPORTED_DIMS if t[:4] == (dims.x, b, u, y)), 1)
+    check_supported(dims, gains_only=True)
+    mats = spec_mats(spec, ACT_KEYS)
+    for k, tr in (("q", 1), ("r", 1), ("P", 2)):
+        v = getattr(spec, k)
+        if v is not None and bool((v != 0).any()):
+            mats[k] = (v if v.dim() == tr + 2 else v.unsqueeze(0)).contiguous()
+    if spec.qf is not None and bool((spec.qf != 0).any()):
+        mats["qf"] = (spec.qf if spec.qf.dim() == 2 else spec.qf.unsqueeze(0)).contiguous()
+    if spec.Qf is not None:
+        mats["Qf"] = _row_major(spec.Qf if spec.Qf.dim() == 3 else spec.Qf.unsqueeze(0))
+    dev = spec.A.device
+    ws = workspace(dev, lib.workspace_bytes(dims, abi.MODE_GAINS, 0))
+    L, l, H = lib.lqr_backward(dims, mats, eps=eps, ws=ws, stream=_stream(dev))
+    if spec.A.dim() == 3:
+        L, l, H = L[0], l[0], H[0]
+    return L, l, H
+
+
+def kf_forward(spec: LQGSpec, Sigma0: Optional[torch.Tensor]):
+    """CUDA forward Kalman-gain sweep.  Returns K shaped (T,b,y) or (S,T,b,y)."""
+    _require_cuda(spec.A, "spec")
+    lib = abi.load_library()
+    S, T = spec_batch(spec)
+    b, u, y = spec.A.shape[-1], spec.B.shape[-1], spec.F.shape[-2]
+    dims = abi.LqgkDims(S, 1, T, next((t[0] for t in SUPPORTED_DIMS if t[1:4] == (b, u, y)), b), b, u, y, 1)
+    dims.d = next((t[4] for t in SUPPORTED_DIMS if t[:4] == (dims.x, b, u, y)), 1)
+    check_supported(dims, gains_only=True)
+    mats = spec_mats(spec, ACT_KEYS)
+    dev = spec.A.device
+    s0 = None
+    if Sigma0 is not None:
+        s0 = _row_major(Sigma0 if Sigma0.dim() == 3 else Sigma0.unsqueeze(0)).to(spec.A.dtype)
+    ws = workspace(dev, lib.workspace_bytes(dims, abi.MODE_GAINS, 0))
+    K = lib.kf_forward(dims, mats, sigma0=s0, ws=ws, stream=_stream(dev))
+    return K[0] if spec.A.dim() == 3 else K
+
+
+class _LogLikFn(torch.autograd.Function):
+    """ll[S, N] = log p(x_{1:T} | x_0, theta) per parameter sample and trial, with the CUDA adjoint as backward.
+
+    When any input requires grad the forward runs the *fused* forward+adjoint entry point with unit cotangents and
+    caches the per-sample gradients; ``backward`` rescales them when the incoming cotangent is constant over the
+    trials of each sample (the usual ``ll.sum()`` / per-sample weighting) and otherwise re-runs the adjoint with the
+    actual per-trial cotangents.
+    """
+
+    @staticmethod
+    def forward(ctx, x_tm, dims, has_sigma0, n_act, *mats):
+        lib = abi.load_library()
+        act = dict(zip(ACT_KEYS, mats[:n_act]))
+        dyn = dict(zip(DYN_KEYS, mats[n_act:n_act + len(DYN_KEYS)]))
+        sigma0 = mats[-1] if has_sigma0 else None
+        dev = x_tm.device
+        need_grad = any(m.requires_grad for m in mats)
+        ctx.need_grad = need_grad
+        if not need_grad:
+            ws = workspace(dev, lib.workspace_bytes(dims, abi.MODE_FWD, 0))
+            return lib.loglik_fwd(dims, act, dyn, x_tm, sigma0=sigma0, ws=ws, stream=_stream(dev))
+        for m in mats[:n_act + len(DYN_KEYS)]:
+            if m.requires_grad and m.dim() == 4:
+                raise NotImplementedError(
+                    "lqg_b200: gradients are implemented for time-invariant specs (stride-0 time axis, as built by "
+                    "lqg_b200.utils.time_stack); materialised time-varying arrays only support the forward pass.")
+        ws = workspace(dev, lib.workspace_bytes(dims, abi.MODE_VJP, 0))
+        ll, ga, gd, gs = lib.loglik_vjp(dims, act, dyn, x_tm, sigma0=sigma0, ws=ws, stream=_stream(dev))
+        ctx.args = (x_tm, dims, act, dyn, sigma0)
+        ctx.cached = (ga, gd, gs)
+        ctx.shapes = [m.shape for m in mats]
+        ctx.n_act = n_act
+        ctx.has_sigma0 = has_sigma0
+        return ll
+
+    @staticmethod
+    def backward(ctx, ll_bar):
+        if not ctx.need_grad:
+            return (None,) * (4 + len(ctx.shapes))
+        x_tm, dims, act, dyn, sigma0 = ctx.args
+        ga, gd, gs = ctx.cached
+        ll_bar = ll_bar.expand(dims.S, dims.N)
+        row = ll_bar[:, :1]
+        if bool((ll_bar == row).all()):
+            scale = row.reshape(dims.S, 1, 1).to(next(iter(ga.values())).dtype)
+            ga = {k: v * scale for k, v in ga.items()}
+            gd = {k: v * scale for k, v in gd.items()}
+            gs = gs * scale if gs is not None else None
+        else:
+            lib = abi.load_library()
+            dev = x_tm.device
+            ws = workspace(dev, lib.workspace_bytes(dims, abi.MODE_VJP, 0))
+            _, ga, gd, gs = lib.loglik_vjp(dims, act, dyn, x_tm, ll_bar=ll_bar.contiguous(), sigma0=sigma0, ws=ws,
+                                           stream=_stream(dev))
+        grads = [ga[k] for k in ACT_KEYS] + [gd[k] for k in DYN_KEYS] + ([gs] if ctx.has_sigma0 else [])
+        out = []
+        for g, shp in zip(grads, ctx.shapes):
+            if len(shp) == 4:          # materialised time-varying input: forward only (checked in forward)
+                out.append(None)
+                continue
+            # time-invariant base matrix (S|1, r, c): the kernel already summed the cotangent over time
+            out.append(g.sum(0, keepdim=True) if (shp[0] == 1 and g.shape[0] != 1) else g)
+        return (None, None, None, None, *out)
+
+
+def log_likelihood(actor: LQGSpec, dynamics: LQGSpec, x: torch.Tensor, Sigma0: Optional[torch.Tensor] = None,
+                   x_tm: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Per-trial log-likelihood (reference ``System.log_likelihood``, lqg/system.py:246-248).
+
+    x: (n, T+1, d).  Returns (n,) for an un-batched spec, (S, n) for a spec with a sample axis."""
+    _require_cuda(actor.A, "actor spec")
+    _require_cuda(x, "observations")
+    lib = abi.load_library()
+    n, T1, d = x.shape
+    dims = dims_of(actor, dynamics, n, d)
+    if dims.T != T1 - 1:
+        raise ValueError(f"need T+1 = {dims.T + 1} observations per trial, got {T1} (SURVEY H7: spec.T == x.shape[-2] - 1)")
+    check_supported(dims)
+    if x_tm is None:
+        x_tm = lib.pack_obs(x.detach(), stream=_stream(x.device))
+    dt = actor.A.dtype
+    def base(M):
+        """(S|1, r, c) base matrix of a time-invariant array (stride-0 time axis), else the (S|1, T, r, c) array."""
+        M4 = _as4(M)
+        return _row_major(M4[:, 0] if is_time_invariant(M4) else M4).to(dt)
+
+    mats = [base(getattr(actor, k)) for k in ACT_KEYS] + [base(getattr(dynamics, k)) for k in DYN_KEYS]
+    has_s0 = Sigma0 is not None
+    if has_s0:
+        mats.append(_row_major(Sigma0 if Sigma0.dim() == 3 else Sigma0.unsqueeze(0)).to(dt))
+    ll = _LogLikFn.apply(x_tm, dims, has_s0, len(ACT_KEYS), *mats)
+    return ll[0] if (actor.A.dim() == 3 and dynamics.A.dim() == 3) else ll

@@ -1,0 +1,276 @@
+"""``System`` / ``Dynamics`` / ``Actor`` / ``LQG`` / ``NumpyroLQG`` -- drop-in for ``lqg/system.py``.
+
+Hot path (CUDA): ``log_likelihood`` and ``conditional_distribution(x).log_prob(x[:, 1:])`` (lqg/system.py:237-248)
+with the adjoint as autograd backward.  Slow paths (torch ops on the GPU around the CUDA gain kernels):
+``conditional_moments`` (:142-235), ``belief_tracking_distribution`` (:250-257) and ``simulate`` (:62-140).
+Arrays are torch tensors; a leading parameter-sample axis plays the role of ``jax.vmap``.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from lqg_b200 import runtime
+from lqg_b200.belief import kf
+from lqg_b200.control import lqr
+from lqg_b200.spec import LQGSpec
+from lqg_b200.utils import time_stack_spec
+
+mT = lambda M: M.transpose(-1, -2)
+
+
+class MultivariateNormalSeq:
+    """Minimal stand-in for ``numpyro.distributions.MultivariateNormal(mu, Sigma)[.to_event(1)]`` (numpyro is not
+    available in this image): holds per-step moments and evaluates the log-density by Cholesky (system.py:244,257)."""
+
+    def __init__(self, loc, covariance_matrix, event_dims=1):
+        self.loc, self.covariance_matrix, self.event_dims = loc, covariance_matrix, event_dims
+
+    def shape(self):
+        return tuple(self.loc.shape)
+
+    @property
+    def batch_shape(self):
+        return tuple(self.loc.shape[:-1 - (self.event_dims - 1)]) if self.event_dims > 1 else tuple(self.loc.shape[:-1])
+
+    @property
+    def event_shape(self):
+        return tuple(self.loc.shape[-self.event_dims:])
+
+    def log_prob(self, value):
+        Lc = torch.linalg.cholesky(self.covariance_matrix)
+        diff = (value - self.loc).unsqueeze(-1)
+        z = torch.linalg.solve_triangular(Lc.expand(diff.shape[:-2] + Lc.shape[-2:]), diff, upper=False).squeeze(-1)
+        d = value.shape[-1]
+        lp = -0.5 * d * math.log(2 * math.pi) - torch.log(torch.diagonal(Lc, dim1=-2, dim2=-1)).sum(-1) - 0.5 * (z * z).sum(-1)
+        for _ in range(self.event_dims - 1):
+            lp = lp.sum(-1)
+        return lp
+
+
+class ConditionalDistribution:
+    """p(x_{1:T} | x_0, theta) for the trials ``x`` it was built from (``System.conditional_distribution``).
+
+    ``batch_shape = (n,)``, ``event_shape = (T, d)`` as in the reference (system.py:244 ``.to_event(1)``;
+    tests/infer_test.py:16 checks ``.shape()[1] == T``).  ``log_prob(x[:, 1:])`` is the fused CUDA likelihood."""
+
+    def __init__(self, system: "System", x: torch.Tensor, Sigma0=None):
+        self.system, self.x, self.Sigma0 = system, x, Sigma0
+
+    def shape(self):
+        n, T1, d = self.x.shape
+        return (n, T1 - 1, d)
+
+    @property
+    def batch_shape(self):
+        return (self.x.shape[0],)
+
+    @property
+    def event_shape(self):
+        return (self.x.shape[1] - 1, self.x.shape[2])
+
+    def log_prob(self, value: torch.Tensor) -> torch.Tensor:
+        if value.shape != self.x[:, 1:].shape:
+            raise ValueError(f"expected observations of shape {tuple(self.x[:, 1:].shape)}")
+        same = value.data_ptr() == self.x[:, 1:].data_ptr() or bool(torch.equal(value, self.x[:, 1:]))
+        if same:
+            return self.system.log_likelihood(self.x, Sigma0=self.Sigma0)
+        # different values under the moments conditioned on self.x: slow path
+        d = self.x.shape[-1]
+        mu, Sigma = self.system._moments(self.x, self.Sigma0)
+        return MultivariateNormalSeq(mu[..., :d], Sigma[..., :d, :d].unsqueeze(-4), event_dims=2).log_prob(value)
+
+
+class System:
+    def __init__(self, actor: LQGSpec, dynamics: LQGSpec):
+        self.actor = actor
+        self.dynamics = dynamics
+
+    # -- dimensions (system.py:17-60)
+    @property
+    def T(self):
+        return self.dynamics.A.shape[-3]
+
+    @property
+    def xdim(self):
+        return self.dynamics.A.shape[-1]
+
+    @property
+    def ydim(self):
+        return self.dynamics.F.shape[-2]
+
+    @property
+    def bdim(self):
+        return self.actor.A.shape[-1]
+
+    @property
+    def udim(self):
+        return self.dynamics.B.shape[-1]
+
+    @property
+    def device(self):
+        return self.actor.A.device
+
+    @property
+    def dtype(self):
+        return self.actor.A.dtype
+
+    def to(self, *args, **kw) -> "System":
+        mv = lambda s: LQGSpec(*[v.to(*args, **kw) if torch.is_tensor(v) else v for v in s])
+        new = object.__new__(type(self))
+        new.__dict__.update(self.__dict__)
+        new.actor = mv(self.actor)
+        new.dynamics = new.actor if self.dynamics is self.actor else mv(self.dynamics)
+        return new
+
+    def _default_sigma0(self, Sigma0):
+        if Sigma0 is not None:
+            return torch.as_tensor(Sigma0, dtype=self.dtype, device=self.device)
+        V0 = self.actor.V[..., 0, :, :]
+        return V0 @ mT(V0)
+
+    def _gains(self, Sigma0=None):
+        gains = lqr.backward(self.actor)
+        K = kf.forward(self.actor, Sigma0=self._default_sigma0(Sigma0))
+        return gains, K
+
+    # -- hot path ------------------------------------------------------------------------------------------
+    def log_likelihood(self, x: torch.Tensor, Sigma0=None) -> torch.Tensor:
+        """log p(x_{i,1:T} | x_{i,0}) per trial, summed over time (system.py:246-248).  x: (n, T+1, d)."""
+        s0 = None if Sigma0 is None else torch.as_tensor(Sigma0, dtype=self.dtype, device=self.device)
+        return runtime.log_likelihood(self.actor, self.dynamics, x.to(self.device), Sigma0=s0)
+
+    def conditional_distribution(self, x: torch.Tensor, Sigma0=None) -> ConditionalDistribution:
+        return ConditionalDistribution(self, x, Sigma0)
+
+    # -- slow paths ----------------------------------------------------------------------------------------
+    def _joint(self, gains_L, K):
+        """Joint (x, xhat) transition F[...,T,n,n] and noise factor G[...,T,n,x+y] (system.py:163-207)."""
+        a, dn = self.actor, self.dynamics
+        top = torch.cat([dn.A.expand(K.shape[:-2] + dn.A.shape[-2:]), dn.B @ gains_L], -1)
+        bot = torch.cat([K @ dn.F @ dn.A, a.A + a.B @ gains_L - K @ a.F @ a.A + K @ (dn.F @ dn.B - a.F @ a.B) @ gains_L], -1)
+        Fj = torch.cat([top, bot], -2)
+        zeros = torch.zeros(K.shape[:-2] + (self.xdim, self.ydim), dtype=K.dtype, device=K.device)
+        Gj = torch.cat([torch.cat([dn.V.expand(K.shape[:-2] + dn.V.shape[-2:]), zeros], -1),
+                        torch.cat([K @ dn.F @ dn.V, K @ dn.W], -1)], -2)
+        return Fj, Gj
+
+    def _moments(self, x: torch.Tensor, Sigma0=None):
+        """mu[..., n_trials, T, n], Sigma[..., T, n, n]: predictive moments of (x, xhat)_{t+1} given x_{0..t}."""
+        x = x.to(self.device, torch.float64)
+        n, T1, d = x.shape
+        gains, K = self._gains(Sigma0)
+        Fj, Gj = self._joint(gains.L.double(), K.double())
+        T = Fj.shape[-3]
+        if T != T1 - 1:
+            raise ValueError(f"need T+1 = {T + 1} observations per trial, got {T1}")
+        batch = Fj.shape[:-3]
+        nj = Fj.shape[-1]
+        mu = torch.zeros(batch + (n, nj), dtype=torch.float64, device=self.device)
+        mu[..., :d] = x[:, 0]
+        Sig = Gj[..., 0, :, :] @ mT(Gj[..., 0, :, :])
+        mus, Sigs = [], []
+        for t in range(T):
+            F, G = Fj[..., t, :, :], Gj[..., t, :, :]
+            FS = F @ Sig
+            Soo = Sig[..., :d, :d]
+            w = torch.linalg.solve(Soo, mT(x[:, t] - mu[..., :d]))
+            mu = mu @ mT(F) + mT(FS[..., :, :d] @ w)
+            Sig = FS @ mT(F) + G @ mT(G) - FS[..., :, :d] @ torch.linalg.solve(Soo, (Sig @ mT(F))[..., :d, :])
+            mus.append(mu)
+            Sigs.append(Sig)
+        return torch.stack(mus, -2), torch.stack(Sigs, -3)
+
+    def conditional_moments(self, x: torch.Tensor, Sigma0=None):
+        """One trial ``x[T+1, d]`` -> ``mu[T, n]``, ``Sigma[T, n, n]`` (system.py:142-235)."""
+        mu, Sigma = self._moments(x.unsqueeze(0), Sigma0)
+        return mu[..., 0, :, :].to(self.dtype), Sigma.to(self.dtype)
+
+    def belief_tracking_distribution(self, x: torch.Tensor, Sigma0=None) -> MultivariateNormalSeq:
+        """Moments of the belief xhat given the observed states (system.py:250-257)."""
+        d = self.xdim
+        mu, Sigma = self._moments(x, Sigma0)
+        return MultivariateNormalSeq(mu[..., d:].to(self.dtype), Sigma[..., d:, d:].unsqueeze(-4).to(self.dtype))
+
+    def simulate(self, rng_key=None, n=1, x0=None, xhat0=None, Sigma0=None, return_all=False):
+        """Simulate n trials (system.py:62-140).  ``rng_key``: int seed or ``torch.Generator`` (the reference's JAX
+        threefry stream cannot be reproduced; samples differ, the distribution does not).  Un-batched specs only."""
+        if self.actor.A.dim() != 3:
+            raise NotImplementedError("simulate() expects an un-batched system")
+        dev, dt = self.device, self.dtype
+        if isinstance(rng_key, torch.Generator):
+            gen = rng_key
+        else:
+            gen = torch.Generator(device=dev)
+            gen.manual_seed(int(rng_key) if rng_key is not None else 0)
+        gains, K = self._gains(Sigma0)
+        T, xd, bd, yd = self.T, self.xdim, self.bdim, self.ydim
+        x = torch.zeros(n, xd, dtype=dt, device=dev) if x0 is None else torch.as_tensor(x0, dtype=dt, device=dev).expand(n, xd).clone()
+        xh = torch.zeros(n, bd, dtype=dt, device=dev) if xhat0 is None else torch.as_tensor(xhat0, dtype=dt, device=dev).expand(n, bd).clone()
+        eps = torch.randn(T, n, xd, dtype=dt, device=dev, generator=gen)
+        eta = torch.randn(T, n, yd, dtype=dt, device=dev, generator=gen)
+        a, dn = self.actor, self.dynamics
+        xs, xhs, ys, us = [x], [xh], [], []
+        for t in range(T):
+            u = xh @ mT(gains.L[t]) + gains.l[t]
+            x = x @ mT(dn.A[t]) + u @ mT(dn.B[t]) + eps[t] @ mT(dn.V[t])
+            y = x @ mT(dn.F[t]) + eta[t] @ mT(dn.W[t])
+            xp = xh @ mT(a.A[t]) + u @ mT(a.B[t])
+            xh = xp + (y - xp @ mT(a.F[t])) @ mT(K[t])
+            xs.append(x); xhs.append(xh); ys.append(y); us.append(u)
+        X = torch.stack(xs, 1)
+        if return_all:
+            return X, torch.stack(xhs, 1), torch.stack(ys, 1), torch.stack(us, 1)
+        return X
+
+    def to_numpyro(self, Sigma0=None, xdim=None):
+        return NumpyroLQG(self, Sigma0=Sigma0, xdim=xdim)
+
+
+def _mat(M, ref=None):
+    return torch.as_tensor(M) if not torch.is_tensor(M) else M
+
+
+def Dynamics(A, B, F, V, W, T=1000) -> LQGSpec:
+    """system.py:331-345."""
+    A, B, F, V, W = map(_mat, (A, B, F, V, W))
+    xdim, udim = A.shape[-1], B.shape[-1]
+    kw = dict(dtype=A.dtype, device=A.device)
+    return time_stack_spec(A=A, B=B, F=F, V=V, W=W, Q=torch.zeros(xdim, xdim, **kw), R=torch.zeros(udim, udim, **kw), T=T)
+
+
+def Actor(A, B, F, V, W, Q, R, T=1000) -> LQGSpec:
+    """system.py:348-349."""
+    return time_stack_spec(*map(_mat, (A, B, F, V, W, Q, R)), T=T)
+
+
+class LQG(System):
+    """system.py:352-356."""
+
+    def __init__(self, A, B, F, V, W, Q, R, T=1000):
+        spec = time_stack_spec(*map(_mat, (A, B, F, V, W, Q, R)), T=T)
+        super().__init__(actor=spec, dynamics=spec)
+
+
+class NumpyroLQG:
+    """Distribution adaptor with the reference's contract (system.py:358-376): ``event_shape = (T+1, xdim)``,
+    ``batch_shape = ()``, ``log_prob(x[n,T+1,d]) -> [n]``, ``sample(key, sample_shape)``.  numpyro itself is not
+    installable in this image, so this is a plain class with the same methods (see INTEGRATION.md for the
+    numpyro/JAX binding)."""
+
+    def __init__(self, system: System, xdim=None, Sigma0=None):
+        self.system = system
+        self.Sigma0 = Sigma0
+        xdim = system.xdim if xdim is None else xdim
+        self.event_shape = (system.T + 1, xdim)
+        self.batch_shape = ()
+
+    def log_prob(self, x):
+        return self.system.log_likelihood(x, Sigma0=self.Sigma0)
+
+    def sample(self, key, sample_shape=()):
+        if len(sample_shape) == 0:
+            return self.system.simulate(key, n=1, Sigma0=self.Sigma0)[0]
+        return self.system.simulate(key, n=sample_shape[0], Sigma0=self.Sigma0)
