@@ -119,7 +119,8 @@ const char* lqgk_version(void);
 /* Per-kernel timing for bench.py: when enabled, every kernel launch of the calling thread's entry-point calls is
  * bracketed by CUDA events on the launching stream.  lqgk_profile_read() synchronises on those events, sums the
  * elapsed milliseconds (and launch counts) per kernel kind, resets the log and returns the number of kinds:
- * 0 pack, 1 lqr_fwd, 2 kf_fwd, 3 cov_fwd, 4 trial_fwd, 5 misc, 6 trial_rev, 7 cov_rev, 8 kf_rev, 9 lqr_rev, 10 unpack. */
+ * 0 pack, 1 lqr_fwd, 2 kf_fwd, 3 cov_fwd, 4 trial_fwd, 5 misc, 6 trial_rev, 7 cov_rev, 8 kf_rev, 9 lqr_rev, 10 unpack,
+ * 11 cov_contrib, 12 reduce. */
 int lqgk_profile_enable(int on);
 int lqgk_profile_read(float* ms_by_kind, int32_t* launches_by_kind, int nkinds);
 /* Launches an FMA-saturating micro-kernel (fp64 != 0: DFMA, else FFMA) on `stream`; *flop_out = flops it executes.

@@ -217,7 +217,7 @@ class Library:
         return int(self.lib.lqgk_last_launch_count())
 
     PROFILE_KINDS = ("pack", "lqr_fwd", "kf_fwd", "cov_fwd", "trial_fwd", "misc", "trial_rev", "cov_rev", "kf_rev",
-                     "lqr_rev", "unpack")
+                     "lqr_rev", "unpack", "cov_contrib", "reduce")
 
     def profile_enable(self, on: bool):
         self._check(self.lib.lqgk_profile_enable(C.c_int(1 if on else 0)), "lqgk_profile_enable")

@@ -66,7 +66,8 @@ struct Dims {
   static constexpr int REC_F = 0, REC_J = N * N, REC_LINV = REC_J + R * D, REC_LOGDET = REC_LINV + tri(D);
   static constexpr int REC = round4(REC_LOGDET + 1);
   // per-step sums over trials the covariance adjoint consumes (float): Fb (N*N) | Jb (R*D) | Wv (tri D)
-  static constexpr int SUM_F = 0, SUM_J = N * N, SUM_W = SUM_J + R * D, NSUM = SUM_W + tri(D);
+  // (SUM_J is 16-byte aligned so the [SUM_J, SUMP) tail of a row can be fetched with one bulk copy)
+  static constexpr int SUM_F = 0, SUM_J = round4(N * N), SUM_W = SUM_J + R * D, NSUM = SUM_W + tri(D);
   static constexpr int SUMP = round4(NSUM);
   // sample-minor FP64 workspace rows per step
   static constexpr int EL = U * B, EK = B * Y, ES = tri(B), EP = tri(B), EC = tri(R);
@@ -492,24 +493,30 @@ struct CovFwd {
   }
   // Initial C_0 from Sig_0 = N_0                                          system.py:211-212
   template <class V>
-  LQGK_HD static void init(const V& c, const double* K0, double* Cm) {
-    double Nj[N * N], Linv[D * D], J[R * D], ld;
+  LQGK_HD static void init(const V& c, const double* K0, double* Cm, double* J0) {
+    double Nj[N * N], Linv[D * D], ld;
     joint_N(c, K0, Nj);
-    condition(Nj, Linv, ld, J, Cm);
+    condition(Nj, Linv, ld, J0, Cm);
   }
   // One step: C_t -> C_{t+1}; emits the float record for the trial kernels through `put(idx, value)`.
-  template <class V, class Put>
-  LQGK_HD static void step(const V& c, const double* L, const double* K, double* Cm, Put&& put) {
+  // save(which, e, v): optional FP64 outputs for the adjoint: which 0 = Fu_t (N x R row-major), 1 = J_t then S'^-1_t.
+  template <class V, class Put, class Save>
+  LQGK_HD static void step(const V& c, const double* L, const double* K, double* Cm, Put&& put, Save&& save) {
     double Fj[N * N], Nj[N * N], Sig[N * N];
     joint_F(c, L, K, Fj);
     LQGK_UNROLL for (int i = 0; i < N * N; ++i) put(DM::REC_F + i, (float)Fj[i]);
+    LQGK_UNROLL for (int i = 0; i < N; ++i) LQGK_UNROLL for (int j = 0; j < R; ++j) save(0, i * R + j, Fj[i * N + D + j]);
     joint_N(c, K, Nj);
     predict(Fj, Cm, Nj, Sig);
     double Linv[D * D], J[R * D], ld;
     condition(Sig, Linv, ld, J, Cm);
-    LQGK_UNROLL for (int i = 0; i < R * D; ++i) put(DM::REC_J + i, (float)J[i]);
-    LQGK_UNROLL for (int i = 0; i < D; ++i) LQGK_UNROLL for (int j = 0; j <= i; ++j)
+    LQGK_UNROLL for (int i = 0; i < R * D; ++i) { put(DM::REC_J + i, (float)J[i]); save(1, i, J[i]); }
+    LQGK_UNROLL for (int i = 0; i < D; ++i) LQGK_UNROLL for (int j = 0; j <= i; ++j) {
       put(DM::REC_LINV + i * (i + 1) / 2 + j, (float)Linv[i * D + j]);
+      double sv = 0.0;
+      LQGK_UNROLL for (int k = i; k < D; ++k) sv += Linv[k * D + i] * Linv[k * D + j];   // (Linv^T Linv)[i][j], i >= j
+      save(1, R * D + i * (i + 1) / 2 + j, sv);
+    }
     put(DM::REC_LOGDET, (float)ld);
   }
 };
@@ -594,9 +601,9 @@ struct Trial {
   template <int IDX>
   LQGK_HD static float sum_term(const float* cb, const float* eb, const float* x0, const float* c,
                                 const float* e, const float* v, float w) {
-    if constexpr (IDX >= DM::NSUM) {
+    if constexpr (IDX >= DM::NSUM || (IDX >= N * N && IDX < DM::SUM_J)) {
       return 0.f;
-    } else if constexpr (IDX < DM::SUM_J) {
+    } else if constexpr (IDX < N * N) {
       constexpr int i = IDX / N, j = IDX % N;
       float a, b;
       if constexpr (i < D) a = -eb[i]; else a = cb[i - D];
@@ -615,184 +622,225 @@ struct Trial {
 };
 
 // ================================================================================================
-// Covariance adjoint (one step, t descending).  Local constants as CovC; accumulators (cotangents of the
-// derived constants) share CovC's local layout and are updated through `acc(e)` (read-modify-write).
+// Covariance adjoint, restructured for the GPU: the only sequential quantity is the
+// cotangent Cb of the carried covariance block.  CovSeqRev advances Cb by one step using only stored forward
+// quantities (Fu_t, J_t, S'^-1_t) and emits the symmetric joint cotangent Sgb_t and SF_t = Sgb_t Fu_t; the
+// expensive, time-independent contraction of those with (L_t, K_t, constants) is done by CovContrib for all
+// time steps in parallel, which writes per-step contributions that a generic reduction sums over time.
 template <class DM>
-struct CovRev {
+struct CovSeqRev {
+  static constexpr int D = DM::D, N = DM::N, R = DM::R;
+  static constexpr int NSGB = tri(N), NSF = N * R, NJS = R * D + tri(D);
+  static constexpr int SC_BH = 0, SC_SS = R * D, SC_N = R * D + tri(D);   // scratch (shared memory) layout
+
+  // fu(e): Fu_t row-major N x R;  js(e): J_t (R x D) then S'^-1_t (packed lower);  get(idx): float sums of step t
+  // sc(e): per-lane scratch;  Cb: R x R full symmetric (in: cotangent of C_{t+1}; out: of C_t)
+  // esgb(e, v): emit Sgb_t packed lower over the joint index;  esf(e, v): emit SF_t row-major N x R
+  template <class FU, class JS, class Get, class SC, class ESgb, class ESf>
+  LQGK_HD static void step(FU&& fu, JS&& js, Get&& get, double sw, SC&& sc, double* Cb, ESgb&& esgb, ESf&& esf) {
+    {
+      double J[R * D], Sinv[D * D], Ss[D * D];
+      LQGK_UNROLL for (int e = 0; e < R * D; ++e) J[e] = js(e);
+      LQGK_UNROLL for (int i = 0; i < D; ++i) LQGK_UNROLL for (int j = 0; j <= i; ++j) {
+        double a = js(R * D + i * (i + 1) / 2 + j);
+        Sinv[i * D + j] = a;
+        Sinv[j * D + i] = a;
+        Ss[i * D + j] = 0.5 * (double)get(DM::SUM_W + i * (i + 1) / 2 + j) - 0.5 * sw * a;
+      }
+      LQGK_UNROLL for (int i = 0; i < R; ++i) {
+        double z[D];
+        LQGK_UNROLL for (int j = 0; j < D; ++j) {
+          double cbj = 0.0, jbs = 0.0;
+          LQGK_UNROLL for (int k = 0; k < R; ++k) cbj += Cb[i * R + k] * J[k * D + j];
+          LQGK_UNROLL for (int k = 0; k < D; ++k) jbs += (double)get(DM::SUM_J + i * D + k) * Sinv[k * D + j];
+          z[j] = cbj - jbs;
+          double bh = -cbj + 0.5 * jbs;
+          sc(SC_BH + i * D + j) = bh;
+          esgb(sidx(D + i, j), bh);
+        }
+        LQGK_UNROLL for (int a = 0; a < D; ++a) LQGK_UNROLL for (int b = 0; b <= a; ++b)
+          Ss[a * D + b] += 0.5 * (J[i * D + a] * z[b] + J[i * D + b] * z[a]);
+      }
+      LQGK_UNROLL for (int a = 0; a < D; ++a) LQGK_UNROLL for (int b = 0; b <= a; ++b) {
+        sc(SC_SS + a * (a + 1) / 2 + b) = Ss[a * D + b];
+        esgb(sidx(a, b), Ss[a * D + b]);
+      }
+      LQGK_UNROLL for (int i = 0; i < R; ++i) LQGK_UNROLL for (int j = 0; j <= i; ++j) esgb(sidx(D + i, D + j), Cb[i * R + j]);
+    }
+    double Fo[D * R], Fuu[R * R], Cn[R * R];
+    LQGK_UNROLL for (int e = 0; e < D * R; ++e) Fo[e] = fu(e);
+    LQGK_UNROLL for (int e = 0; e < R * R; ++e) Fuu[e] = fu(D * R + e);
+    LQGK_UNROLL for (int e = 0; e < R * R; ++e) Cn[e] = 0.0;
+    LQGK_UNROLL for (int i = 0; i < R; ++i) {            // SF_u row i = Bh[i,:] Fo + Cb[i,:] Fuu
+      double row[R];
+      LQGK_UNROLL for (int c = 0; c < R; ++c) row[c] = 0.0;
+      LQGK_UNROLL for (int k = 0; k < D; ++k) {
+        double b = sc(SC_BH + i * D + k);
+        LQGK_UNROLL for (int c = 0; c < R; ++c) row[c] += b * Fo[k * R + c];
+      }
+      LQGK_UNROLL for (int k = 0; k < R; ++k) LQGK_UNROLL for (int c = 0; c < R; ++c) row[c] += Cb[i * R + k] * Fuu[k * R + c];
+      LQGK_UNROLL for (int c = 0; c < R; ++c) esf((D + i) * R + c, row[c]);
+      LQGK_UNROLL for (int a = 0; a < R; ++a) LQGK_UNROLL for (int b = 0; b <= a; ++b) Cn[a * R + b] += Fuu[i * R + a] * row[b];
+    }
+    LQGK_UNROLL for (int k = 0; k < D; ++k) {            // SF_o row k = Ss[k,:] Fo + Bh[:,k]^T Fuu
+      double row[R];
+      LQGK_UNROLL for (int c = 0; c < R; ++c) row[c] = 0.0;
+      LQGK_UNROLL for (int m = 0; m < D; ++m) {
+        double sv = sc(SC_SS + sidx(k, m));
+        LQGK_UNROLL for (int c = 0; c < R; ++c) row[c] += sv * Fo[m * R + c];
+      }
+      LQGK_UNROLL for (int i = 0; i < R; ++i) {
+        double b = sc(SC_BH + i * D + k);
+        LQGK_UNROLL for (int c = 0; c < R; ++c) row[c] += b * Fuu[i * R + c];
+      }
+      LQGK_UNROLL for (int c = 0; c < R; ++c) esf(k * R + c, row[c]);
+      LQGK_UNROLL for (int a = 0; a < R; ++a) LQGK_UNROLL for (int b = 0; b <= a; ++b) Cn[a * R + b] += Fo[k * R + a] * row[b];
+    }
+    LQGK_UNROLL for (int a = 0; a < R; ++a) LQGK_UNROLL for (int b = 0; b <= a; ++b) {
+      Cb[a * R + b] = Cn[a * R + b];
+      Cb[b * R + a] = Cn[a * R + b];
+    }
+  }
+  // After t = 0: cotangent of C_0 = cond(N_0) as a joint symmetric cotangent (Sgb of the initial condition).
+  template <class J0, class ESgb>
+  LQGK_HD static void init(J0&& j0, const double* Cb, ESgb&& esgb) {
+    double J[R * D], CbJ[R * D];
+    LQGK_UNROLL for (int e = 0; e < R * D; ++e) J[e] = j0(e);
+    mm<R, R, D>(Cb, J, CbJ);
+    LQGK_UNROLL for (int i = 0; i < R; ++i) LQGK_UNROLL for (int j = 0; j <= i; ++j) esgb(sidx(D + i, D + j), Cb[i * R + j]);
+    LQGK_UNROLL for (int i = 0; i < R; ++i) LQGK_UNROLL for (int j = 0; j < D; ++j) esgb(sidx(D + i, j), -CbJ[i * D + j]);
+    LQGK_UNROLL for (int a = 0; a < D; ++a) LQGK_UNROLL for (int b = 0; b <= a; ++b) {
+      double v = 0.0;
+      LQGK_UNROLL for (int k = 0; k < R; ++k) v += J[k * D + a] * CbJ[k * D + b];
+      esgb(sidx(a, b), v);
+    }
+  }
+};
+
+// Time-parallel contraction of (Sgb_t, SF_t, trial sums) with (L_t, K_t, constants): per-step contributions to the
+// derived-constant cotangents (CovC layout) and the gain cotangents Lb_t, Kb_t.  Two passes keep the register
+// footprint below 255: PASS 0 = noise part (N11, FN, Om, Kb noise part) + Ad, Bd, FAd, Aa, Ba, Lb;
+// PASS 1 = FAa, Dm and the transition part of Kb (added to what PASS 0 stored).
+template <class DM>
+struct CovContrib {
   static constexpr int X = DM::X, B = DM::B, U = DM::U, Y = DM::Y, D = DM::D, N = DM::N, R = DM::R;
   using C = CovC<DM>;
-  using F = CovFwd<DM>;
 
-  // Push joint-level cotangents Fb (N x N) and symmetric Nb (N x N) into accumulators and Lb (+=), Kb (+=).
-  template <class V, class A>
-  LQGK_HD static void joint_bar(const V& c, A&& acc, const double* L, const double* K, const double* Fb,
-                                const double* Nb, double* Lb, double* Kb) {
-    // --- F blocks: F11 = Fb[:X,:X], F12 = Fb[:X,X:], F21 = Fb[X:,:X], F22 = Fb[X:,X:]
-    LQGK_UNROLL for (int i = 0; i < X; ++i) LQGK_UNROLL for (int j = 0; j < X; ++j) acc(C::Ad + i * X + j) += Fb[i * N + j];
-    LQGK_UNROLL for (int i = 0; i < X; ++i) LQGK_UNROLL for (int k = 0; k < U; ++k) {   // Bd += F12 L^T
+  // Row m of the joint transition cotangent: trial sums + [0 | 2 SF_m C].
+  template <class SFr, class Get>
+  LQGK_HD static void fb_row(int m, SFr&& sf, Get&& get, const double* Cm, bool use_trial, double* fb) {
+    double sfr[R];
+    LQGK_UNROLL for (int k = 0; k < R; ++k) sfr[k] = sf(m * R + k);
+    LQGK_UNROLL for (int j = 0; j < N; ++j) fb[j] = use_trial ? (double)get(DM::SUM_F + m * N + j) : 0.0;
+    LQGK_UNROLL for (int j = 0; j < R; ++j) {
       double a = 0.0;
-      LQGK_UNROLL for (int j = 0; j < B; ++j) a += Fb[i * N + X + j] * L[k * B + j];
-      acc(C::Bd + i * U + k) += a;
+      LQGK_UNROLL for (int k = 0; k < R; ++k) a += sfr[k] * Cm[k * R + j];
+      fb[D + j] += 2.0 * a;
     }
-    LQGK_UNROLL for (int k = 0; k < Y; ++k) LQGK_UNROLL for (int j = 0; j < X; ++j) {   // FAd += K^T F21
-      double a = 0.0;
-      LQGK_UNROLL for (int i = 0; i < B; ++i) a += K[i * Y + k] * Fb[(X + i) * N + j];
-      acc(C::FAd + k * X + j) += a;
+  }
+  // Noise part for one symmetric joint cotangent Sgb (read through sgb(e), packed lower).  Accumulates (+=) into
+  // n11[tri X], fn[Y*X], om[tri Y] and kb[B*Y].
+  template <class V, class SG>
+  LQGK_HD static void noise_part(const V& c, SG&& sgb, const double* K, double* n11, double* fn, double* om, double* kb) {
+    LQGK_UNROLL for (int i = 0; i < X; ++i) LQGK_UNROLL for (int j = 0; j <= i; ++j) n11[i * (i + 1) / 2 + j] += sgb(sidx(i, j));
+    LQGK_UNROLL for (int i = 0; i < B; ++i) {
+      double nbx[X], nbb[B], nk[Y];
+      LQGK_UNROLL for (int j = 0; j < X; ++j) nbx[j] = sgb(sidx(X + i, j));
+      LQGK_UNROLL for (int j = 0; j < B; ++j) nbb[j] = sgb(sidx(X + i, X + j));
+      LQGK_UNROLL for (int k = 0; k < Y; ++k) {
+        double a = 0.0;
+        LQGK_UNROLL for (int j = 0; j < B; ++j) a += nbb[j] * K[j * Y + k];
+        nk[k] = a;                                                           // (Nbb K)[i, k]
+        LQGK_UNROLL for (int j = 0; j < X; ++j) fn[k * X + j] += 2.0 * K[i * Y + k] * nbx[j];
+      }
+      LQGK_UNROLL for (int k = 0; k < Y; ++k) LQGK_UNROLL for (int m = 0; m <= k; ++m)
+        om[k * (k + 1) / 2 + m] += 0.5 * (K[i * Y + k] * nk[m] + K[i * Y + m] * nk[k]);
+      LQGK_UNROLL for (int k = 0; k < Y; ++k) {
+        double a = 0.0;
+        LQGK_UNROLL for (int j = 0; j < X; ++j) a += nbx[j] * c(C::FN + k * X + j);
+        LQGK_UNROLL for (int m = 0; m < Y; ++m) a += nk[m] * c(C::Om + sidx(m, k));
+        kb[i * Y + k] += 2.0 * a;
+      }
     }
-    LQGK_UNROLL for (int i = 0; i < B; ++i) LQGK_UNROLL for (int j = 0; j < B; ++j) acc(C::Aa + i * B + j) += Fb[(X + i) * N + X + j];
-    double F22Lt[B * U];                                                                 // F22 L^T
-    LQGK_UNROLL for (int i = 0; i < B; ++i) LQGK_UNROLL for (int k = 0; k < U; ++k) {
-      double a = 0.0;
-      LQGK_UNROLL for (int j = 0; j < B; ++j) a += Fb[(X + i) * N + X + j] * L[k * B + j];
-      F22Lt[i * U + k] = a;
-      acc(C::Ba + i * U + k) += a;
+  }
+  // PASS 0.  out(e, v): store contribution e (CovC layout) of this step;  Lb, Kb: overwritten.
+  // `init_sgb` (may be null): second Sgb (initial condition) whose noise part is added at t == 0.
+  template <class V, class SG, class SGI, class SFr, class Get, class Out>
+  LQGK_HD static void pass0(const V& c, SG&& sgb, bool has_init, SGI&& sgb_init, SFr&& sf, Get&& get, const double* Cm,
+                            const double* L, const double* K, Out&& out, double* Lb, double* Kb) {
+    {
+      double n11[tri(X)], fn[Y * X], om[tri(Y)];
+      LQGK_UNROLL for (int e = 0; e < tri(X); ++e) n11[e] = 0.0;
+      LQGK_UNROLL for (int e = 0; e < Y * X; ++e) fn[e] = 0.0;
+      LQGK_UNROLL for (int e = 0; e < tri(Y); ++e) om[e] = 0.0;
+      LQGK_UNROLL for (int e = 0; e < B * Y; ++e) Kb[e] = 0.0;
+      noise_part(c, sgb, K, n11, fn, om, Kb);
+      if (has_init) noise_part(c, sgb_init, K, n11, fn, om, Kb);
+      LQGK_UNROLL for (int e = 0; e < tri(X); ++e) out(C::N11 + e, n11[e]);
+      LQGK_UNROLL for (int e = 0; e < Y * X; ++e) out(C::FN + e, fn[e]);
+      LQGK_UNROLL for (int e = 0; e < tri(Y); ++e) out(C::Om + e, om[e]);
     }
-    LQGK_UNROLL for (int k = 0; k < Y; ++k) LQGK_UNROLL for (int j = 0; j < B; ++j) {   // FAa -= K^T F22
-      double a = 0.0;
-      LQGK_UNROLL for (int i = 0; i < B; ++i) a += K[i * Y + k] * Fb[(X + i) * N + X + j];
-      acc(C::FAa + k * B + j) -= a;
-    }
-    LQGK_UNROLL for (int k = 0; k < Y; ++k) LQGK_UNROLL for (int m = 0; m < U; ++m) {   // D += K^T F22 L^T
-      double a = 0.0;
-      LQGK_UNROLL for (int i = 0; i < B; ++i) a += K[i * Y + k] * F22Lt[i * U + m];
-      acc(C::Dm + k * U + m) += a;
-    }
-    // Lb += Bd^T F12 + (Ba + K D)^T F22
-    double BKD[B * U];
+    double KD[B * U], fad[Y * X];
     LQGK_UNROLL for (int i = 0; i < B; ++i) LQGK_UNROLL for (int m = 0; m < U; ++m) {
       double a = c(C::Ba + i * U + m);
       LQGK_UNROLL for (int k = 0; k < Y; ++k) a += K[i * Y + k] * c(C::Dm + k * U + m);
-      BKD[i * U + m] = a;
+      KD[i * U + m] = a;                                                     // Ba + K D
     }
-    LQGK_UNROLL for (int m = 0; m < U; ++m) LQGK_UNROLL for (int j = 0; j < B; ++j) {
-      double a = 0.0;
-      LQGK_UNROLL for (int i = 0; i < X; ++i) a += c(C::Bd + i * U + m) * Fb[i * N + X + j];
-      LQGK_UNROLL for (int i = 0; i < B; ++i) a += BKD[i * U + m] * Fb[(X + i) * N + X + j];
-      Lb[m * B + j] += a;
-    }
-    // Kb += F21 FAd^T - F22 FAa^T + F22 (D L)^T = F21 FAd^T - F22 FAa^T + (F22 L^T) D^T
-    LQGK_UNROLL for (int i = 0; i < B; ++i) LQGK_UNROLL for (int k = 0; k < Y; ++k) {
-      double a = 0.0;
-      LQGK_UNROLL for (int j = 0; j < X; ++j) a += Fb[(X + i) * N + j] * c(C::FAd + k * X + j);
-      LQGK_UNROLL for (int j = 0; j < B; ++j) a -= Fb[(X + i) * N + X + j] * c(C::FAa + k * B + j);
-      LQGK_UNROLL for (int m = 0; m < U; ++m) a += F22Lt[i * U + m] * c(C::Dm + k * U + m);
-      Kb[i * Y + k] += a;
-    }
-    // --- N blocks (Nb symmetric): N11 += Nxx ; FN += 2 K^T Nbx ; Om += K^T Nbb K ; Kb += 2 Nbx FN^T + 2 Nbb K Om
-    LQGK_UNROLL for (int i = 0; i < X; ++i) LQGK_UNROLL for (int j = 0; j <= i; ++j) acc(C::N11 + i * (i + 1) / 2 + j) += Nb[i * N + j];
-    LQGK_UNROLL for (int k = 0; k < Y; ++k) LQGK_UNROLL for (int j = 0; j < X; ++j) {
-      double a = 0.0;
-      LQGK_UNROLL for (int i = 0; i < B; ++i) a += K[i * Y + k] * Nb[(X + i) * N + j];
-      acc(C::FN + k * X + j) += 2.0 * a;
-    }
-    double NK[B * Y];                                                                    // Nbb K
-    LQGK_UNROLL for (int i = 0; i < B; ++i) LQGK_UNROLL for (int k = 0; k < Y; ++k) {
-      double a = 0.0;
-      LQGK_UNROLL for (int j = 0; j < B; ++j) a += Nb[(X + i) * N + X + j] * K[j * Y + k];
-      NK[i * Y + k] = a;
-    }
-    LQGK_UNROLL for (int k = 0; k < Y; ++k) LQGK_UNROLL for (int m = 0; m <= k; ++m) {
-      double a = 0.0;
-      LQGK_UNROLL for (int i = 0; i < B; ++i) a += K[i * Y + k] * NK[i * Y + m] + K[i * Y + m] * NK[i * Y + k];
-      acc(C::Om + k * (k + 1) / 2 + m) += 0.5 * a;
-    }
-    LQGK_UNROLL for (int i = 0; i < B; ++i) LQGK_UNROLL for (int k = 0; k < Y; ++k) {
-      double a = 0.0;
-      LQGK_UNROLL for (int j = 0; j < X; ++j) a += Nb[(X + i) * N + j] * c(C::FN + k * X + j);
-      LQGK_UNROLL for (int m = 0; m < Y; ++m) a += NK[i * Y + m] * c(C::Om + sidx(m, k));
-      Kb[i * Y + k] += 2.0 * a;
-    }
-  }
-
-  // One reverse step.  In: C_t (Cm), L_t, K_t, the float sums of this step via get(idx), sw = sum of trial
-  // weights, Cb = cotangent of C_{t+1} (R x R sym).  Out: Cb <- cotangent of C_t; Lb, Kb (overwritten).
-  template <class V, class A, class Get>
-  LQGK_HD static void step(const V& c, A&& acc, const double* L, const double* K, const double* Cm, Get&& get,
-                           double sw, double* Cb, double* Lb, double* Kb) {
-    double Fj[N * N], Sgb[N * N];
-    F::joint_F(c, L, K, Fj);
-    double Linv[D * D], J[R * D];
-    {
-      double Nj[N * N], Sig[N * N], Cn[R * R], ld;
-      F::joint_N(c, K, Nj);
-      F::predict(Fj, Cm, Nj, Sig);
-      F::condition(Sig, Linv, ld, J, Cn);
-    }
-    double Sinv[D * D];
-    mm_tn_sym<D, D>(Linv, Linv, Sinv);
-    // JbS = Jb S^-1 (R x D)
-    double JbS[R * D];
-    LQGK_UNROLL for (int i = 0; i < R; ++i) LQGK_UNROLL for (int j = 0; j < D; ++j) {
-      double a = 0.0;
-      LQGK_UNROLL for (int k = 0; k < D; ++k) a += (double)get(DM::SUM_J + i * D + k) * Sinv[k * D + j];
-      JbS[i * D + j] = a;
-    }
-    // CbJ = Cb J (R x D)
-    double CbJ[R * D];
-    mm<R, R, D>(Cb, J, CbJ);
-    // Sb = 1/2 Wv - 1/2 sw S^-1 + J^T Cb J - J^T Jb S^-1 ; symmetrised -> Sgb[o,o]
-    LQGK_UNROLL for (int i = 0; i < D; ++i) LQGK_UNROLL for (int j = 0; j <= i; ++j) {
-      double a = 0.5 * (double)get(DM::SUM_W + i * (i + 1) / 2 + j) - 0.5 * sw * Sinv[i * D + j];
-      LQGK_UNROLL for (int k = 0; k < R; ++k)
-        a += J[k * D + i] * CbJ[k * D + j] - 0.5 * (J[k * D + i] * JbS[k * D + j] + J[k * D + j] * JbS[k * D + i]);
-      Sgb[i * N + j] = a;
-      Sgb[j * N + i] = a;
-    }
-    // Bb/2 = -Cb J + 1/2 Jb S^-1 -> Sgb[u,o] and its transpose
-    LQGK_UNROLL for (int i = 0; i < R; ++i) LQGK_UNROLL for (int j = 0; j < D; ++j) {
-      double a = -CbJ[i * D + j] + 0.5 * JbS[i * D + j];
-      Sgb[(D + i) * N + j] = a;
-      Sgb[j * N + D + i] = a;
-    }
-    LQGK_UNROLL for (int i = 0; i < R; ++i) LQGK_UNROLL for (int j = 0; j < R; ++j) Sgb[(D + i) * N + D + j] = Cb[i * R + j];
-    // SF = Sgb F[:,u]  (N x R) ; Fb = sums.Fb ; Fb[:,u] += 2 SF C ; Cb <- F[:,u]^T SF (sym)
-    double SF[N * R];
-    LQGK_UNROLL for (int i = 0; i < N; ++i) LQGK_UNROLL for (int k = 0; k < R; ++k) {
-      double a = 0.0;
-      LQGK_UNROLL for (int m = 0; m < N; ++m) a += Sgb[i * N + m] * Fj[m * N + D + k];
-      SF[i * R + k] = a;
-    }
-    double Fb[N * N];
-    LQGK_UNROLL for (int i = 0; i < N; ++i) {
-      LQGK_UNROLL for (int j = 0; j < D; ++j) Fb[i * N + j] = (double)get(DM::SUM_F + i * N + j);
-      LQGK_UNROLL for (int j = 0; j < R; ++j) {
-        double a = 0.0;
-        LQGK_UNROLL for (int k = 0; k < R; ++k) a += SF[i * R + k] * Cm[k * R + j];
-        Fb[i * N + D + j] = (double)get(DM::SUM_F + i * N + D + j) + 2.0 * a;
+    LQGK_UNROLL for (int e = 0; e < Y * X; ++e) fad[e] = 0.0;
+    LQGK_UNROLL for (int e = 0; e < U * B; ++e) Lb[e] = 0.0;
+    LQGK_UNROLL for (int m = 0; m < N; ++m) {
+      double fb[N];
+      fb_row(m, sf, get, Cm, true, fb);
+      if (m < X) {
+        LQGK_UNROLL for (int j = 0; j < X; ++j) out(C::Ad + m * X + j, fb[j]);
+        LQGK_UNROLL for (int k = 0; k < U; ++k) {
+          double a = 0.0;
+          LQGK_UNROLL for (int j = 0; j < B; ++j) a += fb[X + j] * L[k * B + j];
+          out(C::Bd + m * U + k, a);
+          double bd = c(C::Bd + m * U + k);
+          LQGK_UNROLL for (int j = 0; j < B; ++j) Lb[k * B + j] += bd * fb[X + j];
+        }
+      } else {
+        const int i = m - X;
+        LQGK_UNROLL for (int k = 0; k < Y; ++k) LQGK_UNROLL for (int j = 0; j < X; ++j) fad[k * X + j] += K[i * Y + k] * fb[j];
+        LQGK_UNROLL for (int j = 0; j < B; ++j) out(C::Aa + i * B + j, fb[X + j]);
+        LQGK_UNROLL for (int k = 0; k < U; ++k) {
+          double a = 0.0;
+          LQGK_UNROLL for (int j = 0; j < B; ++j) a += fb[X + j] * L[k * B + j];
+          out(C::Ba + i * U + k, a);
+          LQGK_UNROLL for (int j = 0; j < B; ++j) Lb[k * B + j] += KD[i * U + k] * fb[X + j];
+        }
       }
     }
-    LQGK_UNROLL for (int i = 0; i < R; ++i) LQGK_UNROLL for (int j = 0; j <= i; ++j) {
-      double a = 0.0;
-      LQGK_UNROLL for (int m = 0; m < N; ++m) a += Fj[m * N + D + i] * SF[m * R + j] + Fj[m * N + D + j] * SF[m * R + i];
-      Cb[i * R + j] = 0.5 * a;
-      Cb[j * R + i] = 0.5 * a;
-    }
-    LQGK_UNROLL for (int i = 0; i < U * B; ++i) Lb[i] = 0.0;
-    LQGK_UNROLL for (int i = 0; i < B * Y; ++i) Kb[i] = 0.0;
-    joint_bar(c, acc, L, K, Fb, Sgb, Lb, Kb);
+    LQGK_UNROLL for (int e = 0; e < Y * X; ++e) out(C::FAd + e, fad[e]);
   }
-  // After t = 0: cotangent of C_0 = cond(N_0) flows into N_0 (adds to Lb0 (unchanged), Kb0 and accumulators).
-  template <class V, class A>
-  LQGK_HD static void init_bar(const V& c, A&& acc, const double* L0, const double* K0, const double* Cb, double* Lb,
-                               double* Kb) {
-    double Nj[N * N], Linv[D * D], J0[R * D], Cn[R * R], ld;
-    F::joint_N(c, K0, Nj);
-    F::condition(Nj, Linv, ld, J0, Cn);
-    double CbJ[R * D], Sgb[N * N], Fb[N * N];
-    mm<R, R, D>(Cb, J0, CbJ);
-    LQGK_UNROLL for (int i = 0; i < N * N; ++i) Fb[i] = 0.0;
-    LQGK_UNROLL for (int i = 0; i < R; ++i) LQGK_UNROLL for (int j = 0; j < R; ++j) Sgb[(D + i) * N + D + j] = Cb[i * R + j];
-    LQGK_UNROLL for (int i = 0; i < R; ++i) LQGK_UNROLL for (int j = 0; j < D; ++j) {
-      Sgb[(D + i) * N + j] = -CbJ[i * D + j];
-      Sgb[j * N + D + i] = -CbJ[i * D + j];
+  // PASS 1.  Kb: in = what PASS 0 stored (noise part), out = total.
+  template <class V, class SFr, class Get, class Out>
+  LQGK_HD static void pass1(const V& c, SFr&& sf, Get&& get, const double* Cm, const double* L, const double* K, Out&& out,
+                            double* Kb) {
+    double faa[Y * B], dm[Y * U];
+    LQGK_UNROLL for (int e = 0; e < Y * B; ++e) faa[e] = 0.0;
+    LQGK_UNROLL for (int e = 0; e < Y * U; ++e) dm[e] = 0.0;
+    LQGK_UNROLL for (int i = 0; i < B; ++i) {
+      double fb[N], t2[U];
+      fb_row(X + i, sf, get, Cm, true, fb);
+      LQGK_UNROLL for (int k = 0; k < U; ++k) {
+        double a = 0.0;
+        LQGK_UNROLL for (int j = 0; j < B; ++j) a += fb[X + j] * L[k * B + j];
+        t2[k] = a;                                                           // (F22 L^T)[i, k]
+      }
+      LQGK_UNROLL for (int k = 0; k < Y; ++k) {
+        LQGK_UNROLL for (int j = 0; j < B; ++j) faa[k * B + j] -= K[i * Y + k] * fb[X + j];
+        LQGK_UNROLL for (int m = 0; m < U; ++m) dm[k * U + m] += K[i * Y + k] * t2[m];
+        double a = 0.0;
+        LQGK_UNROLL for (int j = 0; j < X; ++j) a += fb[j] * c(C::FAd + k * X + j);
+        LQGK_UNROLL for (int j = 0; j < B; ++j) a -= fb[X + j] * c(C::FAa + k * B + j);
+        LQGK_UNROLL for (int m = 0; m < U; ++m) a += t2[m] * c(C::Dm + k * U + m);
+        Kb[i * Y + k] += a;
+      }
     }
-    LQGK_UNROLL for (int i = 0; i < D; ++i) LQGK_UNROLL for (int j = 0; j <= i; ++j) {
-      double a = 0.0;
-      LQGK_UNROLL for (int k = 0; k < R; ++k) a += J0[k * D + i] * CbJ[k * D + j];
-      Sgb[i * N + j] = a;
-      Sgb[j * N + i] = a;
-    }
-    joint_bar(c, acc, L0, K0, Fb, Sgb, Lb, Kb);
+    LQGK_UNROLL for (int e = 0; e < Y * B; ++e) out(C::FAa + e, faa[e]);
+    LQGK_UNROLL for (int e = 0; e < Y * U; ++e) out(C::Dm + e, dm[e]);
   }
 };
 

@@ -123,6 +123,69 @@ __global__ void __launch_bounds__(32) k_kf_fwd(const double* cst, size_t Sc, siz
   kf_fwd_body<DM>(GCst{cst + s, Sc, tstride}, WView{sm + lane, 32}, Tn, WView{K + s, Sc}, save_P != 0, WView{Pkf + s, Sc});
 }
 
+// ------------------------------------------------------------------------------------------- step-input ring
+// The sequential per-sample kernels are latency-bound if each step's inputs are fetched with ordinary loads (one
+// HBM round trip per dependent phase, ~1 warp per scheduler).  Instead each warp keeps a ring of NST "step input"
+// stages in shared memory that the TMA engine fills ahead of time: for a warp's 32 consecutive samples, row e of
+// step t of a sample-minor array is one contiguous 256-byte line, copied with one cp.async.bulk issued by lane
+// (e mod 32); an optional float source copies one [CNTF]-float row per sample (lane = sample) from the
+// sample-major sums array.  The stage layout is [row][32 lanes] doubles (lane-strided, bank-conflict free).
+struct RingSrc {
+  const double* base;   // array base + first sample of the warp
+  int rows;             // rows (elements) per time step
+};
+template <int NSRC, int NST>
+struct StepRing {
+  RingSrc src[NSRC];
+  size_t Sc;
+  const float* fsrc;    // optional: sums + s0 * Tn * SUMP + LO   (nullptr = none)
+  int frow_stride;      // Tn * SUMP (floats between consecutive samples)
+  int fstep_stride;     // SUMP
+  int fcnt;             // floats per row copy (multiple of 4)
+  double* buf;          // [NST][stage_doubles]
+  uint64_t* bars;       // [NST]
+  int lane, total_rows, stage_doubles;
+  uint32_t phase_bits;
+
+  __host__ __device__ __forceinline__ static constexpr int stage_size(int total_rows, int fcnt) { return total_rows * 32 + (32 * fcnt + 1) / 2; }
+  __device__ __forceinline__ void init() {
+    if (lane == 0) {
+      for (int i = 0; i < NST; ++i) mbar_init(&bars[i], 1);
+      fence_mbar_init();
+    }
+    phase_bits = 0;
+    __syncwarp();
+  }
+  // Caller guarantees (by __syncwarp) that no lane still reads stage `st`.
+  __device__ __forceinline__ void issue(int t, int st) {
+    double* dst = buf + (size_t)st * stage_doubles;
+    fence_proxy_async();
+    if (lane == 0) mbar_expect_tx(&bars[st], (uint32_t)(total_rows * 256 + (fsrc ? 32 * fcnt * 4 : 0)));
+    int row = 0;
+    LQGK_UNROLL for (int i = 0; i < NSRC; ++i) {
+      for (int r = lane; r < src[i].rows; r += 32)
+        bulk_g2s(dst + (size_t)(row + r) * 32, src[i].base + ((size_t)t * src[i].rows + r) * Sc, 256, &bars[st]);
+      row += src[i].rows;
+    }
+    if (fsrc) {
+      float* fdst = reinterpret_cast<float*>(dst + (size_t)total_rows * 32);
+      bulk_g2s(fdst + lane * fcnt, fsrc + (size_t)lane * frow_stride + (size_t)t * fstep_stride, (uint32_t)fcnt * 4, &bars[st]);
+    }
+  }
+  __device__ __forceinline__ const double* wait(int st) {
+    mbar_wait(&bars[st], (phase_bits >> st) & 1u);
+    phase_bits ^= (1u << st);
+    return buf + (size_t)st * stage_doubles;
+  }
+  // view of source-row offset `row_off` for this lane
+  __device__ __forceinline__ WView view(const double* stage, int row_off) const {
+    return WView{const_cast<double*>(stage) + (size_t)row_off * 32 + lane, 32};
+  }
+  __device__ __forceinline__ const float* frow(const double* stage) const {
+    return reinterpret_cast<const float*>(stage + (size_t)total_rows * 32) + lane * fcnt;
+  }
+};
+
 // Record sink: each lane writes its sample's record into a padded shared-memory row, then the warp copies the 32
 // rows to HBM ([sample][t][REC], 128-byte coalesced stores).
 template <class DM>
@@ -142,75 +205,308 @@ struct SmemRecSink {
   }
 };
 
+constexpr int SEQ_NST = 3;   // ring depth of the sequential kernels
+
+// Covariance pass (forward).  Ring inputs per step: L_t, K_t.
 template <class DM>
 __global__ void __launch_bounds__(32) k_cov_fwd(const double* cst, size_t Sc, size_t tstride, int Tn, const double* L,
-                                                const double* K, int save_C, double* Cs, float* rec) {
-  extern __shared__ __align__(16) double sm[];
+                                                const double* K, int save_adj, double* Cs, double* FU, double* JS, double* J0,
+                                                float* rec) {
+  extern __shared__ __align__(128) double sm[];
+  constexpr int B = DM::B, U = DM::U, Y = DM::Y, R = DM::R, D = DM::D;
+  using C = CovC<DM>;
+  using SR = CovSeqRev<DM>;
+  using Ring = StepRing<2, SEQ_NST>;
   const int lane = threadIdx.x;
   const size_t s0 = (size_t)blockIdx.x * 32, s = s0 + lane;
-  float* stage = reinterpret_cast<float*>(sm + CovC<DM>::n * 32);
+  constexpr int ROWS = DM::EL + DM::EK;
+  double* ring_buf = sm;
+  double* lcp = ring_buf + (size_t)SEQ_NST * ROWS * 32;
+  float* stage = reinterpret_cast<float*>(lcp + C::n * 32);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage + 32 * SmemRecSink<DM>::RS + (32 * SmemRecSink<DM>::RS & 1));
   for (int i = lane; i < 32 * SmemRecSink<DM>::RS; i += 32) stage[i] = 0.f;
-  __syncwarp();
+  Ring ring{{{L + s0, DM::EL}, {K + s0, DM::EK}}, Sc, nullptr, 0, 0, 0, ring_buf, bars, lane, ROWS, ROWS * 32, 0};
+  ring.init();
+  for (int k = 0; k < SEQ_NST && k < Tn; ++k) ring.issue(k, k);
+  WView lc{lcp + lane, 32};
+  GCst g{cst + s, Sc, tstride};
+  load_consts<C>(g.at(0), lc, C::NSEG);
   SmemRecSink<DM> sink{stage, rec + s0 * Tn * DM::REC, lane, Tn};
-  cov_fwd_body<DM>(GCst{cst + s, Sc, tstride}, WView{sm + lane, 32}, Tn, WView{const_cast<double*>(L) + s, Sc},
-                   WView{const_cast<double*>(K) + s, Sc}, save_C != 0, WView{Cs + s, Sc}, sink);
-}
-
-template <class DM>
-struct SmemSumSrc {
-  static constexpr int RS = DM::SUMP + 1;
-  float* stage;
-  const float* gbase;   // sums + (first sample of this warp) * Tn * SUMP
-  int lane, Tn;
-  __device__ __forceinline__ void fetch(int t) {
-    __syncwarp();
-    for (int j = 0; j < 32; ++j) {
-      const float* src = gbase + ((size_t)j * Tn + t) * DM::SUMP;
-      for (int i = lane; i < DM::SUMP; i += 32) stage[j * RS + i] = src[i];
+  double Cm[R * R];
+  {
+    double K0[B * Y], J0v[R * D];
+    LQGK_UNROLL for (int i = 0; i < B * Y; ++i) K0[i] = K[(size_t)i * Sc + s];
+    CovFwd<DM>::init(lc, K0, Cm, J0v);
+    if (save_adj) { LQGK_UNROLL for (int i = 0; i < R * D; ++i) J0[(size_t)i * Sc + s] = J0v[i]; }
+  }
+  for (int t = 0; t < Tn; ++t) {
+    const int st = t % SEQ_NST;
+    const double* stg = ring.wait(st);
+    if (tstride && t != 0) load_consts<C>(g.at(t), lc, C::NSEG);
+    double Lt[U * B], Kt[B * Y];
+    {
+      WView lv = ring.view(stg, 0), kv = ring.view(stg, DM::EL);
+      LQGK_UNROLL for (int i = 0; i < U * B; ++i) Lt[i] = lv(i);
+      LQGK_UNROLL for (int i = 0; i < B * Y; ++i) Kt[i] = kv(i);
     }
     __syncwarp();
+    if (t + SEQ_NST < Tn) ring.issue(t + SEQ_NST, st);
+    if (save_adj) store_sym<R>(WView{Cs + s, Sc}, (size_t)t * DM::EC, Cm);
+    CovFwd<DM>::step(lc, Lt, Kt, Cm, [&](int idx, float v) { sink.put(idx, v); },
+                     [&](int which, int e, double v) {
+                       if (save_adj) {
+                         if (which == 0) FU[((size_t)t * SR::NSF + e) * Sc + s] = v;
+                         else JS[((size_t)t * SR::NJS + e) * Sc + s] = v;
+                       }
+                     });
+    sink.commit(t);
   }
-  __device__ __forceinline__ float get(int idx) const { return stage[lane * RS + idx]; }
-};
-
-template <class DM>
-__global__ void __launch_bounds__(32) k_cov_rev(const double* cst, size_t Sc, int Tn, int N, const float* w, const double* L,
-                                                const double* K, const double* Cs, const float* sums, double* Lbar,
-                                                double* Kbar, double* acc) {
-  extern __shared__ __align__(16) double sm[];
-  const int lane = threadIdx.x;
-  const size_t s0 = (size_t)blockIdx.x * 32, s = s0 + lane;
-  double* la = sm + CovC<DM>::n * 32;
-  float* stage = reinterpret_cast<float*>(la + CovC<DM>::n * 32);
-  double sw = 0.0;
-  for (int i = 0; i < N; ++i) sw += (double)w[s * N + i];
-  SmemSumSrc<DM> src{stage, sums + s0 * Tn * DM::SUMP, lane, Tn};
-  auto cv = [&](const double* p) { return WView{const_cast<double*>(p) + s, Sc}; };
-  cov_rev_body<DM>(GCst{cst + s, Sc, 0}, WView{sm + lane, 32}, WView{la + lane, 32}, Tn, sw, cv(L), cv(K), cv(Cs), src,
-                   cv(Lbar), cv(Kbar), cv(acc));
 }
 
+// Sequential covariance adjoint: lean (no constants, no accumulators); emits Sgb_t, SF_t for the parallel contraction.
+// Ring inputs per step: Fu_t, (J_t, S'^-1_t) and the [SUM_J, SUMP) tail of the trial sums.
+template <class DM>
+__global__ void __launch_bounds__(32) k_cov_seq_rev(size_t Sc, int Tn, int N, const float* w, const double* FU, const double* JS,
+                                                    const double* J0, const float* sums, double* SGB, double* SGBI, double* SFW) {
+  extern __shared__ __align__(128) double sm[];
+  using SR = CovSeqRev<DM>;
+  using Ring = StepRing<2, SEQ_NST>;
+  constexpr int R = DM::R;
+  constexpr int ROWS = SR::NSF + SR::NJS, FCNT = DM::SUMP - DM::SUM_J;
+  constexpr int STAGE = Ring::stage_size(ROWS, FCNT);
+  const int lane = threadIdx.x;
+  const size_t s0 = (size_t)blockIdx.x * 32, s = s0 + lane;
+  double* scp = sm + (size_t)SEQ_NST * STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(scp + SR::SC_N * 32);
+  Ring ring{{{FU + s0, SR::NSF}, {JS + s0, SR::NJS}}, Sc, sums + s0 * Tn * DM::SUMP + DM::SUM_J, Tn * DM::SUMP, DM::SUMP, FCNT,
+            sm, bars, lane, ROWS, STAGE, 0};
+  ring.init();
+  for (int k = 0; k < SEQ_NST && k < Tn; ++k) ring.issue(Tn - 1 - k, k);
+  double sw = 0.0;
+  for (int i = 0; i < N; ++i) sw += (double)w[s * N + i];
+  WView sc{scp + lane, 32};
+  double Cb[R * R];
+  LQGK_UNROLL for (int i = 0; i < R * R; ++i) Cb[i] = 0.0;
+  for (int kk = 0; kk < Tn; ++kk) {
+    const int t = Tn - 1 - kk, st = kk % SEQ_NST;
+    const double* stg = ring.wait(st);
+    WView fuv = ring.view(stg, 0), jsv = ring.view(stg, SR::NSF);
+    const float* fr = ring.frow(stg);
+    SR::step([&](int e) { return fuv(e); }, [&](int e) { return jsv(e); }, [&](int idx) { return fr[idx - DM::SUM_J]; }, sw, sc, Cb,
+             [&](int e, double v) { SGB[((size_t)t * SR::NSGB + e) * Sc + s] = v; },
+             [&](int e, double v) { SFW[((size_t)t * SR::NSF + e) * Sc + s] = v; });
+    __syncwarp();
+    if (kk + SEQ_NST < Tn) ring.issue(Tn - 1 - (kk + SEQ_NST), st);
+  }
+  SR::init([&](int e) { return J0[(size_t)e * Sc + s]; }, Cb, [&](int e, double v) { SGBI[(size_t)e * Sc + s] = v; });
+}
+
+// Time-parallel contraction.  grid = (Sc / 32, chunks), block = one warp owning a contiguous range of time steps of
+// its 32 samples.  Ring inputs per step: L_t, K_t, C_t, (Sgb_t,) SF_t and the trial sums F-block.
+constexpr int PAR_NST = 2;
+template <class DM, int PASS>
+__global__ void __launch_bounds__(32) k_cov_contrib(const double* cst, size_t Sc, int Tn, const double* L, const double* K,
+                                                    const double* Cs, const double* SGB, const double* SGBI, const double* SFW,
+                                                    const float* sums, double* CT, double* Lbar, double* Kbar) {
+  extern __shared__ __align__(128) double sm[];
+  constexpr int B = DM::B, U = DM::U, Y = DM::Y, R = DM::R;
+  using SR = CovSeqRev<DM>;
+  using CC = CovContrib<DM>;
+  using C = CovC<DM>;
+  constexpr int NSRC = PASS == 0 ? 5 : 4;
+  using Ring = StepRing<NSRC, PAR_NST>;
+  constexpr int ROWS = DM::EL + DM::EK + DM::EC + SR::NSF + (PASS == 0 ? SR::NSGB : 0);
+  constexpr int FCNT = DM::SUM_J;   // = round4(N*N)
+  constexpr int STAGE = Ring::stage_size(ROWS, FCNT);
+  constexpr int NC = C::n;
+  const int lane = threadIdx.x;
+  const size_t s0 = (size_t)blockIdx.x * 32, s = s0 + lane;
+  double* lcp = sm + (size_t)PAR_NST * STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(lcp + C::n * 32);
+  const int nq = gridDim.y, q = blockIdx.y;
+  const int per = (Tn + nq - 1) / nq;
+  const int t0 = min(Tn, q * per), t1 = min(Tn, t0 + per);
+  if (t0 >= t1) return;
+  Ring ring;
+  ring.src[0] = {L + s0, DM::EL};
+  ring.src[1] = {K + s0, DM::EK};
+  ring.src[2] = {Cs + s0, DM::EC};
+  ring.src[3] = {SFW + s0, SR::NSF};
+  if constexpr (PASS == 0) ring.src[4] = {SGB + s0, SR::NSGB};
+  ring.Sc = Sc; ring.fsrc = sums + s0 * Tn * DM::SUMP; ring.frow_stride = Tn * DM::SUMP; ring.fstep_stride = DM::SUMP;
+  ring.fcnt = FCNT; ring.buf = sm; ring.bars = bars; ring.lane = lane; ring.total_rows = ROWS; ring.stage_doubles = STAGE;
+  ring.init();
+  for (int k = 0; k < PAR_NST && t0 + k < t1; ++k) ring.issue(t0 + k, k);
+  WView lc{lcp + lane, 32};
+  load_consts<C>(WView{const_cast<double*>(cst) + s, Sc}, lc, C::NSEG);
+  for (int t = t0; t < t1; ++t) {
+    const int st = (t - t0) % PAR_NST;
+    const double* stg = ring.wait(st);
+    WView lv = ring.view(stg, 0), kv = ring.view(stg, DM::EL), cvw = ring.view(stg, DM::EL + DM::EK),
+          sfv = ring.view(stg, DM::EL + DM::EK + DM::EC), sgv = ring.view(stg, DM::EL + DM::EK + DM::EC + SR::NSF);
+    const float* fr = ring.frow(stg);
+    double Cm[R * R], Lt[U * B], Kt[B * Y];
+    LQGK_UNROLL for (int i = 0; i < U * B; ++i) Lt[i] = lv(i);
+    LQGK_UNROLL for (int i = 0; i < B * Y; ++i) Kt[i] = kv(i);
+    load_sym_ws<R>(cvw, 0, Cm);
+    auto sf = [&](int e) { return sfv(e); };
+    auto get = [&](int idx) { return fr[idx]; };
+    auto out = [&](int e, double v) { CT[((size_t)t * NC + e) * Sc + s] = v; };
+    if constexpr (PASS == 0) {
+      double Lb[U * B], Kb[B * Y];
+      CC::pass0(lc, [&](int e) { return sgv(e); }, t == 0, [&](int e) { return SGBI[(size_t)e * Sc + s]; }, sf, get, Cm, Lt, Kt, out,
+                Lb, Kb);
+      LQGK_UNROLL for (int i = 0; i < U * B; ++i) Lbar[((size_t)t * DM::EL + i) * Sc + s] = Lb[i];
+      LQGK_UNROLL for (int i = 0; i < B * Y; ++i) Kbar[((size_t)t * DM::EK + i) * Sc + s] = Kb[i];
+    } else {
+      double Kb[B * Y];
+      LQGK_UNROLL for (int i = 0; i < B * Y; ++i) Kb[i] = Kbar[((size_t)t * DM::EK + i) * Sc + s];
+      CC::pass1(lc, sf, get, Cm, Lt, Kt, out, Kb);
+      LQGK_UNROLL for (int i = 0; i < B * Y; ++i) Kbar[((size_t)t * DM::EK + i) * Sc + s] = Kb[i];
+    }
+    __syncwarp();
+    if (t + PAR_NST < t1) ring.issue(t + PAR_NST, st);
+  }
+}
+
+// Sum the per-step contributions over time into the (global-layout) cotangent accumulators:
+// acc[gmap(e)][s] += sum_t CT[t][e][s].  grid = (ceil(Sc / 128), NC), block = 128.
+template <class KC>
+__global__ void __launch_bounds__(128) k_reduce_time(const double* CT, size_t Sc, int Tn, double* acc) {
+  const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = blockIdx.y;
+  if (s >= Sc) return;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  const size_t stride = (size_t)KC::n * Sc;
+  const double* p = CT + (size_t)e * Sc + s;
+  int t = 0;
+  for (; t + 4 <= Tn; t += 4) {
+    a0 += p[(size_t)t * stride];
+    a1 += p[(size_t)(t + 1) * stride];
+    a2 += p[(size_t)(t + 2) * stride];
+    a3 += p[(size_t)(t + 3) * stride];
+  }
+  for (; t < Tn; ++t) a0 += p[(size_t)t * stride];
+  int ge = -1;
+  for (int i = 0; i < KC::NSEG; ++i) {
+    int go, lo, len;
+    KC::seg(i, go, lo, len);
+    if (e >= lo && e < lo + len) ge = go + (e - lo);
+  }
+  acc[(size_t)ge * Sc + s] += (a0 + a1) + (a2 + a3);
+}
+
+// Kalman-gain adjoint (sequential, t descending).  Ring inputs per step: P_t, Kbar_t.
 template <class DM>
 __global__ void __launch_bounds__(32) k_kf_rev(const double* cst, size_t Sc, int Tn, const double* Pkf, const double* Kbar,
                                                double* acc) {
-  extern __shared__ __align__(16) double sm[];
+  extern __shared__ __align__(128) double sm[];
+  constexpr int B = DM::B, Y = DM::Y;
+  using C = KfC<DM>;
+  using Ring = StepRing<2, SEQ_NST>;
+  constexpr int ROWS = DM::EP + DM::EK;
   const int lane = threadIdx.x;
-  const size_t s = (size_t)blockIdx.x * 32 + lane;
-  double* la = sm + KfC<DM>::n * 32;
-  auto cv = [&](const double* p) { return WView{const_cast<double*>(p) + s, Sc}; };
-  kf_rev_body<DM>(GCst{cst + s, Sc, 0}, WView{sm + lane, 32}, WView{la + lane, 32}, Tn, cv(Pkf), cv(Kbar), cv(acc));
+  const size_t s0 = (size_t)blockIdx.x * 32, s = s0 + lane;
+  double* lcp = sm + (size_t)SEQ_NST * ROWS * 32;
+  double* lap = lcp + C::n * 32;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(lap + C::n * 32);
+  Ring ring{{{Pkf + s0, DM::EP}, {Kbar + s0, DM::EK}}, Sc, nullptr, 0, 0, 0, sm, bars, lane, ROWS, ROWS * 32, 0};
+  ring.init();
+  for (int k = 0; k < SEQ_NST && k < Tn; ++k) ring.issue(Tn - 1 - k, k);
+  WView lc{lcp + lane, 32}, la{lap + lane, 32};
+  load_consts<C>(WView{const_cast<double*>(cst) + s, Sc}, lc, C::NSEG);
+  for (int e = 0; e < C::n; ++e) la(e) = 0.0;
+  auto accf = [&](int e) -> double& { return la(e); };
+  double Pnb[B * B];
+  LQGK_UNROLL for (int i = 0; i < B * B; ++i) Pnb[i] = 0.0;
+  for (int kk = 0; kk < Tn; ++kk) {
+    const int st = kk % SEQ_NST;
+    const double* stg = ring.wait(st);
+    double P[B * B], Kb[B * Y];
+    load_sym_ws<B>(ring.view(stg, 0), 0, P);
+    {
+      WView kv = ring.view(stg, DM::EP);
+      LQGK_UNROLL for (int i = 0; i < B * Y; ++i) Kb[i] = kv(i);
+    }
+    __syncwarp();
+    if (kk + SEQ_NST < Tn) ring.issue(Tn - 1 - (kk + SEQ_NST), st);
+    KfRev<DM>::step(lc, accf, P, Kb, Pnb);
+  }
+  KfRev<DM>::finish(accf, Pnb);
+  flush_acc<C>(WView{acc + s, Sc}, la, C::NSEG);
 }
 
+// Riccati adjoint (sequential, t ascending).  Ring inputs per step: S_{t+1}, L_t, Lbar_t.
 template <class DM>
 __global__ void __launch_bounds__(32) k_lqr_rev(const double* cst, size_t Sc, int Tn, double eps, const double* L,
                                                 const double* Sric, const double* Lbar, double* acc) {
-  extern __shared__ __align__(16) double sm[];
+  extern __shared__ __align__(128) double sm[];
+  constexpr int B = DM::B, U = DM::U;
+  using C = LqrC<DM>;
+  using Ring = StepRing<3, SEQ_NST>;
+  constexpr int ROWS = DM::ES + 2 * DM::EL;
   const int lane = threadIdx.x;
-  const size_t s = (size_t)blockIdx.x * 32 + lane;
-  double* la = sm + LqrC<DM>::n * 32;
-  auto cv = [&](const double* p) { return WView{const_cast<double*>(p) + s, Sc}; };
-  lqr_rev_body<DM>(GCst{cst + s, Sc, 0}, WView{sm + lane, 32}, WView{la + lane, 32}, Tn, eps, cv(L), cv(Sric), cv(Lbar),
-                   cv(acc));
+  const size_t s0 = (size_t)blockIdx.x * 32, s = s0 + lane;
+  double* lcp = sm + (size_t)SEQ_NST * ROWS * 32;
+  double* lap = lcp + C::n * 32;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(lap + C::n * 32);
+  Ring ring{{{Sric + s0, DM::ES}, {L + s0, DM::EL}, {Lbar + s0, DM::EL}}, Sc, nullptr, 0, 0, 0, sm, bars, lane, ROWS, ROWS * 32, 0};
+  ring.init();
+  for (int k = 0; k < SEQ_NST && k < Tn; ++k) ring.issue(k, k);
+  WView lc{lcp + lane, 32}, la{lap + lane, 32};
+  load_consts<C>(WView{const_cast<double*>(cst) + s, Sc}, lc, C::NSEG);
+  for (int e = 0; e < C::n; ++e) la(e) = 0.0;
+  auto accf = [&](int e) -> double& { return la(e); };
+  double Sn[B * B];
+  LQGK_UNROLL for (int i = 0; i < B * B; ++i) Sn[i] = 0.0;
+  for (int t = 0; t < Tn; ++t) {
+    const int st = t % SEQ_NST;
+    const double* stg = ring.wait(st);
+    double S[B * B], Lt[U * B], Lb[U * B];
+    load_sym_ws<B>(ring.view(stg, 0), 0, S);
+    {
+      WView lv = ring.view(stg, DM::ES), bv = ring.view(stg, DM::ES + DM::EL);
+      LQGK_UNROLL for (int i = 0; i < U * B; ++i) { Lt[i] = lv(i); Lb[i] = bv(i); }
+    }
+    __syncwarp();
+    if (t + SEQ_NST < Tn) ring.issue(t + SEQ_NST, st);
+    double shift;
+    {
+      double Bm[B * U], SB[B * U], H[U * U];
+      load_mat<B, U>(lc, C::Ba, Bm);
+      mm<B, B, U>(S, Bm, SB);
+      load_sym<U>(lc, C::R, H);
+      mm_tn_sym<U, B, true>(Bm, SB, H);
+      shift = eps - lambda_min<U>(H);
+      shift = shift > 0.0 ? shift : 0.0;
+    }
+    LqrRev<DM>::step(lc, accf, S, Lt, Lb, shift, Sn);
+  }
+  LqrRev<DM>::finish(accf, Sn);
+  flush_acc<C>(WView{acc + s, Sc}, la, C::NSEG);
+}
+
+// Dynamic shared-memory sizes of the per-sample kernels (must mirror the carve-up inside each kernel).
+template <class DM> constexpr size_t smem_cov_fwd() {
+  return sizeof(double) * ((size_t)SEQ_NST * (DM::EL + DM::EK) * 32 + CovC<DM>::n * 32) +
+         sizeof(float) * (32 * SmemRecSink<DM>::RS + 2) + sizeof(uint64_t) * SEQ_NST;
+}
+template <class DM> constexpr size_t smem_cov_seq_rev() {
+  using SR = CovSeqRev<DM>;
+  return sizeof(double) * ((size_t)SEQ_NST * StepRing<2, SEQ_NST>::stage_size(SR::NSF + SR::NJS, DM::SUMP - DM::SUM_J) + SR::SC_N * 32) +
+         sizeof(uint64_t) * SEQ_NST;
+}
+template <class DM, int PASS> constexpr size_t smem_cov_contrib() {
+  using SR = CovSeqRev<DM>;
+  constexpr int ROWS = DM::EL + DM::EK + DM::EC + SR::NSF + (PASS == 0 ? SR::NSGB : 0);
+  return sizeof(double) * ((size_t)PAR_NST * StepRing<5, PAR_NST>::stage_size(ROWS, DM::SUM_J) + CovC<DM>::n * 32) +
+         sizeof(uint64_t) * PAR_NST;
+}
+template <class DM> constexpr size_t smem_kf_rev() {
+  return sizeof(double) * ((size_t)SEQ_NST * (DM::EP + DM::EK) * 32 + 2 * KfC<DM>::n * 32) + sizeof(uint64_t) * SEQ_NST;
+}
+template <class DM> constexpr size_t smem_lqr_rev() {
+  return sizeof(double) * ((size_t)SEQ_NST * (DM::ES + 2 * DM::EL) * 32 + 2 * LqrC<DM>::n * 32) + sizeof(uint64_t) * SEQ_NST;
 }
 
 // =========================================================================================== per-trial kernels
@@ -275,6 +571,27 @@ struct RecRing {
   }
 };
 
+// Largest number of trials one lane carries: small systems leave room for 8 (amortises the broadcast record loads and
+// the cross-lane reductions over more FMAs), large ones for 4.
+template <class DM>
+__host__ __device__ constexpr int trial_rt_max() { return DM::N * DM::N <= 36 ? 8 : 4; }
+
+// Copy one step's record from the shared-memory ring into registers (small systems) with 128-bit broadcast loads.
+template <class DM>
+struct RecRegs {
+  float v[DM::REC];
+  __device__ __forceinline__ void load(const float* r) {
+    const float4* r4 = reinterpret_cast<const float4*>(r);
+    LQGK_UNROLL for (int k = 0; k < DM::REC / 4; ++k) {
+      float4 q = r4[k];
+      v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+    }
+  }
+  __device__ __forceinline__ float operator[](int i) const { return v[i]; }
+};
+template <class DM>
+__host__ __device__ constexpr bool rec_in_regs() { return DM::REC <= 48; }
+
 // Forward: per-trial mean recursion + log-density.  grid = (ceil(n_samples / TRIAL_WARPS)), block = 32 * TRIAL_WARPS.
 // Trials are processed in passes of 32*RT (lane owns trials base + lane + 32*j, j < RT).
 template <class DM, int RT>
@@ -300,33 +617,46 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_fwd(const float* __r
       ok[j] = i < N;
       tr[j] = ok[j] ? i : N - 1;
     }
-    float c[RT][R], x0[RT][D], x1[RT][D];
+    float c[RT][R], x0[RT][D], x1[RT][D], x2[RT][D];
     double ll[RT];
     LQGK_UNROLL for (int j = 0; j < RT; ++j) {
       ll[j] = 0.0;
       LQGK_UNROLL for (int k = 0; k < R; ++k) c[j][k] = 0.f;
       load_obs<D>(x_tm + (size_t)tr[j] * D, x0[j]);
+      load_obs<D>(x_tm + ((size_t)N + tr[j]) * D, x1[j]);
     }
     for (int k = 0; k < TRIAL_NST && k < nchunk; ++k) ring.issue(k, k);
     for (int k = 0; k < nchunk; ++k) {
       const int st = k % TRIAL_NST;
       const float* chunk = ring.wait(st);
       const int t0 = k * TRIAL_TB, nst = min(TRIAL_TB, Tn - t0);
+      float part[RT];
+      LQGK_UNROLL for (int j = 0; j < RT; ++j) part[j] = 0.f;
       for (int q = 0; q < nst; ++q) {
         const int t = t0 + q;
         const float* r = chunk + q * DM::REC;
-        LQGK_UNROLL for (int j = 0; j < RT; ++j) load_obs<D>(x_tm + ((size_t)(t + 1) * N + tr[j]) * D, x1[j]);
+        const int tn = min(t + 2, Tn);                      // prefetch the observation two steps ahead
+        LQGK_UNROLL for (int j = 0; j < RT; ++j) load_obs<D>(x_tm + ((size_t)tn * N + tr[j]) * D, x2[j]);
         if (hist != nullptr) {
           LQGK_UNROLL for (int j = 0; j < RT; ++j)
             if (ok[j]) {
               LQGK_UNROLL for (int m = 0; m < R; ++m) hist[(((size_t)s * Tn + t) * R + m) * N + tr[j]] = c[j][m];
             }
         }
-        LQGK_UNROLL for (int j = 0; j < RT; ++j) {
-          ll[j] += (double)Trial<DM>::fwd(r, x0[j], x1[j], c[j]);
-          LQGK_UNROLL for (int m = 0; m < D; ++m) x0[j][m] = x1[j][m];
+        if constexpr (rec_in_regs<DM>()) {
+          RecRegs<DM> rr;
+          rr.load(r);
+          LQGK_UNROLL for (int j = 0; j < RT; ++j) part[j] += Trial<DM>::fwd(rr, x0[j], x1[j], c[j]);
+        } else {
+          LQGK_UNROLL for (int j = 0; j < RT; ++j) part[j] += Trial<DM>::fwd(r, x0[j], x1[j], c[j]);
+        }
+        LQGK_UNROLL for (int j = 0; j < RT; ++j) LQGK_UNROLL for (int m = 0; m < D; ++m) {
+          x0[j][m] = x1[j][m];
+          x1[j][m] = x2[j][m];
         }
       }
+      // FP32 partial sum over <= TRIAL_TB steps, FP64 across chunks (log-likelihood error ~1e-7 relative)
+      LQGK_UNROLL for (int j = 0; j < RT; ++j) ll[j] += (double)part[j];
       __syncwarp();
       if (k + TRIAL_NST < nchunk) ring.issue(k + TRIAL_NST, st);
     }
@@ -335,18 +665,25 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_fwd(const float* __r
   }
 }
 
-// Transposing butterfly: every lane holds 32 partial values; afterwards lane L holds the warp-wide total of value L.
-__device__ __forceinline__ float warp_transpose_reduce(float (&val)[32], int lane) {
-  LQGK_UNROLL for (int h = 16; h >= 1; h >>= 1) {
-    const bool up = (lane & h) != 0;
+// Transposing butterfly over V = 2^k <= 32 values: every lane holds V partial values; afterwards the lanes whose top
+// log2(V) lane-index bits equal i hold the warp-wide total of value i (V == 32: lane L holds value L).
+template <int V>
+__device__ __forceinline__ float warp_transpose_reduce(float (&val)[V], int lane) {
+  int bit = 16;
+  LQGK_UNROLL for (int h = V / 2; h >= 1; h >>= 1) {
+    const bool up = (lane & bit) != 0;
     LQGK_UNROLL for (int j = 0; j < h; ++j) {
       float send = up ? val[j] : val[j + h];
       float keep = up ? val[j + h] : val[j];
-      val[j] = keep + __shfl_xor_sync(FULL, send, h);
+      val[j] = keep + __shfl_xor_sync(FULL, send, bit);
     }
+    bit >>= 1;
   }
-  return val[0];
+  float tot = val[0];
+  LQGK_UNROLL for (int m = 16 / V; m >= 1; m >>= 1) tot += __shfl_xor_sync(FULL, tot, m);
+  return tot;
 }
+__host__ __device__ constexpr int pow2_ceil(int v) { return v <= 1 ? 1 : (v <= 2 ? 2 : (v <= 4 ? 4 : (v <= 8 ? 8 : (v <= 16 ? 16 : 32)))); }
 
 // Reverse: per-trial adjoint, t = T-1..0, plus the per-step sums over trials (DM::SUM_* layout) written to
 // sums[s][t][SUMP].  Passes over trial blocks accumulate (+=) into the sums.
@@ -355,7 +692,7 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __r
                                                                 const float* __restrict__ hist, const float* __restrict__ w,
                                                                 int n_samples, int N, int Tn, float* __restrict__ sums) {
   constexpr int D = DM::D, R = DM::R;
-  constexpr int NG = (DM::NSUM + 31) / 32;
+  constexpr int NFULL = DM::NSUM / 32, REM = DM::NSUM % 32, VREM = pow2_ceil(REM);
   extern __shared__ __align__(128) unsigned char smraw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = blockIdx.x * TRIAL_WARPS + warp;
@@ -375,10 +712,12 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __r
       tr[j] = ok ? i : N - 1;
       wt[j] = ok ? w[(size_t)s * N + tr[j]] : 0.f;   // masked trials contribute nothing (cb stays 0, w = 0)
     }
-    float cb[RT][R], x1[RT][D];
+    float cb[RT][R], x1[RT][D], x0[RT][D], c[RT][R];
     LQGK_UNROLL for (int j = 0; j < RT; ++j) {
       LQGK_UNROLL for (int k = 0; k < R; ++k) cb[j][k] = 0.f;
       load_obs<D>(x_tm + ((size_t)Tn * N + tr[j]) * D, x1[j]);
+      load_obs<D>(x_tm + ((size_t)(Tn - 1) * N + tr[j]) * D, x0[j]);
+      LQGK_UNROLL for (int m = 0; m < R; ++m) c[j][m] = __ldg(&hist[(((size_t)s * Tn + (Tn - 1)) * R + m) * N + tr[j]]);
     }
     for (int k = 0; k < TRIAL_NST && k < nchunk; ++k) ring.issue(nchunk - 1 - k, k);
     for (int kk = 0; kk < nchunk; ++kk) {
@@ -389,14 +728,21 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __r
       for (int q = nst - 1; q >= 0; --q) {
         const int t = t0 + q;
         const float* r = chunk + q * DM::REC;
-        float c[RT][R], x0[RT][D], e[RT][D], v[RT][D], eb[RT][D], cbn[RT][R];
+        float e[RT][D], v[RT][D], eb[RT][D], cbn[RT][R], xp[RT][D], cp[RT][R];
+        const int tp = max(t - 1, 0);                        // prefetch the previous step's observation and state
         LQGK_UNROLL for (int j = 0; j < RT; ++j) {
-          load_obs<D>(x_tm + ((size_t)t * N + tr[j]) * D, x0[j]);
-          LQGK_UNROLL for (int m = 0; m < R; ++m) c[j][m] = __ldg(&hist[(((size_t)s * Tn + t) * R + m) * N + tr[j]]);
+          load_obs<D>(x_tm + ((size_t)tp * N + tr[j]) * D, xp[j]);
+          LQGK_UNROLL for (int m = 0; m < R; ++m) cp[j][m] = __ldg(&hist[(((size_t)s * Tn + tp) * R + m) * N + tr[j]]);
         }
-        LQGK_UNROLL for (int j = 0; j < RT; ++j) Trial<DM>::rev(r, x0[j], x1[j], c[j], wt[j], cb[j], e[j], v[j], eb[j], cbn[j]);
+        if constexpr (rec_in_regs<DM>()) {
+          RecRegs<DM> rr;
+          rr.load(r);
+          LQGK_UNROLL for (int j = 0; j < RT; ++j) Trial<DM>::rev(rr, x0[j], x1[j], c[j], wt[j], cb[j], e[j], v[j], eb[j], cbn[j]);
+        } else {
+          LQGK_UNROLL for (int j = 0; j < RT; ++j) Trial<DM>::rev(r, x0[j], x1[j], c[j], wt[j], cb[j], e[j], v[j], eb[j], cbn[j]);
+        }
         float* out = sums + ((size_t)s * Tn + t) * DM::SUMP;
-        static_for<0, NG>([&](auto G) {
+        static_for<0, NFULL>([&](auto G) {
           float val[32];
           static_for<0, 32>([&](auto J) {
             constexpr int IDX = decltype(G)::value * 32 + decltype(J)::value;
@@ -405,16 +751,31 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __r
               a += Trial<DM>::template sum_term<IDX>(cb[j], eb[j], x0[j], c[j], e[j], v[j], wt[j]);
             val[decltype(J)::value] = a;
           });
-          float tot = warp_transpose_reduce(val, lane);
+          float tot = warp_transpose_reduce<32>(val, lane);
           const int idx = decltype(G)::value * 32 + lane;
-          if (idx < DM::SUMP) {
+          if (base == 0) out[idx] = tot;
+          else out[idx] += tot;
+        });
+        if constexpr (REM > 0) {
+          float val[VREM];
+          static_for<0, VREM>([&](auto J) {
+            constexpr int IDX = NFULL * 32 + decltype(J)::value;
+            float a = 0.f;
+            LQGK_UNROLL for (int j = 0; j < RT; ++j)
+              a += Trial<DM>::template sum_term<IDX>(cb[j], eb[j], x0[j], c[j], e[j], v[j], wt[j]);
+            val[decltype(J)::value] = a;
+          });
+          float tot = warp_transpose_reduce<VREM>(val, lane);
+          const int vi = lane / (32 / VREM);
+          const int idx = NFULL * 32 + vi;
+          if ((lane % (32 / VREM)) == 0 && idx < DM::SUMP) {
             if (base == 0) out[idx] = tot;
             else out[idx] += tot;
           }
-        });
+        }
         LQGK_UNROLL for (int j = 0; j < RT; ++j) {
-          LQGK_UNROLL for (int m = 0; m < R; ++m) cb[j][m] = cbn[j][m];
-          LQGK_UNROLL for (int m = 0; m < D; ++m) x1[j][m] = x0[j][m];
+          LQGK_UNROLL for (int m = 0; m < R; ++m) { cb[j][m] = cbn[j][m]; c[j][m] = cp[j][m]; }
+          LQGK_UNROLL for (int m = 0; m < D; ++m) { x1[j][m] = x0[j][m]; x0[j][m] = xp[j][m]; }
         }
       }
       __syncwarp();

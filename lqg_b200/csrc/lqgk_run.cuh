@@ -15,7 +15,7 @@ extern thread_local int g_launches;
 
 // Optional per-kernel timing (bench.py): CUDA events recorded on the launching stream around every launch.
 enum ProfKind { PK_PACK = 0, PK_LQR_FWD, PK_KF_FWD, PK_COV_FWD, PK_TRIAL_FWD, PK_MISC, PK_TRIAL_REV, PK_COV_REV, PK_KF_REV,
-                PK_LQR_REV, PK_UNPACK, PK_COUNT };
+                PK_LQR_REV, PK_UNPACK, PK_COV_CONTRIB, PK_REDUCE, PK_COUNT };
 struct Profiler {
   bool on = false;
   std::vector<cudaEvent_t> ev;   // pairs (start, stop)
@@ -67,7 +67,7 @@ inline bool spec_time_varying(const LqgkSpec& s, bool actor) {
 struct Plan {
   size_t Sc = 0, bytes = 0;
   size_t cst = 0, acc = 0, L = 0, K = 0, l = 0, H = 0, Sric = 0, Pkf = 0, Cs = 0, Lbar = 0, Kbar = 0, rec = 0, ll = 0,
-         sums = 0, hist = 0, w = 0;
+         sums = 0, hist = 0, w = 0, FU = 0, JS = 0, J0 = 0, SGB = 0, SGBI = 0, SFW = 0, CT = 0;
 };
 
 template <class DM>
@@ -98,6 +98,14 @@ Plan make_plan(const LqgkDims& d, int mode, bool tv, size_t Sc) {
     p.sums = take(sizeof(float) * Sc * T * DM::SUMP);
     p.hist = take(sizeof(float) * Sc * T * DM::R * N);
     p.w = take(sizeof(float) * Sc * N);
+    using SR = CovSeqRev<DM>;
+    p.FU = take(sizeof(double) * T * SR::NSF * Sc);
+    p.JS = take(sizeof(double) * T * SR::NJS * Sc);
+    p.J0 = take(sizeof(double) * DM::R * DM::D * Sc);
+    p.SGB = take(sizeof(double) * T * SR::NSGB * Sc);
+    p.SGBI = take(sizeof(double) * SR::NSGB * Sc);
+    p.SFW = take(sizeof(double) * T * SR::NSF * Sc);
+    p.CT = take(sizeof(double) * T * CovC<DM>::n * Sc);
   }
   p.bytes = off;
   return p;
@@ -246,17 +254,19 @@ int run(const Call& c) {
       LQGK_LAUNCH_CHECK();
     }
     {
-      size_t smem = sizeof(double) * 32 * CovC<DM>::n + sizeof(float) * 32 * SmemRecSink<DM>::RS;
+      size_t smem = smem_cov_fwd<DM>();
       if ((rc = set_smem<DM>((const void*)k_cov_fwd<DM>, smem))) return rc;
       ProfScope ps_(PK_COV_FWD, st);
-      k_cov_fwd<DM><<<nblk, 32, smem, st>>>(D(p.cst), Sc, tstride, Tn, D(p.L), D(p.K), vjp, vjp ? D(p.Cs) : nullptr, F(p.rec));
+      k_cov_fwd<DM><<<nblk, 32, smem, st>>>(D(p.cst), Sc, tstride, Tn, D(p.L), D(p.K), vjp, vjp ? D(p.Cs) : nullptr, vjp ? D(p.FU) : nullptr,
+                                            vjp ? D(p.JS) : nullptr, vjp ? D(p.J0) : nullptr, F(p.rec));
       LQGK_LAUNCH_CHECK();
     }
-    const int RT = N <= 32 ? 1 : (N <= 64 ? 2 : 4);
+    const int RT = std::min((N + 31) / 32, trial_rt_max<DM>());
     float* hist = vjp ? F(p.hist) : nullptr;
-    if (RT == 1) rc = launch_trial_fwd<DM, 1>(st, F(p.rec), c.x_tm, n, N, Tn, D(p.ll), hist);
-    else if (RT == 2) rc = launch_trial_fwd<DM, 2>(st, F(p.rec), c.x_tm, n, N, Tn, D(p.ll), hist);
-    else rc = launch_trial_fwd<DM, 4>(st, F(p.rec), c.x_tm, n, N, Tn, D(p.ll), hist);
+    rc = LQGK_E_UNSUPPORTED;
+    static_for<1, trial_rt_max<DM>() + 1>([&](auto RTC) {
+      if (RT == decltype(RTC)::value) rc = launch_trial_fwd<DM, decltype(RTC)::value>(st, F(p.rec), c.x_tm, n, N, Tn, D(p.ll), hist);
+    });
     if (rc) return rc;
     {
       size_t total = (size_t)n * N;
@@ -276,9 +286,11 @@ int run(const Call& c) {
         LQGK_LAUNCH_CHECK();
       }
     }
-    if (RT == 1) rc = launch_trial_rev<DM, 1>(st, F(p.rec), c.x_tm, hist, F(p.w), n, N, Tn, F(p.sums));
-    else if (RT == 2) rc = launch_trial_rev<DM, 2>(st, F(p.rec), c.x_tm, hist, F(p.w), n, N, Tn, F(p.sums));
-    else rc = launch_trial_rev<DM, 4>(st, F(p.rec), c.x_tm, hist, F(p.w), n, N, Tn, F(p.sums));
+    rc = LQGK_E_UNSUPPORTED;
+    static_for<1, trial_rt_max<DM>() + 1>([&](auto RTC) {
+      if (RT == decltype(RTC)::value)
+        rc = launch_trial_rev<DM, decltype(RTC)::value>(st, F(p.rec), c.x_tm, hist, F(p.w), n, N, Tn, F(p.sums));
+    });
     if (rc) return rc;
     if (cudaMemsetAsync(D(p.acc), 0, sizeof(double) * cl.total * Sc, st) != cudaSuccess) return LQGK_E_CUDA;
     if (npad > n) {   // sums of padded samples are never written by k_trial_rev: zero them so k_cov_rev reads finite data
@@ -286,21 +298,47 @@ int run(const Call& c) {
         return LQGK_E_CUDA;
     }
     {
-      size_t smem = sizeof(double) * 32 * 2 * CovC<DM>::n + sizeof(float) * 32 * SmemSumSrc<DM>::RS;
-      if ((rc = set_smem<DM>((const void*)k_cov_rev<DM>, smem))) return rc;
+      size_t smem = smem_cov_seq_rev<DM>();
+      if ((rc = set_smem<DM>((const void*)k_cov_seq_rev<DM>, smem))) return rc;
       ProfScope ps_(PK_COV_REV, st);
-      k_cov_rev<DM><<<nblk, 32, smem, st>>>(D(p.cst), Sc, Tn, N, F(p.w), D(p.L), D(p.K), D(p.Cs), F(p.sums), D(p.Lbar), D(p.Kbar), D(p.acc));
+      k_cov_seq_rev<DM><<<nblk, 32, smem, st>>>(Sc, Tn, N, F(p.w), D(p.FU), D(p.JS), D(p.J0), F(p.sums), D(p.SGB), D(p.SGBI), D(p.SFW));
       LQGK_LAUNCH_CHECK();
     }
     {
-      size_t smem = sizeof(double) * 32 * 2 * KfC<DM>::n;
+      size_t smem0 = smem_cov_contrib<DM, 0>(), smem1 = smem_cov_contrib<DM, 1>();
+      if ((rc = set_smem<DM>((const void*)k_cov_contrib<DM, 0>, smem0))) return rc;
+      if ((rc = set_smem<DM>((const void*)k_cov_contrib<DM, 1>, smem1))) return rc;
+      // (sample-group x time-range) warps: enough to occupy every SM a few times over
+      int chunks = std::max(1, std::min((Tn + 7) / 8, (148 * 4 + nblk - 1) / nblk));
+      dim3 grid(nblk, chunks);
+      {
+        ProfScope ps_(PK_COV_CONTRIB, st);
+        k_cov_contrib<DM, 0><<<grid, 32, smem0, st>>>(D(p.cst), Sc, Tn, D(p.L), D(p.K), D(p.Cs), D(p.SGB), D(p.SGBI), D(p.SFW), F(p.sums),
+                                                     D(p.CT), D(p.Lbar), D(p.Kbar));
+        LQGK_LAUNCH_CHECK();
+      }
+      {
+        ProfScope ps_(PK_COV_CONTRIB, st);
+        k_cov_contrib<DM, 1><<<grid, 32, smem1, st>>>(D(p.cst), Sc, Tn, D(p.L), D(p.K), D(p.Cs), D(p.SGB), D(p.SGBI), D(p.SFW), F(p.sums),
+                                                     D(p.CT), D(p.Lbar), D(p.Kbar));
+        LQGK_LAUNCH_CHECK();
+      }
+      {
+        ProfScope ps_(PK_REDUCE, st);
+        dim3 rgrid((unsigned)((Sc + 127) / 128), CovC<DM>::n);
+        k_reduce_time<CovC<DM>><<<rgrid, 128, 0, st>>>(D(p.CT), Sc, Tn, D(p.acc));
+        LQGK_LAUNCH_CHECK();
+      }
+    }
+    {
+      size_t smem = smem_kf_rev<DM>();
       if ((rc = set_smem<DM>((const void*)k_kf_rev<DM>, smem))) return rc;
       ProfScope ps_(PK_KF_REV, st);
       k_kf_rev<DM><<<nblk, 32, smem, st>>>(D(p.cst), Sc, Tn, D(p.Pkf), D(p.Kbar), D(p.acc));
       LQGK_LAUNCH_CHECK();
     }
     {
-      size_t smem = sizeof(double) * 32 * 2 * LqrC<DM>::n;
+      size_t smem = smem_lqr_rev<DM>();
       if ((rc = set_smem<DM>((const void*)k_lqr_rev<DM>, smem))) return rc;
       ProfScope ps_(PK_LQR_REV, st);
       k_lqr_rev<DM><<<nblk, 32, smem, st>>>(D(p.cst), Sc, Tn, c.eps, D(p.L), D(p.Sric), D(p.Lbar), D(p.acc));

@@ -89,48 +89,86 @@ LQGK_HD void kf_fwd_body(const GCst& g, WView lc, int T, WView Kw, bool save_P, 
 
 // ---------------------------------------------------------------------------------------------- COV fwd
 // Sink: put(idx, v) stores one float of the current step's record; commit(t) publishes the record.
+// When save_adj: C_t -> Cw, Fu_t -> FUw, (J_t, S'^-1_t) -> JSw, J_0 (initial conditioning gain) -> J0w.
 template <class DM, class Sink>
-LQGK_HD void cov_fwd_body(const GCst& g, WView lc, int T, WView Lw, WView Kw, bool save_C, WView Cw, Sink&& sink) {
-  constexpr int B = DM::B, U = DM::U, Y = DM::Y, R = DM::R;
+LQGK_HD void cov_fwd_body(const GCst& g, WView lc, int T, WView Lw, WView Kw, bool save_adj, WView Cw, WView FUw, WView JSw,
+                          WView J0w, Sink&& sink) {
+  constexpr int B = DM::B, U = DM::U, Y = DM::Y, R = DM::R, D = DM::D;
   using C = CovC<DM>;
+  using SR = CovSeqRev<DM>;
   load_consts<C>(g.at(0), lc, C::NSEG);
   double Cm[R * R], L[U * B], K[B * Y];
   LQGK_UNROLL for (int i = 0; i < B * Y; ++i) K[i] = Kw(i);
-  CovFwd<DM>::init(lc, K, Cm);
+  {
+    double J0[R * D];
+    CovFwd<DM>::init(lc, K, Cm, J0);
+    if (save_adj) { LQGK_UNROLL for (int i = 0; i < R * D; ++i) J0w(i) = J0[i]; }
+  }
   for (int t = 0; t < T; ++t) {
     if (g.tstride && t != 0) load_consts<C>(g.at(t), lc, C::NSEG);
     LQGK_UNROLL for (int i = 0; i < U * B; ++i) L[i] = Lw((size_t)t * DM::EL + i);
     LQGK_UNROLL for (int i = 0; i < B * Y; ++i) K[i] = Kw((size_t)t * DM::EK + i);
-    if (save_C) store_sym<R>(Cw, (size_t)t * DM::EC, Cm);
-    CovFwd<DM>::step(lc, L, K, Cm, [&](int idx, float v) { sink.put(idx, v); });
+    if (save_adj) store_sym<R>(Cw, (size_t)t * DM::EC, Cm);
+    CovFwd<DM>::step(lc, L, K, Cm, [&](int idx, float v) { sink.put(idx, v); },
+                     [&](int which, int e, double v) {
+                       if (save_adj) {
+                         if (which == 0) FUw((size_t)t * SR::NSF + e) = v;
+                         else JSw((size_t)t * SR::NJS + e) = v;
+                       }
+                     });
     sink.commit(t);
   }
 }
 
-// ---------------------------------------------------------------------------------------------- COV rev
-// Source: fetch(t) makes the float sums of step t available; get(idx) reads one.
+// ---------------------------------------------------------------------------------------------- COV rev (sequential)
+// Source: fetch(t) makes the float sums of step t available (only SUM_J.. and SUM_W.. are read); get(idx) reads one.
 template <class DM, class Source>
-LQGK_HD void cov_rev_body(const GCst& g, WView lc, WView la, int T, double sw, WView Lw, WView Kw, WView Cw,
-                          Source&& src, WView Lbw, WView Kbw, WView gacc) {
-  constexpr int B = DM::B, U = DM::U, Y = DM::Y, R = DM::R;
-  using C = CovC<DM>;
-  load_consts<C>(g.at(0), lc, C::NSEG);
-  for (int e = 0; e < C::n; ++e) la(e) = 0.0;
-  auto acc = [&](int e) -> double& { return la(e); };
-  double Cb[R * R], L[U * B], K[B * Y], Lb[U * B], Kb[B * Y];
+LQGK_HD void cov_seq_rev_body(int T, double sw, WView FUw, WView JSw, WView J0w, Source&& src, WView sc, WView SGBw, WView SGBIw,
+                              WView SFw) {
+  constexpr int R = DM::R;
+  using SR = CovSeqRev<DM>;
+  double Cb[R * R];
   LQGK_UNROLL for (int i = 0; i < R * R; ++i) Cb[i] = 0.0;
   for (int t = T - 1; t >= 0; --t) {
-    double Cm[R * R];
+    src.fetch(t);
+    SR::step([&](int e) { return FUw((size_t)t * SR::NSF + e); }, [&](int e) { return JSw((size_t)t * SR::NJS + e); },
+             [&](int idx) { return src.get(idx); }, sw, sc, Cb,
+             [&](int e, double v) { SGBw((size_t)t * SR::NSGB + e) = v; }, [&](int e, double v) { SFw((size_t)t * SR::NSF + e) = v; });
+  }
+  SR::init([&](int e) { return J0w(e); }, Cb, [&](int e, double v) { SGBIw(e) = v; });
+}
+
+// ---------------------------------------------------------------------------------------------- COV rev (time-parallel)
+// lc: local copy of the CovC constants (already loaded).  Processes steps [t0, t1).
+template <class DM, int PASS, class Source>
+LQGK_HD void cov_contrib_body(WView lc, int t0, int t1, WView Lw, WView Kw, WView Cw, WView SGBw, WView SGBIw, WView SFw,
+                              Source&& src, WView CTw, WView Lbw, WView Kbw) {
+  constexpr int B = DM::B, U = DM::U, Y = DM::Y, R = DM::R;
+  using SR = CovSeqRev<DM>;
+  using CC = CovContrib<DM>;
+  constexpr int NC = CovC<DM>::n;
+  for (int t = t0; t < t1; ++t) {
+    double Cm[R * R], L[U * B], K[B * Y];
     LQGK_UNROLL for (int i = 0; i < U * B; ++i) L[i] = Lw((size_t)t * DM::EL + i);
     LQGK_UNROLL for (int i = 0; i < B * Y; ++i) K[i] = Kw((size_t)t * DM::EK + i);
     load_sym_ws<R>(Cw, (size_t)t * DM::EC, Cm);
     src.fetch(t);
-    CovRev<DM>::step(lc, acc, L, K, Cm, [&](int idx) { return src.get(idx); }, sw, Cb, Lb, Kb);
-    if (t == 0) CovRev<DM>::init_bar(lc, acc, L, K, Cb, Lb, Kb);
-    LQGK_UNROLL for (int i = 0; i < U * B; ++i) Lbw((size_t)t * DM::EL + i) = Lb[i];
-    LQGK_UNROLL for (int i = 0; i < B * Y; ++i) Kbw((size_t)t * DM::EK + i) = Kb[i];
+    auto sf = [&](int e) { return SFw((size_t)t * SR::NSF + e); };
+    auto get = [&](int idx) { return src.get(idx); };
+    auto out = [&](int e, double v) { CTw((size_t)t * NC + e) = v; };
+    if (PASS == 0) {
+      double Lb[U * B], Kb[B * Y];
+      CC::pass0(lc, [&](int e) { return SGBw((size_t)t * SR::NSGB + e); }, t == 0, [&](int e) { return SGBIw(e); }, sf, get, Cm,
+                L, K, out, Lb, Kb);
+      LQGK_UNROLL for (int i = 0; i < U * B; ++i) Lbw((size_t)t * DM::EL + i) = Lb[i];
+      LQGK_UNROLL for (int i = 0; i < B * Y; ++i) Kbw((size_t)t * DM::EK + i) = Kb[i];
+    } else {
+      double Kb[B * Y];
+      LQGK_UNROLL for (int i = 0; i < B * Y; ++i) Kb[i] = Kbw((size_t)t * DM::EK + i);
+      CC::pass1(lc, sf, get, Cm, L, K, out, Kb);
+      LQGK_UNROLL for (int i = 0; i < B * Y; ++i) Kbw((size_t)t * DM::EK + i) = Kb[i];
+    }
   }
-  flush_acc<C>(gacc, la, C::NSEG);
 }
 
 // ---------------------------------------------------------------------------------------------- KF rev

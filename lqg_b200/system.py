@@ -139,6 +139,17 @@ class System:
     # -- hot path ------------------------------------------------------------------------------------------
     def log_likelihood(self, x: torch.Tensor, Sigma0=None) -> torch.Tensor:
         """log p(x_{i,1:T} | x_{i,0}) per trial, summed over time (system.py:246-248).  x: (n, T+1, d)."""
+        axis = getattr(self, "_axis_system", None)
+        if axis is not None and Sigma0 is None and x.shape[-1] == self.xdim:
+            # Exact factorisation (SURVEY 7.2, checked to 1e-15): a dim-axis tracking model with shared parameters is
+            # block diagonal, so its likelihood is the sum over axes of the 1-axis model's likelihood on that axis'
+            # (target, cursor) columns.  The per-sample recursions then run once on n/dim-sized matrices and the
+            # axes become extra trials: x[n, T+1, dim*da] -> [dim*n, T+1, da].
+            n, T1, d = x.shape
+            dim = self.dim
+            xa = x.reshape(n, T1, dim, d // dim).permute(2, 0, 1, 3).reshape(dim * n, T1, d // dim)
+            ll = axis.log_likelihood(xa)
+            return ll.reshape(*ll.shape[:-1], dim, n).sum(-2)
         s0 = None if Sigma0 is None else torch.as_tensor(Sigma0, dtype=self.dtype, device=self.device)
         return runtime.log_likelihood(self.actor, self.dynamics, x.to(self.device), Sigma0=s0)
 
@@ -148,7 +159,8 @@ class System:
     # -- slow paths ----------------------------------------------------------------------------------------
     def _joint(self, gains_L, K):
         """Joint (x, xhat) transition F[...,T,n,n] and noise factor G[...,T,n,x+y] (system.py:163-207)."""
-        a, dn = self.actor, self.dynamics
+        cast = lambda spec: LQGSpec(*[v.to(K.dtype) if torch.is_tensor(v) else v for v in spec])
+        a, dn = cast(self.actor), cast(self.dynamics)
         top = torch.cat([dn.A.expand(K.shape[:-2] + dn.A.shape[-2:]), dn.B @ gains_L], -1)
         bot = torch.cat([K @ dn.F @ dn.A, a.A + a.B @ gains_L - K @ a.F @ a.A + K @ (dn.F @ dn.B - a.F @ a.B) @ gains_L], -1)
         Fj = torch.cat([top, bot], -2)

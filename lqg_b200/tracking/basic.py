@@ -24,6 +24,10 @@ class TrackingTask(System):
         R = torch.eye(dim, dtype=dtype, device=device) * ac[..., None, None]
         spec = Actor(A=A, B=Bm, F=F, V=V, W=W, Q=Q, R=R, T=T)
         super().__init__(actor=spec, dynamics=spec)
+        if dim > 1:   # identical independent axes: the likelihood factorises (System.log_likelihood)
+            self._axis_system = TrackingTask(dim=1, process_noise=process_noise, action_variability=action_variability,
+                                             sigma_target=sigma_target, sigma_cursor=sigma_cursor, action_cost=action_cost,
+                                             dt=dt, T=T, dtype=dtype, device=device)
 
 
 class BoundedActor(TrackingTask):
@@ -58,3 +62,7 @@ class RelativeObservationBoundedActor(System):
         R = torch.eye(dim, dtype=dtype, device=device) * ac[..., None, None]
         spec = Actor(A=A, B=Bm, F=F, V=V, W=W, Q=Q, R=R, T=T)
         super().__init__(actor=spec, dynamics=spec)
+        if dim > 1:
+            self._axis_system = RelativeObservationBoundedActor(dim=1, process_noise=process_noise,
+                                                                action_variability=action_variability, sigma=sigma,
+                                                                action_cost=action_cost, dt=dt, T=T, dtype=dtype, device=device)

@@ -36,3 +36,8 @@ class SubjectiveActor(System):
         Q = Q[dims, :][:, dims]
         act = Actor(A=A, B=Bm, F=F, V=V, W=W, Q=Q, R=R, T=T)
         super().__init__(actor=act, dynamics=dyn)
+        if dim > 1:   # identical independent axes: the likelihood factorises (System.log_likelihood)
+            self._axis_system = SubjectiveActor(dim=1, process_noise=process_noise, action_cost=action_cost,
+                                                action_variability=action_variability, subj_noise=subj_noise,
+                                                subj_vel_noise=subj_vel_noise, sigma_target=sigma_target,
+                                                sigma_cursor=sigma_cursor, dt=dt, T=T, dtype=dtype, device=device)

@@ -62,6 +62,11 @@ int run(const LqgkDims& d, const LqgkSpec* act, const LqgkSpec* dyn, const LqgkM
   std::vector<double> Lw((size_t)Tn * DM::EL * Sc), Kw((size_t)Tn * DM::EK * Sc), Sw((size_t)Tn * DM::ES * Sc),
       Pw((size_t)Tn * DM::EP * Sc), Cw((size_t)Tn * DM::EC * Sc), Lbw((size_t)Tn * DM::EL * Sc),
       Kbw((size_t)Tn * DM::EK * Sc), lw((size_t)Tn * DM::U * Sc), Hw((size_t)Tn * DM::U * DM::U * Sc);
+  using SR = CovSeqRev<DM>;
+  constexpr int NC = CovC<DM>::n;
+  const size_t adj = want_grad ? 1 : 0;
+  std::vector<double> FUw(adj * Tn * SR::NSF * Sc), JSw(adj * Tn * SR::NJS * Sc), J0w(adj * DM::R * DM::D * Sc),
+      SGBw(adj * Tn * SR::NSGB * Sc), SGBIw(adj * SR::NSGB * Sc), SFw(adj * Tn * SR::NSF * Sc), CTw(adj * Tn * NC * Sc);
   std::vector<double> lc(cl.total + 8), la(cl.total + 8);
   auto V = [&](std::vector<double>& v, int s) { return WView{v.data() + s, Sc}; };
   for (int s = 0; s < S; ++s) {
@@ -91,7 +96,7 @@ int run(const LqgkDims& d, const LqgkSpec* act, const LqgkSpec* dyn, const LqgkM
   for (int s = 0; s < S; ++s) {
     GCst g{cst.data() + s, Sc, tstride};
     RecSink sink{rec.data() + (size_t)s * Tn * DM::REC, DM::REC, rec.data() + (size_t)s * Tn * DM::REC};
-    cov_fwd_body<DM>(g, WView{lc.data(), 1}, Tn, V(Lw, s), V(Kw, s), want_grad, V(Cw, s), sink);
+    cov_fwd_body<DM>(g, WView{lc.data(), 1}, Tn, V(Lw, s), V(Kw, s), want_grad, V(Cw, s), V(FUw, s), V(JSw, s), V(J0w, s), sink);
   }
   using TR = Trial<DM>;
   constexpr int D = DM::D, R = DM::R;
@@ -128,7 +133,19 @@ int run(const LqgkDims& d, const LqgkSpec* act, const LqgkSpec* dyn, const LqgkM
     GCst g{cst.data() + s, Sc, 0};
     WView ga{acc.data() + s, Sc};
     SumSrc src{sums.data() + (size_t)s * Tn * DM::SUMP, DM::SUMP, nullptr};
-    cov_rev_body<DM>(g, WView{lc.data(), 1}, WView{la.data(), 1}, Tn, sw, V(Lw, s), V(Kw, s), V(Cw, s), src, V(Lbw, s), V(Kbw, s), ga);
+    {
+      std::vector<double> sc(SR::SC_N + 8);
+      cov_seq_rev_body<DM>(Tn, sw, V(FUw, s), V(JSw, s), V(J0w, s), src, WView{sc.data(), 1}, V(SGBw, s), V(SGBIw, s), V(SFw, s));
+      load_consts<CovC<DM>>(g.at(0), WView{lc.data(), 1}, CovC<DM>::NSEG);
+      cov_contrib_body<DM, 0>(WView{lc.data(), 1}, 0, Tn, V(Lw, s), V(Kw, s), V(Cw, s), V(SGBw, s), V(SGBIw, s), V(SFw, s), src,
+                              V(CTw, s), V(Lbw, s), V(Kbw, s));
+      cov_contrib_body<DM, 1>(WView{lc.data(), 1}, 0, Tn, V(Lw, s), V(Kw, s), V(Cw, s), V(SGBw, s), V(SGBIw, s), V(SFw, s), src,
+                              V(CTw, s), V(Lbw, s), V(Kbw, s));
+      for (int e = 0; e < NC; ++e) la[e] = 0.0;               // time reduction of the per-step contributions
+      for (int t = 0; t < Tn; ++t)
+        for (int e = 0; e < NC; ++e) la[e] += CTw[((size_t)t * NC + e) * Sc + s];
+      flush_acc<CovC<DM>>(ga, WView{la.data(), 1}, CovC<DM>::NSEG);
+    }
     kf_rev_body<DM>(g, WView{lc.data(), 1}, WView{la.data(), 1}, Tn, V(Pw, s), V(Kbw, s), ga);
     lqr_rev_body<DM>(g, WView{lc.data(), 1}, WView{la.data(), 1}, Tn, eps, V(Lw, s), V(Sw, s), V(Lbw, s), ga);
     UnpackArgs<T> ua{};
