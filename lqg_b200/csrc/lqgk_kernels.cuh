@@ -51,6 +51,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// Per-thread asynchronous global->shared copies (LDGSTS) used as a register-free software prefetch.
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(dst)), "l"(src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // =========================================================================================== boundary kernels
 template <class T>
@@ -531,9 +539,24 @@ constexpr int TRIAL_WARPS = 4;   // warps (= samples) per CTA
 constexpr int TRIAL_TB = 8;      // time steps per ring stage
 constexpr int TRIAL_NST = 3;     // ring stages
 
-template <class DM>
+constexpr int TRIAL_PF = 4;      // observation / state prefetch distance in time steps (cp.async groups in flight)
+// Per-lane prefetch slots: [TRIAL_PF + 1][RT][W floats][32 lanes] per warp.
+template <class DM, int RT, bool REV>
 constexpr size_t trial_smem_bytes() {
-  return (size_t)TRIAL_WARPS * TRIAL_NST * TRIAL_TB * DM::REC * sizeof(float) + TRIAL_WARPS * TRIAL_NST * sizeof(uint64_t);
+  size_t ring = (size_t)TRIAL_WARPS * TRIAL_NST * TRIAL_TB * DM::REC * sizeof(float) + TRIAL_WARPS * TRIAL_NST * sizeof(uint64_t);
+  size_t pf = REV ? 0 : (size_t)TRIAL_WARPS * (TRIAL_PF + 1) * RT * 32 * DM::D * sizeof(float);   // forward only
+  return ring + pf;
+}
+// observation x[t][trial][0..D) -> this lane's slot (vector copy of D floats, D*4 in {4, 8, 16} bytes, else scalars)
+template <int D>
+__device__ __forceinline__ void prefetch_obs(float* slot, int lane, const float* src) {
+  if constexpr (D == 1 || D == 2 || D == 4) cp_async<D * 4>(slot + lane * D, src);
+  else { LQGK_UNROLL for (int k = 0; k < D; ++k) cp_async<4>(slot + k * 32 + lane, src + k); }
+}
+template <int D>
+__device__ __forceinline__ void read_obs(const float* slot, int lane, float* out) {
+  if constexpr (D == 1 || D == 2 || D == 4) { LQGK_UNROLL for (int k = 0; k < D; ++k) out[k] = slot[lane * D + k]; }
+  else { LQGK_UNROLL for (int k = 0; k < D; ++k) out[k] = slot[k * 32 + lane]; }
 }
 
 // Per-warp ring of record chunks filled by bulk async copies.  Chunk k covers steps [k*TB, min(T,(k+1)*TB)).
@@ -593,18 +616,22 @@ template <class DM>
 __host__ __device__ constexpr bool rec_in_regs() { return DM::REC <= 48; }
 
 // Forward: per-trial mean recursion + log-density.  grid = (ceil(n_samples / TRIAL_WARPS)), block = 32 * TRIAL_WARPS.
-// Trials are processed in passes of 32*RT (lane owns trials base + lane + 32*j, j < RT).
+// Trials are processed in passes of 32*RT (lane owns trials base + lane + 32*j, j < RT).  Observations are prefetched
+// TRIAL_PF steps ahead with per-lane cp.async copies into shared-memory slots (no registers held, no stalls on the
+// L2 round trip).
 template <class DM, int RT>
 __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_fwd(const float* __restrict__ rec, const float* __restrict__ x_tm,
                                                                 int n_samples, int N, int Tn, double* __restrict__ ll_ws,
                                                                 float* __restrict__ hist) {
-  constexpr int D = DM::D, R = DM::R;
+  constexpr int D = DM::D, R = DM::R, NSLOT = TRIAL_PF + 1;
   extern __shared__ __align__(128) unsigned char smraw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = blockIdx.x * TRIAL_WARPS + warp;
   if (s >= n_samples) return;
+  constexpr size_t RING_BYTES = (size_t)TRIAL_WARPS * TRIAL_NST * TRIAL_TB * DM::REC * sizeof(float);
   float* ring_base = reinterpret_cast<float*>(smraw);
-  uint64_t* bar_base = reinterpret_cast<uint64_t*>(smraw + (size_t)TRIAL_WARPS * TRIAL_NST * TRIAL_TB * DM::REC * sizeof(float));
+  uint64_t* bar_base = reinterpret_cast<uint64_t*>(smraw + RING_BYTES);
+  float* pf = reinterpret_cast<float*>(smraw + RING_BYTES + TRIAL_WARPS * TRIAL_NST * sizeof(uint64_t)) + (size_t)warp * NSLOT * RT * 32 * D;
   RecRing<DM> ring{ring_base + (size_t)warp * TRIAL_NST * TRIAL_TB * DM::REC, bar_base + warp * TRIAL_NST,
                    rec + (size_t)s * Tn * DM::REC, Tn, (Tn + TRIAL_TB - 1) / TRIAL_TB, lane, 0};
   ring.init();
@@ -617,13 +644,18 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_fwd(const float* __r
       ok[j] = i < N;
       tr[j] = ok[j] ? i : N - 1;
     }
-    float c[RT][R], x0[RT][D], x1[RT][D], x2[RT][D];
+    float c[RT][R], x0[RT][D], x1[RT][D];
     double ll[RT];
     LQGK_UNROLL for (int j = 0; j < RT; ++j) {
       ll[j] = 0.0;
       LQGK_UNROLL for (int k = 0; k < R; ++k) c[j][k] = 0.f;
       load_obs<D>(x_tm + (size_t)tr[j] * D, x0[j]);
-      load_obs<D>(x_tm + ((size_t)N + tr[j]) * D, x1[j]);
+    }
+    // prologue: x_{1..PF} in flight (one commit group per step)
+    for (int p = 0; p < TRIAL_PF; ++p) {
+      const int tp = min(1 + p, Tn);
+      LQGK_UNROLL for (int j = 0; j < RT; ++j) prefetch_obs<D>(pf + ((size_t)(p % NSLOT) * RT + j) * 32 * D, lane, x_tm + ((size_t)tp * N + tr[j]) * D);
+      cp_async_commit();
     }
     for (int k = 0; k < TRIAL_NST && k < nchunk; ++k) ring.issue(k, k);
     for (int k = 0; k < nchunk; ++k) {
@@ -635,8 +667,15 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_fwd(const float* __r
       for (int q = 0; q < nst; ++q) {
         const int t = t0 + q;
         const float* r = chunk + q * DM::REC;
-        const int tn = min(t + 2, Tn);                      // prefetch the observation two steps ahead
-        LQGK_UNROLL for (int j = 0; j < RT; ++j) load_obs<D>(x_tm + ((size_t)tn * N + tr[j]) * D, x2[j]);
+        {   // prefetch x_{t+1+PF}, then make sure x_{t+1} has landed
+          const int tn = min(t + 1 + TRIAL_PF, Tn);
+          float* slot = pf + (size_t)((t + TRIAL_PF) % NSLOT) * RT * 32 * D;
+          LQGK_UNROLL for (int j = 0; j < RT; ++j) prefetch_obs<D>(slot + (size_t)j * 32 * D, lane, x_tm + ((size_t)tn * N + tr[j]) * D);
+          cp_async_commit();
+          cp_async_wait<TRIAL_PF>();
+          const float* cur = pf + (size_t)(t % NSLOT) * RT * 32 * D;
+          LQGK_UNROLL for (int j = 0; j < RT; ++j) read_obs<D>(cur + (size_t)j * 32 * D, lane, x1[j]);
+        }
         if (hist != nullptr) {
           LQGK_UNROLL for (int j = 0; j < RT; ++j)
             if (ok[j]) {
@@ -650,16 +689,14 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_fwd(const float* __r
         } else {
           LQGK_UNROLL for (int j = 0; j < RT; ++j) part[j] += Trial<DM>::fwd(r, x0[j], x1[j], c[j]);
         }
-        LQGK_UNROLL for (int j = 0; j < RT; ++j) LQGK_UNROLL for (int m = 0; m < D; ++m) {
-          x0[j][m] = x1[j][m];
-          x1[j][m] = x2[j][m];
-        }
+        LQGK_UNROLL for (int j = 0; j < RT; ++j) LQGK_UNROLL for (int m = 0; m < D; ++m) x0[j][m] = x1[j][m];
       }
       // FP32 partial sum over <= TRIAL_TB steps, FP64 across chunks (log-likelihood error ~1e-7 relative)
       LQGK_UNROLL for (int j = 0; j < RT; ++j) ll[j] += (double)part[j];
       __syncwarp();
       if (k + TRIAL_NST < nchunk) ring.issue(k + TRIAL_NST, st);
     }
+    cp_async_wait<0>();
     LQGK_UNROLL for (int j = 0; j < RT; ++j)
       if (ok[j]) ll_ws[(size_t)s * N + tr[j]] = ll[j];
   }

@@ -137,7 +137,7 @@ int set_smem(const void* fn, size_t bytes) {
 
 template <class DM, int RT>
 int launch_trial_fwd(cudaStream_t st, const float* rec, const float* x_tm, int n, int N, int T, double* ll, float* hist) {
-  size_t smem = trial_smem_bytes<DM>();
+  size_t smem = trial_smem_bytes<DM, RT, false>();
   int rc = set_smem<DM>((const void*)k_trial_fwd<DM, RT>, smem);
   if (rc) return rc;
   ProfScope ps_(PK_TRIAL_FWD, st);
@@ -148,7 +148,7 @@ int launch_trial_fwd(cudaStream_t st, const float* rec, const float* x_tm, int n
 template <class DM, int RT>
 int launch_trial_rev(cudaStream_t st, const float* rec, const float* x_tm, const float* hist, const float* w, int n, int N,
                      int T, float* sums) {
-  size_t smem = trial_smem_bytes<DM>();
+  size_t smem = trial_smem_bytes<DM, RT, true>();
   int rc = set_smem<DM>((const void*)k_trial_rev<DM, RT>, smem);
   if (rc) return rc;
   ProfScope ps_(PK_TRIAL_REV, st);
