@@ -504,7 +504,9 @@ struct CovFwd {
   LQGK_HD static void step(const V& c, const double* L, const double* K, double* Cm, Put&& put, Save&& save) {
     double Fj[N * N], Nj[N * N], Sig[N * N];
     joint_F(c, L, K, Fj);
-    LQGK_UNROLL for (int i = 0; i < N * N; ++i) put(DM::REC_F + i, (float)Fj[i]);
+    // the observed rows are stored negated so the trial kernels form e = x1 + (-F[o,:]) [x0; c] with plain FMAs, starting
+    // from x1 (x1 - x0 is exact when A_d = I, which keeps the residual accurate in FP32)
+    LQGK_UNROLL for (int i = 0; i < N * N; ++i) put(DM::REC_F + i, (float)(i < D * N ? -Fj[i] : Fj[i]));
     LQGK_UNROLL for (int i = 0; i < N; ++i) LQGK_UNROLL for (int j = 0; j < R; ++j) save(0, i * R + j, Fj[i * N + D + j]);
     joint_N(c, K, Nj);
     predict(Fj, Cm, Nj, Sig);
@@ -522,72 +524,133 @@ struct CovFwd {
 };
 
 // ================================================================================================
-// Per-trial mean / likelihood recursion (system.py:219-221 + MVN log_prob), FP32, one lane per trial.
+// Scalar types of the per-trial recursions: `float` (one trial) or `f32x2` (two trials packed in one 64-bit
+// register pair, executed by Blackwell's packed FP32 instructions fma/mul/add.rn.f32x2 -- one issue slot for two
+// FMAs; device only).
+struct f32x2 {
+  float x, y;
+};
+template <class S>
+struct Ops;
+template <>
+struct Ops<float> {
+  LQGK_HD static float bc(float r) { return r; }
+  LQGK_HD static float zero() { return 0.f; }
+  LQGK_HD static float fma(float a, float b, float c) { return fmaf(a, b, c); }
+  LQGK_HD static float mul(float a, float b) { return a * b; }
+  LQGK_HD static float add(float a, float b) { return a + b; }
+  LQGK_HD static float sub(float a, float b) { return a - b; }
+  LQGK_HD static float neg(float a) { return -a; }
+  LQGK_HD static float hsum(float a) { return a; }
+};
+#if defined(__CUDACC__)
+template <>
+struct Ops<f32x2> {
+  using U = unsigned long long;
+  __device__ __forceinline__ static U u(const f32x2& a) { return *reinterpret_cast<const U*>(&a); }
+  __device__ __forceinline__ static f32x2 f(U v) { return *reinterpret_cast<f32x2*>(&v); }
+  __device__ __forceinline__ static f32x2 bc(float r) { return f32x2{r, r}; }
+  __device__ __forceinline__ static f32x2 zero() { return f32x2{0.f, 0.f}; }
+  __device__ __forceinline__ static f32x2 fma(f32x2 a, f32x2 b, f32x2 c) {
+    U d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(u(a)), "l"(u(b)), "l"(u(c)));
+    return f(d);
+  }
+  __device__ __forceinline__ static f32x2 mul(f32x2 a, f32x2 b) {
+    U d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(u(a)), "l"(u(b)));
+    return f(d);
+  }
+  __device__ __forceinline__ static f32x2 add(f32x2 a, f32x2 b) {
+    U d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(u(a)), "l"(u(b)));
+    return f(d);
+  }
+  __device__ __forceinline__ static f32x2 sub(f32x2 a, f32x2 b) {
+    U d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(u(a)), "l"(u(b)));
+    return f(d);
+  }
+  __device__ __forceinline__ static f32x2 neg(f32x2 a) { return f32x2{-a.x, -a.y}; }
+  __device__ __forceinline__ static float hsum(f32x2 a) { return a.x + a.y; }
+};
+#endif
+
+// ================================================================================================
+// Per-trial mean / likelihood recursion (system.py:219-221 + MVN log_prob), FP32, one lane per trial (S = float) or
+// per pair of trials (S = f32x2).
 //   e = x1 - F[o,o] x0 - F[o,u] c ;  c' = F[u,o] x0 + F[u,u] c + J e ;  ll -= 1/2 |Linv e|^2 + logdet + const
-// `rec` is the float record of this step (any indexable: shared-memory pointer on the device).
+// `rec` is the float record of this step (any indexable: shared-memory pointer or register copy).
 template <class DM>
 struct Trial {
   static constexpr int D = DM::D, N = DM::N, R = DM::R;
   static constexpr float HALF_LOG2PI_D = 0.91893853320467274178f * D;
 
-  template <class Rec>
-  LQGK_HD static void residual(const Rec& rec, const float* x0, const float* x1, const float* c, float* e) {
-    LQGK_UNROLL for (int i = 0; i < D; ++i) {
-      float a = x1[i];
-      LQGK_UNROLL for (int j = 0; j < D; ++j) a -= rec[DM::REC_F + i * N + j] * x0[j];
-      LQGK_UNROLL for (int j = 0; j < R; ++j) a -= rec[DM::REC_F + i * N + D + j] * c[j];
+  template <class S, class Rec>
+  LQGK_HD static void residual(const Rec& rec, const S* x0, const S* x1, const S* c, S* e) {
+    using O = Ops<S>;
+    LQGK_UNROLL for (int i = 0; i < D; ++i) {                         // record rows o hold -F[o,:]
+      S a = x1[i];
+      LQGK_UNROLL for (int j = 0; j < D; ++j) a = O::fma(O::bc(rec[DM::REC_F + i * N + j]), x0[j], a);
+      LQGK_UNROLL for (int j = 0; j < R; ++j) a = O::fma(O::bc(rec[DM::REC_F + i * N + D + j]), c[j], a);
       e[i] = a;
     }
   }
-  template <class Rec>
-  LQGK_HD static void whiten(const Rec& rec, const float* e, float* z) {   // z = Linv e
+  template <class S, class Rec>
+  LQGK_HD static void whiten(const Rec& rec, const S* e, S* z) {   // z = Linv e
+    using O = Ops<S>;
     LQGK_UNROLL for (int i = 0; i < D; ++i) {
-      float a = 0.f;
-      LQGK_UNROLL for (int j = 0; j <= i; ++j) a += rec[DM::REC_LINV + i * (i + 1) / 2 + j] * e[j];
+      S a = O::zero();
+      LQGK_UNROLL for (int j = 0; j <= i; ++j) a = O::fma(O::bc(rec[DM::REC_LINV + i * (i + 1) / 2 + j]), e[j], a);
       z[i] = a;
     }
   }
   // forward step; returns this step's log-density term
-  template <class Rec>
-  LQGK_HD static float fwd(const Rec& rec, const float* x0, const float* x1, float* c) {
-    float e[D], z[D], cn[R];
-    residual(rec, x0, x1, c, e);
-    whiten(rec, e, z);
-    float qf = 0.f;
-    LQGK_UNROLL for (int i = 0; i < D; ++i) qf += z[i] * z[i];
+  template <class S, class Rec>
+  LQGK_HD static S fwd(const Rec& rec, const S* x0, const S* x1, S* c) {
+    using O = Ops<S>;
+    S e[D], z[D], cn[R];
+    residual<S>(rec, x0, x1, c, e);
+    whiten<S>(rec, e, z);
+    S qf = O::zero();
+    LQGK_UNROLL for (int i = 0; i < D; ++i) qf = O::fma(z[i], z[i], qf);
     LQGK_UNROLL for (int i = 0; i < R; ++i) {
-      float a = 0.f;
-      LQGK_UNROLL for (int j = 0; j < D; ++j) a += rec[DM::REC_F + (D + i) * N + j] * x0[j];
-      LQGK_UNROLL for (int j = 0; j < R; ++j) a += rec[DM::REC_F + (D + i) * N + D + j] * c[j];
-      LQGK_UNROLL for (int j = 0; j < D; ++j) a += rec[DM::REC_J + i * D + j] * e[j];
+      S a = O::zero();
+      LQGK_UNROLL for (int j = 0; j < D; ++j) a = O::fma(O::bc(rec[DM::REC_F + (D + i) * N + j]), x0[j], a);
+      LQGK_UNROLL for (int j = 0; j < R; ++j) a = O::fma(O::bc(rec[DM::REC_F + (D + i) * N + D + j]), c[j], a);
+      LQGK_UNROLL for (int j = 0; j < D; ++j) a = O::fma(O::bc(rec[DM::REC_J + i * D + j]), e[j], a);
       cn[i] = a;
     }
     LQGK_UNROLL for (int i = 0; i < R; ++i) c[i] = cn[i];
-    return -0.5f * qf - rec[DM::REC_LOGDET] - HALF_LOG2PI_D;
+    return O::fma(O::bc(-0.5f), qf, O::bc(-rec[DM::REC_LOGDET] - HALF_LOG2PI_D));
   }
-  // reverse step for one trial: given c (= c_t), x0 = x_t, x1 = x_{t+1}, weight w and the incoming
-  // cotangent cb (of c_{t+1}); produces e, v = S'^-1 e, eb = J^T cb - w v and the outgoing cotangent
-  // cbn = F[u,u]^T cb - F[o,u]^T eb (of c_t).  Sums over trials are formed by the caller (sum_term).
-  template <class Rec>
-  LQGK_HD static void rev(const Rec& rec, const float* x0, const float* x1, const float* c, float w,
-                          const float* cb, float* e, float* v, float* eb, float* cbn) {
-    float z[D];
-    residual(rec, x0, x1, c, e);
-    whiten(rec, e, z);
-    LQGK_UNROLL for (int i = 0; i < D; ++i) {                         // v = Linv^T z
-      float a = 0.f;
-      LQGK_UNROLL for (int k = i; k < D; ++k) a += rec[DM::REC_LINV + k * (k + 1) / 2 + i] * z[k];
+  // reverse step: given c (= c_t), x0 = x_t, x1 = x_{t+1}, weight w and the incoming cotangent cb (of c_{t+1});
+  // produces e, v = S'^-1 e, wv = w v, eb = J^T cb - w v, neb = -eb and the outgoing cotangent
+  // cbn = F[u,u]^T cb - F[o,u]^T eb (of c_t; the record holds -F[o,:]).  Sums over trials: sum_acc.
+  template <class S, class Rec>
+  LQGK_HD static void rev(const Rec& rec, const S* x0, const S* x1, const S* c, S w, const S* cb, S* e, S* v, S* wv, S* neb,
+                          S* cbn) {
+    using O = Ops<S>;
+    S z[D];
+    residual<S>(rec, x0, x1, c, e);
+    whiten<S>(rec, e, z);
+    LQGK_UNROLL for (int i = 0; i < D; ++i) {                         // v = Linv^T z ; wv = w v
+      S a = O::zero();
+      LQGK_UNROLL for (int k = i; k < D; ++k) a = O::fma(O::bc(rec[DM::REC_LINV + k * (k + 1) / 2 + i]), z[k], a);
       v[i] = a;
+      wv[i] = O::mul(w, a);
     }
+    S eb[D];
     LQGK_UNROLL for (int j = 0; j < D; ++j) {                         // eb = J^T cb - w v
-      float a = -w * v[j];
-      LQGK_UNROLL for (int i = 0; i < R; ++i) a += rec[DM::REC_J + i * D + j] * cb[i];
-      eb[j] = a;
+      S a = O::zero();
+      LQGK_UNROLL for (int i = 0; i < R; ++i) a = O::fma(O::bc(rec[DM::REC_J + i * D + j]), cb[i], a);
+      eb[j] = O::sub(a, wv[j]);
+      neb[j] = O::sub(wv[j], a);
     }
-    LQGK_UNROLL for (int j = 0; j < R; ++j) {
-      float a = 0.f;
-      LQGK_UNROLL for (int i = 0; i < R; ++i) a += rec[DM::REC_F + (D + i) * N + D + j] * cb[i];
-      LQGK_UNROLL for (int i = 0; i < D; ++i) a -= rec[DM::REC_F + i * N + D + j] * eb[i];
+    LQGK_UNROLL for (int j = 0; j < R; ++j) {                         // cbn = F[u,u]^T cb + (-F[o,u])^T eb
+      S a = O::zero();
+      LQGK_UNROLL for (int i = 0; i < R; ++i) a = O::fma(O::bc(rec[DM::REC_F + (D + i) * N + D + j]), cb[i], a);
+      LQGK_UNROLL for (int i = 0; i < D; ++i) a = O::fma(O::bc(rec[DM::REC_F + i * N + D + j]), eb[i], a);
       cbn[j] = a;
     }
   }
@@ -596,27 +659,27 @@ struct Trial {
     while ((i + 1) * (i + 2) / 2 <= k) ++i;
     return i;
   }
-  // Term IDX (compile-time) of the per-step sums for one trial (layout DM::SUM_*):
-  //   Fb[i][j] = a_i b_j with a = [-eb ; cb], b = [x0 ; c];  Jb[i][j] = cb_i e_j;  Wv[i>=j] = w v_i v_j.
-  template <int IDX>
-  LQGK_HD static float sum_term(const float* cb, const float* eb, const float* x0, const float* c,
-                                const float* e, const float* v, float w) {
+  // acc += term IDX (compile-time) of the per-step sums (layout DM::SUM_*):
+  //   Fb[i][j] = a_i b_j with a = [neb ; cb], b = [x0 ; c];  Jb[i][j] = cb_i e_j;  Wv[i>=j] = (w v_i) v_j.
+  template <int IDX, class S>
+  LQGK_HD static S sum_acc(S acc, const S* cb, const S* neb, const S* x0, const S* c, const S* e, const S* v, const S* wv) {
+    using O = Ops<S>;
     if constexpr (IDX >= DM::NSUM || (IDX >= N * N && IDX < DM::SUM_J)) {
-      return 0.f;
+      return acc;
     } else if constexpr (IDX < N * N) {
       constexpr int i = IDX / N, j = IDX % N;
-      float a, b;
-      if constexpr (i < D) a = -eb[i]; else a = cb[i - D];
+      S a, b;
+      if constexpr (i < D) a = neb[i]; else a = cb[i - D];
       if constexpr (j < D) b = x0[j]; else b = c[j - D];
-      return a * b;
+      return O::fma(a, b, acc);
     } else if constexpr (IDX < DM::SUM_W) {
       constexpr int k = IDX - DM::SUM_J;
-      return cb[k / D] * e[k % D];
+      return O::fma(cb[k / D], e[k % D], acc);
     } else {
       constexpr int k = IDX - DM::SUM_W;
       constexpr int i = tri_row(k);
       constexpr int j = k - i * (i + 1) / 2;
-      return w * v[i] * v[j];
+      return O::fma(wv[i], v[j], acc);
     }
   }
 };

@@ -637,24 +637,36 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_fwd(const float* __r
   ring.init();
   const int nchunk = ring.nchunk;
   for (int base = 0; base < N; base += 32 * RT) {
-    int tr[RT];
+    int tr[RT], trD[RT];
     bool ok[RT];
     LQGK_UNROLL for (int j = 0; j < RT; ++j) {
       int i = base + lane + 32 * j;
       ok[j] = i < N;
       tr[j] = ok[j] ? i : N - 1;
+      trD[j] = tr[j] * D;            // 32-bit element offsets: one 64-bit row pointer per step + cheap lane offsets
     }
-    float c[RT][R], x0[RT][D], x1[RT][D];
+    // trials 2p, 2p+1 are packed into one f32x2 lane-pair state (Blackwell FFMA2); an odd last trial stays scalar
+    constexpr int NP = RT / 2, NS = RT % 2;
+    f32x2 cP[NP > 0 ? NP : 1][R], x0P[NP > 0 ? NP : 1][D];
+    float cS[R], x0S[D];
     double ll[RT];
-    LQGK_UNROLL for (int j = 0; j < RT; ++j) {
-      ll[j] = 0.0;
-      LQGK_UNROLL for (int k = 0; k < R; ++k) c[j][k] = 0.f;
-      load_obs<D>(x_tm + (size_t)tr[j] * D, x0[j]);
+    {
+      float x0[RT][D];
+      LQGK_UNROLL for (int j = 0; j < RT; ++j) {
+        ll[j] = 0.0;
+        load_obs<D>(x_tm + (size_t)tr[j] * D, x0[j]);
+      }
+      LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) {
+        LQGK_UNROLL for (int k = 0; k < R; ++k) cP[p2][k] = f32x2{0.f, 0.f};
+        LQGK_UNROLL for (int m = 0; m < D; ++m) x0P[p2][m] = f32x2{x0[2 * p2][m], x0[2 * p2 + 1][m]};
+      }
+      LQGK_UNROLL for (int k = 0; k < R; ++k) cS[k] = 0.f;
+      LQGK_UNROLL for (int m = 0; m < D; ++m) x0S[m] = x0[RT - 1][m];
     }
     // prologue: x_{1..PF} in flight (one commit group per step)
     for (int p = 0; p < TRIAL_PF; ++p) {
-      const int tp = min(1 + p, Tn);
-      LQGK_UNROLL for (int j = 0; j < RT; ++j) prefetch_obs<D>(pf + ((size_t)(p % NSLOT) * RT + j) * 32 * D, lane, x_tm + ((size_t)tp * N + tr[j]) * D);
+      const float* xrow = x_tm + (size_t)min(1 + p, Tn) * N * D;
+      LQGK_UNROLL for (int j = 0; j < RT; ++j) prefetch_obs<D>(pf + ((p % NSLOT) * RT + j) * 32 * D, lane, xrow + trD[j]);
       cp_async_commit();
     }
     for (int k = 0; k < TRIAL_NST && k < nchunk; ++k) ring.issue(k, k);
@@ -662,37 +674,61 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_fwd(const float* __r
       const int st = k % TRIAL_NST;
       const float* chunk = ring.wait(st);
       const int t0 = k * TRIAL_TB, nst = min(TRIAL_TB, Tn - t0);
-      float part[RT];
-      LQGK_UNROLL for (int j = 0; j < RT; ++j) part[j] = 0.f;
+      f32x2 partP[NP > 0 ? NP : 1];
+      float partS = 0.f;
+      LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) partP[p2] = f32x2{0.f, 0.f};
+#pragma unroll 1
       for (int q = 0; q < nst; ++q) {
         const int t = t0 + q;
         const float* r = chunk + q * DM::REC;
+        f32x2 x1P[NP > 0 ? NP : 1][D];
+        float x1S[D];
         {   // prefetch x_{t+1+PF}, then make sure x_{t+1} has landed
-          const int tn = min(t + 1 + TRIAL_PF, Tn);
-          float* slot = pf + (size_t)((t + TRIAL_PF) % NSLOT) * RT * 32 * D;
-          LQGK_UNROLL for (int j = 0; j < RT; ++j) prefetch_obs<D>(slot + (size_t)j * 32 * D, lane, x_tm + ((size_t)tn * N + tr[j]) * D);
+          const float* xrow = x_tm + (size_t)min(t + 1 + TRIAL_PF, Tn) * N * D;
+          float* slot = pf + ((t + TRIAL_PF) % NSLOT) * (RT * 32 * D);
+          LQGK_UNROLL for (int j = 0; j < RT; ++j) prefetch_obs<D>(slot + j * 32 * D, lane, xrow + trD[j]);
           cp_async_commit();
           cp_async_wait<TRIAL_PF>();
-          const float* cur = pf + (size_t)(t % NSLOT) * RT * 32 * D;
-          LQGK_UNROLL for (int j = 0; j < RT; ++j) read_obs<D>(cur + (size_t)j * 32 * D, lane, x1[j]);
+          const float* cur = pf + (t % NSLOT) * (RT * 32 * D);
+          LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) {
+            float xa[D], xb[D];
+            read_obs<D>(cur + (2 * p2) * 32 * D, lane, xa);
+            read_obs<D>(cur + (2 * p2 + 1) * 32 * D, lane, xb);
+            LQGK_UNROLL for (int m = 0; m < D; ++m) x1P[p2][m] = f32x2{xa[m], xb[m]};
+          }
+          if constexpr (NS) read_obs<D>(cur + (RT - 1) * 32 * D, lane, x1S);
         }
         if (hist != nullptr) {
-          LQGK_UNROLL for (int j = 0; j < RT; ++j)
-            if (ok[j]) {
-              LQGK_UNROLL for (int m = 0; m < R; ++m) hist[(((size_t)s * Tn + t) * R + m) * N + tr[j]] = c[j][m];
-            }
+          float* hrow = hist + ((size_t)s * Tn + t) * R * N;
+          LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) {
+            if (ok[2 * p2]) { LQGK_UNROLL for (int m = 0; m < R; ++m) hrow[m * N + tr[2 * p2]] = cP[p2][m].x; }
+            if (ok[2 * p2 + 1]) { LQGK_UNROLL for (int m = 0; m < R; ++m) hrow[m * N + tr[2 * p2 + 1]] = cP[p2][m].y; }
+          }
+          if constexpr (NS) {
+            if (ok[RT - 1]) { LQGK_UNROLL for (int m = 0; m < R; ++m) hrow[m * N + tr[RT - 1]] = cS[m]; }
+          }
         }
+        auto run = [&](const auto& rr) {
+          LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2)
+            partP[p2] = Ops<f32x2>::add(partP[p2], Trial<DM>::template fwd<f32x2>(rr, x0P[p2], x1P[p2], cP[p2]));
+          if constexpr (NS) partS += Trial<DM>::template fwd<float>(rr, x0S, x1S, cS);
+        };
         if constexpr (rec_in_regs<DM>()) {
           RecRegs<DM> rr;
           rr.load(r);
-          LQGK_UNROLL for (int j = 0; j < RT; ++j) part[j] += Trial<DM>::fwd(rr, x0[j], x1[j], c[j]);
+          run(rr);
         } else {
-          LQGK_UNROLL for (int j = 0; j < RT; ++j) part[j] += Trial<DM>::fwd(r, x0[j], x1[j], c[j]);
+          run(r);
         }
-        LQGK_UNROLL for (int j = 0; j < RT; ++j) LQGK_UNROLL for (int m = 0; m < D; ++m) x0[j][m] = x1[j][m];
+        LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) LQGK_UNROLL for (int m = 0; m < D; ++m) x0P[p2][m] = x1P[p2][m];
+        if constexpr (NS) { LQGK_UNROLL for (int m = 0; m < D; ++m) x0S[m] = x1S[m]; }
       }
       // FP32 partial sum over <= TRIAL_TB steps, FP64 across chunks (log-likelihood error ~1e-7 relative)
-      LQGK_UNROLL for (int j = 0; j < RT; ++j) ll[j] += (double)part[j];
+      LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) {
+        ll[2 * p2] += (double)partP[p2].x;
+        ll[2 * p2 + 1] += (double)partP[p2].y;
+      }
+      if constexpr (NS) ll[RT - 1] += (double)partS;
       __syncwarp();
       if (k + TRIAL_NST < nchunk) ring.issue(k + TRIAL_NST, st);
     }
@@ -741,20 +777,34 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __r
   ring.init();
   const int nchunk = ring.nchunk;
   for (int base = 0; base < N; base += 32 * RT) {
-    int tr[RT];
+    int tr[RT], trD[RT];
     float wt[RT];
     LQGK_UNROLL for (int j = 0; j < RT; ++j) {
       int i = base + lane + 32 * j;
       bool ok = i < N;
       tr[j] = ok ? i : N - 1;
+      trD[j] = tr[j] * D;
       wt[j] = ok ? w[(size_t)s * N + tr[j]] : 0.f;   // masked trials contribute nothing (cb stays 0, w = 0)
     }
-    float cb[RT][R], x1[RT][D], x0[RT][D], c[RT][R];
+    constexpr int NP = RT / 2, NS = RT % 2, NPA = NP > 0 ? NP : 1;
+    // persistent state: cotangent cb, x_{t+1}; prefetched (x_t, c_t) of the next step to process
+    f32x2 cbP[NPA][R], x1P[NPA][D], wP[NPA];
+    float cbS[R], x1S[D], wS = wt[RT - 1];
+    float x0n[RT][D], cn_[RT][R];          // "next" = values for the step about to be processed
     LQGK_UNROLL for (int j = 0; j < RT; ++j) {
-      LQGK_UNROLL for (int k = 0; k < R; ++k) cb[j][k] = 0.f;
-      load_obs<D>(x_tm + ((size_t)Tn * N + tr[j]) * D, x1[j]);
-      load_obs<D>(x_tm + ((size_t)(Tn - 1) * N + tr[j]) * D, x0[j]);
-      LQGK_UNROLL for (int m = 0; m < R; ++m) c[j][m] = __ldg(&hist[(((size_t)s * Tn + (Tn - 1)) * R + m) * N + tr[j]]);
+      load_obs<D>(x_tm + ((size_t)(Tn - 1) * N + tr[j]) * D, x0n[j]);
+      LQGK_UNROLL for (int m = 0; m < R; ++m) cn_[j][m] = __ldg(&hist[(((size_t)s * Tn + (Tn - 1)) * R + m) * N + tr[j]]);
+    }
+    {
+      float x1[RT][D];
+      LQGK_UNROLL for (int j = 0; j < RT; ++j) load_obs<D>(x_tm + ((size_t)Tn * N + tr[j]) * D, x1[j]);
+      LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) {
+        LQGK_UNROLL for (int k = 0; k < R; ++k) cbP[p2][k] = f32x2{0.f, 0.f};
+        LQGK_UNROLL for (int m = 0; m < D; ++m) x1P[p2][m] = f32x2{x1[2 * p2][m], x1[2 * p2 + 1][m]};
+        wP[p2] = f32x2{wt[2 * p2], wt[2 * p2 + 1]};
+      }
+      LQGK_UNROLL for (int k = 0; k < R; ++k) cbS[k] = 0.f;
+      LQGK_UNROLL for (int m = 0; m < D; ++m) x1S[m] = x1[RT - 1][m];
     }
     for (int k = 0; k < TRIAL_NST && k < nchunk; ++k) ring.issue(nchunk - 1 - k, k);
     for (int kk = 0; kk < nchunk; ++kk) {
@@ -762,31 +812,59 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __r
       const int st = kk % TRIAL_NST;
       const float* chunk = ring.wait(st);
       const int t0 = k * TRIAL_TB, nst = min(TRIAL_TB, Tn - t0);
+#pragma unroll 1
       for (int q = nst - 1; q >= 0; --q) {
         const int t = t0 + q;
         const float* r = chunk + q * DM::REC;
-        float e[RT][D], v[RT][D], eb[RT][D], cbn[RT][R], xp[RT][D], cp[RT][R];
-        const int tp = max(t - 1, 0);                        // prefetch the previous step's observation and state
-        LQGK_UNROLL for (int j = 0; j < RT; ++j) {
-          load_obs<D>(x_tm + ((size_t)tp * N + tr[j]) * D, xp[j]);
-          LQGK_UNROLL for (int m = 0; m < R; ++m) cp[j][m] = __ldg(&hist[(((size_t)s * Tn + tp) * R + m) * N + tr[j]]);
+        // pack this step's (x_t, c_t), then start loading the previous step's
+        f32x2 x0P[NPA][D], cP[NPA][R];
+        float x0S[D], cS[R];
+        LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) {
+          LQGK_UNROLL for (int m = 0; m < D; ++m) x0P[p2][m] = f32x2{x0n[2 * p2][m], x0n[2 * p2 + 1][m]};
+          LQGK_UNROLL for (int m = 0; m < R; ++m) cP[p2][m] = f32x2{cn_[2 * p2][m], cn_[2 * p2 + 1][m]};
         }
+        LQGK_UNROLL for (int m = 0; m < D; ++m) x0S[m] = x0n[RT - 1][m];
+        LQGK_UNROLL for (int m = 0; m < R; ++m) cS[m] = cn_[RT - 1][m];
+        {
+          const int tp = max(t - 1, 0);
+          const float* hrow = hist + ((size_t)s * Tn + tp) * R * N;
+          const float* xrow = x_tm + (size_t)tp * N * D;
+          LQGK_UNROLL for (int j = 0; j < RT; ++j) {
+            load_obs<D>(xrow + trD[j], x0n[j]);
+            LQGK_UNROLL for (int m = 0; m < R; ++m) cn_[j][m] = __ldg(hrow + (m * N + tr[j]));
+          }
+        }
+        f32x2 eP[NPA][D], vP[NPA][D], wvP[NPA][D], nebP[NPA][D], cbnP[NPA][R];
+        float eS[D], vS[D], wvS[D], nebS[D], cbnS[R];
+        auto run = [&](const auto& rr) {
+          LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2)
+            Trial<DM>::template rev<f32x2>(rr, x0P[p2], x1P[p2], cP[p2], wP[p2], cbP[p2], eP[p2], vP[p2], wvP[p2], nebP[p2], cbnP[p2]);
+          if constexpr (NS) Trial<DM>::template rev<float>(rr, x0S, x1S, cS, wS, cbS, eS, vS, wvS, nebS, cbnS);
+        };
         if constexpr (rec_in_regs<DM>()) {
           RecRegs<DM> rr;
           rr.load(r);
-          LQGK_UNROLL for (int j = 0; j < RT; ++j) Trial<DM>::rev(rr, x0[j], x1[j], c[j], wt[j], cb[j], e[j], v[j], eb[j], cbn[j]);
+          run(rr);
         } else {
-          LQGK_UNROLL for (int j = 0; j < RT; ++j) Trial<DM>::rev(r, x0[j], x1[j], c[j], wt[j], cb[j], e[j], v[j], eb[j], cbn[j]);
+          run(r);
         }
         float* out = sums + ((size_t)s * Tn + t) * DM::SUMP;
+        auto term = [&](auto IDXC) -> float {
+          constexpr int IDX = decltype(IDXC)::value;
+          float a = 0.f;
+          if constexpr (NP > 0) {
+            f32x2 acc = f32x2{0.f, 0.f};
+            LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2)
+              acc = Trial<DM>::template sum_acc<IDX, f32x2>(acc, cbP[p2], nebP[p2], x0P[p2], cP[p2], eP[p2], vP[p2], wvP[p2]);
+            a = acc.x + acc.y;
+          }
+          if constexpr (NS) a = Trial<DM>::template sum_acc<IDX, float>(a, cbS, nebS, x0S, cS, eS, vS, wvS);
+          return a;
+        };
         static_for<0, NFULL>([&](auto G) {
           float val[32];
           static_for<0, 32>([&](auto J) {
-            constexpr int IDX = decltype(G)::value * 32 + decltype(J)::value;
-            float a = 0.f;
-            LQGK_UNROLL for (int j = 0; j < RT; ++j)
-              a += Trial<DM>::template sum_term<IDX>(cb[j], eb[j], x0[j], c[j], e[j], v[j], wt[j]);
-            val[decltype(J)::value] = a;
+            val[decltype(J)::value] = term(std::integral_constant<int, decltype(G)::value * 32 + decltype(J)::value>{});
           });
           float tot = warp_transpose_reduce<32>(val, lane);
           const int idx = decltype(G)::value * 32 + lane;
@@ -795,13 +873,7 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __r
         });
         if constexpr (REM > 0) {
           float val[VREM];
-          static_for<0, VREM>([&](auto J) {
-            constexpr int IDX = NFULL * 32 + decltype(J)::value;
-            float a = 0.f;
-            LQGK_UNROLL for (int j = 0; j < RT; ++j)
-              a += Trial<DM>::template sum_term<IDX>(cb[j], eb[j], x0[j], c[j], e[j], v[j], wt[j]);
-            val[decltype(J)::value] = a;
-          });
+          static_for<0, VREM>([&](auto J) { val[decltype(J)::value] = term(std::integral_constant<int, NFULL * 32 + decltype(J)::value>{}); });
           float tot = warp_transpose_reduce<VREM>(val, lane);
           const int vi = lane / (32 / VREM);
           const int idx = NFULL * 32 + vi;
@@ -810,9 +882,13 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __r
             else out[idx] += tot;
           }
         }
-        LQGK_UNROLL for (int j = 0; j < RT; ++j) {
-          LQGK_UNROLL for (int m = 0; m < R; ++m) { cb[j][m] = cbn[j][m]; c[j][m] = cp[j][m]; }
-          LQGK_UNROLL for (int m = 0; m < D; ++m) { x1[j][m] = x0[j][m]; x0[j][m] = xp[j][m]; }
+        LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) {
+          LQGK_UNROLL for (int m = 0; m < R; ++m) cbP[p2][m] = cbnP[p2][m];
+          LQGK_UNROLL for (int m = 0; m < D; ++m) x1P[p2][m] = x0P[p2][m];
+        }
+        if constexpr (NS) {
+          LQGK_UNROLL for (int m = 0; m < R; ++m) cbS[m] = cbnS[m];
+          LQGK_UNROLL for (int m = 0; m < D; ++m) x1S[m] = x0S[m];
         }
       }
       __syncwarp();

@@ -107,7 +107,7 @@ int run(const LqgkDims& d, const LqgkSpec* act, const LqgkSpec* dyn, const LqgkM
       for (int t = 0; t < Tn; ++t) {
         const float* r = rec.data() + ((size_t)s * Tn + t) * DM::REC;
         if (want_grad) std::memcpy(&hist[(((size_t)s * Tn + t) * N + i) * R], c, sizeof(float) * R);
-        ll += (double)TR::fwd(r, x_tm + ((size_t)t * N + i) * D, x_tm + ((size_t)(t + 1) * N + i) * D, c);
+        ll += (double)TR::template fwd<float>(r, x_tm + ((size_t)t * N + i) * D, x_tm + ((size_t)(t + 1) * N + i) * D, c);
       }
       ll_out[(size_t)s * N + i] = (T)ll;
     }
@@ -123,10 +123,12 @@ int run(const LqgkDims& d, const LqgkSpec* act, const LqgkSpec* dyn, const LqgkM
         const float* c = &hist[(((size_t)s * Tn + t) * N + i) * R];
         const float* x0 = x_tm + ((size_t)t * N + i) * D;
         const float* x1 = x_tm + ((size_t)(t + 1) * N + i) * D;
-        float e[D], v[D], eb[D], cbn[R];
-        TR::rev(r, x0, x1, c, w, cb, e, v, eb, cbn);
+        float e[D], v[D], wv[D], neb[D], cbn[R];
+        TR::template rev<float>(r, x0, x1, c, w, cb, e, v, wv, neb, cbn);
         float* sm = sums.data() + ((size_t)s * Tn + t) * DM::SUMP;
-        static_for<0, DM::NSUM>([&](auto I) { sm[decltype(I)::value] += TR::template sum_term<decltype(I)::value>(cb, eb, x0, c, e, v, w); });
+        static_for<0, DM::NSUM>([&](auto I) {
+          sm[decltype(I)::value] = TR::template sum_acc<decltype(I)::value, float>(sm[decltype(I)::value], cb, neb, x0, c, e, v, wv);
+        });
         for (int j = 0; j < R; ++j) cb[j] = cbn[j];
       }
     }
