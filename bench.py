@@ -87,7 +87,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -186,6 +186,10 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = abi.load_library()
+    if args.streams > 0:
+        lib.set_streams(args.streams)
+    if args.overlap >= 0:
+        lib.set_kernel_overlap(args.overlap)
     S, N, T = args.samples, args.trials, args.T
     X = make_data(N, T)
     theta_np = make_theta(S, 11 + rank)
@@ -375,6 +379,8 @@ def main():
     ap.add_argument("--chunk", type=int, default=0, help="max samples per internal workspace chunk (0 = as many as fit)")
     ap.add_argument("--cpu-samples", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=0, help="internal concurrent sample slices (0 = library default)")
+    ap.add_argument("--overlap", type=int, default=-1, help="kernel-overlap mask (see lqgk_set_kernel_overlap); -1 = library default")
     ap.add_argument("--no-factorize", action="store_true", help="run the general 2-D (n=10) kernels instead of the per-axis factorisation")
     args = ap.parse_args()
     if args.impl == "reference":

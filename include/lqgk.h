@@ -116,6 +116,13 @@ size_t lqgk_workspace_bytes(const LqgkDims* dims, int mode, int32_t max_chunk);
 int lqgk_dims_supported(const LqgkDims* dims);
 const char* lqgk_strerror(int code);
 const char* lqgk_version(void);
+/* Number of internal concurrent sample slices (streams) used by the likelihood entry points of the calling thread
+ * (default 1 = everything on the caller's stream; 4 gives ~3 % at the benchmark size).  Work is always forked from / joined to the caller's stream. */
+int lqgk_set_streams(int n);
+/* Run the independent kernels of one chunk (lqr_fwd | kf_fwd, the two contraction passes, kf_rev | lqr_rev | reduction)
+ * concurrently on internal auxiliary streams.  mask bit 0: lqr_fwd | kf_fwd, bit 1: contraction passes, bit 2: adjoint tail;
+ * default 6. */
+int lqgk_set_kernel_overlap(int mask);
 /* Per-kernel timing for bench.py: when enabled, every kernel launch of the calling thread's entry-point calls is
  * bracketed by CUDA events on the launching stream.  lqgk_profile_read() synchronises on those events, sums the
  * elapsed milliseconds (and launch counts) per kernel kind, resets the log and returns the number of kinds:
@@ -123,6 +130,9 @@ const char* lqgk_version(void);
  * 11 cov_contrib, 12 reduce. */
 int lqgk_profile_enable(int on);
 int lqgk_profile_read(float* ms_by_kind, int32_t* launches_by_kind, int nkinds);
+/* Start / end (ms, relative to the first recorded launch) and kind of every recorded launch; returns the count.
+ * Call before lqgk_profile_read (which resets the log). */
+int lqgk_profile_timeline(float* start_ms, float* end_ms, int32_t* kind, int max_entries);
 /* Launches an FMA-saturating micro-kernel (fp64 != 0: DFMA, else FFMA) on `stream`; *flop_out = flops it executes.
  * Time it with CUDA events to obtain the measured CUDA-core peak used as the roofline denominator. `sink`: >= 8 bytes. */
 int lqgk_peak_fma(int fp64, int iters, void* sink, void* stream, double* flop_out);

@@ -107,7 +107,9 @@ class Library:
     def workspace_bytes(self, dims: LqgkDims, mode: int, max_chunk: int = 0) -> int:
         if not hasattr(self.lib, "lqgk_workspace_bytes"):
             return 0
-        return int(self.lib.lqgk_workspace_bytes(C.byref(dims), mode, max_chunk))
+        n = int(self.lib.lqgk_workspace_bytes(C.byref(dims), mode, max_chunk))
+        # slack for the per-slice alignment of the internal concurrent slices (lqgk_set_streams)
+        return n + n // 64 + (1 << 20) if n else 0
 
     @staticmethod
     def _suffix(dtype) -> str:
@@ -219,6 +221,12 @@ class Library:
     PROFILE_KINDS = ("pack", "lqr_fwd", "kf_fwd", "cov_fwd", "trial_fwd", "misc", "trial_rev", "cov_rev", "kf_rev",
                      "lqr_rev", "unpack", "cov_contrib", "reduce")
 
+    def set_streams(self, n: int):
+        self._check(self.lib.lqgk_set_streams(C.c_int(n)), "lqgk_set_streams")
+
+    def set_kernel_overlap(self, mask: int):
+        self._check(self.lib.lqgk_set_kernel_overlap(C.c_int(int(mask))), "lqgk_set_kernel_overlap")
+
     def profile_enable(self, on: bool):
         self._check(self.lib.lqgk_profile_enable(C.c_int(1 if on else 0)), "lqgk_profile_enable")
 
@@ -231,6 +239,16 @@ class Library:
         if rc < 0:
             self._check(rc, "lqgk_profile_read")
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.PROFILE_KINDS)}
+
+    def profile_timeline(self, max_entries=4096):
+        """[(kind, start_ms, end_ms)] of every launch recorded since the last profile_read."""
+        st = (C.c_float * max_entries)()
+        en = (C.c_float * max_entries)()
+        kd = (C.c_int32 * max_entries)()
+        n = self.lib.lqgk_profile_timeline(st, en, kd, C.c_int(max_entries))
+        if n < 0:
+            self._check(n, "lqgk_profile_timeline")
+        return [(self.PROFILE_KINDS[kd[i]], float(st[i]), float(en[i])) for i in range(n)]
 
     def peak_fma(self, fp64: bool, device, iters=4096, reps=5) -> float:
         """Measured CUDA-core FMA peak in TFLOP/s (best of `reps`), CUDA events on the current stream."""

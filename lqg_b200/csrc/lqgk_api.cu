@@ -14,6 +14,9 @@ using namespace lqgk;
 namespace lqgk {
 thread_local int g_launches = 0;
 thread_local Profiler g_prof;
+thread_local int g_streams = 1;
+thread_local int g_aux_streams = 6;
+thread_local StreamPool g_pool;
 }
 
 namespace {
@@ -164,10 +167,32 @@ const char* lqgk_strerror(int code) {
     default: return "unknown error";
   }
 }
+int lqgk_set_streams(int n) {
+  if (n < 1 || n > 32) return LQGK_E_INVALID;
+  g_streams = n;
+  return LQGK_OK;
+}
+int lqgk_set_kernel_overlap(int mask) {
+  if (mask < 0 || mask > 7) return LQGK_E_INVALID;
+  g_aux_streams = mask;
+  return LQGK_OK;
+}
 int lqgk_profile_enable(int on) {
   g_prof.on = on != 0;
   g_prof.used = 0;
   return LQGK_OK;
+}
+int lqgk_profile_timeline(float* start_ms, float* end_ms, int32_t* kind, int max_entries) {
+  // start/end of every recorded launch relative to the first recorded event (call before lqgk_profile_read)
+  int n = 0;
+  if (g_prof.used < 2) return 0;
+  for (size_t i = 0; i + 1 < g_prof.used && n < max_entries; i += 2, ++n) {
+    if (cudaEventSynchronize(g_prof.ev[i + 1]) != cudaSuccess) return LQGK_E_CUDA;
+    cudaEventElapsedTime(&start_ms[n], g_prof.ev[0], g_prof.ev[i]);
+    cudaEventElapsedTime(&end_ms[n], g_prof.ev[0], g_prof.ev[i + 1]);
+    kind[n] = g_prof.kinds[i / 2];
+  }
+  return n;
 }
 int lqgk_profile_read(float* ms_by_kind, int32_t* launches_by_kind, int nkinds) {
   if (!ms_by_kind || nkinds <= 0) return LQGK_E_INVALID;

@@ -49,6 +49,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// 1-D bulk async copy shared -> global (TMA store, bulk-group completion).
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 // Per-thread asynchronous global->shared copies (LDGSTS) used as a register-free software prefetch.
@@ -131,6 +140,15 @@ __global__ void __launch_bounds__(32) k_kf_fwd(const double* cst, size_t Sc, siz
   kf_fwd_body<DM>(GCst{cst + s, Sc, tstride}, WView{sm + lane, 32}, Tn, WView{K + s, Sc}, save_P != 0, WView{Pkf + s, Sc});
 }
 
+template <class KC, class La>
+__device__ __forceinline__ void flush_acc_atomic(double* g, size_t stride, const La& l, int nseg) {
+  for (int i = 0; i < nseg; ++i) {
+    int go, lo, len;
+    KC::seg(i, go, lo, len);
+    for (int e = 0; e < len; ++e) atomicAdd(&g[(size_t)(go + e) * stride], l(lo + e));
+  }
+}
+
 // ------------------------------------------------------------------------------------------- step-input ring
 // The sequential per-sample kernels are latency-bound if each step's inputs are fetched with ordinary loads (one
 // HBM round trip per dependent phase, ~1 warp per scheduler).  Instead each warp keeps a ring of NST "step input"
@@ -194,23 +212,25 @@ struct StepRing {
   }
 };
 
-// Record sink: each lane writes its sample's record into a padded shared-memory row, then the warp copies the 32
-// rows to HBM ([sample][t][REC], 128-byte coalesced stores).
+// Record sink: each lane assembles its sample's record ([REC] floats, one 16-byte-aligned row) in shared memory and
+// hands it to the TMA engine: one bulk store per lane and step into rec[sample][t][REC].  Two row buffers alternate so
+// the store of step t overlaps the arithmetic of step t+1 (no per-element copy loop, no warp synchronisation).
 template <class DM>
 struct SmemRecSink {
-  static constexpr int RS = DM::REC + 1;   // odd row stride -> lane-strided accesses hit 32 distinct banks
+  static constexpr int RS = DM::REC;          // floats per row
+  static constexpr int FLOATS = 2 * 32 * RS;  // two buffers
   float* stage;
-  float* gbase;   // rec + (first sample of this warp) * Tn * REC
-  int lane, Tn;
-  __device__ __forceinline__ void put(int idx, float v) { stage[lane * RS + idx] = v; }
+  float* gbase;   // rec + (this lane's sample) * Tn * REC
+  int lane, buf;
+  __device__ __forceinline__ void put(int idx, float v) { stage[(buf * 32 + lane) * RS + idx] = v; }
   __device__ __forceinline__ void commit(int t) {
-    __syncwarp();
-    for (int j = 0; j < 32; ++j) {
-      float* dst = gbase + ((size_t)j * Tn + t) * DM::REC;
-      for (int i = lane; i < DM::REC; i += 32) dst[i] = stage[j * RS + i];
-    }
-    __syncwarp();
+    fence_proxy_async();                       // my generic-proxy writes -> visible to the async proxy
+    bulk_s2g(gbase + (size_t)t * DM::REC, stage + (buf * 32 + lane) * RS, DM::REC * sizeof(float));
+    bulk_commit();
+    buf ^= 1;
+    bulk_wait_read<1>();                       // the buffer about to be rewritten (store of step t-1) has been read
   }
+  __device__ __forceinline__ void finish() { bulk_wait<0>(); }
 };
 
 constexpr int SEQ_NST = 3;   // ring depth of the sequential kernels
@@ -231,15 +251,16 @@ __global__ void __launch_bounds__(32) k_cov_fwd(const double* cst, size_t Sc, si
   double* ring_buf = sm;
   double* lcp = ring_buf + (size_t)SEQ_NST * ROWS * 32;
   float* stage = reinterpret_cast<float*>(lcp + C::n * 32);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage + 32 * SmemRecSink<DM>::RS + (32 * SmemRecSink<DM>::RS & 1));
-  for (int i = lane; i < 32 * SmemRecSink<DM>::RS; i += 32) stage[i] = 0.f;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage + SmemRecSink<DM>::FLOATS);
+  for (int i = lane; i < SmemRecSink<DM>::FLOATS; i += 32) stage[i] = 0.f;
+  __syncwarp();
   Ring ring{{{L + s0, DM::EL}, {K + s0, DM::EK}}, Sc, nullptr, 0, 0, 0, ring_buf, bars, lane, ROWS, ROWS * 32, 0};
   ring.init();
   for (int k = 0; k < SEQ_NST && k < Tn; ++k) ring.issue(k, k);
   WView lc{lcp + lane, 32};
   GCst g{cst + s, Sc, tstride};
   load_consts<C>(g.at(0), lc, C::NSEG);
-  SmemRecSink<DM> sink{stage, rec + s0 * Tn * DM::REC, lane, Tn};
+  SmemRecSink<DM> sink{stage, rec + s * Tn * DM::REC, lane, 0};
   double Cm[R * R];
   {
     double K0[B * Y], J0v[R * D];
@@ -269,6 +290,7 @@ __global__ void __launch_bounds__(32) k_cov_fwd(const double* cst, size_t Sc, si
                      });
     sink.commit(t);
   }
+  sink.finish();
 }
 
 // Sequential covariance adjoint: lean (no constants, no accumulators); emits Sgb_t, SF_t for the parallel contraction.
@@ -367,8 +389,8 @@ __global__ void __launch_bounds__(32) k_cov_contrib(const double* cst, size_t Sc
       LQGK_UNROLL for (int i = 0; i < U * B; ++i) Lbar[((size_t)t * DM::EL + i) * Sc + s] = Lb[i];
       LQGK_UNROLL for (int i = 0; i < B * Y; ++i) Kbar[((size_t)t * DM::EK + i) * Sc + s] = Kb[i];
     } else {
-      double Kb[B * Y];
-      LQGK_UNROLL for (int i = 0; i < B * Y; ++i) Kb[i] = Kbar[((size_t)t * DM::EK + i) * Sc + s];
+      double Kb[B * Y];                       // transition part of Kbar_t, stored separately (summed by k_kf_rev) so the
+      LQGK_UNROLL for (int i = 0; i < B * Y; ++i) Kb[i] = 0.0;   // two passes can run concurrently on different streams
       CC::pass1(lc, sf, get, Cm, Lt, Kt, out, Kb);
       LQGK_UNROLL for (int i = 0; i < B * Y; ++i) Kbar[((size_t)t * DM::EK + i) * Sc + s] = Kb[i];
     }
@@ -401,24 +423,24 @@ __global__ void __launch_bounds__(128) k_reduce_time(const double* CT, size_t Sc
     KC::seg(i, go, lo, len);
     if (e >= lo && e < lo + len) ge = go + (e - lo);
   }
-  acc[(size_t)ge * Sc + s] += (a0 + a1) + (a2 + a3);
+  atomicAdd(&acc[(size_t)ge * Sc + s], (a0 + a1) + (a2 + a3));   // other adjoint kernels add into acc concurrently
 }
 
 // Kalman-gain adjoint (sequential, t descending).  Ring inputs per step: P_t, Kbar_t.
 template <class DM>
 __global__ void __launch_bounds__(32) k_kf_rev(const double* cst, size_t Sc, int Tn, const double* Pkf, const double* Kbar,
-                                               double* acc) {
+                                               const double* KbarF, double* acc) {
   extern __shared__ __align__(128) double sm[];
   constexpr int B = DM::B, Y = DM::Y;
   using C = KfC<DM>;
-  using Ring = StepRing<2, SEQ_NST>;
-  constexpr int ROWS = DM::EP + DM::EK;
+  using Ring = StepRing<3, SEQ_NST>;
+  constexpr int ROWS = DM::EP + 2 * DM::EK;
   const int lane = threadIdx.x;
   const size_t s0 = (size_t)blockIdx.x * 32, s = s0 + lane;
   double* lcp = sm + (size_t)SEQ_NST * ROWS * 32;
   double* lap = lcp + C::n * 32;
   uint64_t* bars = reinterpret_cast<uint64_t*>(lap + C::n * 32);
-  Ring ring{{{Pkf + s0, DM::EP}, {Kbar + s0, DM::EK}}, Sc, nullptr, 0, 0, 0, sm, bars, lane, ROWS, ROWS * 32, 0};
+  Ring ring{{{Pkf + s0, DM::EP}, {Kbar + s0, DM::EK}, {KbarF + s0, DM::EK}}, Sc, nullptr, 0, 0, 0, sm, bars, lane, ROWS, ROWS * 32, 0};
   ring.init();
   for (int k = 0; k < SEQ_NST && k < Tn; ++k) ring.issue(Tn - 1 - k, k);
   WView lc{lcp + lane, 32}, la{lap + lane, 32};
@@ -433,15 +455,15 @@ __global__ void __launch_bounds__(32) k_kf_rev(const double* cst, size_t Sc, int
     double P[B * B], Kb[B * Y];
     load_sym_ws<B>(ring.view(stg, 0), 0, P);
     {
-      WView kv = ring.view(stg, DM::EP);
-      LQGK_UNROLL for (int i = 0; i < B * Y; ++i) Kb[i] = kv(i);
+      WView kv = ring.view(stg, DM::EP), kv2 = ring.view(stg, DM::EP + DM::EK);
+      LQGK_UNROLL for (int i = 0; i < B * Y; ++i) Kb[i] = kv(i) + kv2(i);
     }
     __syncwarp();
     if (kk + SEQ_NST < Tn) ring.issue(Tn - 1 - (kk + SEQ_NST), st);
     KfRev<DM>::step(lc, accf, P, Kb, Pnb);
   }
   KfRev<DM>::finish(accf, Pnb);
-  flush_acc<C>(WView{acc + s, Sc}, la, C::NSEG);
+  flush_acc_atomic<C>(acc + s, Sc, la, C::NSEG);
 }
 
 // Riccati adjoint (sequential, t ascending).  Ring inputs per step: S_{t+1}, L_t, Lbar_t.
@@ -491,13 +513,13 @@ __global__ void __launch_bounds__(32) k_lqr_rev(const double* cst, size_t Sc, in
     LqrRev<DM>::step(lc, accf, S, Lt, Lb, shift, Sn);
   }
   LqrRev<DM>::finish(accf, Sn);
-  flush_acc<C>(WView{acc + s, Sc}, la, C::NSEG);
+  flush_acc_atomic<C>(acc + s, Sc, la, C::NSEG);
 }
 
 // Dynamic shared-memory sizes of the per-sample kernels (must mirror the carve-up inside each kernel).
 template <class DM> constexpr size_t smem_cov_fwd() {
   return sizeof(double) * ((size_t)SEQ_NST * (DM::EL + DM::EK) * 32 + CovC<DM>::n * 32) +
-         sizeof(float) * (32 * SmemRecSink<DM>::RS + 2) + sizeof(uint64_t) * SEQ_NST;
+         sizeof(float) * SmemRecSink<DM>::FLOATS + sizeof(uint64_t) * SEQ_NST;
 }
 template <class DM> constexpr size_t smem_cov_seq_rev() {
   using SR = CovSeqRev<DM>;
@@ -511,7 +533,7 @@ template <class DM, int PASS> constexpr size_t smem_cov_contrib() {
          sizeof(uint64_t) * PAR_NST;
 }
 template <class DM> constexpr size_t smem_kf_rev() {
-  return sizeof(double) * ((size_t)SEQ_NST * (DM::EP + DM::EK) * 32 + 2 * KfC<DM>::n * 32) + sizeof(uint64_t) * SEQ_NST;
+  return sizeof(double) * ((size_t)SEQ_NST * (DM::EP + 2 * DM::EK) * 32 + 2 * KfC<DM>::n * 32) + sizeof(uint64_t) * SEQ_NST;
 }
 template <class DM> constexpr size_t smem_lqr_rev() {
   return sizeof(double) * ((size_t)SEQ_NST * (DM::ES + 2 * DM::EL) * 32 + 2 * LqrC<DM>::n * 32) + sizeof(uint64_t) * SEQ_NST;

@@ -23,6 +23,51 @@ struct Profiler {
   size_t used = 0;
 };
 extern thread_local Profiler g_prof;
+
+// Concurrent sample slices: the per-sample kernels are latency-bound (about one warp per scheduler), so a call splits
+// its samples into up to g_streams slices that run the whole kernel sequence concurrently on internal non-blocking
+// streams (forked from / joined to the caller's stream with events); each slice owns a part of the workspace.
+extern thread_local int g_streams;
+extern thread_local int g_aux_streams;   // bit 0: lqr_fwd | kf_fwd, bit 1: contraction passes, bit 2: kf_rev | lqr_rev | reduce
+struct StreamPool {
+  int device = -1;
+  std::vector<cudaStream_t> streams;
+  std::vector<cudaEvent_t> joins;
+  cudaEvent_t fork = nullptr;
+  std::vector<cudaEvent_t> evs;   // round-robin pool for intra-chunk dependencies (timing disabled)
+  size_t ev_next = 0;
+  cudaEvent_t next_event() {
+    if (evs.size() < 64) {
+      cudaEvent_t e;
+      cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+      evs.push_back(e);
+      return e;
+    }
+    return evs[ev_next++ % evs.size()];
+  }
+  int ensure(int n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return LQGK_E_CUDA;
+    if (dev != device) {   // one pool per thread and device; streams of another device are simply abandoned
+      streams.clear();
+      joins.clear();
+      evs.clear();
+      fork = nullptr;
+      device = dev;
+    }
+    if (!fork && cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess) return LQGK_E_CUDA;
+    while ((int)streams.size() < n) {
+      cudaStream_t st;
+      cudaEvent_t ev;
+      if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return LQGK_E_CUDA;
+      if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return LQGK_E_CUDA;
+      streams.push_back(st);
+      joins.push_back(ev);
+    }
+    return LQGK_OK;
+  }
+};
+extern thread_local StreamPool g_pool;
 struct ProfScope {
   cudaStream_t st;
   bool active;
@@ -67,7 +112,7 @@ inline bool spec_time_varying(const LqgkSpec& s, bool actor) {
 struct Plan {
   size_t Sc = 0, bytes = 0;
   size_t cst = 0, acc = 0, L = 0, K = 0, l = 0, H = 0, Sric = 0, Pkf = 0, Cs = 0, Lbar = 0, Kbar = 0, rec = 0, ll = 0,
-         sums = 0, hist = 0, w = 0, FU = 0, JS = 0, J0 = 0, SGB = 0, SGBI = 0, SFW = 0, CT = 0;
+         sums = 0, hist = 0, w = 0, FU = 0, JS = 0, J0 = 0, SGB = 0, SGBI = 0, SFW = 0, CT = 0, KbarF = 0;
 };
 
 template <class DM>
@@ -95,6 +140,7 @@ Plan make_plan(const LqgkDims& d, int mode, bool tv, size_t Sc) {
     p.Cs = take(sizeof(double) * T * DM::EC * Sc);
     p.Lbar = take(sizeof(double) * T * DM::EL * Sc);
     p.Kbar = take(sizeof(double) * T * DM::EK * Sc);
+    p.KbarF = take(sizeof(double) * T * DM::EK * Sc);
     p.sums = take(sizeof(float) * Sc * T * DM::SUMP);
     p.hist = take(sizeof(float) * Sc * T * DM::R * N);
     p.w = take(sizeof(float) * Sc * N);
@@ -184,13 +230,52 @@ int run(const Call& c) {
   const bool tv = spec_time_varying(*c.act, true) || (has_dyn && spec_time_varying(*c.dyn, false));
   if (tv && c.mode == LQGK_MODE_VJP) return LQGK_E_UNSUPPORTED;
   if (!c.ws || ((uintptr_t)c.ws % ALIGN) != 0) return LQGK_E_INVALID;
-  const size_t Sc = choose_chunk<DM>(d, c.mode, tv, c.ws_bytes, 0);
+  // slices: ns concurrent streams, each with its own workspace part and chunk size Sc
+  int ns = c.mode == LQGK_MODE_GAINS ? 1 : std::max(1, std::min(g_streams, (int)((d.S + 31) / 32)));
+  size_t Sc = 0;
+  for (; ns >= 1; --ns) {
+    const int32_t want = (int32_t)up(((size_t)d.S + ns - 1) / ns, 32);
+    Sc = choose_chunk<DM>(d, c.mode, tv, c.ws_bytes / ns / ALIGN * ALIGN, want);
+    if (Sc > 0) break;
+  }
   if (Sc == 0) return LQGK_E_WORKSPACE;
   const Plan p = make_plan<DM>(d, c.mode, tv, Sc);
+  const size_t slice_bytes = up(p.bytes, ALIGN);
   char* base = (char*)c.ws;
   auto D = [&](size_t off) { return (double*)(base + off); };
   auto F = [&](size_t off) { return (float*)(base + off); };
   cudaStream_t st = c.stream;
+  const int auxm = c.mode == LQGK_MODE_VJP ? g_aux_streams : 0;
+  const bool aux = auxm != 0;
+  const int nstreams = (ns > 1 ? ns : 0) + (aux ? 2 * ns : 0);
+  if (nstreams > 0) {
+    if (int rcp = g_pool.ensure(nstreams)) return rcp;
+  }
+  const int aux0 = ns > 1 ? ns : 0;     // index of the first auxiliary stream
+  // make `to` wait for everything enqueued on `from` so far
+  auto dep = [&](cudaStream_t from, cudaStream_t to) {
+    if (from == to) return;
+    cudaEvent_t e = g_pool.next_event();
+    cudaEventRecord(e, from);
+    cudaStreamWaitEvent(to, e, 0);
+  };
+  if (ns > 1) {
+    if (cudaEventRecord(g_pool.fork, c.stream) != cudaSuccess) return LQGK_E_CUDA;
+    for (int i = 0; i < ns; ++i)
+      if (cudaStreamWaitEvent(g_pool.streams[i], g_pool.fork, 0) != cudaSuccess) return LQGK_E_CUDA;
+  }
+  // join on every exit path once side streams may have work
+  struct Joiner {
+    int ns, nstreams;
+    cudaStream_t main;
+    ~Joiner() {
+      // slice streams (and, on error paths, auxiliary streams) rejoin the caller's stream
+      for (int i = 0; i < nstreams; ++i) {
+        cudaEventRecord(g_pool.joins[i], g_pool.streams[i]);
+        cudaStreamWaitEvent(main, g_pool.joins[i], 0);
+      }
+    }
+  } joiner{ns, nstreams, c.stream};
   const int Tn = d.T, N = d.N;
   const size_t tstride = tv ? (size_t)cl.total * Sc : 0;
 
@@ -200,10 +285,19 @@ int run(const Call& c) {
   pa.sigma0 = c.sigma0 ? *c.sigma0 : LqgkMat{nullptr, 0, 0};
   pa.x = DM::X; pa.b = DM::B; pa.u = DM::U; pa.y = DM::Y; pa.nT = Tn; pa.has_dyn = has_dyn;
 
-  for (size_t s0 = 0; s0 < (size_t)d.S; s0 += Sc) {
+  int chunk_idx = 0;
+  for (size_t s0 = 0; s0 < (size_t)d.S; s0 += Sc, ++chunk_idx) {
     const int n = (int)std::min(Sc, (size_t)d.S - s0);
     const int npad = (int)up(n, 32);
     const int nblk = npad / 32;
+    if (ns > 1) {
+      st = g_pool.streams[chunk_idx % ns];
+      base = (char*)c.ws + (size_t)(chunk_idx % ns) * slice_bytes;
+    }
+    // auxiliary streams of this slice: independent kernels of one chunk run concurrently (they are latency-bound)
+    cudaStream_t x1 = aux ? g_pool.streams[aux0 + 2 * (chunk_idx % ns)] : st;
+    cudaStream_t x2 = aux ? g_pool.streams[aux0 + 2 * (chunk_idx % ns) + 1] : st;
+    cudaStream_t a1 = (auxm & 1) ? x1 : st, a2 = st;
     {
       dim3 grid((npad + 127) / 128, tv ? Tn : 1);
       ProfScope ps_(PK_PACK, st);
@@ -241,6 +335,7 @@ int run(const Call& c) {
     }
     const bool vjp = c.mode == LQGK_MODE_VJP;
     int rc;
+    dep(st, a1);                                   // pack done -> kf_fwd (a1) may run beside lqr_fwd (st)
     {
       size_t smem = sizeof(double) * 32 * LqrC<DM>::n;
       ProfScope ps_(PK_LQR_FWD, st);
@@ -249,10 +344,11 @@ int run(const Call& c) {
     }
     {
       size_t smem = sizeof(double) * 32 * KfC<DM>::n;
-      ProfScope ps_(PK_KF_FWD, st);
-      k_kf_fwd<DM><<<nblk, 32, smem, st>>>(D(p.cst), Sc, tstride, Tn, D(p.K), vjp, vjp ? D(p.Pkf) : nullptr);
+      ProfScope ps_(PK_KF_FWD, a1);
+      k_kf_fwd<DM><<<nblk, 32, smem, a1>>>(D(p.cst), Sc, tstride, Tn, D(p.K), vjp, vjp ? D(p.Pkf) : nullptr);
       LQGK_LAUNCH_CHECK();
     }
+    dep(a1, st);
     {
       size_t smem = smem_cov_fwd<DM>();
       if ((rc = set_smem<DM>((const void*)k_cov_fwd<DM>, smem))) return rc;
@@ -311,6 +407,8 @@ int run(const Call& c) {
       // (sample-group x time-range) warps: enough to occupy every SM a few times over
       int chunks = std::max(1, std::min((Tn + 7) / 8, (148 * 4 + nblk - 1) / nblk));
       dim3 grid(nblk, chunks);
+      a1 = (auxm & 2) ? x1 : st;
+      dep(st, a1);                                 // cov_seq_rev done -> the two contraction passes run side by side
       {
         ProfScope ps_(PK_COV_CONTRIB, st);
         k_cov_contrib<DM, 0><<<grid, 32, smem0, st>>>(D(p.cst), Sc, Tn, D(p.L), D(p.K), D(p.Cs), D(p.SGB), D(p.SGBI), D(p.SFW), F(p.sums),
@@ -318,32 +416,50 @@ int run(const Call& c) {
         LQGK_LAUNCH_CHECK();
       }
       {
-        ProfScope ps_(PK_COV_CONTRIB, st);
-        k_cov_contrib<DM, 1><<<grid, 32, smem1, st>>>(D(p.cst), Sc, Tn, D(p.L), D(p.K), D(p.Cs), D(p.SGB), D(p.SGBI), D(p.SFW), F(p.sums),
-                                                     D(p.CT), D(p.Lbar), D(p.Kbar));
-        LQGK_LAUNCH_CHECK();
-      }
-      {
-        ProfScope ps_(PK_REDUCE, st);
-        dim3 rgrid((unsigned)((Sc + 127) / 128), CovC<DM>::n);
-        k_reduce_time<CovC<DM>><<<rgrid, 128, 0, st>>>(D(p.CT), Sc, Tn, D(p.acc));
+        ProfScope ps_(PK_COV_CONTRIB, a1);
+        k_cov_contrib<DM, 1><<<grid, 32, smem1, a1>>>(D(p.cst), Sc, Tn, D(p.L), D(p.K), D(p.Cs), D(p.SGB), D(p.SGBI), D(p.SFW), F(p.sums),
+                                                     D(p.CT), D(p.Lbar), D(p.KbarF));
         LQGK_LAUNCH_CHECK();
       }
     }
+    cudaEvent_t pass1_done = nullptr;
+    if (a1 != st) {
+      pass1_done = g_pool.next_event();
+      cudaEventRecord(pass1_done, a1);
+    }
+    if (!(auxm & 4)) {                             // no tail overlap: fold everything back onto st
+      dep(a1, st);
+      a1 = st;
+      pass1_done = nullptr;
+    } else {
+      a1 = x1;
+      a2 = x2;
+    }
+    dep(st, a2);                                   // pass 0 done -> Lbar complete -> Riccati adjoint on a2
+    {
+      size_t smem = smem_lqr_rev<DM>();
+      if ((rc = set_smem<DM>((const void*)k_lqr_rev<DM>, smem))) return rc;
+      ProfScope ps_(PK_LQR_REV, a2);
+      k_lqr_rev<DM><<<nblk, 32, smem, a2>>>(D(p.cst), Sc, Tn, c.eps, D(p.L), D(p.Sric), D(p.Lbar), D(p.acc));
+      LQGK_LAUNCH_CHECK();
+    }
+    dep(st, a1);                                   // both passes done on a1 -> time reduction of the contributions
+    {
+      ProfScope ps_(PK_REDUCE, a1);
+      dim3 rgrid((unsigned)((Sc + 127) / 128), CovC<DM>::n);
+      k_reduce_time<CovC<DM>><<<rgrid, 128, 0, a1>>>(D(p.CT), Sc, Tn, D(p.acc));
+      LQGK_LAUNCH_CHECK();
+    }
+    if (pass1_done) cudaStreamWaitEvent(st, pass1_done, 0);   // Kbar parts complete -> Kalman adjoint on st
     {
       size_t smem = smem_kf_rev<DM>();
       if ((rc = set_smem<DM>((const void*)k_kf_rev<DM>, smem))) return rc;
       ProfScope ps_(PK_KF_REV, st);
-      k_kf_rev<DM><<<nblk, 32, smem, st>>>(D(p.cst), Sc, Tn, D(p.Pkf), D(p.Kbar), D(p.acc));
+      k_kf_rev<DM><<<nblk, 32, smem, st>>>(D(p.cst), Sc, Tn, D(p.Pkf), D(p.Kbar), D(p.KbarF), D(p.acc));
       LQGK_LAUNCH_CHECK();
     }
-    {
-      size_t smem = smem_lqr_rev<DM>();
-      if ((rc = set_smem<DM>((const void*)k_lqr_rev<DM>, smem))) return rc;
-      ProfScope ps_(PK_LQR_REV, st);
-      k_lqr_rev<DM><<<nblk, 32, smem, st>>>(D(p.cst), Sc, Tn, c.eps, D(p.L), D(p.Sric), D(p.Lbar), D(p.acc));
-      LQGK_LAUNCH_CHECK();
-    }
+    dep(a1, st);
+    dep(a2, st);
     {
       UnpackArgs<T> ua{};
       ua.act = *c.act; ua.dyn = *c.dyn; ua.sigma0 = pa.sigma0;
