@@ -3,8 +3,8 @@
 next to the reference algorithm on the host CPU.
 
 Workload (config c3 of BASELINE.json): SubjectiveActor 2-D tracking, N=100 trials x T=1200, a sweep of
-S parameter samples PER GPU (default 16,384; weak scaling: N GPUs evaluate N*S samples; 8 GPUs x 8,192 = the
-65,536-sample target).  One "step" = one log-likelihood + parameter-gradient evaluation of all S samples
+S parameter samples PER GPU (default 32,768 = half of the 65,536-sample target on every GPU; weak scaling: N GPUs
+evaluate N*S samples per step).  One "step" = one log-likelihood + parameter-gradient evaluation of all S samples
 (S*100 trial evals).  Data are synthetic (float64 restatement of System.simulate, NumPy PCG64 seed 7); parameter
 samples are theta_true * exp(0.25 z), z ~ N(0, I_6), seed 11 + rank.
 
@@ -373,7 +373,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--samples", type=int, default=16384, help="parameter samples per GPU per step")
+    ap.add_argument("--samples", type=int, default=32768, help="parameter samples per GPU per step")
     ap.add_argument("--trials", type=int, default=100)
     ap.add_argument("--T", type=int, default=1200)
     ap.add_argument("--chunk", type=int, default=0, help="max samples per internal workspace chunk (0 = as many as fit)")

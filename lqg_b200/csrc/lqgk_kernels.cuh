@@ -332,27 +332,33 @@ __global__ void __launch_bounds__(32) k_cov_seq_rev(size_t Sc, int Tn, int N, co
 }
 
 // Time-parallel contraction.  grid = (Sc / 32, chunks), block = one warp owning a contiguous range of time steps of
-// its 32 samples.  Ring inputs per step: L_t, K_t, C_t, (Sgb_t,) SF_t and the trial sums F-block.
+// its 32 samples.  Ring inputs per step: L_t, K_t, C_t, SF_t (, Sgb_t) and the trial sums F-block.  The contributions
+// to the derived-constant cotangents are accumulated over the warp's time range in shared memory ([element][lane])
+// and added to the global accumulators with one atomicAdd per element at the end.
+// PASS 0 / 1: the two register-limited halves (run concurrently on two streams); PASS 2: both in one kernel (small systems).
 constexpr int PAR_NST = 2;
+template <class DM>
+__host__ __device__ constexpr bool contrib_merged() { return DM::N <= 6; }
 template <class DM, int PASS>
 __global__ void __launch_bounds__(32) k_cov_contrib(const double* cst, size_t Sc, int Tn, const double* L, const double* K,
                                                     const double* Cs, const double* SGB, const double* SGBI, const double* SFW,
-                                                    const float* sums, double* CT, double* Lbar, double* Kbar) {
+                                                    const float* sums, double* acc, double* Lbar, double* Kbar, double* KbarF) {
   extern __shared__ __align__(128) double sm[];
   constexpr int B = DM::B, U = DM::U, Y = DM::Y, R = DM::R;
   using SR = CovSeqRev<DM>;
   using CC = CovContrib<DM>;
   using C = CovC<DM>;
-  constexpr int NSRC = PASS == 0 ? 5 : 4;
+  constexpr bool P0 = PASS == 0 || PASS == 2, P1 = PASS == 1 || PASS == 2;
+  constexpr int NSRC = P0 ? 5 : 4;
   using Ring = StepRing<NSRC, PAR_NST>;
-  constexpr int ROWS = DM::EL + DM::EK + DM::EC + SR::NSF + (PASS == 0 ? SR::NSGB : 0);
+  constexpr int ROWS = DM::EL + DM::EK + DM::EC + SR::NSF + (P0 ? SR::NSGB : 0);
   constexpr int FCNT = DM::SUM_J;   // = round4(N*N)
   constexpr int STAGE = Ring::stage_size(ROWS, FCNT);
-  constexpr int NC = C::n;
   const int lane = threadIdx.x;
   const size_t s0 = (size_t)blockIdx.x * 32, s = s0 + lane;
   double* lcp = sm + (size_t)PAR_NST * STAGE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(lcp + C::n * 32);
+  double* lap = lcp + C::n * 32;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(lap + C::n * 32);
   const int nq = gridDim.y, q = blockIdx.y;
   const int per = (Tn + nq - 1) / nq;
   const int t0 = min(Tn, q * per), t1 = min(Tn, t0 + per);
@@ -362,13 +368,14 @@ __global__ void __launch_bounds__(32) k_cov_contrib(const double* cst, size_t Sc
   ring.src[1] = {K + s0, DM::EK};
   ring.src[2] = {Cs + s0, DM::EC};
   ring.src[3] = {SFW + s0, SR::NSF};
-  if constexpr (PASS == 0) ring.src[4] = {SGB + s0, SR::NSGB};
+  if constexpr (P0) ring.src[4] = {SGB + s0, SR::NSGB};
   ring.Sc = Sc; ring.fsrc = sums + s0 * Tn * DM::SUMP; ring.frow_stride = Tn * DM::SUMP; ring.fstep_stride = DM::SUMP;
   ring.fcnt = FCNT; ring.buf = sm; ring.bars = bars; ring.lane = lane; ring.total_rows = ROWS; ring.stage_doubles = STAGE;
   ring.init();
   for (int k = 0; k < PAR_NST && t0 + k < t1; ++k) ring.issue(t0 + k, k);
-  WView lc{lcp + lane, 32};
+  WView lc{lcp + lane, 32}, la{lap + lane, 32};
   load_consts<C>(WView{const_cast<double*>(cst) + s, Sc}, lc, C::NSEG);
+  for (int e = 0; e < C::n; ++e) la(e) = 0.0;
   for (int t = t0; t < t1; ++t) {
     const int st = (t - t0) % PAR_NST;
     const double* stg = ring.wait(st);
@@ -381,49 +388,28 @@ __global__ void __launch_bounds__(32) k_cov_contrib(const double* cst, size_t Sc
     load_sym_ws<R>(cvw, 0, Cm);
     auto sf = [&](int e) { return sfv(e); };
     auto get = [&](int idx) { return fr[idx]; };
-    auto out = [&](int e, double v) { CT[((size_t)t * NC + e) * Sc + s] = v; };
-    if constexpr (PASS == 0) {
-      double Lb[U * B], Kb[B * Y];
+    auto out = [&](int e, double v) { la(e) += v; };
+    double Kb[B * Y];
+    if constexpr (P0) {
+      double Lb[U * B];
       CC::pass0(lc, [&](int e) { return sgv(e); }, t == 0, [&](int e) { return SGBI[(size_t)e * Sc + s]; }, sf, get, Cm, Lt, Kt, out,
                 Lb, Kb);
       LQGK_UNROLL for (int i = 0; i < U * B; ++i) Lbar[((size_t)t * DM::EL + i) * Sc + s] = Lb[i];
-      LQGK_UNROLL for (int i = 0; i < B * Y; ++i) Kbar[((size_t)t * DM::EK + i) * Sc + s] = Kb[i];
+      if constexpr (!P1) { LQGK_UNROLL for (int i = 0; i < B * Y; ++i) Kbar[((size_t)t * DM::EK + i) * Sc + s] = Kb[i]; }
     } else {
-      double Kb[B * Y];                       // transition part of Kbar_t, stored separately (summed by k_kf_rev) so the
-      LQGK_UNROLL for (int i = 0; i < B * Y; ++i) Kb[i] = 0.0;   // two passes can run concurrently on different streams
+      LQGK_UNROLL for (int i = 0; i < B * Y; ++i) Kb[i] = 0.0;
+    }
+    if constexpr (P1) {
       CC::pass1(lc, sf, get, Cm, Lt, Kt, out, Kb);
-      LQGK_UNROLL for (int i = 0; i < B * Y; ++i) Kbar[((size_t)t * DM::EK + i) * Sc + s] = Kb[i];
+      // PASS 1 alone stores the transition part separately (k_kf_rev adds the two parts); PASS 2 stores the total
+      double* dst = PASS == 1 ? KbarF : Kbar;
+      LQGK_UNROLL for (int i = 0; i < B * Y; ++i) dst[((size_t)t * DM::EK + i) * Sc + s] = Kb[i];
+      if constexpr (PASS == 2) { LQGK_UNROLL for (int i = 0; i < B * Y; ++i) KbarF[((size_t)t * DM::EK + i) * Sc + s] = 0.0; }
     }
     __syncwarp();
     if (t + PAR_NST < t1) ring.issue(t + PAR_NST, st);
   }
-}
-
-// Sum the per-step contributions over time into the (global-layout) cotangent accumulators:
-// acc[gmap(e)][s] += sum_t CT[t][e][s].  grid = (ceil(Sc / 128), NC), block = 128.
-template <class KC>
-__global__ void __launch_bounds__(128) k_reduce_time(const double* CT, size_t Sc, int Tn, double* acc) {
-  const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int e = blockIdx.y;
-  if (s >= Sc) return;
-  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-  const size_t stride = (size_t)KC::n * Sc;
-  const double* p = CT + (size_t)e * Sc + s;
-  int t = 0;
-  for (; t + 4 <= Tn; t += 4) {
-    a0 += p[(size_t)t * stride];
-    a1 += p[(size_t)(t + 1) * stride];
-    a2 += p[(size_t)(t + 2) * stride];
-    a3 += p[(size_t)(t + 3) * stride];
-  }
-  for (; t < Tn; ++t) a0 += p[(size_t)t * stride];
-  int ge = -1;
-  for (int i = 0; i < KC::NSEG; ++i) {
-    int go, lo, len;
-    KC::seg(i, go, lo, len);
-    if (e >= lo && e < lo + len) ge = go + (e - lo);
-  }
-  atomicAdd(&acc[(size_t)ge * Sc + s], (a0 + a1) + (a2 + a3));   // other adjoint kernels add into acc concurrently
+  flush_acc_atomic<C>(acc + s, Sc, la, C::NSEG);
 }
 
 // Kalman-gain adjoint (sequential, t descending).  Ring inputs per step: P_t, Kbar_t.
@@ -528,8 +514,8 @@ template <class DM> constexpr size_t smem_cov_seq_rev() {
 }
 template <class DM, int PASS> constexpr size_t smem_cov_contrib() {
   using SR = CovSeqRev<DM>;
-  constexpr int ROWS = DM::EL + DM::EK + DM::EC + SR::NSF + (PASS == 0 ? SR::NSGB : 0);
-  return sizeof(double) * ((size_t)PAR_NST * StepRing<5, PAR_NST>::stage_size(ROWS, DM::SUM_J) + CovC<DM>::n * 32) +
+  constexpr int ROWS = DM::EL + DM::EK + DM::EC + SR::NSF + (PASS != 1 ? SR::NSGB : 0);
+  return sizeof(double) * ((size_t)PAR_NST * StepRing<5, PAR_NST>::stage_size(ROWS, DM::SUM_J) + 2 * CovC<DM>::n * 32) +
          sizeof(uint64_t) * PAR_NST;
 }
 template <class DM> constexpr size_t smem_kf_rev() {

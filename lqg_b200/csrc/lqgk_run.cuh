@@ -112,7 +112,7 @@ inline bool spec_time_varying(const LqgkSpec& s, bool actor) {
 struct Plan {
   size_t Sc = 0, bytes = 0;
   size_t cst = 0, acc = 0, L = 0, K = 0, l = 0, H = 0, Sric = 0, Pkf = 0, Cs = 0, Lbar = 0, Kbar = 0, rec = 0, ll = 0,
-         sums = 0, hist = 0, w = 0, FU = 0, JS = 0, J0 = 0, SGB = 0, SGBI = 0, SFW = 0, CT = 0, KbarF = 0;
+         sums = 0, hist = 0, w = 0, FU = 0, JS = 0, J0 = 0, SGB = 0, SGBI = 0, SFW = 0, KbarF = 0;
 };
 
 template <class DM>
@@ -151,7 +151,6 @@ Plan make_plan(const LqgkDims& d, int mode, bool tv, size_t Sc) {
     p.SGB = take(sizeof(double) * T * SR::NSGB * Sc);
     p.SGBI = take(sizeof(double) * SR::NSGB * Sc);
     p.SFW = take(sizeof(double) * T * SR::NSF * Sc);
-    p.CT = take(sizeof(double) * T * CovC<DM>::n * Sc);
   }
   p.bytes = off;
   return p;
@@ -401,25 +400,34 @@ int run(const Call& c) {
       LQGK_LAUNCH_CHECK();
     }
     {
-      size_t smem0 = smem_cov_contrib<DM, 0>(), smem1 = smem_cov_contrib<DM, 1>();
-      if ((rc = set_smem<DM>((const void*)k_cov_contrib<DM, 0>, smem0))) return rc;
-      if ((rc = set_smem<DM>((const void*)k_cov_contrib<DM, 1>, smem1))) return rc;
       // (sample-group x time-range) warps: enough to occupy every SM a few times over
       int chunks = std::max(1, std::min((Tn + 7) / 8, (148 * 4 + nblk - 1) / nblk));
       dim3 grid(nblk, chunks);
-      a1 = (auxm & 2) ? x1 : st;
-      dep(st, a1);                                 // cov_seq_rev done -> the two contraction passes run side by side
-      {
+      if constexpr (contrib_merged<DM>()) {
+        size_t smem = smem_cov_contrib<DM, 2>();
+        if ((rc = set_smem<DM>((const void*)k_cov_contrib<DM, 2>, smem))) return rc;
         ProfScope ps_(PK_COV_CONTRIB, st);
-        k_cov_contrib<DM, 0><<<grid, 32, smem0, st>>>(D(p.cst), Sc, Tn, D(p.L), D(p.K), D(p.Cs), D(p.SGB), D(p.SGBI), D(p.SFW), F(p.sums),
-                                                     D(p.CT), D(p.Lbar), D(p.Kbar));
+        k_cov_contrib<DM, 2><<<grid, 32, smem, st>>>(D(p.cst), Sc, Tn, D(p.L), D(p.K), D(p.Cs), D(p.SGB), D(p.SGBI), D(p.SFW), F(p.sums),
+                                                    D(p.acc), D(p.Lbar), D(p.Kbar), D(p.KbarF));
         LQGK_LAUNCH_CHECK();
-      }
-      {
-        ProfScope ps_(PK_COV_CONTRIB, a1);
-        k_cov_contrib<DM, 1><<<grid, 32, smem1, a1>>>(D(p.cst), Sc, Tn, D(p.L), D(p.K), D(p.Cs), D(p.SGB), D(p.SGBI), D(p.SFW), F(p.sums),
-                                                     D(p.CT), D(p.Lbar), D(p.KbarF));
-        LQGK_LAUNCH_CHECK();
+      } else {
+        size_t smem0 = smem_cov_contrib<DM, 0>(), smem1 = smem_cov_contrib<DM, 1>();
+        if ((rc = set_smem<DM>((const void*)k_cov_contrib<DM, 0>, smem0))) return rc;
+        if ((rc = set_smem<DM>((const void*)k_cov_contrib<DM, 1>, smem1))) return rc;
+        a1 = (auxm & 2) ? x1 : st;
+        dep(st, a1);                               // cov_seq_rev done -> the two contraction passes run side by side
+        {
+          ProfScope ps_(PK_COV_CONTRIB, st);
+          k_cov_contrib<DM, 0><<<grid, 32, smem0, st>>>(D(p.cst), Sc, Tn, D(p.L), D(p.K), D(p.Cs), D(p.SGB), D(p.SGBI), D(p.SFW),
+                                                       F(p.sums), D(p.acc), D(p.Lbar), D(p.Kbar), D(p.KbarF));
+          LQGK_LAUNCH_CHECK();
+        }
+        {
+          ProfScope ps_(PK_COV_CONTRIB, a1);
+          k_cov_contrib<DM, 1><<<grid, 32, smem1, a1>>>(D(p.cst), Sc, Tn, D(p.L), D(p.K), D(p.Cs), D(p.SGB), D(p.SGBI), D(p.SFW),
+                                                       F(p.sums), D(p.acc), D(p.Lbar), D(p.Kbar), D(p.KbarF));
+          LQGK_LAUNCH_CHECK();
+        }
       }
     }
     cudaEvent_t pass1_done = nullptr;
@@ -441,13 +449,6 @@ int run(const Call& c) {
       if ((rc = set_smem<DM>((const void*)k_lqr_rev<DM>, smem))) return rc;
       ProfScope ps_(PK_LQR_REV, a2);
       k_lqr_rev<DM><<<nblk, 32, smem, a2>>>(D(p.cst), Sc, Tn, c.eps, D(p.L), D(p.Sric), D(p.Lbar), D(p.acc));
-      LQGK_LAUNCH_CHECK();
-    }
-    dep(st, a1);                                   // both passes done on a1 -> time reduction of the contributions
-    {
-      ProfScope ps_(PK_REDUCE, a1);
-      dim3 rgrid((unsigned)((Sc + 127) / 128), CovC<DM>::n);
-      k_reduce_time<CovC<DM>><<<rgrid, 128, 0, a1>>>(D(p.CT), Sc, Tn, D(p.acc));
       LQGK_LAUNCH_CHECK();
     }
     if (pass1_done) cudaStreamWaitEvent(st, pass1_done, 0);   // Kbar parts complete -> Kalman adjoint on st

@@ -19,8 +19,8 @@ from lqg_b200 import abi
 from lqg_b200.dims import SUPPORTED_DIMS
 from lqg_b200.spec import LQGSpec
 
-WORKSPACE_FRACTION = 0.6          # of currently free device memory, upper bound for the cached workspace
-WORKSPACE_MAX_BYTES = 96 << 30
+WORKSPACE_FRACTION = 0.85         # of currently free device memory, upper bound for the cached workspace
+WORKSPACE_MAX_BYTES = 150 << 30   # B200: 180 GB HBM3e; more samples in flight = better latency hiding in the per-sample kernels
 _WS: Dict[int, torch.Tensor] = {}
 
 ACT_KEYS = abi.ACTOR_KEYS
