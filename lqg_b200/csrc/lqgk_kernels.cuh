@@ -336,9 +336,16 @@ __global__ void __launch_bounds__(32) k_cov_seq_rev(size_t Sc, int Tn, int N, co
 // to the derived-constant cotangents are accumulated over the warp's time range in shared memory ([element][lane])
 // and added to the global accumulators with one atomicAdd per element at the end.
 // PASS 0 / 1: the two register-limited halves (run concurrently on two streams); PASS 2: both in one kernel (small systems).
-constexpr int PAR_NST = 2;
 template <class DM>
 __host__ __device__ constexpr bool contrib_merged() { return DM::N <= 6; }
+// ring depth of the contraction kernels: 2 stages when they fit in shared memory beside the constants, else 1
+template <class DM, int PASS>
+__host__ __device__ constexpr int contrib_nst() {
+  using SR = CovSeqRev<DM>;
+  constexpr int ROWS = DM::EL + DM::EK + DM::EC + SR::NSF + (PASS != 1 ? SR::NSGB : 0);
+  constexpr size_t two = sizeof(double) * ((size_t)2 * (ROWS * 32 + 16 * DM::SUM_J) + 2 * CovC<DM>::n * 32);
+  return two <= 200 * 1024 ? 2 : 1;
+}
 template <class DM, int PASS>
 __global__ void __launch_bounds__(32) k_cov_contrib(const double* cst, size_t Sc, int Tn, const double* L, const double* K,
                                                     const double* Cs, const double* SGB, const double* SGBI, const double* SFW,
@@ -350,6 +357,7 @@ __global__ void __launch_bounds__(32) k_cov_contrib(const double* cst, size_t Sc
   using C = CovC<DM>;
   constexpr bool P0 = PASS == 0 || PASS == 2, P1 = PASS == 1 || PASS == 2;
   constexpr int NSRC = P0 ? 5 : 4;
+  constexpr int PAR_NST = contrib_nst<DM, PASS>();
   using Ring = StepRing<NSRC, PAR_NST>;
   constexpr int ROWS = DM::EL + DM::EK + DM::EC + SR::NSF + (P0 ? SR::NSGB : 0);
   constexpr int FCNT = DM::SUM_J;   // = round4(N*N)
@@ -515,6 +523,7 @@ template <class DM> constexpr size_t smem_cov_seq_rev() {
 template <class DM, int PASS> constexpr size_t smem_cov_contrib() {
   using SR = CovSeqRev<DM>;
   constexpr int ROWS = DM::EL + DM::EK + DM::EC + SR::NSF + (PASS != 1 ? SR::NSGB : 0);
+  constexpr int PAR_NST = contrib_nst<DM, PASS>();
   return sizeof(double) * ((size_t)PAR_NST * StepRing<5, PAR_NST>::stage_size(ROWS, DM::SUM_J) + 2 * CovC<DM>::n * 32) +
          sizeof(uint64_t) * PAR_NST;
 }

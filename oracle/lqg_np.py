@@ -244,6 +244,21 @@ def point_mass_mats(process_noise=1.0, action_variability=1e-3, sigma_target=6.0
     return act, dict(act)
 
 
+def hand_model_mats(process_noise=1.0, action_variability=0.5, sigma_target=6.0, sigma_cursor=6.0, action_cost=1.0,
+                    dt=1.0 / 60.0, m=1.0, tau=0.04, position_noise=0.0):
+    """notebooks/HandModel.ipynb cell 2 (HandMotionModelTrackingTask); position_noise is this repo's regulariser."""
+    A = np.zeros((5, 5)); A[0, 0] = 1.0
+    A[1:, 1:] = [[1.0, dt, 0.0, 0.0], [0.0, 1.0, dt / m, 0.0], [0.0, 0.0, 1.0 - dt / tau, dt / tau], [0.0, 0.0, 0.0, 1.0 - dt / tau]]
+    B = np.zeros((5, 1)); B[4, 0] = dt / tau
+    F = np.eye(2, 5)
+    V = np.diag([process_noise, position_noise, 0.0, 0.0, action_variability])
+    W = np.diag([sigma_target, sigma_cursor])
+    Q = np.zeros((5, 5)); Q[:2, :2] = [[1.0, -1.0], [-1.0, 1.0]]
+    R = np.eye(1) * action_cost
+    act = dict(A=A, B=B, F=F, V=V, W=W, Q=Q, R=R)
+    return act, dict(act)
+
+
 def delay_mats(mats, delay):
     """lqg/tracking/delay.py:9-33 applied to base matrices (shift-register augmentation)."""
     A, B, F, V, W, Q, R = (mats[k] for k in ("A", "B", "F", "V", "W", "Q", "R"))

@@ -21,22 +21,27 @@ def model_mats(name, **kw):
     return {"bounded": O.bounded_actor_mats, "bounded2": lambda **k: O.bounded_actor_mats(dim=2, **k),
             "subjective": O.subjective_actor_mats, "subjective2": lambda **k: O.subjective_actor_mats(dim=2, **k),
             "relobs": O.relative_observation_mats, "relobs2": lambda **k: O.relative_observation_mats(dim=2, **k),
-            "pointmass": O.point_mass_mats}[name](**kw)
+            "pointmass": O.point_mass_mats,
+            "hand": lambda **k: O.hand_model_mats(position_noise=0.3, **k),
+            "delay2": lambda **k: tuple(O.delay_mats(m, 2) for m in O.bounded_actor_mats(**k))}[name](**kw)
 
 
 MODEL_DIMS = {"bounded": (2, 2, 1, 2), "bounded2": (4, 4, 2, 4), "subjective": (2, 3, 1, 2), "subjective2": (4, 6, 2, 4),
-              "relobs": (2, 2, 1, 1), "relobs2": (4, 4, 2, 2), "pointmass": (4, 4, 1, 3)}
+              "relobs": (2, 2, 1, 1), "relobs2": (4, 4, 2, 2), "pointmass": (4, 4, 1, 3), "hand": (5, 5, 1, 2), "delay2": (6, 6, 1, 2)}
 MODEL_PARAMS = {"bounded": ("action_variability", "sigma_target", "sigma_cursor", "action_cost"),
                 "subjective": ("action_variability", "sigma_target", "sigma_cursor", "action_cost", "subj_noise",
                                "subj_vel_noise"),
                 "relobs": ("action_variability", "sigma", "action_cost"),
-                "pointmass": ("action_variability", "sigma_target", "sigma_cursor", "action_cost")}
+                "pointmass": ("action_variability", "sigma_target", "sigma_cursor", "action_cost"),
+                "hand": ("action_variability", "sigma_target", "sigma_cursor", "action_cost"),
+                "delay": ("action_variability", "sigma_target", "sigma_cursor", "action_cost")}
 DEFAULTS = dict(action_variability=0.5, sigma_target=6.0, sigma_cursor=6.0, action_cost=1.0, subj_noise=1.0,
                 subj_vel_noise=0.5, sigma=6.0)
 
 
 def jittered_params(name, S, seed, scale=0.25):
     base = name.rstrip("2")
+    
     rng = np.random.default_rng(seed)
     out = []
     for s in range(S):

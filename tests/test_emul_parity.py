@@ -23,7 +23,7 @@ CPU = torch.device("cpu")
 
 
 @pytest.mark.parametrize("name,d", [("bounded", 2), ("subjective", 2), ("relobs", 2), ("bounded2", 4), ("relobs2", 4),
-                                    ("subjective2", 4), ("pointmass", 2)])
+                                    ("subjective2", 4), ("pointmass", 2), ("hand", 2), ("delay2", 2)])
 def test_step_functions_match_oracle(lib, name, d):
     case = H.Case(name, S=2, T=80, N=5, d=d, weights=True)
     H.check_gains(lib, CPU, case, torch.float64, rtol=1e-9)

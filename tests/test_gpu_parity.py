@@ -23,7 +23,7 @@ def dev():
 
 
 @pytest.mark.parametrize("name,d", [("bounded", 2), ("subjective", 2), ("relobs", 2), ("bounded2", 4), ("relobs2", 4),
-                                    ("subjective2", 4), ("pointmass", 2)])
+                                    ("subjective2", 4), ("pointmass", 2), ("hand", 2), ("delay2", 2)])
 def test_gains_match_oracle(lib, dev, name, d):
     case = H.Case(name, S=3, T=300, N=2, d=d, want_grad=False)
     H.check_gains(lib, dev, case, torch.float64, rtol=1e-9)
@@ -31,7 +31,8 @@ def test_gains_match_oracle(lib, dev, name, d):
 
 
 @pytest.mark.parametrize("name,d,N", [("bounded", 2, 20), ("subjective", 2, 33), ("relobs", 2, 7), ("bounded2", 4, 64),
-                                      ("relobs2", 4, 20), ("subjective2", 4, 100), ("pointmass", 2, 50)])
+                                      ("relobs2", 4, 20), ("subjective2", 4, 100), ("pointmass", 2, 50), ("hand", 2, 50),
+                                      ("delay2", 2, 40)])
 def test_loglik_and_gradients_match_oracle(lib, dev, name, d, N):
     case = H.Case(name, S=3, T=200, N=N, d=d, weights=True)
     H.check_fwd(lib, dev, case, torch.float32)
