@@ -157,7 +157,7 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": "trial-evals/s", "cores": cores, "kind": "port",
                              "sample": f"{S} parameter samples x {N} trials x T={T}, fwd+grad by torch autograd, float64"},
             "e2e": {"value": val, "unit": "trial-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, S_per_gpu, note=None):
@@ -322,16 +322,34 @@ def run_ours(args):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         ws_bytes = 2.0 * lib.workspace_bytes(dims, abi.MODE_VJP, 0)   # every workspace array is written once and read (at least) once
-        roofline = {"bound": "fp32", "kernel": "+".join(kernels[dom]["kernels"]), "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-                    "frac": achieved / fp32_peak, "traffic": None,
-                    "algorithmic_flops_per_step": kind_flops[dom] * S, "ms_per_step": kernels[dom]["ms_per_step"],
+        dom_kernel = max(kernels[dom]["kernels"], key=lambda k: kernels[dom]["kernels"][k])
+        dom_ms = kernels[dom]["kernels"][dom_kernel]                  # live CUDA-event time of that kernel per step
+        # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture, if it was taken on this launch shape
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath)).get(dom_kernel)
+            launches = max(1.0, kernels[dom]["launches_per_step"] if len(kernels[dom]["kernels"]) == 1 else 1.0)
+            if tj and tj["samples_per_launch"] * launches == S and tj["pseudo_trials"] == dims.N and tj["T"] == T:
+                traffic = tj["dram_bytes_per_launch"]
+        # FMAs the kernels actually execute per trial-step after the reduced form + axis factorisation
+        executed = {"trial_fwd": 2 * 2 * 36.0 * N * T, "trial_rev": 2 * 2 * 77.0 * N * T}
+        roofline = {"bound": "fp32", "kernel": dom_kernel, "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                    "frac": achieved / fp32_peak, "traffic": traffic,
+                    "algorithmic_flops_per_launch": kind_flops[dom] * S / dom_launches, "launch_ms": dom_ms / dom_launches,
                     "launches_per_step": dom_launches,
-                    "peak_source": "FFMA micro-kernel measured in this run (lqgk_peak_fma); nominal 74.5 TFLOP/s",
+                    "peak_source": "FFMA micro-kernel measured in this run (lqgk_peak_fma); MEASURED_PEAKS.json has no FP32 figure; nominal 74.5",
+                    "note": "achieved = algorithmic FLOPs of the reference recursion this kernel replaces (SURVEY 8d: dense count, adjoint = 2x "
+                            "forward) / live CUDA-event time; the kernel executes fewer FLOPs than that (reduced form + per-axis factorisation)",
+                    "executed": ({"tflops": executed[dom] * S / (dom_ms * 1e-3) / 1e12, "frac": executed[dom] * S / (dom_ms * 1e-3) / 1e12 / fp32_peak}
+                                 if dom in executed else None),
                     "fp64_peak_tflops_measured": fp64_peak,
                     "step": {"achieved": step_flops / (ms_per_step * 1e-3) / 1e12, "frac": step_flops / (ms_per_step * 1e-3) / 1e12 / fp32_peak,
                              "algorithmic_flops": step_flops},
-                    "hbm": {"achieved_gbs": ws_bytes / (ms_per_step * 1e-3) / 1e9, "peak_gbs": hbm_peak,
-                            "frac": ws_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
+                    "hbm": {"kernel_gbs": (traffic / (dom_ms / dom_launches * 1e-3) / 1e9) if traffic else None,
+                            "step_gbs": ws_bytes / (ms_per_step * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                            "kernel_frac": (traffic / (dom_ms / dom_launches * 1e-3) / 1e9 / hbm_peak) if traffic else None,
+                            "step_frac": ws_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
                             "bytes_per_step_workspace_model": ws_bytes}}
         # ---------------- CPU baseline (bounded sample) on this box's host cores
@@ -352,7 +370,7 @@ def run_ours(args):
                         "d2h_bytes_per_step": int(out_host.numel() * 4)},
                 "gpu_launches": int(launches_per_step * args.steps),
                 "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -367,7 +385,26 @@ def split_sample_flops():
     return lqr, kf
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Route everything that libraries print on fd 1 (e.g. the NCCL version banner) to stderr; the one JSON line is
+    written to the real stdout by emit()."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
