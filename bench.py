@@ -134,6 +134,44 @@ def cpu_port_eval(S, N, T, X, seed=3):
     return time.perf_counter() - t0
 
 
+def bench_c2(dev, reps=10):
+    """Config c2 of BASELINE.json (latency case): SubjectiveActor 2-D, 6 blob-width conditions x 20 trials x T=1200, gradient
+    w.r.t. 5 shared + 6 per-condition parameters, ONE fused call (conditions = the kernels' sample axis, every condition its
+    own trials), through the public API.  Returns (trial-evals/s, ms per evaluation)."""
+    from lqg_b200.tracking import SubjectiveActor
+    from oracle import lqg_np as O
+    sig = [8.5, 9.7, 11.8, 19.9, 28.5, 51.6]
+    T, N = 1200, 20
+    xs = []
+    for c, s_t in enumerate(sig):
+        sa, sd = O.make_system(O.subjective_actor_mats(dim=2, sigma_target=s_t), T)
+        xs.append(O.simulate(sa, sd, N, np.random.default_rng(c)).astype(np.float32))
+    x = torch.tensor(np.stack(xs), device=dev)
+    shared = torch.tensor([1.0, 0.5, 1.0, 0.5, 6.0], device=dev, requires_grad=True)   # cost, variab., subj, subj_vel, sigma_cursor
+    st = torch.tensor(sig, device=dev, requires_grad=True)
+
+    def evaluate():
+        shared.grad = st.grad = None
+        m = SubjectiveActor(dim=2, T=T, device=dev, action_cost=shared[0], action_variability=shared[1], subj_noise=shared[2],
+                            subj_vel_noise=shared[3], sigma_cursor=shared[4], sigma_target=st)
+        ll = m.log_likelihood(x).sum()
+        ll.backward()
+        return ll
+
+    for _ in range(3):
+        evaluate()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        ll = evaluate()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    assert torch.isfinite(ll) and torch.isfinite(shared.grad).all() and torch.isfinite(st.grad).all()
+    return len(sig) * N / (ms * 1e-3), ms
+
+
 # ----------------------------------------------------------------------------------------------- reference arm
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -359,6 +397,12 @@ def run_ours(args):
             cpu = {"value": args.cpu_samples * N / sec, "unit": "trial-evals/s", "cores": os.cpu_count() or 1, "kind": "port",
                    "sample": f"{args.cpu_samples} parameter samples x {N} trials x T={T}, one fwd+grad eval by torch-float64 "
                              f"autograd over the oracle's restatement of the reference scans ({sec:.1f} s)"}
+        secondary = None
+        if world == 1:
+            c2_val, c2_ms = bench_c2(dev)
+            secondary = {"workload": "c2: SubjectiveActor dim=2, 6 conditions x 20 trials x T=1200, grad wrt 5 shared + 6 per-condition "
+                                     "parameters, one fused call through the public API (latency-bound: 6 systems)",
+                         "value": c2_val, "unit": "trial-evals/s", "ms_per_eval": c2_ms}
         line = {"metric": "trial log-lik+grad evals/sec", "value": value, "unit": "trial-evals/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64 per-sample recursions + f32 per-trial recursions (f32 I/O)",
@@ -369,7 +413,7 @@ def run_ours(args):
                         "h2d_bytes_per_step": int(theta_host.numel() * 4 + x_host.numel() * 4),
                         "d2h_bytes_per_step": int(out_host.numel() * 4)},
                 "gpu_launches": int(launches_per_step * args.steps),
-                "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks}
+                "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "secondary": secondary, "clocks": clocks}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -39,6 +39,10 @@ typedef struct {
   int32_t N; /* trials per system                                                     */
   int32_t T; /* time steps; observations have T+1 rows (lqg/system.py:233) */
   int32_t x, b, u, y, d;
+  int64_t x_sample_stride; /* floats between the observation sets of consecutive samples in x_tm;
+                              0 = all samples share one data set x_tm[T+1][N][d] (parameter sweeps);
+                              (T+1)*N*d = every sample has its own data x_tm[S][T+1][N][d] (e.g. one sample per
+                              experimental condition, lqg/infer/models.py:38-61) */
 } LqgkDims;
 
 typedef struct {

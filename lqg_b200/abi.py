@@ -23,7 +23,7 @@ DYN_KEYS = ("A", "B", "F", "V", "W")
 
 
 class LqgkDims(C.Structure):
-    _fields_ = [(k, C.c_int32) for k in ("S", "N", "T", "x", "b", "u", "y", "d")]
+    _fields_ = [(k, C.c_int32) for k in ("S", "N", "T", "x", "b", "u", "y", "d")] + [("x_sample_stride", C.c_int64)]
 
 
 class LqgkMat(C.Structure):
@@ -127,6 +127,18 @@ class Library:
         return sp
 
     @staticmethod
+    def _check_obs(dims, x_tm):
+        """x_tm: float32 contiguous, [T+1, N, d] shared by all samples or [S, T+1, N, d] with one data set per sample;
+        sets dims.x_sample_stride accordingly."""
+        assert x_tm.dtype == torch.float32 and x_tm.is_contiguous()
+        if x_tm.dim() == 3:
+            assert tuple(x_tm.shape) == (dims.T + 1, dims.N, dims.d), tuple(x_tm.shape)
+            dims.x_sample_stride = 0
+        else:
+            assert tuple(x_tm.shape) == (dims.S, dims.T + 1, dims.N, dims.d), tuple(x_tm.shape)
+            dims.x_sample_stride = x_tm.stride(0)
+
+    @staticmethod
     def _ws(ws: Optional[torch.Tensor]):
         return (ws.data_ptr(), ws.numel() * ws.element_size()) if ws is not None else (None, 0)
 
@@ -160,7 +172,7 @@ class Library:
     def loglik_fwd(self, dims, actor, dyn, x_tm, sigma0=None, ws=None, stream=0):
         dt, dev = actor["A"].dtype, actor["A"].device
         S, T = dims.S, dims.T
-        assert x_tm.dtype == torch.float32 and x_tm.is_contiguous() and tuple(x_tm.shape) == (T + 1, dims.N, dims.d)
+        self._check_obs(dims, x_tm)
         ll = torch.empty((S, dims.N), dtype=dt, device=dev)
         sa, sd = self._spec(actor, S, T, ACTOR_KEYS), self._spec(dyn, S, T, DYN_KEYS)
         s0 = _mat(sigma0, S, 1) if sigma0 is not None else None
@@ -176,7 +188,7 @@ class Library:
         """Returns ll[S,N], grads_actor{name: [S,r,c]}, grads_dyn{...}, grad_sigma0 or None."""
         dt, dev = actor["A"].dtype, actor["A"].device
         S, T = dims.S, dims.T
-        assert x_tm.dtype == torch.float32 and x_tm.is_contiguous() and tuple(x_tm.shape) == (T + 1, dims.N, dims.d)
+        self._check_obs(dims, x_tm)
         ll = torch.empty((S, dims.N), dtype=dt, device=dev)
         sa, sd = self._spec(actor, S, T, ACTOR_KEYS), self._spec(dyn, S, T, DYN_KEYS)
         s0 = _mat(sigma0, S, 1) if sigma0 is not None else None

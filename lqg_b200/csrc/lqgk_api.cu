@@ -33,6 +33,7 @@ int validate(const Call& c) {
     for (auto m : need)
       if (!m->ptr) return LQGK_E_INVALID;
     if (((uintptr_t)c.x_tm % 16) != 0) return LQGK_E_INVALID;
+    if (d.x_sample_stride < 0 || (d.x_sample_stride * sizeof(float)) % 16 != 0) return LQGK_E_INVALID;
   }
   return LQGK_OK;
 }

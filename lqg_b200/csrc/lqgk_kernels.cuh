@@ -637,14 +637,15 @@ __host__ __device__ constexpr bool rec_in_regs() { return DM::REC <= 48; }
 // TRIAL_PF steps ahead with per-lane cp.async copies into shared-memory slots (no registers held, no stalls on the
 // L2 round trip).
 template <class DM, int RT>
-__global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_fwd(const float* __restrict__ rec, const float* __restrict__ x_tm,
-                                                                int n_samples, int N, int Tn, double* __restrict__ ll_ws,
-                                                                float* __restrict__ hist) {
+__global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_fwd(const float* __restrict__ rec, const float* __restrict__ x_all,
+                                                                size_t x_sample_stride, int s_first, int n_samples, int N, int Tn,
+                                                                double* __restrict__ ll_ws, float* __restrict__ hist) {
   constexpr int D = DM::D, R = DM::R, NSLOT = TRIAL_PF + 1;
   extern __shared__ __align__(128) unsigned char smraw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = blockIdx.x * TRIAL_WARPS + warp;
   if (s >= n_samples) return;
+  const float* __restrict__ x_tm = x_all + (size_t)(s_first + s) * x_sample_stride;   // this sample's observations
   constexpr size_t RING_BYTES = (size_t)TRIAL_WARPS * TRIAL_NST * TRIAL_TB * DM::REC * sizeof(float);
   float* ring_base = reinterpret_cast<float*>(smraw);
   uint64_t* bar_base = reinterpret_cast<uint64_t*>(smraw + RING_BYTES);
@@ -778,15 +779,17 @@ __host__ __device__ constexpr int pow2_ceil(int v) { return v <= 1 ? 1 : (v <= 2
 // Reverse: per-trial adjoint, t = T-1..0, plus the per-step sums over trials (DM::SUM_* layout) written to
 // sums[s][t][SUMP].  Passes over trial blocks accumulate (+=) into the sums.
 template <class DM, int RT>
-__global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __restrict__ rec, const float* __restrict__ x_tm,
-                                                                const float* __restrict__ hist, const float* __restrict__ w,
-                                                                int n_samples, int N, int Tn, float* __restrict__ sums) {
+__global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __restrict__ rec, const float* __restrict__ x_all,
+                                                                size_t x_sample_stride, int s_first, const float* __restrict__ hist,
+                                                                const float* __restrict__ w, int n_samples, int N, int Tn,
+                                                                float* __restrict__ sums) {
   constexpr int D = DM::D, R = DM::R;
   constexpr int NFULL = DM::NSUM / 32, REM = DM::NSUM % 32, VREM = pow2_ceil(REM);
   extern __shared__ __align__(128) unsigned char smraw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = blockIdx.x * TRIAL_WARPS + warp;
   if (s >= n_samples) return;
+  const float* __restrict__ x_tm = x_all + (size_t)(s_first + s) * x_sample_stride;   // this sample's observations
   float* ring_base = reinterpret_cast<float*>(smraw);
   uint64_t* bar_base = reinterpret_cast<uint64_t*>(smraw + (size_t)TRIAL_WARPS * TRIAL_NST * TRIAL_TB * DM::REC * sizeof(float));
   RecRing<DM> ring{ring_base + (size_t)warp * TRIAL_NST * TRIAL_TB * DM::REC, bar_base + warp * TRIAL_NST,

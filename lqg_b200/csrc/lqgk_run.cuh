@@ -181,23 +181,24 @@ int set_smem(const void* fn, size_t bytes) {
 }
 
 template <class DM, int RT>
-int launch_trial_fwd(cudaStream_t st, const float* rec, const float* x_tm, int n, int N, int T, double* ll, float* hist) {
+int launch_trial_fwd(cudaStream_t st, const float* rec, const float* x_tm, size_t xs, int s_first, int n, int N, int T, double* ll,
+                     float* hist) {
   size_t smem = trial_smem_bytes<DM, RT, false>();
   int rc = set_smem<DM>((const void*)k_trial_fwd<DM, RT>, smem);
   if (rc) return rc;
   ProfScope ps_(PK_TRIAL_FWD, st);
-  k_trial_fwd<DM, RT><<<(n + TRIAL_WARPS - 1) / TRIAL_WARPS, 32 * TRIAL_WARPS, smem, st>>>(rec, x_tm, n, N, T, ll, hist);
+  k_trial_fwd<DM, RT><<<(n + TRIAL_WARPS - 1) / TRIAL_WARPS, 32 * TRIAL_WARPS, smem, st>>>(rec, x_tm, xs, s_first, n, N, T, ll, hist);
   LQGK_LAUNCH_CHECK();
   return LQGK_OK;
 }
 template <class DM, int RT>
-int launch_trial_rev(cudaStream_t st, const float* rec, const float* x_tm, const float* hist, const float* w, int n, int N,
+int launch_trial_rev(cudaStream_t st, const float* rec, const float* x_tm, size_t xs, int s_first, const float* hist, const float* w, int n, int N,
                      int T, float* sums) {
   size_t smem = trial_smem_bytes<DM, RT, true>();
   int rc = set_smem<DM>((const void*)k_trial_rev<DM, RT>, smem);
   if (rc) return rc;
   ProfScope ps_(PK_TRIAL_REV, st);
-  k_trial_rev<DM, RT><<<(n + TRIAL_WARPS - 1) / TRIAL_WARPS, 32 * TRIAL_WARPS, smem, st>>>(rec, x_tm, hist, w, n, N, T, sums);
+  k_trial_rev<DM, RT><<<(n + TRIAL_WARPS - 1) / TRIAL_WARPS, 32 * TRIAL_WARPS, smem, st>>>(rec, x_tm, xs, s_first, hist, w, n, N, T, sums);
   LQGK_LAUNCH_CHECK();
   return LQGK_OK;
 }
@@ -360,7 +361,7 @@ int run(const Call& c) {
     float* hist = vjp ? F(p.hist) : nullptr;
     rc = LQGK_E_UNSUPPORTED;
     static_for<1, trial_rt_max<DM>() + 1>([&](auto RTC) {
-      if (RT == decltype(RTC)::value) rc = launch_trial_fwd<DM, decltype(RTC)::value>(st, F(p.rec), c.x_tm, n, N, Tn, D(p.ll), hist);
+      if (RT == decltype(RTC)::value) rc = launch_trial_fwd<DM, decltype(RTC)::value>(st, F(p.rec), c.x_tm, (size_t)d.x_sample_stride, (int)s0, n, N, Tn, D(p.ll), hist);
     });
     if (rc) return rc;
     {
@@ -384,7 +385,7 @@ int run(const Call& c) {
     rc = LQGK_E_UNSUPPORTED;
     static_for<1, trial_rt_max<DM>() + 1>([&](auto RTC) {
       if (RT == decltype(RTC)::value)
-        rc = launch_trial_rev<DM, decltype(RTC)::value>(st, F(p.rec), c.x_tm, hist, F(p.w), n, N, Tn, F(p.sums));
+        rc = launch_trial_rev<DM, decltype(RTC)::value>(st, F(p.rec), c.x_tm, (size_t)d.x_sample_stride, (int)s0, hist, F(p.w), n, N, Tn, F(p.sums));
     });
     if (rc) return rc;
     if (cudaMemsetAsync(D(p.acc), 0, sizeof(double) * cl.total * Sc, st) != cudaSuccess) return LQGK_E_CUDA;

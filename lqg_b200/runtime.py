@@ -229,17 +229,24 @@ def log_likelihood(actor: LQGSpec, dynamics: LQGSpec, x: torch.Tensor, Sigma0: O
                    x_tm: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Per-trial log-likelihood (reference ``System.log_likelihood``, lqg/system.py:246-248).
 
-    x: (n, T+1, d).  Returns (n,) for an un-batched spec, (S, n) for a spec with a sample axis."""
+    x: (n, T+1, d) -- one data set shared by all parameter samples -- or (S, n, T+1, d) -- one data set per sample
+    (e.g. one sample per experimental condition).  Returns (n,) for an un-batched spec, (S, n) otherwise."""
     _require_cuda(actor.A, "actor spec")
     _require_cuda(x, "observations")
     lib = abi.load_library()
-    n, T1, d = x.shape
+    per_sample = x.dim() == 4
+    n, T1, d = x.shape[-3:]
     dims = dims_of(actor, dynamics, n, d)
+    if per_sample and x.shape[0] != dims.S:
+        raise ValueError(f"per-sample observations need a leading axis of {dims.S} samples, got {x.shape[0]}")
     if dims.T != T1 - 1:
         raise ValueError(f"need T+1 = {dims.T + 1} observations per trial, got {T1} (SURVEY H7: spec.T == x.shape[-2] - 1)")
     check_supported(dims)
     if x_tm is None:
-        x_tm = lib.pack_obs(x.detach(), stream=_stream(x.device))
+        if per_sample:   # [S, n, T+1, d] -> [S, T+1, n, d] float32
+            x_tm = x.detach().permute(0, 2, 1, 3).to(torch.float32).contiguous()
+        else:
+            x_tm = lib.pack_obs(x.detach(), stream=_stream(x.device))
     dt = actor.A.dtype
     def base(M):
         """(S|1, r, c) base matrix of a time-invariant array (stride-0 time axis), else the (S|1, T, r, c) array."""

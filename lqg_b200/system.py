@@ -138,16 +138,17 @@ class System:
 
     # -- hot path ------------------------------------------------------------------------------------------
     def log_likelihood(self, x: torch.Tensor, Sigma0=None) -> torch.Tensor:
-        """log p(x_{i,1:T} | x_{i,0}) per trial, summed over time (system.py:246-248).  x: (n, T+1, d)."""
+        """log p(x_{i,1:T} | x_{i,0}) per trial, summed over time (system.py:246-248).  x: (n, T+1, d), or
+        (S, n, T+1, d) to give every parameter sample (e.g. experimental condition) its own trials."""
         axis = getattr(self, "_axis_system", None)
         if axis is not None and Sigma0 is None and x.shape[-1] == self.xdim:
             # Exact factorisation (SURVEY 7.2, checked to 1e-15): a dim-axis tracking model with shared parameters is
             # block diagonal, so its likelihood is the sum over axes of the 1-axis model's likelihood on that axis'
             # (target, cursor) columns.  The per-sample recursions then run once on n/dim-sized matrices and the
             # axes become extra trials: x[n, T+1, dim*da] -> [dim*n, T+1, da].
-            n, T1, d = x.shape
+            lead, (n, T1, d) = x.shape[:-3], x.shape[-3:]
             dim = self.dim
-            xa = x.reshape(n, T1, dim, d // dim).permute(2, 0, 1, 3).reshape(dim * n, T1, d // dim)
+            xa = x.reshape(*lead, n, T1, dim, d // dim).movedim(-2, -4).reshape(*lead, dim * n, T1, d // dim)
             ll = axis.log_likelihood(xa)
             return ll.reshape(*ll.shape[:-1], dim, n).sum(-2)
         s0 = None if Sigma0 is None else torch.as_tensor(Sigma0, dtype=self.dtype, device=self.device)

@@ -39,9 +39,9 @@ def _base(M):
 
 def _workspace_bytes(S, N, T, x, b, u, y, d, mode):
     class Dims(ctypes.Structure):
-        _fields_ = [(k, ctypes.c_int32) for k in ("S", "N", "T", "x", "b", "u", "y", "d")]
+        _fields_ = [(k, ctypes.c_int32) for k in ("S", "N", "T", "x", "b", "u", "y", "d")] + [("x_sample_stride", ctypes.c_int64)]
     _ABI.lqgk_workspace_bytes.restype = ctypes.c_size_t
-    return int(_ABI.lqgk_workspace_bytes(ctypes.byref(Dims(S, N, T, x, b, u, y, d)), mode, 8192))
+    return int(_ABI.lqgk_workspace_bytes(ctypes.byref(Dims(S, N, T, x, b, u, y, d, 0)), mode, 8192))
 
 
 def _mats(actor, dynamics):

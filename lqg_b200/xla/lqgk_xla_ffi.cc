@@ -50,6 +50,7 @@ LqgkDims dims_of(const F32& Aa, const F32& Ad, const F32& Ba, const F32& Fa, con
   d.b = (int32_t)Aa.dimensions()[1];
   d.u = (int32_t)Ba.dimensions()[2];
   d.y = (int32_t)Fa.dimensions()[1];
+  d.x_sample_stride = 0;   // one shared data set (parameter sweeps / vmap over parameters)
   return d;
 }
 

@@ -100,8 +100,10 @@ int run(const LqgkDims& d, const LqgkSpec* act, const LqgkSpec* dyn, const LqgkM
   }
   using TR = Trial<DM>;
   constexpr int D = DM::D, R = DM::R;
+  const float* x_all = x_tm;
   for (int s = 0; s < S; ++s)
     for (int i = 0; i < N; ++i) {
+      const float* x_tm = x_all + (size_t)s * d.x_sample_stride;
       float c[R] = {0};
       double ll = 0.0;
       for (int t = 0; t < Tn; ++t) {
@@ -113,6 +115,7 @@ int run(const LqgkDims& d, const LqgkSpec* act, const LqgkSpec* dyn, const LqgkM
     }
   if (!want_grad) return LQGK_OK;
   for (int s = 0; s < S; ++s) {
+    const float* x_tm = x_all + (size_t)s * d.x_sample_stride;
     double sw = 0.0;
     for (int i = 0; i < N; ++i) {
       float w = ll_bar ? (float)ll_bar[(size_t)s * N + i] : 1.f;

@@ -47,6 +47,6 @@ def test_host_side_queries_without_gpu():
 
 
 def test_struct_layouts_match_header():
-    assert ctypes.sizeof(abi.LqgkDims) == 32
+    assert ctypes.sizeof(abi.LqgkDims) == 40
     assert ctypes.sizeof(abi.LqgkMat) == 24 and ctypes.sizeof(abi.LqgkSpec) == 12 * 24
     assert ctypes.sizeof(abi.LqgkMatGrad) == 16 and ctypes.sizeof(abi.LqgkSpecGrad) == 8 * 16

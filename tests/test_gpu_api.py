@@ -138,3 +138,28 @@ def test_no_cpu_fallback():
     m = tracking.BoundedActor(T=10, device="cpu")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m.log_likelihood(torch.zeros(2, 11, 2))
+
+
+def test_per_condition_data_in_one_call():
+    """Config c2 shape: one sample per blob-width condition, each with its own trials (reference loops over
+    conditions, lqg/infer/models.py:38-61; here the conditions are the kernels' sample axis)."""
+    T, N, C = 120, 7, 3
+    sig = [8.5, 19.9, 51.6]
+    Xs, lls, grads = [], [], []
+    for c in range(C):
+        mats = O.subjective_actor_mats(dim=2, sigma_target=sig[c])
+        X = _sim(mats, T, N, seed=10 + c).astype(np.float32)
+        Xs.append(X)
+        so = torch.tensor(sig[c], dtype=torch.float64, requires_grad=True)
+        a, d = OT.subjective_actor(dim=2, sigma_target=so)
+        ll = OT.log_likelihood(a, d, torch.tensor(X, dtype=torch.float64))
+        ll.sum().backward()
+        lls.append(ll.detach().numpy()); grads.append(so.grad.item())
+    st = torch.tensor(sig, device=DEV, requires_grad=True)
+    m = tracking.SubjectiveActor(dim=2, T=T, sigma_target=st)
+    x = torch.tensor(np.stack(Xs), device=DEV)                       # (C, N, T+1, 4)
+    ll = m.log_likelihood(x)
+    assert ll.shape == (C, N)
+    ll.sum().backward()
+    assert np.allclose(ll.detach().cpu().numpy(), np.stack(lls), rtol=1e-4)
+    assert np.allclose(st.grad.cpu().numpy(), np.array(grads), rtol=1e-3)
