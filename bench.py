@@ -95,7 +95,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
@@ -107,7 +113,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        t0, t1 = getattr(self, "t0", 0.0), getattr(self, "t1", float("inf"))
+        inside = [r for ts, r in self.rows if t0 <= ts <= t1 + 0.15]
+        # nvidia-smi needs a few hundred ms per sample on an 8-GPU box: fall back to the samples nearest to the region
+        use = inside if inside else [r for _, r in self.rows[-3:]]
+        for r in use:
             f = [c.strip() for c in r.split(",")]
             try:
                 sm.append(float(f[0])); mx.append(float(f[1]))
@@ -117,7 +127,7 @@ class ClockSampler:
             except Exception:
                 continue
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "samples_inside_timed_region": len(inside), "reasons": sorted(reasons)}
 
 
 def cpu_port_eval(S, N, T, X, seed=3):
@@ -269,20 +279,22 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()                                   # started before the warm-up so samples exist when the timed region begins
     for _ in range(args.warmup):
         ll = step_resident()
     barrier()
     launches_per_step = lib.last_launch_count()
-    sampler = ClockSampler(local)
-    sampler.start()
     lib.profile_enable(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_start()
     e0.record()
     for _ in range(args.steps):
         ll = step_resident()
     e1.record()
     barrier()
+    sampler.mark_end()
     ms = e0.elapsed_time(e1)
     prof = lib.profile_read()
     lib.profile_enable(False)
