@@ -238,6 +238,8 @@ def run_ours(args):
         lib.set_streams(args.streams)
     if args.overlap >= 0:
         lib.set_kernel_overlap(args.overlap)
+    if args.contrib_warps > 0:
+        lib.lib.lqgk_set_contrib_warps(args.contrib_warps)
     S, N, T = args.samples, args.trials, args.T
     X = make_data(N, T)
     theta_np = make_theta(S, 11 + rank)
@@ -473,6 +475,7 @@ def main():
     ap.add_argument("--cpu-samples", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=0, help="internal concurrent sample slices (0 = library default)")
+    ap.add_argument("--contrib-warps", type=int, default=0)
     ap.add_argument("--overlap", type=int, default=-1, help="kernel-overlap mask (see lqgk_set_kernel_overlap); -1 = library default")
     ap.add_argument("--no-factorize", action="store_true", help="run the general 2-D (n=10) kernels instead of the per-axis factorisation")
     args = ap.parse_args()

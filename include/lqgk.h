@@ -127,6 +127,8 @@ int lqgk_set_streams(int n);
  * concurrently on internal auxiliary streams.  mask bit 0: lqr_fwd | kf_fwd, bit 1: contraction passes, bit 2: adjoint tail;
  * default 6. */
 int lqgk_set_kernel_overlap(int mask);
+/* Tuning knob: target number of (32-sample group x time-range) warps of the time-parallel contraction kernels. */
+int lqgk_set_contrib_warps(int n);
 /* Per-kernel timing for bench.py: when enabled, every kernel launch of the calling thread's entry-point calls is
  * bracketed by CUDA events on the launching stream.  lqgk_profile_read() synchronises on those events, sums the
  * elapsed milliseconds (and launch counts) per kernel kind, resets the log and returns the number of kinds:

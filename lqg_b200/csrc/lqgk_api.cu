@@ -15,6 +15,7 @@ namespace lqgk {
 thread_local int g_launches = 0;
 thread_local Profiler g_prof;
 thread_local int g_streams = 1;
+thread_local int g_contrib_warps = 148 * 30;
 thread_local int g_aux_streams = 6;
 thread_local StreamPool g_pool;
 }
@@ -171,6 +172,11 @@ const char* lqgk_strerror(int code) {
 int lqgk_set_streams(int n) {
   if (n < 1 || n > 32) return LQGK_E_INVALID;
   g_streams = n;
+  return LQGK_OK;
+}
+int lqgk_set_contrib_warps(int n) {
+  if (n < 1) return LQGK_E_INVALID;
+  g_contrib_warps = n;
   return LQGK_OK;
 }
 int lqgk_set_kernel_overlap(int mask) {

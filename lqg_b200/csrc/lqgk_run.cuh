@@ -28,6 +28,7 @@ extern thread_local Profiler g_prof;
 // its samples into up to g_streams slices that run the whole kernel sequence concurrently on internal non-blocking
 // streams (forked from / joined to the caller's stream with events); each slice owns a part of the workspace.
 extern thread_local int g_streams;
+extern thread_local int g_contrib_warps;   // target number of (sample-group x time-range) warps of the contraction kernels
 extern thread_local int g_aux_streams;   // bit 0: lqr_fwd | kf_fwd, bit 1: contraction passes, bit 2: kf_rev | lqr_rev | reduce
 struct StreamPool {
   int device = -1;
@@ -402,7 +403,7 @@ int run(const Call& c) {
     }
     {
       // (sample-group x time-range) warps: enough to occupy every SM a few times over
-      int chunks = std::max(1, std::min((Tn + 7) / 8, (148 * 4 + nblk - 1) / nblk));
+      int chunks = std::max(1, std::min((Tn + 7) / 8, (g_contrib_warps + nblk - 1) / nblk));
       dim3 grid(nblk, chunks);
       if constexpr (contrib_merged<DM>()) {
         size_t smem = smem_cov_contrib<DM, 2>();
