@@ -5,8 +5,9 @@ next to the reference algorithm on the host CPU.
 Workload (config c3 of BASELINE.json): SubjectiveActor 2-D tracking, N=100 trials x T=1200, a sweep of
 S parameter samples PER GPU (default 32,768 = half of the 65,536-sample target on every GPU; weak scaling: N GPUs
 evaluate N*S samples per step).  One "step" = one log-likelihood + parameter-gradient evaluation of all S samples
-(S*100 trial evals).  Data are synthetic (float64 restatement of System.simulate, NumPy PCG64 seed 7); parameter
-samples are theta_true * exp(0.25 z), z ~ N(0, I_6), seed 11 + rank.
+(S*100 trial evals).  Data are synthetic: the GPU legs simulate them with the product's own System.simulate (torch Philox,
+seed 7), the CPU legs with the oracle's restatement (NumPy PCG64, seed 7); parameter samples are theta_true * exp(0.25 z),
+z ~ N(0, I_6), seed 11 + rank.
 
   value : device-resident (base matrices + observations already in HBM), CUDA events, max over ranks.
   e2e   : through the public API (lqg_b200.tracking.SubjectiveActor(...).log_likelihood(x).sum().backward()) with
@@ -65,10 +66,20 @@ def algorithmic_flops(x, b, u, y, d, N, T):
 
 # ----------------------------------------------------------------------------------------------- helpers
 def make_data(N, T, seed=7):
+    """Synthetic tracking data for the CPU legs: float64 restatement of System.simulate (oracle), NumPy PCG64."""
     from oracle import lqg_np as O
     kw = dict(zip(PARAM_NAMES, THETA_TRUE))
     sa, sd = O.make_system(O.subjective_actor_mats(dim=2, **kw), T)
     return O.simulate(sa, sd, N, np.random.default_rng(seed)).astype(np.float32)
+
+
+def make_data_gpu(N, T, dev, seed=7, **overrides):
+    """Synthetic tracking data for the GPU legs from the product's own simulator (lqg_b200 System.simulate, torch Philox);
+    the oracle is not involved in anything the GPU legs measure."""
+    from lqg_b200.tracking import SubjectiveActor
+    kw = dict(zip(PARAM_NAMES, THETA_TRUE))
+    kw.update(overrides)
+    return SubjectiveActor(dim=2, T=T, device=dev, **kw).simulate(seed, n=N).to(torch.float32)
 
 
 def make_theta(S, seed):
@@ -149,14 +160,9 @@ def bench_c2(dev, reps=10):
     w.r.t. 5 shared + 6 per-condition parameters, ONE fused call (conditions = the kernels' sample axis, every condition its
     own trials), through the public API.  Returns (trial-evals/s, ms per evaluation)."""
     from lqg_b200.tracking import SubjectiveActor
-    from oracle import lqg_np as O
     sig = [8.5, 9.7, 11.8, 19.9, 28.5, 51.6]
     T, N = 1200, 20
-    xs = []
-    for c, s_t in enumerate(sig):
-        sa, sd = O.make_system(O.subjective_actor_mats(dim=2, sigma_target=s_t), T)
-        xs.append(O.simulate(sa, sd, N, np.random.default_rng(c)).astype(np.float32))
-    x = torch.tensor(np.stack(xs), device=dev)
+    x = torch.stack([make_data_gpu(N, T, dev, seed=c, sigma_target=s_t, action_cost=1.0, sigma_cursor=6.0) for c, s_t in enumerate(sig)])
     shared = torch.tensor([1.0, 0.5, 1.0, 0.5, 6.0], device=dev, requires_grad=True)   # cost, variab., subj, subj_vel, sigma_cursor
     st = torch.tensor(sig, device=dev, requires_grad=True)
 
@@ -241,14 +247,14 @@ def run_ours(args):
     if args.contrib_warps > 0:
         lib.lib.lqgk_set_contrib_warps(args.contrib_warps)
     S, N, T = args.samples, args.trials, args.T
-    X = make_data(N, T)
     theta_np = make_theta(S, 11 + rank)
     P = theta_np.shape[1]
 
     # ---------------- device-resident leg
     theta = torch.tensor(theta_np, device=dev)
     model = SubjectiveActor(dim=2, T=T, device=dev, **{n: theta[:, i] for i, n in enumerate(PARAM_NAMES)})
-    x_dev = torch.tensor(X, device=dev)
+    x_dev = make_data_gpu(N, T, dev)
+    X = x_dev.cpu().numpy()
     if args.no_factorize:
         sysm, xk, Nk = model, x_dev, N
         dims = abi.LqgkDims(S, N, T, DIMS["x"], DIMS["b"], DIMS["u"], DIMS["y"], DIMS["d"])
@@ -407,7 +413,7 @@ def run_ours(args):
         # ---------------- CPU baseline (bounded sample) on this box's host cores
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            sec = cpu_port_eval(args.cpu_samples, N, T, X)
+            sec = cpu_port_eval(args.cpu_samples, N, T, make_data(N, T))
             cpu = {"value": args.cpu_samples * N / sec, "unit": "trial-evals/s", "cores": os.cpu_count() or 1, "kind": "port",
                    "sample": f"{args.cpu_samples} parameter samples x {N} trials x T={T}, one fwd+grad eval by torch-float64 "
                              f"autograd over the oracle's restatement of the reference scans ({sec:.1f} s)"}

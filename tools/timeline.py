@@ -20,7 +20,7 @@ dev = torch.device("cuda:0")
 lib = abi.load_library()
 lib.set_streams(a.streams)
 N, T, S = 100, 1200, a.samples
-X = torch.tensor(bench.make_data(N, T), device=dev)
+X = bench.make_data_gpu(N, T, dev)
 theta = torch.tensor(bench.make_theta(S, 11), device=dev)
 m = SubjectiveActor(dim=2, T=T, device=dev, **{n: theta[:, i] for i, n in enumerate(bench.PARAM_NAMES)})._axis_system
 xk = X.reshape(N, T + 1, 2, 2).permute(2, 0, 1, 3).reshape(2 * N, T + 1, 2).contiguous()
