@@ -188,6 +188,38 @@ def bench_c2(dev, reps=10):
     return len(sig) * N / (ms * 1e-3), ms
 
 
+def bench_c4(dev, S=4096, N=50, T=600, reps=2):
+    """Config c4 of BASELINE.json: TemporalDelayModel(PointMassBoundedActor(T=600), delay=2) -- 12-dim state, joint dim 24
+    (large-system kernels, lqgk_big.cuh) --, 4,096 parameter samples x 50 trials, log-likelihood + gradient w.r.t. 4
+    parameters per sample through the public API.  Returns (trial-evals/s, ms per evaluation)."""
+    from lqg_b200.tracking import PointMassBoundedActor
+    from lqg_b200.tracking.delay import TemporalDelayModel
+    base = dict(action_variability=1e-3, sigma_target=6.0, sigma_cursor=6.0, action_cost=0.01)
+    x = TemporalDelayModel(PointMassBoundedActor(T=T, device=dev, **base), 2).simulate(13, n=N)[..., :2].to(torch.float32)
+    rng = np.random.default_rng(17)
+    th = {k: torch.tensor(v * np.exp(0.25 * rng.standard_normal(S)), dtype=torch.float32, device=dev, requires_grad=True)
+          for k, v in base.items()}
+
+    def evaluate():
+        for t in th.values():
+            t.grad = None
+        ll = TemporalDelayModel(PointMassBoundedActor(T=T, device=dev, **th), 2).log_likelihood(x).sum()
+        ll.backward()
+        return ll
+
+    evaluate()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        ll = evaluate()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    assert torch.isfinite(ll) and all(torch.isfinite(t.grad).all() for t in th.values())
+    return S * N / (ms * 1e-3), ms
+
+
 # ----------------------------------------------------------------------------------------------- reference arm
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -423,6 +455,12 @@ def run_ours(args):
             secondary = {"workload": "c2: SubjectiveActor dim=2, 6 conditions x 20 trials x T=1200, grad wrt 5 shared + 6 per-condition "
                                      "parameters, one fused call through the public API (latency-bound: 6 systems)",
                          "value": c2_val, "unit": "trial-evals/s", "ms_per_eval": c2_ms}
+            if not args.no_c4:
+                c4_val, c4_ms = bench_c4(dev)
+                secondary = [secondary,
+                             {"workload": "c4: TemporalDelayModel(PointMassBoundedActor, delay=2) (x=b=12, joint dim 24), 4,096 parameter "
+                                          "samples x 50 trials x T=600, grad wrt 4 parameters per sample, public API (large-system kernels)",
+                              "value": c4_val, "unit": "trial-evals/s", "ms_per_eval": c4_ms}]
         line = {"metric": "trial log-lik+grad evals/sec", "value": value, "unit": "trial-evals/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64 per-sample recursions + f32 per-trial recursions (f32 I/O)",
@@ -480,6 +518,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=0, help="max samples per internal workspace chunk (0 = as many as fit)")
     ap.add_argument("--cpu-samples", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c4", action="store_true", help="skip the secondary c4 (large-system) measurement")
     ap.add_argument("--streams", type=int, default=0, help="internal concurrent sample slices (0 = library default)")
     ap.add_argument("--contrib-warps", type=int, default=0)
     ap.add_argument("--overlap", type=int, default=-1, help="kernel-overlap mask (see lqgk_set_kernel_overlap); -1 = library default")

@@ -26,6 +26,19 @@
 #define LQGK_HD inline
 #define LQGK_UNROLL
 #endif
+// Loops of the per-sample FP64 recursions: fully unrolled (matrices in registers) for the small systems; systems
+// compiled with -DLQGK_BIG (joint dim > 12, e.g. the 24-dim delayed point-mass model of config c4) keep them rolled --
+// their matrices live in local memory and a fully unrolled body would neither fit registers nor compile in minutes.
+#if defined(__CUDACC__) && !defined(LQGK_BIG)
+#define LQGK_UNROLL64 _Pragma("unroll")
+#elif defined(__CUDACC__)
+// No pragma at all (the compiler's own heuristics): with `#pragma unroll 1` on these loop nests the NVVM optimiser of
+// CUDA 12.9 (-O3; correct at -Xcicc -O1) miscompiled cov_fwd_body -- device results differed from the host run of the
+// same code (gpurun_scratch/dbg_body.cu reproduces it) -- while the un-annotated loops compile correctly.
+#define LQGK_UNROLL64
+#else
+#define LQGK_UNROLL64
+#endif
 
 namespace lqgk {
 
@@ -92,34 +105,34 @@ struct WView {
 // Small dense helpers on row-major statically sized arrays.  Fully unrolled on the device.
 template <int M, int K, int N, bool ACC = false, class TA, class TB, class TC>
 LQGK_HD void mm(const TA* A, const TB* Bm, TC* C) {  // C[M,N] (+)= A[M,K] B[K,N]
-  LQGK_UNROLL for (int i = 0; i < M; ++i) LQGK_UNROLL for (int j = 0; j < N; ++j) {
+  LQGK_UNROLL64 for (int i = 0; i < M; ++i) LQGK_UNROLL64 for (int j = 0; j < N; ++j) {
     TC acc = ACC ? C[i * N + j] : TC(0);
-    LQGK_UNROLL for (int k = 0; k < K; ++k) acc += A[i * K + k] * Bm[k * N + j];
+    LQGK_UNROLL64 for (int k = 0; k < K; ++k) acc += A[i * K + k] * Bm[k * N + j];
     C[i * N + j] = acc;
   }
 }
 template <int M, int K, int N, bool ACC = false, class TA, class TB, class TC>
 LQGK_HD void mm_nt(const TA* A, const TB* Bm, TC* C) {  // C[M,N] (+)= A[M,K] B[N,K]^T
-  LQGK_UNROLL for (int i = 0; i < M; ++i) LQGK_UNROLL for (int j = 0; j < N; ++j) {
+  LQGK_UNROLL64 for (int i = 0; i < M; ++i) LQGK_UNROLL64 for (int j = 0; j < N; ++j) {
     TC acc = ACC ? C[i * N + j] : TC(0);
-    LQGK_UNROLL for (int k = 0; k < K; ++k) acc += A[i * K + k] * Bm[j * K + k];
+    LQGK_UNROLL64 for (int k = 0; k < K; ++k) acc += A[i * K + k] * Bm[j * K + k];
     C[i * N + j] = acc;
   }
 }
 template <int M, int K, int N, bool ACC = false, class TA, class TB, class TC>
 LQGK_HD void mm_tn(const TA* A, const TB* Bm, TC* C) {  // C[M,N] (+)= A[K,M]^T B[K,N]
-  LQGK_UNROLL for (int i = 0; i < M; ++i) LQGK_UNROLL for (int j = 0; j < N; ++j) {
+  LQGK_UNROLL64 for (int i = 0; i < M; ++i) LQGK_UNROLL64 for (int j = 0; j < N; ++j) {
     TC acc = ACC ? C[i * N + j] : TC(0);
-    LQGK_UNROLL for (int k = 0; k < K; ++k) acc += A[k * M + i] * Bm[k * N + j];
+    LQGK_UNROLL64 for (int k = 0; k < K; ++k) acc += A[k * M + i] * Bm[k * N + j];
     C[i * N + j] = acc;
   }
 }
 // C[M,M] (+)= A[M,K] B[M,K]^T where the result is known symmetric: lower triangle computed, mirrored.
 template <int M, int K, bool ACC = false>
 LQGK_HD void mm_nt_sym(const double* A, const double* Bm, double* C) {
-  LQGK_UNROLL for (int i = 0; i < M; ++i) LQGK_UNROLL for (int j = 0; j <= i; ++j) {
+  LQGK_UNROLL64 for (int i = 0; i < M; ++i) LQGK_UNROLL64 for (int j = 0; j <= i; ++j) {
     double acc = ACC ? C[i * M + j] : 0.0;
-    LQGK_UNROLL for (int k = 0; k < K; ++k) acc += A[i * K + k] * Bm[j * K + k];
+    LQGK_UNROLL64 for (int k = 0; k < K; ++k) acc += A[i * K + k] * Bm[j * K + k];
     C[i * M + j] = acc;
     C[j * M + i] = acc;
   }
@@ -127,16 +140,16 @@ LQGK_HD void mm_nt_sym(const double* A, const double* Bm, double* C) {
 // C[M,M] (+)= A[K,M]^T B[K,M], result known symmetric.
 template <int M, int K, bool ACC = false>
 LQGK_HD void mm_tn_sym(const double* A, const double* Bm, double* C) {
-  LQGK_UNROLL for (int i = 0; i < M; ++i) LQGK_UNROLL for (int j = 0; j <= i; ++j) {
+  LQGK_UNROLL64 for (int i = 0; i < M; ++i) LQGK_UNROLL64 for (int j = 0; j <= i; ++j) {
     double acc = ACC ? C[i * M + j] : 0.0;
-    LQGK_UNROLL for (int k = 0; k < K; ++k) acc += A[k * M + i] * Bm[k * M + j];
+    LQGK_UNROLL64 for (int k = 0; k < K; ++k) acc += A[k * M + i] * Bm[k * M + j];
     C[i * M + j] = acc;
     C[j * M + i] = acc;
   }
 }
 template <int M>
 LQGK_HD void symmetrize(double* C) {  // C <- (C + C^T)/2
-  LQGK_UNROLL for (int i = 0; i < M; ++i) LQGK_UNROLL for (int j = 0; j < i; ++j) {
+  LQGK_UNROLL64 for (int i = 0; i < M; ++i) LQGK_UNROLL64 for (int j = 0; j < i; ++j) {
     double v = 0.5 * (C[i * M + j] + C[j * M + i]);
     C[i * M + j] = v;
     C[j * M + i] = v;
@@ -144,7 +157,7 @@ LQGK_HD void symmetrize(double* C) {  // C <- (C + C^T)/2
 }
 template <int M, class V>
 LQGK_HD void load_sym(const V& v, int off, double* C) {  // packed lower -> full
-  LQGK_UNROLL for (int i = 0; i < M; ++i) LQGK_UNROLL for (int j = 0; j <= i; ++j) {
+  LQGK_UNROLL64 for (int i = 0; i < M; ++i) LQGK_UNROLL64 for (int j = 0; j <= i; ++j) {
     double a = v(off + i * (i + 1) / 2 + j);
     C[i * M + j] = a;
     C[j * M + i] = a;
@@ -152,20 +165,20 @@ LQGK_HD void load_sym(const V& v, int off, double* C) {  // packed lower -> full
 }
 template <int M, int N, class V>
 LQGK_HD void load_mat(const V& v, int off, double* C) {
-  LQGK_UNROLL for (int i = 0; i < M * N; ++i) C[i] = v(off + i);
+  LQGK_UNROLL64 for (int i = 0; i < M * N; ++i) C[i] = v(off + i);
 }
 // In-place Cholesky of a symmetric positive definite M x M matrix (lower factor; upper part untouched).
 template <int M>
 LQGK_HD void chol(double* A) {
-  LQGK_UNROLL for (int j = 0; j < M; ++j) {
+  LQGK_UNROLL64 for (int j = 0; j < M; ++j) {
     double djj = A[j * M + j];
-    LQGK_UNROLL for (int k = 0; k < j; ++k) djj -= A[j * M + k] * A[j * M + k];
+    LQGK_UNROLL64 for (int k = 0; k < j; ++k) djj -= A[j * M + k] * A[j * M + k];
     djj = sqrt(djj);
     A[j * M + j] = djj;
     double inv = 1.0 / djj;
-    LQGK_UNROLL for (int i = j + 1; i < M; ++i) {
+    LQGK_UNROLL64 for (int i = j + 1; i < M; ++i) {
       double v = A[i * M + j];
-      LQGK_UNROLL for (int k = 0; k < j; ++k) v -= A[i * M + k] * A[j * M + k];
+      LQGK_UNROLL64 for (int k = 0; k < j; ++k) v -= A[i * M + k] * A[j * M + k];
       A[i * M + j] = v * inv;
     }
   }
@@ -173,12 +186,12 @@ LQGK_HD void chol(double* A) {
 // Inverse of a lower-triangular matrix (lower part of Lc) into Li (lower part; upper part zeroed).
 template <int M>
 LQGK_HD void tri_inv(const double* Lc, double* Li) {
-  LQGK_UNROLL for (int i = 0; i < M * M; ++i) Li[i] = 0.0;
-  LQGK_UNROLL for (int j = 0; j < M; ++j) {
+  LQGK_UNROLL64 for (int i = 0; i < M * M; ++i) Li[i] = 0.0;
+  LQGK_UNROLL64 for (int j = 0; j < M; ++j) {
     Li[j * M + j] = 1.0 / Lc[j * M + j];
-    LQGK_UNROLL for (int i = j + 1; i < M; ++i) {
+    LQGK_UNROLL64 for (int i = j + 1; i < M; ++i) {
       double v = 0.0;
-      LQGK_UNROLL for (int k = j; k < i; ++k) v -= Lc[i * M + k] * Li[k * M + j];
+      LQGK_UNROLL64 for (int k = j; k < i; ++k) v -= Lc[i * M + k] * Li[k * M + j];
       Li[i * M + j] = v / Lc[i * M + i];
     }
   }
@@ -262,52 +275,52 @@ struct LqrFwd {
     mm_tn<U, B, B>(Bm, SA, G);                   // G = B^T S A (+ P)          lqr.py:23
     double g[U];
     if (AFFINE) {
-      LQGK_UNROLL for (int i = 0; i < U * B; ++i) G[i] += c(C::P + i);
-      LQGK_UNROLL for (int i = 0; i < U; ++i) {
+      LQGK_UNROLL64 for (int i = 0; i < U * B; ++i) G[i] += c(C::P + i);
+      LQGK_UNROLL64 for (int i = 0; i < U; ++i) {
         double a = c(C::r + i);
-        LQGK_UNROLL for (int k = 0; k < B; ++k) a += Bm[k * U + i] * s[k];   // g = r + B^T s   lqr.py:24
+        LQGK_UNROLL64 for (int k = 0; k < B; ++k) a += Bm[k * U + i] * s[k];   // g = r + B^T s   lqr.py:24
         g[i] = a;
       }
     }
     shift = eps - lambda_min<U>(H);              // lqr.py:27-28
     shift = shift > 0.0 ? shift : 0.0;
     double Lc[U * U];
-    LQGK_UNROLL for (int i = 0; i < U * U; ++i) { Lc[i] = H[i]; Ht[i] = H[i]; }
-    LQGK_UNROLL for (int i = 0; i < U; ++i) { Lc[i * U + i] += shift; Ht[i * U + i] += shift; }
+    LQGK_UNROLL64 for (int i = 0; i < U * U; ++i) { Lc[i] = H[i]; Ht[i] = H[i]; }
+    LQGK_UNROLL64 for (int i = 0; i < U; ++i) { Lc[i * U + i] += shift; Ht[i * U + i] += shift; }
     chol<U>(Lc);                                  // Ht is SPD after the shift
     double Li[U * U], Hi[U * U];
     tri_inv<U>(Lc, Li);
     mm_tn<U, U, U>(Li, Li, Hi);                   // Ht^-1
     mm<U, U, B>(Hi, G, L);
-    LQGK_UNROLL for (int i = 0; i < U * B; ++i) L[i] = -L[i];                 // L = -Ht^-1 G   lqr.py:30
+    LQGK_UNROLL64 for (int i = 0; i < U * B; ++i) L[i] = -L[i];                 // L = -Ht^-1 G   lqr.py:30
     // S <- Q + A^T S A + L^T H L + L^T G + G^T L      (un-shifted H)       lqr.py:33
     double HL[U * B];
     mm<U, U, B>(H, L, HL);
-    LQGK_UNROLL for (int i = 0; i < U * B; ++i) HL[i] += 2.0 * G[i];          // L^T(HL + 2G) sym part
+    LQGK_UNROLL64 for (int i = 0; i < U * B; ++i) HL[i] += 2.0 * G[i];          // L^T(HL + 2G) sym part
     double Sn[B * B];
     load_sym<B>(c, C::Q, Sn);
     mm_tn_sym<B, B, true>(A, SA, Sn);
     // L^T H L + L^T G + G^T L = sym(L^T (H L + 2 G))
-    LQGK_UNROLL for (int i = 0; i < B; ++i) LQGK_UNROLL for (int j = 0; j <= i; ++j) {
+    LQGK_UNROLL64 for (int i = 0; i < B; ++i) LQGK_UNROLL64 for (int j = 0; j <= i; ++j) {
       double a = 0.0;
-      LQGK_UNROLL for (int k = 0; k < U; ++k) a += L[k * B + i] * HL[k * B + j] + L[k * B + j] * HL[k * B + i];
+      LQGK_UNROLL64 for (int k = 0; k < U; ++k) a += L[k * B + i] * HL[k * B + j] + L[k * B + j] * HL[k * B + i];
       Sn[i * B + j] += 0.5 * a;
       if (i != j) Sn[j * B + i] += 0.5 * a;
     }
     if (AFFINE) {
       mm<U, U, 1>(Hi, g, l);
-      LQGK_UNROLL for (int i = 0; i < U; ++i) l[i] = -l[i];                   // l = -Ht^-1 g   lqr.py:31
+      LQGK_UNROLL64 for (int i = 0; i < U; ++i) l[i] = -l[i];                   // l = -Ht^-1 g   lqr.py:31
       double Hl[U], sn[B];
       mm<U, U, 1>(H, l, Hl);
-      LQGK_UNROLL for (int i = 0; i < B; ++i) {                               // lqr.py:34
+      LQGK_UNROLL64 for (int i = 0; i < B; ++i) {                               // lqr.py:34
         double a = c(C::q + i);
-        LQGK_UNROLL for (int k = 0; k < B; ++k) a += A[k * B + i] * s[k];
-        LQGK_UNROLL for (int k = 0; k < U; ++k) a += G[k * B + i] * l[k] + L[k * B + i] * (Hl[k] + g[k]);
+        LQGK_UNROLL64 for (int k = 0; k < B; ++k) a += A[k * B + i] * s[k];
+        LQGK_UNROLL64 for (int k = 0; k < U; ++k) a += G[k * B + i] * l[k] + L[k * B + i] * (Hl[k] + g[k]);
         sn[i] = a;
       }
-      LQGK_UNROLL for (int i = 0; i < B; ++i) s[i] = sn[i];
+      LQGK_UNROLL64 for (int i = 0; i < B; ++i) s[i] = sn[i];
     }
-    LQGK_UNROLL for (int i = 0; i < B * B; ++i) S[i] = Sn[i];
+    LQGK_UNROLL64 for (int i = 0; i < B * B; ++i) S[i] = Sn[i];
   }
 };
 
@@ -356,9 +369,9 @@ struct KfFwd {
     double Pp[B * B], M[Y * B], Gi[Y * Y];
     gain(c, P, Pp, M, Gi, K);
     // P <- (I - K F) Pp = Pp - K M   (symmetric)                               kf.py:14
-    LQGK_UNROLL for (int i = 0; i < B; ++i) LQGK_UNROLL for (int j = 0; j <= i; ++j) {
+    LQGK_UNROLL64 for (int i = 0; i < B; ++i) LQGK_UNROLL64 for (int j = 0; j <= i; ++j) {
       double a = Pp[i * B + j];
-      LQGK_UNROLL for (int k = 0; k < Y; ++k) a -= 0.5 * (K[i * Y + k] * M[k * B + j] + K[j * Y + k] * M[k * B + i]);
+      LQGK_UNROLL64 for (int k = 0; k < Y; ++k) a -= 0.5 * (K[i * Y + k] * M[k * B + j] + K[j * Y + k] * M[k * B + i]);
       P[i * B + j] = a;
       P[j * B + i] = a;
     }
@@ -398,24 +411,24 @@ struct CovFwd {
       load_mat<Y, U>(c, C::Dm, Dm);
       mm<B, Y, U>(K, Dm, KD);
     }
-    LQGK_UNROLL for (int i = 0; i < X; ++i) {
-      LQGK_UNROLL for (int j = 0; j < X; ++j) Fj[i * N + j] = c(C::Ad + i * X + j);
-      LQGK_UNROLL for (int j = 0; j < B; ++j) {
+    LQGK_UNROLL64 for (int i = 0; i < X; ++i) {
+      LQGK_UNROLL64 for (int j = 0; j < X; ++j) Fj[i * N + j] = c(C::Ad + i * X + j);
+      LQGK_UNROLL64 for (int j = 0; j < B; ++j) {
         double a = 0.0;
-        LQGK_UNROLL for (int k = 0; k < U; ++k) a += c(C::Bd + i * U + k) * L[k * B + j];
+        LQGK_UNROLL64 for (int k = 0; k < U; ++k) a += c(C::Bd + i * U + k) * L[k * B + j];
         Fj[i * N + X + j] = a;                                        // Bd L
       }
     }
-    LQGK_UNROLL for (int i = 0; i < B; ++i) {
-      LQGK_UNROLL for (int j = 0; j < X; ++j) {
+    LQGK_UNROLL64 for (int i = 0; i < B; ++i) {
+      LQGK_UNROLL64 for (int j = 0; j < X; ++j) {
         double a = 0.0;
-        LQGK_UNROLL for (int k = 0; k < Y; ++k) a += K[i * Y + k] * c(C::FAd + k * X + j);
+        LQGK_UNROLL64 for (int k = 0; k < Y; ++k) a += K[i * Y + k] * c(C::FAd + k * X + j);
         Fj[(X + i) * N + j] = a;                                      // K Fd Ad
       }
-      LQGK_UNROLL for (int j = 0; j < B; ++j) {
+      LQGK_UNROLL64 for (int j = 0; j < B; ++j) {
         double a = c(C::Aa + i * B + j);
-        LQGK_UNROLL for (int k = 0; k < U; ++k) a += (c(C::Ba + i * U + k) + KD[i * U + k]) * L[k * B + j];
-        LQGK_UNROLL for (int k = 0; k < Y; ++k) a -= K[i * Y + k] * c(C::FAa + k * B + j);
+        LQGK_UNROLL64 for (int k = 0; k < U; ++k) a += (c(C::Ba + i * U + k) + KD[i * U + k]) * L[k * B + j];
+        LQGK_UNROLL64 for (int k = 0; k < Y; ++k) a -= K[i * Y + k] * c(C::FAa + k * B + j);
         Fj[(X + i) * N + X + j] = a;                                  // Aa + Ba L - K Fa Aa + K D L
       }
     }
@@ -426,66 +439,69 @@ struct CovFwd {
     double Om[Y * Y], KO[B * Y];
     load_sym<Y>(c, C::Om, Om);
     mm<B, Y, Y>(K, Om, KO);
-    LQGK_UNROLL for (int i = 0; i < X; ++i) LQGK_UNROLL for (int j = 0; j <= i; ++j) {
+    LQGK_UNROLL64 for (int i = 0; i < X; ++i) LQGK_UNROLL64 for (int j = 0; j <= i; ++j) {
       double a = c(C::N11 + i * (i + 1) / 2 + j);
       Nj[i * N + j] = a;
       Nj[j * N + i] = a;
     }
-    LQGK_UNROLL for (int i = 0; i < B; ++i) {
-      LQGK_UNROLL for (int j = 0; j < X; ++j) {
+    LQGK_UNROLL64 for (int i = 0; i < B; ++i) {
+      LQGK_UNROLL64 for (int j = 0; j < X; ++j) {
         double a = 0.0;
-        LQGK_UNROLL for (int k = 0; k < Y; ++k) a += K[i * Y + k] * c(C::FN + k * X + j);
+        LQGK_UNROLL64 for (int k = 0; k < Y; ++k) a += K[i * Y + k] * c(C::FN + k * X + j);
         Nj[(X + i) * N + j] = a;
         Nj[j * N + X + i] = a;
       }
-      LQGK_UNROLL for (int j = 0; j <= i; ++j) {
+      LQGK_UNROLL64 for (int j = 0; j <= i; ++j) {
         double a = 0.0;
-        LQGK_UNROLL for (int k = 0; k < Y; ++k) a += KO[i * Y + k] * K[j * Y + k];
+        LQGK_UNROLL64 for (int k = 0; k < Y; ++k) a += KO[i * Y + k] * K[j * Y + k];
         Nj[(X + i) * N + X + j] = a;
         Nj[(X + j) * N + X + i] = a;
       }
     }
   }
   // Condition Sig (full symmetric N x N) on its first D coordinates:
-  //   Linv = chol(S)^-1 (lower), logdet = sum log diag chol(S), J = Sig[u,o] S^-1 (R x D),
-  //   C = Sig[u,u] - J S J^T (R x R full symmetric).
-  LQGK_HD static void condition(const double* Sig, double* Linv, double& logdet, double* J, double* Cn) {
+  //   Linv = chol(S)^-1 (lower), logdet = sum log diag chol(S), J = Sig[u,o] S^-1 (R x D, handed element by element to
+  //   emit_j(index, value)), C = Sig[u,u] - J S J^T (R x R full symmetric).
+  // J is emitted rather than returned in an array: with the rolled loops of the large-system build nvcc 12.9 gave a
+  // caller-side J array the same local-memory slot as Cn (the record then held rows of C instead of J).
+  template <class EmitJ>
+  LQGK_HD static void condition(const double* Sig, double* Linv, double& logdet, EmitJ&& emit_j, double* Cn) {
     double Lc[D * D];
-    LQGK_UNROLL for (int i = 0; i < D; ++i) LQGK_UNROLL for (int j = 0; j < D; ++j) Lc[i * D + j] = Sig[i * N + j];
+    LQGK_UNROLL64 for (int i = 0; i < D; ++i) LQGK_UNROLL64 for (int j = 0; j < D; ++j) Lc[i * D + j] = Sig[i * N + j];
     chol<D>(Lc);
     logdet = 0.0;
-    LQGK_UNROLL for (int i = 0; i < D; ++i) logdet += log(Lc[i * D + i]);
+    LQGK_UNROLL64 for (int i = 0; i < D; ++i) logdet += log(Lc[i * D + i]);
     tri_inv<D>(Lc, Linv);
     double Z[R * D];                                                 // Z = Sig[u,o] Linv^T
-    LQGK_UNROLL for (int i = 0; i < R; ++i) LQGK_UNROLL for (int j = 0; j < D; ++j) {
+    LQGK_UNROLL64 for (int i = 0; i < R; ++i) LQGK_UNROLL64 for (int j = 0; j < D; ++j) {
       double a = 0.0;
-      LQGK_UNROLL for (int k = 0; k <= j; ++k) a += Sig[(D + i) * N + k] * Linv[j * D + k];
+      LQGK_UNROLL64 for (int k = 0; k <= j; ++k) a += Sig[(D + i) * N + k] * Linv[j * D + k];
       Z[i * D + j] = a;
     }
-    LQGK_UNROLL for (int i = 0; i < R; ++i) LQGK_UNROLL for (int j = 0; j < D; ++j) {
+    LQGK_UNROLL64 for (int i = 0; i < R; ++i) LQGK_UNROLL64 for (int j = 0; j < D; ++j) {
       double a = 0.0;
-      LQGK_UNROLL for (int k = j; k < D; ++k) a += Z[i * D + k] * Linv[k * D + j];
-      J[i * D + j] = a;                                              // J = Z Linv
+      LQGK_UNROLL64 for (int k = j; k < D; ++k) a += Z[i * D + k] * Linv[k * D + j];
+      emit_j(i * D + j, a);                                          // J = Z Linv
     }
-    LQGK_UNROLL for (int i = 0; i < R; ++i) LQGK_UNROLL for (int j = 0; j <= i; ++j) {
+    LQGK_UNROLL64 for (int i = 0; i < R; ++i) LQGK_UNROLL64 for (int j = 0; j <= i; ++j) {
       double a = Sig[(D + i) * N + D + j];
-      LQGK_UNROLL for (int k = 0; k < D; ++k) a -= Z[i * D + k] * Z[j * D + k];
+      LQGK_UNROLL64 for (int k = 0; k < D; ++k) a -= Z[i * D + k] * Z[j * D + k];
       Cn[i * R + j] = a;
       Cn[j * R + i] = a;
     }
   }
   // Sig' = F[:,u] C F[:,u]^T + N   (full symmetric N x N)
   LQGK_HD static void predict(const double* Fj, const double* Cm, const double* Nj, double* Sig) {
-    LQGK_UNROLL for (int i = 0; i < N; ++i) {
+    LQGK_UNROLL64 for (int i = 0; i < N; ++i) {
       double t1[R];
-      LQGK_UNROLL for (int k = 0; k < R; ++k) {
+      LQGK_UNROLL64 for (int k = 0; k < R; ++k) {
         double a = 0.0;
-        LQGK_UNROLL for (int m = 0; m < R; ++m) a += Fj[i * N + D + m] * Cm[m * R + k];
+        LQGK_UNROLL64 for (int m = 0; m < R; ++m) a += Fj[i * N + D + m] * Cm[m * R + k];
         t1[k] = a;
       }
-      LQGK_UNROLL for (int j = 0; j <= i; ++j) {
+      LQGK_UNROLL64 for (int j = 0; j <= i; ++j) {
         double a = Nj[i * N + j];
-        LQGK_UNROLL for (int k = 0; k < R; ++k) a += t1[k] * Fj[j * N + D + k];
+        LQGK_UNROLL64 for (int k = 0; k < R; ++k) a += t1[k] * Fj[j * N + D + k];
         Sig[i * N + j] = a;
         Sig[j * N + i] = a;
       }
@@ -496,7 +512,7 @@ struct CovFwd {
   LQGK_HD static void init(const V& c, const double* K0, double* Cm, double* J0) {
     double Nj[N * N], Linv[D * D], ld;
     joint_N(c, K0, Nj);
-    condition(Nj, Linv, ld, J0, Cm);
+    condition(Nj, Linv, ld, [&](int i, double v) { J0[i] = v; }, Cm);
   }
   // One step: C_t -> C_{t+1}; emits the float record for the trial kernels through `put(idx, value)`.
   // save(which, e, v): optional FP64 outputs for the adjoint: which 0 = Fu_t (N x R row-major), 1 = J_t then S'^-1_t.
@@ -506,17 +522,16 @@ struct CovFwd {
     joint_F(c, L, K, Fj);
     // the observed rows are stored negated so the trial kernels form e = x1 + (-F[o,:]) [x0; c] with plain FMAs, starting
     // from x1 (x1 - x0 is exact when A_d = I, which keeps the residual accurate in FP32)
-    LQGK_UNROLL for (int i = 0; i < N * N; ++i) put(DM::REC_F + i, (float)(i < D * N ? -Fj[i] : Fj[i]));
-    LQGK_UNROLL for (int i = 0; i < N; ++i) LQGK_UNROLL for (int j = 0; j < R; ++j) save(0, i * R + j, Fj[i * N + D + j]);
+    LQGK_UNROLL64 for (int i = 0; i < N * N; ++i) put(DM::REC_F + i, (float)(i < D * N ? -Fj[i] : Fj[i]));
+    LQGK_UNROLL64 for (int i = 0; i < N; ++i) LQGK_UNROLL64 for (int j = 0; j < R; ++j) save(0, i * R + j, Fj[i * N + D + j]);
     joint_N(c, K, Nj);
     predict(Fj, Cm, Nj, Sig);
-    double Linv[D * D], J[R * D], ld;
-    condition(Sig, Linv, ld, J, Cm);
-    LQGK_UNROLL for (int i = 0; i < R * D; ++i) { put(DM::REC_J + i, (float)J[i]); save(1, i, J[i]); }
-    LQGK_UNROLL for (int i = 0; i < D; ++i) LQGK_UNROLL for (int j = 0; j <= i; ++j) {
+    double Linv[D * D], ld;
+    condition(Sig, Linv, ld, [&](int i, double v) { put(DM::REC_J + i, (float)v); save(1, i, v); }, Cm);
+    LQGK_UNROLL64 for (int i = 0; i < D; ++i) LQGK_UNROLL64 for (int j = 0; j <= i; ++j) {
       put(DM::REC_LINV + i * (i + 1) / 2 + j, (float)Linv[i * D + j]);
       double sv = 0.0;
-      LQGK_UNROLL for (int k = i; k < D; ++k) sv += Linv[k * D + i] * Linv[k * D + j];   // (Linv^T Linv)[i][j], i >= j
+      LQGK_UNROLL64 for (int k = i; k < D; ++k) sv += Linv[k * D + i] * Linv[k * D + j];   // (Linv^T Linv)[i][j], i >= j
       save(1, R * D + i * (i + 1) / 2 + j, sv);
     }
     put(DM::REC_LOGDET, (float)ld);
@@ -703,63 +718,63 @@ struct CovSeqRev {
   LQGK_HD static void step(FU&& fu, JS&& js, Get&& get, double sw, SC&& sc, double* Cb, ESgb&& esgb, ESf&& esf) {
     {
       double J[R * D], Sinv[D * D], Ss[D * D];
-      LQGK_UNROLL for (int e = 0; e < R * D; ++e) J[e] = js(e);
-      LQGK_UNROLL for (int i = 0; i < D; ++i) LQGK_UNROLL for (int j = 0; j <= i; ++j) {
+      LQGK_UNROLL64 for (int e = 0; e < R * D; ++e) J[e] = js(e);
+      LQGK_UNROLL64 for (int i = 0; i < D; ++i) LQGK_UNROLL64 for (int j = 0; j <= i; ++j) {
         double a = js(R * D + i * (i + 1) / 2 + j);
         Sinv[i * D + j] = a;
         Sinv[j * D + i] = a;
         Ss[i * D + j] = 0.5 * (double)get(DM::SUM_W + i * (i + 1) / 2 + j) - 0.5 * sw * a;
       }
-      LQGK_UNROLL for (int i = 0; i < R; ++i) {
+      LQGK_UNROLL64 for (int i = 0; i < R; ++i) {
         double z[D];
-        LQGK_UNROLL for (int j = 0; j < D; ++j) {
+        LQGK_UNROLL64 for (int j = 0; j < D; ++j) {
           double cbj = 0.0, jbs = 0.0;
-          LQGK_UNROLL for (int k = 0; k < R; ++k) cbj += Cb[i * R + k] * J[k * D + j];
-          LQGK_UNROLL for (int k = 0; k < D; ++k) jbs += (double)get(DM::SUM_J + i * D + k) * Sinv[k * D + j];
+          LQGK_UNROLL64 for (int k = 0; k < R; ++k) cbj += Cb[i * R + k] * J[k * D + j];
+          LQGK_UNROLL64 for (int k = 0; k < D; ++k) jbs += (double)get(DM::SUM_J + i * D + k) * Sinv[k * D + j];
           z[j] = cbj - jbs;
           double bh = -cbj + 0.5 * jbs;
           sc(SC_BH + i * D + j) = bh;
           esgb(sidx(D + i, j), bh);
         }
-        LQGK_UNROLL for (int a = 0; a < D; ++a) LQGK_UNROLL for (int b = 0; b <= a; ++b)
+        LQGK_UNROLL64 for (int a = 0; a < D; ++a) LQGK_UNROLL64 for (int b = 0; b <= a; ++b)
           Ss[a * D + b] += 0.5 * (J[i * D + a] * z[b] + J[i * D + b] * z[a]);
       }
-      LQGK_UNROLL for (int a = 0; a < D; ++a) LQGK_UNROLL for (int b = 0; b <= a; ++b) {
+      LQGK_UNROLL64 for (int a = 0; a < D; ++a) LQGK_UNROLL64 for (int b = 0; b <= a; ++b) {
         sc(SC_SS + a * (a + 1) / 2 + b) = Ss[a * D + b];
         esgb(sidx(a, b), Ss[a * D + b]);
       }
-      LQGK_UNROLL for (int i = 0; i < R; ++i) LQGK_UNROLL for (int j = 0; j <= i; ++j) esgb(sidx(D + i, D + j), Cb[i * R + j]);
+      LQGK_UNROLL64 for (int i = 0; i < R; ++i) LQGK_UNROLL64 for (int j = 0; j <= i; ++j) esgb(sidx(D + i, D + j), Cb[i * R + j]);
     }
     double Fo[D * R], Fuu[R * R], Cn[R * R];
-    LQGK_UNROLL for (int e = 0; e < D * R; ++e) Fo[e] = fu(e);
-    LQGK_UNROLL for (int e = 0; e < R * R; ++e) Fuu[e] = fu(D * R + e);
-    LQGK_UNROLL for (int e = 0; e < R * R; ++e) Cn[e] = 0.0;
-    LQGK_UNROLL for (int i = 0; i < R; ++i) {            // SF_u row i = Bh[i,:] Fo + Cb[i,:] Fuu
+    LQGK_UNROLL64 for (int e = 0; e < D * R; ++e) Fo[e] = fu(e);
+    LQGK_UNROLL64 for (int e = 0; e < R * R; ++e) Fuu[e] = fu(D * R + e);
+    LQGK_UNROLL64 for (int e = 0; e < R * R; ++e) Cn[e] = 0.0;
+    LQGK_UNROLL64 for (int i = 0; i < R; ++i) {            // SF_u row i = Bh[i,:] Fo + Cb[i,:] Fuu
       double row[R];
-      LQGK_UNROLL for (int c = 0; c < R; ++c) row[c] = 0.0;
-      LQGK_UNROLL for (int k = 0; k < D; ++k) {
+      LQGK_UNROLL64 for (int c = 0; c < R; ++c) row[c] = 0.0;
+      LQGK_UNROLL64 for (int k = 0; k < D; ++k) {
         double b = sc(SC_BH + i * D + k);
-        LQGK_UNROLL for (int c = 0; c < R; ++c) row[c] += b * Fo[k * R + c];
+        LQGK_UNROLL64 for (int c = 0; c < R; ++c) row[c] += b * Fo[k * R + c];
       }
-      LQGK_UNROLL for (int k = 0; k < R; ++k) LQGK_UNROLL for (int c = 0; c < R; ++c) row[c] += Cb[i * R + k] * Fuu[k * R + c];
-      LQGK_UNROLL for (int c = 0; c < R; ++c) esf((D + i) * R + c, row[c]);
-      LQGK_UNROLL for (int a = 0; a < R; ++a) LQGK_UNROLL for (int b = 0; b <= a; ++b) Cn[a * R + b] += Fuu[i * R + a] * row[b];
+      LQGK_UNROLL64 for (int k = 0; k < R; ++k) LQGK_UNROLL64 for (int c = 0; c < R; ++c) row[c] += Cb[i * R + k] * Fuu[k * R + c];
+      LQGK_UNROLL64 for (int c = 0; c < R; ++c) esf((D + i) * R + c, row[c]);
+      LQGK_UNROLL64 for (int a = 0; a < R; ++a) LQGK_UNROLL64 for (int b = 0; b <= a; ++b) Cn[a * R + b] += Fuu[i * R + a] * row[b];
     }
-    LQGK_UNROLL for (int k = 0; k < D; ++k) {            // SF_o row k = Ss[k,:] Fo + Bh[:,k]^T Fuu
+    LQGK_UNROLL64 for (int k = 0; k < D; ++k) {            // SF_o row k = Ss[k,:] Fo + Bh[:,k]^T Fuu
       double row[R];
-      LQGK_UNROLL for (int c = 0; c < R; ++c) row[c] = 0.0;
-      LQGK_UNROLL for (int m = 0; m < D; ++m) {
+      LQGK_UNROLL64 for (int c = 0; c < R; ++c) row[c] = 0.0;
+      LQGK_UNROLL64 for (int m = 0; m < D; ++m) {
         double sv = sc(SC_SS + sidx(k, m));
-        LQGK_UNROLL for (int c = 0; c < R; ++c) row[c] += sv * Fo[m * R + c];
+        LQGK_UNROLL64 for (int c = 0; c < R; ++c) row[c] += sv * Fo[m * R + c];
       }
-      LQGK_UNROLL for (int i = 0; i < R; ++i) {
+      LQGK_UNROLL64 for (int i = 0; i < R; ++i) {
         double b = sc(SC_BH + i * D + k);
-        LQGK_UNROLL for (int c = 0; c < R; ++c) row[c] += b * Fuu[i * R + c];
+        LQGK_UNROLL64 for (int c = 0; c < R; ++c) row[c] += b * Fuu[i * R + c];
       }
-      LQGK_UNROLL for (int c = 0; c < R; ++c) esf(k * R + c, row[c]);
-      LQGK_UNROLL for (int a = 0; a < R; ++a) LQGK_UNROLL for (int b = 0; b <= a; ++b) Cn[a * R + b] += Fo[k * R + a] * row[b];
+      LQGK_UNROLL64 for (int c = 0; c < R; ++c) esf(k * R + c, row[c]);
+      LQGK_UNROLL64 for (int a = 0; a < R; ++a) LQGK_UNROLL64 for (int b = 0; b <= a; ++b) Cn[a * R + b] += Fo[k * R + a] * row[b];
     }
-    LQGK_UNROLL for (int a = 0; a < R; ++a) LQGK_UNROLL for (int b = 0; b <= a; ++b) {
+    LQGK_UNROLL64 for (int a = 0; a < R; ++a) LQGK_UNROLL64 for (int b = 0; b <= a; ++b) {
       Cb[a * R + b] = Cn[a * R + b];
       Cb[b * R + a] = Cn[a * R + b];
     }
@@ -768,13 +783,13 @@ struct CovSeqRev {
   template <class J0, class ESgb>
   LQGK_HD static void init(J0&& j0, const double* Cb, ESgb&& esgb) {
     double J[R * D], CbJ[R * D];
-    LQGK_UNROLL for (int e = 0; e < R * D; ++e) J[e] = j0(e);
+    LQGK_UNROLL64 for (int e = 0; e < R * D; ++e) J[e] = j0(e);
     mm<R, R, D>(Cb, J, CbJ);
-    LQGK_UNROLL for (int i = 0; i < R; ++i) LQGK_UNROLL for (int j = 0; j <= i; ++j) esgb(sidx(D + i, D + j), Cb[i * R + j]);
-    LQGK_UNROLL for (int i = 0; i < R; ++i) LQGK_UNROLL for (int j = 0; j < D; ++j) esgb(sidx(D + i, j), -CbJ[i * D + j]);
-    LQGK_UNROLL for (int a = 0; a < D; ++a) LQGK_UNROLL for (int b = 0; b <= a; ++b) {
+    LQGK_UNROLL64 for (int i = 0; i < R; ++i) LQGK_UNROLL64 for (int j = 0; j <= i; ++j) esgb(sidx(D + i, D + j), Cb[i * R + j]);
+    LQGK_UNROLL64 for (int i = 0; i < R; ++i) LQGK_UNROLL64 for (int j = 0; j < D; ++j) esgb(sidx(D + i, j), -CbJ[i * D + j]);
+    LQGK_UNROLL64 for (int a = 0; a < D; ++a) LQGK_UNROLL64 for (int b = 0; b <= a; ++b) {
       double v = 0.0;
-      LQGK_UNROLL for (int k = 0; k < R; ++k) v += J[k * D + a] * CbJ[k * D + b];
+      LQGK_UNROLL64 for (int k = 0; k < R; ++k) v += J[k * D + a] * CbJ[k * D + b];
       esgb(sidx(a, b), v);
     }
   }
@@ -793,11 +808,11 @@ struct CovContrib {
   template <class SFr, class Get>
   LQGK_HD static void fb_row(int m, SFr&& sf, Get&& get, const double* Cm, bool use_trial, double* fb) {
     double sfr[R];
-    LQGK_UNROLL for (int k = 0; k < R; ++k) sfr[k] = sf(m * R + k);
-    LQGK_UNROLL for (int j = 0; j < N; ++j) fb[j] = use_trial ? (double)get(DM::SUM_F + m * N + j) : 0.0;
-    LQGK_UNROLL for (int j = 0; j < R; ++j) {
+    LQGK_UNROLL64 for (int k = 0; k < R; ++k) sfr[k] = sf(m * R + k);
+    LQGK_UNROLL64 for (int j = 0; j < N; ++j) fb[j] = use_trial ? (double)get(DM::SUM_F + m * N + j) : 0.0;
+    LQGK_UNROLL64 for (int j = 0; j < R; ++j) {
       double a = 0.0;
-      LQGK_UNROLL for (int k = 0; k < R; ++k) a += sfr[k] * Cm[k * R + j];
+      LQGK_UNROLL64 for (int k = 0; k < R; ++k) a += sfr[k] * Cm[k * R + j];
       fb[D + j] += 2.0 * a;
     }
   }
@@ -805,23 +820,23 @@ struct CovContrib {
   // n11[tri X], fn[Y*X], om[tri Y] and kb[B*Y].
   template <class V, class SG>
   LQGK_HD static void noise_part(const V& c, SG&& sgb, const double* K, double* n11, double* fn, double* om, double* kb) {
-    LQGK_UNROLL for (int i = 0; i < X; ++i) LQGK_UNROLL for (int j = 0; j <= i; ++j) n11[i * (i + 1) / 2 + j] += sgb(sidx(i, j));
-    LQGK_UNROLL for (int i = 0; i < B; ++i) {
+    LQGK_UNROLL64 for (int i = 0; i < X; ++i) LQGK_UNROLL64 for (int j = 0; j <= i; ++j) n11[i * (i + 1) / 2 + j] += sgb(sidx(i, j));
+    LQGK_UNROLL64 for (int i = 0; i < B; ++i) {
       double nbx[X], nbb[B], nk[Y];
-      LQGK_UNROLL for (int j = 0; j < X; ++j) nbx[j] = sgb(sidx(X + i, j));
-      LQGK_UNROLL for (int j = 0; j < B; ++j) nbb[j] = sgb(sidx(X + i, X + j));
-      LQGK_UNROLL for (int k = 0; k < Y; ++k) {
+      LQGK_UNROLL64 for (int j = 0; j < X; ++j) nbx[j] = sgb(sidx(X + i, j));
+      LQGK_UNROLL64 for (int j = 0; j < B; ++j) nbb[j] = sgb(sidx(X + i, X + j));
+      LQGK_UNROLL64 for (int k = 0; k < Y; ++k) {
         double a = 0.0;
-        LQGK_UNROLL for (int j = 0; j < B; ++j) a += nbb[j] * K[j * Y + k];
+        LQGK_UNROLL64 for (int j = 0; j < B; ++j) a += nbb[j] * K[j * Y + k];
         nk[k] = a;                                                           // (Nbb K)[i, k]
-        LQGK_UNROLL for (int j = 0; j < X; ++j) fn[k * X + j] += 2.0 * K[i * Y + k] * nbx[j];
+        LQGK_UNROLL64 for (int j = 0; j < X; ++j) fn[k * X + j] += 2.0 * K[i * Y + k] * nbx[j];
       }
-      LQGK_UNROLL for (int k = 0; k < Y; ++k) LQGK_UNROLL for (int m = 0; m <= k; ++m)
+      LQGK_UNROLL64 for (int k = 0; k < Y; ++k) LQGK_UNROLL64 for (int m = 0; m <= k; ++m)
         om[k * (k + 1) / 2 + m] += 0.5 * (K[i * Y + k] * nk[m] + K[i * Y + m] * nk[k]);
-      LQGK_UNROLL for (int k = 0; k < Y; ++k) {
+      LQGK_UNROLL64 for (int k = 0; k < Y; ++k) {
         double a = 0.0;
-        LQGK_UNROLL for (int j = 0; j < X; ++j) a += nbx[j] * c(C::FN + k * X + j);
-        LQGK_UNROLL for (int m = 0; m < Y; ++m) a += nk[m] * c(C::Om + sidx(m, k));
+        LQGK_UNROLL64 for (int j = 0; j < X; ++j) a += nbx[j] * c(C::FN + k * X + j);
+        LQGK_UNROLL64 for (int m = 0; m < Y; ++m) a += nk[m] * c(C::Om + sidx(m, k));
         kb[i * Y + k] += 2.0 * a;
       }
     }
@@ -833,77 +848,77 @@ struct CovContrib {
                             const double* L, const double* K, Out&& out, double* Lb, double* Kb) {
     {
       double n11[tri(X)], fn[Y * X], om[tri(Y)];
-      LQGK_UNROLL for (int e = 0; e < tri(X); ++e) n11[e] = 0.0;
-      LQGK_UNROLL for (int e = 0; e < Y * X; ++e) fn[e] = 0.0;
-      LQGK_UNROLL for (int e = 0; e < tri(Y); ++e) om[e] = 0.0;
-      LQGK_UNROLL for (int e = 0; e < B * Y; ++e) Kb[e] = 0.0;
+      LQGK_UNROLL64 for (int e = 0; e < tri(X); ++e) n11[e] = 0.0;
+      LQGK_UNROLL64 for (int e = 0; e < Y * X; ++e) fn[e] = 0.0;
+      LQGK_UNROLL64 for (int e = 0; e < tri(Y); ++e) om[e] = 0.0;
+      LQGK_UNROLL64 for (int e = 0; e < B * Y; ++e) Kb[e] = 0.0;
       noise_part(c, sgb, K, n11, fn, om, Kb);
       if (has_init) noise_part(c, sgb_init, K, n11, fn, om, Kb);
-      LQGK_UNROLL for (int e = 0; e < tri(X); ++e) out(C::N11 + e, n11[e]);
-      LQGK_UNROLL for (int e = 0; e < Y * X; ++e) out(C::FN + e, fn[e]);
-      LQGK_UNROLL for (int e = 0; e < tri(Y); ++e) out(C::Om + e, om[e]);
+      LQGK_UNROLL64 for (int e = 0; e < tri(X); ++e) out(C::N11 + e, n11[e]);
+      LQGK_UNROLL64 for (int e = 0; e < Y * X; ++e) out(C::FN + e, fn[e]);
+      LQGK_UNROLL64 for (int e = 0; e < tri(Y); ++e) out(C::Om + e, om[e]);
     }
     double KD[B * U], fad[Y * X];
-    LQGK_UNROLL for (int i = 0; i < B; ++i) LQGK_UNROLL for (int m = 0; m < U; ++m) {
+    LQGK_UNROLL64 for (int i = 0; i < B; ++i) LQGK_UNROLL64 for (int m = 0; m < U; ++m) {
       double a = c(C::Ba + i * U + m);
-      LQGK_UNROLL for (int k = 0; k < Y; ++k) a += K[i * Y + k] * c(C::Dm + k * U + m);
+      LQGK_UNROLL64 for (int k = 0; k < Y; ++k) a += K[i * Y + k] * c(C::Dm + k * U + m);
       KD[i * U + m] = a;                                                     // Ba + K D
     }
-    LQGK_UNROLL for (int e = 0; e < Y * X; ++e) fad[e] = 0.0;
-    LQGK_UNROLL for (int e = 0; e < U * B; ++e) Lb[e] = 0.0;
-    LQGK_UNROLL for (int m = 0; m < N; ++m) {
+    LQGK_UNROLL64 for (int e = 0; e < Y * X; ++e) fad[e] = 0.0;
+    LQGK_UNROLL64 for (int e = 0; e < U * B; ++e) Lb[e] = 0.0;
+    LQGK_UNROLL64 for (int m = 0; m < N; ++m) {
       double fb[N];
       fb_row(m, sf, get, Cm, true, fb);
       if (m < X) {
-        LQGK_UNROLL for (int j = 0; j < X; ++j) out(C::Ad + m * X + j, fb[j]);
-        LQGK_UNROLL for (int k = 0; k < U; ++k) {
+        LQGK_UNROLL64 for (int j = 0; j < X; ++j) out(C::Ad + m * X + j, fb[j]);
+        LQGK_UNROLL64 for (int k = 0; k < U; ++k) {
           double a = 0.0;
-          LQGK_UNROLL for (int j = 0; j < B; ++j) a += fb[X + j] * L[k * B + j];
+          LQGK_UNROLL64 for (int j = 0; j < B; ++j) a += fb[X + j] * L[k * B + j];
           out(C::Bd + m * U + k, a);
           double bd = c(C::Bd + m * U + k);
-          LQGK_UNROLL for (int j = 0; j < B; ++j) Lb[k * B + j] += bd * fb[X + j];
+          LQGK_UNROLL64 for (int j = 0; j < B; ++j) Lb[k * B + j] += bd * fb[X + j];
         }
       } else {
         const int i = m - X;
-        LQGK_UNROLL for (int k = 0; k < Y; ++k) LQGK_UNROLL for (int j = 0; j < X; ++j) fad[k * X + j] += K[i * Y + k] * fb[j];
-        LQGK_UNROLL for (int j = 0; j < B; ++j) out(C::Aa + i * B + j, fb[X + j]);
-        LQGK_UNROLL for (int k = 0; k < U; ++k) {
+        LQGK_UNROLL64 for (int k = 0; k < Y; ++k) LQGK_UNROLL64 for (int j = 0; j < X; ++j) fad[k * X + j] += K[i * Y + k] * fb[j];
+        LQGK_UNROLL64 for (int j = 0; j < B; ++j) out(C::Aa + i * B + j, fb[X + j]);
+        LQGK_UNROLL64 for (int k = 0; k < U; ++k) {
           double a = 0.0;
-          LQGK_UNROLL for (int j = 0; j < B; ++j) a += fb[X + j] * L[k * B + j];
+          LQGK_UNROLL64 for (int j = 0; j < B; ++j) a += fb[X + j] * L[k * B + j];
           out(C::Ba + i * U + k, a);
-          LQGK_UNROLL for (int j = 0; j < B; ++j) Lb[k * B + j] += KD[i * U + k] * fb[X + j];
+          LQGK_UNROLL64 for (int j = 0; j < B; ++j) Lb[k * B + j] += KD[i * U + k] * fb[X + j];
         }
       }
     }
-    LQGK_UNROLL for (int e = 0; e < Y * X; ++e) out(C::FAd + e, fad[e]);
+    LQGK_UNROLL64 for (int e = 0; e < Y * X; ++e) out(C::FAd + e, fad[e]);
   }
   // PASS 1.  Kb: in = what PASS 0 stored (noise part), out = total.
   template <class V, class SFr, class Get, class Out>
   LQGK_HD static void pass1(const V& c, SFr&& sf, Get&& get, const double* Cm, const double* L, const double* K, Out&& out,
                             double* Kb) {
     double faa[Y * B], dm[Y * U];
-    LQGK_UNROLL for (int e = 0; e < Y * B; ++e) faa[e] = 0.0;
-    LQGK_UNROLL for (int e = 0; e < Y * U; ++e) dm[e] = 0.0;
-    LQGK_UNROLL for (int i = 0; i < B; ++i) {
+    LQGK_UNROLL64 for (int e = 0; e < Y * B; ++e) faa[e] = 0.0;
+    LQGK_UNROLL64 for (int e = 0; e < Y * U; ++e) dm[e] = 0.0;
+    LQGK_UNROLL64 for (int i = 0; i < B; ++i) {
       double fb[N], t2[U];
       fb_row(X + i, sf, get, Cm, true, fb);
-      LQGK_UNROLL for (int k = 0; k < U; ++k) {
+      LQGK_UNROLL64 for (int k = 0; k < U; ++k) {
         double a = 0.0;
-        LQGK_UNROLL for (int j = 0; j < B; ++j) a += fb[X + j] * L[k * B + j];
+        LQGK_UNROLL64 for (int j = 0; j < B; ++j) a += fb[X + j] * L[k * B + j];
         t2[k] = a;                                                           // (F22 L^T)[i, k]
       }
-      LQGK_UNROLL for (int k = 0; k < Y; ++k) {
-        LQGK_UNROLL for (int j = 0; j < B; ++j) faa[k * B + j] -= K[i * Y + k] * fb[X + j];
-        LQGK_UNROLL for (int m = 0; m < U; ++m) dm[k * U + m] += K[i * Y + k] * t2[m];
+      LQGK_UNROLL64 for (int k = 0; k < Y; ++k) {
+        LQGK_UNROLL64 for (int j = 0; j < B; ++j) faa[k * B + j] -= K[i * Y + k] * fb[X + j];
+        LQGK_UNROLL64 for (int m = 0; m < U; ++m) dm[k * U + m] += K[i * Y + k] * t2[m];
         double a = 0.0;
-        LQGK_UNROLL for (int j = 0; j < X; ++j) a += fb[j] * c(C::FAd + k * X + j);
-        LQGK_UNROLL for (int j = 0; j < B; ++j) a -= fb[X + j] * c(C::FAa + k * B + j);
-        LQGK_UNROLL for (int m = 0; m < U; ++m) a += t2[m] * c(C::Dm + k * U + m);
+        LQGK_UNROLL64 for (int j = 0; j < X; ++j) a += fb[j] * c(C::FAd + k * X + j);
+        LQGK_UNROLL64 for (int j = 0; j < B; ++j) a -= fb[X + j] * c(C::FAa + k * B + j);
+        LQGK_UNROLL64 for (int m = 0; m < U; ++m) a += t2[m] * c(C::Dm + k * U + m);
         Kb[i * Y + k] += a;
       }
     }
-    LQGK_UNROLL for (int e = 0; e < Y * B; ++e) out(C::FAa + e, faa[e]);
-    LQGK_UNROLL for (int e = 0; e < Y * U; ++e) out(C::Dm + e, dm[e]);
+    LQGK_UNROLL64 for (int e = 0; e < Y * B; ++e) out(C::FAa + e, faa[e]);
+    LQGK_UNROLL64 for (int e = 0; e < Y * U; ++e) out(C::Dm + e, dm[e]);
   }
 };
 
@@ -923,41 +938,41 @@ struct KfRev {
     load_mat<Y, B>(c, C::Fa, F);
     // Ktot = Kb - Pnb M^T ; Y = Ktot Gi
     double Ktot[B * Y], Yv[B * Y];
-    LQGK_UNROLL for (int i = 0; i < B; ++i) LQGK_UNROLL for (int k = 0; k < Y; ++k) {
+    LQGK_UNROLL64 for (int i = 0; i < B; ++i) LQGK_UNROLL64 for (int k = 0; k < Y; ++k) {
       double a = Kb[i * Y + k];
-      LQGK_UNROLL for (int j = 0; j < B; ++j) a -= Pnb[i * B + j] * M[k * B + j];
+      LQGK_UNROLL64 for (int j = 0; j < B; ++j) a -= Pnb[i * B + j] * M[k * B + j];
       Ktot[i * Y + k] = a;
     }
     mm<B, Y, Y>(Ktot, Gi, Yv);
     // Mb = -K^T Pnb + Y^T  (Y x B)
     double Mb[Y * B];
-    LQGK_UNROLL for (int k = 0; k < Y; ++k) LQGK_UNROLL for (int j = 0; j < B; ++j) {
+    LQGK_UNROLL64 for (int k = 0; k < Y; ++k) LQGK_UNROLL64 for (int j = 0; j < B; ++j) {
       double a = Yv[j * Y + k];
-      LQGK_UNROLL for (int i = 0; i < B; ++i) a -= K[i * Y + k] * Pnb[i * B + j];
+      LQGK_UNROLL64 for (int i = 0; i < B; ++i) a -= K[i * Y + k] * Pnb[i * B + j];
       Mb[k * B + j] = a;
     }
     // Gmb = -sym(K^T Y)  (Y x Y)
     double Gmb[Y * Y];
-    LQGK_UNROLL for (int k = 0; k < Y; ++k) LQGK_UNROLL for (int m = 0; m <= k; ++m) {
+    LQGK_UNROLL64 for (int k = 0; k < Y; ++k) LQGK_UNROLL64 for (int m = 0; m <= k; ++m) {
       double a = 0.0;
-      LQGK_UNROLL for (int i = 0; i < B; ++i) a += K[i * Y + k] * Yv[i * Y + m] + K[i * Y + m] * Yv[i * Y + k];
+      LQGK_UNROLL64 for (int i = 0; i < B; ++i) a += K[i * Y + k] * Yv[i * Y + m] + K[i * Y + m] * Yv[i * Y + k];
       Gmb[k * Y + m] = -0.5 * a;
       Gmb[m * Y + k] = -0.5 * a;
       acc(C::WWa + k * (k + 1) / 2 + m) += -0.5 * a;
     }
     // Fa += Mb Pp + 2 Gmb M
-    LQGK_UNROLL for (int k = 0; k < Y; ++k) LQGK_UNROLL for (int j = 0; j < B; ++j) {
+    LQGK_UNROLL64 for (int k = 0; k < Y; ++k) LQGK_UNROLL64 for (int j = 0; j < B; ++j) {
       double a = 0.0;
-      LQGK_UNROLL for (int i = 0; i < B; ++i) a += Mb[k * B + i] * Pp[i * B + j];
-      LQGK_UNROLL for (int m = 0; m < Y; ++m) a += 2.0 * Gmb[k * Y + m] * M[m * B + j];
+      LQGK_UNROLL64 for (int i = 0; i < B; ++i) a += Mb[k * B + i] * Pp[i * B + j];
+      LQGK_UNROLL64 for (int m = 0; m < Y; ++m) a += 2.0 * Gmb[k * Y + m] * M[m * B + j];
       acc(C::Fa + k * B + j) += a;
     }
     // Ppb = Pnb + sym(F^T Mb) + F^T Gmb F
     double GF[Y * B], Ppb[B * B];
     mm<Y, Y, B>(Gmb, F, GF);
-    LQGK_UNROLL for (int i = 0; i < B; ++i) LQGK_UNROLL for (int j = 0; j <= i; ++j) {
+    LQGK_UNROLL64 for (int i = 0; i < B; ++i) LQGK_UNROLL64 for (int j = 0; j <= i; ++j) {
       double a = Pnb[i * B + j];
-      LQGK_UNROLL for (int k = 0; k < Y; ++k)
+      LQGK_UNROLL64 for (int k = 0; k < Y; ++k)
         a += 0.5 * (F[k * B + i] * Mb[k * B + j] + F[k * B + j] * Mb[k * B + i]) + F[k * B + i] * GF[k * B + j];
       Ppb[i * B + j] = a;
       Ppb[j * B + i] = a;
@@ -967,9 +982,9 @@ struct KfRev {
     double PA[B * B], AP[B * B];
     mm<B, B, B>(Ppb, Am, PA);                       // Ppb A
     mm<B, B, B>(Am, P, AP);                         // A P
-    LQGK_UNROLL for (int i = 0; i < B; ++i) LQGK_UNROLL for (int j = 0; j < B; ++j) {
+    LQGK_UNROLL64 for (int i = 0; i < B; ++i) LQGK_UNROLL64 for (int j = 0; j < B; ++j) {
       double a = 0.0;
-      LQGK_UNROLL for (int k = 0; k < B; ++k) a += Ppb[i * B + k] * AP[k * B + j];
+      LQGK_UNROLL64 for (int k = 0; k < B; ++k) a += Ppb[i * B + k] * AP[k * B + j];
       acc(C::Aa + i * B + j) += 2.0 * a;
     }
     mm_tn_sym<B, B>(Am, PA, Pnb);
@@ -977,7 +992,7 @@ struct KfRev {
   // After t = 0: P_0 = Sig0
   template <class A>
   LQGK_HD static void finish(A&& acc, const double* Pnb) {
-    LQGK_UNROLL for (int i = 0; i < B; ++i) LQGK_UNROLL for (int j = 0; j <= i; ++j) acc(C::Sig0 + i * (i + 1) / 2 + j) += Pnb[i * B + j];
+    LQGK_UNROLL64 for (int i = 0; i < B; ++i) LQGK_UNROLL64 for (int j = 0; j <= i; ++j) acc(C::Sig0 + i * (i + 1) / 2 + j) += Pnb[i * B + j];
   }
 };
 
@@ -1003,48 +1018,48 @@ struct LqrRev {
     double Hi[U * U];
     {
       double Lc[U * U], Li[U * U];
-      LQGK_UNROLL for (int i = 0; i < U * U; ++i) Lc[i] = H[i];
-      LQGK_UNROLL for (int i = 0; i < U; ++i) Lc[i * U + i] += shift;
+      LQGK_UNROLL64 for (int i = 0; i < U * U; ++i) Lc[i] = H[i];
+      LQGK_UNROLL64 for (int i = 0; i < U; ++i) Lc[i * U + i] += shift;
       chol<U>(Lc);
       tri_inv<U>(Lc, Li);
       mm_tn_sym<U, U>(Li, Li, Hi);
     }
     // Q += Sn ; Aa += 2 SA Sn
-    LQGK_UNROLL for (int i = 0; i < B; ++i) LQGK_UNROLL for (int j = 0; j <= i; ++j) acc(C::Q + i * (i + 1) / 2 + j) += Sn[i * B + j];
-    LQGK_UNROLL for (int i = 0; i < B; ++i) LQGK_UNROLL for (int j = 0; j < B; ++j) {
+    LQGK_UNROLL64 for (int i = 0; i < B; ++i) LQGK_UNROLL64 for (int j = 0; j <= i; ++j) acc(C::Q + i * (i + 1) / 2 + j) += Sn[i * B + j];
+    LQGK_UNROLL64 for (int i = 0; i < B; ++i) LQGK_UNROLL64 for (int j = 0; j < B; ++j) {
       double a = 0.0;
-      LQGK_UNROLL for (int k = 0; k < B; ++k) a += SA[i * B + k] * Sn[k * B + j];
+      LQGK_UNROLL64 for (int k = 0; k < B; ++k) a += SA[i * B + k] * Sn[k * B + j];
       acc(C::Aa + i * B + j) += 2.0 * a;
     }
     // LS = L Sn (U x B) ; Lb = Lbar + 2 (H L + G) Sn ; Hb = LS L^T ; Gb = 2 LS
     double LS[U * B], HLG[U * B], Lb[U * B], Hb[U * U], Gb[U * B];
     mm<U, B, B>(L, Sn, LS);
     mm<U, U, B>(H, L, HLG);
-    LQGK_UNROLL for (int i = 0; i < U * B; ++i) HLG[i] += G[i];
+    LQGK_UNROLL64 for (int i = 0; i < U * B; ++i) HLG[i] += G[i];
     mm<U, B, B>(HLG, Sn, Lb);
-    LQGK_UNROLL for (int i = 0; i < U * B; ++i) Lb[i] = Lbar[i] + 2.0 * Lb[i];
+    LQGK_UNROLL64 for (int i = 0; i < U * B; ++i) Lb[i] = Lbar[i] + 2.0 * Lb[i];
     mm_nt<U, B, U>(LS, L, Hb);
     // HiLb = Ht^-1 Lb ; Gb = 2 LS - HiLb ; Hb -= HiLb L^T ; Hb <- sym
     double HiLb[U * B];
     mm<U, U, B>(Hi, Lb, HiLb);
-    LQGK_UNROLL for (int i = 0; i < U * B; ++i) Gb[i] = 2.0 * LS[i] - HiLb[i];
-    LQGK_UNROLL for (int i = 0; i < U; ++i) LQGK_UNROLL for (int j = 0; j < U; ++j) {
+    LQGK_UNROLL64 for (int i = 0; i < U * B; ++i) Gb[i] = 2.0 * LS[i] - HiLb[i];
+    LQGK_UNROLL64 for (int i = 0; i < U; ++i) LQGK_UNROLL64 for (int j = 0; j < U; ++j) {
       double a = Hb[i * U + j];
-      LQGK_UNROLL for (int k = 0; k < B; ++k) a -= HiLb[i * B + k] * L[j * B + k];
+      LQGK_UNROLL64 for (int k = 0; k < B; ++k) a -= HiLb[i * B + k] * L[j * B + k];
       Hb[i * U + j] = a;
     }
     symmetrize<U>(Hb);
-    LQGK_UNROLL for (int i = 0; i < U; ++i) LQGK_UNROLL for (int j = 0; j <= i; ++j) acc(C::R + i * (i + 1) / 2 + j) += Hb[i * U + j];
+    LQGK_UNROLL64 for (int i = 0; i < U; ++i) LQGK_UNROLL64 for (int j = 0; j <= i; ++j) acc(C::R + i * (i + 1) / 2 + j) += Hb[i * U + j];
     // Ba += 2 SB Hb + SA Gb^T ; Aa += SB Gb
-    LQGK_UNROLL for (int i = 0; i < B; ++i) LQGK_UNROLL for (int m = 0; m < U; ++m) {
+    LQGK_UNROLL64 for (int i = 0; i < B; ++i) LQGK_UNROLL64 for (int m = 0; m < U; ++m) {
       double a = 0.0;
-      LQGK_UNROLL for (int k = 0; k < U; ++k) a += 2.0 * SB[i * U + k] * Hb[k * U + m];
-      LQGK_UNROLL for (int k = 0; k < B; ++k) a += SA[i * B + k] * Gb[m * B + k];
+      LQGK_UNROLL64 for (int k = 0; k < U; ++k) a += 2.0 * SB[i * U + k] * Hb[k * U + m];
+      LQGK_UNROLL64 for (int k = 0; k < B; ++k) a += SA[i * B + k] * Gb[m * B + k];
       acc(C::Ba + i * U + m) += a;
     }
-    LQGK_UNROLL for (int i = 0; i < B; ++i) LQGK_UNROLL for (int j = 0; j < B; ++j) {
+    LQGK_UNROLL64 for (int i = 0; i < B; ++i) LQGK_UNROLL64 for (int j = 0; j < B; ++j) {
       double a = 0.0;
-      LQGK_UNROLL for (int k = 0; k < U; ++k) a += SB[i * U + k] * Gb[k * B + j];
+      LQGK_UNROLL64 for (int k = 0; k < U; ++k) a += SB[i * U + k] * Gb[k * B + j];
       acc(C::Aa + i * B + j) += a;
     }
     // Sn <- A Sn A^T + B Hb B^T + sym(B Gb A^T)
@@ -1054,17 +1069,17 @@ struct LqrRev {
     mm<B, U, U>(Bm, Hb, BH);
     mm_nt_sym<B, U, true>(BH, Bm, Sb);
     mm<B, U, B>(Bm, Gb, BG);                                       // B Gb (B x B), then (B Gb) A^T
-    LQGK_UNROLL for (int i = 0; i < B; ++i) LQGK_UNROLL for (int j = 0; j <= i; ++j) {
+    LQGK_UNROLL64 for (int i = 0; i < B; ++i) LQGK_UNROLL64 for (int j = 0; j <= i; ++j) {
       double a = 0.0;
-      LQGK_UNROLL for (int k = 0; k < B; ++k) a += BG[i * B + k] * Am[j * B + k] + BG[j * B + k] * Am[i * B + k];
+      LQGK_UNROLL64 for (int k = 0; k < B; ++k) a += BG[i * B + k] * Am[j * B + k] + BG[j * B + k] * Am[i * B + k];
       Sb[i * B + j] += 0.5 * a;
       if (i != j) Sb[j * B + i] += 0.5 * a;
     }
-    LQGK_UNROLL for (int i = 0; i < B * B; ++i) Sn[i] = Sb[i];
+    LQGK_UNROLL64 for (int i = 0; i < B * B; ++i) Sn[i] = Sb[i];
   }
   template <class A>
   LQGK_HD static void finish(A&& acc, const double* Sn) {   // S_T = Qf
-    LQGK_UNROLL for (int i = 0; i < B; ++i) LQGK_UNROLL for (int j = 0; j <= i; ++j) acc(C::Qf + i * (i + 1) / 2 + j) += Sn[i * B + j];
+    LQGK_UNROLL64 for (int i = 0; i < B; ++i) LQGK_UNROLL64 for (int j = 0; j <= i; ++j) acc(C::Qf + i * (i + 1) / 2 + j) += Sn[i * B + j];
   }
 };
 

@@ -11,5 +11,6 @@
   M(4, 6, 2, 4, 4)   /* SubjectiveActor dim=2                               [configs c2, c3, c5] */ \
   M(4, 4, 1, 3, 2)   /* PointMassBoundedActor, observed target+cursor (point_mass.py, main.py:51) */ \
   M(5, 5, 1, 2, 2)   /* HandMotionModelTrackingTask (notebooks/HandModel.ipynb): target + pos/vel/force/act. */ \
-  M(6, 6, 1, 2, 2)   /* TemporalDelayModel(BoundedActor dim=1, delay=2) (delay.py:9-41): motor-delay family */
+  M(6, 6, 1, 2, 2)   /* TemporalDelayModel(BoundedActor dim=1, delay=2) (delay.py:9-41): motor-delay family */ \
+  M(12, 12, 1, 3, 2) /* TemporalDelayModel(PointMassBoundedActor, delay=2): 12-dim state, joint dim 24 [config c4]; large-system path (lqgk_big.cuh) */
 // clang-format on

@@ -553,14 +553,16 @@ __device__ __forceinline__ void load_obs(const float* __restrict__ p, float* out
 }
 
 constexpr int TRIAL_WARPS = 4;   // warps (= samples) per CTA
-constexpr int TRIAL_TB = 8;      // time steps per ring stage
+// time steps per ring stage: 8 for the small records, fewer when one record is KBs (large systems)
+template <class DM>
+__host__ __device__ constexpr int trial_tb() { return DM::REC <= 128 ? 8 : (DM::REC <= 256 ? 4 : 2); }
 constexpr int TRIAL_NST = 3;     // ring stages
 
 constexpr int TRIAL_PF = 4;      // observation / state prefetch distance in time steps (cp.async groups in flight)
 // Per-lane prefetch slots: [TRIAL_PF + 1][RT][W floats][32 lanes] per warp.
 template <class DM, int RT, bool REV>
 constexpr size_t trial_smem_bytes() {
-  size_t ring = (size_t)TRIAL_WARPS * TRIAL_NST * TRIAL_TB * DM::REC * sizeof(float) + TRIAL_WARPS * TRIAL_NST * sizeof(uint64_t);
+  size_t ring = (size_t)TRIAL_WARPS * TRIAL_NST * trial_tb<DM>() * DM::REC * sizeof(float) + TRIAL_WARPS * TRIAL_NST * sizeof(uint64_t);
   size_t pf = REV ? 0 : (size_t)TRIAL_WARPS * (TRIAL_PF + 1) * RT * 32 * DM::D * sizeof(float);   // forward only
   return ring + pf;
 }
@@ -596,18 +598,18 @@ struct RecRing {
   // issue the copy of chunk `k` into stage `st` (lane 0 only; caller guarantees the stage is no longer read)
   __device__ __forceinline__ void issue(int k, int st) {
     if (lane == 0) {
-      int t0 = k * TRIAL_TB;
-      int nst = min(TRIAL_TB, Tn - t0);
+      int t0 = k * trial_tb<DM>();
+      int nst = min(trial_tb<DM>(), Tn - t0);
       uint32_t bytes = (uint32_t)nst * DM::REC * sizeof(float);
       fence_proxy_async();
       mbar_expect_tx(&bars[st], bytes);
-      bulk_g2s(buf + (size_t)st * TRIAL_TB * DM::REC, src + (size_t)t0 * DM::REC, bytes, &bars[st]);
+      bulk_g2s(buf + (size_t)st * trial_tb<DM>() * DM::REC, src + (size_t)t0 * DM::REC, bytes, &bars[st]);
     }
   }
   __device__ __forceinline__ const float* wait(int st) {
     mbar_wait(&bars[st], (phase_bits >> st) & 1u);
     phase_bits ^= (1u << st);
-    return buf + (size_t)st * TRIAL_TB * DM::REC;
+    return buf + (size_t)st * trial_tb<DM>() * DM::REC;
   }
 };
 
@@ -646,12 +648,12 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_fwd(const float* __r
   const int s = blockIdx.x * TRIAL_WARPS + warp;
   if (s >= n_samples) return;
   const float* __restrict__ x_tm = x_all + (size_t)(s_first + s) * x_sample_stride;   // this sample's observations
-  constexpr size_t RING_BYTES = (size_t)TRIAL_WARPS * TRIAL_NST * TRIAL_TB * DM::REC * sizeof(float);
+  constexpr size_t RING_BYTES = (size_t)TRIAL_WARPS * TRIAL_NST * trial_tb<DM>() * DM::REC * sizeof(float);
   float* ring_base = reinterpret_cast<float*>(smraw);
   uint64_t* bar_base = reinterpret_cast<uint64_t*>(smraw + RING_BYTES);
   float* pf = reinterpret_cast<float*>(smraw + RING_BYTES + TRIAL_WARPS * TRIAL_NST * sizeof(uint64_t)) + (size_t)warp * NSLOT * RT * 32 * D;
-  RecRing<DM> ring{ring_base + (size_t)warp * TRIAL_NST * TRIAL_TB * DM::REC, bar_base + warp * TRIAL_NST,
-                   rec + (size_t)s * Tn * DM::REC, Tn, (Tn + TRIAL_TB - 1) / TRIAL_TB, lane, 0};
+  RecRing<DM> ring{ring_base + (size_t)warp * TRIAL_NST * trial_tb<DM>() * DM::REC, bar_base + warp * TRIAL_NST,
+                   rec + (size_t)s * Tn * DM::REC, Tn, (Tn + trial_tb<DM>() - 1) / trial_tb<DM>(), lane, 0};
   ring.init();
   const int nchunk = ring.nchunk;
   for (int base = 0; base < N; base += 32 * RT) {
@@ -691,7 +693,7 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_fwd(const float* __r
     for (int k = 0; k < nchunk; ++k) {
       const int st = k % TRIAL_NST;
       const float* chunk = ring.wait(st);
-      const int t0 = k * TRIAL_TB, nst = min(TRIAL_TB, Tn - t0);
+      const int t0 = k * trial_tb<DM>(), nst = min(trial_tb<DM>(), Tn - t0);
       f32x2 partP[NP > 0 ? NP : 1];
       float partS = 0.f;
       LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) partP[p2] = f32x2{0.f, 0.f};
@@ -741,7 +743,7 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_fwd(const float* __r
         LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) LQGK_UNROLL for (int m = 0; m < D; ++m) x0P[p2][m] = x1P[p2][m];
         if constexpr (NS) { LQGK_UNROLL for (int m = 0; m < D; ++m) x0S[m] = x1S[m]; }
       }
-      // FP32 partial sum over <= TRIAL_TB steps, FP64 across chunks (log-likelihood error ~1e-7 relative)
+      // FP32 partial sum over <= trial_tb<DM>() steps, FP64 across chunks (log-likelihood error ~1e-7 relative)
       LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) {
         ll[2 * p2] += (double)partP[p2].x;
         ll[2 * p2 + 1] += (double)partP[p2].y;
@@ -791,9 +793,9 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __r
   if (s >= n_samples) return;
   const float* __restrict__ x_tm = x_all + (size_t)(s_first + s) * x_sample_stride;   // this sample's observations
   float* ring_base = reinterpret_cast<float*>(smraw);
-  uint64_t* bar_base = reinterpret_cast<uint64_t*>(smraw + (size_t)TRIAL_WARPS * TRIAL_NST * TRIAL_TB * DM::REC * sizeof(float));
-  RecRing<DM> ring{ring_base + (size_t)warp * TRIAL_NST * TRIAL_TB * DM::REC, bar_base + warp * TRIAL_NST,
-                   rec + (size_t)s * Tn * DM::REC, Tn, (Tn + TRIAL_TB - 1) / TRIAL_TB, lane, 0};
+  uint64_t* bar_base = reinterpret_cast<uint64_t*>(smraw + (size_t)TRIAL_WARPS * TRIAL_NST * trial_tb<DM>() * DM::REC * sizeof(float));
+  RecRing<DM> ring{ring_base + (size_t)warp * TRIAL_NST * trial_tb<DM>() * DM::REC, bar_base + warp * TRIAL_NST,
+                   rec + (size_t)s * Tn * DM::REC, Tn, (Tn + trial_tb<DM>() - 1) / trial_tb<DM>(), lane, 0};
   ring.init();
   const int nchunk = ring.nchunk;
   for (int base = 0; base < N; base += 32 * RT) {
@@ -831,7 +833,7 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __r
       const int k = nchunk - 1 - kk;
       const int st = kk % TRIAL_NST;
       const float* chunk = ring.wait(st);
-      const int t0 = k * TRIAL_TB, nst = min(TRIAL_TB, Tn - t0);
+      const int t0 = k * trial_tb<DM>(), nst = min(trial_tb<DM>(), Tn - t0);
 #pragma unroll 1
       for (int q = nst - 1; q >= 0; --q) {
         const int t = t0 + q;

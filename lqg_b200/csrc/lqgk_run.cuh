@@ -109,11 +109,17 @@ inline bool spec_time_varying(const LqgkSpec& s, bool actor) {
   return false;
 }
 
+// Large systems (joint dim > 12) take the local-memory path of lqgk_big.cuh (compiled with -DLQGK_BIG).
+template <class DM>
+constexpr bool is_big() { return DM::N > 12; }
+template <class DM>
+constexpr int big_scratch_rows();
+
 // Workspace plan for one chunk of Sc (multiple of 32) samples.
 struct Plan {
   size_t Sc = 0, bytes = 0;
   size_t cst = 0, acc = 0, L = 0, K = 0, l = 0, H = 0, Sric = 0, Pkf = 0, Cs = 0, Lbar = 0, Kbar = 0, rec = 0, ll = 0,
-         sums = 0, hist = 0, w = 0, FU = 0, JS = 0, J0 = 0, SGB = 0, SGBI = 0, SFW = 0, KbarF = 0;
+         sums = 0, hist = 0, w = 0, FU = 0, JS = 0, J0 = 0, SGB = 0, SGBI = 0, SFW = 0, KbarF = 0, scr = 0;
 };
 
 template <class DM>
@@ -153,6 +159,7 @@ Plan make_plan(const LqgkDims& d, int mode, bool tv, size_t Sc) {
     p.SGBI = take(sizeof(double) * SR::NSGB * Sc);
     p.SFW = take(sizeof(double) * T * SR::NSF * Sc);
   }
+  if constexpr (is_big<DM>()) p.scr = take(sizeof(double) * 2 * big_scratch_rows<DM>() * Sc);
   p.bytes = off;
   return p;
 }

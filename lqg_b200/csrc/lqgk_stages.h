@@ -27,11 +27,11 @@ LQGK_HD void flush_acc(G&& g, const La& l, int nseg) {
 }
 template <int M, class W>
 LQGK_HD void store_sym(W&& w, size_t off, const double* C) {
-  LQGK_UNROLL for (int i = 0; i < M; ++i) LQGK_UNROLL for (int j = 0; j <= i; ++j) w(off + i * (i + 1) / 2 + j) = C[i * M + j];
+  LQGK_UNROLL64 for (int i = 0; i < M; ++i) LQGK_UNROLL64 for (int j = 0; j <= i; ++j) w(off + i * (i + 1) / 2 + j) = C[i * M + j];
 }
 template <int M, class W>
 LQGK_HD void load_sym_ws(const W& w, size_t off, double* C) {
-  LQGK_UNROLL for (int i = 0; i < M; ++i) LQGK_UNROLL for (int j = 0; j <= i; ++j) {
+  LQGK_UNROLL64 for (int i = 0; i < M; ++i) LQGK_UNROLL64 for (int j = 0; j <= i; ++j) {
     double a = w(off + i * (i + 1) / 2 + j);
     C[i * M + j] = a;
     C[j * M + i] = a;
@@ -56,16 +56,16 @@ LQGK_HD void lqr_fwd_body(const GCst& g, WView lc, int T, double eps, WView Lw, 
   load_consts<C>(g.at(g.tstride ? T - 1 : 0), lc, nseg);
   double S[B * B], s[B];
   load_sym<B>(lc, C::Qf, S);
-  if (AFFINE) { LQGK_UNROLL for (int i = 0; i < B; ++i) s[i] = lc(C::qf + i); }
+  if (AFFINE) { LQGK_UNROLL64 for (int i = 0; i < B; ++i) s[i] = lc(C::qf + i); }
   for (int t = T - 1; t >= 0; --t) {
     if (g.tstride && t != T - 1) load_consts<C>(g.at(t), lc, nseg);
     if (save_S) store_sym<B>(Sw, (size_t)t * DM::ES, S);
     double L[U * B], l[U], Ht[U * U], shift;
     LqrFwd<DM, AFFINE>::step(lc, eps, S, s, L, l, Ht, shift);
-    LQGK_UNROLL for (int i = 0; i < U * B; ++i) Lw((size_t)t * DM::EL + i) = L[i];
+    LQGK_UNROLL64 for (int i = 0; i < U * B; ++i) Lw((size_t)t * DM::EL + i) = L[i];
     if (AFFINE) {
-      LQGK_UNROLL for (int i = 0; i < U; ++i) lw((size_t)t * U + i) = l[i];
-      LQGK_UNROLL for (int i = 0; i < U * U; ++i) Hw((size_t)t * U * U + i) = Ht[i];
+      LQGK_UNROLL64 for (int i = 0; i < U; ++i) lw((size_t)t * U + i) = l[i];
+      LQGK_UNROLL64 for (int i = 0; i < U * U; ++i) Hw((size_t)t * U * U + i) = Ht[i];
     }
   }
 }
@@ -83,7 +83,7 @@ LQGK_HD void kf_fwd_body(const GCst& g, WView lc, int T, WView Kw, bool save_P, 
     if (save_P) store_sym<B>(Pw, (size_t)t * DM::EP, P);
     double K[B * Y];
     KfFwd<DM>::step(lc, P, K);
-    LQGK_UNROLL for (int i = 0; i < B * Y; ++i) Kw((size_t)t * DM::EK + i) = K[i];
+    LQGK_UNROLL64 for (int i = 0; i < B * Y; ++i) Kw((size_t)t * DM::EK + i) = K[i];
   }
 }
 
@@ -98,16 +98,16 @@ LQGK_HD void cov_fwd_body(const GCst& g, WView lc, int T, WView Lw, WView Kw, bo
   using SR = CovSeqRev<DM>;
   load_consts<C>(g.at(0), lc, C::NSEG);
   double Cm[R * R], L[U * B], K[B * Y];
-  LQGK_UNROLL for (int i = 0; i < B * Y; ++i) K[i] = Kw(i);
+  LQGK_UNROLL64 for (int i = 0; i < B * Y; ++i) K[i] = Kw(i);
   {
     double J0[R * D];
     CovFwd<DM>::init(lc, K, Cm, J0);
-    if (save_adj) { LQGK_UNROLL for (int i = 0; i < R * D; ++i) J0w(i) = J0[i]; }
+    if (save_adj) { LQGK_UNROLL64 for (int i = 0; i < R * D; ++i) J0w(i) = J0[i]; }
   }
   for (int t = 0; t < T; ++t) {
     if (g.tstride && t != 0) load_consts<C>(g.at(t), lc, C::NSEG);
-    LQGK_UNROLL for (int i = 0; i < U * B; ++i) L[i] = Lw((size_t)t * DM::EL + i);
-    LQGK_UNROLL for (int i = 0; i < B * Y; ++i) K[i] = Kw((size_t)t * DM::EK + i);
+    LQGK_UNROLL64 for (int i = 0; i < U * B; ++i) L[i] = Lw((size_t)t * DM::EL + i);
+    LQGK_UNROLL64 for (int i = 0; i < B * Y; ++i) K[i] = Kw((size_t)t * DM::EK + i);
     if (save_adj) store_sym<R>(Cw, (size_t)t * DM::EC, Cm);
     CovFwd<DM>::step(lc, L, K, Cm, [&](int idx, float v) { sink.put(idx, v); },
                      [&](int which, int e, double v) {
@@ -128,7 +128,7 @@ LQGK_HD void cov_seq_rev_body(int T, double sw, WView FUw, WView JSw, WView J0w,
   constexpr int R = DM::R;
   using SR = CovSeqRev<DM>;
   double Cb[R * R];
-  LQGK_UNROLL for (int i = 0; i < R * R; ++i) Cb[i] = 0.0;
+  LQGK_UNROLL64 for (int i = 0; i < R * R; ++i) Cb[i] = 0.0;
   for (int t = T - 1; t >= 0; --t) {
     src.fetch(t);
     SR::step([&](int e) { return FUw((size_t)t * SR::NSF + e); }, [&](int e) { return JSw((size_t)t * SR::NJS + e); },
@@ -140,33 +140,33 @@ LQGK_HD void cov_seq_rev_body(int T, double sw, WView FUw, WView JSw, WView J0w,
 
 // ---------------------------------------------------------------------------------------------- COV rev (time-parallel)
 // lc: local copy of the CovC constants (already loaded).  Processes steps [t0, t1).
-template <class DM, int PASS, class Source>
+// ct(t, e, v): sink of contribution e (CovC layout) of step t.
+template <class DM, int PASS, class Source, class CT>
 LQGK_HD void cov_contrib_body(WView lc, int t0, int t1, WView Lw, WView Kw, WView Cw, WView SGBw, WView SGBIw, WView SFw,
-                              Source&& src, WView CTw, WView Lbw, WView Kbw) {
+                              Source&& src, CT&& ct, WView Lbw, WView Kbw) {
   constexpr int B = DM::B, U = DM::U, Y = DM::Y, R = DM::R;
   using SR = CovSeqRev<DM>;
   using CC = CovContrib<DM>;
-  constexpr int NC = CovC<DM>::n;
   for (int t = t0; t < t1; ++t) {
     double Cm[R * R], L[U * B], K[B * Y];
-    LQGK_UNROLL for (int i = 0; i < U * B; ++i) L[i] = Lw((size_t)t * DM::EL + i);
-    LQGK_UNROLL for (int i = 0; i < B * Y; ++i) K[i] = Kw((size_t)t * DM::EK + i);
+    LQGK_UNROLL64 for (int i = 0; i < U * B; ++i) L[i] = Lw((size_t)t * DM::EL + i);
+    LQGK_UNROLL64 for (int i = 0; i < B * Y; ++i) K[i] = Kw((size_t)t * DM::EK + i);
     load_sym_ws<R>(Cw, (size_t)t * DM::EC, Cm);
     src.fetch(t);
     auto sf = [&](int e) { return SFw((size_t)t * SR::NSF + e); };
     auto get = [&](int idx) { return src.get(idx); };
-    auto out = [&](int e, double v) { CTw((size_t)t * NC + e) = v; };
+    auto out = [&](int e, double v) { ct(t, e, v); };
     if (PASS == 0) {
       double Lb[U * B], Kb[B * Y];
       CC::pass0(lc, [&](int e) { return SGBw((size_t)t * SR::NSGB + e); }, t == 0, [&](int e) { return SGBIw(e); }, sf, get, Cm,
                 L, K, out, Lb, Kb);
-      LQGK_UNROLL for (int i = 0; i < U * B; ++i) Lbw((size_t)t * DM::EL + i) = Lb[i];
-      LQGK_UNROLL for (int i = 0; i < B * Y; ++i) Kbw((size_t)t * DM::EK + i) = Kb[i];
+      LQGK_UNROLL64 for (int i = 0; i < U * B; ++i) Lbw((size_t)t * DM::EL + i) = Lb[i];
+      LQGK_UNROLL64 for (int i = 0; i < B * Y; ++i) Kbw((size_t)t * DM::EK + i) = Kb[i];
     } else {
       double Kb[B * Y];
-      LQGK_UNROLL for (int i = 0; i < B * Y; ++i) Kb[i] = Kbw((size_t)t * DM::EK + i);
+      LQGK_UNROLL64 for (int i = 0; i < B * Y; ++i) Kb[i] = Kbw((size_t)t * DM::EK + i);
       CC::pass1(lc, sf, get, Cm, L, K, out, Kb);
-      LQGK_UNROLL for (int i = 0; i < B * Y; ++i) Kbw((size_t)t * DM::EK + i) = Kb[i];
+      LQGK_UNROLL64 for (int i = 0; i < B * Y; ++i) Kbw((size_t)t * DM::EK + i) = Kb[i];
     }
   }
 }
@@ -180,11 +180,11 @@ LQGK_HD void kf_rev_body(const GCst& g, WView lc, WView la, int T, WView Pw, WVi
   for (int e = 0; e < C::n; ++e) la(e) = 0.0;
   auto acc = [&](int e) -> double& { return la(e); };
   double Pnb[B * B];
-  LQGK_UNROLL for (int i = 0; i < B * B; ++i) Pnb[i] = 0.0;
+  LQGK_UNROLL64 for (int i = 0; i < B * B; ++i) Pnb[i] = 0.0;
   for (int t = T - 1; t >= 0; --t) {
     double P[B * B], Kb[B * Y];
     load_sym_ws<B>(Pw, (size_t)t * DM::EP, P);
-    LQGK_UNROLL for (int i = 0; i < B * Y; ++i) Kb[i] = Kbw((size_t)t * DM::EK + i);
+    LQGK_UNROLL64 for (int i = 0; i < B * Y; ++i) Kb[i] = Kbw((size_t)t * DM::EK + i);
     KfRev<DM>::step(lc, acc, P, Kb, Pnb);
   }
   KfRev<DM>::finish(acc, Pnb);
@@ -200,11 +200,11 @@ LQGK_HD void lqr_rev_body(const GCst& g, WView lc, WView la, int T, double eps, 
   for (int e = 0; e < C::n; ++e) la(e) = 0.0;
   auto acc = [&](int e) -> double& { return la(e); };
   double Sn[B * B];
-  LQGK_UNROLL for (int i = 0; i < B * B; ++i) Sn[i] = 0.0;
+  LQGK_UNROLL64 for (int i = 0; i < B * B; ++i) Sn[i] = 0.0;
   for (int t = 0; t < T; ++t) {
     double S[B * B], L[U * B], Lb[U * B];
     load_sym_ws<B>(Sw, (size_t)t * DM::ES, S);
-    LQGK_UNROLL for (int i = 0; i < U * B; ++i) { L[i] = Lw((size_t)t * DM::EL + i); Lb[i] = Lbw((size_t)t * DM::EL + i); }
+    LQGK_UNROLL64 for (int i = 0; i < U * B; ++i) { L[i] = Lw((size_t)t * DM::EL + i); Lb[i] = Lbw((size_t)t * DM::EL + i); }
     // eigen-shift recomputed from S_{t+1} (lqr.py:27-28); zero in every well-posed model
     double shift;
     {

@@ -142,10 +142,11 @@ int run(const LqgkDims& d, const LqgkSpec* act, const LqgkSpec* dyn, const LqgkM
       std::vector<double> sc(SR::SC_N + 8);
       cov_seq_rev_body<DM>(Tn, sw, V(FUw, s), V(JSw, s), V(J0w, s), src, WView{sc.data(), 1}, V(SGBw, s), V(SGBIw, s), V(SFw, s));
       load_consts<CovC<DM>>(g.at(0), WView{lc.data(), 1}, CovC<DM>::NSEG);
+      auto ct = [&](int t, int e, double v) { CTw[((size_t)t * NC + e) * Sc + s] = v; };
       cov_contrib_body<DM, 0>(WView{lc.data(), 1}, 0, Tn, V(Lw, s), V(Kw, s), V(Cw, s), V(SGBw, s), V(SGBIw, s), V(SFw, s), src,
-                              V(CTw, s), V(Lbw, s), V(Kbw, s));
+                              ct, V(Lbw, s), V(Kbw, s));
       cov_contrib_body<DM, 1>(WView{lc.data(), 1}, 0, Tn, V(Lw, s), V(Kw, s), V(Cw, s), V(SGBw, s), V(SGBIw, s), V(SFw, s), src,
-                              V(CTw, s), V(Lbw, s), V(Kbw, s));
+                              ct, V(Lbw, s), V(Kbw, s));
       for (int e = 0; e < NC; ++e) la[e] = 0.0;               // time reduction of the per-step contributions
       for (int t = 0; t < Tn; ++t)
         for (int e = 0; e < NC; ++e) la[e] += CTw[((size_t)t * NC + e) * Sc + s];

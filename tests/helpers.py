@@ -23,18 +23,21 @@ def model_mats(name, **kw):
             "relobs": O.relative_observation_mats, "relobs2": lambda **k: O.relative_observation_mats(dim=2, **k),
             "pointmass": O.point_mass_mats,
             "hand": lambda **k: O.hand_model_mats(position_noise=0.3, **k),
-            "delay2": lambda **k: tuple(O.delay_mats(m, 2) for m in O.bounded_actor_mats(**k))}[name](**kw)
+            "delay2": lambda **k: tuple(O.delay_mats(m, 2) for m in O.bounded_actor_mats(**k)),
+            # BASELINE config c4: TemporalDelayModel(PointMassBoundedActor, delay=2), 12-dim state (joint dim 24)
+            "pmdelay2": lambda **k: tuple(O.delay_mats(m, 2) for m in O.point_mass_mats(**k))}[name](**kw)
 
 
 MODEL_DIMS = {"bounded": (2, 2, 1, 2), "bounded2": (4, 4, 2, 4), "subjective": (2, 3, 1, 2), "subjective2": (4, 6, 2, 4),
-              "relobs": (2, 2, 1, 1), "relobs2": (4, 4, 2, 2), "pointmass": (4, 4, 1, 3), "hand": (5, 5, 1, 2), "delay2": (6, 6, 1, 2)}
+              "relobs": (2, 2, 1, 1), "relobs2": (4, 4, 2, 2), "pointmass": (4, 4, 1, 3), "hand": (5, 5, 1, 2), "delay2": (6, 6, 1, 2), "pmdelay2": (12, 12, 1, 3)}
 MODEL_PARAMS = {"bounded": ("action_variability", "sigma_target", "sigma_cursor", "action_cost"),
                 "subjective": ("action_variability", "sigma_target", "sigma_cursor", "action_cost", "subj_noise",
                                "subj_vel_noise"),
                 "relobs": ("action_variability", "sigma", "action_cost"),
                 "pointmass": ("action_variability", "sigma_target", "sigma_cursor", "action_cost"),
                 "hand": ("action_variability", "sigma_target", "sigma_cursor", "action_cost"),
-                "delay": ("action_variability", "sigma_target", "sigma_cursor", "action_cost")}
+                "delay": ("action_variability", "sigma_target", "sigma_cursor", "action_cost"),
+                "pmdelay": ("action_variability", "sigma_target", "sigma_cursor", "action_cost")}
 DEFAULTS = dict(action_variability=0.5, sigma_target=6.0, sigma_cursor=6.0, action_cost=1.0, subj_noise=1.0,
                 subj_vel_noise=0.5, sigma=6.0)
 
@@ -47,7 +50,7 @@ def jittered_params(name, S, seed, scale=0.25):
     for s in range(S):
         kw = {}
         for k in MODEL_PARAMS[base]:
-            v0 = DEFAULTS[k] if base != "pointmass" else dict(action_variability=1e-3, sigma_target=6.0,
+            v0 = DEFAULTS[k] if base not in ("pointmass", "pmdelay") else dict(action_variability=1e-3, sigma_target=6.0,
                                                               sigma_cursor=6.0, action_cost=0.01)[k]
             kw[k] = v0 * (1.0 if s == 0 else float(np.exp(scale * rng.standard_normal())))
         out.append(kw)
@@ -130,6 +133,36 @@ def check_vjp(lib, device, case: Case, dtype=torch.float32, max_chunk=0, ll_rtol
                 scale = np.abs(ref[s][k]).max()
                 assert err <= g_rtol * scale + floor, (who, k, s, err, scale)
                 worst = max(worst, err / (scale + floor))
+    return worst
+
+
+def check_param_vjp(lib, device, case: Case, dtype=torch.float32, ll_rtol=1e-4, g_rtol=1e-3):
+    """lqgk_loglik_vjp on `case`, compared with the oracle at the level BASELINE.json's tolerance is stated for: the
+    gradient w.r.t. the model PARAMETERS (base-matrix cotangents chained through the constructor's Jacobian, central
+    differences of the oracle's constructor).  Criterion per sample: |g - g_ref| <= g_rtol * |g_ref| + 1e-4 * max|g_ref|."""
+    dims = case.lqgk_dims()
+    act, dyn = case.tensors(device, dtype)
+    x_tm = lib.pack_obs(torch.tensor(case.X, device=device), stream=stream_of(device))
+    ws = workspace(lib, dims, abi.MODE_VJP, device)
+    ll, oa, od, _ = lib.loglik_vjp(dims, act, dyn, x_tm, ws=ws, stream=stream_of(device))
+    if device.type == "cuda":
+        torch.cuda.synchronize(device)
+    assert np.allclose(ll.double().cpu().numpy(), case.ll, rtol=ll_rtol)
+    names = MODEL_PARAMS[case.name.rstrip("2")]
+    worst = 0.0
+    for s in range(case.S):
+        kw = case.params[s]
+        g, g_ref = np.zeros(len(names)), np.zeros(len(names))
+        for i, k in enumerate(names):
+            h = 1e-6 * kw[k]
+            mp, mm = model_mats(case.name, **dict(kw, **{k: kw[k] + h})), model_mats(case.name, **dict(kw, **{k: kw[k] - h}))
+            for who, keys, out, ref in ((0, abi.ACTOR_KEYS, oa, case.ga), (1, abi.DYN_KEYS, od, case.gd)):
+                for kk in keys:
+                    J = (mp[who][kk] - mm[who][kk]) / (2 * h)
+                    g[i] += float((J * out[kk][s].double().cpu().numpy()).sum())
+                    g_ref[i] += float((J * ref[s][kk]).sum())
+        assert np.allclose(g, g_ref, rtol=g_rtol, atol=1e-4 * np.abs(g_ref).max()), (s, g, g_ref)
+        worst = max(worst, float(np.abs(g - g_ref).max() / np.abs(g_ref).max()))
     return worst
 
 

@@ -15,7 +15,7 @@ from tests import helpers as H
 def lib():
     src = os.path.join(H.ROOT, "tests", "emul", "lqgk_emul.cpp")
     if not os.path.exists(H.EMUL_PATH) or os.path.getmtime(H.EMUL_PATH) < os.path.getmtime(src):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", H.EMUL_PATH, src])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ftemplate-depth=2000", "-shared", "-fPIC", "-o", H.EMUL_PATH, src])
     return abi.Library(H.EMUL_PATH)
 
 
@@ -30,6 +30,20 @@ def test_step_functions_match_oracle(lib, name, d):
     H.check_fwd(lib, CPU, case, torch.float64)
     H.check_vjp(lib, CPU, case, torch.float64)
     H.check_vjp(lib, CPU, case, torch.float32)
+
+
+def test_large_system_c4(lib):
+    """BASELINE config c4 model: TemporalDelayModel(PointMassBoundedActor, delay=2), joint dim 24 (rolled-loop build on the GPU)."""
+    case = H.Case("pmdelay2", S=2, T=60, N=4, d=2, weights=True)
+    H.check_gains(lib, CPU, case, torch.float64, rtol=1e-9)
+    H.check_vjp(lib, CPU, case, torch.float64)
+    H.check_vjp(lib, CPU, case, torch.float32)
+
+
+def test_large_system_c4_full_horizon_parameter_gradients(lib):
+    """c4 horizon (T=600, 50 trials): parameter gradients of the FP32 per-trial arithmetic within rtol 1e-3."""
+    case = H.Case("pmdelay2", S=2, T=600, N=50, d=2)
+    assert H.check_param_vjp(lib, CPU, case, torch.float32) < 1e-3
 
 
 def test_long_horizon_gradient_tolerance(lib):

@@ -13,7 +13,7 @@ from lqg_b200 import abi, tracking
 from oracle import lqg_np as O
 from tests import helpers as H
 
-FIXTURES = sorted(glob.glob(os.path.join(H.ROOT, "tests", "golden", "*.npz")))
+FIXTURES = sorted(p for p in glob.glob(os.path.join(H.ROOT, "tests", "golden", "*.npz")) if not os.path.basename(p).startswith("ref_"))   # ref_*: tests/test_reference_golden.py
 CLS = {"bounded": tracking.BoundedActor, "subjective": tracking.SubjectiveActor}
 NPB = {"bounded": O.bounded_actor_mats, "subjective": O.subjective_actor_mats}
 GRAD_ATOL_FRAC = 1e-5     # absolute slack as a fraction of max |grad| (tiny components near an optimum)

@@ -41,6 +41,24 @@ def test_loglik_and_gradients_match_oracle(lib, dev, name, d, N):
     H.check_vjp(lib, dev, case, torch.float64)
 
 
+def test_large_system_c4(lib, dev):
+    """BASELINE config c4 model: TemporalDelayModel(PointMassBoundedActor, delay=2): x=b=12, joint dim 24 -- the
+    large-system path (lqgk_big.cuh), 50 trials as in the config."""
+    case = H.Case("pmdelay2", S=40, T=120, N=50, d=2, weights=True)
+    H.check_gains(lib, dev, case, torch.float64, rtol=1e-9)
+    H.check_fwd(lib, dev, case, torch.float32)
+    H.check_vjp(lib, dev, case, torch.float32)
+    H.check_vjp(lib, dev, case, torch.float64, max_chunk=32)      # two chunks
+
+
+def test_large_system_c4_full_horizon(lib, dev):
+    """c4 horizon T=600, 50 trials: log-likelihood rtol 1e-4 and PARAMETER gradients rtol 1e-3.  (With action_variability
+    1e-3 the innovation covariance is ~1e-6 and the FP32 per-trial arithmetic leaves 3e-3..6e-3 relative error in single
+    base-matrix cotangents such as dA, which no model parameter feeds; the per-matrix check is made at T=120 above.)"""
+    case = H.Case("pmdelay2", S=3, T=600, N=50, d=2)
+    assert H.check_param_vjp(lib, dev, case, torch.float32) < 1e-3
+
+
 def test_many_samples_multiple_warps_and_chunks(lib, dev):
     case = H.Case("subjective2", S=70, T=60, N=12)
     H.check_vjp(lib, dev, case, torch.float32)                  # one chunk, 3 warps, padded

@@ -1,0 +1,161 @@
+"""Parity against fixtures produced by EXECUTING THE REFERENCE'S OWN SOURCE (tests/golden/ref_*.npz, made by
+tests/golden/make_reference_golden.py: lqg/{spec,utils,system}.py, lqg/control/lqr.py, lqg/belief/kf.py and
+lqg/tracking/*.py imported unmodified from /root/reference over a float64 NumPy stand-in for jax/numpyro).
+
+not-gpu : the oracle (values, gains, moments, hand adjoint) and the kernels' step functions (host emulation) reproduce the
+          reference; the product's model constructors build the reference's matrices.
+gpu     : the CUDA library through the public Python API reproduces the reference's log-likelihood (rtol 1e-4), parameter
+          gradient (rtol 1e-3) and gains (rtol 1e-4) -- BASELINE.json's tolerances.
+Nothing here reads /root/reference at run time."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from lqg_b200 import abi, tracking
+from lqg_b200.tracking.delay import TemporalDelayModel
+from oracle import adjoint_np as AD
+from oracle import lqg_np as O
+from tests import helpers as H
+
+FIXTURES = sorted(glob.glob(os.path.join(H.ROOT, "tests", "golden", "ref_*.npz")))
+IDS = [os.path.basename(p)[4:-4] for p in FIXTURES]
+ORACLE_BUILDERS = {"BoundedActor": O.bounded_actor_mats, "OptimalActor": O.optimal_actor_mats, "SubjectiveActor": O.subjective_actor_mats,
+                   "RelativeObservationBoundedActor": O.relative_observation_mats, "PointMassBoundedActor": O.point_mass_mats}
+LL_RTOL, GRAD_RTOL, GAIN_RTOL = 1e-4, 1e-3, 1e-4        # BASELINE.json north_star tolerances (CUDA vs float64 reference)
+
+
+class Fixture:
+    def __init__(self, path):
+        z = np.load(path)
+        self.z = z
+        self.model, self.delay, self.T, self.N, self.d = str(z["model"]), int(z["delay"]), int(z["T"]), int(z["N"]), int(z["obs_dim"])
+        self.fixed = {str(k): (int(v) if float(v).is_integer() else float(v)) for k, v in zip(z["fixed_names"], z["fixed_values"])}
+        self.names = [str(k) for k in z["param_names"]]
+        self.params = dict(zip(self.names, [float(v) for v in z["param_values"]]))
+        self.X = z["X"]
+        self.ref_act = {k: z["actor_" + k] for k in abi.ACTOR_KEYS}
+        self.ref_dyn = {k: z["dyn_" + k] for k in abi.DYN_KEYS}
+        # tiny gradient components (near an optimum) are compared on the scale of the largest one; the finite-difference
+        # error estimate of the fixture itself is added
+        self.g_atol = 1e-5 * np.abs(z["grad"]).max() + 10 * z["grad_err"]
+
+    def oracle_mats(self):
+        kw = {k: v for k, v in self.fixed.items() if k != "T"}
+        if self.model in ("PointMassBoundedActor",):
+            kw.pop("dim", None)
+        m = ORACLE_BUILDERS[self.model](**kw, **self.params)
+        return tuple(O.delay_mats(mm, self.delay) for mm in m) if self.delay else m
+
+    def product_model(self, device, dtype, requires_grad=False):
+        th = [torch.tensor(self.params[k], dtype=dtype, device=device, requires_grad=requires_grad) for k in self.names]
+        m = getattr(tracking, self.model)(**self.fixed, device=device, dtype=dtype, **dict(zip(self.names, th)))
+        return (TemporalDelayModel(m, self.delay) if self.delay else m), th
+
+    def chain(self, ga, gd):
+        """Parameter gradient from base-matrix cotangents and the reference constructor's Jacobians."""
+        g = np.zeros(len(self.names))
+        for k in abi.ACTOR_KEYS:
+            g += np.tensordot(self.z["jac_actor_" + k], np.asarray(ga[k], dtype=np.float64), axes=([1, 2], [0, 1]))
+        for k in abi.DYN_KEYS:
+            g += np.tensordot(self.z["jac_dyn_" + k], np.asarray(gd[k], dtype=np.float64), axes=([1, 2], [0, 1]))
+        return g
+
+
+@pytest.fixture(params=FIXTURES, ids=IDS)
+def fx(request):
+    return Fixture(request.param)
+
+
+def test_fixtures_present():
+    assert len(FIXTURES) >= 9
+
+
+def test_oracle_constructors_build_the_reference_matrices(fx):
+    a, d = fx.oracle_mats()
+    for k in abi.ACTOR_KEYS:
+        assert np.allclose(a[k], fx.ref_act[k], rtol=1e-12, atol=1e-14), ("actor", k)
+    for k in abi.DYN_KEYS:
+        assert np.allclose(d[k], fx.ref_dyn[k], rtol=1e-12, atol=1e-14), ("dyn", k)
+
+
+def test_product_constructors_build_the_reference_matrices(fx):
+    m, _ = fx.product_model("cpu", torch.float64)
+    for k in abi.ACTOR_KEYS:
+        assert np.allclose(getattr(m.actor, k)[0].numpy(), fx.ref_act[k], rtol=1e-10, atol=1e-13), ("actor", k)
+    for k in abi.DYN_KEYS:
+        assert np.allclose(getattr(m.dynamics, k)[0].numpy(), fx.ref_dyn[k], rtol=1e-10, atol=1e-13), ("dyn", k)
+    assert (m.T, m.xdim, m.bdim) == (fx.T, fx.ref_dyn["A"].shape[0], fx.ref_act["A"].shape[0])
+
+
+def test_oracle_reproduces_reference_values(fx):
+    """lqr.backward, kf.forward, conditional_moments and log_likelihood of the float64 oracle == the reference's."""
+    x, u = fx.ref_dyn["A"].shape[0], fx.ref_dyn["B"].shape[1]
+    sa, sd = O.make_system((fx.ref_act, dict(fx.ref_dyn, Q=np.zeros((x, x)), R=np.zeros((u, u)))), fx.T)   # system.py:331-345
+    z = fx.z
+    L, l, Hh = O.lqr_backward(sa)
+    K = O.kf_forward(sa, sa["V"][0] @ sa["V"][0].T)
+    assert np.allclose(L, z["L"], rtol=1e-9, atol=1e-12 * np.abs(z["L"]).max())
+    assert np.allclose(Hh, z["H"], rtol=1e-9)
+    assert np.allclose(K, z["K"], rtol=1e-9, atol=1e-12 * np.abs(z["K"]).max())
+    assert np.abs(l).max() == 0.0 and float(z["l_absmax"]) == 0.0
+    X = fx.X.astype(np.float64)
+    mu, Sig = O.conditional_moments(sa, sd, X[0])
+    st = z["steps"]
+    assert np.allclose(mu[st], z["mu_steps"], rtol=1e-8, atol=1e-9 * np.abs(z["mu_steps"]).max())
+    assert np.allclose(Sig[st], z["Sigma_steps"], rtol=1e-8, atol=1e-9 * np.abs(z["Sigma_steps"]).max())
+    ll = O.log_likelihood(sa, sd, X)
+    assert np.allclose(ll, z["ll"], rtol=1e-10)
+
+
+def test_oracle_adjoint_matches_reference_gradient(fx):
+    """Hand adjoint (the kernels' mathematical spec) chained through the reference constructor's Jacobians == central
+    differences of sum(log_likelihood) through the reference."""
+    ll, (ga, gd) = AD.value_and_grad(fx.ref_act, fx.ref_dyn, fx.X.astype(np.float64))
+    assert np.allclose(ll, fx.z["ll"], rtol=1e-10)
+    g = fx.chain(ga, gd)
+    assert np.allclose(g, fx.z["grad"], rtol=1e-5, atol=fx.g_atol), (g, fx.z["grad"])
+
+
+def test_step_functions_reproduce_reference(fx):
+    """The kernels' own step functions (host emulation through the C ABI structs) against the reference."""
+    lib = abi.Library(H.EMUL_PATH)
+    x, b, u, y = fx.ref_dyn["A"].shape[0], fx.ref_act["A"].shape[0], fx.ref_act["B"].shape[1], fx.ref_act["F"].shape[0]
+    dims = abi.LqgkDims(1, fx.N, fx.T, x, b, u, y, fx.d)
+    act = {k: torch.tensor(np.ascontiguousarray(fx.ref_act[k]))[None] for k in abi.ACTOR_KEYS}
+    dyn = {k: torch.tensor(np.ascontiguousarray(fx.ref_dyn[k]))[None] for k in abi.DYN_KEYS}
+    ll, ga, gd, _ = lib.loglik_vjp(dims, act, dyn, lib.pack_obs(torch.tensor(fx.X)))
+    assert np.allclose(ll[0].numpy(), fx.z["ll"], rtol=LL_RTOL)
+    g = fx.chain({k: v[0].numpy() for k, v in ga.items()}, {k: v[0].numpy() for k, v in gd.items()})
+    assert np.allclose(g, fx.z["grad"], rtol=GRAD_RTOL, atol=fx.g_atol), (g, fx.z["grad"])
+    L, _, Hh = lib.lqr_backward(dims, act)
+    K = lib.kf_forward(dims, act)
+    assert np.allclose(L[0].numpy(), fx.z["L"], rtol=1e-8, atol=1e-11 * np.abs(fx.z["L"]).max())
+    assert np.allclose(K[0].numpy(), fx.z["K"], rtol=1e-8, atol=1e-11 * np.abs(fx.z["K"]).max())
+    assert np.allclose(Hh[0].numpy(), fx.z["H"], rtol=1e-8)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32", "f64"])
+def test_cuda_public_api_reproduces_reference(fx, dtype):
+    """CUDA path (public API: model constructor -> log_likelihood -> backward, lqr.backward, kf.forward) vs the reference."""
+    from lqg_b200.belief import kf
+    from lqg_b200.control import lqr
+    dev = torch.device("cuda:0")
+    m, th = fx.product_model(dev, dtype, requires_grad=True)
+    ll = m.log_likelihood(torch.tensor(fx.X, device=dev))
+    ll.sum().backward()
+    assert np.allclose(ll.detach().double().cpu().numpy(), fx.z["ll"], rtol=LL_RTOL)
+    g = np.array([t.grad.item() for t in th])
+    assert np.allclose(g, fx.z["grad"], rtol=GRAD_RTOL, atol=fx.g_atol + 1e-5 * np.abs(fx.z["grad"]).max()), (g, fx.z["grad"])
+    with torch.no_grad():
+        m64, _ = fx.product_model(dev, torch.float64)
+        gains = lqr.backward(m64.actor)
+        K = kf.forward(m64.actor, m64.actor.V[0] @ m64.actor.V[0].T)
+    zl, zk = fx.z["L"], fx.z["K"]
+    assert np.allclose(gains.L.cpu().numpy(), zl, rtol=GAIN_RTOL, atol=1e-7 * np.abs(zl).max())
+    assert np.allclose(K.cpu().numpy(), zk, rtol=GAIN_RTOL, atol=1e-7 * np.abs(zk).max())
+    assert np.allclose(gains.H.cpu().numpy(), fx.z["H"], rtol=GAIN_RTOL)
+    assert float(gains.l.abs().max()) == 0.0
