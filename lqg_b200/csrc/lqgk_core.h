@@ -31,10 +31,12 @@
 // their matrices live in local memory and a fully unrolled body would neither fit registers nor compile in minutes.
 #if defined(__CUDACC__) && !defined(LQGK_BIG)
 #define LQGK_UNROLL64 _Pragma("unroll")
+#elif defined(__CUDACC__) && defined(LQGK_UNROLL64_FORCE_1)
+#define LQGK_UNROLL64 _Pragma("unroll 1")
 #elif defined(__CUDACC__)
 // No pragma at all (the compiler's own heuristics): with `#pragma unroll 1` on these loop nests the NVVM optimiser of
 // CUDA 12.9 (-O3; correct at -Xcicc -O1) miscompiled cov_fwd_body -- device results differed from the host run of the
-// same code (gpurun_scratch/dbg_body.cu reproduces it) -- while the un-annotated loops compile correctly.
+// same code (tools/repro/nvvm_unroll1_cov_fwd.cu reproduces it with -DLQGK_UNROLL64_FORCE_1) -- while the un-annotated loops compile correctly.
 #define LQGK_UNROLL64
 #else
 #define LQGK_UNROLL64

@@ -2,7 +2,10 @@
 #include <cstdio>
 #include <vector>
 #include <cstdlib>
-#include "../lqg_b200/csrc/lqgk_stages.h"
+// Reproducer: with `#pragma unroll 1` on the FP64 loop nests (LQGK_UNROLL64), nvcc 12.9 -O3 produced device results that differ
+// from the host run of the same code; correct with -Xcicc -O1 or without the pragma.  Build: nvcc -std=c++17 -O3 -gencode
+// arch=compute_100a,code=sm_100a -DLQGK_UNROLL64_FORCE_1 tools/repro/nvvm_unroll1_cov_fwd.cu ; run on a B200: ./a.out 1
+#include "../../lqg_b200/csrc/lqgk_stages.h"
 using namespace lqgk;
 using DM = Dims<12, 12, 1, 3, 2>;
 using C = CovC<DM>;
