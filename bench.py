@@ -207,17 +207,22 @@ def bench_c4(dev, S=4096, N=50, T=600, reps=2):
         ll.backward()
         return ll
 
+    from lqg_b200 import abi
+    lib = abi.load_library()
     evaluate()
     torch.cuda.synchronize()
+    lib.profile_enable(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
         ll = evaluate()
     e1.record()
     torch.cuda.synchronize()
+    prof = lib.profile_read()
+    lib.profile_enable(False)
     ms = e0.elapsed_time(e1) / reps
     assert torch.isfinite(ll) and all(torch.isfinite(t.grad).all() for t in th.values())
-    return S * N / (ms * 1e-3), ms
+    return S * N / (ms * 1e-3), ms, {k: round(v[0] / reps, 2) for k, v in prof.items() if v[1]}
 
 
 # ----------------------------------------------------------------------------------------------- reference arm
@@ -456,11 +461,11 @@ def run_ours(args):
                                      "parameters, one fused call through the public API (latency-bound: 6 systems)",
                          "value": c2_val, "unit": "trial-evals/s", "ms_per_eval": c2_ms}
             if not args.no_c4:
-                c4_val, c4_ms = bench_c4(dev)
+                c4_val, c4_ms, c4_k = bench_c4(dev)
                 secondary = [secondary,
                              {"workload": "c4: TemporalDelayModel(PointMassBoundedActor, delay=2) (x=b=12, joint dim 24), 4,096 parameter "
                                           "samples x 50 trials x T=600, grad wrt 4 parameters per sample, public API (large-system kernels)",
-                              "value": c4_val, "unit": "trial-evals/s", "ms_per_eval": c4_ms}]
+                              "value": c4_val, "unit": "trial-evals/s", "ms_per_eval": c4_ms, "kernel_ms": c4_k}]
         line = {"metric": "trial log-lik+grad evals/sec", "value": value, "unit": "trial-evals/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64 per-sample recursions + f32 per-trial recursions (f32 I/O)",
