@@ -13,25 +13,12 @@
 // The per-trial FP32 kernels (k_trial_fwd / k_trial_rev: warp per sample, lane = trial, TMA-staged records) are shared
 // with the small-system path; only their ring geometry adapts to the record size.
 #pragma once
+#include "lqgk_bigw.cuh"
 #include "lqgk_run.cuh"
 
 namespace lqgk {
 
 constexpr int BIG_TPB = 8;   // samples (threads) per CTA
-
-struct GlobalRecSink {
-  float* row;
-  int rec;
-  __device__ __forceinline__ void put(int idx, float v) { row[idx] = v; }
-  __device__ __forceinline__ void commit(int) { row += rec; }
-};
-struct GlobalSumSrc {
-  const float* base;
-  int sump;
-  const float* row;
-  __device__ __forceinline__ void fetch(int t) { row = base + (size_t)t * sump; }
-  __device__ __forceinline__ float get(int idx) const { return row[idx]; }
-};
 
 template <class DM, bool AFFINE>
 __global__ void __launch_bounds__(BIG_TPB) kb_lqr_fwd(const double* cst, size_t Sc, size_t tstride, int npad, int Tn, double eps,
@@ -50,54 +37,12 @@ __global__ void __launch_bounds__(BIG_TPB) kb_kf_fwd(const double* cst, size_t S
   kf_fwd_body<DM>(GCst{cst + s, Sc, tstride}, WView{scr + s, Sc}, Tn, WView{K + s, Sc}, save_P != 0, WView{Pkf + s, Sc});
 }
 
-template <class DM>
-__global__ void __launch_bounds__(BIG_TPB) kb_cov_fwd(const double* cst, size_t Sc, size_t tstride, int npad, int Tn, const double* L,
-                                                      const double* K, int save_adj, double* Cs, double* FU, double* JS, double* J0,
-                                                      float* rec, double* scr) {
-  const size_t s = (size_t)blockIdx.x * BIG_TPB + threadIdx.x;
-  if (s >= (size_t)npad) return;
-  GlobalRecSink sink{rec + s * Tn * DM::REC, DM::REC};
-  cov_fwd_body<DM>(GCst{cst + s, Sc, tstride}, WView{scr + s, Sc}, Tn, WView{const_cast<double*>(L) + s, Sc},
-                   WView{const_cast<double*>(K) + s, Sc}, save_adj != 0, WView{Cs + s, Sc}, WView{FU + s, Sc}, WView{JS + s, Sc},
-                   WView{J0 + s, Sc}, sink);
-}
-
-template <class DM>
-__global__ void __launch_bounds__(BIG_TPB) kb_cov_seq_rev(size_t Sc, int npad, int Tn, int N, const float* w, const double* FU,
-                                                          const double* JS, const double* J0, const float* sums, double* SGB,
-                                                          double* SGBI, double* SFW, double* scr) {
-  const size_t s = (size_t)blockIdx.x * BIG_TPB + threadIdx.x;
-  if (s >= (size_t)npad) return;
-  double sw = 0.0;
-  for (int i = 0; i < N; ++i) sw += (double)w[s * N + i];
-  GlobalSumSrc src{sums + s * Tn * DM::SUMP, DM::SUMP, nullptr};
-  auto V = [&](const double* p) { return WView{const_cast<double*>(p) + s, Sc}; };
-  cov_seq_rev_body<DM>(Tn, sw, V(FU), V(JS), V(J0), src, WView{scr + s, Sc}, V(SGB), V(SGBI), V(SFW));
-}
-
 // lcc: CovC-layout constants [C::n][Sc] (filled by kb_load_cov_consts); la: accumulators [C::n][Sc] (zeroed by the caller).
 template <class DM>
 __global__ void __launch_bounds__(BIG_TPB) kb_load_cov_consts(const double* cst, size_t Sc, int npad, double* lcc) {
   const size_t s = (size_t)blockIdx.x * BIG_TPB + threadIdx.x;
   if (s >= (size_t)npad) return;
   load_consts<CovC<DM>>(WView{const_cast<double*>(cst) + s, Sc}, WView{lcc + s, Sc}, CovC<DM>::NSEG);
-}
-template <class DM>
-__global__ void __launch_bounds__(BIG_TPB) kb_cov_contrib(size_t Sc, int npad, int Tn, const double* lcc, const double* L,
-                                                          const double* K, const double* Cs, const double* SGB, const double* SGBI,
-                                                          const double* SFW, const float* sums, double* la, double* Lbar,
-                                                          double* Kbar) {
-  const size_t s = (size_t)blockIdx.x * BIG_TPB + threadIdx.x;
-  if (s >= (size_t)npad) return;
-  const int nq = gridDim.y, q = blockIdx.y;
-  const int per = (Tn + nq - 1) / nq;
-  const int t0 = min(Tn, q * per), t1 = min(Tn, t0 + per);
-  if (t0 >= t1) return;
-  GlobalSumSrc src{sums + s * Tn * DM::SUMP, DM::SUMP, nullptr};
-  auto V = [&](const double* p) { return WView{const_cast<double*>(p) + s, Sc}; };
-  auto ct = [&](int, int e, double v) { atomicAdd(la + (size_t)e * Sc + s, v); };
-  cov_contrib_body<DM, 0>(V(lcc), t0, t1, V(L), V(K), V(Cs), V(SGB), V(SGBI), V(SFW), src, ct, V(Lbar), V(Kbar));
-  cov_contrib_body<DM, 1>(V(lcc), t0, t1, V(L), V(K), V(Cs), V(SGB), V(SGBI), V(SFW), src, ct, V(Lbar), V(Kbar));
 }
 template <class DM>
 __global__ void __launch_bounds__(BIG_TPB) kb_flush_cov(size_t Sc, int npad, const double* la, double* acc) {
@@ -208,10 +153,16 @@ int run_big(const Call& c) {
       kb_kf_fwd<DM><<<nblk, BIG_TPB, 0, st>>>(D(p.cst), Sc, tstride, npad, Tn, D(p.K), vjp, vjp ? D(p.Pkf) : nullptr, lc);
       LQGK_LAUNCH_CHECK();
     }
+    const int wblk = (npad + BW_WARPS - 1) / BW_WARPS;
     {
+      if (tv) return LQGK_E_UNSUPPORTED;   // time-varying specs: gains API only on the large-system path
+      size_t smem = BigW<DM>::smem_fwd();
+      if ((rc = set_smem<DM>((const void*)kw_cov_fwd<DM>, smem))) return rc;
       ProfScope ps_(PK_COV_FWD, st);
-      kb_cov_fwd<DM><<<nblk, BIG_TPB, 0, st>>>(D(p.cst), Sc, tstride, npad, Tn, D(p.L), D(p.K), vjp, vjp ? D(p.Cs) : nullptr,
-                                               vjp ? D(p.FU) : nullptr, vjp ? D(p.JS) : nullptr, vjp ? D(p.J0) : nullptr, F(p.rec), lc);
+      kb_load_cov_consts<DM><<<nblk, BIG_TPB, 0, st>>>(D(p.cst), Sc, npad, lc);
+      LQGK_LAUNCH_CHECK();
+      kw_cov_fwd<DM><<<wblk, 32 * BW_WARPS, smem, st>>>(lc, Sc, npad, Tn, D(p.L), D(p.K), vjp, vjp ? D(p.Cs) : nullptr, vjp ? D(p.FU) : nullptr,
+                                                       vjp ? D(p.JS) : nullptr, vjp ? D(p.J0) : nullptr, F(p.rec));
       LQGK_LAUNCH_CHECK();
     }
     const int RT = std::min((N + 31) / 32, trial_rt_max<DM>());
@@ -251,20 +202,22 @@ int run_big(const Call& c) {
         return LQGK_E_CUDA;
     }
     {
+      size_t smem = BigW<DM>::smem_seq();
+      if ((rc = set_smem<DM>((const void*)kw_cov_seq_rev<DM>, smem))) return rc;
       ProfScope ps_(PK_COV_REV, st);
-      kb_cov_seq_rev<DM><<<nblk, BIG_TPB, 0, st>>>(Sc, npad, Tn, N, F(p.w), D(p.FU), D(p.JS), D(p.J0), F(p.sums), D(p.SGB), D(p.SGBI),
-                                                   D(p.SFW), lc);
+      kw_cov_seq_rev<DM><<<wblk, 32 * BW_WARPS, smem, st>>>(npad, Tn, N, F(p.w), D(p.FU), D(p.JS), D(p.J0), F(p.sums), D(p.SGB), D(p.SGBI),
+                                                           D(p.SFW));
       LQGK_LAUNCH_CHECK();
     }
     {
+      size_t smem = BigW<DM>::smem_con();
+      if ((rc = set_smem<DM>((const void*)kw_cov_contrib<DM>, smem))) return rc;
       ProfScope ps_(PK_COV_CONTRIB, st);
-      kb_load_cov_consts<DM><<<nblk, BIG_TPB, 0, st>>>(D(p.cst), Sc, npad, lc);
-      LQGK_LAUNCH_CHECK();
       if (cudaMemsetAsync(la, 0, sizeof(double) * SROWS * Sc, st) != cudaSuccess) return LQGK_E_CUDA;
-      // time ranges: enough (sample-group x range) CTAs to put several warps on every SM
-      int chunks = std::max(1, std::min((Tn + 3) / 4, (148 * 16 + nblk - 1) / nblk));
-      kb_cov_contrib<DM><<<dim3(nblk, chunks), BIG_TPB, 0, st>>>(Sc, npad, Tn, lc, D(p.L), D(p.K), D(p.Cs), D(p.SGB), D(p.SGBI), D(p.SFW),
-                                                                F(p.sums), la, D(p.Lbar), D(p.Kbar));
+      // time ranges: enough (sample x range) warps to put ~12 on every SM when there are few samples
+      int chunks = std::max(1, std::min((Tn + 3) / 4, (148 * 12 + npad - 1) / npad));
+      kw_cov_contrib<DM><<<dim3(wblk, chunks), 32 * BW_WARPS, smem, st>>>(lc, Sc, npad, Tn, D(p.L), D(p.K), D(p.Cs), D(p.SGB), D(p.SGBI),
+                                                                         D(p.SFW), F(p.sums), la, D(p.Lbar), D(p.Kbar));
       LQGK_LAUNCH_CHECK();
       kb_flush_cov<DM><<<nblk, BIG_TPB, 0, st>>>(Sc, npad, la, D(p.acc));
       LQGK_LAUNCH_CHECK();
