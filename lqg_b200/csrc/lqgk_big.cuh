@@ -1,82 +1,19 @@
-// lqgk_big.cuh -- per-sample (FP64) kernels and launch sequence for LARGE systems (joint dim n = x + b > 12, e.g. the
-// 24-dim delayed point-mass model of BASELINE config c4: TemporalDelayModel(PointMassBoundedActor, delay=2)).
+// lqgk_big.cuh -- launch sequence for LARGE systems (joint dim n = x + b > 12, e.g. the 24-dim delayed point-mass model
+// of BASELINE config c4: TemporalDelayModel(PointMassBoundedActor, delay=2)).
 //
-// The small-system kernels keep every matrix of a sample in registers (fully unrolled templates) and its constants in
-// shared memory; neither fits at n = 24 (576-entry joint matrices, ~900 derived constants per sample).  This path runs
-// the SAME step functions (lqgk_core.h / lqgk_stages.h, compiled with -DLQGK_BIG so their loops stay rolled) with
-//   * one thread per parameter sample, BIG_TPB samples per CTA (few lanes per warp: these systems come in thousands,
-//     not hundreds of thousands, of samples, and the recursions are latency-bound -- more warps beat fuller warps),
-//   * matrices in per-thread local memory (L1-resident, interleaved per lane by the hardware),
-//   * derived constants / cotangent accumulators in sample-minor global scratch (coalesced across a warp's samples),
-//   * the time-parallel contraction of the covariance adjoint split over blockIdx.y time ranges, accumulating into the
-//     per-sample accumulator block with FP64 atomics.
-// The per-trial FP32 kernels (k_trial_fwd / k_trial_rev: warp per sample, lane = trial, TMA-staged records) are shared
-// with the small-system path; only their ring geometry adapts to the record size.
+// The small-system kernels keep every matrix of a sample in registers (one thread per sample, fully unrolled templates)
+// and its constants in shared memory; neither fits at n = 24 (576-entry joint matrices, ~900 derived constants per sample),
+// and these systems come in thousands, not hundreds of thousands, of samples.  The large-system path therefore maps ONE
+// WARP PER PARAMETER SAMPLE with the matrices in shared memory (lqgk_bigw.cuh: kw_lqr_fwd, kw_kf_fwd, kw_cov_fwd,
+// kw_cov_seq_rev, kw_cov_contrib, kw_kf_rev, kw_lqr_rev) and sample-major workspace arrays.  The per-trial FP32 kernels
+// (k_trial_fwd / k_trial_rev: warp per sample, lane = trial, TMA-staged records) are shared with the small-system path;
+// only their ring geometry adapts to the record size.  The object is compiled with -DLQGK_BIG (rolled FP64 loops in the
+// scalar helpers the lanes still call for the u x u / y x y / d x d factorisations).
 #pragma once
 #include "lqgk_bigw.cuh"
 #include "lqgk_run.cuh"
 
 namespace lqgk {
-
-constexpr int BIG_TPB = 8;   // samples (threads) per CTA
-
-template <class DM, bool AFFINE>
-__global__ void __launch_bounds__(BIG_TPB) kb_lqr_fwd(const double* cst, size_t Sc, size_t tstride, int npad, int Tn, double eps,
-                                                      double* L, int save_S, double* Sric, double* l, double* H, double* scr) {
-  const size_t s = (size_t)blockIdx.x * BIG_TPB + threadIdx.x;
-  if (s >= (size_t)npad) return;
-  lqr_fwd_body<DM, AFFINE>(GCst{cst + s, Sc, tstride}, WView{scr + s, Sc}, Tn, eps, WView{L + s, Sc}, save_S != 0, WView{Sric + s, Sc},
-                           WView{l + s, Sc}, WView{H + s, Sc});
-}
-
-template <class DM>
-__global__ void __launch_bounds__(BIG_TPB) kb_kf_fwd(const double* cst, size_t Sc, size_t tstride, int npad, int Tn, double* K,
-                                                     int save_P, double* Pkf, double* scr) {
-  const size_t s = (size_t)blockIdx.x * BIG_TPB + threadIdx.x;
-  if (s >= (size_t)npad) return;
-  kf_fwd_body<DM>(GCst{cst + s, Sc, tstride}, WView{scr + s, Sc}, Tn, WView{K + s, Sc}, save_P != 0, WView{Pkf + s, Sc});
-}
-
-// lcc: CovC-layout constants [C::n][Sc] (filled by kb_load_cov_consts); la: accumulators [C::n][Sc] (zeroed by the caller).
-template <class DM>
-__global__ void __launch_bounds__(BIG_TPB) kb_load_cov_consts(const double* cst, size_t Sc, int npad, double* lcc) {
-  const size_t s = (size_t)blockIdx.x * BIG_TPB + threadIdx.x;
-  if (s >= (size_t)npad) return;
-  load_consts<CovC<DM>>(WView{const_cast<double*>(cst) + s, Sc}, WView{lcc + s, Sc}, CovC<DM>::NSEG);
-}
-template <class DM>
-__global__ void __launch_bounds__(BIG_TPB) kb_flush_cov(size_t Sc, int npad, const double* la, double* acc) {
-  const size_t s = (size_t)blockIdx.x * BIG_TPB + threadIdx.x;
-  if (s >= (size_t)npad) return;
-  flush_acc<CovC<DM>>(WView{acc + s, Sc}, WView{const_cast<double*>(la) + s, Sc}, CovC<DM>::NSEG);
-}
-
-template <class DM>
-__global__ void __launch_bounds__(BIG_TPB) kb_kf_rev(const double* cst, size_t Sc, int npad, int Tn, const double* Pkf,
-                                                     const double* Kbar, double* acc, double* lc, double* la) {
-  const size_t s = (size_t)blockIdx.x * BIG_TPB + threadIdx.x;
-  if (s >= (size_t)npad) return;
-  kf_rev_body<DM>(GCst{cst + s, Sc, 0}, WView{lc + s, Sc}, WView{la + s, Sc}, Tn, WView{const_cast<double*>(Pkf) + s, Sc},
-                  WView{const_cast<double*>(Kbar) + s, Sc}, WView{acc + s, Sc});
-}
-template <class DM>
-__global__ void __launch_bounds__(BIG_TPB) kb_lqr_rev(const double* cst, size_t Sc, int npad, int Tn, double eps, const double* L,
-                                                      const double* Sric, const double* Lbar, double* acc, double* lc, double* la) {
-  const size_t s = (size_t)blockIdx.x * BIG_TPB + threadIdx.x;
-  if (s >= (size_t)npad) return;
-  lqr_rev_body<DM>(GCst{cst + s, Sc, 0}, WView{lc + s, Sc}, WView{la + s, Sc}, Tn, eps, WView{const_cast<double*>(L) + s, Sc},
-                   WView{const_cast<double*>(Sric) + s, Sc}, WView{const_cast<double*>(Lbar) + s, Sc}, WView{acc + s, Sc});
-}
-
-// rows of the shared scratch block (two halves: constants copy | accumulators)
-template <class DM>
-constexpr int big_scratch_rows() {
-  int m = CovC<DM>::n;
-  m = LqrC<DM>::n_affine > m ? LqrC<DM>::n_affine : m;
-  m = KfC<DM>::n > m ? KfC<DM>::n : m;
-  m = CovSeqRev<DM>::SC_N > m ? CovSeqRev<DM>::SC_N : m;
-  return m;
-}
 
 template <class DM, class T>
 int run_big(const Call& c) {
@@ -95,9 +32,6 @@ int run_big(const Call& c) {
   cudaStream_t st = c.stream;
   const int Tn = d.T, N = d.N;
   const size_t tstride = tv ? (size_t)cl.total * Sc : 0;
-  constexpr int SROWS = big_scratch_rows<DM>();
-  double* lc = D(p.scr);
-  double* la = lc + (size_t)SROWS * Sc;
 
   PackArgs<T> pa{};
   pa.act = *c.act;
@@ -108,33 +42,38 @@ int run_big(const Call& c) {
   for (size_t s0 = 0; s0 < (size_t)d.S; s0 += Sc) {
     const int n = (int)std::min(Sc, (size_t)d.S - s0);
     const int npad = (int)up(n, 32);
-    const int nblk = (npad + BIG_TPB - 1) / BIG_TPB;
+    const int wblk = (npad + BW_WARPS - 1) / BW_WARPS;
+    const unsigned wthr = 32 * BW_WARPS;
+    const size_t sm_lqr = BigG<DM>::smem_lqr(), sm_kf = BigG<DM>::smem_kf();
     {
       dim3 grid((npad + 127) / 128, tv ? Tn : 1);
       ProfScope ps_(PK_PACK, st);
       k_pack<T><<<grid, 128, 0, st>>>(pa, (int)s0, n, npad, D(p.cst), Sc, tstride, tv ? Tn : 1);
       LQGK_LAUNCH_CHECK();
     }
-    auto store = [&](size_t off, int E, void* out) -> int {
+    auto store = [&](size_t off, int E, void* out) -> int {   // workspace arrays are sample-major [s][t][E] = the user layout
       if (!out) return LQGK_OK;
       size_t total = (size_t)n * Tn * E;
-      k_store_rows<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(D(off), Sc, n, Tn, E, (T*)out + s0 * Tn * E);
+      k_store_ll<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(D(off), total, (T*)out + s0 * Tn * E);
       LQGK_LAUNCH_CHECK();
       return LQGK_OK;
     };
+    if (tv) return LQGK_E_UNSUPPORTED;   // time-varying specs are not implemented on the large-system path
     if (c.mode == LQGK_MODE_GAINS) {
       int rc;
       if (c.L_out) {
+        if ((rc = set_smem<DM>((const void*)kw_lqr_fwd<DM, true>, sm_lqr))) return rc;
         ProfScope ps_(PK_LQR_FWD, st);
-        kb_lqr_fwd<DM, true><<<nblk, BIG_TPB, 0, st>>>(D(p.cst), Sc, tstride, npad, Tn, c.eps, D(p.L), 0, nullptr, D(p.l), D(p.H), lc);
+        kw_lqr_fwd<DM, true><<<wblk, wthr, sm_lqr, st>>>(D(p.cst), Sc, npad, Tn, c.eps, D(p.L), 0, nullptr, D(p.l), D(p.H));
         LQGK_LAUNCH_CHECK();
         if ((rc = store(p.L, DM::EL, c.L_out))) return rc;
         if ((rc = store(p.l, DM::U, c.l_out))) return rc;
         if ((rc = store(p.H, DM::U * DM::U, c.H_out))) return rc;
       }
       if (c.K_out) {
+        if ((rc = set_smem<DM>((const void*)kw_kf_fwd<DM>, sm_kf))) return rc;
         ProfScope ps_(PK_KF_FWD, st);
-        kb_kf_fwd<DM><<<nblk, BIG_TPB, 0, st>>>(D(p.cst), Sc, tstride, npad, Tn, D(p.K), 0, nullptr, lc);
+        kw_kf_fwd<DM><<<wblk, wthr, sm_kf, st>>>(D(p.cst), Sc, npad, Tn, D(p.K), 0, nullptr);
         LQGK_LAUNCH_CHECK();
         if ((rc = store(p.K, DM::EK, c.K_out))) return rc;
       }
@@ -143,26 +82,23 @@ int run_big(const Call& c) {
     const bool vjp = c.mode == LQGK_MODE_VJP;
     int rc;
     {
+      if ((rc = set_smem<DM>((const void*)kw_lqr_fwd<DM, false>, sm_lqr))) return rc;
       ProfScope ps_(PK_LQR_FWD, st);
-      kb_lqr_fwd<DM, false><<<nblk, BIG_TPB, 0, st>>>(D(p.cst), Sc, tstride, npad, Tn, c.eps, D(p.L), vjp, vjp ? D(p.Sric) : nullptr,
-                                                      nullptr, nullptr, lc);
+      kw_lqr_fwd<DM, false><<<wblk, wthr, sm_lqr, st>>>(D(p.cst), Sc, npad, Tn, c.eps, D(p.L), vjp, vjp ? D(p.Sric) : nullptr, nullptr, nullptr);
       LQGK_LAUNCH_CHECK();
     }
     {
+      if ((rc = set_smem<DM>((const void*)kw_kf_fwd<DM>, sm_kf))) return rc;
       ProfScope ps_(PK_KF_FWD, st);
-      kb_kf_fwd<DM><<<nblk, BIG_TPB, 0, st>>>(D(p.cst), Sc, tstride, npad, Tn, D(p.K), vjp, vjp ? D(p.Pkf) : nullptr, lc);
+      kw_kf_fwd<DM><<<wblk, wthr, sm_kf, st>>>(D(p.cst), Sc, npad, Tn, D(p.K), vjp, vjp ? D(p.Pkf) : nullptr);
       LQGK_LAUNCH_CHECK();
     }
-    const int wblk = (npad + BW_WARPS - 1) / BW_WARPS;
     {
-      if (tv) return LQGK_E_UNSUPPORTED;   // time-varying specs: gains API only on the large-system path
       size_t smem = BigW<DM>::smem_fwd();
       if ((rc = set_smem<DM>((const void*)kw_cov_fwd<DM>, smem))) return rc;
       ProfScope ps_(PK_COV_FWD, st);
-      kb_load_cov_consts<DM><<<nblk, BIG_TPB, 0, st>>>(D(p.cst), Sc, npad, lc);
-      LQGK_LAUNCH_CHECK();
-      kw_cov_fwd<DM><<<wblk, 32 * BW_WARPS, smem, st>>>(lc, Sc, npad, Tn, D(p.L), D(p.K), vjp, vjp ? D(p.Cs) : nullptr, vjp ? D(p.FU) : nullptr,
-                                                       vjp ? D(p.JS) : nullptr, vjp ? D(p.J0) : nullptr, F(p.rec));
+      kw_cov_fwd<DM><<<wblk, wthr, smem, st>>>(D(p.cst), Sc, npad, Tn, D(p.L), D(p.K), vjp, vjp ? D(p.Cs) : nullptr, vjp ? D(p.FU) : nullptr,
+                                               vjp ? D(p.JS) : nullptr, vjp ? D(p.J0) : nullptr, F(p.rec));
       LQGK_LAUNCH_CHECK();
     }
     const int RT = std::min((N + 31) / 32, trial_rt_max<DM>());
@@ -213,23 +149,22 @@ int run_big(const Call& c) {
       size_t smem = BigW<DM>::smem_con();
       if ((rc = set_smem<DM>((const void*)kw_cov_contrib<DM>, smem))) return rc;
       ProfScope ps_(PK_COV_CONTRIB, st);
-      if (cudaMemsetAsync(la, 0, sizeof(double) * SROWS * Sc, st) != cudaSuccess) return LQGK_E_CUDA;
       // time ranges: enough (sample x range) warps to put ~12 on every SM when there are few samples
       int chunks = std::max(1, std::min((Tn + 3) / 4, (148 * 12 + npad - 1) / npad));
-      kw_cov_contrib<DM><<<dim3(wblk, chunks), 32 * BW_WARPS, smem, st>>>(lc, Sc, npad, Tn, D(p.L), D(p.K), D(p.Cs), D(p.SGB), D(p.SGBI),
-                                                                         D(p.SFW), F(p.sums), la, D(p.Lbar), D(p.Kbar));
-      LQGK_LAUNCH_CHECK();
-      kb_flush_cov<DM><<<nblk, BIG_TPB, 0, st>>>(Sc, npad, la, D(p.acc));
+      kw_cov_contrib<DM><<<dim3(wblk, chunks), wthr, smem, st>>>(D(p.cst), Sc, npad, Tn, D(p.L), D(p.K), D(p.Cs), D(p.SGB), D(p.SGBI),
+                                                                D(p.SFW), F(p.sums), D(p.acc), D(p.Lbar), D(p.Kbar));
       LQGK_LAUNCH_CHECK();
     }
     {
+      if ((rc = set_smem<DM>((const void*)kw_kf_rev<DM>, sm_kf))) return rc;
       ProfScope ps_(PK_KF_REV, st);
-      kb_kf_rev<DM><<<nblk, BIG_TPB, 0, st>>>(D(p.cst), Sc, npad, Tn, D(p.Pkf), D(p.Kbar), D(p.acc), lc, la);
+      kw_kf_rev<DM><<<wblk, wthr, sm_kf, st>>>(D(p.cst), Sc, npad, Tn, D(p.Pkf), D(p.Kbar), D(p.acc));
       LQGK_LAUNCH_CHECK();
     }
     {
+      if ((rc = set_smem<DM>((const void*)kw_lqr_rev<DM>, sm_lqr))) return rc;
       ProfScope ps_(PK_LQR_REV, st);
-      kb_lqr_rev<DM><<<nblk, BIG_TPB, 0, st>>>(D(p.cst), Sc, npad, Tn, c.eps, D(p.L), D(p.Sric), D(p.Lbar), D(p.acc), lc, la);
+      kw_lqr_rev<DM><<<wblk, wthr, sm_lqr, st>>>(D(p.cst), Sc, npad, Tn, c.eps, D(p.L), D(p.Sric), D(p.Lbar), D(p.acc));
       LQGK_LAUNCH_CHECK();
     }
     {

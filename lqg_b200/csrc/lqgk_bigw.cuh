@@ -3,9 +3,9 @@
 // The joint-system covariance scan and its adjoint carry the big matrices of a large system (n x n, n x r, r x r with
 // n = 24, r = 22 at config c4): one warp owns one parameter sample, the matrices live in that warp's slice of shared memory
 // (FP64, row-major), every matrix product is spread over the 32 lanes by output element, and dependent products are
-// separated by __syncwarp().  Per-step inputs/outputs of these three kernels use SAMPLE-MAJOR workspace arrays
-// ([sample][t][element]) so a warp's loads and stores are contiguous; the small per-step gain arrays (L, K, Lbar, Kbar)
-// stay sample-minor because the thread-per-sample Riccati / Kalman kernels produce and consume them.
+// separated by __syncwarp().  Per-step inputs/outputs use SAMPLE-MAJOR workspace arrays ([sample][t][element]) so a
+// warp's loads and stores are contiguous; the small per-step gain arrays (L, K, Lbar, Kbar)
+// are sample-major as well (every kernel of the large-system path is warp-per-sample).
 //
 // Mathematics: identical to CovFwd / CovSeqRev / CovContrib in lqgk_core.h (which the host emulation and the small-system
 // kernels execute) and to oracle/adjoint_np.py; reference lines: lqg/system.py:163-212, 223-230 and their reverse mode.
@@ -25,6 +25,39 @@ __device__ __forceinline__ void wmm(int lane, FA&& a, FB&& b, Out&& out) {
 #pragma unroll 4
     for (int k = 0; k < K; ++k) acc += a(i, k) * b(k, j);
     out(i, j, acc);
+  }
+}
+
+// Derived constants of one sample: global block (sample-minor, stride Sc, CLayout order) -> this warp's shared copy in the
+// kernel-local layout KC (LqrC / KfC / CovC), and the reverse for cotangent accumulators (FP64 atomics: several warps --
+// time ranges, or the Riccati and Kalman adjoints -- add into the same per-sample block).
+template <class KC>
+__device__ __forceinline__ void bw_load_consts(int lane, const double* g, size_t Sc, double* c, int nseg) {
+  for (int i = 0; i < nseg; ++i) {
+    int go, lo, len;
+    KC::seg(i, go, lo, len);
+    for (int e = lane; e < len; e += 32) c[lo + e] = g[(size_t)(go + e) * Sc];
+  }
+}
+template <class KC>
+__device__ __forceinline__ void bw_flush_acc(int lane, double* g, size_t Sc, const double* a, int nseg) {
+  for (int i = 0; i < nseg; ++i) {
+    int go, lo, len;
+    KC::seg(i, go, lo, len);
+    for (int e = lane; e < len; e += 32) atomicAdd(g + (size_t)(go + e) * Sc, a[lo + e]);
+  }
+}
+// C[M,M] = base(i,j) + sum_k a(i,k) b(k,j), result known symmetric: lower triangle computed, mirrored.
+template <int M, int K, class Base, class FA, class FB>
+__device__ __forceinline__ void wmm_sym(int lane, Base&& base, FA&& a, FB&& b, double* Cm) {
+  for (int e = lane; e < M * M; e += 32) {
+    const int i = e / M, j = e - i * M;
+    if (j > i) continue;
+    double acc = base(i, j);
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) acc += a(i, k) * b(k, j);
+    Cm[i * M + j] = acc;
+    Cm[j * M + i] = acc;
   }
 }
 
@@ -106,9 +139,10 @@ __device__ __forceinline__ void bw_condition(int lane, const double* Sig, double
   __syncwarp();
 }
 
-// Covariance pass (forward), warp per sample.  L, K: sample-minor [t][e][Sc];  Cs, FU, JS, J0: sample-major;  rec [s][t][REC].
+// Covariance pass (forward), warp per sample.  cst: derived constants [element][Sc];  L, K, Cs, FU, JS, J0: sample-major;
+// rec [s][t][REC].
 template <class DM>
-__global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_fwd(const double* lcc, size_t Sc, int npad, int Tn, const double* L, const double* K,
+__global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_fwd(const double* cst, size_t Sc, int npad, int Tn, const double* L, const double* K,
                                                             int save_adj, double* Cs, double* FU, double* JS, double* J0, float* rec) {
   using W = BigW<DM>;
   using C = typename W::C;
@@ -131,16 +165,16 @@ __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_fwd(const double* lcc, s
   double* Z = T1 + N * R;
   double* Linv = Z + R * D;
   double* ld = Linv + 3 * D * D;
-  for (int e = lane; e < NC; e += 32) c[e] = lcc[(size_t)e * Sc + s];
-  for (int e = lane; e < B * Y; e += 32) Kt[e] = K[(size_t)e * Sc + s];
+  bw_load_consts<C>(lane, cst + s, Sc, c, C::NSEG);
+  for (int e = lane; e < B * Y; e += 32) Kt[e] = K[s * (size_t)Tn * DM::EK + e];
   __syncwarp();
   bw_joint_N<DM>(lane, c, Kt, KO, Nj);
   __syncwarp();
   bw_condition<DM>(lane, Nj, Linv, Z, ld, [&](int e, double v) { if (save_adj) J0[s * (R * D) + e] = v; }, Cm);
   float* recs = rec + s * (size_t)Tn * DM::REC;
   for (int t = 0; t < Tn; ++t) {
-    for (int e = lane; e < U * B; e += 32) Lt[e] = L[((size_t)t * DM::EL + e) * Sc + s];
-    for (int e = lane; e < B * Y; e += 32) Kt[e] = K[((size_t)t * DM::EK + e) * Sc + s];
+    for (int e = lane; e < U * B; e += 32) Lt[e] = L[(s * Tn + t) * (size_t)DM::EL + e];
+    for (int e = lane; e < B * Y; e += 32) Kt[e] = K[(s * Tn + t) * (size_t)DM::EK + e];
     if (save_adj) {
       double* cs = Cs + (s * Tn + t) * (size_t)DM::EC;
       for (int e = lane; e < R * R; e += 32) {
@@ -316,12 +350,12 @@ __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_seq_rev(int npad, int Tn
   }
 }
 
-// Time-parallel contraction (CovContrib pass 0 + pass 1), warp per (sample, time range).  la: [NC][Sc] accumulators
-// (CovC layout, zeroed by the caller) updated with one FP64 atomicAdd per element and warp.
+// Time-parallel contraction (CovContrib pass 0 + pass 1), warp per (sample, time range).  gacc: the per-sample cotangent
+// accumulators [element][Sc] (CLayout order, zeroed by the caller), updated with one FP64 atomicAdd per element and warp.
 template <class DM>
-__global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_contrib(const double* lcc, size_t Sc, int npad, int Tn, const double* L, const double* K,
+__global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_contrib(const double* cst, size_t Sc, int npad, int Tn, const double* L, const double* K,
                                                                 const double* Cs, const double* SGB, const double* SGBI, const double* SFW,
-                                                                const float* sums, double* la, double* Lbar, double* Kbar) {
+                                                                const float* sums, double* gacc, double* Lbar, double* Kbar) {
   using W = BigW<DM>;
   using C = typename W::C;
   using SR = typename W::SR;
@@ -347,7 +381,8 @@ __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_contrib(const double* lc
   double* KD = Kb + B * Y;
   double* T2 = KD + B * U;
   double* Lb = T2 + B * U;
-  for (int e = lane; e < NC; e += 32) { c[e] = lcc[(size_t)e * Sc + s]; acc[e] = 0.0; }
+  bw_load_consts<C>(lane, cst + s, Sc, c, C::NSEG);
+  for (int e = lane; e < NC; e += 32) acc[e] = 0.0;
   __syncwarp();
   // noise part of one symmetric joint cotangent Nb (CovContrib::noise_part); first = overwrite Kb, else accumulate
   auto noise = [&](bool first) {
@@ -386,8 +421,8 @@ __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_contrib(const double* lc
     const float* sm = sums + (s * Tn + t) * (size_t)DM::SUMP;
     const double* cs = Cs + (s * Tn + t) * (size_t)DM::EC;
     const double* sfw = SFW + (s * Tn + t) * (size_t)SR::NSF;
-    for (int e = lane; e < U * B; e += 32) Lt[e] = L[((size_t)t * DM::EL + e) * Sc + s];
-    for (int e = lane; e < B * Y; e += 32) Kt[e] = K[((size_t)t * DM::EK + e) * Sc + s];
+    for (int e = lane; e < U * B; e += 32) Lt[e] = L[(s * Tn + t) * (size_t)DM::EL + e];
+    for (int e = lane; e < B * Y; e += 32) Kt[e] = K[(s * Tn + t) * (size_t)DM::EK + e];
     for (int e = lane; e < R * R; e += 32) {
       const int i = e / R, j = e - i * R;
       Cm[e] = cs[sidx(i, j)];
@@ -443,12 +478,433 @@ __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_contrib(const double* lc
       for (int j = 0; j < X; ++j) a += Fb[(X + i) * N + j] * c[C::FAd + k * X + j];
       for (int j = 0; j < B; ++j) a -= Fb[(X + i) * N + X + j] * c[C::FAa + k * B + j];
       for (int m = 0; m < U; ++m) a += T2[i * U + m] * c[C::Dm + k * U + m];
-      Kbar[((size_t)t * DM::EK + e) * Sc + s] = Kb[e] + a;
+      Kbar[(s * Tn + t) * (size_t)DM::EK + e] = Kb[e] + a;
     }
-    for (int e = lane; e < U * B; e += 32) Lbar[((size_t)t * DM::EL + e) * Sc + s] = Lb[e];
+    for (int e = lane; e < U * B; e += 32) Lbar[(s * Tn + t) * (size_t)DM::EL + e] = Lb[e];
     __syncwarp();
   }
-  for (int e = lane; e < NC; e += 32) atomicAdd(la + (size_t)e * Sc + s, acc[e]);
+  bw_flush_acc<C>(lane, gacc + s, Sc, acc, C::NSEG);
+}
+
+// =========================================================================================== Riccati / Kalman sweeps
+// Warp-per-sample versions of LqrFwd / KfFwd / KfRev / LqrRev (lqgk_core.h): b x b matrices in shared memory, the u x u and
+// y x y factorisations (u <= 2, y <= 4) by lane 0 with the scalar templates.  L, K, l, H, Sric, Pkf, Lbar, Kbar: sample-major.
+template <class DM>
+struct BigG {
+  static constexpr int B = DM::B, U = DM::U, Y = DM::Y;
+  static constexpr int LQR_DOUBLES = LqrC<DM>::n_affine + LqrC<DM>::n + 8 * B * B + 10 * B * U + 6 * U * U + 4 * B + 4 * U + 8;
+  static constexpr int KF_DOUBLES = 2 * KfC<DM>::n + 7 * B * B + 9 * B * Y + 4 * Y * Y + 8;
+  static size_t smem_lqr() { return sizeof(double) * LQR_DOUBLES * BW_WARPS; }
+  static size_t smem_kf() { return sizeof(double) * KF_DOUBLES * BW_WARPS; }
+};
+
+// H = R + B^T S B, G = B^T S A (+P), shift, Ht^-1 from S (full symmetric) -- shared by the forward sweep and its adjoint.
+// SA, SB, H, G, Hi: shared-memory outputs; returns the eigen-shift (lqr.py:22-28).  Ends synchronised.
+template <class DM, bool AFFINE>
+__device__ __forceinline__ double bw_lqr_common(int lane, const double* c, double eps, const double* S, double* SA, double* SB, double* H,
+                                                double* G, double* Hi, double* shift_sm) {
+  using C = LqrC<DM>;
+  constexpr int B = DM::B, U = DM::U;
+  wmm<B, B, B>(lane, [&](int i, int k) { return S[i * B + k]; }, [&](int k, int j) { return c[C::Aa + k * B + j]; },
+               [&](int i, int j, double v) { SA[i * B + j] = v; });
+  wmm<B, U, B>(lane, [&](int i, int k) { return S[i * B + k]; }, [&](int k, int j) { return c[C::Ba + k * U + j]; },
+               [&](int i, int j, double v) { SB[i * U + j] = v; });
+  __syncwarp();
+  wmm_sym<U, B>(lane, [&](int i, int j) { return c[C::R + sidx(i, j)]; }, [&](int i, int k) { return c[C::Ba + k * U + i]; },
+                [&](int k, int j) { return SB[k * U + j]; }, H);
+  wmm<U, B, B>(lane, [&](int i, int k) { return c[C::Ba + k * U + i]; }, [&](int k, int j) { return SA[k * B + j]; },
+               [&](int i, int j, double v) { G[i * B + j] = v + (AFFINE ? c[C::P + i * B + j] : 0.0); });
+  __syncwarp();
+  if (lane == 0) {
+    double Hl[U * U], Lc[U * U], Li[U * U], Hv[U * U];
+    for (int i = 0; i < U * U; ++i) Hl[i] = H[i];
+    double shift = eps - lambda_min<U>(Hl);
+    shift = shift > 0.0 ? shift : 0.0;
+    for (int i = 0; i < U * U; ++i) Lc[i] = Hl[i];
+    for (int i = 0; i < U; ++i) Lc[i * U + i] += shift;
+    chol<U>(Lc);
+    tri_inv<U>(Lc, Li);
+    mm_tn<U, U, U>(Li, Li, Hv);
+    for (int i = 0; i < U * U; ++i) Hi[i] = Hv[i];
+    *shift_sm = shift;
+  }
+  __syncwarp();
+  return *shift_sm;
+}
+
+template <class DM, bool AFFINE>
+__global__ void __launch_bounds__(32 * BW_WARPS) kw_lqr_fwd(const double* cst, size_t Sc, int npad, int Tn, double eps, double* L, int save_S,
+                                                            double* Sric, double* l, double* H_out) {
+  using C = LqrC<DM>;
+  constexpr int B = DM::B, U = DM::U;
+  extern __shared__ __align__(16) double smw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t s = (size_t)blockIdx.x * BW_WARPS + warp;
+  if (s >= (size_t)npad) return;
+  double* c = smw + (size_t)warp * BigG<DM>::LQR_DOUBLES;
+  double* S = c + C::n_affine + C::n;
+  double* Sn = S + B * B;
+  double* SA = Sn + B * B;
+  double* SB = SA + 6 * B * B;            // (unused b x b slots belong to the adjoint kernel)
+  double* G = SB + B * U;
+  double* Lm = G + B * U;
+  double* HL = Lm + B * U;
+  double* H = HL + 7 * B * U;
+  double* Hi = H + U * U;
+  double* sv = Hi + 5 * U * U;            // s (B) | sn (B) | 2 B spare
+  double* gv = sv + 4 * B;                // g (U) | l (U) | Hl (U) | spare
+  double* shift_sm = gv + 4 * U;
+  bw_load_consts<C>(lane, cst + s, Sc, c, AFFINE ? C::NSEG_AFF : C::NSEG);
+  __syncwarp();
+  for (int e = lane; e < B * B; e += 32) { const int i = e / B, j = e - i * B; S[e] = c[C::Qf + sidx(i, j)]; }
+  if (AFFINE) { for (int e = lane; e < B; e += 32) sv[e] = c[C::qf + e]; }
+  __syncwarp();
+  for (int t = Tn - 1; t >= 0; --t) {
+    if (save_S) {
+      double* so = Sric + (s * Tn + t) * (size_t)DM::ES;
+      for (int e = lane; e < B * B; e += 32) { const int i = e / B, j = e - i * B; if (j <= i) so[i * (i + 1) / 2 + j] = S[e]; }
+    }
+    const double shift = bw_lqr_common<DM, AFFINE>(lane, c, eps, S, SA, SB, H, G, Hi, shift_sm);
+    if (AFFINE) {
+      for (int e = lane; e < U; e += 32) {
+        double a = c[C::r + e];
+        for (int k = 0; k < B; ++k) a += c[C::Ba + k * U + e] * sv[k];
+        gv[e] = a;
+      }
+    }
+    wmm<U, B, U>(lane, [&](int i, int k) { return Hi[i * U + k]; }, [&](int k, int j) { return G[k * B + j]; },
+                 [&](int i, int j, double v) { Lm[i * B + j] = -v; L[(s * Tn + t) * (size_t)DM::EL + i * B + j] = -v; });
+    __syncwarp();
+    wmm<U, B, U>(lane, [&](int i, int k) { return H[i * U + k]; }, [&](int k, int j) { return Lm[k * B + j]; },
+                 [&](int i, int j, double v) { HL[i * B + j] = v + 2.0 * G[i * B + j]; });
+    if (AFFINE) {
+      for (int e = lane; e < U; e += 32) {
+        double a = 0.0;
+        for (int k = 0; k < U; ++k) a += Hi[e * U + k] * gv[k];
+        gv[U + e] = -a;
+        l[(s * Tn + t) * (size_t)U + e] = -a;
+      }
+      for (int e = lane; e < U * U; e += 32) {
+        const int i = e / U, j = e - i * U;
+        H_out[(s * Tn + t) * (size_t)(U * U) + e] = H[e] + (i == j ? shift : 0.0);
+      }
+    }
+    __syncwarp();
+    // S <- Q + A^T S A + sym(L^T (H L + 2 G))                                    lqr.py:33
+    for (int e = lane; e < B * B; e += 32) {
+      const int i = e / B, j = e - i * B;
+      if (j > i) continue;
+      double a = c[C::Q + sidx(i, j)];
+      for (int k = 0; k < B; ++k) a += c[C::Aa + k * B + i] * SA[k * B + j];
+      double b2 = 0.0;
+      for (int k = 0; k < U; ++k) b2 += Lm[k * B + i] * HL[k * B + j] + Lm[k * B + j] * HL[k * B + i];
+      a += 0.5 * b2;
+      Sn[i * B + j] = a;
+      Sn[j * B + i] = a;
+    }
+    if (AFFINE) {
+      for (int e = lane; e < U; e += 32) {
+        double a = 0.0;
+        for (int k = 0; k < U; ++k) a += H[e * U + k] * gv[U + k];
+        gv[2 * U + e] = a;                                                     // H l
+      }
+      __syncwarp();
+      for (int e = lane; e < B; e += 32) {                                     // lqr.py:34
+        double a = c[C::q + e];
+        for (int k = 0; k < B; ++k) a += c[C::Aa + k * B + e] * sv[k];
+        for (int k = 0; k < U; ++k) a += G[k * B + e] * gv[U + k] + Lm[k * B + e] * (gv[2 * U + k] + gv[k]);
+        sv[B + e] = a;
+      }
+      __syncwarp();
+      for (int e = lane; e < B; e += 32) sv[e] = sv[B + e];
+    }
+    __syncwarp();
+    double* tmp = S; S = Sn; Sn = tmp;
+  }
+}
+
+// Kalman gain from P (full symmetric): Pp, M = F Pp, Gi = Gm^-1, K (KfFwd::gain, kf.py:10-12).  AP: b x b scratch.
+template <class DM>
+__device__ __forceinline__ void bw_kf_gain(int lane, const double* c, const double* P, double* AP, double* Pp, double* M, double* Gm, double* Gi,
+                                           double* K) {
+  using C = KfC<DM>;
+  constexpr int B = DM::B, Y = DM::Y;
+  wmm<B, B, B>(lane, [&](int i, int k) { return c[C::Aa + i * B + k]; }, [&](int k, int j) { return P[k * B + j]; },
+               [&](int i, int j, double v) { AP[i * B + j] = v; });
+  __syncwarp();
+  wmm_sym<B, B>(lane, [&](int i, int j) { return c[C::VVa + sidx(i, j)]; }, [&](int i, int k) { return AP[i * B + k]; },
+                [&](int k, int j) { return c[C::Aa + j * B + k]; }, Pp);
+  __syncwarp();
+  wmm<Y, B, B>(lane, [&](int i, int k) { return c[C::Fa + i * B + k]; }, [&](int k, int j) { return Pp[k * B + j]; },
+               [&](int i, int j, double v) { M[i * B + j] = v; });
+  __syncwarp();
+  wmm_sym<Y, B>(lane, [&](int i, int j) { return c[C::WWa + sidx(i, j)]; }, [&](int i, int k) { return M[i * B + k]; },
+                [&](int k, int j) { return c[C::Fa + j * B + k]; }, Gm);
+  __syncwarp();
+  if (lane == 0) {
+    double Gl[Y * Y], Li[Y * Y], Gv[Y * Y];
+    for (int i = 0; i < Y * Y; ++i) Gl[i] = Gm[i];
+    chol<Y>(Gl);
+    tri_inv<Y>(Gl, Li);
+    mm_tn_sym<Y, Y>(Li, Li, Gv);
+    for (int i = 0; i < Y * Y; ++i) Gi[i] = Gv[i];
+  }
+  __syncwarp();
+  wmm<B, Y, Y>(lane, [&](int i, int k) { return M[k * B + i]; }, [&](int k, int j) { return Gi[k * Y + j]; },
+               [&](int i, int j, double v) { K[i * Y + j] = v; });
+  __syncwarp();
+}
+
+template <class DM>
+__global__ void __launch_bounds__(32 * BW_WARPS) kw_kf_fwd(const double* cst, size_t Sc, int npad, int Tn, double* Kout, int save_P, double* Pkf) {
+  using C = KfC<DM>;
+  constexpr int B = DM::B, Y = DM::Y;
+  extern __shared__ __align__(16) double smw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t s = (size_t)blockIdx.x * BW_WARPS + warp;
+  if (s >= (size_t)npad) return;
+  double* c = smw + (size_t)warp * BigG<DM>::KF_DOUBLES;
+  double* P = c + 2 * C::n;
+  double* Pn = P + B * B;
+  double* AP = Pn + B * B;
+  double* Pp = AP + B * B;
+  double* M = Pp + 4 * B * B;
+  double* K = M + B * Y;
+  double* Gm = K + 8 * B * Y;
+  double* Gi = Gm + Y * Y;
+  bw_load_consts<C>(lane, cst + s, Sc, c, C::NSEG);
+  __syncwarp();
+  for (int e = lane; e < B * B; e += 32) { const int i = e / B, j = e - i * B; P[e] = c[C::Sig0 + sidx(i, j)]; }
+  __syncwarp();
+  for (int t = 0; t < Tn; ++t) {
+    if (save_P) {
+      double* po = Pkf + (s * Tn + t) * (size_t)DM::EP;
+      for (int e = lane; e < B * B; e += 32) { const int i = e / B, j = e - i * B; if (j <= i) po[i * (i + 1) / 2 + j] = P[e]; }
+    }
+    bw_kf_gain<DM>(lane, c, P, AP, Pp, M, Gm, Gi, K);
+    for (int e = lane; e < B * Y; e += 32) Kout[(s * Tn + t) * (size_t)DM::EK + e] = K[e];
+    for (int e = lane; e < B * B; e += 32) {                                   // P <- Pp - K M (symmetric)   kf.py:14
+      const int i = e / B, j = e - i * B;
+      if (j > i) continue;
+      double a = Pp[i * B + j];
+      for (int k = 0; k < Y; ++k) a -= 0.5 * (K[i * Y + k] * M[k * B + j] + K[j * Y + k] * M[k * B + i]);
+      Pn[i * B + j] = a;
+      Pn[j * B + i] = a;
+    }
+    __syncwarp();
+    double* tmp = P; P = Pn; Pn = tmp;
+  }
+}
+
+// Kalman-gain adjoint (KfRev), t descending.  gacc: per-sample cotangent accumulators [element][Sc] (atomicAdd at the end).
+template <class DM>
+__global__ void __launch_bounds__(32 * BW_WARPS) kw_kf_rev(const double* cst, size_t Sc, int npad, int Tn, const double* Pkf, const double* Kbar,
+                                                           double* gacc) {
+  using C = KfC<DM>;
+  constexpr int B = DM::B, Y = DM::Y;
+  extern __shared__ __align__(16) double smw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t s = (size_t)blockIdx.x * BW_WARPS + warp;
+  if (s >= (size_t)npad) return;
+  double* c = smw + (size_t)warp * BigG<DM>::KF_DOUBLES;
+  double* acc = c + C::n;
+  double* P = acc + C::n;
+  double* Pnb = P + B * B;
+  double* AP = Pnb + B * B;
+  double* Pp = AP + B * B;
+  double* Ppb = Pp + B * B;
+  double* PA = Ppb + B * B;
+  double* Pn2 = PA + B * B;
+  double* M = Pn2 + B * B;
+  double* K = M + B * Y;
+  double* Kb = K + B * Y;
+  double* Ktot = Kb + B * Y;
+  double* Yv = Ktot + B * Y;
+  double* Mb = Yv + B * Y;
+  double* GF = Mb + B * Y;
+  double* Gm = GF + 3 * B * Y;
+  double* Gi = Gm + Y * Y;
+  double* Gmb = Gi + Y * Y;
+  bw_load_consts<C>(lane, cst + s, Sc, c, C::NSEG);
+  for (int e = lane; e < C::n; e += 32) acc[e] = 0.0;
+  for (int e = lane; e < B * B; e += 32) Pnb[e] = 0.0;
+  __syncwarp();
+  for (int t = Tn - 1; t >= 0; --t) {
+    const double* po = Pkf + (s * Tn + t) * (size_t)DM::EP;
+    for (int e = lane; e < B * B; e += 32) { const int i = e / B, j = e - i * B; P[e] = po[sidx(i, j)]; }
+    for (int e = lane; e < B * Y; e += 32) Kb[e] = Kbar[(s * Tn + t) * (size_t)DM::EK + e];
+    __syncwarp();
+    bw_kf_gain<DM>(lane, c, P, AP, Pp, M, Gm, Gi, K);
+    // Ktot = Kb - Pnb M^T ; Y = Ktot Gi
+    wmm<B, Y, B>(lane, [&](int i, int j) { return Pnb[i * B + j]; }, [&](int j, int k) { return M[k * B + j]; },
+                 [&](int i, int k, double v) { Ktot[i * Y + k] = Kb[i * Y + k] - v; });
+    __syncwarp();
+    wmm<B, Y, Y>(lane, [&](int i, int k) { return Ktot[i * Y + k]; }, [&](int k, int j) { return Gi[k * Y + j]; },
+                 [&](int i, int j, double v) { Yv[i * Y + j] = v; });
+    __syncwarp();
+    // Mb = Y^T - K^T Pnb (Y x B) ; Gmb = -sym(K^T Y) (Y x Y)
+    wmm<Y, B, B>(lane, [&](int k, int i) { return K[i * Y + k]; }, [&](int i, int j) { return Pnb[i * B + j]; },
+                 [&](int k, int j, double v) { Mb[k * B + j] = Yv[j * Y + k] - v; });
+    for (int e = lane; e < Y * Y; e += 32) {
+      const int k = e / Y, m = e - k * Y;
+      if (m > k) continue;
+      double a = 0.0;
+      for (int i = 0; i < B; ++i) a += K[i * Y + k] * Yv[i * Y + m] + K[i * Y + m] * Yv[i * Y + k];
+      Gmb[k * Y + m] = -0.5 * a;
+      Gmb[m * Y + k] = -0.5 * a;
+      acc[C::WWa + k * (k + 1) / 2 + m] += -0.5 * a;
+    }
+    __syncwarp();
+    // Fa += Mb Pp + 2 Gmb M ; GF = Gmb F
+    for (int e = lane; e < Y * B; e += 32) {
+      const int k = e / B, j = e - k * B;
+      double a = 0.0, g = 0.0;
+      for (int i = 0; i < B; ++i) a += Mb[k * B + i] * Pp[i * B + j];
+      for (int m = 0; m < Y; ++m) { a += 2.0 * Gmb[k * Y + m] * M[m * B + j]; g += Gmb[k * Y + m] * c[C::Fa + m * B + j]; }
+      acc[C::Fa + e] += a;
+      GF[e] = g;
+    }
+    __syncwarp();
+    // Ppb = Pnb + sym(F^T Mb) + F^T Gmb F
+    for (int e = lane; e < B * B; e += 32) {
+      const int i = e / B, j = e - i * B;
+      if (j > i) continue;
+      double a = Pnb[i * B + j];
+      for (int k = 0; k < Y; ++k)
+        a += 0.5 * (c[C::Fa + k * B + i] * Mb[k * B + j] + c[C::Fa + k * B + j] * Mb[k * B + i]) + c[C::Fa + k * B + i] * GF[k * B + j];
+      Ppb[i * B + j] = a;
+      Ppb[j * B + i] = a;
+      acc[C::VVa + i * (i + 1) / 2 + j] += a;
+    }
+    __syncwarp();
+    // Aa += 2 Ppb (A P) ; Pnb <- A^T (Ppb A)        (AP = A P is still valid from bw_kf_gain)
+    wmm<B, B, B>(lane, [&](int i, int k) { return Ppb[i * B + k]; }, [&](int k, int j) { return c[C::Aa + k * B + j]; },
+                 [&](int i, int j, double v) { PA[i * B + j] = v; });
+    wmm<B, B, B>(lane, [&](int i, int k) { return Ppb[i * B + k]; }, [&](int k, int j) { return AP[k * B + j]; },
+                 [&](int i, int j, double v) { acc[C::Aa + i * B + j] += 2.0 * v; });
+    __syncwarp();
+    wmm_sym<B, B>(lane, [&](int, int) { return 0.0; }, [&](int i, int k) { return c[C::Aa + k * B + i]; },
+                  [&](int k, int j) { return PA[k * B + j]; }, Pn2);
+    __syncwarp();
+    double* tmp = Pnb; Pnb = Pn2; Pn2 = tmp;
+  }
+  for (int e = lane; e < B * B; e += 32) { const int i = e / B, j = e - i * B; if (j <= i) acc[C::Sig0 + i * (i + 1) / 2 + j] += Pnb[e]; }
+  __syncwarp();
+  bw_flush_acc<C>(lane, gacc + s, Sc, acc, C::NSEG);
+}
+
+// Riccati adjoint (LqrRev), t ascending; the eigen-shift is a constant of the adjoint (zero whenever R > 0).
+template <class DM>
+__global__ void __launch_bounds__(32 * BW_WARPS) kw_lqr_rev(const double* cst, size_t Sc, int npad, int Tn, double eps, const double* L,
+                                                            const double* Sric, const double* Lbar, double* gacc) {
+  using C = LqrC<DM>;
+  constexpr int B = DM::B, U = DM::U;
+  extern __shared__ __align__(16) double smw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t s = (size_t)blockIdx.x * BW_WARPS + warp;
+  if (s >= (size_t)npad) return;
+  double* c = smw + (size_t)warp * BigG<DM>::LQR_DOUBLES;
+  double* acc = c + C::n_affine;
+  double* S = acc + C::n;
+  double* Sn = S + B * B;
+  double* SA = Sn + B * B;
+  double* AS = SA + B * B;
+  double* BG = AS + B * B;
+  double* Sb = BG + B * B;
+  double* spare = Sb + B * B;             // 2 b x b spare
+  double* SB = spare + 2 * B * B;
+  double* G = SB + B * U;
+  double* Lm = G + B * U;
+  double* Lbr = Lm + B * U;
+  double* LS = Lbr + B * U;
+  double* HLG = LS + B * U;
+  double* Lb = HLG + B * U;
+  double* HiLb = Lb + B * U;
+  double* Gb = HiLb + B * U;
+  double* BH = Gb + B * U;
+  double* H = BH + B * U;
+  double* Hi = H + U * U;
+  double* Hb = Hi + U * U;
+  double* shift_sm = Hb + 4 * U * U + 4 * B + 4 * U;
+  bw_load_consts<C>(lane, cst + s, Sc, c, C::NSEG);
+  for (int e = lane; e < C::n; e += 32) acc[e] = 0.0;
+  for (int e = lane; e < B * B; e += 32) Sn[e] = 0.0;
+  __syncwarp();
+  for (int t = 0; t < Tn; ++t) {
+    const double* so = Sric + (s * Tn + t) * (size_t)DM::ES;
+    for (int e = lane; e < B * B; e += 32) { const int i = e / B, j = e - i * B; S[e] = so[sidx(i, j)]; }
+    for (int e = lane; e < U * B; e += 32) { Lm[e] = L[(s * Tn + t) * (size_t)DM::EL + e]; Lbr[e] = Lbar[(s * Tn + t) * (size_t)DM::EL + e]; }
+    __syncwarp();
+    bw_lqr_common<DM, false>(lane, c, eps, S, SA, SB, H, G, Hi, shift_sm);
+    // Q += Sn ; Aa += 2 SA Sn ; LS = L Sn ; HLG = H L + G
+    for (int e = lane; e < B * B; e += 32) { const int i = e / B, j = e - i * B; if (j <= i) acc[C::Q + i * (i + 1) / 2 + j] += Sn[e]; }
+    wmm<B, B, B>(lane, [&](int i, int k) { return SA[i * B + k]; }, [&](int k, int j) { return Sn[k * B + j]; },
+                 [&](int i, int j, double v) { acc[C::Aa + i * B + j] += 2.0 * v; });
+    wmm<U, B, B>(lane, [&](int i, int k) { return Lm[i * B + k]; }, [&](int k, int j) { return Sn[k * B + j]; },
+                 [&](int i, int j, double v) { LS[i * B + j] = v; });
+    wmm<U, B, U>(lane, [&](int i, int k) { return H[i * U + k]; }, [&](int k, int j) { return Lm[k * B + j]; },
+                 [&](int i, int j, double v) { HLG[i * B + j] = v + G[i * B + j]; });
+    __syncwarp();
+    // Lb = Lbar + 2 HLG Sn ; Hb = LS L^T
+    wmm<U, B, B>(lane, [&](int i, int k) { return HLG[i * B + k]; }, [&](int k, int j) { return Sn[k * B + j]; },
+                 [&](int i, int j, double v) { Lb[i * B + j] = Lbr[i * B + j] + 2.0 * v; });
+    __syncwarp();
+    // HiLb = Ht^-1 Lb ; Gb = 2 LS - HiLb
+    wmm<U, B, U>(lane, [&](int i, int k) { return Hi[i * U + k]; }, [&](int k, int j) { return Lb[k * B + j]; },
+                 [&](int i, int j, double v) { HiLb[i * B + j] = v; Gb[i * B + j] = 2.0 * LS[i * B + j] - v; });
+    __syncwarp();
+    // Hb = sym(LS L^T - HiLb L^T) ; R += Hb
+    for (int e = lane; e < U * U; e += 32) {
+      const int i = e / U, j = e - i * U;
+      if (j > i) continue;
+      double a = 0.0, b2 = 0.0;
+      for (int k = 0; k < B; ++k) {
+        a += (LS[i * B + k] - HiLb[i * B + k]) * Lm[j * B + k];
+        b2 += (LS[j * B + k] - HiLb[j * B + k]) * Lm[i * B + k];
+      }
+      const double v = 0.5 * (a + b2);
+      Hb[i * U + j] = v;
+      Hb[j * U + i] = v;
+      acc[C::R + i * (i + 1) / 2 + j] += v;
+    }
+    __syncwarp();
+    // Ba += 2 SB Hb + SA Gb^T ; Aa += SB Gb ; AS = A Sn ; BH = B Hb ; BG = B Gb
+    for (int e = lane; e < B * U; e += 32) {
+      const int i = e / U, m = e - i * U;
+      double a = 0.0, h = 0.0;
+      for (int k = 0; k < U; ++k) { a += 2.0 * SB[i * U + k] * Hb[k * U + m]; h += c[C::Ba + i * U + k] * Hb[k * U + m]; }
+      for (int k = 0; k < B; ++k) a += SA[i * B + k] * Gb[m * B + k];
+      acc[C::Ba + e] += a;
+      BH[e] = h;
+    }
+    __syncwarp();                                                            // acc.Aa: the 2 SA Sn pass above is complete
+    wmm<B, B, U>(lane, [&](int i, int k) { return SB[i * U + k]; }, [&](int k, int j) { return Gb[k * B + j]; },
+                 [&](int i, int j, double v) { acc[C::Aa + i * B + j] += v; });
+    wmm<B, B, B>(lane, [&](int i, int k) { return c[C::Aa + i * B + k]; }, [&](int k, int j) { return Sn[k * B + j]; },
+                 [&](int i, int j, double v) { AS[i * B + j] = v; });
+    wmm<B, B, U>(lane, [&](int i, int k) { return c[C::Ba + i * U + k]; }, [&](int k, int j) { return Gb[k * B + j]; },
+                 [&](int i, int j, double v) { BG[i * B + j] = v; });
+    __syncwarp();
+    // Sn <- A Sn A^T + B Hb B^T + sym(B Gb A^T)
+    for (int e = lane; e < B * B; e += 32) {
+      const int i = e / B, j = e - i * B;
+      if (j > i) continue;
+      double a = 0.0, b2 = 0.0;
+      for (int k = 0; k < B; ++k) {
+        a += AS[i * B + k] * c[C::Aa + j * B + k];
+        b2 += BG[i * B + k] * c[C::Aa + j * B + k] + BG[j * B + k] * c[C::Aa + i * B + k];
+      }
+      for (int k = 0; k < U; ++k) a += BH[i * U + k] * c[C::Ba + j * U + k];
+      a += 0.5 * b2;
+      Sb[i * B + j] = a;
+      Sb[j * B + i] = a;
+    }
+    __syncwarp();
+    double* tmp = Sn; Sn = Sb; Sb = tmp;
+  }
+  for (int e = lane; e < B * B; e += 32) { const int i = e / B, j = e - i * B; if (j <= i) acc[C::Qf + i * (i + 1) / 2 + j] += Sn[e]; }
+  __syncwarp();
+  bw_flush_acc<C>(lane, gacc + s, Sc, acc, C::NSEG);
 }
 
 }  // namespace lqgk

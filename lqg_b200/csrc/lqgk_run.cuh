@@ -112,9 +112,6 @@ inline bool spec_time_varying(const LqgkSpec& s, bool actor) {
 // Large systems (joint dim > 12) take the local-memory path of lqgk_big.cuh (compiled with -DLQGK_BIG).
 template <class DM>
 constexpr bool is_big() { return DM::N > 12; }
-template <class DM>
-constexpr int big_scratch_rows();
-
 // Workspace plan for one chunk of Sc (multiple of 32) samples.
 struct Plan {
   size_t Sc = 0, bytes = 0;
@@ -159,7 +156,6 @@ Plan make_plan(const LqgkDims& d, int mode, bool tv, size_t Sc) {
     p.SGBI = take(sizeof(double) * SR::NSGB * Sc);
     p.SFW = take(sizeof(double) * T * SR::NSF * Sc);
   }
-  if constexpr (is_big<DM>()) p.scr = take(sizeof(double) * 2 * big_scratch_rows<DM>() * Sc);
   p.bytes = off;
   return p;
 }
