@@ -613,6 +613,19 @@ struct RecRing {
   }
 };
 
+// Trial -> lane assignment of one pass (32*RT trials starting at `base`): pair p of a lane holds the ADJACENT trials
+// base + 64p + 2*lane and +1, so one 64-bit access moves the pair's entry of the state history, already in f32x2 register
+// order (no packing moves, half the memory instructions); an odd RT adds the single trial base + 64*(RT/2) + lane.
+// Flat slot j: 2p, 2p+1 = the two halves of pair p; RT-1 = the single.
+template <int RT>
+__device__ __forceinline__ int trial_of(int base, int lane, int j) {
+  constexpr int NP = RT / 2;
+  return j < 2 * NP ? base + 64 * (j >> 1) + 2 * lane + (j & 1) : base + 64 * NP + lane;
+}
+// Row stride of the state history [s][t][R][hist_stride(N)]: even, so a pair's entry is 8-byte aligned.  The forward
+// kernel stores 0 into the pad element of an odd N; the adjoint reads pairs whenever the first half is a real trial.
+__host__ __device__ __forceinline__ constexpr int hist_stride(int N) { return (N + 1) & ~1; }
+
 // Largest number of trials one lane carries: small systems leave room for 8 (amortises the broadcast record loads and
 // the cross-lane reductions over more FMAs), large ones for 4.
 template <class DM>
@@ -656,15 +669,24 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_fwd(const float* __r
                    rec + (size_t)s * Tn * DM::REC, Tn, (Tn + trial_tb<DM>() - 1) / trial_tb<DM>(), lane, 0};
   ring.init();
   const int nchunk = ring.nchunk;
+  const int Nh = hist_stride(N);
   for (int base = 0; base < N; base += 32 * RT) {
     int tr[RT], trD[RT];
     bool ok[RT];
     LQGK_UNROLL for (int j = 0; j < RT; ++j) {
-      int i = base + lane + 32 * j;
+      int i = trial_of<RT>(base, lane, j);
       ok[j] = i < N;
       tr[j] = ok[j] ? i : N - 1;
       trD[j] = tr[j] * D;            // 32-bit element offsets: one 64-bit row pointer per step + cheap lane offsets
     }
+    // state-history row pointers of this lane (one per state component), advanced by one step per iteration
+    // (small systems: one pointer per component -> every access is pointer + immediate; large ones: one pointer + m * Nh)
+    constexpr bool HPTRS = R <= 6;
+    constexpr int NHP = HPTRS ? R : 1;
+    float* hw[NHP];
+    LQGK_UNROLL for (int m = 0; m < NHP; ++m) hw[m] = hist + ((size_t)s * Tn * R + m) * Nh + (base + 2 * lane);
+    auto hrow = [&](int m) -> float* { if constexpr (HPTRS) return hw[m]; else return hw[0] + m * Nh; };
+    const int hstep = R * Nh, hsingle = 64 * (RT / 2) - lane;
     // trials 2p, 2p+1 are packed into one f32x2 lane-pair state (Blackwell FFMA2); an odd last trial stays scalar
     constexpr int NP = RT / 2, NS = RT % 2;
     f32x2 cP[NP > 0 ? NP : 1][R], x0P[NP > 0 ? NP : 1][D];
@@ -719,14 +741,18 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_fwd(const float* __r
           if constexpr (NS) read_obs<D>(cur + (RT - 1) * 32 * D, lane, x1S);
         }
         if (hist != nullptr) {
-          float* hrow = hist + ((size_t)s * Tn + t) * R * N;
           LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) {
-            if (ok[2 * p2]) { LQGK_UNROLL for (int m = 0; m < R; ++m) hrow[m * N + tr[2 * p2]] = cP[p2][m].x; }
-            if (ok[2 * p2 + 1]) { LQGK_UNROLL for (int m = 0; m < R; ++m) hrow[m * N + tr[2 * p2 + 1]] = cP[p2][m].y; }
+            if (ok[2 * p2 + 1]) {   // pair entry in one 64-bit store, straight from the f32x2 register pair
+              LQGK_UNROLL for (int m = 0; m < R; ++m)
+                *reinterpret_cast<float2*>(hrow(m) + 64 * p2) = make_float2(cP[p2][m].x, cP[p2][m].y);
+            } else if (ok[2 * p2]) {   // odd N: the pad element gets 0
+              LQGK_UNROLL for (int m = 0; m < R; ++m) *reinterpret_cast<float2*>(hrow(m) + 64 * p2) = make_float2(cP[p2][m].x, 0.f);
+            }
           }
           if constexpr (NS) {
-            if (ok[RT - 1]) { LQGK_UNROLL for (int m = 0; m < R; ++m) hrow[m * N + tr[RT - 1]] = cS[m]; }
+            if (ok[RT - 1]) { LQGK_UNROLL for (int m = 0; m < R; ++m) hrow(m)[hsingle] = cS[m]; }
           }
+          LQGK_UNROLL for (int m = 0; m < NHP; ++m) hw[m] += hstep;
         }
         auto run = [&](const auto& rr) {
           LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2)
@@ -798,28 +824,45 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __r
                    rec + (size_t)s * Tn * DM::REC, Tn, (Tn + trial_tb<DM>() - 1) / trial_tb<DM>(), lane, 0};
   ring.init();
   const int nchunk = ring.nchunk;
+  const int Nh = hist_stride(N);
   for (int base = 0; base < N; base += 32 * RT) {
-    int tr[RT], trD[RT];
-    float wt[RT];
-    LQGK_UNROLL for (int j = 0; j < RT; ++j) {
-      int i = base + lane + 32 * j;
-      bool ok = i < N;
-      tr[j] = ok ? i : N - 1;
-      trD[j] = tr[j] * D;
-      wt[j] = ok ? w[(size_t)s * N + tr[j]] : 0.f;   // masked trials contribute nothing (cb stays 0, w = 0)
-    }
     constexpr int NP = RT / 2, NS = RT % 2, NPA = NP > 0 ? NP : 1;
+    int trD[RT];
+    float wt[RT];
+    bool okP[NPA], okS = false;
+    LQGK_UNROLL for (int j = 0; j < RT; ++j) {
+      int i = trial_of<RT>(base, lane, j);
+      bool ok = i < N;
+      int tr = ok ? i : N - 1;
+      trD[j] = tr * D;
+      wt[j] = ok ? w[(size_t)s * N + tr] : 0.f;   // masked trials contribute nothing (c = 0, cb stays 0, w = 0)
+      if (j < 2 * NP) { if ((j & 1) == 0) okP[j >> 1] = ok; } else okS = ok;
+    }
+    // state-history row pointers of this lane (one per state component), walked backwards one step per iteration
+    constexpr bool HPTRS = R <= 6;
+    constexpr int NHP = HPTRS ? R : 1;
+    const float* hr[NHP];
+    LQGK_UNROLL for (int m = 0; m < NHP; ++m) hr[m] = hist + (((size_t)s * Tn + (Tn - 1)) * R + m) * Nh + (base + 2 * lane);
+    auto hrow = [&](int m) -> const float* { if constexpr (HPTRS) return hr[m]; else return hr[0] + m * Nh; };
+    const int hstep = R * Nh, hsingle = 64 * NP - lane;
+    auto load_hist = [&](f32x2 (&cp)[NPA][R], float (&cs)[R]) {
+      LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) LQGK_UNROLL for (int m = 0; m < R; ++m) {
+        float2 v = okP[p2] ? __ldg(reinterpret_cast<const float2*>(hrow(m) + 64 * p2)) : make_float2(0.f, 0.f);
+        cp[p2][m] = f32x2{v.x, v.y};
+      }
+      if constexpr (NS) { LQGK_UNROLL for (int m = 0; m < R; ++m) cs[m] = okS ? __ldg(hrow(m) + hsingle) : 0.f; }
+    };
     // persistent state: cotangent cb, x_{t+1}; prefetched (x_t, c_t) of the next step to process
     f32x2 cbP[NPA][R], x1P[NPA][D], wP[NPA];
     float cbS[R], x1S[D], wS = wt[RT - 1];
-    float x0n[RT][D], cn_[RT][R];          // "next" = values for the step about to be processed
-    LQGK_UNROLL for (int j = 0; j < RT; ++j) {
-      load_obs<D>(x_tm + ((size_t)(Tn - 1) * N + tr[j]) * D, x0n[j]);
-      LQGK_UNROLL for (int m = 0; m < R; ++m) cn_[j][m] = __ldg(&hist[(((size_t)s * Tn + (Tn - 1)) * R + m) * N + tr[j]]);
-    }
+    float x0n[RT][D];                      // "next" = values for the step about to be processed
+    f32x2 cnP[NPA][R];
+    float cnS[R];
+    LQGK_UNROLL for (int j = 0; j < RT; ++j) load_obs<D>(x_tm + (size_t)(Tn - 1) * N * D + trD[j], x0n[j]);
+    load_hist(cnP, cnS);
     {
       float x1[RT][D];
-      LQGK_UNROLL for (int j = 0; j < RT; ++j) load_obs<D>(x_tm + ((size_t)Tn * N + tr[j]) * D, x1[j]);
+      LQGK_UNROLL for (int j = 0; j < RT; ++j) load_obs<D>(x_tm + (size_t)Tn * N * D + trD[j], x1[j]);
       LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) {
         LQGK_UNROLL for (int k = 0; k < R; ++k) cbP[p2][k] = f32x2{0.f, 0.f};
         LQGK_UNROLL for (int m = 0; m < D; ++m) x1P[p2][m] = f32x2{x1[2 * p2][m], x1[2 * p2 + 1][m]};
@@ -828,6 +871,7 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __r
       LQGK_UNROLL for (int k = 0; k < R; ++k) cbS[k] = 0.f;
       LQGK_UNROLL for (int m = 0; m < D; ++m) x1S[m] = x1[RT - 1][m];
     }
+    float* out = sums + ((size_t)s * Tn + (Tn - 1)) * DM::SUMP;
     for (int k = 0; k < TRIAL_NST && k < nchunk; ++k) ring.issue(nchunk - 1 - k, k);
     for (int kk = 0; kk < nchunk; ++kk) {
       const int k = nchunk - 1 - kk;
@@ -838,23 +882,20 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __r
       for (int q = nst - 1; q >= 0; --q) {
         const int t = t0 + q;
         const float* r = chunk + q * DM::REC;
-        // pack this step's (x_t, c_t), then start loading the previous step's
+        // this step's (x_t, c_t) were prefetched; start loading the previous step's
         f32x2 x0P[NPA][D], cP[NPA][R];
         float x0S[D], cS[R];
         LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) {
           LQGK_UNROLL for (int m = 0; m < D; ++m) x0P[p2][m] = f32x2{x0n[2 * p2][m], x0n[2 * p2 + 1][m]};
-          LQGK_UNROLL for (int m = 0; m < R; ++m) cP[p2][m] = f32x2{cn_[2 * p2][m], cn_[2 * p2 + 1][m]};
+          LQGK_UNROLL for (int m = 0; m < R; ++m) cP[p2][m] = cnP[p2][m];
         }
         LQGK_UNROLL for (int m = 0; m < D; ++m) x0S[m] = x0n[RT - 1][m];
-        LQGK_UNROLL for (int m = 0; m < R; ++m) cS[m] = cn_[RT - 1][m];
-        {
-          const int tp = max(t - 1, 0);
-          const float* hrow = hist + ((size_t)s * Tn + tp) * R * N;
-          const float* xrow = x_tm + (size_t)tp * N * D;
-          LQGK_UNROLL for (int j = 0; j < RT; ++j) {
-            load_obs<D>(xrow + trD[j], x0n[j]);
-            LQGK_UNROLL for (int m = 0; m < R; ++m) cn_[j][m] = __ldg(hrow + (m * N + tr[j]));
-          }
+        LQGK_UNROLL for (int m = 0; m < R; ++m) cS[m] = cnS[m];
+        if (t > 0) {
+          LQGK_UNROLL for (int m = 0; m < NHP; ++m) hr[m] -= hstep;
+          const float* xrow = x_tm + (size_t)(t - 1) * N * D;
+          LQGK_UNROLL for (int j = 0; j < RT; ++j) load_obs<D>(xrow + trD[j], x0n[j]);
+          load_hist(cnP, cnS);
         }
         f32x2 eP[NPA][D], vP[NPA][D], wvP[NPA][D], nebP[NPA][D], cbnP[NPA][R];
         float eS[D], vS[D], wvS[D], nebS[D], cbnS[R];
@@ -870,7 +911,6 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __r
         } else {
           run(r);
         }
-        float* out = sums + ((size_t)s * Tn + t) * DM::SUMP;
         auto term = [&](auto IDXC) -> float {
           constexpr int IDX = decltype(IDXC)::value;
           float a = 0.f;
@@ -912,6 +952,7 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __r
           LQGK_UNROLL for (int m = 0; m < R; ++m) cbS[m] = cbnS[m];
           LQGK_UNROLL for (int m = 0; m < D; ++m) x1S[m] = x0S[m];
         }
+        out -= DM::SUMP;
       }
       __syncwarp();
       if (kk + TRIAL_NST < nchunk) ring.issue(nchunk - 1 - (kk + TRIAL_NST), st);

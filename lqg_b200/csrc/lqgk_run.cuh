@@ -146,7 +146,7 @@ Plan make_plan(const LqgkDims& d, int mode, bool tv, size_t Sc) {
     p.Kbar = take(sizeof(double) * T * DM::EK * Sc);
     p.KbarF = take(sizeof(double) * T * DM::EK * Sc);
     p.sums = take(sizeof(float) * Sc * T * DM::SUMP);
-    p.hist = take(sizeof(float) * Sc * T * DM::R * N);
+    p.hist = take(sizeof(float) * Sc * T * DM::R * hist_stride((int)N));
     p.w = take(sizeof(float) * Sc * N);
     using SR = CovSeqRev<DM>;
     p.FU = take(sizeof(double) * T * SR::NSF * Sc);
