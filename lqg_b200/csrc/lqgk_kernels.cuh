@@ -552,6 +552,11 @@ __device__ __forceinline__ void load_obs(const float* __restrict__ p, float* out
   }
 }
 
+// Resident CTAs per SM the forward per-trial kernel is compiled for: the small systems are latency-bound at 2 CTAs (8 warps)
+// per SM, so the register budget is capped at 65536 / (3 * 128) = 170 to fit 3 (no spills: 204 -> 164 registers, -5 % time).
+// The adjoint kernel needs 240 registers; capped at 170 it spills and runs 1.6x slower (measured), so it stays at 2 CTAs.
+template <class DM>
+__host__ __device__ constexpr int trial_min_ctas() { return DM::N <= 6 ? 3 : 1; }
 constexpr int TRIAL_WARPS = 4;   // warps (= samples) per CTA
 // time steps per ring stage: 8 for the small records, fewer when one record is KBs (large systems)
 template <class DM>
@@ -559,12 +564,17 @@ __host__ __device__ constexpr int trial_tb() { return DM::REC <= 128 ? 8 : (DM::
 constexpr int TRIAL_NST = 3;     // ring stages
 
 constexpr int TRIAL_PF = 4;      // observation / state prefetch distance in time steps (cp.async groups in flight)
+// Sums over trials in the adjoint: every lane holds 32 partial values; they are transposed through shared memory (lane L
+// writes its 32 values as 8 x 128-bit stores into row L of a [32][36] tile -- conflict-free per quarter warp --, then sums
+// column L: 32 conflict-free loads) instead of a 31-shuffle butterfly with 62 selects.
+constexpr int TRIAL_RED_STRIDE = 36;
 // Per-lane prefetch slots: [TRIAL_PF + 1][RT][W floats][32 lanes] per warp.
 template <class DM, int RT, bool REV>
 constexpr size_t trial_smem_bytes() {
   size_t ring = (size_t)TRIAL_WARPS * TRIAL_NST * trial_tb<DM>() * DM::REC * sizeof(float) + TRIAL_WARPS * TRIAL_NST * sizeof(uint64_t);
   size_t pf = REV ? 0 : (size_t)TRIAL_WARPS * (TRIAL_PF + 1) * RT * 32 * DM::D * sizeof(float);   // forward only
-  return ring + pf;
+  size_t red = REV && DM::NSUM >= 32 ? (size_t)TRIAL_WARPS * 32 * TRIAL_RED_STRIDE * sizeof(float) : 0;   // adjoint: sum transposition
+  return ring + pf + red;
 }
 // observation x[t][trial][0..D) -> this lane's slot (vector copy of D floats, D*4 in {4, 8, 16} bytes, else scalars)
 template <int D>
@@ -652,7 +662,7 @@ __host__ __device__ constexpr bool rec_in_regs() { return DM::REC <= 48; }
 // TRIAL_PF steps ahead with per-lane cp.async copies into shared-memory slots (no registers held, no stalls on the
 // L2 round trip).
 template <class DM, int RT>
-__global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_fwd(const float* __restrict__ rec, const float* __restrict__ x_all,
+__global__ void __launch_bounds__(32 * TRIAL_WARPS, trial_min_ctas<DM>()) k_trial_fwd(const float* __restrict__ rec, const float* __restrict__ x_all,
                                                                 size_t x_sample_stride, int s_first, int n_samples, int N, int Tn,
                                                                 double* __restrict__ ll_ws, float* __restrict__ hist) {
   constexpr int D = DM::D, R = DM::R, NSLOT = TRIAL_PF + 1;
@@ -820,6 +830,7 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __r
   const float* __restrict__ x_tm = x_all + (size_t)(s_first + s) * x_sample_stride;   // this sample's observations
   float* ring_base = reinterpret_cast<float*>(smraw);
   uint64_t* bar_base = reinterpret_cast<uint64_t*>(smraw + (size_t)TRIAL_WARPS * TRIAL_NST * trial_tb<DM>() * DM::REC * sizeof(float));
+  float* red = reinterpret_cast<float*>(bar_base + TRIAL_WARPS * TRIAL_NST) + (size_t)warp * 32 * TRIAL_RED_STRIDE;   // 16-byte aligned
   RecRing<DM> ring{ring_base + (size_t)warp * TRIAL_NST * trial_tb<DM>() * DM::REC, bar_base + warp * TRIAL_NST,
                    rec + (size_t)s * Tn * DM::REC, Tn, (Tn + trial_tb<DM>() - 1) / trial_tb<DM>(), lane, 0};
   ring.init();
@@ -928,7 +939,13 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __r
           static_for<0, 32>([&](auto J) {
             val[decltype(J)::value] = term(std::integral_constant<int, decltype(G)::value * 32 + decltype(J)::value>{});
           });
-          float tot = warp_transpose_reduce<32>(val, lane);
+          float4* dst = reinterpret_cast<float4*>(red + lane * TRIAL_RED_STRIDE);
+          LQGK_UNROLL for (int q4 = 0; q4 < 8; ++q4) dst[q4] = make_float4(val[4 * q4], val[4 * q4 + 1], val[4 * q4 + 2], val[4 * q4 + 3]);
+          __syncwarp();
+          float part[4] = {0.f, 0.f, 0.f, 0.f};
+          LQGK_UNROLL for (int k2 = 0; k2 < 32; ++k2) part[k2 & 3] += red[k2 * TRIAL_RED_STRIDE + lane];
+          const float tot = (part[0] + part[1]) + (part[2] + part[3]);
+          __syncwarp();
           const int idx = decltype(G)::value * 32 + lane;
           if (base == 0) out[idx] = tot;
           else out[idx] += tot;
