@@ -71,10 +71,19 @@ CASES = {
     # BASELINE config c4: TemporalDelayModel(PointMassBoundedActor(T=600), delay=2) -- 12-dim state, joint dim 24
     "ref_c4_pmdelay2_T600": ("PointMassBoundedActor", dict(T=600), dict(action_variability=1e-3, sigma_target=6.0, sigma_cursor=6.0,
                                                                           action_cost=0.01), 2, 2, 4, 13),
+    # BASELINE config c2r: the REAL tracking data of the reference repository (data/data.mat, Bonnen et al. 2015) through
+    # the reference's own loader lqg/io.py:45-98 (delay=12, clip=120), narrowest-blob condition: 20 trials x 1068 samples x (target,
+    # cursor); BoundedActor dim=1 at sigma_target 8.5 (the notebook's posterior mean for that condition)
+    "ref_c2r_bounded_realdata_T1067": ("BoundedActor", dict(T=1067), dict(action_variability=0.5, sigma_target=8.5, sigma_cursor=6.0,
+                                                                          action_cost=1.0), 0, None, 20, "realdata:0"),
 }
 
 ACTOR_KEYS = ("A", "B", "F", "V", "W", "Q", "R")
 DYN_KEYS = ("A", "B", "F", "V", "W")
+
+
+def T_of(fixed):
+    return int(fixed["T"])
 
 
 def main(argv):
@@ -94,7 +103,16 @@ def main(argv):
             continue
         t0 = time.time()
         m = build(cls, fixed, params, delay)
-        X = np.asarray(m.simulate(random.PRNGKey(seed), n=N))
+        if isinstance(seed, str) and seed.startswith("realdata:"):
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("lqg_io", os.path.join(REF, "lqg", "io.py"))
+            io = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(io)
+            data, sigmas = io.load_tracking_data(delay=12, clip=120, data_path=os.path.join(REF, "data"))
+            X = np.asarray(data[int(seed.split(":")[1])][:N], dtype=np.float64)
+            assert X.shape == (N, T_of(fixed) + 1, 2), X.shape
+        else:
+            X = np.asarray(m.simulate(random.PRNGKey(seed), n=N))
         if obs is not None:
             X = X[..., :obs]
         X = X.astype(np.float32)

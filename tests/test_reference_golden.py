@@ -70,7 +70,7 @@ def fx(request):
 
 
 def test_fixtures_present():
-    assert len(FIXTURES) >= 9
+    assert len(FIXTURES) >= 11
 
 
 def test_oracle_constructors_build_the_reference_matrices(fx):
