@@ -106,6 +106,26 @@ int lqgk_loglik_vjp_f64(const LqgkDims* dims, const LqgkSpec* actor, const LqgkS
                         const LqgkSpecGrad* actor_grad, const LqgkSpecGrad* dynamics_grad,
                         const LqgkMatGrad* sigma0_grad, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- signal-dependent noise (extension; NOT in the reference, see DESIGN.md and oracle/sdn_np.py) -------------
+ * lqgk_sdn_gains_f64: Todorov (2005) alternating iterations for the control gains L and estimator gains K of
+ *     x' = A x + B u + xi + sum_i eps_i C_i u,   y = H x + om + sum_i eta_i D_i x,
+ *     xhat' = A xhat + B u + K (y - H xhat),     u = -L xhat,     cost = sum x'Qx + u'Ru + x_T' Qf x_T
+ *   in ONE kernel (`sweeps` backward/forward sweeps starting from K = 0, then a final backward sweep).  With nc = nd = 0 a
+ *   single sweep reproduces lqr.backward (lqg/control/lqr.py:16-42; L has the opposite sign: u = -L xhat) and the
+ *   predictor-form Kalman gains.  All matrices FP64, time-invariant, row-major with a leading sample axis
+ *   (sample_stride 0 = shared; time_stride ignored): A[b][b], B[b][u], H[y][b], C[nc][b][u], D[nd][y][b], Q[b][b],
+ *   R[u][u], Qf[b][b] (absent -> Q), Om_xi[b][b], Om_omega[y][y] (noise covariances), Sigma1[b][b], xhat1[b].
+ *   Outputs L[S][T][u][b], K[S][T][b][y], cost[S] (expected total cost; may be NULL).  (b, u, y) must be the belief / control
+ *   / observation dims of a compiled small-system tuple.                                                                  */
+typedef struct {
+  int32_t S, T, b, u, y, nc, nd, sweeps;
+} LqgkSdnDims;
+typedef struct {
+  LqgkMat A, B, H, C, D, Q, R, Qf, Om_xi, Om_omega, Sigma1, xhat1;
+} LqgkSdnSpec;
+int lqgk_sdn_gains_f64(const LqgkSdnDims* dims, const LqgkSdnSpec* spec, double* L_out, double* K_out, double* cost_out,
+                       void* stream);
+
 /* ---- helpers ------------------------------------------------------------------------------------------ */
 /* x[N][T+1][d] (f32 or f64, trial-major as in the reference) -> x_tm[T+1][N][d] float. */
 int lqgk_pack_obs_f32(int32_t N, int32_t T1, int32_t d, const float* x, float* x_tm, void* stream);

@@ -74,6 +74,14 @@ def _mat(t: Optional[torch.Tensor], S: int, T: int, trailing: int = 2) -> LqgkMa
     return LqgkMat(t.data_ptr(), ss, ts)
 
 
+class LqgkSdnDims(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("S", "T", "b", "u", "y", "nc", "nd", "sweeps")]
+
+
+class LqgkSdnSpec(C.Structure):
+    _fields_ = [(k, LqgkMat) for k in ("A", "B", "H", "C", "D", "Q", "R", "Qf", "Om_xi", "Om_omega", "Sigma1", "xhat1")]
+
+
 class Library:
     """One loaded implementation of the C ABI."""
 
@@ -232,6 +240,42 @@ class Library:
 
     PROFILE_KINDS = ("pack", "lqr_fwd", "kf_fwd", "cov_fwd", "trial_fwd", "misc", "trial_rev", "cov_rev", "kf_rev",
                      "lqr_rev", "unpack", "cov_contrib", "reduce")
+
+    def sdn_gains(self, mats: Dict[str, torch.Tensor], T: int, sweeps: int = 10, stream=0):
+        """Signal-dependent-noise gains (extension, include/lqgk.h).  mats: float64 CUDA tensors A[S?,b,b], B[S?,b,u],
+        H[S?,y,b], C[S?,nc,b,u], D[S?,nd,y,b], Q, R, (Qf), Om_xi, Om_omega, Sigma1, xhat1[S?,b]; a leading sample axis is
+        optional per tensor (absent / size 1 = shared).  Returns L[S,T,u,b], K[S,T,b,y], cost[S]."""
+        A, Bm, H = mats["A"], mats["B"], mats["H"]
+        b, u, y = A.shape[-1], Bm.shape[-1], H.shape[-2]
+        base_nd = dict(A=2, B=2, H=2, C=3, D=3, Q=2, R=2, Qf=2, Om_xi=2, Om_omega=2, Sigma1=2, xhat1=1)
+        S = 1
+        for k, v in mats.items():
+            if v is not None and v.dim() == base_nd[k] + 1:
+                S = max(S, v.shape[0])
+        sp = LqgkSdnSpec()
+        keep = []
+        for k in base_nd:
+            v = mats.get(k)
+            if v is None or v.numel() == 0:
+                setattr(sp, k, LqgkMat(None, 0, 0))
+                continue
+            assert v.dtype == torch.float64 and v.is_cuda, k
+            v = v.contiguous()
+            keep.append(v)
+            lead = v.dim() - base_nd[k]
+            ss = v.stride(0) if lead == 1 and v.shape[0] == S and S > 1 else 0
+            setattr(sp, k, LqgkMat(v.data_ptr(), ss, 0))
+        nc = 0 if mats.get("C") is None else mats["C"].shape[-3]
+        nd = 0 if mats.get("D") is None else mats["D"].shape[-3]
+        dims = LqgkSdnDims(S, T, b, u, y, nc, nd, sweeps)
+        dev = A.device
+        L = torch.empty((S, T, u, b), dtype=torch.float64, device=dev)
+        K = torch.empty((S, T, b, y), dtype=torch.float64, device=dev)
+        cost = torch.empty((S,), dtype=torch.float64, device=dev)
+        rc = self.lib.lqgk_sdn_gains_f64(C.byref(dims), C.byref(sp), C.c_void_p(L.data_ptr()), C.c_void_p(K.data_ptr()),
+                                         C.c_void_p(cost.data_ptr()), C.c_void_p(stream))
+        self._check(rc, "lqgk_sdn_gains_f64")
+        return L, K, cost
 
     def set_streams(self, n: int):
         self._check(self.lib.lqgk_set_streams(C.c_int(n)), "lqgk_set_streams")

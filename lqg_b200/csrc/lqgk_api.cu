@@ -84,6 +84,38 @@ __global__ void k_peak_fma(int iters, T* sink) {
 }
 extern "C" {
 
+int lqgk_sdn_gains_f64(const LqgkSdnDims* d, const LqgkSdnSpec* sp, double* L_out, double* K_out, double* cost_out, void* stream) {
+  g_launches = 0;
+  if (!d || !sp || !L_out || !K_out) return LQGK_E_INVALID;
+  if (d->S <= 0 || d->T <= 0 || d->b <= 0 || d->u <= 0 || d->y <= 0 || d->nc < 0 || d->nd < 0 || d->sweeps < 0) return LQGK_E_INVALID;
+  const LqgkMat* need[] = {&sp->A, &sp->B, &sp->H, &sp->Q, &sp->R, &sp->Om_xi, &sp->Om_omega, &sp->Sigma1};
+  for (auto m : need)
+    if (!m->ptr) return LQGK_E_INVALID;
+  if ((d->nc > 0 && !sp->C.ptr) || (d->nd > 0 && !sp->D.ptr)) return LQGK_E_INVALID;
+  SdnArgs a{};
+  auto P = [](const LqgkMat& m) { return (const double*)m.ptr; };
+  a.A = P(sp->A); a.sA = sp->A.sample_stride;
+  a.B = P(sp->B); a.sB = sp->B.sample_stride;
+  a.H = P(sp->H); a.sH = sp->H.sample_stride;
+  a.C = P(sp->C); a.sC = sp->C.sample_stride;
+  a.D = P(sp->D); a.sD = sp->D.sample_stride;
+  a.Q = P(sp->Q); a.sQ = sp->Q.sample_stride;
+  a.R = P(sp->R); a.sR = sp->R.sample_stride;
+  a.Qf = sp->Qf.ptr ? P(sp->Qf) : P(sp->Q); a.sQf = sp->Qf.ptr ? sp->Qf.sample_stride : sp->Q.sample_stride;
+  a.Omxi = P(sp->Om_xi); a.sOmxi = sp->Om_xi.sample_stride;
+  a.Omom = P(sp->Om_omega); a.sOmom = sp->Om_omega.sample_stride;
+  a.Sig1 = P(sp->Sigma1); a.sSig1 = sp->Sigma1.sample_stride;
+  if (!sp->xhat1.ptr) return LQGK_E_INVALID;
+  a.xh1 = P(sp->xhat1); a.sxh1 = sp->xhat1.sample_stride;
+  a.S = d->S; a.T = d->T; a.nc = d->nc; a.nd = d->nd; a.sweeps = d->sweeps;
+  a.L = L_out; a.K = K_out; a.cost = cost_out;
+#define LQGK_CASE(X, B, U, Y, DD) \
+  if (X + B <= 12 && d->b == B && d->u == U && d->y == Y) return Runner<X, B, U, Y, DD>::run_sdn(a, (cudaStream_t)stream);
+  LQGK_FOR_EACH_DIMS(LQGK_CASE)
+#undef LQGK_CASE
+  return LQGK_E_UNSUPPORTED;
+}
+
 int lqgk_lqr_backward_f32(const LqgkDims* dims, const LqgkSpec* actor, double eps, float* L_out, float* l_out, float* H_out,
                           void* ws, size_t ws_bytes, void* stream) {
   Call c{dims, actor, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, L_out, l_out, H_out, nullptr, eps, LQGK_MODE_GAINS, ws, ws_bytes, (cudaStream_t)stream};

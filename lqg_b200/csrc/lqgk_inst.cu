@@ -24,4 +24,15 @@ size_t Runner<LQGK_INST_X, LQGK_INST_B, LQGK_INST_U, LQGK_INST_Y, LQGK_INST_D>::
   size_t Sc = choose_chunk<DMI>(d, mode, false, (size_t)-1, max_chunk);
   return make_plan<DMI>(d, mode, false, Sc).bytes;
 }
+template <>
+int Runner<LQGK_INST_X, LQGK_INST_B, LQGK_INST_U, LQGK_INST_Y, LQGK_INST_D>::run_sdn(const SdnArgs& a, cudaStream_t st) {
+#if defined(LQGK_BIG)
+  (void)a; (void)st;
+  return LQGK_E_UNSUPPORTED;
+#else
+  k_sdn_gains<DMI><<<(a.S + 31) / 32, 32, 0, st>>>(a);
+  LQGK_LAUNCH_CHECK();
+  return LQGK_OK;
+#endif
+}
 }  // namespace lqgk

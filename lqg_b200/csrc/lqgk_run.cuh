@@ -8,6 +8,7 @@
 
 #include "../../include/lqgk.h"
 #include "lqgk_kernels.cuh"
+#include "lqgk_sdn.cuh"
 
 namespace lqgk {
 
@@ -488,6 +489,7 @@ struct Runner {
   static int run_f32(const Call& c);
   static int run_f64(const Call& c);
   static size_t plan_bytes(const LqgkDims& d, int mode, int32_t max_chunk);
+  static int run_sdn(const SdnArgs& a, cudaStream_t st);   // signal-dependent-noise gains (b, u, y of this tuple)
 };
 
 }  // namespace lqgk
