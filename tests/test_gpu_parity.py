@@ -71,6 +71,16 @@ def test_more_trials_than_one_pass(lib, dev):
     H.check_vjp(lib, dev, case, torch.float32)
 
 
+@pytest.mark.parametrize("name,d,N", [("bounded", 2, 301), ("subjective", 2, 300), ("bounded2", 4, 150), ("subjective2", 4, 131),
+                                      ("delay2", 2, 129)])
+def test_several_trial_passes_and_odd_trial_counts(lib, dev, name, d, N):
+    """More trials than one pass of 32 x RT per warp (RT <= 8 small systems, <= 4 larger ones): the second pass starts at
+    base > 0 and accumulates into the per-step sums; odd N exercises the zero pad element of the paired state history."""
+    case = H.Case(name, S=3, T=40, N=N, d=d, weights=True)
+    H.check_fwd(lib, dev, case, torch.float32)
+    H.check_vjp(lib, dev, case, torch.float32)
+
+
 def test_config_c1_shape(lib, dev):
     """BASELINE config 1: BoundedActor 1-D, T=500, 20 trials (reference tests/infer_test.py:19-26 shape)."""
     case = H.Case("bounded", S=1, T=500, N=20, seed=123)
