@@ -16,15 +16,26 @@ namespace lqgk {
 
 constexpr int BW_WARPS = 4;   // samples (warps) per CTA
 
-// C[M,N] (op)= A B with A addressed as a(i,k), B as b(k,j); out(i, j, value) consumes each element once.
+// C[M,N] (op)= A B with A addressed as a(i,k), B as b(k,j); out(i, j, value) consumes each element once.  Every lane
+// owns 2 x 2 tiles of the output: 4 shared-memory loads feed 4 FMAs (the kernels are shared-memory-bandwidth bound; an
+// element-per-lane product needs 2 loads per FMA).
 template <int M, int N, int K, class FA, class FB, class Out>
 __device__ __forceinline__ void wmm(int lane, FA&& a, FB&& b, Out&& out) {
-  for (int e = lane; e < M * N; e += 32) {
-    const int i = e / N, j = e - i * N;
-    double acc = 0.0;
+  constexpr int MT = (M + 1) / 2, NT = (N + 1) / 2;
+  for (int e = lane; e < MT * NT; e += 32) {
+    const int it = e / NT;
+    const int i0 = 2 * it, j0 = 2 * (e - it * NT);
+    const bool hi = i0 + 1 < M, hj = j0 + 1 < N;
+    const int i1 = hi ? i0 + 1 : i0, j1 = hj ? j0 + 1 : j0;          // clamped: the duplicate results are discarded
+    double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
 #pragma unroll 4
-    for (int k = 0; k < K; ++k) acc += a(i, k) * b(k, j);
-    out(i, j, acc);
+    for (int k = 0; k < K; ++k) {
+      const double a0 = a(i0, k), a1 = a(i1, k), b0 = b(k, j0), b1 = b(k, j1);
+      c00 += a0 * b0; c01 += a0 * b1; c10 += a1 * b0; c11 += a1 * b1;
+    }
+    out(i0, j0, c00);
+    if (hj) out(i0, j1, c01);
+    if (hi) { out(i1, j0, c10); if (hj) out(i1, j1, c11); }
   }
 }
 
@@ -47,17 +58,28 @@ __device__ __forceinline__ void bw_flush_acc(int lane, double* g, size_t Sc, con
     for (int e = lane; e < len; e += 32) atomicAdd(g + (size_t)(go + e) * Sc, a[lo + e]);
   }
 }
-// C[M,M] = base(i,j) + sum_k a(i,k) b(k,j), result known symmetric: lower triangle computed, mirrored.
+// C[M,M] = base(i,j) + sum_k a(i,k) b(k,j), result known symmetric: lower triangle computed (2 x 2 tiles), mirrored.
 template <int M, int K, class Base, class FA, class FB>
 __device__ __forceinline__ void wmm_sym(int lane, Base&& base, FA&& a, FB&& b, double* Cm) {
-  for (int e = lane; e < M * M; e += 32) {
-    const int i = e / M, j = e - i * M;
-    if (j > i) continue;
-    double acc = base(i, j);
+  constexpr int MT = (M + 1) / 2;
+  for (int e = lane; e < MT * MT; e += 32) {
+    const int it = e / MT, jt = e - it * MT;
+    if (jt > it) continue;
+    const int i0 = 2 * it, j0 = 2 * jt;
+    const bool hi = i0 + 1 < M, hj = j0 + 1 < M;
+    const int i1 = hi ? i0 + 1 : i0, j1 = hj ? j0 + 1 : j0;
+    double c00 = base(i0, j0), c01 = base(i0, j1), c10 = base(i1, j0), c11 = base(i1, j1);
 #pragma unroll 4
-    for (int k = 0; k < K; ++k) acc += a(i, k) * b(k, j);
-    Cm[i * M + j] = acc;
-    Cm[j * M + i] = acc;
+    for (int k = 0; k < K; ++k) {
+      const double a0 = a(i0, k), a1 = a(i1, k), b0 = b(k, j0), b1 = b(k, j1);
+      c00 += a0 * b0; c01 += a0 * b1; c10 += a1 * b0; c11 += a1 * b1;
+    }
+    Cm[i0 * M + j0] = c00; Cm[j0 * M + i0] = c00;
+    if (hj && j1 <= i0) { Cm[i0 * M + j1] = c01; Cm[j1 * M + i0] = c01; }     // off-diagonal tiles only (j1 > i0 on the diagonal)
+    if (hi) {
+      Cm[i1 * M + j0] = c10; Cm[j0 * M + i1] = c10;
+      if (hj) { Cm[i1 * M + j1] = c11; Cm[j1 * M + i1] = c11; }
+    }
   }
 }
 
@@ -71,7 +93,7 @@ struct BigW {
   // ------------------------------------------------------------------------------------------ forward
   static constexpr int FWD_DOUBLES = NC + U * B + B * Y + B * U + B * Y + 3 * N * N + R * R + N * R + R * D + 3 * D * D + 8;
   static size_t smem_fwd() { return sizeof(double) * FWD_DOUBLES * BW_WARPS; }
-  static constexpr int SEQ_DOUBLES = 2 * R * R + 2 * N * R + 5 * R * D + 2 * D * D + 8;
+  static constexpr int SEQ_DOUBLES = 2 * R * R + 2 * N * R + 5 * R * D + 2 * D * D + N * N + 8;
   static size_t smem_seq() { return sizeof(double) * SEQ_DOUBLES * BW_WARPS; }
   static constexpr int CON_DOUBLES = 2 * NC + U * B + B * Y + R * R + N * R + 2 * N * N + 2 * B * Y + 2 * B * U + U * B + 8;
   static size_t smem_con() { return sizeof(double) * CON_DOUBLES * BW_WARPS; }
@@ -213,14 +235,8 @@ __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_fwd(const double* cst, s
     wmm<N, R, R>(lane, [&](int i, int k) { return Fj[i * N + D + k]; }, [&](int k, int j) { return Cm[k * R + j]; },
                  [&](int i, int j, double v) { T1[i * R + j] = v; });
     __syncwarp();
-    for (int e = lane; e < N * N; e += 32) {                               // Sig' = Fu C Fu^T + N (lower, mirrored)
-      const int i = e / N, j = e - i * N;
-      if (j > i) continue;
-      double a = Nj[e];
-      for (int k = 0; k < R; ++k) a += T1[i * R + k] * Fj[j * N + D + k];
-      Sig[i * N + j] = a;
-      Sig[j * N + i] = a;
-    }
+    wmm_sym<N, R>(lane, [&](int i, int j) { return Nj[i * N + j]; }, [&](int i, int k) { return T1[i * R + k]; },
+                  [&](int k, int j) { return Fj[j * N + D + k]; }, Sig);   // Sig' = Fu C Fu^T + N (lower, mirrored)
     __syncwarp();
     double* js = JS + (s * Tn + t) * (size_t)SR::NJS;
     bw_condition<DM>(lane, Sig, Linv, Z, ld, [&](int e, double v) { rt[DM::REC_J + e] = (float)v; if (save_adj) js[e] = v; }, Cm);
@@ -261,6 +277,7 @@ __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_seq_rev(int npad, int Tn
   double* CJ = Bh + R * D;
   double* Sinv = CJ + R * D;
   double* Ss = Sinv + D * D;
+  double* Sg = Ss + D * D;          // full symmetric joint cotangent Sgb_t (N x N)
   double sw = 0.0;
   for (int i = lane; i < Ntr; i += 32) sw += (double)w[s * Ntr + i];
   for (int m = 16; m >= 1; m >>= 1) sw += __shfl_xor_sync(FULL, sw, m);
@@ -296,35 +313,21 @@ __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_seq_rev(int npad, int Tn
     }
     __syncwarp();
     double* sgb = SGB + (s * Tn + t) * (size_t)SR::NSGB;
-    for (int e = lane; e < N * N; e += 32) {                               // Sgb_t, packed lower over the joint index
+    for (int e = lane; e < N * N; e += 32) {                               // Sgb_t: full symmetric in shared memory, packed lower out
       const int i = e / N, j = e - i * N;
       if (j > i) continue;
-      sgb[i * (i + 1) / 2 + j] = i < D ? Ss[i * D + j] : (j < D ? Bh[(i - D) * D + j] : Cb[(i - D) * R + (j - D)]);
-    }
-    double* sfw = SFW + (s * Tn + t) * (size_t)SR::NSF;
-    for (int e = lane; e < N * R; e += 32) {                               // SF_t = Sgb_t Fu_t
-      const int m = e / R, cc = e - m * R;
-      double a = 0.0;
-      if (m < D) {
-        for (int k = 0; k < D; ++k) a += Ss[m * D + k] * Fu[k * R + cc];
-        for (int i = 0; i < R; ++i) a += Bh[i * D + m] * Fu[(D + i) * R + cc];
-      } else {
-        const int i = m - D;
-        for (int k = 0; k < D; ++k) a += Bh[i * D + k] * Fu[k * R + cc];
-        for (int k = 0; k < R; ++k) a += Cb[i * R + k] * Fu[(D + k) * R + cc];
-      }
-      SF[e] = a;
-      sfw[e] = a;
+      const double v = i < D ? Ss[i * D + j] : (j < D ? Bh[(i - D) * D + j] : Cb[(i - D) * R + (j - D)]);
+      sgb[i * (i + 1) / 2 + j] = v;
+      Sg[i * N + j] = v;
+      Sg[j * N + i] = v;
     }
     __syncwarp();
-    for (int e = lane; e < R * R; e += 32) {                               // Cb <- Fu^T SF (lower, mirrored)
-      const int a = e / R, b = e - a * R;
-      if (b > a) continue;
-      double v = 0.0;
-      for (int m = 0; m < N; ++m) v += Fu[m * R + a] * SF[m * R + b];
-      Cn[a * R + b] = v;
-      Cn[b * R + a] = v;
-    }
+    double* sfw = SFW + (s * Tn + t) * (size_t)SR::NSF;
+    wmm<N, R, N>(lane, [&](int m, int k) { return Sg[m * N + k]; }, [&](int k, int cc) { return Fu[k * R + cc]; },
+                 [&](int m, int cc, double v) { SF[m * R + cc] = v; sfw[m * R + cc] = v; });   // SF_t = Sgb_t Fu_t
+    __syncwarp();
+    wmm_sym<R, N>(lane, [&](int, int) { return 0.0; }, [&](int a, int m) { return Fu[m * R + a]; },
+                  [&](int m, int b) { return SF[m * R + b]; }, Cn);        // Cb <- Fu^T SF (lower, mirrored)
     __syncwarp();
     double* tmp = Cb; Cb = Cn; Cn = tmp;
   }
@@ -437,16 +440,9 @@ __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_contrib(const double* cs
       noise(false);
     }
     // Fb = trial sums + [0 | 2 SF C]   (CovContrib::fb_row)
-    for (int e = lane; e < N * N; e += 32) {
-      const int m = e / N, j = e - m * N;
-      double a = (double)sm[DM::SUM_F + e];
-      if (j >= D) {
-        double v = 0.0;
-        for (int k = 0; k < R; ++k) v += SF[m * R + k] * Cm[k * R + (j - D)];
-        a += 2.0 * v;
-      }
-      Fb[e] = a;
-    }
+    for (int e = lane; e < N * D; e += 32) { const int m = e / D, j = e - m * D; Fb[m * N + j] = (double)sm[DM::SUM_F + m * N + j]; }
+    wmm<N, R, R>(lane, [&](int m, int k) { return SF[m * R + k]; }, [&](int k, int j) { return Cm[k * R + j]; },
+                 [&](int m, int j, double v) { Fb[m * N + D + j] = (double)sm[DM::SUM_F + m * N + D + j] + 2.0 * v; });
     wmm<B, U, Y>(lane, [&](int i, int k) { return Kt[i * Y + k]; }, [&](int k, int j) { return c[C::Dm + k * U + j]; },
                  [&](int i, int j, double v) { KD[i * U + j] = c[C::Ba + i * U + j] + v; });
     __syncwarp();

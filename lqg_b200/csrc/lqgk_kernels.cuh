@@ -268,6 +268,7 @@ __global__ void __launch_bounds__(32) k_cov_fwd(const double* cst, size_t Sc, si
     CovFwd<DM>::init(lc, K0, Cm, J0v);
     if (save_adj) { LQGK_UNROLL for (int i = 0; i < R * D; ++i) J0[(size_t)i * Sc + s] = J0v[i]; }
   }
+  // (constants stay in shared memory here: a register copy of the 40 covariance constants made this kernel 10 % slower)
   for (int t = 0; t < Tn; ++t) {
     const int st = t % SEQ_NST;
     const double* stg = ring.wait(st);
@@ -443,18 +444,27 @@ __global__ void __launch_bounds__(32) k_kf_rev(const double* cst, size_t Sc, int
   auto accf = [&](int e) -> double& { return la(e); };
   double Pnb[B * B];
   LQGK_UNROLL for (int i = 0; i < B * B; ++i) Pnb[i] = 0.0;
-  for (int kk = 0; kk < Tn; ++kk) {
-    const int st = kk % SEQ_NST;
-    const double* stg = ring.wait(st);
-    double P[B * B], Kb[B * Y];
-    load_sym_ws<B>(ring.view(stg, 0), 0, P);
-    {
-      WView kv = ring.view(stg, DM::EP), kv2 = ring.view(stg, DM::EP + DM::EK);
-      LQGK_UNROLL for (int i = 0; i < B * Y; ++i) Kb[i] = kv(i) + kv2(i);
+  auto sweep = [&](const auto& cv) {
+    for (int kk = 0; kk < Tn; ++kk) {
+      const int st = kk % SEQ_NST;
+      const double* stg = ring.wait(st);
+      double P[B * B], Kb[B * Y];
+      load_sym_ws<B>(ring.view(stg, 0), 0, P);
+      {
+        WView kv = ring.view(stg, DM::EP), kv2 = ring.view(stg, DM::EP + DM::EK);
+        LQGK_UNROLL for (int i = 0; i < B * Y; ++i) Kb[i] = kv(i) + kv2(i);
+      }
+      __syncwarp();
+      if (kk + SEQ_NST < Tn) ring.issue(Tn - 1 - (kk + SEQ_NST), st);
+      KfRev<DM>::step(cv, accf, P, Kb, Pnb);
     }
-    __syncwarp();
-    if (kk + SEQ_NST < Tn) ring.issue(Tn - 1 - (kk + SEQ_NST), st);
-    KfRev<DM>::step(lc, accf, P, Kb, Pnb);
+  };
+  if constexpr (C::n <= LQGK_REG_CONSTS_MAX) {
+    RegView<C::n> rc;
+    LQGK_UNROLL for (int e = 0; e < C::n; ++e) rc.v[e] = lc(e);
+    sweep(rc);
+  } else {
+    sweep(lc);
   }
   KfRev<DM>::finish(accf, Pnb);
   flush_acc_atomic<C>(acc + s, Sc, la, C::NSEG);
@@ -483,28 +493,37 @@ __global__ void __launch_bounds__(32) k_lqr_rev(const double* cst, size_t Sc, in
   auto accf = [&](int e) -> double& { return la(e); };
   double Sn[B * B];
   LQGK_UNROLL for (int i = 0; i < B * B; ++i) Sn[i] = 0.0;
-  for (int t = 0; t < Tn; ++t) {
-    const int st = t % SEQ_NST;
-    const double* stg = ring.wait(st);
-    double S[B * B], Lt[U * B], Lb[U * B];
-    load_sym_ws<B>(ring.view(stg, 0), 0, S);
-    {
-      WView lv = ring.view(stg, DM::ES), bv = ring.view(stg, DM::ES + DM::EL);
-      LQGK_UNROLL for (int i = 0; i < U * B; ++i) { Lt[i] = lv(i); Lb[i] = bv(i); }
+  auto sweep = [&](const auto& cv) {
+    for (int t = 0; t < Tn; ++t) {
+      const int st = t % SEQ_NST;
+      const double* stg = ring.wait(st);
+      double S[B * B], Lt[U * B], Lb[U * B];
+      load_sym_ws<B>(ring.view(stg, 0), 0, S);
+      {
+        WView lv = ring.view(stg, DM::ES), bv = ring.view(stg, DM::ES + DM::EL);
+        LQGK_UNROLL for (int i = 0; i < U * B; ++i) { Lt[i] = lv(i); Lb[i] = bv(i); }
+      }
+      __syncwarp();
+      if (t + SEQ_NST < Tn) ring.issue(t + SEQ_NST, st);
+      double shift;
+      {
+        double Bm[B * U], SB[B * U], H[U * U];
+        load_mat<B, U>(cv, C::Ba, Bm);
+        mm<B, B, U>(S, Bm, SB);
+        load_sym<U>(cv, C::R, H);
+        mm_tn_sym<U, B, true>(Bm, SB, H);
+        shift = eps - lambda_min<U>(H);
+        shift = shift > 0.0 ? shift : 0.0;
+      }
+      LqrRev<DM>::step(cv, accf, S, Lt, Lb, shift, Sn);
     }
-    __syncwarp();
-    if (t + SEQ_NST < Tn) ring.issue(t + SEQ_NST, st);
-    double shift;
-    {
-      double Bm[B * U], SB[B * U], H[U * U];
-      load_mat<B, U>(lc, C::Ba, Bm);
-      mm<B, B, U>(S, Bm, SB);
-      load_sym<U>(lc, C::R, H);
-      mm_tn_sym<U, B, true>(Bm, SB, H);
-      shift = eps - lambda_min<U>(H);
-      shift = shift > 0.0 ? shift : 0.0;
-    }
-    LqrRev<DM>::step(lc, accf, S, Lt, Lb, shift, Sn);
+  };
+  if constexpr (C::n <= LQGK_REG_CONSTS_MAX) {
+    RegView<C::n> rc;
+    LQGK_UNROLL for (int e = 0; e < C::n; ++e) rc.v[e] = lc(e);
+    sweep(rc);
+  } else {
+    sweep(lc);
   }
   LqrRev<DM>::finish(accf, Sn);
   flush_acc_atomic<C>(acc + s, Sc, la, C::NSEG);
@@ -883,6 +902,9 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __r
       LQGK_UNROLL for (int m = 0; m < D; ++m) x1S[m] = x1[RT - 1][m];
     }
     float* out = sums + ((size_t)s * Tn + (Tn - 1)) * DM::SUMP;
+    const int xstep = N * D;
+    const float* xq = x_tm + (size_t)(Tn - 1) * N * D + (size_t)(base + 2 * lane) * D;              // pairs: trials base + 64p + 2 lane (+1)
+    const float* xqs = x_tm + (size_t)(Tn - 1) * N * D + (size_t)(base + 64 * NP + lane) * D;       // single: base + 64 NP + lane
     for (int k = 0; k < TRIAL_NST && k < nchunk; ++k) ring.issue(nchunk - 1 - k, k);
     for (int kk = 0; kk < nchunk; ++kk) {
       const int k = nchunk - 1 - kk;
@@ -904,8 +926,12 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __r
         LQGK_UNROLL for (int m = 0; m < R; ++m) cS[m] = cnS[m];
         if (t > 0) {
           LQGK_UNROLL for (int m = 0; m < NHP; ++m) hr[m] -= hstep;
-          const float* xrow = x_tm + (size_t)(t - 1) * N * D;
-          LQGK_UNROLL for (int j = 0; j < RT; ++j) load_obs<D>(xrow + trD[j], x0n[j]);
+          // observations of step t-1 through two walking pointers + immediate offsets.  Slots beyond the last trial read the
+          // neighbouring entries of the row (or the start of row t <= Tn-1: inside the array); they are finite and masked
+          // (w = 0, c = 0), so no per-step index clamping is needed here (the prologue, which touches row Tn, clamps).
+          xq -= xstep;
+          LQGK_UNROLL for (int j = 0; j < 2 * NP; ++j) load_obs<D>(xq + (64 * (j >> 1) + (j & 1)) * D, x0n[j]);
+          if constexpr (NS) { xqs -= xstep; load_obs<D>(xqs, x0n[RT - 1]); }
           load_hist(cnP, cnS);
         }
         f32x2 eP[NPA][D], vP[NPA][D], wvP[NPA][D], nebP[NPA][D], cbnP[NPA][R];

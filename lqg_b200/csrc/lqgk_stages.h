@@ -7,6 +7,11 @@
 #pragma once
 #include "lqgk_core.h"
 
+// Largest constant block (doubles) that is copied into registers (RegView below); larger systems read shared memory.
+#ifndef LQGK_REG_CONSTS_MAX
+#define LQGK_REG_CONSTS_MAX 48
+#endif
+
 namespace lqgk {
 
 template <class KC, class G, class Lc>
@@ -38,6 +43,15 @@ LQGK_HD void load_sym_ws(const W& w, size_t off, double* C) {
   }
 }
 
+// Register copy of a kernel-local constant block: with the fully unrolled step functions every index is a compile-time
+// constant, so the block lives in registers and the per-step shared-memory reads of the constants (and their latency, which
+// bounds the sequential kernels) disappear.  Used for time-invariant specs; time-varying ones keep reading the reloaded block.
+template <int NN>
+struct RegView {
+  double v[NN];
+  LQGK_HD double operator()(int e) const { return v[e]; }
+};
+
 // gcst: this sample's global constant block (stride = chunk size); tstride: elements between consecutive
 // time steps of that block (0 = time-invariant).  lc: local (shared-memory) copy used by the step functions.
 struct GCst {
@@ -57,17 +71,30 @@ LQGK_HD void lqr_fwd_body(const GCst& g, WView lc, int T, double eps, WView Lw, 
   double S[B * B], s[B];
   load_sym<B>(lc, C::Qf, S);
   if (AFFINE) { LQGK_UNROLL64 for (int i = 0; i < B; ++i) s[i] = lc(C::qf + i); }
-  for (int t = T - 1; t >= 0; --t) {
-    if (g.tstride && t != T - 1) load_consts<C>(g.at(t), lc, nseg);
-    if (save_S) store_sym<B>(Sw, (size_t)t * DM::ES, S);
-    double L[U * B], l[U], Ht[U * U], shift;
-    LqrFwd<DM, AFFINE>::step(lc, eps, S, s, L, l, Ht, shift);
-    LQGK_UNROLL64 for (int i = 0; i < U * B; ++i) Lw((size_t)t * DM::EL + i) = L[i];
-    if (AFFINE) {
-      LQGK_UNROLL64 for (int i = 0; i < U; ++i) lw((size_t)t * U + i) = l[i];
-      LQGK_UNROLL64 for (int i = 0; i < U * U; ++i) Hw((size_t)t * U * U + i) = Ht[i];
+  auto sweep = [&](const auto& cv, bool reload) {
+    for (int t = T - 1; t >= 0; --t) {
+      if (reload && t != T - 1) load_consts<C>(g.at(t), lc, nseg);
+      if (save_S) store_sym<B>(Sw, (size_t)t * DM::ES, S);
+      double L[U * B], l[U], Ht[U * U], shift;
+      LqrFwd<DM, AFFINE>::step(cv, eps, S, s, L, l, Ht, shift);
+      LQGK_UNROLL64 for (int i = 0; i < U * B; ++i) Lw((size_t)t * DM::EL + i) = L[i];
+      if (AFFINE) {
+        LQGK_UNROLL64 for (int i = 0; i < U; ++i) lw((size_t)t * U + i) = l[i];
+        LQGK_UNROLL64 for (int i = 0; i < U * U; ++i) Hw((size_t)t * U * U + i) = Ht[i];
+      }
+    }
+  };
+  constexpr int NCST = AFFINE ? C::n_affine : C::n;
+  bool done = false;
+  if constexpr (NCST <= LQGK_REG_CONSTS_MAX) {
+    if (g.tstride == 0) {
+      RegView<NCST> rc;
+      LQGK_UNROLL64 for (int e = 0; e < NCST; ++e) rc.v[e] = lc(e);
+      sweep(rc, false);
+      done = true;
     }
   }
+  if (!done) sweep(lc, g.tstride != 0);
 }
 
 // ---------------------------------------------------------------------------------------------- KF fwd
@@ -78,13 +105,25 @@ LQGK_HD void kf_fwd_body(const GCst& g, WView lc, int T, WView Kw, bool save_P, 
   load_consts<C>(g.at(0), lc, C::NSEG);
   double P[B * B];
   load_sym<B>(lc, C::Sig0, P);
-  for (int t = 0; t < T; ++t) {
-    if (g.tstride && t != 0) load_consts<C>(g.at(t), lc, C::NSEG);
-    if (save_P) store_sym<B>(Pw, (size_t)t * DM::EP, P);
-    double K[B * Y];
-    KfFwd<DM>::step(lc, P, K);
-    LQGK_UNROLL64 for (int i = 0; i < B * Y; ++i) Kw((size_t)t * DM::EK + i) = K[i];
+  auto sweep = [&](const auto& cv, bool reload) {
+    for (int t = 0; t < T; ++t) {
+      if (reload && t != 0) load_consts<C>(g.at(t), lc, C::NSEG);
+      if (save_P) store_sym<B>(Pw, (size_t)t * DM::EP, P);
+      double K[B * Y];
+      KfFwd<DM>::step(cv, P, K);
+      LQGK_UNROLL64 for (int i = 0; i < B * Y; ++i) Kw((size_t)t * DM::EK + i) = K[i];
+    }
+  };
+  bool done = false;
+  if constexpr (C::n <= LQGK_REG_CONSTS_MAX) {
+    if (g.tstride == 0) {
+      RegView<C::n> rc;
+      LQGK_UNROLL64 for (int e = 0; e < C::n; ++e) rc.v[e] = lc(e);
+      sweep(rc, false);
+      done = true;
+    }
   }
+  if (!done) sweep(lc, g.tstride != 0);
 }
 
 // ---------------------------------------------------------------------------------------------- COV fwd
