@@ -129,10 +129,8 @@ __device__ __forceinline__ void bw_condition(int lane, const double* Sig, double
   if (lane == 0) {
     double Lc[D * D], Li[D * D];
     for (int i = 0; i < D; ++i) for (int j = 0; j < D; ++j) Lc[i * D + j] = Sig[i * N + j];
-    chol<D>(Lc);
-    double l = 0.0;
-    for (int i = 0; i < D; ++i) l += log(Lc[i * D + i]);
-    tri_inv<D>(Lc, Li);
+    double l;
+    chol_and_inverse<D>(Lc, Li, &l);
     for (int i = 0; i < D * D; ++i) Linv[i] = Li[i];
     *ld = l;
   }
@@ -518,8 +516,7 @@ __device__ __forceinline__ double bw_lqr_common(int lane, const double* c, doubl
     shift = shift > 0.0 ? shift : 0.0;
     for (int i = 0; i < U * U; ++i) Lc[i] = Hl[i];
     for (int i = 0; i < U; ++i) Lc[i * U + i] += shift;
-    chol<U>(Lc);
-    tri_inv<U>(Lc, Li);
+    chol_and_inverse<U>(Lc, Li);
     mm_tn<U, U, U>(Li, Li, Hv);
     for (int i = 0; i < U * U; ++i) Hi[i] = Hv[i];
     *shift_sm = shift;
@@ -640,8 +637,7 @@ __device__ __forceinline__ void bw_kf_gain(int lane, const double* c, const doub
   if (lane == 0) {
     double Gl[Y * Y], Li[Y * Y], Gv[Y * Y];
     for (int i = 0; i < Y * Y; ++i) Gl[i] = Gm[i];
-    chol<Y>(Gl);
-    tri_inv<Y>(Gl, Li);
+    chol_and_inverse<Y>(Gl, Li);
     mm_tn_sym<Y, Y>(Li, Li, Gv);
     for (int i = 0; i < Y * Y; ++i) Gi[i] = Gv[i];
   }

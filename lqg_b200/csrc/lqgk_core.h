@@ -198,6 +198,47 @@ LQGK_HD void tri_inv(const double* Lc, double* Li) {
     }
   }
 }
+// Cholesky factor (in place, lower) AND its inverse in one pass.  The diagonal uses one reciprocal square root per column
+// (rsqrt on the device) and every later division becomes a multiplication by that reciprocal: the double-precision sqrt /
+// divide / log sequences are the longest links of the per-step dependency chains that bound the sequential kernels.
+// `half_logdet` (optional): sum_i log L_ii, from a single log of the product of the reciprocals (M <= 4: no range issue).
+LQGK_HD double rsqrt_f64(double x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrt(x);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+template <int M>
+LQGK_HD void chol_and_inverse(double* A, double* Li, double* half_logdet = nullptr) {
+  double rinv[M];
+  LQGK_UNROLL64 for (int j = 0; j < M; ++j) {
+    double djj = A[j * M + j];
+    LQGK_UNROLL64 for (int k = 0; k < j; ++k) djj -= A[j * M + k] * A[j * M + k];
+    const double r = rsqrt_f64(djj);
+    rinv[j] = r;
+    A[j * M + j] = djj * r;
+    LQGK_UNROLL64 for (int i = j + 1; i < M; ++i) {
+      double v = A[i * M + j];
+      LQGK_UNROLL64 for (int k = 0; k < j; ++k) v -= A[i * M + k] * A[j * M + k];
+      A[i * M + j] = v * r;
+    }
+  }
+  LQGK_UNROLL64 for (int i = 0; i < M * M; ++i) Li[i] = 0.0;
+  LQGK_UNROLL64 for (int j = 0; j < M; ++j) {
+    Li[j * M + j] = rinv[j];
+    LQGK_UNROLL64 for (int i = j + 1; i < M; ++i) {
+      double v = 0.0;
+      LQGK_UNROLL64 for (int k = j; k < i; ++k) v -= A[i * M + k] * Li[k * M + j];
+      Li[i * M + j] = v * rinv[i];
+    }
+  }
+  if (half_logdet) {
+    double prod = 1.0;
+    LQGK_UNROLL64 for (int j = 0; j < M; ++j) prod *= rinv[j];
+    *half_logdet = -log(prod);
+  }
+}
 // Smallest eigenvalue of a symmetric M x M matrix (closed form for M <= 2, cyclic Jacobi otherwise).
 template <int M>
 LQGK_HD double lambda_min(const double* H) {
@@ -289,9 +330,8 @@ struct LqrFwd {
     double Lc[U * U];
     LQGK_UNROLL64 for (int i = 0; i < U * U; ++i) { Lc[i] = H[i]; Ht[i] = H[i]; }
     LQGK_UNROLL64 for (int i = 0; i < U; ++i) { Lc[i * U + i] += shift; Ht[i * U + i] += shift; }
-    chol<U>(Lc);                                  // Ht is SPD after the shift
     double Li[U * U], Hi[U * U];
-    tri_inv<U>(Lc, Li);
+    chol_and_inverse<U>(Lc, Li);                  // Ht is SPD after the shift
     mm_tn<U, U, U>(Li, Li, Hi);                   // Ht^-1
     mm<U, U, B>(Hi, G, L);
     LQGK_UNROLL64 for (int i = 0; i < U * B; ++i) L[i] = -L[i];                 // L = -Ht^-1 G   lqr.py:30
@@ -360,9 +400,8 @@ struct KfFwd {
     double Gm[Y * Y];
     load_sym<Y>(c, C::WWa, Gm);
     mm_nt_sym<Y, B, true>(M, F, Gm);                 // Gm = F Pp F^T + W W^T       kf.py:11
-    chol<Y>(Gm);
     double Li[Y * Y];
-    tri_inv<Y>(Gm, Li);
+    chol_and_inverse<Y>(Gm, Li);
     mm_tn_sym<Y, Y>(Li, Li, Gi);
     mm_tn<B, Y, Y>(M, Gi, K);                        // K = Pp F^T Gm^-1            kf.py:12
   }
@@ -470,10 +509,7 @@ struct CovFwd {
   LQGK_HD static void condition(const double* Sig, double* Linv, double& logdet, EmitJ&& emit_j, double* Cn) {
     double Lc[D * D];
     LQGK_UNROLL64 for (int i = 0; i < D; ++i) LQGK_UNROLL64 for (int j = 0; j < D; ++j) Lc[i * D + j] = Sig[i * N + j];
-    chol<D>(Lc);
-    logdet = 0.0;
-    LQGK_UNROLL64 for (int i = 0; i < D; ++i) logdet += log(Lc[i * D + i]);
-    tri_inv<D>(Lc, Linv);
+    chol_and_inverse<D>(Lc, Linv, &logdet);
     double Z[R * D];                                                 // Z = Sig[u,o] Linv^T
     LQGK_UNROLL64 for (int i = 0; i < R; ++i) LQGK_UNROLL64 for (int j = 0; j < D; ++j) {
       double a = 0.0;
@@ -1022,8 +1058,7 @@ struct LqrRev {
       double Lc[U * U], Li[U * U];
       LQGK_UNROLL64 for (int i = 0; i < U * U; ++i) Lc[i] = H[i];
       LQGK_UNROLL64 for (int i = 0; i < U; ++i) Lc[i * U + i] += shift;
-      chol<U>(Lc);
-      tri_inv<U>(Lc, Li);
+      chol_and_inverse<U>(Lc, Li);
       mm_tn_sym<U, U>(Li, Li, Hi);
     }
     // Q += Sn ; Aa += 2 SA Sn

@@ -54,8 +54,7 @@ struct Sdn {
       mm_tn<U, B, B>(Bm, SA, G);                             // B' Sx A
       double Mi[U * U], Li[U * U], Lt[U * B];
       symmetrize<U>(M);
-      chol<U>(M);
-      tri_inv<U>(M, Li);
+      chol_and_inverse<U>(M, Li);
       mm_tn<U, U, U>(Li, Li, Mi);
       mm<U, U, B>(Mi, G, Lt);                                // L_t = M^-1 B' Sx A
       double* lp = a.L + ((size_t)s * a.T + t) * (U * B);
@@ -134,8 +133,7 @@ struct Sdn {
       }
       double Li[Y * Y], Gi[Y * Y], ASH[B * Y], Kt[B * Y];
       symmetrize<Y>(G);
-      chol<Y>(G);
-      tri_inv<Y>(G, Li);
+      chol_and_inverse<Y>(G, Li);
       mm_tn<Y, Y, Y>(Li, Li, Gi);
       LQGK_UNROLL64 for (int i = 0; i < B; ++i) LQGK_UNROLL64 for (int j = 0; j < Y; ++j) {
         double v = 0.0;                                      // A Se H' = A (H Se)'
