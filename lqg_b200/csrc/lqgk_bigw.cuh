@@ -14,7 +14,7 @@
 
 namespace lqgk {
 
-constexpr int BW_WARPS = 4;   // samples (warps) per CTA
+constexpr int BW_WARPS = 2;   // samples (warps) per CTA: small CTAs pack the 227 KB of shared memory better (18-23 KB per warp)
 
 // C[M,N] (op)= A B with A addressed as a(i,k), B as b(k,j); out(i, j, value) consumes each element once.  Every lane
 // owns 2 x 2 tiles of the output: 4 shared-memory loads feed 4 FMAs (the kernels are shared-memory-bandwidth bound; an
@@ -91,7 +91,7 @@ struct BigW {
   static constexpr int NC = C::n;
 
   // ------------------------------------------------------------------------------------------ forward
-  static constexpr int FWD_DOUBLES = NC + U * B + B * Y + B * U + B * Y + 3 * N * N + R * R + N * R + R * D + 3 * D * D + 8;
+  static constexpr int FWD_DOUBLES = NC + U * B + B * Y + B * U + B * Y + 2 * N * N + R * R + N * R + R * D + 3 * D * D + 8;
   static size_t smem_fwd() { return sizeof(double) * FWD_DOUBLES * BW_WARPS; }
   static constexpr int SEQ_DOUBLES = 2 * R * R + 2 * N * R + 5 * R * D + 2 * D * D + N * N + 8;
   static size_t smem_seq() { return sizeof(double) * SEQ_DOUBLES * BW_WARPS; }
@@ -179,8 +179,8 @@ __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_fwd(const double* cst, s
   double* KO = KD + B * U;
   double* Fj = KO + B * Y;
   double* Nj = Fj + N * N;
-  double* Sig = Nj + N * N;
-  double* Cm = Sig + N * N;
+  double* Sig = Nj;                 // Sig' = N + Fu C Fu^T is accumulated in place (every element is read and written by one lane)
+  double* Cm = Nj + N * N;
   double* T1 = Cm + R * R;
   double* Z = T1 + N * R;
   double* Linv = Z + R * D;
