@@ -152,7 +152,7 @@ int run_big(const Call& c) {
       // time ranges: enough (sample x range) warps to put ~12 on every SM when there are few samples
       int chunks = std::max(1, std::min((Tn + 3) / 4, (148 * 12 + npad - 1) / npad));
       kw_cov_contrib<DM><<<dim3(wblk, chunks), wthr, smem, st>>>(D(p.cst), Sc, npad, Tn, D(p.L), D(p.K), D(p.Cs), D(p.SGB), D(p.SGBI),
-                                                                D(p.SFW), F(p.sums), D(p.acc), D(p.Lbar), D(p.Kbar));
+                                                                D(p.SFW), F(p.sums), D(p.acc), D(p.Lbar), D(p.Kbar), nullptr);
       LQGK_LAUNCH_CHECK();
     }
     {

@@ -10,7 +10,7 @@
 // Mathematics: identical to CovFwd / CovSeqRev / CovContrib in lqgk_core.h (which the host emulation and the small-system
 // kernels execute) and to oracle/adjoint_np.py; reference lines: lqg/system.py:163-212, 223-230 and their reverse mode.
 #pragma once
-#include "lqgk_run.cuh"
+#include "lqgk_kernels.cuh"
 
 namespace lqgk {
 
@@ -161,7 +161,8 @@ __device__ __forceinline__ void bw_condition(int lane, const double* Sig, double
 
 // Covariance pass (forward), warp per sample.  cst: derived constants [element][Sc];  L, K, Cs, FU, JS, J0: sample-major;
 // rec [s][t][REC].
-template <class DM>
+// GAINS_MINOR: L, K are sample-minor [t][e][Sc] (written by the thread-per-sample Riccati / Kalman kernels of the small systems).
+template <class DM, bool GAINS_MINOR = false>
 __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_fwd(const double* cst, size_t Sc, int npad, int Tn, const double* L, const double* K,
                                                             int save_adj, double* Cs, double* FU, double* JS, double* J0, float* rec) {
   using W = BigW<DM>;
@@ -185,16 +186,17 @@ __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_fwd(const double* cst, s
   double* Z = T1 + N * R;
   double* Linv = Z + R * D;
   double* ld = Linv + 3 * D * D;
+  auto gi = [&](int t, int E, int e) -> size_t { return GAINS_MINOR ? ((size_t)t * E + e) * Sc + s : (s * Tn + t) * (size_t)E + e; };
   bw_load_consts<C>(lane, cst + s, Sc, c, C::NSEG);
-  for (int e = lane; e < B * Y; e += 32) Kt[e] = K[s * (size_t)Tn * DM::EK + e];
+  for (int e = lane; e < B * Y; e += 32) Kt[e] = K[gi(0, DM::EK, e)];
   __syncwarp();
   bw_joint_N<DM>(lane, c, Kt, KO, Nj);
   __syncwarp();
   bw_condition<DM>(lane, Nj, Linv, Z, ld, [&](int e, double v) { if (save_adj) J0[s * (R * D) + e] = v; }, Cm);
   float* recs = rec + s * (size_t)Tn * DM::REC;
   for (int t = 0; t < Tn; ++t) {
-    for (int e = lane; e < U * B; e += 32) Lt[e] = L[(s * Tn + t) * (size_t)DM::EL + e];
-    for (int e = lane; e < B * Y; e += 32) Kt[e] = K[(s * Tn + t) * (size_t)DM::EK + e];
+    for (int e = lane; e < U * B; e += 32) Lt[e] = L[gi(t, DM::EL, e)];
+    for (int e = lane; e < B * Y; e += 32) Kt[e] = K[gi(t, DM::EK, e)];
     if (save_adj) {
       double* cs = Cs + (s * Tn + t) * (size_t)DM::EC;
       for (int e = lane; e < R * R; e += 32) {
@@ -353,10 +355,11 @@ __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_seq_rev(int npad, int Tn
 
 // Time-parallel contraction (CovContrib pass 0 + pass 1), warp per (sample, time range).  gacc: the per-sample cotangent
 // accumulators [element][Sc] (CLayout order, zeroed by the caller), updated with one FP64 atomicAdd per element and warp.
-template <class DM>
+// GAINS_MINOR: L, K, Lbar, Kbar sample-minor (small systems); KbarF (their second Kalman-cotangent part) is then zeroed.
+template <class DM, bool GAINS_MINOR = false>
 __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_contrib(const double* cst, size_t Sc, int npad, int Tn, const double* L, const double* K,
                                                                 const double* Cs, const double* SGB, const double* SGBI, const double* SFW,
-                                                                const float* sums, double* gacc, double* Lbar, double* Kbar) {
+                                                                const float* sums, double* gacc, double* Lbar, double* Kbar, double* KbarF) {
   using W = BigW<DM>;
   using C = typename W::C;
   using SR = typename W::SR;
@@ -382,6 +385,7 @@ __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_contrib(const double* cs
   double* KD = Kb + B * Y;
   double* T2 = KD + B * U;
   double* Lb = T2 + B * U;
+  auto gi = [&](int t, int E, int e) -> size_t { return GAINS_MINOR ? ((size_t)t * E + e) * Sc + s : (s * Tn + t) * (size_t)E + e; };
   bw_load_consts<C>(lane, cst + s, Sc, c, C::NSEG);
   for (int e = lane; e < NC; e += 32) acc[e] = 0.0;
   __syncwarp();
@@ -422,8 +426,8 @@ __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_contrib(const double* cs
     const float* sm = sums + (s * Tn + t) * (size_t)DM::SUMP;
     const double* cs = Cs + (s * Tn + t) * (size_t)DM::EC;
     const double* sfw = SFW + (s * Tn + t) * (size_t)SR::NSF;
-    for (int e = lane; e < U * B; e += 32) Lt[e] = L[(s * Tn + t) * (size_t)DM::EL + e];
-    for (int e = lane; e < B * Y; e += 32) Kt[e] = K[(s * Tn + t) * (size_t)DM::EK + e];
+    for (int e = lane; e < U * B; e += 32) Lt[e] = L[gi(t, DM::EL, e)];
+    for (int e = lane; e < B * Y; e += 32) Kt[e] = K[gi(t, DM::EK, e)];
     for (int e = lane; e < R * R; e += 32) {
       const int i = e / R, j = e - i * R;
       Cm[e] = cs[sidx(i, j)];
@@ -472,9 +476,10 @@ __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_contrib(const double* cs
       for (int j = 0; j < X; ++j) a += Fb[(X + i) * N + j] * c[C::FAd + k * X + j];
       for (int j = 0; j < B; ++j) a -= Fb[(X + i) * N + X + j] * c[C::FAa + k * B + j];
       for (int m = 0; m < U; ++m) a += T2[i * U + m] * c[C::Dm + k * U + m];
-      Kbar[(s * Tn + t) * (size_t)DM::EK + e] = Kb[e] + a;
+      Kbar[gi(t, DM::EK, e)] = Kb[e] + a;
+      if (GAINS_MINOR && KbarF) KbarF[gi(t, DM::EK, e)] = 0.0;
     }
-    for (int e = lane; e < U * B; e += 32) Lbar[(s * Tn + t) * (size_t)DM::EL + e] = Lb[e];
+    for (int e = lane; e < U * B; e += 32) Lbar[gi(t, DM::EL, e)] = Lb[e];
     __syncwarp();
   }
   bw_flush_acc<C>(lane, gacc + s, Sc, acc, C::NSEG);

@@ -136,6 +136,31 @@ def check_vjp(lib, device, case: Case, dtype=torch.float32, max_chunk=0, ll_rtol
     return worst
 
 
+def check_vjp_tiled(lib, device, case: Case, reps: int, dtype=torch.float32, ll_rtol=1e-4, g_rtol=1e-3):
+    """check_vjp with the case's samples repeated `reps` times (S * reps systems in one call): reaches sample counts whose
+    kernels differ from the small-batch ones (thread-per-sample covariance kernels above 1,024 samples) at the oracle cost of S."""
+    S = case.S
+    dims = abi.LqgkDims(S * reps, case.N, case.T, *case.dims)
+    act, dyn = case.tensors(device, dtype)
+    act = {k: v.repeat(reps, 1, 1).contiguous() for k, v in act.items()}
+    dyn = {k: v.repeat(reps, 1, 1).contiguous() for k, v in dyn.items()}
+    x_tm = lib.pack_obs(torch.tensor(case.X, device=device), stream=stream_of(device))
+    ws = workspace(lib, dims, abi.MODE_VJP, device)
+    ll_bar = None if case.w is None else torch.tensor(case.w, dtype=dtype, device=device).repeat(reps, 1).contiguous()
+    ll, oa, od, _ = lib.loglik_vjp(dims, act, dyn, x_tm, ll_bar=ll_bar, ws=ws, stream=stream_of(device))
+    if device.type == "cuda":
+        torch.cuda.synchronize(device)
+    ll = ll.double().cpu().numpy()
+    for r in (0, reps // 2, reps - 1):
+        assert np.allclose(ll[r * S:(r + 1) * S], case.ll, rtol=ll_rtol)
+        for s in range(S):
+            floor = 1e-9 * max(max(np.abs(case.ga[s][k]).max() for k in abi.ACTOR_KEYS), max(np.abs(case.gd[s][k]).max() for k in abi.DYN_KEYS))
+            for keys, out, ref in ((abi.ACTOR_KEYS, oa, case.ga), (abi.DYN_KEYS, od, case.gd)):
+                for k in keys:
+                    err = np.abs(out[k][r * S + s].double().cpu().numpy() - ref[s][k]).max()
+                    assert err <= g_rtol * np.abs(ref[s][k]).max() + floor, (k, r, s, err)
+
+
 def check_param_vjp(lib, device, case: Case, dtype=torch.float32, ll_rtol=1e-4, g_rtol=1e-3):
     """lqgk_loglik_vjp on `case`, compared with the oracle at the level BASELINE.json's tolerance is stated for: the
     gradient w.r.t. the model PARAMETERS (base-matrix cotangents chained through the constructor's Jacobian, central
