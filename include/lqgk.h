@@ -149,6 +149,10 @@ int lqgk_set_streams(int n);
 int lqgk_set_kernel_overlap(int mask);
 /* Tuning knob: target number of (32-sample group x time-range) warps of the time-parallel contraction kernels. */
 int lqgk_set_contrib_warps(int n);
+/* Tuning knob: likelihood calls with at most n parameter samples run the covariance kernels one WARP per sample (shared-memory
+ * matrices, lower per-step latency when the GPU is not full), larger calls one THREAD per sample (higher throughput).
+ * Default 512 (measured crossover 512..1,024); 0 = always thread per sample.  Systems with joint dim > 12 always use the warp-per-sample kernels. */
+int lqgk_set_warp_cov_max_samples(int n);
 /* Per-kernel timing for bench.py: when enabled, every kernel launch of the calling thread's entry-point calls is
  * bracketed by CUDA events on the launching stream.  lqgk_profile_read() synchronises on those events, sums the
  * elapsed milliseconds (and launch counts) per kernel kind, resets the log and returns the number of kinds:

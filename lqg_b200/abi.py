@@ -280,6 +280,9 @@ class Library:
     def set_streams(self, n: int):
         self._check(self.lib.lqgk_set_streams(C.c_int(n)), "lqgk_set_streams")
 
+    def set_warp_cov_max_samples(self, n: int):
+        self._check(self.lib.lqgk_set_warp_cov_max_samples(C.c_int(int(n))), "lqgk_set_warp_cov_max_samples")
+
     def set_kernel_overlap(self, mask: int):
         self._check(self.lib.lqgk_set_kernel_overlap(C.c_int(int(mask))), "lqgk_set_kernel_overlap")
 

@@ -17,6 +17,7 @@ thread_local Profiler g_prof;
 thread_local int g_streams = 1;
 thread_local int g_contrib_warps = 148 * 30;
 thread_local int g_aux_streams = 6;
+thread_local int g_warp_cov_max_samples = 512;   // measured crossover between 512 and 1,024 samples (profiles/r01_e_*.md)
 thread_local StreamPool g_pool;
 }
 
@@ -209,6 +210,11 @@ int lqgk_set_streams(int n) {
 int lqgk_set_contrib_warps(int n) {
   if (n < 1) return LQGK_E_INVALID;
   g_contrib_warps = n;
+  return LQGK_OK;
+}
+int lqgk_set_warp_cov_max_samples(int n) {
+  if (n < 0) return LQGK_E_INVALID;
+  g_warp_cov_max_samples = n;
   return LQGK_OK;
 }
 int lqgk_set_kernel_overlap(int mask) {

@@ -101,7 +101,7 @@ struct ProfScope {
   } while (0)
 
 constexpr size_t ALIGN = 256;
-constexpr int WARP_COV_MAX_SAMPLES = 1024;   // calls with at most this many samples use the warp-per-sample covariance kernels
+extern thread_local int g_warp_cov_max_samples;   // calls with at most this many samples use the warp-per-sample covariance kernels
 inline size_t up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 inline bool spec_time_varying(const LqgkSpec& s, bool actor) {
@@ -360,7 +360,7 @@ int run(const Call& c) {
     // GPU idle and every step costs one thread's instruction stream; the warp-per-sample kernels of the large systems spread
     // a step over 32 lanes (S = 8: covariance forward 3.3 -> 2.4 ms, sequential adjoint 2.5 -> 1.0 ms) and win up to ~1,000
     // samples.  The Riccati / Kalman sweeps stay thread-per-sample (3 x 3 products do not spread), hence GAINS_MINOR.
-    const bool warp_cov = !tv && d.S <= WARP_COV_MAX_SAMPLES;
+    const bool warp_cov = !tv && d.S <= g_warp_cov_max_samples;
     const int wblk = (npad + BW_WARPS - 1) / BW_WARPS;
     if (warp_cov) {
       size_t smem = BigW<DM>::smem_fwd();

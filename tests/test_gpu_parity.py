@@ -61,11 +61,27 @@ def test_large_system_c4_full_horizon(lib, dev):
 
 @pytest.mark.parametrize("name,d,N", [("bounded", 2, 20), ("subjective", 2, 33), ("relobs", 2, 7), ("subjective2", 4, 40), ("pointmass", 2, 20),
                                       ("hand", 2, 20), ("delay2", 2, 20)])
-def test_more_than_1024_samples_use_the_thread_per_sample_covariance_kernels(lib, dev, name, d, N):
-    """Calls with at most 1,024 samples run the warp-per-sample covariance kernels (everything above in this file); larger
-    ones the thread-per-sample kernels with the TMA rings -- checked here against the same oracle (samples repeated)."""
+def test_many_samples_use_the_thread_per_sample_covariance_kernels(lib, dev, name, d, N):
+    """Calls with at most 512 samples (lqgk_set_warp_cov_max_samples) run the warp-per-sample covariance kernels (everything
+    above in this file); larger ones the thread-per-sample kernels with the TMA rings -- checked here against the same
+    oracle (samples repeated)."""
     case = H.Case(name, S=3, T=100, N=N, d=d, weights=True)
     H.check_vjp_tiled(lib, dev, case, reps=352)       # 1,056 systems
+
+
+def test_covariance_kernel_variants_agree(lib, dev):
+    """Same call with the threshold forced either way: thread-per-sample and warp-per-sample covariance kernels give the same
+    log-likelihoods and gradients (to FP64 rounding of the gradient accumulators)."""
+    case = H.Case("subjective", S=40, T=120, N=30, d=2, weights=True)
+    try:
+        lib.set_warp_cov_max_samples(0)
+        H.check_vjp(lib, dev, case, torch.float64)
+        H.check_fwd(lib, dev, case, torch.float32)
+        lib.set_warp_cov_max_samples(1 << 30)
+        H.check_vjp(lib, dev, case, torch.float64)
+        H.check_fwd(lib, dev, case, torch.float32)
+    finally:
+        lib.set_warp_cov_max_samples(512)
     case = H.Case("subjective2", S=70, T=60, N=12)
     H.check_vjp(lib, dev, case, torch.float32)                  # one chunk, 3 warps, padded
     H.check_vjp(lib, dev, case, torch.float32, max_chunk=32)    # three chunks
