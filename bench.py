@@ -188,6 +188,34 @@ def bench_c2(dev, reps=10):
     return len(sig) * N / (ms * 1e-3), ms
 
 
+def bench_c5(dev, chains=4096, N=100, T=1200, reps=5):
+    """Config c5 of BASELINE.json without numpyro (not installable): the work of ONE leapfrog step of 4,096 lock-step chains =
+    one fused log-likelihood + gradient evaluation of 4,096 parameter vectors on the c3 data, through the public API.
+    Returns (leapfrog-equivalents/s, ms per evaluation)."""
+    from lqg_b200.tracking import SubjectiveActor
+    x = make_data_gpu(N, T, dev)
+    theta = torch.tensor(make_theta(chains, 23), device=dev, requires_grad=True)
+
+    def evaluate():
+        theta.grad = None
+        m = SubjectiveActor(dim=2, T=T, device=dev, **{n: theta[:, i] for i, n in enumerate(PARAM_NAMES)})
+        ll = m.log_likelihood(x).sum()
+        ll.backward()
+        return ll
+
+    evaluate()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        ll = evaluate()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    assert torch.isfinite(ll) and torch.isfinite(theta.grad).all()
+    return 1e3 / ms, ms
+
+
 def bench_c4(dev, S=4096, N=50, T=600, reps=2):
     """Config c4 of BASELINE.json: TemporalDelayModel(PointMassBoundedActor(T=600), delay=2) -- 12-dim state, joint dim 24
     (large-system kernels, lqgk_big.cuh) --, 4,096 parameter samples x 50 trials, log-likelihood + gradient w.r.t. 4
@@ -460,12 +488,18 @@ def run_ours(args):
             secondary = {"workload": "c2: SubjectiveActor dim=2, 6 conditions x 20 trials x T=1200, grad wrt 5 shared + 6 per-condition "
                                      "parameters, one fused call through the public API (latency-bound: 6 systems)",
                          "value": c2_val, "unit": "trial-evals/s", "ms_per_eval": c2_ms}
+            c5_val, c5_ms = bench_c5(dev)
+            c5 = {"workload": "c5: one leapfrog of 4,096 lock-step chains = one fused log-lik+gradient of 4,096 parameter vectors x 100 trials x "
+                              "T=1200 on this GPU, public API (numpyro/NUTS itself is not installable here)",
+                  "value": c5_val, "unit": "leapfrog-equivalents/s", "ms_per_eval": c5_ms}
+            if args.no_c4:
+                secondary = [secondary, c5]
             if not args.no_c4:
                 c4_val, c4_ms, c4_k = bench_c4(dev)
                 secondary = [secondary,
                              {"workload": "c4: TemporalDelayModel(PointMassBoundedActor, delay=2) (x=b=12, joint dim 24), 4,096 parameter "
                                           "samples x 50 trials x T=600, grad wrt 4 parameters per sample, public API (large-system kernels)",
-                              "value": c4_val, "unit": "trial-evals/s", "ms_per_eval": c4_ms, "kernel_ms": c4_k}]
+                              "value": c4_val, "unit": "trial-evals/s", "ms_per_eval": c4_ms, "kernel_ms": c4_k}, c5]
         line = {"metric": "trial log-lik+grad evals/sec", "value": value, "unit": "trial-evals/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64 per-sample recursions + f32 per-trial recursions (f32 I/O)",
