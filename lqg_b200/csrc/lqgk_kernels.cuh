@@ -773,13 +773,13 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS, trial_min_ctas<DM>()) k_tria
           LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) {
             if (ok[2 * p2 + 1]) {   // pair entry in one 64-bit store, straight from the f32x2 register pair
               LQGK_UNROLL for (int m = 0; m < R; ++m)
-                *reinterpret_cast<float2*>(hrow(m) + 64 * p2) = make_float2(cP[p2][m].x, cP[p2][m].y);
+                __stcs(reinterpret_cast<float2*>(hrow(m) + 64 * p2), make_float2(cP[p2][m].x, cP[p2][m].y));   // streaming: written once, read once
             } else if (ok[2 * p2]) {   // odd N: the pad element gets 0
-              LQGK_UNROLL for (int m = 0; m < R; ++m) *reinterpret_cast<float2*>(hrow(m) + 64 * p2) = make_float2(cP[p2][m].x, 0.f);
+              LQGK_UNROLL for (int m = 0; m < R; ++m) __stcs(reinterpret_cast<float2*>(hrow(m) + 64 * p2), make_float2(cP[p2][m].x, 0.f));
             }
           }
           if constexpr (NS) {
-            if (ok[RT - 1]) { LQGK_UNROLL for (int m = 0; m < R; ++m) hrow(m)[hsingle] = cS[m]; }
+            if (ok[RT - 1]) { LQGK_UNROLL for (int m = 0; m < R; ++m) __stcs(hrow(m) + hsingle, cS[m]); }
           }
           LQGK_UNROLL for (int m = 0; m < NHP; ++m) hw[m] += hstep;
         }
@@ -877,10 +877,10 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __r
     const int hstep = R * Nh, hsingle = 64 * NP - lane;
     auto load_hist = [&](f32x2 (&cp)[NPA][R], float (&cs)[R]) {
       LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) LQGK_UNROLL for (int m = 0; m < R; ++m) {
-        float2 v = okP[p2] ? __ldg(reinterpret_cast<const float2*>(hrow(m) + 64 * p2)) : make_float2(0.f, 0.f);
+        float2 v = okP[p2] ? __ldcs(reinterpret_cast<const float2*>(hrow(m) + 64 * p2)) : make_float2(0.f, 0.f);   // streaming
         cp[p2][m] = f32x2{v.x, v.y};
       }
-      if constexpr (NS) { LQGK_UNROLL for (int m = 0; m < R; ++m) cs[m] = okS ? __ldg(hrow(m) + hsingle) : 0.f; }
+      if constexpr (NS) { LQGK_UNROLL for (int m = 0; m < R; ++m) cs[m] = okS ? __ldcs(hrow(m) + hsingle) : 0.f; }
     };
     // persistent state: cotangent cb, x_{t+1}; prefetched (x_t, c_t) of the next step to process
     f32x2 cbP[NPA][R], x1P[NPA][D], wP[NPA];
