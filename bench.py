@@ -483,7 +483,7 @@ def run_ours(args):
                    "sample": f"{args.cpu_samples} parameter samples x {N} trials x T={T}, one fwd+grad eval by torch-float64 "
                              f"autograd over the oracle's restatement of the reference scans ({sec:.1f} s)"}
         secondary = None
-        if world == 1:
+        if world == 1 and not args.no_secondary:
             c2_val, c2_ms = bench_c2(dev)
             secondary = {"workload": "c2: SubjectiveActor dim=2, 6 conditions x 20 trials x T=1200, grad wrt 5 shared + 6 per-condition "
                                      "parameters, one fused call through the public API (latency-bound: 6 systems)",
@@ -558,6 +558,7 @@ def main():
     ap.add_argument("--cpu-samples", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c4", action="store_true", help="skip the secondary c4 (large-system) measurement")
+    ap.add_argument("--no-secondary", action="store_true", help="skip all secondary workloads (c2, c4, c5)")
     ap.add_argument("--streams", type=int, default=0, help="internal concurrent sample slices (0 = library default)")
     ap.add_argument("--contrib-warps", type=int, default=0)
     ap.add_argument("--overlap", type=int, default=-1, help="kernel-overlap mask (see lqgk_set_kernel_overlap); -1 = library default")

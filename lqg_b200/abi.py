@@ -15,7 +15,7 @@ from typing import Dict, Optional
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "liblqgk.so")
+LIB_PATH = os.environ.get("LQGK_LIB_PATH") or os.path.join(HERE, "csrc", "liblqgk.so")   # override: tuning experiments (tools/)
 
 MODE_GAINS, MODE_FWD, MODE_VJP = 0, 1, 2
 ACTOR_KEYS = ("A", "B", "F", "V", "W", "Q", "R")

@@ -35,7 +35,10 @@ int validate(const Call& c) {
     for (auto m : need)
       if (!m->ptr) return LQGK_E_INVALID;
     if (((uintptr_t)c.x_tm % 16) != 0) return LQGK_E_INVALID;
-    if (d.x_sample_stride < 0 || (d.x_sample_stride * sizeof(float)) % 16 != 0) return LQGK_E_INVALID;
+    // per-sample data sets: every sample's block must keep the alignment of the kernels' observation accesses (one d-float
+    // vector per trial: 16 bytes when d % 4 == 0, 8 when d % 2 == 0, else scalar loads)
+    const size_t xalign = d.d % 4 == 0 ? 16 : (d.d % 2 == 0 ? 8 : 4);
+    if (d.x_sample_stride < 0 || (d.x_sample_stride * sizeof(float)) % xalign != 0) return LQGK_E_INVALID;
   }
   return LQGK_OK;
 }

@@ -658,15 +658,11 @@ struct Trial {
       z[i] = a;
     }
   }
-  // forward step; returns this step's log-density term
+  // c <- F[u,o] x0 + F[u,u] c + J e   (the carried conditional mean of the unobserved block)
   template <class S, class Rec>
-  LQGK_HD static S fwd(const Rec& rec, const S* x0, const S* x1, S* c) {
+  LQGK_HD static void update(const Rec& rec, const S* x0, const S* e, S* c) {
     using O = Ops<S>;
-    S e[D], z[D], cn[R];
-    residual<S>(rec, x0, x1, c, e);
-    whiten<S>(rec, e, z);
-    S qf = O::zero();
-    LQGK_UNROLL for (int i = 0; i < D; ++i) qf = O::fma(z[i], z[i], qf);
+    S cn[R];
     LQGK_UNROLL for (int i = 0; i < R; ++i) {
       S a = O::zero();
       LQGK_UNROLL for (int j = 0; j < D; ++j) a = O::fma(O::bc(rec[DM::REC_F + (D + i) * N + j]), x0[j], a);
@@ -675,7 +671,26 @@ struct Trial {
       cn[i] = a;
     }
     LQGK_UNROLL for (int i = 0; i < R; ++i) c[i] = cn[i];
+  }
+  // forward step; returns this step's log-density term
+  template <class S, class Rec>
+  LQGK_HD static S fwd(const Rec& rec, const S* x0, const S* x1, S* c) {
+    using O = Ops<S>;
+    S e[D], z[D];
+    residual<S>(rec, x0, x1, c, e);
+    whiten<S>(rec, e, z);
+    S qf = O::zero();
+    LQGK_UNROLL for (int i = 0; i < D; ++i) qf = O::fma(z[i], z[i], qf);
+    update<S>(rec, x0, e, c);
     return O::fma(O::bc(-0.5f), qf, O::bc(-rec[DM::REC_LOGDET] - HALF_LOG2PI_D));
+  }
+  // state-only forward step (no log-density): what the adjoint kernel re-runs between two checkpoints of c.  Same
+  // operation sequence as fwd(), so the recomputed states are bit-identical to the ones the forward pass carried.
+  template <class S, class Rec>
+  LQGK_HD static void advance(const Rec& rec, const S* x0, const S* x1, S* c) {
+    S e[D];
+    residual<S>(rec, x0, x1, c, e);
+    update<S>(rec, x0, e, c);
   }
   // reverse step: given c (= c_t), x0 = x_t, x1 = x_{t+1}, weight w and the incoming cotangent cb (of c_{t+1});
   // produces e, v = S'^-1 e, wv = w v, eb = J^T cb - w v, neb = -eb and the outgoing cotangent

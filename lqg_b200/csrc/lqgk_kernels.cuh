@@ -573,27 +573,69 @@ __device__ __forceinline__ void load_obs(const float* __restrict__ p, float* out
 
 // Resident CTAs per SM the forward per-trial kernel is compiled for: the small systems are latency-bound at 2 CTAs (8 warps)
 // per SM, so the register budget is capped at 65536 / (3 * 128) = 170 to fit 3 (no spills: 204 -> 164 registers, -5 % time).
-// The adjoint kernel needs 240 registers; capped at 170 it spills and runs 1.6x slower (measured), so it stays at 2 CTAs.
+// The adjoint kernel needs ~240 registers; capped at 170 it spills and runs 1.6x slower (measured), so it stays at 2 CTAs.
 template <class DM>
 __host__ __device__ constexpr int trial_min_ctas() { return DM::N <= 6 ? 3 : 1; }
 constexpr int TRIAL_WARPS = 4;   // warps (= samples) per CTA
-// time steps per ring stage: 8 for the small records, fewer when one record is KBs (large systems)
+// time steps per ring stage of the forward kernel: 8 for the small records, fewer when one record is KBs (large systems)
 template <class DM>
 __host__ __device__ constexpr int trial_tb() { return DM::REC <= 128 ? 8 : (DM::REC <= 256 ? 4 : 2); }
-constexpr int TRIAL_NST = 3;     // ring stages
+constexpr int TRIAL_NST = 3;     // ring stages of the forward kernel
 
-constexpr int TRIAL_PF = 4;      // observation / state prefetch distance in time steps (cp.async groups in flight)
+constexpr int TRIAL_PF = 4;      // observation prefetch distance in time steps (cp.async groups in flight)
 // Sums over trials in the adjoint: every lane holds 32 partial values; they are transposed through shared memory (lane L
 // writes its 32 values as 8 x 128-bit stores into row L of a [32][36] tile -- conflict-free per quarter warp --, then sums
 // column L: 32 conflict-free loads) instead of a 31-shuffle butterfly with 62 selects.
 constexpr int TRIAL_RED_STRIDE = 36;
-// Per-lane prefetch slots: [TRIAL_PF + 1][RT][W floats][32 lanes] per warp.
+
+// ------------------------------------------------------------------------------------------- checkpointed state history
+// The adjoint needs the carried mean c_t of every trial at every step.  Storing all of them (T x R x N floats per sample,
+// 2.9 MB at the benchmark size) made the forward kernel HBM-bound and was 70 % of the step's DRAM traffic (round 1).  Now the
+// forward kernel stores c_t only at the segment starts t = k * CK ("checkpoints"); the adjoint kernel processes one segment at
+// a time: it re-runs the state recursion from the checkpoint (Trial::advance, CK - 1 steps, bit-identical to the forward pass)
+// into a per-warp shared-memory buffer [CK][R][32 RT] and then walks the segment backwards reading c_t from that buffer.
+// CK is the largest interval whose buffer + record ring fits the per-warp share of shared memory that keeps 2 CTAs (8 warps)
+// resident per SM.
+#ifndef LQGK_TRIAL_CK_MAX
+#define LQGK_TRIAL_CK_MAX 8
+#endif
+constexpr int TRIAL_CK_MAX = LQGK_TRIAL_CK_MAX;
+#ifndef LQGK_TRIAL_WARP_SMEM
+#define LQGK_TRIAL_WARP_SMEM 28440    // bytes per warp: 2 CTAs x 4 warps x 28,440 B + 2 KB reserved < 228 KB per SM
+#endif
+template <class DM>
+__host__ __device__ constexpr int trial_red_bytes() { return DM::NSUM >= 32 ? 32 * TRIAL_RED_STRIDE * (int)sizeof(float) : 0; }
+template <class DM>
+__host__ __device__ constexpr int trial_ck(int RT) {
+  const int per_step = 2 * DM::REC * (int)sizeof(float) + DM::R * 32 * RT * (int)sizeof(float);   // 2 ring stages + 1 state slot
+  const int ck = (LQGK_TRIAL_WARP_SMEM - trial_red_bytes<DM>() - 16) / per_step;
+  return ck < 1 ? 1 : (ck > TRIAL_CK_MAX ? TRIAL_CK_MAX : ck);
+}
+// Largest number of trials one lane carries: small systems leave room for 8 (amortises the broadcast record loads and
+// the cross-lane reductions over more FMAs), large ones for 4.
+template <class DM>
+__host__ __device__ constexpr int trial_rt_max() { return DM::N * DM::N <= 36 ? 8 : 4; }
+__host__ __device__ __forceinline__ constexpr int trial_rt(int N, int rt_max) { return (N + 31) / 32 < rt_max ? (N + 31) / 32 : rt_max; }
+// Row stride of the checkpoints [s][segment][R][hist_stride(N)]: even, so a pair's entry is 8-byte aligned.  The forward
+// kernel stores 0 into the pad element of an odd N; the adjoint reads pairs whenever the first half is a real trial.
+__host__ __device__ __forceinline__ constexpr int hist_stride(int N) { return (N + 1) & ~1; }
+template <class DM>
+__host__ __device__ constexpr int trial_nseg(int N, int T) {
+  const int ck = trial_ck<DM>(trial_rt(N, trial_rt_max<DM>()));
+  return (T + ck - 1) / ck;
+}
+
 template <class DM, int RT, bool REV>
 constexpr size_t trial_smem_bytes() {
-  size_t ring = (size_t)TRIAL_WARPS * TRIAL_NST * trial_tb<DM>() * DM::REC * sizeof(float) + TRIAL_WARPS * TRIAL_NST * sizeof(uint64_t);
-  size_t pf = REV ? 0 : (size_t)TRIAL_WARPS * (TRIAL_PF + 1) * RT * 32 * DM::D * sizeof(float);   // forward only
-  size_t red = REV && DM::NSUM >= 32 ? (size_t)TRIAL_WARPS * 32 * TRIAL_RED_STRIDE * sizeof(float) : 0;   // adjoint: sum transposition
-  return ring + pf + red;
+  if constexpr (REV) {
+    constexpr int CK = trial_ck<DM>(RT);
+    return (size_t)TRIAL_WARPS * (2 * CK * DM::REC * sizeof(float) + 2 * sizeof(uint64_t) + trial_red_bytes<DM>() +
+                                  (size_t)CK * DM::R * 32 * RT * sizeof(float));
+  } else {
+    size_t ring = (size_t)TRIAL_WARPS * TRIAL_NST * trial_tb<DM>() * DM::REC * sizeof(float) + TRIAL_WARPS * TRIAL_NST * sizeof(uint64_t);
+    size_t pf = (size_t)TRIAL_WARPS * (TRIAL_PF + 1) * RT * 32 * DM::D * sizeof(float);
+    return ring + pf;
+  }
 }
 // observation x[t][trial][0..D) -> this lane's slot (vector copy of D floats, D*4 in {4, 8, 16} bytes, else scalars)
 template <int D>
@@ -603,22 +645,29 @@ __device__ __forceinline__ void prefetch_obs(float* slot, int lane, const float*
 }
 template <int D>
 __device__ __forceinline__ void read_obs(const float* slot, int lane, float* out) {
-  if constexpr (D == 1 || D == 2 || D == 4) { LQGK_UNROLL for (int k = 0; k < D; ++k) out[k] = slot[lane * D + k]; }
-  else { LQGK_UNROLL for (int k = 0; k < D; ++k) out[k] = slot[k * 32 + lane]; }
+  if constexpr (D == 2) {          // one 64-bit access per lane (scalar reads at stride 2 are 2-way bank conflicts)
+    float2 v = *reinterpret_cast<const float2*>(slot + lane * 2);
+    out[0] = v.x; out[1] = v.y;
+  } else if constexpr (D == 4) {
+    float4 v = *reinterpret_cast<const float4*>(slot + lane * 4);
+    out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+  } else if constexpr (D == 1) {
+    out[0] = slot[lane];
+  } else { LQGK_UNROLL for (int k = 0; k < D; ++k) out[k] = slot[k * 32 + lane]; }
 }
 
-// Per-warp ring of record chunks filled by bulk async copies.  Chunk k covers steps [k*TB, min(T,(k+1)*TB)).
-// `forward` walks chunks 0..nchunk-1, otherwise nchunk-1..0.
-template <class DM>
+// Per-warp ring of NST record chunks of TB time steps, filled by bulk async copies.  Chunk k covers steps
+// [k*TB, min(T,(k+1)*TB)).
+template <class DM, int TB, int NST>
 struct RecRing {
   float* buf;        // [NST][TB*REC]
   uint64_t* bars;    // [NST]
   const float* src;  // this sample's records [Tn][REC]
-  int Tn, nchunk, lane;
+  int Tn, lane;
   uint32_t phase_bits;
   __device__ __forceinline__ void init() {
     if (lane == 0) {
-      for (int i = 0; i < TRIAL_NST; ++i) mbar_init(&bars[i], 1);
+      for (int i = 0; i < NST; ++i) mbar_init(&bars[i], 1);
       fence_mbar_init();
     }
     phase_bits = 0;
@@ -627,23 +676,23 @@ struct RecRing {
   // issue the copy of chunk `k` into stage `st` (lane 0 only; caller guarantees the stage is no longer read)
   __device__ __forceinline__ void issue(int k, int st) {
     if (lane == 0) {
-      int t0 = k * trial_tb<DM>();
-      int nst = min(trial_tb<DM>(), Tn - t0);
+      int t0 = k * TB;
+      int nst = min(TB, Tn - t0);
       uint32_t bytes = (uint32_t)nst * DM::REC * sizeof(float);
       fence_proxy_async();
       mbar_expect_tx(&bars[st], bytes);
-      bulk_g2s(buf + (size_t)st * trial_tb<DM>() * DM::REC, src + (size_t)t0 * DM::REC, bytes, &bars[st]);
+      bulk_g2s(buf + (size_t)st * TB * DM::REC, src + (size_t)t0 * DM::REC, bytes, &bars[st]);
     }
   }
   __device__ __forceinline__ const float* wait(int st) {
     mbar_wait(&bars[st], (phase_bits >> st) & 1u);
     phase_bits ^= (1u << st);
-    return buf + (size_t)st * trial_tb<DM>() * DM::REC;
+    return buf + (size_t)st * TB * DM::REC;
   }
 };
 
 // Trial -> lane assignment of one pass (32*RT trials starting at `base`): pair p of a lane holds the ADJACENT trials
-// base + 64p + 2*lane and +1, so one 64-bit access moves the pair's entry of the state history, already in f32x2 register
+// base + 64p + 2*lane and +1, so one 64-bit access moves the pair's entry of a checkpoint, already in f32x2 register
 // order (no packing moves, half the memory instructions); an odd RT adds the single trial base + 64*(RT/2) + lane.
 // Flat slot j: 2p, 2p+1 = the two halves of pair p; RT-1 = the single.
 template <int RT>
@@ -651,14 +700,6 @@ __device__ __forceinline__ int trial_of(int base, int lane, int j) {
   constexpr int NP = RT / 2;
   return j < 2 * NP ? base + 64 * (j >> 1) + 2 * lane + (j & 1) : base + 64 * NP + lane;
 }
-// Row stride of the state history [s][t][R][hist_stride(N)]: even, so a pair's entry is 8-byte aligned.  The forward
-// kernel stores 0 into the pad element of an odd N; the adjoint reads pairs whenever the first half is a real trial.
-__host__ __device__ __forceinline__ constexpr int hist_stride(int N) { return (N + 1) & ~1; }
-
-// Largest number of trials one lane carries: small systems leave room for 8 (amortises the broadcast record loads and
-// the cross-lane reductions over more FMAs), large ones for 4.
-template <class DM>
-__host__ __device__ constexpr int trial_rt_max() { return DM::N * DM::N <= 36 ? 8 : 4; }
 
 // Copy one step's record from the shared-memory ring into registers (small systems) with 128-bit broadcast loads.
 template <class DM>
@@ -677,28 +718,29 @@ template <class DM>
 __host__ __device__ constexpr bool rec_in_regs() { return DM::REC <= 48; }
 
 // Forward: per-trial mean recursion + log-density.  grid = (ceil(n_samples / TRIAL_WARPS)), block = 32 * TRIAL_WARPS.
-// Trials are processed in passes of 32*RT (lane owns trials base + lane + 32*j, j < RT).  Observations are prefetched
+// Trials are processed in passes of 32*RT (lane owns the trials trial_of(base, lane, j), j < RT).  Observations are prefetched
 // TRIAL_PF steps ahead with per-lane cp.async copies into shared-memory slots (no registers held, no stalls on the
-// L2 round trip).
+// L2 round trip).  `hist` (VJP only): checkpoints of the carried state at the segment starts, [s][segment][R][hist_stride(N)].
 template <class DM, int RT>
 __global__ void __launch_bounds__(32 * TRIAL_WARPS, trial_min_ctas<DM>()) k_trial_fwd(const float* __restrict__ rec, const float* __restrict__ x_all,
                                                                 size_t x_sample_stride, int s_first, int n_samples, int N, int Tn,
                                                                 double* __restrict__ ll_ws, float* __restrict__ hist) {
-  constexpr int D = DM::D, R = DM::R, NSLOT = TRIAL_PF + 1;
+  constexpr int D = DM::D, R = DM::R, NSLOT = TRIAL_PF + 1, TB = trial_tb<DM>(), CK = trial_ck<DM>(RT);
   extern __shared__ __align__(128) unsigned char smraw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = blockIdx.x * TRIAL_WARPS + warp;
   if (s >= n_samples) return;
   const float* __restrict__ x_tm = x_all + (size_t)(s_first + s) * x_sample_stride;   // this sample's observations
-  constexpr size_t RING_BYTES = (size_t)TRIAL_WARPS * TRIAL_NST * trial_tb<DM>() * DM::REC * sizeof(float);
+  constexpr size_t RING_BYTES = (size_t)TRIAL_WARPS * TRIAL_NST * TB * DM::REC * sizeof(float);
   float* ring_base = reinterpret_cast<float*>(smraw);
   uint64_t* bar_base = reinterpret_cast<uint64_t*>(smraw + RING_BYTES);
   float* pf = reinterpret_cast<float*>(smraw + RING_BYTES + TRIAL_WARPS * TRIAL_NST * sizeof(uint64_t)) + (size_t)warp * NSLOT * RT * 32 * D;
-  RecRing<DM> ring{ring_base + (size_t)warp * TRIAL_NST * trial_tb<DM>() * DM::REC, bar_base + warp * TRIAL_NST,
-                   rec + (size_t)s * Tn * DM::REC, Tn, (Tn + trial_tb<DM>() - 1) / trial_tb<DM>(), lane, 0};
+  RecRing<DM, TB, TRIAL_NST> ring{ring_base + (size_t)warp * TRIAL_NST * TB * DM::REC, bar_base + warp * TRIAL_NST,
+                                  rec + (size_t)s * Tn * DM::REC, Tn, lane, 0};
   ring.init();
-  const int nchunk = ring.nchunk;
+  const int nchunk = (Tn + TB - 1) / TB;
   const int Nh = hist_stride(N);
+  const int nseg = (Tn + CK - 1) / CK;
   for (int base = 0; base < N; base += 32 * RT) {
     int tr[RT], trD[RT];
     bool ok[RT];
@@ -708,14 +750,15 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS, trial_min_ctas<DM>()) k_tria
       tr[j] = ok[j] ? i : N - 1;
       trD[j] = tr[j] * D;            // 32-bit element offsets: one 64-bit row pointer per step + cheap lane offsets
     }
-    // state-history row pointers of this lane (one per state component), advanced by one step per iteration
+    // checkpoint row pointers of this lane (one per state component), advanced by one segment per stored checkpoint
     // (small systems: one pointer per component -> every access is pointer + immediate; large ones: one pointer + m * Nh)
     constexpr bool HPTRS = R <= 6;
     constexpr int NHP = HPTRS ? R : 1;
     float* hw[NHP];
-    LQGK_UNROLL for (int m = 0; m < NHP; ++m) hw[m] = hist + ((size_t)s * Tn * R + m) * Nh + (base + 2 * lane);
+    LQGK_UNROLL for (int m = 0; m < NHP; ++m) hw[m] = hist + ((size_t)s * nseg * R + m) * Nh + (base + 2 * lane);
     auto hrow = [&](int m) -> float* { if constexpr (HPTRS) return hw[m]; else return hw[0] + m * Nh; };
     const int hstep = R * Nh, hsingle = 64 * (RT / 2) - lane;
+    int ckc = 0;                     // steps until the next checkpoint
     // trials 2p, 2p+1 are packed into one f32x2 lane-pair state (Blackwell FFMA2); an odd last trial stays scalar
     constexpr int NP = RT / 2, NS = RT % 2;
     f32x2 cP[NP > 0 ? NP : 1][R], x0P[NP > 0 ? NP : 1][D];
@@ -744,7 +787,7 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS, trial_min_ctas<DM>()) k_tria
     for (int k = 0; k < nchunk; ++k) {
       const int st = k % TRIAL_NST;
       const float* chunk = ring.wait(st);
-      const int t0 = k * trial_tb<DM>(), nst = min(trial_tb<DM>(), Tn - t0);
+      const int t0 = k * TB, nst = min(TB, Tn - t0);
       f32x2 partP[NP > 0 ? NP : 1];
       float partS = 0.f;
       LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) partP[p2] = f32x2{0.f, 0.f};
@@ -770,18 +813,22 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS, trial_min_ctas<DM>()) k_tria
           if constexpr (NS) read_obs<D>(cur + (RT - 1) * 32 * D, lane, x1S);
         }
         if (hist != nullptr) {
-          LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) {
-            if (ok[2 * p2 + 1]) {   // pair entry in one 64-bit store, straight from the f32x2 register pair
-              LQGK_UNROLL for (int m = 0; m < R; ++m)
-                __stcs(reinterpret_cast<float2*>(hrow(m) + 64 * p2), make_float2(cP[p2][m].x, cP[p2][m].y));   // streaming: written once, read once
-            } else if (ok[2 * p2]) {   // odd N: the pad element gets 0
-              LQGK_UNROLL for (int m = 0; m < R; ++m) __stcs(reinterpret_cast<float2*>(hrow(m) + 64 * p2), make_float2(cP[p2][m].x, 0.f));
+          if (ckc == 0) {            // t is a segment start: store the checkpoint c_t
+            ckc = CK;
+            LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) {
+              if (ok[2 * p2 + 1]) {   // pair entry in one 64-bit store, straight from the f32x2 register pair
+                LQGK_UNROLL for (int m = 0; m < R; ++m)
+                  __stcs(reinterpret_cast<float2*>(hrow(m) + 64 * p2), make_float2(cP[p2][m].x, cP[p2][m].y));   // streaming: written once, read once
+              } else if (ok[2 * p2]) {   // odd N: the pad element gets 0
+                LQGK_UNROLL for (int m = 0; m < R; ++m) __stcs(reinterpret_cast<float2*>(hrow(m) + 64 * p2), make_float2(cP[p2][m].x, 0.f));
+              }
             }
+            if constexpr (NS) {
+              if (ok[RT - 1]) { LQGK_UNROLL for (int m = 0; m < R; ++m) __stcs(hrow(m) + hsingle, cS[m]); }
+            }
+            LQGK_UNROLL for (int m = 0; m < NHP; ++m) hw[m] += hstep;
           }
-          if constexpr (NS) {
-            if (ok[RT - 1]) { LQGK_UNROLL for (int m = 0; m < R; ++m) __stcs(hrow(m) + hsingle, cS[m]); }
-          }
-          LQGK_UNROLL for (int m = 0; m < NHP; ++m) hw[m] += hstep;
+          --ckc;
         }
         auto run = [&](const auto& rr) {
           LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2)
@@ -798,7 +845,7 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS, trial_min_ctas<DM>()) k_tria
         LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) LQGK_UNROLL for (int m = 0; m < D; ++m) x0P[p2][m] = x1P[p2][m];
         if constexpr (NS) { LQGK_UNROLL for (int m = 0; m < D; ++m) x0S[m] = x1S[m]; }
       }
-      // FP32 partial sum over <= trial_tb<DM>() steps, FP64 across chunks (log-likelihood error ~1e-7 relative)
+      // FP32 partial sum over <= TB steps, FP64 across chunks (log-likelihood error ~1e-7 relative)
       LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) {
         ll[2 * p2] += (double)partP[p2].x;
         ll[2 * p2 + 1] += (double)partP[p2].y;
@@ -833,30 +880,37 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&val)[V], int lane
 }
 __host__ __device__ constexpr int pow2_ceil(int v) { return v <= 1 ? 1 : (v <= 2 ? 2 : (v <= 4 ? 4 : (v <= 8 ? 8 : (v <= 16 ? 16 : 32)))); }
 
-// Reverse: per-trial adjoint, t = T-1..0, plus the per-step sums over trials (DM::SUM_* layout) written to
-// sums[s][t][SUMP].  Passes over trial blocks accumulate (+=) into the sums.
+// Reverse: per-trial adjoint, segment by segment from the last one: (1) the checkpoint c_{k CK} arrives in the segment
+// buffer by per-lane cp.async (issued one segment ahead into the slot the previous segment freed first), (2) the state
+// recursion is re-run forward through the segment, c_t -> buffer slot t - k CK, (3) the adjoint walks the segment backwards
+// reading c_t from the buffer, and writes the per-step sums over trials (DM::SUM_* layout) to sums[s][t][SUMP].  Every buffer
+// entry is private to the lane that owns the trial, so no warp synchronisation is needed around it.  Passes over trial blocks
+// accumulate (+=) into the sums.
 template <class DM, int RT>
 __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __restrict__ rec, const float* __restrict__ x_all,
                                                                 size_t x_sample_stride, int s_first, const float* __restrict__ hist,
                                                                 const float* __restrict__ w, int n_samples, int N, int Tn,
                                                                 float* __restrict__ sums) {
   constexpr int D = DM::D, R = DM::R;
+  constexpr int CK = trial_ck<DM>(RT), ROW = 32 * RT, SLOT = R * ROW;
   constexpr int NFULL = DM::NSUM / 32, REM = DM::NSUM % 32, VREM = pow2_ceil(REM);
+  constexpr int NP = RT / 2, NS = RT % 2, NPA = NP > 0 ? NP : 1;
   extern __shared__ __align__(128) unsigned char smraw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = blockIdx.x * TRIAL_WARPS + warp;
   if (s >= n_samples) return;
   const float* __restrict__ x_tm = x_all + (size_t)(s_first + s) * x_sample_stride;   // this sample's observations
+  constexpr size_t RING_FLOATS = (size_t)2 * CK * DM::REC;
   float* ring_base = reinterpret_cast<float*>(smraw);
-  uint64_t* bar_base = reinterpret_cast<uint64_t*>(smraw + (size_t)TRIAL_WARPS * TRIAL_NST * trial_tb<DM>() * DM::REC * sizeof(float));
-  float* red = reinterpret_cast<float*>(bar_base + TRIAL_WARPS * TRIAL_NST) + (size_t)warp * 32 * TRIAL_RED_STRIDE;   // 16-byte aligned
-  RecRing<DM> ring{ring_base + (size_t)warp * TRIAL_NST * trial_tb<DM>() * DM::REC, bar_base + warp * TRIAL_NST,
-                   rec + (size_t)s * Tn * DM::REC, Tn, (Tn + trial_tb<DM>() - 1) / trial_tb<DM>(), lane, 0};
+  uint64_t* bar_base = reinterpret_cast<uint64_t*>(ring_base + TRIAL_WARPS * RING_FLOATS);
+  float* red_base = reinterpret_cast<float*>(bar_base + TRIAL_WARPS * 2);                     // 16-byte aligned
+  float* red = red_base + (size_t)warp * (trial_red_bytes<DM>() / sizeof(float));
+  float* seg = red_base + (size_t)TRIAL_WARPS * (trial_red_bytes<DM>() / sizeof(float)) + (size_t)warp * CK * SLOT;
+  RecRing<DM, CK, 2> ring{ring_base + (size_t)warp * RING_FLOATS, bar_base + warp * 2, rec + (size_t)s * Tn * DM::REC, Tn, lane, 0};
   ring.init();
-  const int nchunk = ring.nchunk;
+  const int nseg = (Tn + CK - 1) / CK;
   const int Nh = hist_stride(N);
   for (int base = 0; base < N; base += 32 * RT) {
-    constexpr int NP = RT / 2, NS = RT % 2, NPA = NP > 0 ? NP : 1;
     int trD[RT];
     float wt[RT];
     bool okP[NPA], okS = false;
@@ -864,35 +918,51 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __r
       int i = trial_of<RT>(base, lane, j);
       bool ok = i < N;
       int tr = ok ? i : N - 1;
-      trD[j] = tr * D;
-      wt[j] = ok ? w[(size_t)s * N + tr] : 0.f;   // masked trials contribute nothing (c = 0, cb stays 0, w = 0)
+      trD[j] = tr * D;                            // slots beyond the last trial re-read trial N-1 (finite; masked by w = 0, cb = 0)
+      wt[j] = ok ? w[(size_t)s * N + tr] : 0.f;
       if (j < 2 * NP) { if ((j & 1) == 0) okP[j >> 1] = ok; } else okS = ok;
     }
-    // state-history row pointers of this lane (one per state component), walked backwards one step per iteration
-    constexpr bool HPTRS = R <= 6;
-    constexpr int NHP = HPTRS ? R : 1;
-    const float* hr[NHP];
-    LQGK_UNROLL for (int m = 0; m < NHP; ++m) hr[m] = hist + (((size_t)s * Tn + (Tn - 1)) * R + m) * Nh + (base + 2 * lane);
-    auto hrow = [&](int m) -> const float* { if constexpr (HPTRS) return hr[m]; else return hr[0] + m * Nh; };
-    const int hstep = R * Nh, hsingle = 64 * NP - lane;
-    auto load_hist = [&](f32x2 (&cp)[NPA][R], float (&cs)[R]) {
+    auto load_x = [&](int t, float (&x)[RT][D]) {
+      const float* xrow = x_tm + (size_t)t * N * D;
+      LQGK_UNROLL for (int j = 0; j < RT; ++j) load_obs<D>(xrow + trD[j], x[j]);
+    };
+    // this lane's entries of one buffer slot / one checkpoint: pair p at [m][64 p + 2 lane], the single at [m][64 NP + lane]
+    const int lofs = 2 * lane, sofs = 64 * NP + lane;
+    auto fetch_ckpt = [&](float* slot, const float* hk) {   // hk = hist + ((s * nseg + k) * R) * Nh + base
       LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) LQGK_UNROLL for (int m = 0; m < R; ++m) {
-        float2 v = okP[p2] ? __ldcs(reinterpret_cast<const float2*>(hrow(m) + 64 * p2)) : make_float2(0.f, 0.f);   // streaming
+        float* dst = slot + m * ROW + 64 * p2 + lofs;
+        if (okP[p2]) cp_async<8>(dst, hk + (size_t)m * Nh + 64 * p2 + lofs);
+        else *reinterpret_cast<float2*>(dst) = make_float2(0.f, 0.f);
+      }
+      if constexpr (NS) {
+        LQGK_UNROLL for (int m = 0; m < R; ++m) {
+          float* dst = slot + m * ROW + sofs;
+          if (okS) cp_async<4>(dst, hk + (size_t)m * Nh + sofs);
+          else *dst = 0.f;
+        }
+      }
+      cp_async_commit();
+    };
+    auto load_slot = [&](const float* slot, f32x2 (&cp)[NPA][R], float (&cs)[R]) {
+      LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) LQGK_UNROLL for (int m = 0; m < R; ++m) {
+        float2 v = *reinterpret_cast<const float2*>(slot + m * ROW + 64 * p2 + lofs);
         cp[p2][m] = f32x2{v.x, v.y};
       }
-      if constexpr (NS) { LQGK_UNROLL for (int m = 0; m < R; ++m) cs[m] = okS ? __ldcs(hrow(m) + hsingle) : 0.f; }
+      if constexpr (NS) { LQGK_UNROLL for (int m = 0; m < R; ++m) cs[m] = slot[m * ROW + sofs]; }
     };
-    // persistent state: cotangent cb, x_{t+1}; prefetched (x_t, c_t) of the next step to process
+    auto store_slot = [&](float* slot, const f32x2 (&cp)[NPA][R], const float (&cs)[R]) {
+      LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) LQGK_UNROLL for (int m = 0; m < R; ++m)
+        *reinterpret_cast<float2*>(slot + m * ROW + 64 * p2 + lofs) = make_float2(cp[p2][m].x, cp[p2][m].y);
+      if constexpr (NS) { LQGK_UNROLL for (int m = 0; m < R; ++m) slot[m * ROW + sofs] = cs[m]; }
+    };
+    auto next_slot = [&](float* p) { p += SLOT; return p == seg + CK * SLOT ? seg : p; };
+    auto prev_slot = [&](float* p) { return (p == seg ? seg + CK * SLOT : p) - SLOT; };
+    // persistent state: cotangent cb of c_{t+1}, x_{t+1}, weights
     f32x2 cbP[NPA][R], x1P[NPA][D], wP[NPA];
     float cbS[R], x1S[D], wS = wt[RT - 1];
-    float x0n[RT][D];                      // "next" = values for the step about to be processed
-    f32x2 cnP[NPA][R];
-    float cnS[R];
-    LQGK_UNROLL for (int j = 0; j < RT; ++j) load_obs<D>(x_tm + (size_t)(Tn - 1) * N * D + trD[j], x0n[j]);
-    load_hist(cnP, cnS);
     {
       float x1[RT][D];
-      LQGK_UNROLL for (int j = 0; j < RT; ++j) load_obs<D>(x_tm + (size_t)Tn * N * D + trD[j], x1[j]);
+      load_x(Tn, x1);
       LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) {
         LQGK_UNROLL for (int k = 0; k < R; ++k) cbP[p2][k] = f32x2{0.f, 0.f};
         LQGK_UNROLL for (int m = 0; m < D; ++m) x1P[p2][m] = f32x2{x1[2 * p2][m], x1[2 * p2 + 1][m]};
@@ -901,39 +971,73 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __r
       LQGK_UNROLL for (int k = 0; k < R; ++k) cbS[k] = 0.f;
       LQGK_UNROLL for (int m = 0; m < D; ++m) x1S[m] = x1[RT - 1][m];
     }
+    const float* hk = hist + ((size_t)s * nseg + (nseg - 1)) * R * Nh + base;
+    float* slot0 = seg;                            // buffer slot of the current segment's first step
+    fetch_ckpt(slot0, hk);
+    ring.issue(nseg - 1, 0);
+    if (nseg > 1) ring.issue(nseg - 2, 1);
     float* out = sums + ((size_t)s * Tn + (Tn - 1)) * DM::SUMP;
-    const int xstep = N * D;
-    const float* xq = x_tm + (size_t)(Tn - 1) * N * D + (size_t)(base + 2 * lane) * D;              // pairs: trials base + 64p + 2 lane (+1)
-    const float* xqs = x_tm + (size_t)(Tn - 1) * N * D + (size_t)(base + 64 * NP + lane) * D;       // single: base + 64 NP + lane
-    for (int k = 0; k < TRIAL_NST && k < nchunk; ++k) ring.issue(nchunk - 1 - k, k);
-    for (int kk = 0; kk < nchunk; ++kk) {
-      const int k = nchunk - 1 - kk;
-      const int st = kk % TRIAL_NST;
+    for (int kk = 0; kk < nseg; ++kk) {
+      const int k = nseg - 1 - kk, st = kk & 1;
+      const int t0 = k * CK, nst = min(CK, Tn - t0);
       const float* chunk = ring.wait(st);
-      const int t0 = k * trial_tb<DM>(), nst = min(trial_tb<DM>(), Tn - t0);
+      cp_async_wait<0>();                          // checkpoint k is in slot0 (lane-private data: no warp sync needed)
+      // ---- (2) re-run the state recursion through the segment.  Fully unrolled (CK - 1 steps) so that the rotating buffer of
+      // observation rows xs[row % 4] has static indices: row j + 3 is requested while step j runs (the L2 round trip is
+      // longer than one of these short steps).
+      float x0c[RT][D];                            // x_t of the step the reverse walk starts with (t0 + nst - 1)
+      float* sp = slot0;
+      {
+        f32x2 cP[NPA][R];
+        float cS[R];
+        float xs[4][RT][D];
+        load_slot(sp, cP, cS);
+        load_x(t0, xs[0]);
+        if (nst > 1) load_x(t0 + 1, xs[1]);
+        if (nst > 2) load_x(t0 + 2, xs[2]);
+        static_for<0, CK - 1>([&](auto QC) {
+          constexpr int q = decltype(QC)::value;
+          if (q + 1 < nst) {
+            if (q + 3 < nst) load_x(t0 + q + 3, xs[(q + 3) % 4]);
+            f32x2 xaP[NPA][D], xbP[NPA][D];
+            float xaS[D], xbS[D];
+            LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) LQGK_UNROLL for (int m = 0; m < D; ++m) {
+              xaP[p2][m] = f32x2{xs[q % 4][2 * p2][m], xs[q % 4][2 * p2 + 1][m]};
+              xbP[p2][m] = f32x2{xs[(q + 1) % 4][2 * p2][m], xs[(q + 1) % 4][2 * p2 + 1][m]};
+            }
+            LQGK_UNROLL for (int m = 0; m < D; ++m) { xaS[m] = xs[q % 4][RT - 1][m]; xbS[m] = xs[(q + 1) % 4][RT - 1][m]; }
+            const float* r = chunk + q * DM::REC;
+            auto run = [&](const auto& rr) {
+              LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) Trial<DM>::template advance<f32x2>(rr, xaP[p2], xbP[p2], cP[p2]);
+              if constexpr (NS) Trial<DM>::template advance<float>(rr, xaS, xbS, cS);
+            };
+            if constexpr (rec_in_regs<DM>()) {
+              RecRegs<DM> rr;
+              rr.load(r);
+              run(rr);
+            } else {
+              run(r);
+            }
+            sp = next_slot(sp);
+            store_slot(sp, cP, cS);
+          }
+        });
+        static_for<0, CK>([&](auto JC) {             // x_{t0 + nst - 1}: static for full segments, selected for the ragged last one
+          constexpr int j = decltype(JC)::value;
+          if (nst - 1 == j) { LQGK_UNROLL for (int jj = 0; jj < RT; ++jj) LQGK_UNROLL for (int m = 0; m < D; ++m) x0c[jj][m] = xs[j % 4][jj][m]; }
+        });
+      }
+      // ---- (3) walk the segment backwards; sp = slot of its last step, x0c = x_{t0 + nst - 1}
 #pragma unroll 1
       for (int q = nst - 1; q >= 0; --q) {
         const int t = t0 + q;
         const float* r = chunk + q * DM::REC;
-        // this step's (x_t, c_t) were prefetched; start loading the previous step's
         f32x2 x0P[NPA][D], cP[NPA][R];
         float x0S[D], cS[R];
-        LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) {
-          LQGK_UNROLL for (int m = 0; m < D; ++m) x0P[p2][m] = f32x2{x0n[2 * p2][m], x0n[2 * p2 + 1][m]};
-          LQGK_UNROLL for (int m = 0; m < R; ++m) cP[p2][m] = cnP[p2][m];
-        }
-        LQGK_UNROLL for (int m = 0; m < D; ++m) x0S[m] = x0n[RT - 1][m];
-        LQGK_UNROLL for (int m = 0; m < R; ++m) cS[m] = cnS[m];
-        if (t > 0) {
-          LQGK_UNROLL for (int m = 0; m < NHP; ++m) hr[m] -= hstep;
-          // observations of step t-1 through two walking pointers + immediate offsets.  Slots beyond the last trial read the
-          // neighbouring entries of the row (or the start of row t <= Tn-1: inside the array); they are finite and masked
-          // (w = 0, c = 0), so no per-step index clamping is needed here (the prologue, which touches row Tn, clamps).
-          xq -= xstep;
-          LQGK_UNROLL for (int j = 0; j < 2 * NP; ++j) load_obs<D>(xq + (64 * (j >> 1) + (j & 1)) * D, x0n[j]);
-          if constexpr (NS) { xqs -= xstep; load_obs<D>(xqs, x0n[RT - 1]); }
-          load_hist(cnP, cnS);
-        }
+        load_slot(sp, cP, cS);
+        LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) LQGK_UNROLL for (int m = 0; m < D; ++m) x0P[p2][m] = f32x2{x0c[2 * p2][m], x0c[2 * p2 + 1][m]};
+        LQGK_UNROLL for (int m = 0; m < D; ++m) x0S[m] = x0c[RT - 1][m];
+        if (q > 0) load_x(t - 1, x0c);              // next reverse step's x_t, one step ahead of its use
         f32x2 eP[NPA][D], vP[NPA][D], wvP[NPA][D], nebP[NPA][D], cbnP[NPA][R];
         float eS[D], vS[D], wvS[D], nebS[D], cbnS[R];
         auto run = [&](const auto& rr) {
@@ -947,6 +1051,13 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __r
           run(rr);
         } else {
           run(r);
+        }
+        if (q == nst - 1 && k > 0) {
+          // the slot of the segment's last step has been consumed (its values are operands of the arithmetic above):
+          // the checkpoint of the next segment to process lands there while this one is walked
+          hk -= (size_t)R * Nh;
+          fetch_ckpt(sp, hk);
+          slot0 = sp;
         }
         auto term = [&](auto IDXC) -> float {
           constexpr int IDX = decltype(IDXC)::value;
@@ -996,9 +1107,10 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __r
           LQGK_UNROLL for (int m = 0; m < D; ++m) x1S[m] = x0S[m];
         }
         out -= DM::SUMP;
+        sp = prev_slot(sp);
       }
       __syncwarp();
-      if (kk + TRIAL_NST < nchunk) ring.issue(nchunk - 1 - (kk + TRIAL_NST), st);
+      if (kk + 2 < nseg) ring.issue(nseg - 1 - (kk + 2), st);
     }
   }
 }

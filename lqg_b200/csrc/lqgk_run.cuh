@@ -149,7 +149,7 @@ Plan make_plan(const LqgkDims& d, int mode, bool tv, size_t Sc) {
     p.Kbar = take(sizeof(double) * T * DM::EK * Sc);
     p.KbarF = take(sizeof(double) * T * DM::EK * Sc);
     p.sums = take(sizeof(float) * Sc * T * DM::SUMP);
-    p.hist = take(sizeof(float) * Sc * T * DM::R * hist_stride((int)N));
+    p.hist = take(sizeof(float) * Sc * trial_nseg<DM>((int)N, (int)T) * DM::R * hist_stride((int)N));   // checkpoints of the carried state
     p.w = take(sizeof(float) * Sc * N);
     using SR = CovSeqRev<DM>;
     p.FU = take(sizeof(double) * T * SR::NSF * Sc);

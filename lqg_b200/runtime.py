@@ -80,6 +80,14 @@ def _row_major(M: torch.Tensor) -> torch.Tensor:
     return M[idx].contiguous().expand(*lead, r, c)
 
 
+def _vec_rows(v: torch.Tensor) -> torch.Tensor:
+    """(S|1, T, k) vectors with a contiguous last axis, keeping stride-0 leading axes un-materialised."""
+    if v.stride(-1) == 1 or v.shape[-1] == 1:
+        return v
+    idx = tuple(slice(0, 1) if (v.stride(i) == 0 and v.shape[i] > 1) else slice(None) for i in range(v.dim() - 1))
+    return v[idx].contiguous().expand(*v.shape)
+
+
 def spec_mats(spec: LQGSpec, keys) -> Dict[str, torch.Tensor]:
     return {k: _row_major(_as4(getattr(spec, k))) for k in keys}
 
@@ -125,11 +133,13 @@ def lqr_backward(spec: LQGSpec, eps: float = 1e-8):
     dims.d = next((t[4] for t in SUPPORTED_DIMS if t[:4] == (dims.x, b, u, y)), 1)
     check_supported(dims, gains_only=True)
     mats = spec_mats(spec, ACT_KEYS)
+    # affine terms are always handed to the kernel (zeros in every reference model): no host-side "is it zero?" sync
     for k, tr in (("q", 1), ("r", 1), ("P", 2)):
         v = getattr(spec, k)
-        if v is not None and bool((v != 0).any()):
-            mats[k] = (v if v.dim() == tr + 2 else v.unsqueeze(0)).contiguous()
-    if spec.qf is not None and bool((spec.qf != 0).any()):
+        if v is not None:
+            v = v if v.dim() == tr + 2 else v.unsqueeze(0)
+            mats[k] = _row_major(v) if tr == 2 else _vec_rows(v)
+    if spec.qf is not None:
         mats["qf"] = (spec.qf if spec.qf.dim() == 2 else spec.qf.unsqueeze(0)).contiguous()
     if spec.Qf is not None:
         mats["Qf"] = _row_major(spec.Qf if spec.Qf.dim() == 3 else spec.Qf.unsqueeze(0))
@@ -167,14 +177,19 @@ class _LogLikFn(torch.autograd.Function):
     caches the per-sample gradients; ``backward`` rescales them when the incoming cotangent is constant over the
     trials of each sample (the usual ``ll.sum()`` / per-sample weighting) and otherwise re-runs the adjoint with the
     actual per-trial cotangents.
+
+    ``mats`` = the 7 actor base matrices, the 5 dynamics base matrices, then optionally ``Qf`` and ``Sigma0``.
     """
 
     @staticmethod
-    def forward(ctx, x_tm, dims, has_sigma0, n_act, *mats):
+    def forward(ctx, x_tm, dims, has_qf, has_sigma0, n_act, *mats):
         lib = abi.load_library()
         act = dict(zip(ACT_KEYS, mats[:n_act]))
         dyn = dict(zip(DYN_KEYS, mats[n_act:n_act + len(DYN_KEYS)]))
-        sigma0 = mats[-1] if has_sigma0 else None
+        extra = list(mats[n_act + len(DYN_KEYS):])
+        if has_qf:
+            act["Qf"] = extra.pop(0)
+        sigma0 = extra.pop(0) if has_sigma0 else None
         dev = x_tm.device
         need_grad = any(m.requires_grad for m in mats)
         ctx.need_grad = need_grad
@@ -187,23 +202,26 @@ class _LogLikFn(torch.autograd.Function):
                     "lqg_b200: gradients are implemented for time-invariant specs (stride-0 time axis, as built by "
                     "lqg_b200.utils.time_stack); materialised time-varying arrays only support the forward pass.")
         ws = workspace(dev, lib.workspace_bytes(dims, abi.MODE_VJP, 0))
-        ll, ga, gd, gs = lib.loglik_vjp(dims, act, dyn, x_tm, sigma0=sigma0, ws=ws, stream=_stream(dev))
+        ll, ga, gd, gs = lib.loglik_vjp(dims, act, dyn, x_tm, sigma0=sigma0, want_qf=has_qf, ws=ws, stream=_stream(dev))
         ctx.args = (x_tm, dims, act, dyn, sigma0)
         ctx.cached = (ga, gd, gs)
         ctx.shapes = [m.shape for m in mats]
         ctx.n_act = n_act
-        ctx.has_sigma0 = has_sigma0
+        ctx.has_qf, ctx.has_sigma0 = has_qf, has_sigma0
         return ll
 
     @staticmethod
     def backward(ctx, ll_bar):
         if not ctx.need_grad:
-            return (None,) * (4 + len(ctx.shapes))
+            return (None,) * (5 + len(ctx.shapes))
         x_tm, dims, act, dyn, sigma0 = ctx.args
         ga, gd, gs = ctx.cached
         ll_bar = ll_bar.expand(dims.S, dims.N)
         row = ll_bar[:, :1]
-        if bool((ll_bar == row).all()):
+        # A cotangent that is constant over the trials of each sample (what `.sum()` / `.sum(-1)` / per-sample weights
+        # produce: autograd hands it over as an expanded, stride-0 view) only rescales the cached unit-cotangent gradients.
+        # Decided from the strides, never from the values: no host synchronisation on the autograd path.
+        if dims.N == 1 or ll_bar.stride(-1) == 0:
             scale = row.reshape(dims.S, 1, 1).to(next(iter(ga.values())).dtype)
             ga = {k: v * scale for k, v in ga.items()}
             gd = {k: v * scale for k, v in gd.items()}
@@ -212,9 +230,10 @@ class _LogLikFn(torch.autograd.Function):
             lib = abi.load_library()
             dev = x_tm.device
             ws = workspace(dev, lib.workspace_bytes(dims, abi.MODE_VJP, 0))
-            _, ga, gd, gs = lib.loglik_vjp(dims, act, dyn, x_tm, ll_bar=ll_bar.contiguous(), sigma0=sigma0, ws=ws,
-                                           stream=_stream(dev))
-        grads = [ga[k] for k in ACT_KEYS] + [gd[k] for k in DYN_KEYS] + ([gs] if ctx.has_sigma0 else [])
+            _, ga, gd, gs = lib.loglik_vjp(dims, act, dyn, x_tm, ll_bar=ll_bar.contiguous(), sigma0=sigma0,
+                                           want_qf=ctx.has_qf, ws=ws, stream=_stream(dev))
+        grads = [ga[k] for k in ACT_KEYS] + [gd[k] for k in DYN_KEYS] + ([ga["Qf"]] if ctx.has_qf else []) + \
+                ([gs] if ctx.has_sigma0 else [])
         out = []
         for g, shp in zip(grads, ctx.shapes):
             if len(shp) == 4:          # materialised time-varying input: forward only (checked in forward)
@@ -222,7 +241,30 @@ class _LogLikFn(torch.autograd.Function):
                 continue
             # time-invariant base matrix (S|1, r, c): the kernel already summed the cotangent over time
             out.append(g.sum(0, keepdim=True) if (shp[0] == 1 and g.shape[0] != 1) else g)
-        return (None, None, None, None, *out)
+        return (None, None, None, None, None, *out)
+
+
+def _qf_is_default(actor: LQGSpec) -> bool:
+    """True when ``spec.Qf`` is the spec's own ``Q`` base matrix (what ``time_stack_spec`` builds, lqg/utils.py:30):
+    the kernels then default ``Qf`` to ``Q`` and send its gradient there."""
+    Qf, Q = actor.Qf, actor.Q
+    if Qf is None:
+        return True
+    return (Qf.data_ptr() == Q.data_ptr() and Qf.shape[-2:] == Q.shape[-2:] and Qf.stride()[-2:] == Q.stride()[-2:]
+            and is_time_invariant(_as4(Q)) and Qf.dim() == Q.dim() - 1 and Qf.stride()[:-2] == Q.stride()[:-3])
+
+
+def _check_no_cross_cost(actor: LQGSpec):
+    """The fused likelihood assumes ``P = 0`` (state-control cross cost), true for every reference model
+    (lqg/utils.py:32); a spec with ``P != 0`` would silently differ from ``lqr.backward``'s gains, so refuse it.
+    Specs built by ``time_stack_spec`` are recognised without looking at the values (no host sync)."""
+    from lqg_b200.utils import is_known_zero
+    P = actor.P
+    if P is None or is_known_zero(P):
+        return
+    if bool((P != 0).any()):
+        raise NotImplementedError("lqg_b200: the fused log-likelihood kernels assume P = 0 (no state-control cross cost); "
+                                  "use lqr.backward / conditional_moments (slow path) for specs with P != 0")
 
 
 def log_likelihood(actor: LQGSpec, dynamics: LQGSpec, x: torch.Tensor, Sigma0: Optional[torch.Tensor] = None,
@@ -242,6 +284,7 @@ def log_likelihood(actor: LQGSpec, dynamics: LQGSpec, x: torch.Tensor, Sigma0: O
     if dims.T != T1 - 1:
         raise ValueError(f"need T+1 = {dims.T + 1} observations per trial, got {T1} (SURVEY H7: spec.T == x.shape[-2] - 1)")
     check_supported(dims)
+    _check_no_cross_cost(actor)
     if x_tm is None:
         if per_sample:   # [S, n, T+1, d] -> [S, T+1, n, d] float32
             x_tm = x.detach().permute(0, 2, 1, 3).to(torch.float32).contiguous()
@@ -254,8 +297,12 @@ def log_likelihood(actor: LQGSpec, dynamics: LQGSpec, x: torch.Tensor, Sigma0: O
         return _row_major(M4[:, 0] if is_time_invariant(M4) else M4).to(dt)
 
     mats = [base(getattr(actor, k)) for k in ACT_KEYS] + [base(getattr(dynamics, k)) for k in DYN_KEYS]
+    has_qf = not _qf_is_default(actor)
+    if has_qf:   # a terminal cost of its own (lqg/control/lqr.py:37 starts the sweep from spec.Qf)
+        Qf = actor.Qf
+        mats.append(_row_major(Qf if Qf.dim() == 3 else Qf.unsqueeze(0)).to(dt))
     has_s0 = Sigma0 is not None
     if has_s0:
         mats.append(_row_major(Sigma0 if Sigma0.dim() == 3 else Sigma0.unsqueeze(0)).to(dt))
-    ll = _LogLikFn.apply(x_tm, dims, has_s0, len(ACT_KEYS), *mats)
+    ll = _LogLikFn.apply(x_tm, dims, has_qf, has_s0, len(ACT_KEYS), *mats)
     return ll[0] if (actor.A.dim() == 3 and dynamics.A.dim() == 3) else ll

@@ -123,6 +123,9 @@ class System:
         new.__dict__.update(self.__dict__)
         new.actor = mv(self.actor)
         new.dynamics = new.actor if self.dynamics is self.actor else mv(self.dynamics)
+        axis = getattr(self, "_axis_system", None)
+        if axis is not None:   # the factorised dim > 1 likelihood runs on this cached 1-axis model: move it too
+            new._axis_system = axis.to(*args, **kw)
         return new
 
     def _default_sigma0(self, Sigma0):

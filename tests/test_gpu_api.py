@@ -163,3 +163,61 @@ def test_per_condition_data_in_one_call():
     ll.sum().backward()
     assert np.allclose(ll.detach().cpu().numpy(), np.stack(lls), rtol=1e-4)
     assert np.allclose(st.grad.cpu().numpy(), np.array(grads), rtol=1e-3)
+
+
+def test_per_condition_data_odd_stride_dim1():
+    """d = 2 with an odd number of (trial, step) rows per condition: the per-sample stride n*(T+1)*d floats is only 8-byte
+    aligned, which is all the float2 observation accesses need (was rejected as 'invalid argument')."""
+    T, N, C = 120, 7, 3                                               # N * (T + 1) = 847 is odd
+    sig = [5.0, 9.0, 14.0]
+    Xs, lls = [], []
+    for c in range(C):
+        mats = O.bounded_actor_mats(sigma_target=sig[c])
+        X = _sim(mats, T, N, seed=20 + c).astype(np.float32)
+        Xs.append(X)
+        sa, sd = O.make_system(mats, T)
+        lls.append(O.log_likelihood(sa, sd, X.astype(np.float64)))
+    m = tracking.BoundedActor(dim=1, T=T, sigma_target=torch.tensor(sig, device=DEV))
+    ll = m.log_likelihood(torch.tensor(np.stack(Xs), device=DEV))     # (C, N, T+1, 2)
+    assert ll.shape == (C, N)
+    assert np.allclose(ll.cpu().numpy(), np.stack(lls), rtol=1e-4)
+
+
+def test_to_dtype_moves_the_factorised_axis_model():
+    """System.to() must convert the cached 1-axis model the dim > 1 likelihood runs on."""
+    T, N = 60, 5
+    X = torch.tensor(_sim(O.bounded_actor_mats(dim=2), T, N, seed=3), device=DEV)
+    m32 = tracking.BoundedActor(dim=2, T=T, device=DEV)
+    m64 = m32.to(torch.float64)
+    assert m64._axis_system.dtype == torch.float64 and m64.dtype == torch.float64
+    ll64 = m64.log_likelihood(X)
+    assert ll64.dtype == torch.float64
+    gen = System(m64.actor, m64.dynamics).log_likelihood(X)            # un-factorised n = 8 kernels
+    assert torch.allclose(ll64, gen, rtol=1e-6)
+
+
+def test_terminal_cost_is_forwarded_and_cross_cost_refused():
+    """a spec whose Qf differs from Q[-1] must reach the kernels (lqr.py:37 starts from spec.Qf); P != 0 is
+    outside the fused path and must raise instead of being dropped."""
+    T, N = 90, 6
+    mats = O.bounded_actor_mats()
+    X = _sim(mats, T, N, seed=8).astype(np.float32)
+    sa, sd = O.make_system(mats, T)
+    Qf = np.array([[3.0, -2.0], [-2.0, 5.0]])
+    sa2 = dict(sa, Qf=Qf)
+    ll_ref = O.log_likelihood(sa2, sd, X.astype(np.float64))
+    assert not np.allclose(ll_ref, O.log_likelihood(sa, sd, X.astype(np.float64)), rtol=1e-6)
+    m = tracking.BoundedActor(T=T, device=DEV, dtype=torch.float64)
+    Qf_t = torch.tensor(Qf, device=DEV, requires_grad=True)
+    s2 = System(m.actor._replace(Qf=Qf_t), m.dynamics)
+    ll = s2.log_likelihood(torch.tensor(X, device=DEV))
+    assert np.allclose(ll.detach().cpu().numpy(), ll_ref, rtol=1e-6)
+    ll.sum().backward()
+    assert Qf_t.grad is not None and torch.isfinite(Qf_t.grad).all() and Qf_t.grad.abs().max() > 0
+    eps = 1e-5                                                         # finite difference of the oracle in Qf[0, 0]
+    llp = O.log_likelihood(dict(sa, Qf=Qf + np.array([[eps, 0], [0, 0]])), sd, X.astype(np.float64)).sum()
+    llm = O.log_likelihood(dict(sa, Qf=Qf - np.array([[eps, 0], [0, 0]])), sd, X.astype(np.float64)).sum()
+    assert np.isclose(Qf_t.grad[0, 0].item(), (llp - llm) / (2 * eps), rtol=2e-3)
+    P = torch.ones_like(m.actor.P)
+    with pytest.raises(NotImplementedError, match="P = 0"):
+        System(m.actor._replace(P=P), m.dynamics).log_likelihood(torch.tensor(X, device=DEV))
