@@ -103,10 +103,12 @@ int run_big(const Call& c) {
     }
     const int RT = std::min((N + 31) / 32, trial_rt_max<DM>());
     float* hist = vjp ? F(p.hist) : nullptr;
+    size_t xcs = 0;
+    if ((rc = launch_repack_obs(st, d, 32 * RT, c.x_tm, (int)s0, n, F(p.xc), &xcs))) return rc;
     rc = LQGK_E_UNSUPPORTED;
     static_for<1, trial_rt_max<DM>() + 1>([&](auto RTC) {
       if (RT == decltype(RTC)::value)
-        rc = launch_trial_fwd<DM, decltype(RTC)::value>(st, F(p.rec), c.x_tm, (size_t)d.x_sample_stride, (int)s0, n, N, Tn, D(p.ll), hist);
+        rc = launch_trial_fwd<DM, decltype(RTC)::value>(st, F(p.rec), F(p.xc), xcs, n, N, Tn, D(p.ll), hist);
     });
     if (rc) return rc;
     {
@@ -129,7 +131,7 @@ int run_big(const Call& c) {
     rc = LQGK_E_UNSUPPORTED;
     static_for<1, trial_rt_max<DM>() + 1>([&](auto RTC) {
       if (RT == decltype(RTC)::value)
-        rc = launch_trial_rev<DM, decltype(RTC)::value>(st, F(p.rec), c.x_tm, (size_t)d.x_sample_stride, (int)s0, hist, F(p.w), n, N, Tn, F(p.sums));
+        rc = launch_trial_rev<DM, decltype(RTC)::value>(st, F(p.rec), F(p.xc), xcs, hist, F(p.w), n, N, Tn, F(p.sums));
     });
     if (rc) return rc;
     if (cudaMemsetAsync(D(p.acc), 0, sizeof(double) * cl.total * Sc, st) != cudaSuccess) return LQGK_E_CUDA;

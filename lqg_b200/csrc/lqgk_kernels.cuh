@@ -119,6 +119,30 @@ __global__ void k_pack_obs(int N, int T1, int d, const T* x, float* x_tm) {
   x_tm[idx] = (float)x[((size_t)i * T1 + t) * d + k];
 }
 
+// Observations for the per-trial kernels: x_tm[(s)][T+1][N][d] (ABI layout, trial-major inside a step) -> blocked and
+// component-major xc[(s)][T+1][NB][d][ROW]: the trials are cut into NB blocks of ROW = 32 * RT (one block per pass of the
+// per-trial kernels, RT trials per lane), and inside a block every component is one contiguous row.  A lane's pair of
+// ADJACENT trials (2i, 2i+1) of one component is then one aligned 64-bit element = one f32x2 register pair (the trial-major
+// layout cost ~100 register moves per step in the adjoint kernel to pair the trials up), and all of a lane's elements of a
+// step sit at compile-time offsets from one pointer.  Columns beyond the last trial repeat it (finite; masked by weight 0).
+template <class T>   // (a template only so that the header can be included from several translation units)
+__global__ void k_repack_obs(const T* __restrict__ x_tm, size_t x_sample_stride, int s_first, int nsets, int N, int row, int T1, int d,
+                             float* __restrict__ xc) {
+  const int nb = (N + row - 1) / row;
+  const size_t per = (size_t)T1 * nb * d * row;
+  const size_t total = per * nsets;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int col = idx % row;
+    const int m = (idx / row) % d;
+    const int blk = (idx / ((size_t)row * d)) % nb;
+    const int t = (idx / ((size_t)row * d * nb)) % T1;
+    const size_t ds = idx / per;
+    const int i = blk * row + col;
+    const int ic = i < N ? i : N - 1;
+    xc[idx] = x_tm[(size_t)(s_first + ds) * x_sample_stride + ((size_t)t * N + ic) * d + m];
+  }
+}
+
 // =========================================================================================== per-sample kernels
 // All launched with blockDim = 32 and gridDim = Sc / 32 (Sc is padded to a multiple of 32 by k_pack).
 template <class DM, bool AFFINE>
@@ -554,25 +578,8 @@ template <class DM> constexpr size_t smem_lqr_rev() {
 }
 
 // =========================================================================================== per-trial kernels
-template <int D>
-__device__ __forceinline__ void load_obs(const float* __restrict__ p, float* out) {
-  if constexpr (D % 4 == 0) {
-    LQGK_UNROLL for (int k = 0; k < D / 4; ++k) {
-      float4 v = __ldg(reinterpret_cast<const float4*>(p) + k);
-      out[4 * k] = v.x; out[4 * k + 1] = v.y; out[4 * k + 2] = v.z; out[4 * k + 3] = v.w;
-    }
-  } else if constexpr (D % 2 == 0) {
-    LQGK_UNROLL for (int k = 0; k < D / 2; ++k) {
-      float2 v = __ldg(reinterpret_cast<const float2*>(p) + k);
-      out[2 * k] = v.x; out[2 * k + 1] = v.y;
-    }
-  } else {
-    LQGK_UNROLL for (int k = 0; k < D; ++k) out[k] = __ldg(p + k);
-  }
-}
-
 // Resident CTAs per SM the forward per-trial kernel is compiled for: the small systems are latency-bound at 2 CTAs (8 warps)
-// per SM, so the register budget is capped at 65536 / (3 * 128) = 170 to fit 3 (no spills: 204 -> 164 registers, -5 % time).
+// per SM, so the register budget is capped at 65536 / (3 * 128) = 170 to fit 3.
 // The adjoint kernel needs ~240 registers; capped at 170 it spills and runs 1.6x slower (measured), so it stays at 2 CTAs.
 template <class DM>
 __host__ __device__ constexpr int trial_min_ctas() { return DM::N <= 6 ? 3 : 1; }
@@ -589,13 +596,11 @@ constexpr int TRIAL_PF = 4;      // observation prefetch distance in time steps 
 constexpr int TRIAL_RED_STRIDE = 36;
 
 // ------------------------------------------------------------------------------------------- checkpointed state history
-// The adjoint needs the carried mean c_t of every trial at every step.  Storing all of them (T x R x N floats per sample,
-// 2.9 MB at the benchmark size) made the forward kernel HBM-bound and was 70 % of the step's DRAM traffic (round 1).  Now the
-// forward kernel stores c_t only at the segment starts t = k * CK ("checkpoints"); the adjoint kernel processes one segment at
-// a time: it re-runs the state recursion from the checkpoint (Trial::advance, CK - 1 steps, bit-identical to the forward pass)
-// into a per-warp shared-memory buffer [CK][R][32 RT] and then walks the segment backwards reading c_t from that buffer.
-// CK is the largest interval whose buffer + record ring fits the per-warp share of shared memory that keeps 2 CTAs (8 warps)
-// resident per SM.
+// The adjoint needs the carried mean c_t of every trial at every step.  The forward kernel stores c_t only at the segment
+// starts t = k * CK ("checkpoints"); the adjoint kernel processes one segment at a time: it re-runs the state recursion from
+// the checkpoint (Trial::advance, CK - 1 steps, bit-identical to the forward pass) into a per-warp shared-memory buffer
+// [CK][R][32 RT] and then walks the segment backwards reading c_t from that buffer.  CK = 1 stores every step (no
+// recomputation).  CK is bounded by the per-warp share of shared memory that keeps 2 CTAs (8 warps) resident per SM.
 #ifndef LQGK_TRIAL_CK_MAX
 #define LQGK_TRIAL_CK_MAX 8
 #endif
@@ -616,13 +621,16 @@ __host__ __device__ constexpr int trial_ck(int RT) {
 template <class DM>
 __host__ __device__ constexpr int trial_rt_max() { return DM::N * DM::N <= 36 ? 8 : 4; }
 __host__ __device__ __forceinline__ constexpr int trial_rt(int N, int rt_max) { return (N + 31) / 32 < rt_max ? (N + 31) / 32 : rt_max; }
-// Row stride of the checkpoints [s][segment][R][hist_stride(N)]: even, so a pair's entry is 8-byte aligned.  The forward
-// kernel stores 0 into the pad element of an odd N; the adjoint reads pairs whenever the first half is a real trial.
-__host__ __device__ __forceinline__ constexpr int hist_stride(int N) { return (N + 1) & ~1; }
+// Geometry of the per-trial kernels for N trials: RT trials per lane, NB passes ("blocks") of ROW = 32 RT trials, CK steps per
+// segment.  Checkpoints are laid out [s][segment][NB][R][ROW], repacked observations [(s)][T+1][NB][D][ROW] (k_repack_obs).
+struct TrialGeom {
+  int RT, ROW, NB, CK, nseg;
+};
 template <class DM>
-__host__ __device__ constexpr int trial_nseg(int N, int T) {
-  const int ck = trial_ck<DM>(trial_rt(N, trial_rt_max<DM>()));
-  return (T + ck - 1) / ck;
+__host__ __device__ constexpr TrialGeom trial_geom(int N, int T) {
+  const int rt = trial_rt(N, trial_rt_max<DM>());
+  const int ck = trial_ck<DM>(rt);
+  return TrialGeom{rt, 32 * rt, (N + 32 * rt - 1) / (32 * rt), ck, (T + ck - 1) / ck};
 }
 
 template <class DM, int RT, bool REV>
@@ -636,24 +644,6 @@ constexpr size_t trial_smem_bytes() {
     size_t pf = (size_t)TRIAL_WARPS * (TRIAL_PF + 1) * RT * 32 * DM::D * sizeof(float);
     return ring + pf;
   }
-}
-// observation x[t][trial][0..D) -> this lane's slot (vector copy of D floats, D*4 in {4, 8, 16} bytes, else scalars)
-template <int D>
-__device__ __forceinline__ void prefetch_obs(float* slot, int lane, const float* src) {
-  if constexpr (D == 1 || D == 2 || D == 4) cp_async<D * 4>(slot + lane * D, src);
-  else { LQGK_UNROLL for (int k = 0; k < D; ++k) cp_async<4>(slot + k * 32 + lane, src + k); }
-}
-template <int D>
-__device__ __forceinline__ void read_obs(const float* slot, int lane, float* out) {
-  if constexpr (D == 2) {          // one 64-bit access per lane (scalar reads at stride 2 are 2-way bank conflicts)
-    float2 v = *reinterpret_cast<const float2*>(slot + lane * 2);
-    out[0] = v.x; out[1] = v.y;
-  } else if constexpr (D == 4) {
-    float4 v = *reinterpret_cast<const float4*>(slot + lane * 4);
-    out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
-  } else if constexpr (D == 1) {
-    out[0] = slot[lane];
-  } else { LQGK_UNROLL for (int k = 0; k < D; ++k) out[k] = slot[k * 32 + lane]; }
 }
 
 // Per-warp ring of NST record chunks of TB time steps, filled by bulk async copies.  Chunk k covers steps
@@ -691,15 +681,48 @@ struct RecRing {
   }
 };
 
-// Trial -> lane assignment of one pass (32*RT trials starting at `base`): pair p of a lane holds the ADJACENT trials
-// base + 64p + 2*lane and +1, so one 64-bit access moves the pair's entry of a checkpoint, already in f32x2 register
-// order (no packing moves, half the memory instructions); an odd RT adds the single trial base + 64*(RT/2) + lane.
+// Trial -> lane assignment inside one block of ROW = 32 RT trials: pair p of a lane holds the ADJACENT trials (columns)
+// 64p + 2*lane and +1, so one 64-bit access moves the pair's entry of a checkpoint or of an observation row, already in f32x2
+// register order (no packing moves, half the memory instructions); an odd RT adds the single column 64*(RT/2) + lane.
 // Flat slot j: 2p, 2p+1 = the two halves of pair p; RT-1 = the single.
 template <int RT>
-__device__ __forceinline__ int trial_of(int base, int lane, int j) {
+__device__ __forceinline__ int trial_col(int lane, int j) {
   constexpr int NP = RT / 2;
-  return j < 2 * NP ? base + 64 * (j >> 1) + 2 * lane + (j & 1) : base + 64 * NP + lane;
+  return j < 2 * NP ? 64 * (j >> 1) + 2 * lane + (j & 1) : 64 * NP + lane;
 }
+// A lane's view of one row block [M][ROW] (a checkpoint, a shared-memory state slot or an observation row; M components)
+// through two pointers: pp = block + 2 lane (pair p, component m at pp[m ROW + 64 p], 64 bits), ps = block + 64 NP + lane
+// (the single at ps[m ROW]).  Every offset is a compile-time immediate.
+template <int RT, int M>
+struct LaneBlock {
+  static constexpr int NP = RT / 2, NS = RT % 2, NPA = NP > 0 ? NP : 1, ROW = 32 * RT;
+  template <bool LDG>
+  __device__ __forceinline__ static void load(const float* pp, const float* ps, f32x2 (&vp)[NPA][M], float (&vs)[M]) {
+    LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) LQGK_UNROLL for (int m = 0; m < M; ++m) {
+      const float2* a = reinterpret_cast<const float2*>(pp + m * ROW + 64 * p2);
+      float2 v = LDG ? __ldg(a) : *a;
+      vp[p2][m] = f32x2{v.x, v.y};
+    }
+    if constexpr (NS) { LQGK_UNROLL for (int m = 0; m < M; ++m) vs[m] = LDG ? __ldg(ps + m * ROW) : ps[m * ROW]; }
+  }
+  __device__ __forceinline__ static void store(float* pp, float* ps, const f32x2 (&vp)[NPA][M], const float (&vs)[M]) {
+    LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) LQGK_UNROLL for (int m = 0; m < M; ++m)
+      *reinterpret_cast<float2*>(pp + m * ROW + 64 * p2) = make_float2(vp[p2][m].x, vp[p2][m].y);
+    if constexpr (NS) { LQGK_UNROLL for (int m = 0; m < M; ++m) ps[m * ROW] = vs[m]; }
+  }
+  __device__ __forceinline__ static void store_streaming(float* pp, float* ps, const f32x2 (&vp)[NPA][M], const float (&vs)[M]) {
+    LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) LQGK_UNROLL for (int m = 0; m < M; ++m)
+      __stcs(reinterpret_cast<float2*>(pp + m * ROW + 64 * p2), make_float2(vp[p2][m].x, vp[p2][m].y));   // written once, read once
+    if constexpr (NS) { LQGK_UNROLL for (int m = 0; m < M; ++m) __stcs(ps + m * ROW, vs[m]); }
+  }
+  // global -> shared, asynchronously (LDGSTS); dp/ds: this lane's pointers into the shared-memory block
+  __device__ __forceinline__ static void copy_async(float* dp, float* ds, const float* pp, const float* ps) {
+    LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) LQGK_UNROLL for (int m = 0; m < M; ++m)
+      cp_async<8>(dp + m * ROW + 64 * p2, pp + m * ROW + 64 * p2);
+    if constexpr (NS) { LQGK_UNROLL for (int m = 0; m < M; ++m) cp_async<4>(ds + m * ROW, ps + m * ROW); }
+    cp_async_commit();
+  }
+};
 
 // Copy one step's record from the shared-memory ring into registers (small systems) with 128-bit broadcast loads.
 template <class DM>
@@ -718,115 +741,89 @@ template <class DM>
 __host__ __device__ constexpr bool rec_in_regs() { return DM::REC <= 48; }
 
 // Forward: per-trial mean recursion + log-density.  grid = (ceil(n_samples / TRIAL_WARPS)), block = 32 * TRIAL_WARPS.
-// Trials are processed in passes of 32*RT (lane owns the trials trial_of(base, lane, j), j < RT).  Observations are prefetched
-// TRIAL_PF steps ahead with per-lane cp.async copies into shared-memory slots (no registers held, no stalls on the
-// L2 round trip).  `hist` (VJP only): checkpoints of the carried state at the segment starts, [s][segment][R][hist_stride(N)].
+// Trials are processed in NB passes of ROW = 32*RT.  Observations (blocked component-major, k_repack_obs) are prefetched
+// TRIAL_PF steps ahead with per-lane cp.async copies into shared-memory slots laid out like the source block ([D][ROW]: no
+// registers held, no stalls on the L2 round trip) and read back as f32x2 pairs.
+// `hist` (VJP only): checkpoints of the carried state at the segment starts, [s][segment][NB][R][ROW].
 template <class DM, int RT>
-__global__ void __launch_bounds__(32 * TRIAL_WARPS, trial_min_ctas<DM>()) k_trial_fwd(const float* __restrict__ rec, const float* __restrict__ x_all,
-                                                                size_t x_sample_stride, int s_first, int n_samples, int N, int Tn,
+__global__ void __launch_bounds__(32 * TRIAL_WARPS, trial_min_ctas<DM>()) k_trial_fwd(const float* __restrict__ rec, const float* __restrict__ xc_all,
+                                                                size_t xc_sample_stride, int n_samples, int N, int Tn,
                                                                 double* __restrict__ ll_ws, float* __restrict__ hist) {
-  constexpr int D = DM::D, R = DM::R, NSLOT = TRIAL_PF + 1, TB = trial_tb<DM>(), CK = trial_ck<DM>(RT);
+  constexpr int D = DM::D, R = DM::R, NSLOT = TRIAL_PF + 1, TB = trial_tb<DM>(), CK = trial_ck<DM>(RT), ROW = 32 * RT;
+  constexpr int NP = RT / 2, NS = RT % 2, NPA = NP > 0 ? NP : 1;
+  using XB = LaneBlock<RT, D>;
+  using CB = LaneBlock<RT, R>;
   extern __shared__ __align__(128) unsigned char smraw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = blockIdx.x * TRIAL_WARPS + warp;
   if (s >= n_samples) return;
-  const float* __restrict__ x_tm = x_all + (size_t)(s_first + s) * x_sample_stride;   // this sample's observations
+  const int NB = (N + ROW - 1) / ROW;
+  const float* __restrict__ xc = xc_all + (size_t)s * xc_sample_stride;   // this sample's observations [T+1][NB][D][ROW]
   constexpr size_t RING_BYTES = (size_t)TRIAL_WARPS * TRIAL_NST * TB * DM::REC * sizeof(float);
   float* ring_base = reinterpret_cast<float*>(smraw);
   uint64_t* bar_base = reinterpret_cast<uint64_t*>(smraw + RING_BYTES);
-  float* pf = reinterpret_cast<float*>(smraw + RING_BYTES + TRIAL_WARPS * TRIAL_NST * sizeof(uint64_t)) + (size_t)warp * NSLOT * RT * 32 * D;
+  float* pf = reinterpret_cast<float*>(smraw + RING_BYTES + TRIAL_WARPS * TRIAL_NST * sizeof(uint64_t)) + (size_t)warp * NSLOT * D * ROW;
   RecRing<DM, TB, TRIAL_NST> ring{ring_base + (size_t)warp * TRIAL_NST * TB * DM::REC, bar_base + warp * TRIAL_NST,
                                   rec + (size_t)s * Tn * DM::REC, Tn, lane, 0};
   ring.init();
   const int nchunk = (Tn + TB - 1) / TB;
-  const int Nh = hist_stride(N);
   const int nseg = (Tn + CK - 1) / CK;
-  for (int base = 0; base < N; base += 32 * RT) {
-    int tr[RT], trD[RT];
-    bool ok[RT];
-    LQGK_UNROLL for (int j = 0; j < RT; ++j) {
-      int i = trial_of<RT>(base, lane, j);
-      ok[j] = i < N;
-      tr[j] = ok[j] ? i : N - 1;
-      trD[j] = tr[j] * D;            // 32-bit element offsets: one 64-bit row pointer per step + cheap lane offsets
-    }
-    // checkpoint row pointers of this lane (one per state component), advanced by one segment per stored checkpoint
-    // (small systems: one pointer per component -> every access is pointer + immediate; large ones: one pointer + m * Nh)
-    constexpr bool HPTRS = R <= 6;
-    constexpr int NHP = HPTRS ? R : 1;
-    float* hw[NHP];
-    LQGK_UNROLL for (int m = 0; m < NHP; ++m) hw[m] = hist + ((size_t)s * nseg * R + m) * Nh + (base + 2 * lane);
-    auto hrow = [&](int m) -> float* { if constexpr (HPTRS) return hw[m]; else return hw[0] + m * Nh; };
-    const int hstep = R * Nh, hsingle = 64 * (RT / 2) - lane;
+  const size_t xstep = (size_t)NB * D * ROW, hstep = (size_t)NB * R * ROW;
+  const int lp = 2 * lane, ls = 64 * NP + lane;                       // this lane's pair / single column inside a block
+  for (int blk = 0; blk < NB; ++blk) {
+    const float* xlp = xc + (size_t)blk * D * ROW + lp;              // row 0 of this block; row t at + t * xstep
+    const float* xls = xc + (size_t)blk * D * ROW + ls;
+    float* hp = hist + ((size_t)s * nseg * NB + blk) * R * ROW + lp;   // checkpoint 0; advanced by hstep per stored checkpoint
+    float* hs = hist + ((size_t)s * nseg * NB + blk) * R * ROW + ls;
     int ckc = 0;                     // steps until the next checkpoint
     // trials 2p, 2p+1 are packed into one f32x2 lane-pair state (Blackwell FFMA2); an odd last trial stays scalar
-    constexpr int NP = RT / 2, NS = RT % 2;
-    f32x2 cP[NP > 0 ? NP : 1][R], x0P[NP > 0 ? NP : 1][D];
+    f32x2 cP[NPA][R], x0P[NPA][D];
     float cS[R], x0S[D];
     double ll[RT];
-    {
-      float x0[RT][D];
-      LQGK_UNROLL for (int j = 0; j < RT; ++j) {
-        ll[j] = 0.0;
-        load_obs<D>(x_tm + (size_t)tr[j] * D, x0[j]);
-      }
-      LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) {
-        LQGK_UNROLL for (int k = 0; k < R; ++k) cP[p2][k] = f32x2{0.f, 0.f};
-        LQGK_UNROLL for (int m = 0; m < D; ++m) x0P[p2][m] = f32x2{x0[2 * p2][m], x0[2 * p2 + 1][m]};
-      }
-      LQGK_UNROLL for (int k = 0; k < R; ++k) cS[k] = 0.f;
-      LQGK_UNROLL for (int m = 0; m < D; ++m) x0S[m] = x0[RT - 1][m];
-    }
-    // prologue: x_{1..PF} in flight (one commit group per step)
+    LQGK_UNROLL for (int j = 0; j < RT; ++j) ll[j] = 0.0;
+    XB::template load<true>(xlp, xls, x0P, x0S);
+    LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) LQGK_UNROLL for (int k = 0; k < R; ++k) cP[p2][k] = f32x2{0.f, 0.f};
+    LQGK_UNROLL for (int k = 0; k < R; ++k) cS[k] = 0.f;
+    // prologue: x_{1..PF} in flight (one commit group per step); xnp/xns walk one row per step, clamped at row Tn
+    const float* xnp = xlp;
+    const float* xns = xls;
+    int trow = 0;                    // row xnp/xns point at
+    auto advance_row = [&]() { if (trow < Tn) { ++trow; xnp += xstep; xns += xstep; } };
     for (int p = 0; p < TRIAL_PF; ++p) {
-      const float* xrow = x_tm + (size_t)min(1 + p, Tn) * N * D;
-      LQGK_UNROLL for (int j = 0; j < RT; ++j) prefetch_obs<D>(pf + ((p % NSLOT) * RT + j) * 32 * D, lane, xrow + trD[j]);
-      cp_async_commit();
+      advance_row();
+      float* slot = pf + (p % NSLOT) * (D * ROW);
+      XB::copy_async(slot + lp, slot + ls, xnp, xns);
     }
     for (int k = 0; k < TRIAL_NST && k < nchunk; ++k) ring.issue(k, k);
+    int wslot = TRIAL_PF % NSLOT, rslot = 0;       // prefetch slot being filled / slot holding x_{t+1}
     for (int k = 0; k < nchunk; ++k) {
       const int st = k % TRIAL_NST;
       const float* chunk = ring.wait(st);
       const int t0 = k * TB, nst = min(TB, Tn - t0);
-      f32x2 partP[NP > 0 ? NP : 1];
+      f32x2 partP[NPA];
       float partS = 0.f;
       LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) partP[p2] = f32x2{0.f, 0.f};
 #pragma unroll 1
       for (int q = 0; q < nst; ++q) {
-        const int t = t0 + q;
         const float* r = chunk + q * DM::REC;
-        f32x2 x1P[NP > 0 ? NP : 1][D];
+        f32x2 x1P[NPA][D];
         float x1S[D];
         {   // prefetch x_{t+1+PF}, then make sure x_{t+1} has landed
-          const float* xrow = x_tm + (size_t)min(t + 1 + TRIAL_PF, Tn) * N * D;
-          float* slot = pf + ((t + TRIAL_PF) % NSLOT) * (RT * 32 * D);
-          LQGK_UNROLL for (int j = 0; j < RT; ++j) prefetch_obs<D>(slot + j * 32 * D, lane, xrow + trD[j]);
-          cp_async_commit();
+          advance_row();
+          float* slot = pf + wslot * (D * ROW);
+          XB::copy_async(slot + lp, slot + ls, xnp, xns);
           cp_async_wait<TRIAL_PF>();
-          const float* cur = pf + (t % NSLOT) * (RT * 32 * D);
-          LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) {
-            float xa[D], xb[D];
-            read_obs<D>(cur + (2 * p2) * 32 * D, lane, xa);
-            read_obs<D>(cur + (2 * p2 + 1) * 32 * D, lane, xb);
-            LQGK_UNROLL for (int m = 0; m < D; ++m) x1P[p2][m] = f32x2{xa[m], xb[m]};
-          }
-          if constexpr (NS) read_obs<D>(cur + (RT - 1) * 32 * D, lane, x1S);
+          const float* cur = pf + rslot * (D * ROW);
+          XB::template load<false>(cur + lp, cur + ls, x1P, x1S);
+          wslot = wslot + 1 == NSLOT ? 0 : wslot + 1;
+          rslot = rslot + 1 == NSLOT ? 0 : rslot + 1;
         }
         if (hist != nullptr) {
           if (ckc == 0) {            // t is a segment start: store the checkpoint c_t
             ckc = CK;
-            LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) {
-              if (ok[2 * p2 + 1]) {   // pair entry in one 64-bit store, straight from the f32x2 register pair
-                LQGK_UNROLL for (int m = 0; m < R; ++m)
-                  __stcs(reinterpret_cast<float2*>(hrow(m) + 64 * p2), make_float2(cP[p2][m].x, cP[p2][m].y));   // streaming: written once, read once
-              } else if (ok[2 * p2]) {   // odd N: the pad element gets 0
-                LQGK_UNROLL for (int m = 0; m < R; ++m) __stcs(reinterpret_cast<float2*>(hrow(m) + 64 * p2), make_float2(cP[p2][m].x, 0.f));
-              }
-            }
-            if constexpr (NS) {
-              if (ok[RT - 1]) { LQGK_UNROLL for (int m = 0; m < R; ++m) __stcs(hrow(m) + hsingle, cS[m]); }
-            }
-            LQGK_UNROLL for (int m = 0; m < NHP; ++m) hw[m] += hstep;
+            CB::store_streaming(hp, hs, cP, cS);
+            hp += hstep;
+            hs += hstep;
           }
           --ckc;
         }
@@ -855,8 +852,10 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS, trial_min_ctas<DM>()) k_tria
       if (k + TRIAL_NST < nchunk) ring.issue(k + TRIAL_NST, st);
     }
     cp_async_wait<0>();
-    LQGK_UNROLL for (int j = 0; j < RT; ++j)
-      if (ok[j]) ll_ws[(size_t)s * N + tr[j]] = ll[j];
+    LQGK_UNROLL for (int j = 0; j < RT; ++j) {
+      const int i = blk * ROW + trial_col<RT>(lane, j);
+      if (i < N) ll_ws[(size_t)s * N + i] = ll[j];
+    }
   }
 }
 
@@ -886,20 +885,27 @@ __host__ __device__ constexpr int pow2_ceil(int v) { return v <= 1 ? 1 : (v <= 2
 // reading c_t from the buffer, and writes the per-step sums over trials (DM::SUM_* layout) to sums[s][t][SUMP].  Every buffer
 // entry is private to the lane that owns the trial, so no warp synchronisation is needed around it.  Passes over trial blocks
 // accumulate (+=) into the sums.
+//
+// The backward walk is written as two alternating copies of the step (ping-pong): the cotangent cb and the observation rows
+// live in two register sets that swap roles every step, so nothing is copied from "next" to "current" at the loop edge
+// (those copies and the pairing of trial-major observations were a quarter of the instructions of the first version).
 template <class DM, int RT>
-__global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __restrict__ rec, const float* __restrict__ x_all,
-                                                                size_t x_sample_stride, int s_first, const float* __restrict__ hist,
+__global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __restrict__ rec, const float* __restrict__ xc_all,
+                                                                size_t xc_sample_stride, const float* __restrict__ hist,
                                                                 const float* __restrict__ w, int n_samples, int N, int Tn,
                                                                 float* __restrict__ sums) {
   constexpr int D = DM::D, R = DM::R;
   constexpr int CK = trial_ck<DM>(RT), ROW = 32 * RT, SLOT = R * ROW;
   constexpr int NFULL = DM::NSUM / 32, REM = DM::NSUM % 32, VREM = pow2_ceil(REM);
   constexpr int NP = RT / 2, NS = RT % 2, NPA = NP > 0 ? NP : 1;
+  using XB = LaneBlock<RT, D>;
+  using CB = LaneBlock<RT, R>;
   extern __shared__ __align__(128) unsigned char smraw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = blockIdx.x * TRIAL_WARPS + warp;
   if (s >= n_samples) return;
-  const float* __restrict__ x_tm = x_all + (size_t)(s_first + s) * x_sample_stride;   // this sample's observations
+  const int NB = (N + ROW - 1) / ROW;
+  const float* __restrict__ xc = xc_all + (size_t)s * xc_sample_stride;   // this sample's observations [T+1][NB][D][ROW]
   constexpr size_t RING_FLOATS = (size_t)2 * CK * DM::REC;
   float* ring_base = reinterpret_cast<float*>(smraw);
   uint64_t* bar_base = reinterpret_cast<uint64_t*>(ring_base + TRIAL_WARPS * RING_FLOATS);
@@ -909,71 +915,34 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __r
   RecRing<DM, CK, 2> ring{ring_base + (size_t)warp * RING_FLOATS, bar_base + warp * 2, rec + (size_t)s * Tn * DM::REC, Tn, lane, 0};
   ring.init();
   const int nseg = (Tn + CK - 1) / CK;
-  const int Nh = hist_stride(N);
-  for (int base = 0; base < N; base += 32 * RT) {
-    int trD[RT];
+  const size_t xstep = (size_t)NB * D * ROW, hstep = (size_t)NB * R * ROW;
+  const int lp = 2 * lane, ls = 64 * NP + lane;                       // this lane's pair / single column inside a block
+  for (int blk = 0; blk < NB; ++blk) {
     float wt[RT];
-    bool okP[NPA], okS = false;
     LQGK_UNROLL for (int j = 0; j < RT; ++j) {
-      int i = trial_of<RT>(base, lane, j);
-      bool ok = i < N;
-      int tr = ok ? i : N - 1;
-      trD[j] = tr * D;                            // slots beyond the last trial re-read trial N-1 (finite; masked by w = 0, cb = 0)
-      wt[j] = ok ? w[(size_t)s * N + tr] : 0.f;
-      if (j < 2 * NP) { if ((j & 1) == 0) okP[j >> 1] = ok; } else okS = ok;
+      const int i = blk * ROW + trial_col<RT>(lane, j);
+      wt[j] = i < N ? w[(size_t)s * N + i] : 0.f;  // columns beyond the last trial: w = 0, cb stays 0, their data are finite
     }
-    auto load_x = [&](int t, float (&x)[RT][D]) {
-      const float* xrow = x_tm + (size_t)t * N * D;
-      LQGK_UNROLL for (int j = 0; j < RT; ++j) load_obs<D>(xrow + trD[j], x[j]);
-    };
-    // this lane's entries of one buffer slot / one checkpoint: pair p at [m][64 p + 2 lane], the single at [m][64 NP + lane]
-    const int lofs = 2 * lane, sofs = 64 * NP + lane;
-    auto fetch_ckpt = [&](float* slot, const float* hk) {   // hk = hist + ((s * nseg + k) * R) * Nh + base
-      LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) LQGK_UNROLL for (int m = 0; m < R; ++m) {
-        float* dst = slot + m * ROW + 64 * p2 + lofs;
-        if (okP[p2]) cp_async<8>(dst, hk + (size_t)m * Nh + 64 * p2 + lofs);
-        else *reinterpret_cast<float2*>(dst) = make_float2(0.f, 0.f);
-      }
-      if constexpr (NS) {
-        LQGK_UNROLL for (int m = 0; m < R; ++m) {
-          float* dst = slot + m * ROW + sofs;
-          if (okS) cp_async<4>(dst, hk + (size_t)m * Nh + sofs);
-          else *dst = 0.f;
-        }
-      }
-      cp_async_commit();
-    };
-    auto load_slot = [&](const float* slot, f32x2 (&cp)[NPA][R], float (&cs)[R]) {
-      LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) LQGK_UNROLL for (int m = 0; m < R; ++m) {
-        float2 v = *reinterpret_cast<const float2*>(slot + m * ROW + 64 * p2 + lofs);
-        cp[p2][m] = f32x2{v.x, v.y};
-      }
-      if constexpr (NS) { LQGK_UNROLL for (int m = 0; m < R; ++m) cs[m] = slot[m * ROW + sofs]; }
-    };
-    auto store_slot = [&](float* slot, const f32x2 (&cp)[NPA][R], const float (&cs)[R]) {
-      LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) LQGK_UNROLL for (int m = 0; m < R; ++m)
-        *reinterpret_cast<float2*>(slot + m * ROW + 64 * p2 + lofs) = make_float2(cp[p2][m].x, cp[p2][m].y);
-      if constexpr (NS) { LQGK_UNROLL for (int m = 0; m < R; ++m) slot[m * ROW + sofs] = cs[m]; }
-    };
+    const float* xlp = xc + (size_t)blk * D * ROW + lp;              // row 0 of this block; row t at + t * xstep
+    const float* xls = xc + (size_t)blk * D * ROW + ls;
     auto next_slot = [&](float* p) { p += SLOT; return p == seg + CK * SLOT ? seg : p; };
     auto prev_slot = [&](float* p) { return (p == seg ? seg + CK * SLOT : p) - SLOT; };
-    // persistent state: cotangent cb of c_{t+1}, x_{t+1}, weights
-    f32x2 cbP[NPA][R], x1P[NPA][D], wP[NPA];
-    float cbS[R], x1S[D], wS = wt[RT - 1];
-    {
-      float x1[RT][D];
-      load_x(Tn, x1);
-      LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) {
-        LQGK_UNROLL for (int k = 0; k < R; ++k) cbP[p2][k] = f32x2{0.f, 0.f};
-        LQGK_UNROLL for (int m = 0; m < D; ++m) x1P[p2][m] = f32x2{x1[2 * p2][m], x1[2 * p2 + 1][m]};
-        wP[p2] = f32x2{wt[2 * p2], wt[2 * p2 + 1]};
-      }
-      LQGK_UNROLL for (int k = 0; k < R; ++k) cbS[k] = 0.f;
-      LQGK_UNROLL for (int m = 0; m < D; ++m) x1S[m] = x1[RT - 1][m];
+    // Ping-pong state of the backward walk.  A step of parity P reads the cotangent from cb[P] and leaves the next one in
+    // cb[P ^ 1]; it takes x_t from x[P] and x_{t+1} from x[P ^ 1] (the previous step's x_t) and, once the residual no longer
+    // needs x_{t+1}, requests x_{t-1} into x[P ^ 1].  A segment's walk starts with parity 1; after an even number of steps the
+    // carried state sits again where the next walk expects it (cb[1], x_{t+1} in x[0]).
+    f32x2 cbP[2][NPA][R], xP[2][NPA][D], wP[NPA];
+    float cbS[2][R], xS[2][D], wS = wt[RT - 1];
+    XB::template load<true>(xlp + (size_t)Tn * xstep, xls + (size_t)Tn * xstep, xP[0], xS[0]);
+    LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) {
+      LQGK_UNROLL for (int k = 0; k < R; ++k) cbP[1][p2][k] = f32x2{0.f, 0.f};
+      wP[p2] = f32x2{wt[2 * p2], wt[2 * p2 + 1]};
     }
-    const float* hk = hist + ((size_t)s * nseg + (nseg - 1)) * R * Nh + base;
+    LQGK_UNROLL for (int k = 0; k < R; ++k) cbS[1][k] = 0.f;
+    const float* hkp = hist + (((size_t)s * nseg + (nseg - 1)) * NB + blk) * R * ROW + lp;   // checkpoint of the segment to fetch next
+    const float* hks = hist + (((size_t)s * nseg + (nseg - 1)) * NB + blk) * R * ROW + ls;
     float* slot0 = seg;                            // buffer slot of the current segment's first step
-    fetch_ckpt(slot0, hk);
+    CB::copy_async(slot0 + lp, slot0 + ls, hkp, hks);
     ring.issue(nseg - 1, 0);
     if (nseg > 1) ring.issue(nseg - 2, 1);
     float* out = sums + ((size_t)s * Tn + (Tn - 1)) * DM::SUMP;
@@ -982,34 +951,28 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __r
       const int t0 = k * CK, nst = min(CK, Tn - t0);
       const float* chunk = ring.wait(st);
       cp_async_wait<0>();                          // checkpoint k is in slot0 (lane-private data: no warp sync needed)
+      const float* xsp = xlp + (size_t)t0 * xstep;  // observation row t0 of this lane (pairs / single)
+      const float* xss = xls + (size_t)t0 * xstep;
       // ---- (2) re-run the state recursion through the segment.  Fully unrolled (CK - 1 steps) so that the rotating buffer of
-      // observation rows xs[row % 4] has static indices: row j + 3 is requested while step j runs (the L2 round trip is
-      // longer than one of these short steps).
-      float x0c[RT][D];                            // x_t of the step the reverse walk starts with (t0 + nst - 1)
+      // observation rows xr[row % 4] has static indices: row j + 3 is requested while step j runs (the L2 round trip is
+      // longer than one of these short steps).  Leaves x_{t0 + nst - 1} in x[1] for the first step of the walk.
       float* sp = slot0;
       {
-        f32x2 cP[NPA][R];
-        float cS[R];
-        float xs[4][RT][D];
-        load_slot(sp, cP, cS);
-        load_x(t0, xs[0]);
-        if (nst > 1) load_x(t0 + 1, xs[1]);
-        if (nst > 2) load_x(t0 + 2, xs[2]);
+        f32x2 cP[NPA][R], xrP[4][NPA][D];
+        float cS[R], xrS[4][D];
+        CB::template load<false>(sp + lp, sp + ls, cP, cS);
+        XB::template load<true>(xsp, xss, xrP[0], xrS[0]);
+        if (nst > 1) XB::template load<true>(xsp + xstep, xss + xstep, xrP[1], xrS[1]);
+        if (nst > 2) XB::template load<true>(xsp + 2 * xstep, xss + 2 * xstep, xrP[2], xrS[2]);
         static_for<0, CK - 1>([&](auto QC) {
           constexpr int q = decltype(QC)::value;
           if (q + 1 < nst) {
-            if (q + 3 < nst) load_x(t0 + q + 3, xs[(q + 3) % 4]);
-            f32x2 xaP[NPA][D], xbP[NPA][D];
-            float xaS[D], xbS[D];
-            LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) LQGK_UNROLL for (int m = 0; m < D; ++m) {
-              xaP[p2][m] = f32x2{xs[q % 4][2 * p2][m], xs[q % 4][2 * p2 + 1][m]};
-              xbP[p2][m] = f32x2{xs[(q + 1) % 4][2 * p2][m], xs[(q + 1) % 4][2 * p2 + 1][m]};
-            }
-            LQGK_UNROLL for (int m = 0; m < D; ++m) { xaS[m] = xs[q % 4][RT - 1][m]; xbS[m] = xs[(q + 1) % 4][RT - 1][m]; }
+            if (q + 3 < nst) XB::template load<true>(xsp + (q + 3) * xstep, xss + (q + 3) * xstep, xrP[(q + 3) % 4], xrS[(q + 3) % 4]);
             const float* r = chunk + q * DM::REC;
             auto run = [&](const auto& rr) {
-              LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) Trial<DM>::template advance<f32x2>(rr, xaP[p2], xbP[p2], cP[p2]);
-              if constexpr (NS) Trial<DM>::template advance<float>(rr, xaS, xbS, cS);
+              LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2)
+                Trial<DM>::template advance<f32x2>(rr, xrP[q % 4][p2], xrP[(q + 1) % 4][p2], cP[p2]);
+              if constexpr (NS) Trial<DM>::template advance<float>(rr, xrS[q % 4], xrS[(q + 1) % 4], cS);
             };
             if constexpr (rec_in_regs<DM>()) {
               RecRegs<DM> rr;
@@ -1019,31 +982,32 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __r
               run(r);
             }
             sp = next_slot(sp);
-            store_slot(sp, cP, cS);
+            CB::store(sp + lp, sp + ls, cP, cS);
           }
         });
         static_for<0, CK>([&](auto JC) {             // x_{t0 + nst - 1}: static for full segments, selected for the ragged last one
           constexpr int j = decltype(JC)::value;
-          if (nst - 1 == j) { LQGK_UNROLL for (int jj = 0; jj < RT; ++jj) LQGK_UNROLL for (int m = 0; m < D; ++m) x0c[jj][m] = xs[j % 4][jj][m]; }
+          if (nst - 1 == j) {
+            LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) LQGK_UNROLL for (int m = 0; m < D; ++m) xP[1][p2][m] = xrP[j % 4][p2][m];
+            LQGK_UNROLL for (int m = 0; m < D; ++m) xS[1][m] = xrS[j % 4][m];
+          }
         });
       }
-      // ---- (3) walk the segment backwards; sp = slot of its last step, x0c = x_{t0 + nst - 1}
-#pragma unroll 1
-      for (int q = nst - 1; q >= 0; --q) {
-        const int t = t0 + q;
+      // ---- (3) walk the segment backwards; sp = slot of its last step
+      const float* xqp = xsp + (size_t)(nst - 1) * xstep;   // row of the step being processed; walks down one row per step
+      const float* xqs = xss + (size_t)(nst - 1) * xstep;
+      auto step = [&](auto PC, int q, bool top) {
+        constexpr int P = decltype(PC)::value, Q = P ^ 1;
         const float* r = chunk + q * DM::REC;
-        f32x2 x0P[NPA][D], cP[NPA][R];
-        float x0S[D], cS[R];
-        load_slot(sp, cP, cS);
-        LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) LQGK_UNROLL for (int m = 0; m < D; ++m) x0P[p2][m] = f32x2{x0c[2 * p2][m], x0c[2 * p2 + 1][m]};
-        LQGK_UNROLL for (int m = 0; m < D; ++m) x0S[m] = x0c[RT - 1][m];
-        if (q > 0) load_x(t - 1, x0c);              // next reverse step's x_t, one step ahead of its use
-        f32x2 eP[NPA][D], vP[NPA][D], wvP[NPA][D], nebP[NPA][D], cbnP[NPA][R];
-        float eS[D], vS[D], wvS[D], nebS[D], cbnS[R];
+        f32x2 cP[NPA][R];
+        float cS[R];
+        CB::template load<false>(sp + lp, sp + ls, cP, cS);
+        f32x2 eP[NPA][D], vP[NPA][D], wvP[NPA][D], nebP[NPA][D];
+        float eS[D], vS[D], wvS[D], nebS[D];
         auto run = [&](const auto& rr) {
           LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2)
-            Trial<DM>::template rev<f32x2>(rr, x0P[p2], x1P[p2], cP[p2], wP[p2], cbP[p2], eP[p2], vP[p2], wvP[p2], nebP[p2], cbnP[p2]);
-          if constexpr (NS) Trial<DM>::template rev<float>(rr, x0S, x1S, cS, wS, cbS, eS, vS, wvS, nebS, cbnS);
+            Trial<DM>::template rev<f32x2>(rr, xP[P][p2], xP[Q][p2], cP[p2], wP[p2], cbP[P][p2], eP[p2], vP[p2], wvP[p2], nebP[p2], cbP[Q][p2]);
+          if constexpr (NS) Trial<DM>::template rev<float>(rr, xS[P], xS[Q], cS, wS, cbS[P], eS, vS, wvS, nebS, cbS[Q]);
         };
         if constexpr (rec_in_regs<DM>()) {
           RecRegs<DM> rr;
@@ -1052,11 +1016,21 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __r
         } else {
           run(r);
         }
-        if (q == nst - 1 && k > 0) {
+        xqp -= xstep;
+        xqs -= xstep;
+        if (q > 0) {
+          // x_{t-1} for the next step, requested only after this step's residuals exist (the empty asm makes the row pointer
+          // depend on them): x_{t+1} in x[Q] is dead by then, so the loads land in its registers and no copy is needed
+          if constexpr (NP > 0) asm volatile("" : "+l"(xqp) : "l"(Ops<f32x2>::u(eP[0][0])));
+          else asm volatile("" : "+l"(xqs) : "f"(eS[0]));
+          XB::template load<true>(xqp, xqs, xP[Q], xS[Q]);
+        }
+        if (top && k > 0) {
           // the slot of the segment's last step has been consumed (its values are operands of the arithmetic above):
           // the checkpoint of the next segment to process lands there while this one is walked
-          hk -= (size_t)R * Nh;
-          fetch_ckpt(sp, hk);
+          hkp -= hstep;
+          hks -= hstep;
+          CB::copy_async(sp + lp, sp + ls, hkp, hks);
           slot0 = sp;
         }
         auto term = [&](auto IDXC) -> float {
@@ -1065,10 +1039,10 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __r
           if constexpr (NP > 0) {
             f32x2 acc = f32x2{0.f, 0.f};
             LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2)
-              acc = Trial<DM>::template sum_acc<IDX, f32x2>(acc, cbP[p2], nebP[p2], x0P[p2], cP[p2], eP[p2], vP[p2], wvP[p2]);
+              acc = Trial<DM>::template sum_acc<IDX, f32x2>(acc, cbP[P][p2], nebP[p2], xP[P][p2], cP[p2], eP[p2], vP[p2], wvP[p2]);
             a = acc.x + acc.y;
           }
-          if constexpr (NS) a = Trial<DM>::template sum_acc<IDX, float>(a, cbS, nebS, x0S, cS, eS, vS, wvS);
+          if constexpr (NS) a = Trial<DM>::template sum_acc<IDX, float>(a, cbS[P], nebS, xS[P], cS, eS, vS, wvS);
           return a;
         };
         static_for<0, NFULL>([&](auto G) {
@@ -1084,7 +1058,7 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __r
           const float tot = (part[0] + part[1]) + (part[2] + part[3]);
           __syncwarp();
           const int idx = decltype(G)::value * 32 + lane;
-          if (base == 0) out[idx] = tot;
+          if (blk == 0) out[idx] = tot;
           else out[idx] += tot;
         });
         if constexpr (REM > 0) {
@@ -1094,20 +1068,35 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __r
           const int vi = lane / (32 / VREM);
           const int idx = NFULL * 32 + vi;
           if ((lane % (32 / VREM)) == 0 && idx < DM::SUMP) {
-            if (base == 0) out[idx] = tot;
+            if (blk == 0) out[idx] = tot;
             else out[idx] += tot;
           }
         }
-        LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) {
-          LQGK_UNROLL for (int m = 0; m < R; ++m) cbP[p2][m] = cbnP[p2][m];
-          LQGK_UNROLL for (int m = 0; m < D; ++m) x1P[p2][m] = x0P[p2][m];
-        }
-        if constexpr (NS) {
-          LQGK_UNROLL for (int m = 0; m < R; ++m) cbS[m] = cbnS[m];
-          LQGK_UNROLL for (int m = 0; m < D; ++m) x1S[m] = x0S[m];
-        }
         out -= DM::SUMP;
         sp = prev_slot(sp);
+      };
+      {
+        int q = nst - 1;
+        bool top = true;
+#pragma unroll 1
+        while (true) {
+          step(std::integral_constant<int, 1>{}, q, top);
+          top = false;
+          if (--q < 0) {
+            // odd number of steps (ragged last segment, odd CK): put the carried state back where a walk starts from
+            LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) {
+              LQGK_UNROLL for (int m = 0; m < R; ++m) cbP[1][p2][m] = cbP[0][p2][m];
+              LQGK_UNROLL for (int m = 0; m < D; ++m) xP[0][p2][m] = xP[1][p2][m];
+            }
+            if constexpr (NS) {
+              LQGK_UNROLL for (int m = 0; m < R; ++m) cbS[1][m] = cbS[0][m];
+              LQGK_UNROLL for (int m = 0; m < D; ++m) xS[0][m] = xS[1][m];
+            }
+            break;
+          }
+          step(std::integral_constant<int, 0>{}, q, false);
+          if (--q < 0) break;
+        }
       }
       __syncwarp();
       if (kk + 2 < nseg) ring.issue(nseg - 1 - (kk + 2), st);

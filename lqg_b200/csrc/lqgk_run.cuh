@@ -119,7 +119,7 @@ constexpr bool is_big() { return DM::N > 12; }
 struct Plan {
   size_t Sc = 0, bytes = 0;
   size_t cst = 0, acc = 0, L = 0, K = 0, l = 0, H = 0, Sric = 0, Pkf = 0, Cs = 0, Lbar = 0, Kbar = 0, rec = 0, ll = 0,
-         sums = 0, hist = 0, w = 0, FU = 0, JS = 0, J0 = 0, SGB = 0, SGBI = 0, SFW = 0, KbarF = 0, scr = 0;
+         sums = 0, hist = 0, w = 0, FU = 0, JS = 0, J0 = 0, SGB = 0, SGBI = 0, SFW = 0, KbarF = 0, scr = 0, xc = 0;
 };
 
 template <class DM>
@@ -139,6 +139,8 @@ Plan make_plan(const LqgkDims& d, int mode, bool tv, size_t Sc) {
   } else {
     p.rec = take(sizeof(float) * Sc * T * DM::REC);
     p.ll = take(sizeof(double) * Sc * N);
+    const TrialGeom tg = trial_geom<DM>((int)N, (int)T);
+    p.xc = take(sizeof(float) * (d.x_sample_stride != 0 ? Sc : 1) * (T + 1) * tg.NB * d.d * tg.ROW);   // repacked observations
   }
   if (mode == LQGK_MODE_VJP) {
     p.acc = take(sizeof(double) * cl.total * Sc);
@@ -149,7 +151,10 @@ Plan make_plan(const LqgkDims& d, int mode, bool tv, size_t Sc) {
     p.Kbar = take(sizeof(double) * T * DM::EK * Sc);
     p.KbarF = take(sizeof(double) * T * DM::EK * Sc);
     p.sums = take(sizeof(float) * Sc * T * DM::SUMP);
-    p.hist = take(sizeof(float) * Sc * trial_nseg<DM>((int)N, (int)T) * DM::R * hist_stride((int)N));   // checkpoints of the carried state
+    {
+      const TrialGeom tg = trial_geom<DM>((int)N, (int)T);
+      p.hist = take(sizeof(float) * Sc * tg.nseg * tg.NB * DM::R * tg.ROW);   // checkpoints of the carried state
+    }
     p.w = take(sizeof(float) * Sc * N);
     using SR = CovSeqRev<DM>;
     p.FU = take(sizeof(double) * T * SR::NSF * Sc);
@@ -187,25 +192,39 @@ int set_smem(const void* fn, size_t bytes) {
   return LQGK_OK;
 }
 
-template <class DM, int RT>
-int launch_trial_fwd(cudaStream_t st, const float* rec, const float* x_tm, size_t xs, int s_first, int n, int N, int T, double* ll,
-                     float* hist) {
-  size_t smem = trial_smem_bytes<DM, RT, false>();
-  int rc = set_smem<DM>((const void*)k_trial_fwd<DM, RT>, smem);
-  if (rc) return rc;
-  ProfScope ps_(PK_TRIAL_FWD, st);
-  k_trial_fwd<DM, RT><<<(n + TRIAL_WARPS - 1) / TRIAL_WARPS, 32 * TRIAL_WARPS, smem, st>>>(rec, x_tm, xs, s_first, n, N, T, ll, hist);
+// Observations of one chunk in the per-trial kernels' component-major layout (k_repack_obs): one data set shared by all
+// samples (x_sample_stride == 0) or one per sample of the chunk.  Returns the element stride between the data sets in xc.
+inline int launch_repack_obs(cudaStream_t st, const LqgkDims& d, int row, const float* x_tm, int s0, int n, float* xc, size_t* xc_stride) {
+  const int nb = (d.N + row - 1) / row;
+  const bool per_sample = d.x_sample_stride != 0;
+  const size_t per = (size_t)(d.T + 1) * nb * d.d * row;
+  const int nsets = per_sample ? n : 1;
+  *xc_stride = per_sample ? per : 0;
+  const size_t total = per * nsets;
+  const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
+  ProfScope ps_(PK_PACK, st);
+  k_repack_obs<float><<<blocks, 256, 0, st>>>(x_tm, (size_t)d.x_sample_stride, per_sample ? s0 : 0, nsets, d.N, row, d.T + 1, d.d, xc);
   LQGK_LAUNCH_CHECK();
   return LQGK_OK;
 }
 template <class DM, int RT>
-int launch_trial_rev(cudaStream_t st, const float* rec, const float* x_tm, size_t xs, int s_first, const float* hist, const float* w, int n, int N,
-                     int T, float* sums) {
+int launch_trial_fwd(cudaStream_t st, const float* rec, const float* xc, size_t xcs, int n, int N, int T, double* ll, float* hist) {
+  size_t smem = trial_smem_bytes<DM, RT, false>();
+  int rc = set_smem<DM>((const void*)k_trial_fwd<DM, RT>, smem);
+  if (rc) return rc;
+  ProfScope ps_(PK_TRIAL_FWD, st);
+  k_trial_fwd<DM, RT><<<(n + TRIAL_WARPS - 1) / TRIAL_WARPS, 32 * TRIAL_WARPS, smem, st>>>(rec, xc, xcs, n, N, T, ll, hist);
+  LQGK_LAUNCH_CHECK();
+  return LQGK_OK;
+}
+template <class DM, int RT>
+int launch_trial_rev(cudaStream_t st, const float* rec, const float* xc, size_t xcs, const float* hist, const float* w, int n, int N, int T,
+                     float* sums) {
   size_t smem = trial_smem_bytes<DM, RT, true>();
   int rc = set_smem<DM>((const void*)k_trial_rev<DM, RT>, smem);
   if (rc) return rc;
   ProfScope ps_(PK_TRIAL_REV, st);
-  k_trial_rev<DM, RT><<<(n + TRIAL_WARPS - 1) / TRIAL_WARPS, 32 * TRIAL_WARPS, smem, st>>>(rec, x_tm, xs, s_first, hist, w, n, N, T, sums);
+  k_trial_rev<DM, RT><<<(n + TRIAL_WARPS - 1) / TRIAL_WARPS, 32 * TRIAL_WARPS, smem, st>>>(rec, xc, xcs, hist, w, n, N, T, sums);
   LQGK_LAUNCH_CHECK();
   return LQGK_OK;
 }
@@ -379,9 +398,11 @@ int run(const Call& c) {
     }
     const int RT = std::min((N + 31) / 32, trial_rt_max<DM>());
     float* hist = vjp ? F(p.hist) : nullptr;
+    size_t xcs = 0;
+    if ((rc = launch_repack_obs(st, d, 32 * RT, c.x_tm, (int)s0, n, F(p.xc), &xcs))) return rc;
     rc = LQGK_E_UNSUPPORTED;
     static_for<1, trial_rt_max<DM>() + 1>([&](auto RTC) {
-      if (RT == decltype(RTC)::value) rc = launch_trial_fwd<DM, decltype(RTC)::value>(st, F(p.rec), c.x_tm, (size_t)d.x_sample_stride, (int)s0, n, N, Tn, D(p.ll), hist);
+      if (RT == decltype(RTC)::value) rc = launch_trial_fwd<DM, decltype(RTC)::value>(st, F(p.rec), F(p.xc), xcs, n, N, Tn, D(p.ll), hist);
     });
     if (rc) return rc;
     {
@@ -405,7 +426,7 @@ int run(const Call& c) {
     rc = LQGK_E_UNSUPPORTED;
     static_for<1, trial_rt_max<DM>() + 1>([&](auto RTC) {
       if (RT == decltype(RTC)::value)
-        rc = launch_trial_rev<DM, decltype(RTC)::value>(st, F(p.rec), c.x_tm, (size_t)d.x_sample_stride, (int)s0, hist, F(p.w), n, N, Tn, F(p.sums));
+        rc = launch_trial_rev<DM, decltype(RTC)::value>(st, F(p.rec), F(p.xc), xcs, hist, F(p.w), n, N, Tn, F(p.sums));
     });
     if (rc) return rc;
     if (cudaMemsetAsync(D(p.acc), 0, sizeof(double) * cl.total * Sc, st) != cudaSuccess) return LQGK_E_CUDA;
