@@ -583,7 +583,11 @@ template <class DM> constexpr size_t smem_lqr_rev() {
 // The adjoint kernel needs ~240 registers; capped at 170 it spills and runs 1.6x slower (measured), so it stays at 2 CTAs.
 template <class DM>
 __host__ __device__ constexpr int trial_min_ctas() { return DM::N <= 6 ? 3 : 1; }
-constexpr int TRIAL_WARPS = 4;   // warps (= samples) per CTA
+constexpr int TRIAL_WARPS = 4;   // warps (= samples) per CTA of the forward kernel
+#ifndef LQGK_REV_WARPS
+#define LQGK_REV_WARPS 4
+#endif
+constexpr int TRIAL_WARPS_REV = LQGK_REV_WARPS;   // ... and of the adjoint kernel
 // time steps per ring stage of the forward kernel: 8 for the small records, fewer when one record is KBs (large systems)
 template <class DM>
 __host__ __device__ constexpr int trial_tb() { return DM::REC <= 128 ? 8 : (DM::REC <= 256 ? 4 : 2); }
@@ -637,7 +641,7 @@ template <class DM, int RT, bool REV>
 constexpr size_t trial_smem_bytes() {
   if constexpr (REV) {
     constexpr int CK = trial_ck<DM>(RT);
-    return (size_t)TRIAL_WARPS * (2 * CK * DM::REC * sizeof(float) + 2 * sizeof(uint64_t) + trial_red_bytes<DM>() +
+    return (size_t)TRIAL_WARPS_REV * (2 * CK * DM::REC * sizeof(float) + 2 * sizeof(uint64_t) + trial_red_bytes<DM>() +
                                   (size_t)CK * DM::R * 32 * RT * sizeof(float));
   } else {
     size_t ring = (size_t)TRIAL_WARPS * TRIAL_NST * trial_tb<DM>() * DM::REC * sizeof(float) + TRIAL_WARPS * TRIAL_NST * sizeof(uint64_t);
@@ -889,8 +893,14 @@ __host__ __device__ constexpr int pow2_ceil(int v) { return v <= 1 ? 1 : (v <= 2
 // The backward walk is written as two alternating copies of the step (ping-pong): the cotangent cb and the observation rows
 // live in two register sets that swap roles every step, so nothing is copied from "next" to "current" at the loop edge
 // (those copies and the pairing of trial-major observations were a quarter of the instructions of the first version).
+#ifndef LQGK_REV_MIN_CTAS
+#define LQGK_REV_MIN_CTAS 1
+#endif
+#ifndef LQGK_REV_REC_REGS
+#define LQGK_REV_REC_REGS 1
+#endif
 template <class DM, int RT>
-__global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __restrict__ rec, const float* __restrict__ xc_all,
+__global__ void __launch_bounds__(32 * TRIAL_WARPS_REV, LQGK_REV_MIN_CTAS) k_trial_rev(const float* __restrict__ rec, const float* __restrict__ xc_all,
                                                                 size_t xc_sample_stride, const float* __restrict__ hist,
                                                                 const float* __restrict__ w, int n_samples, int N, int Tn,
                                                                 float* __restrict__ sums) {
@@ -902,16 +912,16 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __r
   using CB = LaneBlock<RT, R>;
   extern __shared__ __align__(128) unsigned char smraw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int s = blockIdx.x * TRIAL_WARPS + warp;
+  const int s = blockIdx.x * TRIAL_WARPS_REV + warp;
   if (s >= n_samples) return;
   const int NB = (N + ROW - 1) / ROW;
   const float* __restrict__ xc = xc_all + (size_t)s * xc_sample_stride;   // this sample's observations [T+1][NB][D][ROW]
   constexpr size_t RING_FLOATS = (size_t)2 * CK * DM::REC;
   float* ring_base = reinterpret_cast<float*>(smraw);
-  uint64_t* bar_base = reinterpret_cast<uint64_t*>(ring_base + TRIAL_WARPS * RING_FLOATS);
-  float* red_base = reinterpret_cast<float*>(bar_base + TRIAL_WARPS * 2);                     // 16-byte aligned
+  uint64_t* bar_base = reinterpret_cast<uint64_t*>(ring_base + TRIAL_WARPS_REV * RING_FLOATS);
+  float* red_base = reinterpret_cast<float*>(bar_base + TRIAL_WARPS_REV * 2);                     // 16-byte aligned
   float* red = red_base + (size_t)warp * (trial_red_bytes<DM>() / sizeof(float));
-  float* seg = red_base + (size_t)TRIAL_WARPS * (trial_red_bytes<DM>() / sizeof(float)) + (size_t)warp * CK * SLOT;
+  float* seg = red_base + (size_t)TRIAL_WARPS_REV * (trial_red_bytes<DM>() / sizeof(float)) + (size_t)warp * CK * SLOT;
   RecRing<DM, CK, 2> ring{ring_base + (size_t)warp * RING_FLOATS, bar_base + warp * 2, rec + (size_t)s * Tn * DM::REC, Tn, lane, 0};
   ring.init();
   const int nseg = (Tn + CK - 1) / CK;
@@ -974,7 +984,7 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __r
                 Trial<DM>::template advance<f32x2>(rr, xrP[q % 4][p2], xrP[(q + 1) % 4][p2], cP[p2]);
               if constexpr (NS) Trial<DM>::template advance<float>(rr, xrS[q % 4], xrS[(q + 1) % 4], cS);
             };
-            if constexpr (rec_in_regs<DM>()) {
+            if constexpr (rec_in_regs<DM>() && LQGK_REV_REC_REGS) {
               RecRegs<DM> rr;
               rr.load(r);
               run(rr);
@@ -1009,7 +1019,7 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS) k_trial_rev(const float* __r
             Trial<DM>::template rev<f32x2>(rr, xP[P][p2], xP[Q][p2], cP[p2], wP[p2], cbP[P][p2], eP[p2], vP[p2], wvP[p2], nebP[p2], cbP[Q][p2]);
           if constexpr (NS) Trial<DM>::template rev<float>(rr, xS[P], xS[Q], cS, wS, cbS[P], eS, vS, wvS, nebS, cbS[Q]);
         };
-        if constexpr (rec_in_regs<DM>()) {
+        if constexpr (rec_in_regs<DM>() && LQGK_REV_REC_REGS) {
           RecRegs<DM> rr;
           rr.load(r);
           run(rr);

@@ -224,7 +224,7 @@ int launch_trial_rev(cudaStream_t st, const float* rec, const float* xc, size_t 
   int rc = set_smem<DM>((const void*)k_trial_rev<DM, RT>, smem);
   if (rc) return rc;
   ProfScope ps_(PK_TRIAL_REV, st);
-  k_trial_rev<DM, RT><<<(n + TRIAL_WARPS - 1) / TRIAL_WARPS, 32 * TRIAL_WARPS, smem, st>>>(rec, xc, xcs, hist, w, n, N, T, sums);
+  k_trial_rev<DM, RT><<<(n + TRIAL_WARPS_REV - 1) / TRIAL_WARPS_REV, 32 * TRIAL_WARPS_REV, smem, st>>>(rec, xc, xcs, hist, w, n, N, T, sums);
   LQGK_LAUNCH_CHECK();
   return LQGK_OK;
 }
