@@ -2,30 +2,35 @@
 """bench.py -- headline metric of BASELINE.json: trial log-lik+grad evals/sec on B200, with roofline fractions,
 next to the reference algorithm on the host CPU.
 
-Workload (config c3 of BASELINE.json): SubjectiveActor 2-D tracking, N=100 trials x T=1200, a sweep of
-S parameter samples PER GPU (default 32,768 = half of the 65,536-sample target on every GPU; weak scaling: N GPUs
-evaluate N*S samples per step).  One "step" = one log-likelihood + parameter-gradient evaluation of all S samples
-(S*100 trial evals).  Data are synthetic: the GPU legs simulate them with the product's own System.simulate (torch Philox,
-seed 7), the CPU legs with the oracle's restatement (NumPy PCG64, seed 7); parameter samples are theta_true * exp(0.25 z),
-z ~ N(0, I_6), seed 11 + rank.
+Workload = config c3 of BASELINE.json exactly ("Batched likelihood sweep: 65,536 parameter samples x 100 trials x T=1200,
+sharded over 1/2/4/8 B200"): SubjectiveActor 2-D tracking, N=100 trials x T=1200, a sweep of 65,536 parameter samples IN
+TOTAL, sharded over the GPUs by parameter samples (STRONG scaling: every rank evaluates 65,536 / n_gpus samples).  One
+"step" = one log-likelihood + parameter-gradient evaluation of all 65,536 samples (6,553,600 trial evals).  Data are
+synthetic: the GPU legs simulate them with the product's own System.simulate (torch Philox, seed 7), the CPU legs with the
+oracle's restatement (NumPy PCG64, seed 7); parameter samples are theta_true * exp(0.25 z), z ~ N(0, I_6), seed 11.
 
-  value : device-resident (base matrices + observations already in HBM), CUDA events, max over ranks.
+  value : device-resident (base matrices + observations already in HBM) through the C ABI, CUDA events, max over ranks;
+          every rank ends the step with the complete sweep result (all-gather of the per-sample [ll, base-matrix gradients]
+          through lqg_b200.parallel -- the path's one collective).
   e2e   : through the public API (lqg_b200.tracking.SubjectiveActor(...).log_likelihood(x).sum().backward()) with
-          theta in pinned HOST memory every step: H2D of theta + observations, model construction, fused
-          forward+adjoint, D2H of ll[S] and grad[S,6].
-  roofline : dominant kernel, algorithmic FLOPs (SURVEY 8d convention) / its live CUDA-event time, against the
-          FP32 FMA peak measured in this run by an FFMA-saturating micro-kernel (MEASURED_PEAKS.json has no FP32
-          figure); HBM fraction reported beside it.
+          theta and x in pinned HOST memory every step: H2D of this rank's theta slice + observations, model construction,
+          fused forward+adjoint, all-gather of [ll, grad] over the ranks, D2H of ll[S] and grad[S,6].
+  roofline : dominant kernel.  `frac` = FP32 operations the kernel EXECUTES (instruction counts of this very build from the
+          committed ncu capture, profiles/r02_counters.json, keyed by a hash of the kernel sources) / its live CUDA-event time,
+          against the FP32 FMA peak measured in this run (MEASURED_PEAKS.json has no FP32 figure).  `algorithmic_frac` keeps the
+          SURVEY 8(d) dense-count convention.  `bound` = whichever of the step's HBM floor and FP32 floor is larger.
   cpu_baseline : the oracle's torch-float64 port of the reference algorithm (autodiff through the three scans),
           all host threads, on a bounded sample (64 samples x 100 trials x T=1200).
+  secondary : BASELINE configs c2 (6 conditions x 20 trials, conditions sharded over the ranks + one all-reduce of
+          [ll, grad]), c5 (one leapfrog of 4,096 lock-step chains, chains sharded over the ranks) at every N; c4 at N=1.
 
-`--impl reference` runs only that CPU port (the real JAX reference is not installable in this image).
+`--impl reference` runs only the CPU port (the real JAX reference is not installable in this image).
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
-import math
 import os
 import subprocess
 import sys
@@ -41,6 +46,7 @@ import torch  # noqa: E402
 PARAM_NAMES = ("action_cost", "action_variability", "subj_noise", "subj_vel_noise", "sigma_target", "sigma_cursor")
 THETA_TRUE = (1.0, 0.5, 1.0, 0.5, 19.9, 6.0)
 DIMS = dict(x=4, b=6, u=2, y=4, d=4)
+COUNTERS = os.path.join(ROOT, "profiles", "r02_counters.json")
 
 
 # ----------------------------------------------------------------------------------------------- flop model
@@ -48,20 +54,35 @@ def mm(m, k, n):
     return 2 * m * k * n
 
 
-def algorithmic_flops(x, b, u, y, d, N, T):
-    """Forward flops of one system evaluation, SURVEY 8(d) convention (dense algebra of the reference recursions).
-    Returns (per-sample-per-step, per-trial-per-step, forward total).  fwd+grad = 3x forward by convention."""
-    n, m = x + b, x + y
+def sample_flops(x, b, u, y):
     lqr = (2 * mm(u, b, b) + mm(u, b, u) + mm(u, b, 1) + 10 * u ** 3 + (2 * u ** 3) // 3 + 2 * u * u * b + 2 * u * u
            + 2 * mm(b, b, b) + mm(b, u, u) + 3 * mm(b, u, b) + 4 * b * b + mm(b, b, 1) + 3 * mm(b, u, 1) + mm(u, u, 1) + 4 * b)
     kf = (3 * mm(b, b, b) + b * b + mm(y, b, b) + mm(y, b, y) + mm(y, y, y) + y * y + 2 * y ** 3 + mm(b, b, y) + mm(b, y, y)
           + mm(b, y, b) + b + mm(b, b, b))
+    return lqr, kf
+
+
+def algorithmic_flops(x, b, u, y, d, N, T):
+    """Forward flops of one system evaluation, SURVEY 8(d) convention (dense algebra of the reference recursions).
+    Returns (per-sample-per-step, per-trial-per-step, forward total).  fwd+grad = 3x forward by convention."""
+    n, m = x + b, x + y
+    lqr, kf = sample_flops(x, b, u, y)
     joint = (mm(x, u, b) + 2 * (mm(b, y, x) + mm(b, x, x)) + 2 * mm(b, u, b) + mm(b, y, b) + mm(b, b, b) + mm(y, x, u)
              + mm(y, b, u) + y * u + mm(b, y, u) + 3 * b * b + mm(b, y, y))
     cov = 2 * mm(n, n, n) + mm(n, m, n) + 2 * (d ** 3 // 3) + 2 * n * d * d + mm(n, d, n) + 2 * n * n + d
     trial = 2 * n * n + 2 * n * d + n + d * d + 4 * d
     per_sample = lqr + kf + joint + cov
     return per_sample, trial, T * (per_sample + N * trial)
+
+
+def source_sha():
+    """Hash of the kernel sources: ties profiles/r02_counters.json (instruction counts from an ncu capture) to the build."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "lqg_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".h")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
 
 
 # ----------------------------------------------------------------------------------------------- helpers
@@ -155,71 +176,74 @@ def cpu_port_eval(S, N, T, X, seed=3):
     return time.perf_counter() - t0
 
 
-def bench_c2(dev, reps=10):
+def timed(fn, reps, warm, barrier):
+    """ms per call of fn: CUDA events on the current stream, bracketed by barriers (the caller takes the max over ranks)."""
+    for _ in range(warm):
+        out = fn()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        out = fn()
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1) / reps, out
+
+
+# ----------------------------------------------------------------------------------------------- secondary workloads
+def bench_c2(dev, barrier, reps=10):
     """Config c2 of BASELINE.json (latency case): SubjectiveActor 2-D, 6 blob-width conditions x 20 trials x T=1200, gradient
-    w.r.t. 5 shared + 6 per-condition parameters, ONE fused call (conditions = the kernels' sample axis, every condition its
-    own trials), through the public API.  Returns (trial-evals/s, ms per evaluation)."""
+    w.r.t. 5 shared + 6 per-condition parameters.  The conditions are the kernels' sample axis (every condition its own
+    trials); with several GPUs the conditions are sharded over the ranks and ONE all-reduce sums [ll, grad] (the collective the
+    north star names; lqg_b200.parallel.trial_sharded_value_and_grad).  Returns ms per evaluation."""
+    from lqg_b200 import parallel
     from lqg_b200.tracking import SubjectiveActor
     sig = [8.5, 9.7, 11.8, 19.9, 28.5, 51.6]
     T, N = 1200, 20
     x = torch.stack([make_data_gpu(N, T, dev, seed=c, sigma_target=s_t, action_cost=1.0, sigma_cursor=6.0) for c, s_t in enumerate(sig)])
-    shared = torch.tensor([1.0, 0.5, 1.0, 0.5, 6.0], device=dev, requires_grad=True)   # cost, variab., subj, subj_vel, sigma_cursor
-    st = torch.tensor(sig, device=dev, requires_grad=True)
+    cond = torch.arange(len(sig), device=dev)
 
-    def evaluate():
-        shared.grad = st.grad = None
+    def local(idx):   # idx: this rank's conditions -> (sum ll, grad[5 + 6])
+        shared = torch.tensor([1.0, 0.5, 1.0, 0.5, 6.0], device=dev, requires_grad=True)   # cost, variab., subj, subj_vel, sigma_cursor
+        st = torch.tensor(sig, device=dev, requires_grad=True)
+        if idx.numel() == 0:
+            return torch.zeros((), device=dev), torch.zeros(5 + len(sig), device=dev)
         m = SubjectiveActor(dim=2, T=T, device=dev, action_cost=shared[0], action_variability=shared[1], subj_noise=shared[2],
-                            subj_vel_noise=shared[3], sigma_cursor=shared[4], sigma_target=st)
-        ll = m.log_likelihood(x).sum()
+                            subj_vel_noise=shared[3], sigma_cursor=shared[4], sigma_target=st[idx])
+        ll = m.log_likelihood(x[idx]).sum()
         ll.backward()
-        return ll
+        return ll.detach(), torch.cat([shared.grad, st.grad])
 
-    for _ in range(3):
-        evaluate()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        ll = evaluate()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
-    assert torch.isfinite(ll) and torch.isfinite(shared.grad).all() and torch.isfinite(st.grad).all()
-    return len(sig) * N / (ms * 1e-3), ms
+    ms, (ll, g) = timed(lambda: parallel.trial_sharded_value_and_grad(local, cond), reps, 3, barrier)
+    assert torch.isfinite(ll) and torch.isfinite(g).all()
+    return ms
 
 
-def bench_c5(dev, chains=4096, N=100, T=1200, reps=5):
+def bench_c5(dev, barrier, chains=4096, N=100, T=1200, reps=5):
     """Config c5 of BASELINE.json without numpyro (not installable): the work of ONE leapfrog step of 4,096 lock-step chains =
-    one fused log-likelihood + gradient evaluation of 4,096 parameter vectors on the c3 data, through the public API.
-    Returns (leapfrog-equivalents/s, ms per evaluation)."""
+    one fused log-likelihood + gradient evaluation of 4,096 parameter vectors on the c3 data, chains sharded over the ranks
+    (every rank owns its chains: no collective per leapfrog).  Returns ms per evaluation."""
+    from lqg_b200 import parallel
     from lqg_b200.tracking import SubjectiveActor
     x = make_data_gpu(N, T, dev)
-    theta = torch.tensor(make_theta(chains, 23), device=dev, requires_grad=True)
+    theta = torch.tensor(make_theta(chains, 23), device=dev)
 
-    def evaluate():
-        theta.grad = None
-        m = SubjectiveActor(dim=2, T=T, device=dev, **{n: theta[:, i] for i, n in enumerate(PARAM_NAMES)})
-        ll = m.log_likelihood(x).sum()
-        ll.backward()
-        return ll
+    def local(th):
+        th = th.detach().requires_grad_()
+        m = SubjectiveActor(dim=2, T=T, device=dev, **{n: th[:, i] for i, n in enumerate(PARAM_NAMES)})
+        ll = m.log_likelihood(x).sum(-1)
+        ll.sum().backward()
+        return ll.detach(), th.grad
 
-    evaluate()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        ll = evaluate()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
-    assert torch.isfinite(ll) and torch.isfinite(theta.grad).all()
-    return 1e3 / ms, ms
+    ms, (ll, g) = timed(lambda: parallel.sharded_value_and_grad(local, theta, gather=False), reps, 2, barrier)
+    assert torch.isfinite(ll).all() and torch.isfinite(g).all()
+    return ms
 
 
 def bench_c4(dev, S=4096, N=50, T=600, reps=2):
     """Config c4 of BASELINE.json: TemporalDelayModel(PointMassBoundedActor(T=600), delay=2) -- 12-dim state, joint dim 24
     (large-system kernels, lqgk_big.cuh) --, 4,096 parameter samples x 50 trials, log-likelihood + gradient w.r.t. 4
-    parameters per sample through the public API.  Returns (trial-evals/s, ms per evaluation)."""
+    parameters per sample through the public API.  Returns (trial-evals/s, ms per evaluation, per-kernel ms)."""
     from lqg_b200.tracking import PointMassBoundedActor
     from lqg_b200.tracking.delay import TemporalDelayModel
     base = dict(action_variability=1e-3, sigma_target=6.0, sigma_cursor=6.0, action_cost=0.01)
@@ -254,6 +278,19 @@ def bench_c4(dev, S=4096, N=50, T=600, reps=2):
 
 
 # ----------------------------------------------------------------------------------------------- reference arm
+def workload_config(args, world, note=None):
+    cfg = {"workload": "c3: batched likelihood sweep, 65,536 parameter samples x 100 trials x T=1200 (SubjectiveActor dim=2: x=4,b=6,u=2,"
+                       "y=4,d=4), log-lik + gradient, sharded over the GPUs by parameter samples",
+           "samples_total": args.samples, "samples_per_gpu": args.samples // world, "trials": args.trials, "T": args.T,
+           "params": len(PARAM_NAMES),
+           "sharding": "parameter samples across GPUs (no data-path collective); one all-gather of the per-sample [ll, gradients] "
+                       "(lqg_b200.parallel) so every rank holds the whole sweep",
+           "cache": "per-step workspace traffic (tens of GB) >> 126 MB L2; no explicit flush needed"}
+    if note:
+        cfg["note"] = note
+    return cfg
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -270,30 +307,21 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     line = {"impl": "reference", "metric": "trial log-lik+grad evals/sec", "value": val, "unit": "trial-evals/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, S_per_gpu=S, note="CPU port of the reference algorithm (oracle/lqg_torch.py); "
-                                      "the JAX reference is not installable in this image"),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, max(1, args.gpus),
+                                      note=f"CPU port of the reference algorithm (oracle/lqg_torch.py) on a bounded sample of the workload: "
+                                           f"{S} of the {args.samples} parameter samples per step; the JAX reference is not installable in this image"),
             "cpu_baseline": {"value": val, "unit": "trial-evals/s", "cores": cores, "kind": "port",
                              "sample": f"{S} parameter samples x {N} trials x T={T}, fwd+grad by torch autograd, float64"},
             "e2e": {"value": val, "unit": "trial-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
 
-def workload_config(args, S_per_gpu, note=None):
-    cfg = {"workload": "c3: SubjectiveActor dim=2 (x=4,b=6,u=2,y=4,d=4), parameter-sample sweep, log-lik + gradient",
-           "samples_per_gpu": S_per_gpu, "trials": args.trials, "T": args.T, "params": len(PARAM_NAMES),
-           "sharding": "parameter samples across GPUs (no data-path collective); one NCCL all-reduce of [sum ll, sum grad]",
-           "cache": "per-step workspace traffic (tens of GB) >> 126 MB L2; no explicit flush needed"}
-    if note:
-        cfg["note"] = note
-    return cfg
-
-
 # ----------------------------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch.distributed as dist
 
-    from lqg_b200 import abi, runtime
+    from lqg_b200 import abi, parallel, runtime
     from lqg_b200.tracking import SubjectiveActor
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -311,11 +339,14 @@ def run_ours(args):
         lib.set_kernel_overlap(args.overlap)
     if args.contrib_warps > 0:
         lib.lib.lqgk_set_contrib_warps(args.contrib_warps)
-    S, N, T = args.samples, args.trials, args.T
-    theta_np = make_theta(S, 11 + rank)
+    S_total, N, T = args.samples, args.trials, args.T
+    lo, hi = parallel.shard_range(S_total, rank, world)
+    S = hi - lo                                        # this rank's samples (strong scaling)
+    theta_all = make_theta(S_total, 11)
+    theta_np = theta_all[lo:hi]
     P = theta_np.shape[1]
 
-    # ---------------- device-resident leg
+    # ---------------- device-resident leg (C ABI)
     theta = torch.tensor(theta_np, device=dev)
     model = SubjectiveActor(dim=2, T=T, device=dev, **{n: theta[:, i] for i, n in enumerate(PARAM_NAMES)})
     x_dev = make_data_gpu(N, T, dev)
@@ -333,18 +364,16 @@ def run_ours(args):
     x_tm = lib.pack_obs(xk.contiguous(), stream=torch.cuda.current_stream().cuda_stream)
     act = {k: runtime._row_major(getattr(sysm.actor, k)[:, 0]) for k in abi.ACTOR_KEYS}
     dyn = {k: runtime._row_major(getattr(sysm.dynamics, k)[:, 0]) for k in abi.DYN_KEYS}
-    ws = runtime.workspace(dev, lib.workspace_bytes(dims, abi.MODE_VJP, args.chunk))
-    red = torch.zeros(1 + 12, device=dev)
+    ws_bytes_one_chunk = lib.workspace_bytes(dims, abi.MODE_VJP, args.chunk)
+    ws = runtime.workspace(dev, ws_bytes_one_chunk)
 
     def step_resident():
         st = torch.cuda.current_stream().cuda_stream
         ll, ga, gd, _ = lib.loglik_vjp(dims, act, dyn, x_tm, ws=ws, stream=st)
-        if world > 1:
-            red[0] = ll.sum()
-            for i, g in enumerate(list(ga.values()) + list(gd.values())):
-                red[1 + i] = g.sum()
-            dist.all_reduce(red)          # the path's one collective: [sum ll, sum grad] over NVLink
-        return ll
+        # the sweep result of this rank: per sample [sum_i ll_i, all base-matrix gradients]; gathered so that every rank holds
+        # the complete sweep (the path's one collective, lqg_b200.parallel)
+        packed = torch.cat([ll.sum(1, keepdim=True)] + [g.reshape(S, -1) for g in list(ga.values()) + list(gd.values())], 1)
+        return parallel.gather_samples(packed, S_total)
 
     def barrier():
         torch.cuda.synchronize()
@@ -355,7 +384,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()                                   # started before the warm-up so samples exist when the timed region begins
     for _ in range(args.warmup):
-        ll = step_resident()
+        res = step_resident()
     barrier()
     launches_per_step = lib.last_launch_count()
     lib.profile_enable(True)
@@ -364,7 +393,7 @@ def run_ours(args):
     sampler.mark_start()
     e0.record()
     for _ in range(args.steps):
-        ll = step_resident()
+        res = step_resident()
     e1.record()
     barrier()
     sampler.mark_end()
@@ -372,18 +401,19 @@ def run_ours(args):
     prof = lib.profile_read()
     lib.profile_enable(False)
     clocks = sampler.stop()
-    assert torch.isfinite(ll).all(), "non-finite log-likelihood in the timed region"
+    assert res.shape[0] == S_total and torch.isfinite(res).all(), "non-finite sweep result in the timed region"
+    del res
     t_ms = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms = float(t_ms.item())
     ms_per_step = ms / args.steps
-    value = world * S * N / (ms_per_step * 1e-3)
+    value = S_total * N / (ms_per_step * 1e-3)
 
     # ---------------- end-to-end leg through the public API, host buffers
     theta_host = torch.tensor(theta_np).pin_memory()
     x_host = torch.tensor(X).pin_memory()
-    out_host = torch.empty((S, 1 + P), dtype=torch.float32).pin_memory()
+    out_host = torch.empty((S_total, 1 + P), dtype=torch.float32).pin_memory()
 
     def step_e2e():
         th = theta_host.to(dev, non_blocking=True).requires_grad_()
@@ -391,12 +421,9 @@ def run_ours(args):
         m = SubjectiveActor(dim=2, T=T, device=dev, **{n: th[:, i] for i, n in enumerate(PARAM_NAMES)})
         lls = m.log_likelihood(xd).sum(-1)
         lls.sum().backward()
-        out = torch.cat([lls.detach()[:, None], th.grad], 1)
-        if world > 1:
-            red[:1 + P] = out.sum(0)
-            dist.all_reduce(red)
-        out_host.copy_(out, non_blocking=True)
-        return out
+        full = parallel.gather_samples(torch.cat([lls.detach()[:, None], th.grad], 1), S_total)   # [S_total, 1 + P] on every rank
+        out_host.copy_(full, non_blocking=True)
+        return full
 
     for _ in range(max(1, min(args.warmup, 2))):
         step_e2e()
@@ -410,21 +437,36 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e_ms = float(t_e.item()) / args.steps
-    e2e_val = world * S * N / (e2e_ms * 1e-3)
+    e2e_val = S_total * N / (e2e_ms * 1e-3)
     assert np.isfinite(out_host.numpy()).all()
+
+    # ---------------- secondary workloads (every rank takes part: they shard over the ranks)
+    secondary = []
+    if not args.no_secondary:
+        c2_ms = bench_c2(dev, barrier)
+        c5_ms = bench_c5(dev, barrier)
+        t2 = torch.tensor([c2_ms, c5_ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        c2_ms, c5_ms = [float(v) for v in t2.tolist()]
+        secondary.append({"workload": "c2: SubjectiveActor dim=2, 6 conditions x 20 trials x T=1200, grad wrt 5 shared + 6 per-condition "
+                                      "parameters, public API; conditions sharded over the GPUs + one all-reduce of [ll, grad] (latency-bound)",
+                          "value": 6 * 20 / (c2_ms * 1e-3), "unit": "trial-evals/s", "ms_per_eval": c2_ms})
+        secondary.append({"workload": "c5: one leapfrog of 4,096 lock-step chains = one fused log-lik+gradient of 4,096 parameter vectors x 100 "
+                                      "trials x T=1200, chains sharded over the GPUs, public API (numpyro/NUTS itself is not installable here)",
+                          "value": 1e3 / c5_ms, "unit": "leapfrog-equivalents/s", "ms_per_eval": c5_ms,
+                          "chains_per_gpu": 4096 // world})
 
     if rank == 0:
         # ---------------- roofline of the dominant kernel + whole step
         per_sample, per_trial, fwd = algorithmic_flops(DIMS["x"], DIMS["b"], DIMS["u"], DIMS["y"], DIMS["d"], N, T)
-        step_flops = 3.0 * fwd * S                                 # fwd+grad = 3x forward (SURVEY 8d convention)
-        # attribution of the "fwd+grad = 3x forward" convention to the kernels: forward kernels 1x, adjoints 2x
-        lqr_f, kf_f = [T * v for v in split_sample_flops()[:2]]
+        step_flops = 3.0 * fwd * S_total                           # fwd+grad = 3x forward (SURVEY 8d convention)
+        lqr_f, kf_f = [T * v for v in sample_flops(DIMS["x"], DIMS["b"], DIMS["u"], DIMS["y"])]
         cov_f = T * per_sample - lqr_f - kf_f
         kind_flops = {"lqr_fwd": lqr_f, "kf_fwd": kf_f, "cov_fwd": cov_f, "trial_fwd": T * N * per_trial,
                       "lqr_rev": 2 * lqr_f, "kf_rev": 2 * kf_f, "cov_rev": 2 * cov_f, "trial_rev": 2 * T * N * per_trial}
         fp32_peak = lib.peak_fma(False, dev)
         fp64_peak = lib.peak_fma(True, dev)
-        # stages = groups of kernels that together implement one reference function (row of SURVEY 8a)
         groups = {"lqr_fwd": ["lqr_fwd"], "kf_fwd": ["kf_fwd"], "cov_fwd": ["cov_fwd"], "trial_fwd": ["trial_fwd"],
                   "trial_rev": ["trial_rev"], "cov_rev": ["cov_rev", "cov_contrib", "reduce"], "kf_rev": ["kf_rev"],
                   "lqr_rev": ["lqr_rev"], "boundary": ["pack", "unpack", "misc"]}
@@ -440,41 +482,79 @@ def run_ours(args):
                 entry["algorithmic_tflops"] = kind_flops[g] * S / (g_ms * 1e-3) / 1e12
             kernels[g] = entry
         dom = max((k for k in kernels if k in kind_flops), key=lambda k: kernels[k]["ms_per_step"])
-        dom_launches = max(1.0, kernels[dom]["launches_per_step"])
-        achieved = kernels[dom]["algorithmic_tflops"]
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
-        hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        ws_bytes = 2.0 * lib.workspace_bytes(dims, abi.MODE_VJP, 0)   # every workspace array is written once and read (at least) once
         dom_kernel = max(kernels[dom]["kernels"], key=lambda k: kernels[dom]["kernels"][k])
         dom_ms = kernels[dom]["kernels"][dom_kernel]                  # live CUDA-event time of that kernel per step
-        # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture, if it was taken on this launch shape
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tpath):
-            tj = json.load(open(tpath)).get(dom_kernel)
-            launches = max(1.0, kernels[dom]["launches_per_step"] if len(kernels[dom]["kernels"]) == 1 else 1.0)
-            if tj and tj["samples_per_launch"] * launches == S and tj["pseudo_trials"] == dims.N and tj["T"] == T:
-                traffic = tj["dram_bytes_per_launch"]
-        # FMAs the kernels actually execute per trial-step after the reduced form + axis factorisation
-        executed = {"trial_fwd": 2 * 2 * 36.0 * N * T, "trial_rev": 2 * 2 * 77.0 * N * T}
-        roofline = {"bound": "fp32", "kernel": dom_kernel, "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-                    "frac": achieved / fp32_peak, "traffic": traffic,
-                    "algorithmic_flops_per_launch": kind_flops[dom] * S / dom_launches, "launch_ms": dom_ms / dom_launches,
-                    "launches_per_step": dom_launches,
+        dom_launches = max(1.0, kernels[dom]["launches_per_step"] if len(kernels[dom]["kernels"]) == 1 else 1.0)
+        launch_ms = dom_ms / dom_launches
+        samples_per_launch = S / dom_launches
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        # instruction counts / DRAM bytes of THIS build from the committed ncu capture (tools/ncu_counters.py)
+        counters, counters_note, cj = None, None, None
+        if os.path.exists(COUNTERS):
+            cj = json.load(open(COUNTERS))
+            same_shape = cj.get("trials") == dims.N and cj.get("T") == T and cj.get("kernel_dims") == [dims.x, dims.b, dims.u, dims.y, dims.d]
+            if cj.get("source_sha") != source_sha():
+                counters_note = (f"profiles/r02_counters.json is from another build ({cj.get('source_sha')} != {source_sha()}): "
+                                 "executed-flop fraction and traffic not reported")
+            elif not same_shape:
+                counters_note = "profiles/r02_counters.json was captured on another launch shape: executed-flop fraction and traffic not reported"
+            else:
+                counters = cj
+        else:
+            counters_note = "profiles/r02_counters.json missing: executed-flop fraction and traffic not reported"
+        ck = counters["kernels"].get(dom_kernel) if counters else None
+        executed = traffic = None
+        if ck:
+            # per sample of one launch; the capture used fewer samples per launch than this run (ncu replays every kernel ~40x):
+            # both quantities are per-sample constants of the kernel (no cross-sample reuse), so they scale with the samples
+            flops = ck["fp32_flops_per_sample"] * samples_per_launch
+            executed = {"tflops": flops / (launch_ms * 1e-3) / 1e12, "frac": flops / (launch_ms * 1e-3) / 1e12 / fp32_peak,
+                        "fp32_flops_per_launch": flops, "warp_instructions_per_sample_step": ck["inst_per_sample_step"],
+                        "fp32_share_of_instructions": ck["fp32_inst_share"],
+                        "ncu_fma_pipe_cycles_active_pct": ck["fma_pipe_cycles_active_pct"], "ncu_issue_active_pct": ck["issue_active_pct"],
+                        "source": f"profiles/r02_counters.json (ncu --set full of this build, {cj['samples_per_launch']} samples per launch, scaled per sample)"}
+            traffic = ck["dram_bytes_per_sample"] * samples_per_launch
+        achieved_alg = kernels[dom]["algorithmic_tflops"]
+        # floors of the whole step (this rank's share)
+        step_exec_flops = step_bytes = fp32_floor = fp64_floor = hbm_floor = None
+        bound = "fp32"
+        if counters:
+            step_exec_flops = sum(v["fp32_flops_per_sample"] * S for v in counters["kernels"].values())
+            step_fp64_flops = sum(v.get("fp64_flops_per_sample", 0.0) * S for v in counters["kernels"].values())
+            step_bytes = sum(v["dram_bytes_per_sample"] * S for v in counters["kernels"].values())
+            fp32_floor = step_exec_flops / (fp32_peak * 1e12) * 1e3
+            fp64_floor = step_fp64_flops / (fp64_peak * 1e12) * 1e3
+            hbm_floor = step_bytes / (hbm_peak * 1e9) * 1e3
+            bound = "hbm" if hbm_floor > fp32_floor + fp64_floor else "fp32"
+        if bound == "hbm" and traffic:
+            r_ach, r_peak, r_unit = traffic / (launch_ms * 1e-3) / 1e9, hbm_peak, "GB/s"
+        elif executed:
+            r_ach, r_peak, r_unit = executed["tflops"], fp32_peak, "TFLOP/s"
+        else:
+            r_ach, r_peak, r_unit = None, fp32_peak, "TFLOP/s"
+        roofline = {"bound": bound, "kernel": dom_kernel, "achieved": r_ach, "peak": r_peak, "unit": r_unit,
+                    "frac": (r_ach / r_peak) if r_ach is not None else None, "traffic": traffic,
+                    "launch_ms": launch_ms, "launches_per_step": dom_launches, "samples_per_launch": samples_per_launch,
                     "peak_source": "FFMA micro-kernel measured in this run (lqgk_peak_fma); MEASURED_PEAKS.json has no FP32 figure; nominal 74.5",
-                    "note": "achieved = algorithmic FLOPs of the reference recursion this kernel replaces (SURVEY 8d: dense count, adjoint = 2x "
-                            "forward) / live CUDA-event time; the kernel executes fewer FLOPs than that (reduced form + per-axis factorisation)",
-                    "executed": ({"tflops": executed[dom] * S / (dom_ms * 1e-3) / 1e12, "frac": executed[dom] * S / (dom_ms * 1e-3) / 1e12 / fp32_peak}
-                                 if dom in executed else None),
+                    "note": "achieved = FP32 operations the kernel executes (FFMA2 = 2 FMAs per lane, all 32 lanes counted; counts from the ncu "
+                            "capture of this build) / live CUDA-event time.  algorithmic_* = SURVEY 8(d) dense count of the reference recursion the "
+                            "kernel replaces (adjoint = 2x forward), which the reduced form + per-axis factorisation undercut -- an algorithmic "
+                            "saving, not pipe utilisation",
+                    "executed": executed, "counters_note": counters_note,
+                    "algorithmic_achieved_tflops": achieved_alg, "algorithmic_frac": achieved_alg / fp32_peak,
+                    "algorithmic_flops_per_launch": kind_flops[dom] * samples_per_launch,
                     "fp64_peak_tflops_measured": fp64_peak,
-                    "step": {"achieved": step_flops / (ms_per_step * 1e-3) / 1e12, "frac": step_flops / (ms_per_step * 1e-3) / 1e12 / fp32_peak,
-                             "algorithmic_flops": step_flops},
-                    "hbm": {"kernel_gbs": (traffic / (dom_ms / dom_launches * 1e-3) / 1e9) if traffic else None,
-                            "step_gbs": ws_bytes / (ms_per_step * 1e-3) / 1e9, "peak_gbs": hbm_peak,
-                            "kernel_frac": (traffic / (dom_ms / dom_launches * 1e-3) / 1e9 / hbm_peak) if traffic else None,
-                            "step_frac": ws_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
-                            "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
-                            "bytes_per_step_workspace_model": ws_bytes}}
+                    "step": {"ms": ms_per_step, "fp32_floor_ms": fp32_floor, "fp64_floor_ms": fp64_floor, "hbm_floor_ms": hbm_floor,
+                             "executed_fp32_flops": step_exec_flops, "dram_bytes": step_bytes,
+                             "algorithmic_flops": step_flops,
+                             "algorithmic_frac": step_flops / (ms_per_step * 1e-3) / 1e12 / fp32_peak / world},
+                    "hbm": {"kernel_gbs": (traffic / (launch_ms * 1e-3) / 1e9) if traffic else None,
+                            "kernel_frac": (traffic / (launch_ms * 1e-3) / 1e9 / hbm_peak) if traffic else None,
+                            "step_gbs": (step_bytes / (ms_per_step * 1e-3) / 1e9) if step_bytes else None,
+                            "step_frac": (step_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak) if step_bytes else None,
+                            "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
+                            "workspace_bytes_per_sample": ws_bytes_one_chunk / max(1, min(S, args.chunk) if args.chunk > 0 else S)}}
         # ---------------- CPU baseline (bounded sample) on this box's host cores
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -482,48 +562,26 @@ def run_ours(args):
             cpu = {"value": args.cpu_samples * N / sec, "unit": "trial-evals/s", "cores": os.cpu_count() or 1, "kind": "port",
                    "sample": f"{args.cpu_samples} parameter samples x {N} trials x T={T}, one fwd+grad eval by torch-float64 "
                              f"autograd over the oracle's restatement of the reference scans ({sec:.1f} s)"}
-        secondary = None
-        if world == 1 and not args.no_secondary:
-            c2_val, c2_ms = bench_c2(dev)
-            secondary = {"workload": "c2: SubjectiveActor dim=2, 6 conditions x 20 trials x T=1200, grad wrt 5 shared + 6 per-condition "
-                                     "parameters, one fused call through the public API (latency-bound: 6 systems)",
-                         "value": c2_val, "unit": "trial-evals/s", "ms_per_eval": c2_ms}
-            c5_val, c5_ms = bench_c5(dev)
-            c5 = {"workload": "c5: one leapfrog of 4,096 lock-step chains = one fused log-lik+gradient of 4,096 parameter vectors x 100 trials x "
-                              "T=1200 on this GPU, public API (numpyro/NUTS itself is not installable here)",
-                  "value": c5_val, "unit": "leapfrog-equivalents/s", "ms_per_eval": c5_ms}
-            if args.no_c4:
-                secondary = [secondary, c5]
-            if not args.no_c4:
-                c4_val, c4_ms, c4_k = bench_c4(dev)
-                secondary = [secondary,
-                             {"workload": "c4: TemporalDelayModel(PointMassBoundedActor, delay=2) (x=b=12, joint dim 24), 4,096 parameter "
+        if world == 1 and not args.no_secondary and not args.no_c4:
+            c4_val, c4_ms, c4_k = bench_c4(dev)
+            secondary.append({"workload": "c4: TemporalDelayModel(PointMassBoundedActor, delay=2) (x=b=12, joint dim 24), 4,096 parameter "
                                           "samples x 50 trials x T=600, grad wrt 4 parameters per sample, public API (large-system kernels)",
-                              "value": c4_val, "unit": "trial-evals/s", "ms_per_eval": c4_ms, "kernel_ms": c4_k}, c5]
+                              "value": c4_val, "unit": "trial-evals/s", "ms_per_eval": c4_ms, "kernel_ms": c4_k})
         line = {"metric": "trial log-lik+grad evals/sec", "value": value, "unit": "trial-evals/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64 per-sample recursions + f32 per-trial recursions (f32 I/O)",
-                "data": "synthetic", "config": dict(workload_config(args, S), kernel_dims=[dims.x, dims.b, dims.u, dims.y, dims.d], kernel_trials=dims.N,
-                               factorized_axes=not args.no_factorize),
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64 per-sample recursions + f32 per-trial recursions (f32 I/O)",
+                "data": "synthetic", "config": dict(workload_config(args, world), kernel_dims=[dims.x, dims.b, dims.u, dims.y, dims.d],
+                                                    kernel_trials=dims.N, factorized_axes=not args.no_factorize,
+                                                    chunks_per_step=-(-S // args.chunk) if args.chunk > 0 else 1),
                 "trial_steps_per_sec": value * T,
                 "e2e": {"value": e2e_val, "unit": "trial-evals/s", "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": int(theta_host.numel() * 4 + x_host.numel() * 4),
                         "d2h_bytes_per_step": int(out_host.numel() * 4)},
                 "gpu_launches": int(launches_per_step * args.steps),
-                "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "secondary": secondary, "clocks": clocks}
+                "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "secondary": secondary or None, "clocks": clocks}
         emit(line)
     if world > 1:
         dist.destroy_process_group()
-
-
-def split_sample_flops():
-    """(lqr, kf) per-step forward flops for the c3 dims."""
-    x, b, u, y = DIMS["x"], DIMS["b"], DIMS["u"], DIMS["y"]
-    lqr = (2 * mm(u, b, b) + mm(u, b, u) + mm(u, b, 1) + 10 * u ** 3 + (2 * u ** 3) // 3 + 2 * u * u * b + 2 * u * u
-           + 2 * mm(b, b, b) + mm(b, u, u) + 3 * mm(b, u, b) + 4 * b * b + mm(b, b, 1) + 3 * mm(b, u, 1) + mm(u, u, 1) + 4 * b)
-    kf = (3 * mm(b, b, b) + b * b + mm(y, b, b) + mm(y, b, y) + mm(y, y, y) + y * y + 2 * y ** 3 + mm(b, b, y) + mm(b, y, y)
-          + mm(b, y, b) + b + mm(b, b, b))
-    return lqr, kf
 
 
 _REAL_STDOUT = None
@@ -551,7 +609,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--samples", type=int, default=32768, help="parameter samples per GPU per step")
+    ap.add_argument("--samples", type=int, default=65536, help="parameter samples per step IN TOTAL (config c3: 65,536), sharded over the GPUs")
     ap.add_argument("--trials", type=int, default=100)
     ap.add_argument("--T", type=int, default=1200)
     ap.add_argument("--chunk", type=int, default=0, help="max samples per internal workspace chunk (0 = as many as fit)")

@@ -5,9 +5,13 @@
  * place of the reference functions cited per entry.  All paths below are relative to the reference repo.
  *
  * Conventions
- *  - All buffers are caller-owned DEVICE memory.  No allocation, no host synchronisation and no use of the
+ *  - All buffers are caller-owned DEVICE memory.  No device allocation, no host synchronisation and no use of the
  *    default stream inside; kernels are enqueued on `stream` (a cudaStream_t passed as void*).
- *  - Return 0 (LQGK_OK) or a negative LQGK_E_* code; never throws.  Re-entrant; no mutable globals.
+ *  - Return 0 (LQGK_OK) or a negative LQGK_E_* code; never throws.  Re-entrant: the only state is per host thread (the
+ *    tuning knobs below and a pool of internal streams / events used to run independent kernels of one call side by side,
+ *    always forked from and joined to `stream`).  lqgk_init() creates that pool up front; without it the first call of a
+ *    thread creates it lazily, which is not possible while `stream` is being captured into a CUDA graph
+ *    (-> LQGK_E_NOT_INITIALISED).  After lqgk_init() every entry point is capturable and replayable.
  *  - Matrices are row-major.  Every matrix has a leading parameter-sample axis and a time axis described by
  *    element strides: sample_stride 0 = shared by all samples, time_stride 0 = time-invariant
  *    (the reference stacks T copies: lqg/utils.py:6-35).
@@ -33,6 +37,7 @@ extern "C" {
 #define LQGK_E_UNSUPPORTED (-2)  /* dimension tuple not instantiated, or time-varying spec in the VJP  */
 #define LQGK_E_WORKSPACE (-3)    /* workspace too small for even one 32-sample chunk                   */
 #define LQGK_E_CUDA (-4)         /* a CUDA runtime call failed (see cudaGetLastError)                  */
+#define LQGK_E_NOT_INITIALISED (-5) /* call under CUDA-graph capture before lqgk_init() on this thread */
 
 typedef struct {
   int32_t S; /* parameter samples (systems) in this call                              */
@@ -106,6 +111,26 @@ int lqgk_loglik_vjp_f64(const LqgkDims* dims, const LqgkSpec* actor, const LqgkS
                         const LqgkSpecGrad* actor_grad, const LqgkSpecGrad* dynamics_grad,
                         const LqgkMatGrad* sigma0_grad, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- moments and simulation (the callers either side of the likelihood) -------------------------------------------------
+ * lqgk_moments_*: replaces lqg/system.py:142-235 System.conditional_moments vmapped over trials, as used by
+ *   belief_tracking_distribution (:250-257): predictive moments of the joint state (x, xhat)_{t+1} given x_{0..t}.
+ *   Outputs mu[S][N][T][n] and Sigma[S][T][n][n] with n = x + b (either may be NULL).  Small systems (n <= 12) only.
+ * lqgk_simulate_*: replaces lqg/system.py:62-140 System.simulate for S parameter samples x N trials, given the gains
+ *   L[S][T][u][b], l[S][T][u] (NULL = 0) and K[S][T][b][y] (lqgk_lqr_backward_* / lqgk_kf_forward_*).  x0[x], xhat0[b]: initial
+ *   state / belief (NULL = 0).  Noise: Philox4x32-10 counter stream keyed by (seed, trial) -- the reference's JAX threefry
+ *   samples cannot be reproduced, the distribution is the same.  Outputs x[S][N][T+1][x] and optionally
+ *   xhat[S][N][T+1][b], y[S][N][T][y], u[S][N][T][u].  Any dimension tuple with x, b, u, y <= 40.                        */
+int lqgk_moments_f32(const LqgkDims* dims, const LqgkSpec* actor, const LqgkSpec* dynamics, const LqgkMat* sigma0,
+                     const float* x_tm, float* mu_out, float* Sigma_out, void* workspace, size_t workspace_bytes, void* stream);
+int lqgk_moments_f64(const LqgkDims* dims, const LqgkSpec* actor, const LqgkSpec* dynamics, const LqgkMat* sigma0,
+                     const float* x_tm, double* mu_out, double* Sigma_out, void* workspace, size_t workspace_bytes, void* stream);
+int lqgk_simulate_f32(const LqgkDims* dims, const LqgkSpec* actor, const LqgkSpec* dynamics, const float* L, const float* l,
+                      const float* K, const float* x0, const float* xhat0, uint64_t seed, float* x_out, float* xhat_out,
+                      float* y_out, float* u_out, void* stream);
+int lqgk_simulate_f64(const LqgkDims* dims, const LqgkSpec* actor, const LqgkSpec* dynamics, const double* L, const double* l,
+                      const double* K, const double* x0, const double* xhat0, uint64_t seed, double* x_out, double* xhat_out,
+                      double* y_out, double* u_out, void* stream);
+
 /* ---- signal-dependent noise (extension; NOT in the reference, see DESIGN.md and oracle/sdn_np.py) -------------
  * lqgk_sdn_gains_f64: Todorov (2005) alternating iterations for the control gains L and estimator gains K of
  *     x' = A x + B u + xi + sum_i eps_i C_i u,   y = H x + om + sum_i eta_i D_i x,
@@ -134,12 +159,19 @@ int lqgk_pack_obs_f64(int32_t N, int32_t T1, int32_t d, const double* x, float* 
 #define LQGK_MODE_GAINS 0
 #define LQGK_MODE_FWD 1
 #define LQGK_MODE_VJP 2
+#define LQGK_MODE_MOMENTS 3
 /* Bytes of workspace that let `mode` process min(S, max_chunk) samples per internal chunk (max_chunk <= 0:
  * all S at once).  Any size >= lqgk_workspace_bytes(dims, mode, 32) is accepted; larger = fewer chunks.   */
 size_t lqgk_workspace_bytes(const LqgkDims* dims, int mode, int32_t max_chunk);
 int lqgk_dims_supported(const LqgkDims* dims);
 const char* lqgk_strerror(int code);
 const char* lqgk_version(void);
+/* Text of the CUDA runtime's pending error (cudaPeekAtLastError) -- what went wrong behind an LQGK_E_CUDA return. */
+const char* lqgk_last_cuda_error(void);
+/* Creates the calling thread's internal streams / events for the current device (enough for `max_sample_slices` concurrent
+ * sample slices, see lqgk_set_streams; 1 is the default configuration) and caches the device's SM count.  Optional unless
+ * entry points are to be captured into CUDA graphs. */
+int lqgk_init(int max_sample_slices);
 /* Number of internal concurrent sample slices (streams) used by the likelihood entry points of the calling thread
  * (default 1 = everything on the caller's stream; 4 gives ~3 % at the benchmark size).  Work is always forked from / joined to the caller's stream. */
 int lqgk_set_streams(int n);

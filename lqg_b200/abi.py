@@ -17,7 +17,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("LQGK_LIB_PATH") or os.path.join(HERE, "csrc", "liblqgk.so")   # override: tuning experiments (tools/)
 
-MODE_GAINS, MODE_FWD, MODE_VJP = 0, 1, 2
+MODE_GAINS, MODE_FWD, MODE_VJP, MODE_MOMENTS = 0, 1, 2, 3
 ACTOR_KEYS = ("A", "B", "F", "V", "W", "Q", "R")
 DYN_KEYS = ("A", "B", "F", "V", "W")
 
@@ -106,11 +106,15 @@ class Library:
         if hasattr(self.lib, "lqgk_strerror"):
             return self.lib.lqgk_strerror(code).decode()
         return {-1: "invalid argument", -2: "unsupported dims / time-varying VJP", -3: "workspace too small",
-                -4: "CUDA error"}.get(code, f"error {code}")
+                -4: "CUDA error", -5: "not initialised"}.get(code, f"error {code}")
 
     def _check(self, code: int, what: str):
         if code != 0:
-            raise LqgkError(f"{what} failed: {self.strerror(code)} ({code})")
+            detail = ""
+            if code == -4 and hasattr(self.lib, "lqgk_last_cuda_error"):
+                self.lib.lqgk_last_cuda_error.restype = C.c_char_p
+                detail = ": " + self.lib.lqgk_last_cuda_error().decode()
+            raise LqgkError(f"{what} failed: {self.strerror(code)} ({code}){detail}")
 
     def workspace_bytes(self, dims: LqgkDims, mode: int, max_chunk: int = 0) -> int:
         if not hasattr(self.lib, "lqgk_workspace_bytes"):
@@ -225,6 +229,39 @@ class Library:
                        C.c_void_p(p), C.c_size_t(n), C.c_void_p(stream)), "lqgk_loglik_vjp")
         return ll, out_a, out_d, out_s0
 
+    def moments(self, dims, actor, dyn, x_tm, sigma0=None, want_mu=True, want_sigma=True, ws=None, stream=0):
+        """Predictive moments of the joint state (x, xhat): mu[S, N, T, n], Sigma[S, T, n, n] (None when not wanted)."""
+        dt, dev = actor["A"].dtype, actor["A"].device
+        S, T, n = dims.S, dims.T, dims.x + dims.b
+        self._check_obs(dims, x_tm)
+        mu = torch.empty((S, dims.N, T, n), dtype=dt, device=dev) if want_mu else None
+        Sig = torch.empty((S, T, n, n), dtype=dt, device=dev) if want_sigma else None
+        sa, sd = self._spec(actor, S, T, ACTOR_KEYS), self._spec(dyn, S, T, DYN_KEYS)
+        s0 = _mat(sigma0, S, 1) if sigma0 is not None else None
+        p, nb = self._ws(ws)
+        fn = getattr(self.lib, "lqgk_moments_" + self._suffix(dt))
+        self._check(fn(C.byref(dims), C.byref(sa), C.byref(sd), C.byref(s0) if s0 is not None else None,
+                       C.c_void_p(x_tm.data_ptr()), C.c_void_p(mu.data_ptr() if want_mu else None),
+                       C.c_void_p(Sig.data_ptr() if want_sigma else None), C.c_void_p(p), C.c_size_t(nb), C.c_void_p(stream)),
+                    "lqgk_moments")
+        return mu, Sig
+
+    def simulate(self, dims, actor, dyn, L, l, K, seed, x0=None, xhat0=None, return_all=False, stream=0):
+        """Batched System.simulate: x[S, N, T+1, x] (and xhat, y, u when return_all) for the given gains."""
+        dt, dev = actor["A"].dtype, actor["A"].device
+        S, T, N = dims.S, dims.T, dims.N
+        x = torch.empty((S, N, T + 1, dims.x), dtype=dt, device=dev)
+        xh = torch.empty((S, N, T + 1, dims.b), dtype=dt, device=dev) if return_all else None
+        y = torch.empty((S, N, T, dims.y), dtype=dt, device=dev) if return_all else None
+        u = torch.empty((S, N, T, dims.u), dtype=dt, device=dev) if return_all else None
+        sa, sd = self._spec(actor, S, T, ACTOR_KEYS), self._spec(dyn, S, T, DYN_KEYS)
+        keep = [t.to(dt).contiguous() if t is not None else None for t in (L, l, K, x0, xhat0)]
+        ptr = lambda t: C.c_void_p(t.data_ptr() if t is not None else None)
+        fn = getattr(self.lib, "lqgk_simulate_" + self._suffix(dt))
+        self._check(fn(C.byref(dims), C.byref(sa), C.byref(sd), ptr(keep[0]), ptr(keep[1]), ptr(keep[2]), ptr(keep[3]), ptr(keep[4]),
+                       C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF), ptr(x), ptr(xh), ptr(y), ptr(u), C.c_void_p(stream)), "lqgk_simulate")
+        return (x, xh, y, u) if return_all else x
+
     def pack_obs(self, x: torch.Tensor, stream=0) -> torch.Tensor:
         """x[N, T+1, d] (f32/f64) -> time-major float32 x_tm[T+1, N, d] on the same device."""
         N, T1, d = x.shape
@@ -276,6 +313,10 @@ class Library:
                                          C.c_void_p(cost.data_ptr()), C.c_void_p(stream))
         self._check(rc, "lqgk_sdn_gains_f64")
         return L, K, cost
+
+    def init(self, max_sample_slices: int = 1):
+        """Pre-create the library's internal streams / events (needed before capturing calls into a CUDA graph)."""
+        self._check(self.lib.lqgk_init(C.c_int(int(max_sample_slices))), "lqgk_init")
 
     def set_streams(self, n: int):
         self._check(self.lib.lqgk_set_streams(C.c_int(n)), "lqgk_set_streams")

@@ -1,6 +1,7 @@
 // lqgk_api.cu -- extern "C" entry points of liblqgk.so (see include/lqgk.h): validation, dimension dispatch,
 // workspace planning, chunking over parameter samples and the kernel launch sequence.
 #include <cuda_runtime.h>
+#include <curand_kernel.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -15,7 +16,8 @@ namespace lqgk {
 thread_local int g_launches = 0;
 thread_local Profiler g_prof;
 thread_local int g_streams = 1;
-thread_local int g_contrib_warps = 148 * 30;
+thread_local int g_contrib_warps = 0;    // 0 = 30 warps per SM of the current device
+thread_local DeviceInfo g_dev;
 thread_local int g_aux_streams = 6;
 thread_local int g_warp_cov_max_samples = 512;   // measured crossover between 512 and 1,024 samples (profiles/r01_e_*.md)
 thread_local StreamPool g_pool;
@@ -30,7 +32,8 @@ int validate(const Call& c) {
   if (!c.act->A.ptr || !c.act->B.ptr) return LQGK_E_INVALID;
   if (c.mode != LQGK_MODE_GAINS) {
     if (d.N <= 0 || d.d <= 0 || d.d > d.x) return LQGK_E_INVALID;
-    if (!c.dyn || !c.x_tm || !c.ll_out) return LQGK_E_INVALID;
+    if (!c.dyn || !c.x_tm) return LQGK_E_INVALID;
+    if (c.mode == LQGK_MODE_MOMENTS ? (!c.mu_out && !c.Sig_out) : !c.ll_out) return LQGK_E_INVALID;
     const LqgkMat* need[] = {&c.act->F, &c.act->V, &c.act->W, &c.act->Q, &c.act->R, &c.dyn->A, &c.dyn->B, &c.dyn->F, &c.dyn->V, &c.dyn->W};
     for (auto m : need)
       if (!m->ptr) return LQGK_E_INVALID;
@@ -67,6 +70,104 @@ int pack_obs(int32_t N, int32_t T1, int32_t d, const T* x, float* x_tm, void* st
   return LQGK_OK;
 }
 
+}  // namespace
+
+// ------------------------------------------------------------------------------------------- batched simulator
+// System.simulate (lqg/system.py:62-140) for S parameter samples x N trials: one thread per trial runs the closed loop
+//   u = L_t xhat + l_t;  x <- A_d x + B_d u + V_d eps_t;  y = F_d x + W_d eta_t;  xp = A_a xhat + B_a u;  xhat <- xp + K_t (y - F_a xp)
+// in FP64 with standard-normal draws from a Philox4x32-10 counter stream (subsequence = trial index; the reference's JAX
+// threefry stream cannot be reproduced, so the samples differ and the distribution does not).  Generic in the dimensions
+// (run-time x, b, u, y <= SIM_MAX): it is a data generator, not a hot path.
+constexpr int SIM_MAX = 40;
+template <class T>
+struct SimArgs {
+  LqgkSpec act, dyn;
+  const T *L, *l, *K, *x0, *xhat0;
+  T *x_out, *xhat_out, *y_out, *u_out;
+  int S, N, Tn, x, b, u, y;
+  unsigned long long seed;
+};
+template <class T>
+__global__ void k_simulate(SimArgs<T> a) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)a.S * a.N) return;
+  const int s = (int)(idx / a.N);
+  const int x = a.x, b = a.b, u = a.u, y = a.y, Tn = a.Tn;
+  curandStatePhilox4_32_10_t rng;
+  curand_init(a.seed, idx, 0, &rng);
+  double xv[SIM_MAX], xh[SIM_MAX], xn[SIM_MAX], xp[SIM_MAX], yv[SIM_MAX], uv[SIM_MAX], nz[2 * SIM_MAX + 4];
+  for (int i = 0; i < x; ++i) xv[i] = a.x0 ? (double)a.x0[i] : 0.0;
+  for (int i = 0; i < b; ++i) xh[i] = a.xhat0 ? (double)a.xhat0[i] : 0.0;
+  T* xo = a.x_out + idx * (size_t)(Tn + 1) * x;
+  T* ho = a.xhat_out ? a.xhat_out + idx * (size_t)(Tn + 1) * b : nullptr;
+  T* yo = a.y_out ? a.y_out + idx * (size_t)Tn * y : nullptr;
+  T* uo = a.u_out ? a.u_out + idx * (size_t)Tn * u : nullptr;
+  for (int i = 0; i < x; ++i) xo[i] = (T)xv[i];
+  if (ho) for (int i = 0; i < b; ++i) ho[i] = (T)xh[i];
+  for (int t = 0; t < Tn; ++t) {
+    for (int k = 0; k < x + y; k += 4) {
+      float4 g = curand_normal4(&rng);
+      nz[k] = g.x; nz[k + 1] = g.y; nz[k + 2] = g.z; nz[k + 3] = g.w;
+    }
+    const T* Lt = a.L + ((size_t)s * Tn + t) * u * b;
+    const T* Kt = a.K + ((size_t)s * Tn + t) * b * y;
+    for (int i = 0; i < u; ++i) {                                   // u = L xhat + l
+      double v = a.l ? (double)a.l[((size_t)s * Tn + t) * u + i] : 0.0;
+      for (int j = 0; j < b; ++j) v += (double)Lt[i * b + j] * xh[j];
+      uv[i] = v;
+    }
+    for (int i = 0; i < x; ++i) {                                   // x <- A x + B u + V eps
+      double v = 0.0;
+      for (int j = 0; j < x; ++j) v += mat_at<T>(a.dyn.A, s, t, i * x + j) * xv[j] + mat_at<T>(a.dyn.V, s, t, i * x + j) * nz[j];
+      for (int j = 0; j < u; ++j) v += mat_at<T>(a.dyn.B, s, t, i * u + j) * uv[j];
+      xn[i] = v;
+    }
+    for (int i = 0; i < x; ++i) xv[i] = xn[i];
+    for (int i = 0; i < y; ++i) {                                   // y = F x + W eta
+      double v = 0.0;
+      for (int j = 0; j < x; ++j) v += mat_at<T>(a.dyn.F, s, t, i * x + j) * xv[j];
+      for (int j = 0; j < y; ++j) v += mat_at<T>(a.dyn.W, s, t, i * y + j) * nz[x + j];
+      yv[i] = v;
+    }
+    for (int i = 0; i < b; ++i) {                                   // xp = A_a xhat + B_a u
+      double v = 0.0;
+      for (int j = 0; j < b; ++j) v += mat_at<T>(a.act.A, s, t, i * b + j) * xh[j];
+      for (int j = 0; j < u; ++j) v += mat_at<T>(a.act.B, s, t, i * u + j) * uv[j];
+      xp[i] = v;
+    }
+    for (int i = 0; i < y; ++i) {                                   // innovation y - F_a xp (in place)
+      double v = yv[i];
+      for (int j = 0; j < b; ++j) v -= mat_at<T>(a.act.F, s, t, i * b + j) * xp[j];
+      nz[i] = v;
+    }
+    for (int i = 0; i < b; ++i) {                                   // xhat <- xp + K innovation
+      double v = xp[i];
+      for (int j = 0; j < y; ++j) v += (double)Kt[i * y + j] * nz[j];
+      xh[i] = v;
+    }
+    for (int i = 0; i < x; ++i) xo[(size_t)(t + 1) * x + i] = (T)xv[i];
+    if (ho) for (int i = 0; i < b; ++i) ho[(size_t)(t + 1) * b + i] = (T)xh[i];
+    if (yo) for (int i = 0; i < y; ++i) yo[(size_t)t * y + i] = (T)yv[i];
+    if (uo) for (int i = 0; i < u; ++i) uo[(size_t)t * u + i] = (T)uv[i];
+  }
+}
+namespace {
+template <class T>
+int simulate(const LqgkDims* d, const LqgkSpec* act, const LqgkSpec* dyn, const T* L, const T* l, const T* K, const T* x0, const T* xhat0,
+             uint64_t seed, T* x_out, T* xhat_out, T* y_out, T* u_out, void* stream) {
+  g_launches = 0;
+  if (!d || !act || !dyn || !L || !K || !x_out) return LQGK_E_INVALID;
+  if (d->S <= 0 || d->N <= 0 || d->T <= 0 || d->x <= 0 || d->b <= 0 || d->u <= 0 || d->y <= 0) return LQGK_E_INVALID;
+  if (d->x > SIM_MAX || d->b > SIM_MAX || d->u > SIM_MAX || d->y > SIM_MAX) return LQGK_E_UNSUPPORTED;
+  const LqgkMat* need[] = {&act->A, &act->B, &act->F, &dyn->A, &dyn->B, &dyn->F, &dyn->V, &dyn->W};
+  for (auto m : need)
+    if (!m->ptr) return LQGK_E_INVALID;
+  SimArgs<T> a{*act, *dyn, L, l, K, x0, xhat0, x_out, xhat_out, y_out, u_out, d->S, d->N, d->T, d->x, d->b, d->u, d->y, seed};
+  const size_t total = (size_t)d->S * d->N;
+  k_simulate<T><<<(unsigned)((total + 63) / 64), 64, 0, (cudaStream_t)stream>>>(a);
+  LQGK_LAUNCH_CHECK();
+  return LQGK_OK;
+}
 }  // namespace
 
 // FMA-saturating micro-kernels: the measured FP32 / FP64 CUDA-core peaks used as roofline denominators.
@@ -167,6 +268,29 @@ int lqgk_loglik_vjp_f64(const LqgkDims* dims, const LqgkSpec* actor, const LqgkS
   return dispatch<double>(c);
 }
 
+int lqgk_moments_f32(const LqgkDims* dims, const LqgkSpec* actor, const LqgkSpec* dynamics, const LqgkMat* sigma0, const float* x_tm,
+                     float* mu_out, float* Sigma_out, void* ws, size_t ws_bytes, void* stream) {
+  Call c{dims, actor, dynamics, sigma0, x_tm, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 1e-8, LQGK_MODE_MOMENTS, ws, ws_bytes, (cudaStream_t)stream};
+  c.mu_out = mu_out; c.Sig_out = Sigma_out;
+  return dispatch<float>(c);
+}
+int lqgk_moments_f64(const LqgkDims* dims, const LqgkSpec* actor, const LqgkSpec* dynamics, const LqgkMat* sigma0, const float* x_tm,
+                     double* mu_out, double* Sigma_out, void* ws, size_t ws_bytes, void* stream) {
+  Call c{dims, actor, dynamics, sigma0, x_tm, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 1e-8, LQGK_MODE_MOMENTS, ws, ws_bytes, (cudaStream_t)stream};
+  c.mu_out = mu_out; c.Sig_out = Sigma_out;
+  return dispatch<double>(c);
+}
+int lqgk_simulate_f32(const LqgkDims* dims, const LqgkSpec* actor, const LqgkSpec* dynamics, const float* L, const float* l, const float* K,
+                      const float* x0, const float* xhat0, uint64_t seed, float* x_out, float* xhat_out, float* y_out, float* u_out,
+                      void* stream) {
+  return simulate<float>(dims, actor, dynamics, L, l, K, x0, xhat0, seed, x_out, xhat_out, y_out, u_out, stream);
+}
+int lqgk_simulate_f64(const LqgkDims* dims, const LqgkSpec* actor, const LqgkSpec* dynamics, const double* L, const double* l, const double* K,
+                      const double* x0, const double* xhat0, uint64_t seed, double* x_out, double* xhat_out, double* y_out, double* u_out,
+                      void* stream) {
+  return simulate<double>(dims, actor, dynamics, L, l, K, x0, xhat0, seed, x_out, xhat_out, y_out, u_out, stream);
+}
+
 int lqgk_pack_obs_f32(int32_t N, int32_t T1, int32_t d, const float* x, float* x_tm, void* stream) {
   return pack_obs<float>(N, T1, d, x, x_tm, stream);
 }
@@ -202,8 +326,17 @@ const char* lqgk_strerror(int code) {
     case LQGK_E_UNSUPPORTED: return "unsupported: dimension tuple not compiled in, or time-varying spec passed to the VJP";
     case LQGK_E_WORKSPACE: return "workspace too small for one 32-sample chunk (see lqgk_workspace_bytes)";
     case LQGK_E_CUDA: return "CUDA runtime error";
+    case LQGK_E_NOT_INITIALISED: return "internal streams missing while the caller's stream is being captured: call lqgk_init() on this thread and device before capturing";
     default: return "unknown error";
   }
+}
+int lqgk_init(int max_sample_slices) {
+  // everything an entry point may need later on this thread and device, created now: the internal streams / events (sample
+  // slices + 2 auxiliary streams per slice) and the cached SM count.  After this no entry point creates CUDA objects, so calls
+  // may be captured into CUDA graphs (which is how XLA may run an FFI handler).
+  if (max_sample_slices < 1 || max_sample_slices > 32) return LQGK_E_INVALID;
+  sm_count();
+  return g_pool.ensure(3 * max_sample_slices);
 }
 int lqgk_set_streams(int n) {
   if (n < 1 || n > 32) return LQGK_E_INVALID;
@@ -258,7 +391,7 @@ int lqgk_profile_read(float* ms_by_kind, int32_t* launches_by_kind, int nkinds) 
 
 int lqgk_peak_fma(int fp64, int iters, void* sink, void* stream, double* flop_out) {
   if (!sink || iters <= 0) return LQGK_E_INVALID;
-  const int blocks = 148 * 8, threads = 256;
+  const int blocks = sm_count() * 8, threads = 256;
   if (fp64) k_peak_fma<double><<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, (double*)sink);
   else k_peak_fma<float><<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, (float*)sink);
   if (cudaPeekAtLastError() != cudaSuccess) return LQGK_E_CUDA;
@@ -266,7 +399,8 @@ int lqgk_peak_fma(int fp64, int iters, void* sink, void* stream, double* flop_ou
   return LQGK_OK;
 }
 
-const char* lqgk_version(void) { return "lqgk 0.1.0 (sm_100a)"; }
+const char* lqgk_version(void) { return "lqgk 0.2.0 (sm_100a)"; }
+const char* lqgk_last_cuda_error(void) { return cudaGetErrorString(cudaPeekAtLastError()); }
 int lqgk_last_launch_count(void) { return g_launches; }
 
 }  // extern "C"

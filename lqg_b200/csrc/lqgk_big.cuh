@@ -22,6 +22,7 @@ int run_big(const Call& c) {
   const bool has_dyn = c.dyn != nullptr;
   const bool tv = spec_time_varying(*c.act, true) || (has_dyn && spec_time_varying(*c.dyn, false));
   if (tv && c.mode == LQGK_MODE_VJP) return LQGK_E_UNSUPPORTED;
+  if (c.mode == LQGK_MODE_MOMENTS) return LQGK_E_UNSUPPORTED;   // moments of the large systems stay on the host-side slow path
   if (!c.ws || ((uintptr_t)c.ws % ALIGN) != 0) return LQGK_E_INVALID;
   const size_t Sc = choose_chunk<DM>(d, c.mode, tv, c.ws_bytes / ALIGN * ALIGN, 0);
   if (Sc == 0) return LQGK_E_WORKSPACE;
@@ -152,7 +153,7 @@ int run_big(const Call& c) {
       if ((rc = set_smem<DM>((const void*)kw_cov_contrib<DM>, smem))) return rc;
       ProfScope ps_(PK_COV_CONTRIB, st);
       // time ranges: enough (sample x range) warps to put ~12 on every SM when there are few samples
-      int chunks = std::max(1, std::min((Tn + 3) / 4, (148 * 12 + npad - 1) / npad));
+      int chunks = std::max(1, std::min((Tn + 3) / 4, (sm_count() * 12 + npad - 1) / npad));
       kw_cov_contrib<DM><<<dim3(wblk, chunks), wthr, smem, st>>>(D(p.cst), Sc, npad, Tn, D(p.L), D(p.K), D(p.Cs), D(p.SGB), D(p.SGBI),
                                                                 D(p.SFW), F(p.sums), D(p.acc), D(p.Lbar), D(p.Kbar), nullptr);
       LQGK_LAUNCH_CHECK();

@@ -554,8 +554,13 @@ struct CovFwd {
   }
   // One step: C_t -> C_{t+1}; emits the float record for the trial kernels through `put(idx, value)`.
   // save(which, e, v): optional FP64 outputs for the adjoint: which 0 = Fu_t (N x R row-major), 1 = J_t then S'^-1_t.
-  template <class V, class Put, class Save>
-  LQGK_HD static void step(const V& c, const double* L, const double* K, double* Cm, Put&& put, Save&& save) {
+  struct NoSig {
+    LQGK_HD void operator()(int, double) const {}
+  };
+  // savesig(e, v) (optional): the full predictive joint covariance Sigma'[e] of this step (system.py:223-230), row-major N x N
+  // -- what conditional_moments / belief_tracking_distribution return (moments entry point only).
+  template <class V, class Put, class Save, class SaveSig = NoSig>
+  LQGK_HD static void step(const V& c, const double* L, const double* K, double* Cm, Put&& put, Save&& save, SaveSig&& savesig = SaveSig{}) {
     double Fj[N * N], Nj[N * N], Sig[N * N];
     joint_F(c, L, K, Fj);
     // the observed rows are stored negated so the trial kernels form e = x1 + (-F[o,:]) [x0; c] with plain FMAs, starting
@@ -564,6 +569,7 @@ struct CovFwd {
     LQGK_UNROLL64 for (int i = 0; i < N; ++i) LQGK_UNROLL64 for (int j = 0; j < R; ++j) save(0, i * R + j, Fj[i * N + D + j]);
     joint_N(c, K, Nj);
     predict(Fj, Cm, Nj, Sig);
+    LQGK_UNROLL64 for (int i = 0; i < N * N; ++i) savesig(i, Sig[i]);
     double Linv[D * D], ld;
     condition(Sig, Linv, ld, [&](int i, double v) { put(DM::REC_J + i, (float)v); save(1, i, v); }, Cm);
     LQGK_UNROLL64 for (int i = 0; i < D; ++i) LQGK_UNROLL64 for (int j = 0; j <= i; ++j) {
@@ -683,6 +689,22 @@ struct Trial {
     LQGK_UNROLL for (int i = 0; i < D; ++i) qf = O::fma(z[i], z[i], qf);
     update<S>(rec, x0, e, c);
     return O::fma(O::bc(-0.5f), qf, O::bc(-rec[DM::REC_LOGDET] - HALF_LOG2PI_D));
+  }
+  // predictive mean of the joint state (system.py:219-221): mu'[o] = x1 - e, mu'[u] = F[u,o] x0 + F[u,u] c (before the
+  // correction J e that conditions on x1); then advances c like fwd().  `mu`: N values.
+  template <class S, class Rec>
+  LQGK_HD static void moments(const Rec& rec, const S* x0, const S* x1, S* c, S* mu) {
+    using O = Ops<S>;
+    S e[D];
+    residual<S>(rec, x0, x1, c, e);
+    LQGK_UNROLL for (int i = 0; i < D; ++i) mu[i] = O::sub(x1[i], e[i]);
+    LQGK_UNROLL for (int i = 0; i < R; ++i) {
+      S a = O::zero();
+      LQGK_UNROLL for (int j = 0; j < D; ++j) a = O::fma(O::bc(rec[DM::REC_F + (D + i) * N + j]), x0[j], a);
+      LQGK_UNROLL for (int j = 0; j < R; ++j) a = O::fma(O::bc(rec[DM::REC_F + (D + i) * N + D + j]), c[j], a);
+      mu[D + i] = a;
+    }
+    update<S>(rec, x0, e, c);
   }
   // state-only forward step (no log-density): what the adjoint kernel re-runs between two checkpoints of c.  Same
   // operation sequence as fwd(), so the recomputed states are bit-identical to the ones the forward pass carried.

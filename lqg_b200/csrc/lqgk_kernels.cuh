@@ -318,6 +318,51 @@ __global__ void __launch_bounds__(32) k_cov_fwd(const double* cst, size_t Sc, si
   sink.finish();
 }
 
+// ------------------------------------------------------------------------------------------- moments (slow path)
+// conditional_moments / belief_tracking_distribution (system.py:142-235, 250-257): the same recursions, emitting the full
+// predictive moments instead of the log-density.  Covariances: thread per sample, written straight to the caller's
+// Sigma[s][t][n][n]; means: thread per (sample, trial), written to mu[s][i][t][n].  Output-bound by construction (n^2 + N n
+// numbers per sample-step), so these kernels use plain loads / stores.
+struct DirectRecSink {
+  float* row;
+  int rec;
+  __device__ __forceinline__ void put(int idx, float v) { row[idx] = v; }
+  __device__ __forceinline__ void commit(int) { row += rec; }
+};
+template <class DM, class T>
+__global__ void __launch_bounds__(32) k_cov_moments(const double* cst, size_t Sc, size_t tstride, int Tn, int n_valid, const double* L,
+                                                    const double* K, float* rec, T* __restrict__ Sig_out) {
+  extern __shared__ __align__(16) double sm[];
+  const int lane = threadIdx.x;
+  const size_t s = (size_t)blockIdx.x * 32 + lane;
+  DirectRecSink sink{rec + s * Tn * DM::REC, DM::REC};
+  const bool emit = Sig_out != nullptr && s < (size_t)n_valid;
+  WView none{nullptr, 0};
+  cov_fwd_body<DM>(GCst{cst + s, Sc, tstride}, WView{sm + lane, 32}, Tn, WView{const_cast<double*>(L) + s, Sc},
+                   WView{const_cast<double*>(K) + s, Sc}, false, none, none, none, none, sink,
+                   [&](int t, int e, double v) { if (emit) Sig_out[((size_t)s * Tn + t) * (DM::N * DM::N) + e] = (T)v; });
+}
+template <class DM, class T>
+__global__ void k_trial_moments(const float* __restrict__ rec, const float* __restrict__ x_all, size_t x_sample_stride, int s_first,
+                                int n_samples, int N, int Tn, T* __restrict__ mu_out) {
+  constexpr int D = DM::D, R = DM::R, NJ = DM::N;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t s = idx / N;
+  const int i = (int)(idx % N);
+  if (s >= (size_t)n_samples) return;
+  const float* x_tm = x_all + (size_t)(s_first + s) * x_sample_stride;
+  float c[R], x0[D], x1[D], mu[NJ];
+  LQGK_UNROLL for (int k = 0; k < R; ++k) c[k] = 0.f;
+  LQGK_UNROLL for (int k = 0; k < D; ++k) x0[k] = x_tm[(size_t)i * D + k];
+  T* out = mu_out + (s * N + i) * (size_t)Tn * NJ;
+  for (int t = 0; t < Tn; ++t) {
+    LQGK_UNROLL for (int k = 0; k < D; ++k) x1[k] = x_tm[((size_t)(t + 1) * N + i) * D + k];
+    Trial<DM>::template moments<float>(rec + (s * Tn + t) * DM::REC, x0, x1, c, mu);
+    LQGK_UNROLL for (int k = 0; k < NJ; ++k) out[(size_t)t * NJ + k] = (T)mu[k];
+    LQGK_UNROLL for (int k = 0; k < D; ++k) x0[k] = x1[k];
+  }
+}
+
 // Sequential covariance adjoint: lean (no constants, no accumulators); emits Sgb_t, SF_t for the parallel contraction.
 // Ring inputs per step: Fu_t, (J_t, S'^-1_t) and the [SUM_J, SUMP) tail of the trial sums.
 template <class DM>
@@ -900,7 +945,12 @@ __host__ __device__ constexpr int pow2_ceil(int v) { return v <= 1 ? 1 : (v <= 2
 #define LQGK_REV_REC_REGS 1
 #endif
 template <class DM, int RT>
-__global__ void __launch_bounds__(32 * TRIAL_WARPS_REV, LQGK_REV_MIN_CTAS) k_trial_rev(const float* __restrict__ rec, const float* __restrict__ xc_all,
+#if LQGK_REV_MIN_CTAS > 1
+__global__ void __launch_bounds__(32 * TRIAL_WARPS_REV, LQGK_REV_MIN_CTAS) k_trial_rev(
+#else
+__global__ void __launch_bounds__(32 * TRIAL_WARPS_REV) k_trial_rev(
+#endif
+    const float* __restrict__ rec, const float* __restrict__ xc_all,
                                                                 size_t xc_sample_stride, const float* __restrict__ hist,
                                                                 const float* __restrict__ w, int n_samples, int N, int Tn,
                                                                 float* __restrict__ sums) {

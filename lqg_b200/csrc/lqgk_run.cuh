@@ -32,21 +32,40 @@ extern thread_local Profiler g_prof;
 extern thread_local int g_streams;
 extern thread_local int g_contrib_warps;   // target number of (sample-group x time-range) warps of the contraction kernels
 extern thread_local int g_aux_streams;   // bit 0: lqr_fwd | kf_fwd, bit 1: contraction passes, bit 2: kf_rev | lqr_rev | reduce
+// SM count of the calling thread's current device (queried once per device, never hard-coded): sizes the grids of the
+// time-parallel kernels.
+struct DeviceInfo {
+  int device = -1, sms = 0;
+};
+extern thread_local DeviceInfo g_dev;
+inline int sm_count() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != g_dev.device || g_dev.sms <= 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    g_dev.device = dev;
+    g_dev.sms = n;
+  }
+  return g_dev.sms;
+}
+
+// Internal streams / events of the calling thread (one pool per thread and device).  lqgk_init() creates them up front;
+// entry points only create what is missing when the caller's stream is NOT being captured into a CUDA graph (creating
+// streams inside a capture is illegal) and otherwise return LQGK_E_NOT_INITIALISED.
 struct StreamPool {
+  static constexpr size_t NEV = 64;
   int device = -1;
   std::vector<cudaStream_t> streams;
   std::vector<cudaEvent_t> joins;
   cudaEvent_t fork = nullptr;
   std::vector<cudaEvent_t> evs;   // round-robin pool for intra-chunk dependencies (timing disabled)
   size_t ev_next = 0;
-  cudaEvent_t next_event() {
-    if (evs.size() < 64) {
-      cudaEvent_t e;
-      cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-      evs.push_back(e);
-      return e;
-    }
-    return evs[ev_next++ % evs.size()];
+  cudaEvent_t next_event() { return evs[ev_next++ % evs.size()]; }
+  bool ready(int n) const {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    return dev == device && fork && (int)streams.size() >= n && evs.size() >= NEV;
   }
   int ensure(int n) {
     int dev = 0;
@@ -59,6 +78,11 @@ struct StreamPool {
       device = dev;
     }
     if (!fork && cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess) return LQGK_E_CUDA;
+    while (evs.size() < NEV) {
+      cudaEvent_t e;
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return LQGK_E_CUDA;
+      evs.push_back(e);
+    }
     while ((int)streams.size() < n) {
       cudaStream_t st;
       cudaEvent_t ev;
@@ -68,6 +92,14 @@ struct StreamPool {
       joins.push_back(ev);
     }
     return LQGK_OK;
+  }
+  // what an entry point calls: never creates anything while `caller` is being captured
+  int acquire(int n, cudaStream_t caller) {
+    if (ready(n)) return LQGK_OK;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(caller, &cs) != cudaSuccess) return LQGK_E_CUDA;
+    if (cs != cudaStreamCaptureStatusNone) return LQGK_E_NOT_INITIALISED;
+    return ensure(n);
   }
 };
 extern thread_local StreamPool g_pool;
@@ -136,6 +168,8 @@ Plan make_plan(const LqgkDims& d, int mode, bool tv, size_t Sc) {
   if (mode == LQGK_MODE_GAINS) {
     p.l = take(sizeof(double) * T * DM::U * Sc);
     p.H = take(sizeof(double) * T * DM::U * DM::U * Sc);
+  } else if (mode == LQGK_MODE_MOMENTS) {
+    p.rec = take(sizeof(float) * Sc * T * DM::REC);
   } else {
     p.rec = take(sizeof(float) * Sc * T * DM::REC);
     p.ll = take(sizeof(double) * Sc * N);
@@ -201,7 +235,7 @@ inline int launch_repack_obs(cudaStream_t st, const LqgkDims& d, int row, const 
   const int nsets = per_sample ? n : 1;
   *xc_stride = per_sample ? per : 0;
   const size_t total = per * nsets;
-  const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
+  const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 16);
   ProfScope ps_(PK_PACK, st);
   k_repack_obs<float><<<blocks, 256, 0, st>>>(x_tm, (size_t)d.x_sample_stride, per_sample ? s0 : 0, nsets, d.N, row, d.T + 1, d.d, xc);
   LQGK_LAUNCH_CHECK();
@@ -246,6 +280,7 @@ struct Call {
   void* ws;
   size_t ws_bytes;
   cudaStream_t stream;
+  void *mu_out = nullptr, *Sig_out = nullptr;   // moments entry point
 };
 
 template <class DM, class T>
@@ -275,33 +310,51 @@ int run(const Call& c) {
   const bool aux = auxm != 0;
   const int nstreams = (ns > 1 ? ns : 0) + (aux ? 2 * ns : 0);
   if (nstreams > 0) {
-    if (int rcp = g_pool.ensure(nstreams)) return rcp;
+    if (int rcp = g_pool.acquire(nstreams, c.stream)) return rcp;
   }
   const int aux0 = ns > 1 ? ns : 0;     // index of the first auxiliary stream
+  // internal streams this call has forked work onto (only those are joined back: under CUDA-graph capture a stream that was
+  // never forked from the caller's stream is not part of the capture and must not be waited on)
+  uint64_t touched = 0;
+  auto touch = [&](cudaStream_t s) {
+    for (int i = 0; i < nstreams; ++i)
+      if (g_pool.streams[i] == s) touched |= 1ull << i;
+  };
   // make `to` wait for everything enqueued on `from` so far
+  auto is_idle_pool_stream = [&](cudaStream_t s) {
+    for (int i = 0; i < nstreams; ++i)
+      if (g_pool.streams[i] == s) return ((touched >> i) & 1ull) == 0;
+    return false;
+  };
   auto dep = [&](cudaStream_t from, cudaStream_t to) {
     if (from == to) return;
+    if (is_idle_pool_stream(from)) return;   // nothing of this call runs there (and under capture it is outside the graph)
     cudaEvent_t e = g_pool.next_event();
     cudaEventRecord(e, from);
     cudaStreamWaitEvent(to, e, 0);
+    touch(to);
   };
   if (ns > 1) {
     if (cudaEventRecord(g_pool.fork, c.stream) != cudaSuccess) return LQGK_E_CUDA;
-    for (int i = 0; i < ns; ++i)
+    for (int i = 0; i < ns; ++i) {
       if (cudaStreamWaitEvent(g_pool.streams[i], g_pool.fork, 0) != cudaSuccess) return LQGK_E_CUDA;
+      touched |= 1ull << i;
+    }
   }
   // join on every exit path once side streams may have work
   struct Joiner {
-    int ns, nstreams;
+    int nstreams;
     cudaStream_t main;
+    const uint64_t* touched;
     ~Joiner() {
       // slice streams (and, on error paths, auxiliary streams) rejoin the caller's stream
       for (int i = 0; i < nstreams; ++i) {
+        if (!((*touched >> i) & 1ull)) continue;
         cudaEventRecord(g_pool.joins[i], g_pool.streams[i]);
         cudaStreamWaitEvent(main, g_pool.joins[i], 0);
       }
     }
-  } joiner{ns, nstreams, c.stream};
+  } joiner{nstreams, c.stream, &touched};
   const int Tn = d.T, N = d.N;
   const size_t tstride = tv ? (size_t)cl.total * Sc : 0;
 
@@ -379,6 +432,25 @@ int run(const Call& c) {
     // GPU idle and every step costs one thread's instruction stream; the warp-per-sample kernels of the large systems spread
     // a step over 32 lanes (S = 8: covariance forward 3.3 -> 2.4 ms, sequential adjoint 2.5 -> 1.0 ms) and win up to ~1,000
     // samples.  The Riccati / Kalman sweeps stay thread-per-sample (3 x 3 products do not spread), hence GAINS_MINOR.
+    if (c.mode == LQGK_MODE_MOMENTS) {
+      // slow path: full predictive moments (conditional_moments / belief_tracking_distribution), thread-per-sample covariance
+      // kernel writing Sigma in the caller's layout, thread-per-trial mean kernel
+      {
+        size_t smem = sizeof(double) * 32 * CovC<DM>::n;
+        ProfScope ps_(PK_COV_FWD, st);
+        k_cov_moments<DM, T><<<nblk, 32, smem, st>>>(D(p.cst), Sc, tstride, Tn, n, D(p.L), D(p.K), F(p.rec),
+                                                     c.Sig_out ? (T*)c.Sig_out + s0 * Tn * DM::N * DM::N : nullptr);
+        LQGK_LAUNCH_CHECK();
+      }
+      if (c.mu_out) {
+        size_t total = (size_t)n * N;
+        ProfScope ps_(PK_TRIAL_FWD, st);
+        k_trial_moments<DM, T><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(F(p.rec), c.x_tm, (size_t)d.x_sample_stride, (int)s0, n, N, Tn,
+                                                                              (T*)c.mu_out + s0 * N * Tn * DM::N);
+        LQGK_LAUNCH_CHECK();
+      }
+      continue;
+    }
     const bool warp_cov = !tv && d.S <= g_warp_cov_max_samples;
     const int wblk = (npad + BW_WARPS - 1) / BW_WARPS;
     if (warp_cov) {
@@ -445,7 +517,7 @@ int run(const Call& c) {
         LQGK_LAUNCH_CHECK();
       }
       {
-        int chunks = std::max(1, std::min((Tn + 3) / 4, (148 * 12 + npad - 1) / npad));
+        int chunks = std::max(1, std::min((Tn + 3) / 4, (sm_count() * 12 + npad - 1) / npad));
         ProfScope ps_(PK_COV_CONTRIB, st);
         kw_cov_contrib<DM, true><<<dim3(wblk, chunks), 32 * BW_WARPS, smemc, st>>>(D(p.cst), Sc, npad, Tn, D(p.L), D(p.K), D(p.Cs), D(p.SGB),
                                                                                   D(p.SGBI), D(p.SFW), F(p.sums), D(p.acc), D(p.Lbar), D(p.Kbar),
@@ -462,7 +534,8 @@ int run(const Call& c) {
     }
     {
       // (sample-group x time-range) warps: enough to occupy every SM a few times over
-      int chunks = std::max(1, std::min((Tn + 7) / 8, (g_contrib_warps + nblk - 1) / nblk));
+      const int cwarps = g_contrib_warps > 0 ? g_contrib_warps : sm_count() * 30;
+      int chunks = std::max(1, std::min((Tn + 7) / 8, (cwarps + nblk - 1) / nblk));
       dim3 grid(nblk, chunks);
       if constexpr (contrib_merged<DM>()) {
         size_t smem = smem_cov_contrib<DM, 2>();

@@ -129,9 +129,13 @@ LQGK_HD void kf_fwd_body(const GCst& g, WView lc, int T, WView Kw, bool save_P, 
 // ---------------------------------------------------------------------------------------------- COV fwd
 // Sink: put(idx, v) stores one float of the current step's record; commit(t) publishes the record.
 // When save_adj: C_t -> Cw, Fu_t -> FUw, (J_t, S'^-1_t) -> JSw, J_0 (initial conditioning gain) -> J0w.
-template <class DM, class Sink>
+struct NoSigSink {
+  LQGK_HD void operator()(int, int, double) const {}
+};
+// sig(t, e, v) (optional): full predictive joint covariance of step t (moments entry point).
+template <class DM, class Sink, class SigSink = NoSigSink>
 LQGK_HD void cov_fwd_body(const GCst& g, WView lc, int T, WView Lw, WView Kw, bool save_adj, WView Cw, WView FUw, WView JSw,
-                          WView J0w, Sink&& sink) {
+                          WView J0w, Sink&& sink, SigSink&& sig = SigSink{}) {
   constexpr int B = DM::B, U = DM::U, Y = DM::Y, R = DM::R, D = DM::D;
   using C = CovC<DM>;
   using SR = CovSeqRev<DM>;
@@ -154,7 +158,7 @@ LQGK_HD void cov_fwd_body(const GCst& g, WView lc, int T, WView Lw, WView Kw, bo
                          if (which == 0) FUw((size_t)t * SR::NSF + e) = v;
                          else JSw((size_t)t * SR::NJS + e) = v;
                        }
-                     });
+                     }, [&](int e, double v) { sig(t, e, v); });
     sink.commit(t);
   }
 }

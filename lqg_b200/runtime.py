@@ -306,3 +306,64 @@ def log_likelihood(actor: LQGSpec, dynamics: LQGSpec, x: torch.Tensor, Sigma0: O
         mats.append(_row_major(Sigma0 if Sigma0.dim() == 3 else Sigma0.unsqueeze(0)).to(dt))
     ll = _LogLikFn.apply(x_tm, dims, has_qf, has_s0, len(ACT_KEYS), *mats)
     return ll[0] if (actor.A.dim() == 3 and dynamics.A.dim() == 3) else ll
+
+
+def _base_mats(actor: LQGSpec, dynamics: LQGSpec, dt):
+    def base(M):
+        M4 = _as4(M)
+        return _row_major(M4[:, 0] if is_time_invariant(M4) else M4).to(dt)
+    return {k: base(getattr(actor, k)) for k in ACT_KEYS}, {k: base(getattr(dynamics, k)) for k in DYN_KEYS}
+
+
+def moments(actor: LQGSpec, dynamics: LQGSpec, x: torch.Tensor, Sigma0: Optional[torch.Tensor] = None, want_mu=True, want_sigma=True):
+    """CUDA predictive moments of the joint state (reference ``vmap(System.conditional_moments)``, lqg/system.py:142-235):
+    ``mu[(S,) n, T, nj]``, ``Sigma[(S,) T, nj, nj]``.  Returns None if no kernels are compiled for the dimensions (callers then
+    use the torch slow path)."""
+    _require_cuda(actor.A, "actor spec")
+    lib = abi.load_library()
+    n, T1, d = x.shape[-3:]
+    dims = dims_of(actor, dynamics, n, d)
+    if (dims.x, dims.b, dims.u, dims.y, dims.d) not in SUPPORTED_DIMS or dims.x + dims.b > 12 or dims.T != T1 - 1:
+        return None
+    _check_no_cross_cost(actor)
+    dt = actor.A.dtype
+    act, dyn = _base_mats(actor, dynamics, dt)
+    if not _qf_is_default(actor):
+        Qf = actor.Qf
+        act["Qf"] = _row_major(Qf if Qf.dim() == 3 else Qf.unsqueeze(0)).to(dt)
+    x_tm = lib.pack_obs(x.detach(), stream=_stream(x.device)) if x.dim() == 3 else x.detach().permute(0, 2, 1, 3).to(torch.float32).contiguous()
+    s0 = None if Sigma0 is None else _row_major(Sigma0 if Sigma0.dim() == 3 else Sigma0.unsqueeze(0)).to(dt)
+    dev = actor.A.device
+    ws = workspace(dev, lib.workspace_bytes(dims, abi.MODE_MOMENTS, 0))
+    mu, Sig = lib.moments(dims, act, dyn, x_tm, sigma0=s0, want_mu=want_mu, want_sigma=want_sigma, ws=ws, stream=_stream(dev))
+    if actor.A.dim() == 3 and dynamics.A.dim() == 3:
+        mu, Sig = (mu[0] if mu is not None else None), (Sig[0] if Sig is not None else None)
+    return mu, Sig
+
+
+def simulate(actor: LQGSpec, dynamics: LQGSpec, L, l, K, n: int, seed: int, x0=None, xhat0=None, return_all=False):
+    """CUDA batched simulator (reference ``System.simulate``, lqg/system.py:62-140) for given gains ``L[(S,) T, u, b]``,
+    ``l[(S,) T, u]``, ``K[(S,) T, b, y]``; returns ``x[(S,) n, T+1, xdim]`` (and xhat, y, u).  None if a dimension exceeds the
+    kernel's limit (callers then use the torch slow path)."""
+    _require_cuda(actor.A, "actor spec")
+    lib = abi.load_library()
+    dims = dims_of(actor, dynamics, n, 1)
+    if max(dims.x, dims.b, dims.u, dims.y) > 40:
+        return None
+    dt, dev = actor.A.dtype, actor.A.device
+    S = dims.S
+    act = {k: _row_major(_as4(getattr(actor, k))).to(dt) for k in ("A", "B", "F")}
+    dyn = {k: _row_major(_as4(getattr(dynamics, k))).to(dt) for k in DYN_KEYS}
+
+    def per_sample(t, nd):   # gains with an optional leading sample axis -> (S, ...) contiguous
+        if t is None:
+            return None
+        t = t if t.dim() == nd + 1 else t.unsqueeze(0)
+        return t.expand(S, *t.shape[1:]).to(dt).contiguous()
+
+    vec = lambda v: None if v is None else torch.as_tensor(v, dtype=dt, device=dev).reshape(-1).contiguous()
+    out = lib.simulate(dims, act, dyn, per_sample(L, 3), per_sample(l, 2), per_sample(K, 3), seed, x0=vec(x0), xhat0=vec(xhat0),
+                       return_all=return_all, stream=_stream(dev))
+    if actor.A.dim() == 3 and dynamics.A.dim() == 3:
+        return tuple(o[0] for o in out) if return_all else out[0]
+    return out

@@ -174,7 +174,17 @@ class System:
         return Fj, Gj
 
     def _moments(self, x: torch.Tensor, Sigma0=None):
-        """mu[..., n_trials, T, n], Sigma[..., T, n, n]: predictive moments of (x, xhat)_{t+1} given x_{0..t}."""
+        """mu[..., n_trials, T, n], Sigma[..., T, n, n]: predictive moments of (x, xhat)_{t+1} given x_{0..t}.
+        CUDA kernels (lqgk_moments_*) for the compiled small systems, torch float64 otherwise."""
+        if self.actor.A.is_cuda:
+            s0 = None if Sigma0 is None else torch.as_tensor(Sigma0, dtype=self.dtype, device=self.device)
+            out = runtime.moments(self.actor, self.dynamics, x.to(self.device), Sigma0=s0)
+            if out is not None:
+                return out
+        return self._moments_torch(x, Sigma0)
+
+    def _moments_torch(self, x: torch.Tensor, Sigma0=None):
+        """Host-side slow path of _moments (dimension tuples without kernels; also the check of the kernels in tests)."""
         x = x.to(self.device, torch.float64)
         n, T1, d = x.shape
         gains, K = self._gains(Sigma0)
@@ -213,15 +223,21 @@ class System:
     def simulate(self, rng_key=None, n=1, x0=None, xhat0=None, Sigma0=None, return_all=False):
         """Simulate n trials (system.py:62-140).  ``rng_key``: int seed or ``torch.Generator`` (the reference's JAX
         threefry stream cannot be reproduced; samples differ, the distribution does not).  Un-batched specs only."""
-        if self.actor.A.dim() != 3:
-            raise NotImplementedError("simulate() expects an un-batched system")
         dev, dt = self.device, self.dtype
+        if self.actor.A.dim() != 3 and (dev.type != "cuda" or isinstance(rng_key, torch.Generator)):
+            raise NotImplementedError("simulate() of a batched system needs the CUDA simulator (device 'cuda', integer seed)")
         if isinstance(rng_key, torch.Generator):
             gen = rng_key
         else:
             gen = torch.Generator(device=dev)
             gen.manual_seed(int(rng_key) if rng_key is not None else 0)
         gains, K = self._gains(Sigma0)
+        if dev.type == "cuda" and not isinstance(rng_key, torch.Generator):
+            # batched Philox simulator kernel (lqgk_simulate_*): one thread per trial
+            out = runtime.simulate(self.actor, self.dynamics, gains.L, gains.l, K, n, int(rng_key) if rng_key is not None else 0,
+                                   x0=x0, xhat0=xhat0, return_all=return_all)
+            if out is not None:
+                return out
         T, xd, bd, yd = self.T, self.xdim, self.bdim, self.ydim
         x = torch.zeros(n, xd, dtype=dt, device=dev) if x0 is None else torch.as_tensor(x0, dtype=dt, device=dev).expand(n, xd).clone()
         xh = torch.zeros(n, bd, dtype=dt, device=dev) if xhat0 is None else torch.as_tensor(xhat0, dtype=dt, device=dev).expand(n, bd).clone()

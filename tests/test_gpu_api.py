@@ -221,3 +221,38 @@ def test_terminal_cost_is_forwarded_and_cross_cost_refused():
     P = torch.ones_like(m.actor.P)
     with pytest.raises(NotImplementedError, match="P = 0"):
         System(m.actor._replace(P=P), m.dynamics).log_likelihood(torch.tensor(X, device=DEV))
+
+
+def test_vjp_call_is_capturable_into_a_cuda_graph_and_replays_identically():
+    """After lqgk_init() no entry point creates CUDA objects, so one fused forward+adjoint call (with its internal fork/join
+    over auxiliary streams) can be captured into a CUDA graph -- how XLA may run an FFI handler -- and replayed."""
+    from lqg_b200 import abi
+    lib = abi.load_library()
+    lib.init(1)
+    T, N, S = 100, 10, 40
+    mats = [O.subjective_actor_mats(sigma_target=6.0 + s) for s in range(S)]
+    X = _sim(mats[0], T, N, seed=6).astype(np.float32)
+    dims = abi.LqgkDims(S, N, T, 2, 3, 1, 2, 2)
+    act = {k: torch.tensor(np.stack([np.ascontiguousarray(m[0][k]) for m in mats]), dtype=torch.float32, device=DEV) for k in abi.ACTOR_KEYS}
+    dyn = {k: torch.tensor(np.stack([np.ascontiguousarray(m[1][k]) for m in mats]), dtype=torch.float32, device=DEV) for k in abi.DYN_KEYS}
+    x_tm = lib.pack_obs(torch.tensor(X, device=DEV))
+    ws = torch.empty(lib.workspace_bytes(dims, abi.MODE_VJP, 0), dtype=torch.uint8, device=DEV)
+    st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(st):
+        ll0, ga0, gd0, _ = lib.loglik_vjp(dims, act, dyn, x_tm, ws=ws, stream=st.cuda_stream)   # eager (also sets kernel attributes)
+    st.synchronize()
+    ref = [ll0.clone()] + [v.clone() for v in list(ga0.values()) + list(gd0.values())]
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=st):
+        ll1, ga1, gd1, _ = lib.loglik_vjp(dims, act, dyn, x_tm, ws=ws, stream=torch.cuda.current_stream().cuda_stream)
+    outs = [ll1] + list(ga1.values()) + list(gd1.values())
+    for rep in range(2):
+        for o in outs:
+            o.fill_(float("nan"))
+        ws.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(outs[0], ref[0])                                     # log-likelihoods: bit-identical
+        for o, r in zip(outs[1:], ref[1:]):                                     # gradients: FP64 atomics order may differ in the last bit
+            assert torch.allclose(o, r, rtol=1e-6, atol=1e-7 * r.abs().max().item())

@@ -96,3 +96,26 @@ def test_factorised_axes_equal_general_kernels_and_oracle(data):
         g_ref = torch.autograd.grad(outs, th, grad_outputs=cots, allow_unused=True)
         g_ref = np.array([0.0 if gi is None else gi.item() for gi in g_ref])
         assert np.allclose(g_fac[s].cpu().numpy(), g_ref, rtol=1e-3, atol=1e-5 * np.abs(g_ref).max()), (g_fac[s], g_ref)
+
+
+def test_32_random_samples_of_a_32768_sample_sweep_match_the_oracle(data):
+    """Half of config c3 in ONE call (32,768 parameter samples x 100 trials x T=1200: thread-per-sample covariance kernels,
+    7 trials per lane, checkpointed adjoint) through the public API; 32 randomly chosen samples are compared with the float64
+    autodiff oracle: log-likelihood rtol 1e-4, every gradient component rtol 1e-3 (components below 1e-4 of the largest one
+    on that absolute band)."""
+    from oracle import lqg_torch as OT
+    S = 32768
+    theta = torch.tensor(bench.make_theta(S, 29), device=DEV, requires_grad=True)
+    ll = _model(theta).log_likelihood(data)
+    ll.sum().backward()
+    torch.cuda.synchronize()
+    assert ll.shape == (S, N) and torch.isfinite(ll).all() and torch.isfinite(theta.grad).all()
+    pick = np.sort(np.random.default_rng(31).choice(S, 32, replace=False))
+    tho = theta.detach()[pick].double().cpu().requires_grad_()
+    a, d = OT.subjective_actor(dim=2, **{n: tho[:, i] for i, n in enumerate(bench.PARAM_NAMES)})
+    llo = OT.log_likelihood(a, d, data.double().cpu())
+    llo.sum().backward()
+    assert np.allclose(ll.detach()[pick].cpu().numpy(), llo.detach().numpy(), rtol=1e-4)
+    g, go = theta.grad[pick].double().cpu().numpy(), tho.grad.numpy()
+    band = 1e-3 * np.maximum(np.abs(go), 1e-4 * np.abs(go).max(axis=1, keepdims=True))
+    assert (np.abs(g - go) <= band).all(), float((np.abs(g - go) / band).max())

@@ -30,7 +30,7 @@ LL_RTOL, GRAD_RTOL, GAIN_RTOL = 1e-4, 1e-3, 1e-4        # BASELINE.json north_st
 class Fixture:
     def __init__(self, path):
         z = np.load(path)
-        self.z = z
+        self.z, self.path = z, path
         self.model, self.delay, self.T, self.N, self.d = str(z["model"]), int(z["delay"]), int(z["T"]), int(z["N"]), int(z["obs_dim"])
         self.fixed = {str(k): (int(v) if float(v).is_integer() else float(v)) for k, v in zip(z["fixed_names"], z["fixed_values"])}
         self.names = [str(k) for k in z["param_names"]]
@@ -62,6 +62,22 @@ class Fixture:
         for k in abi.DYN_KEYS:
             g += np.tensordot(self.z["jac_dyn_" + k], np.asarray(gd[k], dtype=np.float64), axes=([1, 2], [0, 1]))
         return g
+
+
+def _record_parity(fx, dtype, ll, g, gref, err):
+    """Measured GPU errors of every fixture -> gpurun_out/parity_errors.jsonl (copied to profiles/ after a GPU run)."""
+    import json
+    out = os.path.join(H.ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    rec = {"fixture": os.path.basename(fx.path)[:-4], "dtype": str(dtype).replace("torch.", ""), "params": fx.names,
+           "ll_max_rel_err": float(np.abs(ll / fx.z["ll"] - 1).max()),
+           "grad_ref_float64_adjoint": [float(v) for v in gref], "grad_ref_reference_fd": [float(v) for v in fx.z["grad"]],
+           "grad_gpu": [float(v) for v in g],
+           "grad_rel_err": [float(e / abs(r)) if r != 0 else None for e, r in zip(err, gref)],
+           "grad_err_over_max": [float(e / np.abs(gref).max()) for e in err],
+           "component_over_max": [float(abs(r) / np.abs(gref).max()) for r in gref]}
+    with open(os.path.join(out, "parity_errors.jsonl"), "a") as f:
+        f.write(json.dumps(rec) + "\n")
 
 
 @pytest.fixture(params=FIXTURES, ids=IDS)
@@ -147,9 +163,22 @@ def test_cuda_public_api_reproduces_reference(fx, dtype):
     m, th = fx.product_model(dev, dtype, requires_grad=True)
     ll = m.log_likelihood(torch.tensor(fx.X, device=dev))
     ll.sum().backward()
-    assert np.allclose(ll.detach().double().cpu().numpy(), fx.z["ll"], rtol=LL_RTOL)
+    llv = ll.detach().double().cpu().numpy()
+    assert np.allclose(llv, fx.z["ll"], rtol=LL_RTOL)
     g = np.array([t.grad.item() for t in th])
-    assert np.allclose(g, fx.z["grad"], rtol=GRAD_RTOL, atol=fx.g_atol + 1e-5 * np.abs(fx.z["grad"]).max()), (g, fx.z["grad"])
+    # ELEMENT-WISE rtol 1e-3 (north star) for every component that is at least 1e-4 of the largest one; smaller components
+    # (parameters sitting at an optimum of this data set) are held to the same absolute band, 1e-3 * 1e-4 * max|g|.
+    # Reference = the float64 hand adjoint of the oracle chained through the REFERENCE constructor's Jacobians: the exact
+    # gradient of the function whose finite differences the fixture stores (test_oracle_adjoint_matches_reference_gradient
+    # pins it to them within their own error estimate, which is too coarse -- up to 2e-4 of max|g| -- to test rtol 1e-3 on
+    # small components directly).
+    _, (oga, ogd) = AD.value_and_grad(fx.ref_act, fx.ref_dyn, fx.X.astype(np.float64))
+    gref = fx.chain(oga, ogd)
+    assert np.allclose(gref, fx.z["grad"], rtol=1e-5, atol=fx.g_atol)
+    band = GRAD_RTOL * np.maximum(np.abs(gref), 1e-4 * np.abs(gref).max())
+    err = np.abs(g - gref)
+    _record_parity(fx, dtype, llv, g, gref, err)
+    assert (err <= band).all(), (fx.names, g, gref, err / np.maximum(np.abs(gref), 1e-300))
     with torch.no_grad():
         m64, _ = fx.product_model(dev, torch.float64)
         gains = lqr.backward(m64.actor)
