@@ -339,6 +339,8 @@ def run_ours(args):
         lib.set_kernel_overlap(args.overlap)
     if args.contrib_warps > 0:
         lib.lib.lqgk_set_contrib_warps(args.contrib_warps)
+    if args.pipe_max >= 0:
+        lib.set_pipeline(args.pipe_max, args.pipe_segments)
     S_total, N, T = args.samples, args.trials, args.T
     lo, hi = parallel.shard_range(S_total, rank, world)
     S = hi - lo                                        # this rank's samples (strong scaling)
@@ -620,6 +622,8 @@ def main():
     ap.add_argument("--streams", type=int, default=0, help="internal concurrent sample slices (0 = library default)")
     ap.add_argument("--contrib-warps", type=int, default=0)
     ap.add_argument("--overlap", type=int, default=-1, help="kernel-overlap mask (see lqgk_set_kernel_overlap); -1 = library default")
+    ap.add_argument("--pipe-max", type=int, default=-1, help="largest chunk (samples) that uses the pipelined launch sequence; -1 = library default")
+    ap.add_argument("--pipe-segments", type=int, default=6)
     ap.add_argument("--no-factorize", action="store_true", help="run the general 2-D (n=10) kernels instead of the per-axis factorisation")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -179,6 +179,12 @@ int lqgk_set_streams(int n);
  * concurrently on internal auxiliary streams.  mask bit 0: lqr_fwd | kf_fwd, bit 1: contraction passes, bit 2: adjoint tail;
  * default 6. */
 int lqgk_set_kernel_overlap(int mask);
+/* Pipelined launch sequence of the fused forward+adjoint call: chunks of at most `max_samples` parameter samples (default:
+ * no limit; 0 = never) cut every sweep over time into `segments` segments (default 6) and run the sweeps of one direction as a
+ * software pipeline over the internal streams (kf_fwd -> cov_fwd -> trial_fwd, then trial_rev -> cov_seq_rev -> contraction ->
+ * kf_rev): at small sample counts every sweep is latency-bound and the chain of nine sweeps, not the arithmetic, sets the time of
+ * one evaluation (a NUTS leapfrog).  Results do not depend on the setting beyond FP64 summation order. */
+int lqgk_set_pipeline(int max_samples, int segments);
 /* Tuning knob: target number of (32-sample group x time-range) warps of the time-parallel contraction kernels. */
 int lqgk_set_contrib_warps(int n);
 /* Tuning knob: likelihood calls with at most n parameter samples run the covariance kernels one WARP per sample (shared-memory

@@ -324,6 +324,9 @@ class Library:
     def set_warp_cov_max_samples(self, n: int):
         self._check(self.lib.lqgk_set_warp_cov_max_samples(C.c_int(int(n))), "lqgk_set_warp_cov_max_samples")
 
+    def set_pipeline(self, max_samples: int, segments: int = 6):
+        self._check(self.lib.lqgk_set_pipeline(C.c_int(int(max_samples)), C.c_int(int(segments))), "lqgk_set_pipeline")
+
     def set_kernel_overlap(self, mask: int):
         self._check(self.lib.lqgk_set_kernel_overlap(C.c_int(int(mask))), "lqgk_set_kernel_overlap")
 

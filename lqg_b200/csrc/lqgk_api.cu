@@ -21,6 +21,8 @@ thread_local DeviceInfo g_dev;
 thread_local int g_aux_streams = 6;
 thread_local int g_warp_cov_max_samples = 512;   // measured crossover between 512 and 1,024 samples (profiles/r01_e_*.md)
 thread_local StreamPool g_pool;
+thread_local int g_pipe_max_samples = 1 << 30;   // measured: 1.2-1.4x at 8..8,192 samples, +2 % at 65,536 (profiles/r02_g_pipeline.md)
+thread_local int g_pipe_segments = 6;
 }
 
 namespace {
@@ -351,6 +353,12 @@ int lqgk_set_contrib_warps(int n) {
 int lqgk_set_warp_cov_max_samples(int n) {
   if (n < 0) return LQGK_E_INVALID;
   g_warp_cov_max_samples = n;
+  return LQGK_OK;
+}
+int lqgk_set_pipeline(int max_samples, int segments) {
+  if (max_samples < 0 || segments < 1 || segments > 64) return LQGK_E_INVALID;
+  g_pipe_max_samples = max_samples;
+  g_pipe_segments = segments;
   return LQGK_OK;
 }
 int lqgk_set_kernel_overlap(int mask) {

@@ -132,7 +132,7 @@ int run_big(const Call& c) {
     rc = LQGK_E_UNSUPPORTED;
     static_for<1, trial_rt_max<DM>() + 1>([&](auto RTC) {
       if (RT == decltype(RTC)::value)
-        rc = launch_trial_rev<DM, decltype(RTC)::value>(st, F(p.rec), F(p.xc), xcs, hist, F(p.w), n, N, Tn, F(p.sums));
+        rc = launch_trial_rev<DM, decltype(RTC)::value>(st, F(p.rec), F(p.xc), xcs, hist, F(p.w), n, N, Tn, F(p.sums), F(p.carcb));
     });
     if (rc) return rc;
     if (cudaMemsetAsync(D(p.acc), 0, sizeof(double) * cl.total * Sc, st) != cudaSuccess) return LQGK_E_CUDA;

@@ -164,7 +164,9 @@ __device__ __forceinline__ void bw_condition(int lane, const double* Sig, double
 // GAINS_MINOR: L, K are sample-minor [t][e][Sc] (written by the thread-per-sample Riccati / Kalman kernels of the small systems).
 template <class DM, bool GAINS_MINOR = false>
 __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_fwd(const double* cst, size_t Sc, int npad, int Tn, const double* L, const double* K,
-                                                            int save_adj, double* Cs, double* FU, double* JS, double* J0, float* rec) {
+                                                            int save_adj, double* Cs, double* FU, double* JS, double* J0, float* rec,
+                                                            int t0 = 0, int t1 = -1) {
+  // [t0, t1): time range of this launch (t1 < 0: up to Tn); t0 > 0 continues from the C_{t0} saved in Cs (save_adj on)
   using W = BigW<DM>;
   using C = typename W::C;
   using SR = typename W::SR;
@@ -188,13 +190,23 @@ __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_fwd(const double* cst, s
   double* ld = Linv + 3 * D * D;
   auto gi = [&](int t, int E, int e) -> size_t { return GAINS_MINOR ? ((size_t)t * E + e) * Sc + s : (s * Tn + t) * (size_t)E + e; };
   bw_load_consts<C>(lane, cst + s, Sc, c, C::NSEG);
-  for (int e = lane; e < B * Y; e += 32) Kt[e] = K[gi(0, DM::EK, e)];
-  __syncwarp();
-  bw_joint_N<DM>(lane, c, Kt, KO, Nj);
-  __syncwarp();
-  bw_condition<DM>(lane, Nj, Linv, Z, ld, [&](int e, double v) { if (save_adj) J0[s * (R * D) + e] = v; }, Cm);
+  if (t1 < 0) t1 = Tn;
+  if (t0 == 0) {
+    for (int e = lane; e < B * Y; e += 32) Kt[e] = K[gi(0, DM::EK, e)];
+    __syncwarp();
+    bw_joint_N<DM>(lane, c, Kt, KO, Nj);
+    __syncwarp();
+    bw_condition<DM>(lane, Nj, Linv, Z, ld, [&](int e, double v) { if (save_adj) J0[s * (R * D) + e] = v; }, Cm);
+  } else {
+    const double* cs = Cs + (s * Tn + t0) * (size_t)DM::EC;
+    for (int e = lane; e < R * R; e += 32) {
+      const int i = e / R, j = e - i * R;
+      Cm[e] = cs[sidx(i, j)];
+    }
+    __syncwarp();
+  }
   float* recs = rec + s * (size_t)Tn * DM::REC;
-  for (int t = 0; t < Tn; ++t) {
+  for (int t = t0; t < t1; ++t) {
     for (int e = lane; e < U * B; e += 32) Lt[e] = L[gi(t, DM::EL, e)];
     for (int e = lane; e < B * Y; e += 32) Kt[e] = K[gi(t, DM::EK, e)];
     if (save_adj) {
@@ -253,12 +265,21 @@ __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_fwd(const double* cst, s
     if (lane == 0) rt[DM::REC_LOGDET] = (float)*ld;
     __syncwarp();
   }
+  if (save_adj && t1 < Tn) {   // where the next time segment continues from
+    double* cs = Cs + (s * Tn + t1) * (size_t)DM::EC;
+    for (int e = lane; e < R * R; e += 32) {
+      const int i = e / R, j = e - i * R;
+      if (j <= i) cs[i * (i + 1) / 2 + j] = Cm[e];
+    }
+  }
 }
 
 // Sequential covariance adjoint (CovSeqRev), warp per sample, t descending.
 template <class DM>
 __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_seq_rev(int npad, int Tn, int Ntr, const float* w, const double* FU, const double* JS,
-                                                                const double* J0, const float* sums, double* SGB, double* SGBI, double* SFW) {
+                                                                const double* J0, const float* sums, double* SGB, double* SGBI, double* SFW,
+                                                                int t0 = 0, int t1 = -1, double* carry = nullptr) {
+  // [t0, t1) walked downwards (t1 < 0: from Tn); `carry` ([s][R*R]) hands Cb from one launch to the next (pipelined sequence)
   using W = BigW<DM>;
   using SR = typename W::SR;
   constexpr int D = W::D, N = W::N, R = W::R;
@@ -281,9 +302,10 @@ __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_seq_rev(int npad, int Tn
   double sw = 0.0;
   for (int i = lane; i < Ntr; i += 32) sw += (double)w[s * Ntr + i];
   for (int m = 16; m >= 1; m >>= 1) sw += __shfl_xor_sync(FULL, sw, m);
-  for (int e = lane; e < R * R; e += 32) Cb[e] = 0.0;
+  if (t1 < 0) t1 = Tn;
+  for (int e = lane; e < R * R; e += 32) Cb[e] = t1 == Tn ? 0.0 : carry[s * (R * R) + e];
   __syncwarp();
-  for (int t = Tn - 1; t >= 0; --t) {
+  for (int t = t1 - 1; t >= t0; --t) {
     const double* fu = FU + (s * Tn + t) * (size_t)SR::NSF;
     const double* js = JS + (s * Tn + t) * (size_t)SR::NJS;
     const float* sm = sums + (s * Tn + t) * (size_t)DM::SUMP;
@@ -331,6 +353,10 @@ __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_seq_rev(int npad, int Tn
     __syncwarp();
     double* tmp = Cb; Cb = Cn; Cn = tmp;
   }
+  if (t0 > 0) {
+    for (int e = lane; e < R * R; e += 32) carry[s * (R * R) + e] = Cb[e];
+    return;
+  }
   // cotangent of C_0 = cond(N_0) as a joint symmetric cotangent (CovSeqRev::init)
   for (int e = lane; e < R * D; e += 32) J[e] = J0[s * (R * D) + e];
   __syncwarp();
@@ -359,7 +385,8 @@ __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_seq_rev(int npad, int Tn
 template <class DM, bool GAINS_MINOR = false>
 __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_contrib(const double* cst, size_t Sc, int npad, int Tn, const double* L, const double* K,
                                                                 const double* Cs, const double* SGB, const double* SGBI, const double* SFW,
-                                                                const float* sums, double* gacc, double* Lbar, double* Kbar, double* KbarF) {
+                                                                const float* sums, double* gacc, double* Lbar, double* Kbar, double* KbarF,
+                                                                int ta = 0, int tb = -1) {
   using W = BigW<DM>;
   using C = typename W::C;
   using SR = typename W::SR;
@@ -368,9 +395,10 @@ __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_contrib(const double* cs
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t s = (size_t)blockIdx.x * BW_WARPS + warp;
   if (s >= (size_t)npad) return;
-  const int nq = gridDim.y, q = blockIdx.y;
-  const int per = (Tn + nq - 1) / nq;
-  const int t0 = min(Tn, q * per), t1 = min(Tn, t0 + per);
+  if (tb < 0) tb = Tn;
+  const int nq = gridDim.y, q = blockIdx.y;       // the launch covers [ta, tb), cut into nq time ranges
+  const int per = (tb - ta + nq - 1) / nq;
+  const int t0 = min(tb, ta + q * per), t1 = min(tb, t0 + per);
   if (t0 >= t1) return;
   double* c = smw + (size_t)warp * W::CON_DOUBLES;
   double* acc = c + NC;

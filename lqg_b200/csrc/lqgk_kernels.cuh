@@ -157,11 +157,11 @@ __global__ void __launch_bounds__(32) k_lqr_fwd(const double* cst, size_t Sc, si
 
 template <class DM>
 __global__ void __launch_bounds__(32) k_kf_fwd(const double* cst, size_t Sc, size_t tstride, int Tn, double* K, int save_P,
-                                               double* Pkf) {
+                                               double* Pkf, int t0, int t1) {
   extern __shared__ __align__(16) double sm[];
   const int lane = threadIdx.x;
   const size_t s = (size_t)blockIdx.x * 32 + lane;
-  kf_fwd_body<DM>(GCst{cst + s, Sc, tstride}, WView{sm + lane, 32}, Tn, WView{K + s, Sc}, save_P != 0, WView{Pkf + s, Sc});
+  kf_fwd_body<DM>(GCst{cst + s, Sc, tstride}, WView{sm + lane, 32}, Tn, WView{K + s, Sc}, save_P != 0, WView{Pkf + s, Sc}, t0, t1);
 }
 
 template <class KC, class La>
@@ -260,10 +260,11 @@ struct SmemRecSink {
 constexpr int SEQ_NST = 3;   // ring depth of the sequential kernels
 
 // Covariance pass (forward).  Ring inputs per step: L_t, K_t.
+// [t0, t1): time range of this launch; t0 > 0 continues from the C_{t0} an earlier launch saved in Cs (save_adj on).
 template <class DM>
 __global__ void __launch_bounds__(32) k_cov_fwd(const double* cst, size_t Sc, size_t tstride, int Tn, const double* L,
                                                 const double* K, int save_adj, double* Cs, double* FU, double* JS, double* J0,
-                                                float* rec) {
+                                                float* rec, int t0, int t1) {
   extern __shared__ __align__(128) double sm[];
   constexpr int B = DM::B, U = DM::U, Y = DM::Y, R = DM::R, D = DM::D;
   using C = CovC<DM>;
@@ -280,23 +281,25 @@ __global__ void __launch_bounds__(32) k_cov_fwd(const double* cst, size_t Sc, si
   __syncwarp();
   Ring ring{{{L + s0, DM::EL}, {K + s0, DM::EK}}, Sc, nullptr, 0, 0, 0, ring_buf, bars, lane, ROWS, ROWS * 32, 0};
   ring.init();
-  for (int k = 0; k < SEQ_NST && k < Tn; ++k) ring.issue(k, k);
+  for (int k = 0; k < SEQ_NST && t0 + k < t1; ++k) ring.issue(t0 + k, k);
   WView lc{lcp + lane, 32};
   GCst g{cst + s, Sc, tstride};
-  load_consts<C>(g.at(0), lc, C::NSEG);
+  load_consts<C>(g.at(tstride ? t0 : 0), lc, C::NSEG);
   SmemRecSink<DM> sink{stage, rec + s * Tn * DM::REC, lane, 0};
   double Cm[R * R];
-  {
+  if (t0 == 0) {
     double K0[B * Y], J0v[R * D];
     LQGK_UNROLL for (int i = 0; i < B * Y; ++i) K0[i] = K[(size_t)i * Sc + s];
     CovFwd<DM>::init(lc, K0, Cm, J0v);
     if (save_adj) { LQGK_UNROLL for (int i = 0; i < R * D; ++i) J0[(size_t)i * Sc + s] = J0v[i]; }
+  } else {
+    load_sym_ws<R>(WView{Cs + s, Sc}, (size_t)t0 * DM::EC, Cm);
   }
   // (constants stay in shared memory here: a register copy of the 40 covariance constants made this kernel 10 % slower)
-  for (int t = 0; t < Tn; ++t) {
-    const int st = t % SEQ_NST;
+  for (int t = t0; t < t1; ++t) {
+    const int st = (t - t0) % SEQ_NST;
     const double* stg = ring.wait(st);
-    if (tstride && t != 0) load_consts<C>(g.at(t), lc, C::NSEG);
+    if (tstride && t != t0) load_consts<C>(g.at(t), lc, C::NSEG);
     double Lt[U * B], Kt[B * Y];
     {
       WView lv = ring.view(stg, 0), kv = ring.view(stg, DM::EL);
@@ -304,7 +307,7 @@ __global__ void __launch_bounds__(32) k_cov_fwd(const double* cst, size_t Sc, si
       LQGK_UNROLL for (int i = 0; i < B * Y; ++i) Kt[i] = kv(i);
     }
     __syncwarp();
-    if (t + SEQ_NST < Tn) ring.issue(t + SEQ_NST, st);
+    if (t + SEQ_NST < t1) ring.issue(t + SEQ_NST, st);
     if (save_adj) store_sym<R>(WView{Cs + s, Sc}, (size_t)t * DM::EC, Cm);
     CovFwd<DM>::step(lc, Lt, Kt, Cm, [&](int idx, float v) { sink.put(idx, v); },
                      [&](int which, int e, double v) {
@@ -315,6 +318,7 @@ __global__ void __launch_bounds__(32) k_cov_fwd(const double* cst, size_t Sc, si
                      });
     sink.commit(t);
   }
+  if (save_adj && t1 < Tn) store_sym<R>(WView{Cs + s, Sc}, (size_t)t1 * DM::EC, Cm);   // where the next time segment continues from
   sink.finish();
 }
 
@@ -365,9 +369,12 @@ __global__ void k_trial_moments(const float* __restrict__ rec, const float* __re
 
 // Sequential covariance adjoint: lean (no constants, no accumulators); emits Sgb_t, SF_t for the parallel contraction.
 // Ring inputs per step: Fu_t, (J_t, S'^-1_t) and the [SUM_J, SUMP) tail of the trial sums.
+// [t0, t1): time range of this launch (walked downwards).  t1 < Tn starts from the cotangent an earlier launch left in
+// `carry` ([R*R][Sc]); t0 > 0 leaves its own there instead of finishing with the initial-condition term.
 template <class DM>
 __global__ void __launch_bounds__(32) k_cov_seq_rev(size_t Sc, int Tn, int N, const float* w, const double* FU, const double* JS,
-                                                    const double* J0, const float* sums, double* SGB, double* SGBI, double* SFW) {
+                                                    const double* J0, const float* sums, double* SGB, double* SGBI, double* SFW,
+                                                    int t0, int t1, double* carry) {
   extern __shared__ __align__(128) double sm[];
   using SR = CovSeqRev<DM>;
   using Ring = StepRing<2, SEQ_NST>;
@@ -381,14 +388,16 @@ __global__ void __launch_bounds__(32) k_cov_seq_rev(size_t Sc, int Tn, int N, co
   Ring ring{{{FU + s0, SR::NSF}, {JS + s0, SR::NJS}}, Sc, sums + s0 * Tn * DM::SUMP + DM::SUM_J, Tn * DM::SUMP, DM::SUMP, FCNT,
             sm, bars, lane, ROWS, STAGE, 0};
   ring.init();
-  for (int k = 0; k < SEQ_NST && k < Tn; ++k) ring.issue(Tn - 1 - k, k);
+  const int nsteps = t1 - t0;
+  for (int k = 0; k < SEQ_NST && k < nsteps; ++k) ring.issue(t1 - 1 - k, k);
   double sw = 0.0;
   for (int i = 0; i < N; ++i) sw += (double)w[s * N + i];
   WView sc{scp + lane, 32};
   double Cb[R * R];
-  LQGK_UNROLL for (int i = 0; i < R * R; ++i) Cb[i] = 0.0;
-  for (int kk = 0; kk < Tn; ++kk) {
-    const int t = Tn - 1 - kk, st = kk % SEQ_NST;
+  if (t1 == Tn) { LQGK_UNROLL for (int i = 0; i < R * R; ++i) Cb[i] = 0.0; }
+  else { LQGK_UNROLL for (int i = 0; i < R * R; ++i) Cb[i] = carry[(size_t)i * Sc + s]; }
+  for (int kk = 0; kk < nsteps; ++kk) {
+    const int t = t1 - 1 - kk, st = kk % SEQ_NST;
     const double* stg = ring.wait(st);
     WView fuv = ring.view(stg, 0), jsv = ring.view(stg, SR::NSF);
     const float* fr = ring.frow(stg);
@@ -396,9 +405,10 @@ __global__ void __launch_bounds__(32) k_cov_seq_rev(size_t Sc, int Tn, int N, co
              [&](int e, double v) { SGB[((size_t)t * SR::NSGB + e) * Sc + s] = v; },
              [&](int e, double v) { SFW[((size_t)t * SR::NSF + e) * Sc + s] = v; });
     __syncwarp();
-    if (kk + SEQ_NST < Tn) ring.issue(Tn - 1 - (kk + SEQ_NST), st);
+    if (kk + SEQ_NST < nsteps) ring.issue(t1 - 1 - (kk + SEQ_NST), st);
   }
-  SR::init([&](int e) { return J0[(size_t)e * Sc + s]; }, Cb, [&](int e, double v) { SGBI[(size_t)e * Sc + s] = v; });
+  if (t0 == 0) SR::init([&](int e) { return J0[(size_t)e * Sc + s]; }, Cb, [&](int e, double v) { SGBI[(size_t)e * Sc + s] = v; });
+  else { LQGK_UNROLL for (int i = 0; i < R * R; ++i) carry[(size_t)i * Sc + s] = Cb[i]; }
 }
 
 // Time-parallel contraction.  grid = (Sc / 32, chunks), block = one warp owning a contiguous range of time steps of
@@ -419,7 +429,8 @@ __host__ __device__ constexpr int contrib_nst() {
 template <class DM, int PASS>
 __global__ void __launch_bounds__(32) k_cov_contrib(const double* cst, size_t Sc, int Tn, const double* L, const double* K,
                                                     const double* Cs, const double* SGB, const double* SGBI, const double* SFW,
-                                                    const float* sums, double* acc, double* Lbar, double* Kbar, double* KbarF) {
+                                                    const float* sums, double* acc, double* Lbar, double* Kbar, double* KbarF,
+                                                    int ta, int tb) {
   extern __shared__ __align__(128) double sm[];
   constexpr int B = DM::B, U = DM::U, Y = DM::Y, R = DM::R;
   using SR = CovSeqRev<DM>;
@@ -437,9 +448,9 @@ __global__ void __launch_bounds__(32) k_cov_contrib(const double* cst, size_t Sc
   double* lcp = sm + (size_t)PAR_NST * STAGE;
   double* lap = lcp + C::n * 32;
   uint64_t* bars = reinterpret_cast<uint64_t*>(lap + C::n * 32);
-  const int nq = gridDim.y, q = blockIdx.y;
-  const int per = (Tn + nq - 1) / nq;
-  const int t0 = min(Tn, q * per), t1 = min(Tn, t0 + per);
+  const int nq = gridDim.y, q = blockIdx.y;       // the launch covers [ta, tb), cut into nq time ranges
+  const int per = (tb - ta + nq - 1) / nq;
+  const int t0 = min(tb, ta + q * per), t1 = min(tb, t0 + per);
   if (t0 >= t1) return;
   Ring ring;
   ring.src[0] = {L + s0, DM::EL};
@@ -491,9 +502,10 @@ __global__ void __launch_bounds__(32) k_cov_contrib(const double* cst, size_t Sc
 }
 
 // Kalman-gain adjoint (sequential, t descending).  Ring inputs per step: P_t, Kbar_t.
+// [t0, t1) walked downwards; `carry` ([B*B][Sc]) hands the cotangent of P from one launch to the next (see k_cov_seq_rev).
 template <class DM>
 __global__ void __launch_bounds__(32) k_kf_rev(const double* cst, size_t Sc, int Tn, const double* Pkf, const double* Kbar,
-                                               const double* KbarF, double* acc) {
+                                               const double* KbarF, double* acc, int t0, int t1, double* carry) {
   extern __shared__ __align__(128) double sm[];
   constexpr int B = DM::B, Y = DM::Y;
   using C = KfC<DM>;
@@ -506,15 +518,17 @@ __global__ void __launch_bounds__(32) k_kf_rev(const double* cst, size_t Sc, int
   uint64_t* bars = reinterpret_cast<uint64_t*>(lap + C::n * 32);
   Ring ring{{{Pkf + s0, DM::EP}, {Kbar + s0, DM::EK}, {KbarF + s0, DM::EK}}, Sc, nullptr, 0, 0, 0, sm, bars, lane, ROWS, ROWS * 32, 0};
   ring.init();
-  for (int k = 0; k < SEQ_NST && k < Tn; ++k) ring.issue(Tn - 1 - k, k);
+  const int nsteps = t1 - t0;
+  for (int k = 0; k < SEQ_NST && k < nsteps; ++k) ring.issue(t1 - 1 - k, k);
   WView lc{lcp + lane, 32}, la{lap + lane, 32};
   load_consts<C>(WView{const_cast<double*>(cst) + s, Sc}, lc, C::NSEG);
   for (int e = 0; e < C::n; ++e) la(e) = 0.0;
   auto accf = [&](int e) -> double& { return la(e); };
   double Pnb[B * B];
-  LQGK_UNROLL for (int i = 0; i < B * B; ++i) Pnb[i] = 0.0;
+  if (t1 == Tn) { LQGK_UNROLL for (int i = 0; i < B * B; ++i) Pnb[i] = 0.0; }
+  else { LQGK_UNROLL for (int i = 0; i < B * B; ++i) Pnb[i] = carry[(size_t)i * Sc + s]; }
   auto sweep = [&](const auto& cv) {
-    for (int kk = 0; kk < Tn; ++kk) {
+    for (int kk = 0; kk < nsteps; ++kk) {
       const int st = kk % SEQ_NST;
       const double* stg = ring.wait(st);
       double P[B * B], Kb[B * Y];
@@ -524,7 +538,7 @@ __global__ void __launch_bounds__(32) k_kf_rev(const double* cst, size_t Sc, int
         LQGK_UNROLL for (int i = 0; i < B * Y; ++i) Kb[i] = kv(i) + kv2(i);
       }
       __syncwarp();
-      if (kk + SEQ_NST < Tn) ring.issue(Tn - 1 - (kk + SEQ_NST), st);
+      if (kk + SEQ_NST < nsteps) ring.issue(t1 - 1 - (kk + SEQ_NST), st);
       KfRev<DM>::step(cv, accf, P, Kb, Pnb);
     }
   };
@@ -535,7 +549,8 @@ __global__ void __launch_bounds__(32) k_kf_rev(const double* cst, size_t Sc, int
   } else {
     sweep(lc);
   }
-  KfRev<DM>::finish(accf, Pnb);
+  if (t0 == 0) KfRev<DM>::finish(accf, Pnb);
+  else { LQGK_UNROLL for (int i = 0; i < B * B; ++i) carry[(size_t)i * Sc + s] = Pnb[i]; }
   flush_acc_atomic<C>(acc + s, Sc, la, C::NSEG);
 }
 
@@ -797,7 +812,9 @@ __host__ __device__ constexpr bool rec_in_regs() { return DM::REC <= 48; }
 template <class DM, int RT>
 __global__ void __launch_bounds__(32 * TRIAL_WARPS, trial_min_ctas<DM>()) k_trial_fwd(const float* __restrict__ rec, const float* __restrict__ xc_all,
                                                                 size_t xc_sample_stride, int n_samples, int N, int Tn,
-                                                                double* __restrict__ ll_ws, float* __restrict__ hist) {
+                                                                double* __restrict__ ll_ws, float* __restrict__ hist, int ka, int kb) {
+  // [ka, kb): range of checkpoint segments (CK steps each) of this launch.  ka > 0 continues from checkpoint ka (needs `hist`)
+  // and adds its log-density terms to what the earlier launches left in ll_ws (pipelined launch sequence).
   constexpr int D = DM::D, R = DM::R, NSLOT = TRIAL_PF + 1, TB = trial_tb<DM>(), CK = trial_ck<DM>(RT), ROW = 32 * RT;
   constexpr int NP = RT / 2, NS = RT % 2, NPA = NP > 0 ? NP : 1;
   using XB = LaneBlock<RT, D>;
@@ -812,18 +829,19 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS, trial_min_ctas<DM>()) k_tria
   float* ring_base = reinterpret_cast<float*>(smraw);
   uint64_t* bar_base = reinterpret_cast<uint64_t*>(smraw + RING_BYTES);
   float* pf = reinterpret_cast<float*>(smraw + RING_BYTES + TRIAL_WARPS * TRIAL_NST * sizeof(uint64_t)) + (size_t)warp * NSLOT * D * ROW;
+  const int ta = ka * CK, tb = min(Tn, kb * CK), Tl = tb - ta;     // time range of this launch
   RecRing<DM, TB, TRIAL_NST> ring{ring_base + (size_t)warp * TRIAL_NST * TB * DM::REC, bar_base + warp * TRIAL_NST,
-                                  rec + (size_t)s * Tn * DM::REC, Tn, lane, 0};
+                                  rec + ((size_t)s * Tn + ta) * DM::REC, Tl, lane, 0};   // ring chunks relative to ta
   ring.init();
-  const int nchunk = (Tn + TB - 1) / TB;
+  const int nchunk = (Tl + TB - 1) / TB;
   const int nseg = (Tn + CK - 1) / CK;
   const size_t xstep = (size_t)NB * D * ROW, hstep = (size_t)NB * R * ROW;
   const int lp = 2 * lane, ls = 64 * NP + lane;                       // this lane's pair / single column inside a block
   for (int blk = 0; blk < NB; ++blk) {
-    const float* xlp = xc + (size_t)blk * D * ROW + lp;              // row 0 of this block; row t at + t * xstep
-    const float* xls = xc + (size_t)blk * D * ROW + ls;
-    float* hp = hist + ((size_t)s * nseg * NB + blk) * R * ROW + lp;   // checkpoint 0; advanced by hstep per stored checkpoint
-    float* hs = hist + ((size_t)s * nseg * NB + blk) * R * ROW + ls;
+    const float* xlp = xc + (size_t)blk * D * ROW + lp + (size_t)ta * xstep;   // row ta of this block; row t at + (t - ta) * xstep
+    const float* xls = xc + (size_t)blk * D * ROW + ls + (size_t)ta * xstep;
+    float* hp = hist + (((size_t)s * nseg + ka) * NB + blk) * R * ROW + lp;   // checkpoint ka; advanced by hstep per stored checkpoint
+    float* hs = hist + (((size_t)s * nseg + ka) * NB + blk) * R * ROW + ls;
     int ckc = 0;                     // steps until the next checkpoint
     // trials 2p, 2p+1 are packed into one f32x2 lane-pair state (Blackwell FFMA2); an odd last trial stays scalar
     f32x2 cP[NPA][R], x0P[NPA][D];
@@ -831,12 +849,16 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS, trial_min_ctas<DM>()) k_tria
     double ll[RT];
     LQGK_UNROLL for (int j = 0; j < RT; ++j) ll[j] = 0.0;
     XB::template load<true>(xlp, xls, x0P, x0S);
-    LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) LQGK_UNROLL for (int k = 0; k < R; ++k) cP[p2][k] = f32x2{0.f, 0.f};
-    LQGK_UNROLL for (int k = 0; k < R; ++k) cS[k] = 0.f;
-    // prologue: x_{1..PF} in flight (one commit group per step); xnp/xns walk one row per step, clamped at row Tn
+    if (ka == 0) {
+      LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) LQGK_UNROLL for (int k = 0; k < R; ++k) cP[p2][k] = f32x2{0.f, 0.f};
+      LQGK_UNROLL for (int k = 0; k < R; ++k) cS[k] = 0.f;
+    } else {
+      CB::template load<true>(hp, hs, cP, cS);   // c_{ta} as the previous launch stored it
+    }
+    // prologue: x_{ta+1..ta+PF} in flight (one commit group per step); xnp/xns walk one row per step, clamped at row Tn
     const float* xnp = xlp;
     const float* xns = xls;
-    int trow = 0;                    // row xnp/xns point at
+    int trow = ta;                   // row xnp/xns point at
     auto advance_row = [&]() { if (trow < Tn) { ++trow; xnp += xstep; xns += xstep; } };
     for (int p = 0; p < TRIAL_PF; ++p) {
       advance_row();
@@ -848,7 +870,7 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS, trial_min_ctas<DM>()) k_tria
     for (int k = 0; k < nchunk; ++k) {
       const int st = k % TRIAL_NST;
       const float* chunk = ring.wait(st);
-      const int t0 = k * TB, nst = min(TB, Tn - t0);
+      const int t0 = k * TB, nst = min(TB, Tl - t0);
       f32x2 partP[NPA];
       float partS = 0.f;
       LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) partP[p2] = f32x2{0.f, 0.f};
@@ -901,9 +923,13 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS, trial_min_ctas<DM>()) k_tria
       if (k + TRIAL_NST < nchunk) ring.issue(k + TRIAL_NST, st);
     }
     cp_async_wait<0>();
+    if (hist != nullptr && kb < nseg) CB::store_streaming(hp, hs, cP, cS);   // checkpoint kb: where the next launch continues from
     LQGK_UNROLL for (int j = 0; j < RT; ++j) {
       const int i = blk * ROW + trial_col<RT>(lane, j);
-      if (i < N) ll_ws[(size_t)s * N + i] = ll[j];
+      if (i < N) {
+        if (ka == 0) ll_ws[(size_t)s * N + i] = ll[j];
+        else ll_ws[(size_t)s * N + i] += ll[j];
+      }
     }
   }
 }
@@ -953,7 +979,9 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS_REV) k_trial_rev(
     const float* __restrict__ rec, const float* __restrict__ xc_all,
                                                                 size_t xc_sample_stride, const float* __restrict__ hist,
                                                                 const float* __restrict__ w, int n_samples, int N, int Tn,
-                                                                float* __restrict__ sums) {
+                                                                float* __restrict__ sums, int ka, int kb, float* __restrict__ cbcar) {
+  // [ka, kb): range of checkpoint segments of this launch, walked downwards.  kb < nseg starts from the cotangent an earlier
+  // launch left in cbcar ([s][NB][R][ROW]); ka > 0 leaves its own there (pipelined launch sequence).
   constexpr int D = DM::D, R = DM::R;
   constexpr int CK = trial_ck<DM>(RT), ROW = 32 * RT, SLOT = R * ROW;
   constexpr int NFULL = DM::NSUM / 32, REM = DM::NSUM % 32, VREM = pow2_ceil(REM);
@@ -993,21 +1021,27 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS_REV) k_trial_rev(
     // carried state sits again where the next walk expects it (cb[1], x_{t+1} in x[0]).
     f32x2 cbP[2][NPA][R], xP[2][NPA][D], wP[NPA];
     float cbS[2][R], xS[2][D], wS = wt[RT - 1];
-    XB::template load<true>(xlp + (size_t)Tn * xstep, xls + (size_t)Tn * xstep, xP[0], xS[0]);
-    LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) {
-      LQGK_UNROLL for (int k = 0; k < R; ++k) cbP[1][p2][k] = f32x2{0.f, 0.f};
-      wP[p2] = f32x2{wt[2 * p2], wt[2 * p2 + 1]};
+    const int tend = min(Tn, kb * CK);             // one past the last step of this launch
+    XB::template load<true>(xlp + (size_t)tend * xstep, xls + (size_t)tend * xstep, xP[0], xS[0]);
+    LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) wP[p2] = f32x2{wt[2 * p2], wt[2 * p2 + 1]};
+    float* carp = cbcar + ((size_t)s * NB + blk) * R * ROW + lp;
+    float* cars = cbcar + ((size_t)s * NB + blk) * R * ROW + ls;
+    if (kb == nseg) {
+      LQGK_UNROLL for (int p2 = 0; p2 < NP; ++p2) LQGK_UNROLL for (int k = 0; k < R; ++k) cbP[1][p2][k] = f32x2{0.f, 0.f};
+      LQGK_UNROLL for (int k = 0; k < R; ++k) cbS[1][k] = 0.f;
+    } else {
+      CB::template load<true>(carp, cars, cbP[1], cbS[1]);
     }
-    LQGK_UNROLL for (int k = 0; k < R; ++k) cbS[1][k] = 0.f;
-    const float* hkp = hist + (((size_t)s * nseg + (nseg - 1)) * NB + blk) * R * ROW + lp;   // checkpoint of the segment to fetch next
-    const float* hks = hist + (((size_t)s * nseg + (nseg - 1)) * NB + blk) * R * ROW + ls;
+    const float* hkp = hist + (((size_t)s * nseg + (kb - 1)) * NB + blk) * R * ROW + lp;   // checkpoint of the segment to fetch next
+    const float* hks = hist + (((size_t)s * nseg + (kb - 1)) * NB + blk) * R * ROW + ls;
     float* slot0 = seg;                            // buffer slot of the current segment's first step
     CB::copy_async(slot0 + lp, slot0 + ls, hkp, hks);
-    ring.issue(nseg - 1, 0);
-    if (nseg > 1) ring.issue(nseg - 2, 1);
-    float* out = sums + ((size_t)s * Tn + (Tn - 1)) * DM::SUMP;
-    for (int kk = 0; kk < nseg; ++kk) {
-      const int k = nseg - 1 - kk, st = kk & 1;
+    ring.issue(kb - 1, 0);
+    if (kb - ka > 1) ring.issue(kb - 2, 1);
+    float* out = sums + ((size_t)s * Tn + (tend - 1)) * DM::SUMP;
+    const int nloc = kb - ka;
+    for (int kk = 0; kk < nloc; ++kk) {
+      const int k = kb - 1 - kk, st = kk & 1;
       const int t0 = k * CK, nst = min(CK, Tn - t0);
       const float* chunk = ring.wait(st);
       cp_async_wait<0>();                          // checkpoint k is in slot0 (lane-private data: no warp sync needed)
@@ -1085,7 +1119,7 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS_REV) k_trial_rev(
           else asm volatile("" : "+l"(xqs) : "f"(eS[0]));
           XB::template load<true>(xqp, xqs, xP[Q], xS[Q]);
         }
-        if (top && k > 0) {
+        if (top && k > ka) {
           // the slot of the segment's last step has been consumed (its values are operands of the arithmetic above):
           // the checkpoint of the next segment to process lands there while this one is walked
           hkp -= hstep;
@@ -1159,8 +1193,9 @@ __global__ void __launch_bounds__(32 * TRIAL_WARPS_REV) k_trial_rev(
         }
       }
       __syncwarp();
-      if (kk + 2 < nseg) ring.issue(nseg - 1 - (kk + 2), st);
+      if (kk + 2 < nloc) ring.issue(kb - 1 - (kk + 2), st);
     }
+    if (ka > 0) CB::store(carp, cars, cbP[1], cbS[1]);   // cotangent of c_{ka CK} for the launch that continues below
   }
 }
 

@@ -86,7 +86,11 @@ struct StreamPool {
     while ((int)streams.size() < n) {
       cudaStream_t st;
       cudaEvent_t ev;
-      if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return LQGK_E_CUDA;
+      // highest priority: the internal streams carry the latency-bound per-sample sweeps of the pipelined launch sequence, whose
+      // small CTAs should get the first free SM resources when they compete with the (throughput-bound) per-trial kernels
+      int prio_lo = 0, prio_hi = 0;
+      cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+      if (cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return LQGK_E_CUDA;
       if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return LQGK_E_CUDA;
       streams.push_back(st);
       joins.push_back(ev);
@@ -134,6 +138,9 @@ struct ProfScope {
 
 constexpr size_t ALIGN = 256;
 extern thread_local int g_warp_cov_max_samples;   // calls with at most this many samples use the warp-per-sample covariance kernels
+// Pipelined launch sequence (VJP): chunks of at most g_pipe_max_samples samples cut every sequential sweep into
+// g_pipe_segments time segments and run the sweeps of one direction as a software pipeline over internal streams.
+extern thread_local int g_pipe_max_samples, g_pipe_segments;
 inline size_t up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 inline bool spec_time_varying(const LqgkSpec& s, bool actor) {
@@ -151,7 +158,8 @@ constexpr bool is_big() { return DM::N > 12; }
 struct Plan {
   size_t Sc = 0, bytes = 0;
   size_t cst = 0, acc = 0, L = 0, K = 0, l = 0, H = 0, Sric = 0, Pkf = 0, Cs = 0, Lbar = 0, Kbar = 0, rec = 0, ll = 0,
-         sums = 0, hist = 0, w = 0, FU = 0, JS = 0, J0 = 0, SGB = 0, SGBI = 0, SFW = 0, KbarF = 0, scr = 0, xc = 0;
+         sums = 0, hist = 0, w = 0, FU = 0, JS = 0, J0 = 0, SGB = 0, SGBI = 0, SFW = 0, KbarF = 0, scr = 0, xc = 0,
+         carC = 0, carP = 0, carcb = 0;
 };
 
 template <class DM>
@@ -188,6 +196,10 @@ Plan make_plan(const LqgkDims& d, int mode, bool tv, size_t Sc) {
     {
       const TrialGeom tg = trial_geom<DM>((int)N, (int)T);
       p.hist = take(sizeof(float) * Sc * tg.nseg * tg.NB * DM::R * tg.ROW);   // checkpoints of the carried state
+      // carries between the time segments of the pipelined launch sequence
+      p.carcb = take(sizeof(float) * Sc * tg.NB * DM::R * tg.ROW);
+      p.carC = take(sizeof(double) * DM::R * DM::R * Sc);
+      p.carP = take(sizeof(double) * DM::B * DM::B * Sc);
     }
     p.w = take(sizeof(float) * Sc * N);
     using SR = CovSeqRev<DM>;
@@ -241,24 +253,29 @@ inline int launch_repack_obs(cudaStream_t st, const LqgkDims& d, int row, const 
   LQGK_LAUNCH_CHECK();
   return LQGK_OK;
 }
+// ka, kb: range of checkpoint segments of this launch (kb < 0: all of them)
 template <class DM, int RT>
-int launch_trial_fwd(cudaStream_t st, const float* rec, const float* xc, size_t xcs, int n, int N, int T, double* ll, float* hist) {
+int launch_trial_fwd(cudaStream_t st, const float* rec, const float* xc, size_t xcs, int n, int N, int T, double* ll, float* hist,
+                     int ka = 0, int kb = -1) {
   size_t smem = trial_smem_bytes<DM, RT, false>();
   int rc = set_smem<DM>((const void*)k_trial_fwd<DM, RT>, smem);
   if (rc) return rc;
+  if (kb < 0) kb = (T + trial_ck<DM>(RT) - 1) / trial_ck<DM>(RT);
   ProfScope ps_(PK_TRIAL_FWD, st);
-  k_trial_fwd<DM, RT><<<(n + TRIAL_WARPS - 1) / TRIAL_WARPS, 32 * TRIAL_WARPS, smem, st>>>(rec, xc, xcs, n, N, T, ll, hist);
+  k_trial_fwd<DM, RT><<<(n + TRIAL_WARPS - 1) / TRIAL_WARPS, 32 * TRIAL_WARPS, smem, st>>>(rec, xc, xcs, n, N, T, ll, hist, ka, kb);
   LQGK_LAUNCH_CHECK();
   return LQGK_OK;
 }
 template <class DM, int RT>
 int launch_trial_rev(cudaStream_t st, const float* rec, const float* xc, size_t xcs, const float* hist, const float* w, int n, int N, int T,
-                     float* sums) {
+                     float* sums, float* cbcar, int ka = 0, int kb = -1) {
   size_t smem = trial_smem_bytes<DM, RT, true>();
   int rc = set_smem<DM>((const void*)k_trial_rev<DM, RT>, smem);
   if (rc) return rc;
+  if (kb < 0) kb = (T + trial_ck<DM>(RT) - 1) / trial_ck<DM>(RT);
   ProfScope ps_(PK_TRIAL_REV, st);
-  k_trial_rev<DM, RT><<<(n + TRIAL_WARPS_REV - 1) / TRIAL_WARPS_REV, 32 * TRIAL_WARPS_REV, smem, st>>>(rec, xc, xcs, hist, w, n, N, T, sums);
+  k_trial_rev<DM, RT><<<(n + TRIAL_WARPS_REV - 1) / TRIAL_WARPS_REV, 32 * TRIAL_WARPS_REV, smem, st>>>(rec, xc, xcs, hist, w, n, N, T, sums, ka,
+                                                                                                     kb, cbcar);
   LQGK_LAUNCH_CHECK();
   return LQGK_OK;
 }
@@ -308,7 +325,7 @@ int run(const Call& c) {
   cudaStream_t st = c.stream;
   const int auxm = c.mode == LQGK_MODE_VJP ? g_aux_streams : 0;
   const bool aux = auxm != 0;
-  const int nstreams = (ns > 1 ? ns : 0) + (aux ? 2 * ns : 0);
+  const int nstreams = (ns > 1 ? ns : 0) + (aux ? 3 * ns : 0);
   if (nstreams > 0) {
     if (int rcp = g_pool.acquire(nstreams, c.stream)) return rcp;
   }
@@ -374,8 +391,9 @@ int run(const Call& c) {
       base = (char*)c.ws + (size_t)(chunk_idx % ns) * slice_bytes;
     }
     // auxiliary streams of this slice: independent kernels of one chunk run concurrently (they are latency-bound)
-    cudaStream_t x1 = aux ? g_pool.streams[aux0 + 2 * (chunk_idx % ns)] : st;
-    cudaStream_t x2 = aux ? g_pool.streams[aux0 + 2 * (chunk_idx % ns) + 1] : st;
+    cudaStream_t x1 = aux ? g_pool.streams[aux0 + 3 * (chunk_idx % ns)] : st;
+    cudaStream_t x2 = aux ? g_pool.streams[aux0 + 3 * (chunk_idx % ns) + 1] : st;
+    cudaStream_t x3 = aux ? g_pool.streams[aux0 + 3 * (chunk_idx % ns) + 2] : st;
     cudaStream_t a1 = (auxm & 1) ? x1 : st, a2 = st;
     {
       dim3 grid((npad + 127) / 128, tv ? Tn : 1);
@@ -404,7 +422,7 @@ int run(const Call& c) {
       if (c.K_out) {
         size_t smem = sizeof(double) * 32 * KfC<DM>::n;
         ProfScope ps_(PK_KF_FWD, st);
-        k_kf_fwd<DM><<<nblk, 32, smem, st>>>(D(p.cst), Sc, tstride, Tn, D(p.K), 0, nullptr);
+        k_kf_fwd<DM><<<nblk, 32, smem, st>>>(D(p.cst), Sc, tstride, Tn, D(p.K), 0, nullptr, 0, Tn);
         LQGK_LAUNCH_CHECK();
         size_t total = (size_t)n * Tn * DM::EK;
         k_store_rows<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(D(p.K), Sc, n, Tn, DM::EK, (T*)c.K_out + s0 * Tn * DM::EK);
@@ -414,6 +432,171 @@ int run(const Call& c) {
     }
     const bool vjp = c.mode == LQGK_MODE_VJP;
     int rc;
+    const TrialGeom tgm = trial_geom<DM>(N, Tn);
+    const int G = (vjp && aux && !tv && n <= g_pipe_max_samples) ? std::max(1, std::min(g_pipe_segments, tgm.nseg)) : 1;
+    if (G > 1) {
+      // ---------------------------------------------------------------------------------------- pipelined launch sequence
+      // Few samples: every sweep over time is latency-bound (T dependent steps, ~1-2.5 ms each whatever the sample count) and the
+      // GPU idles behind the chain of nine sweeps.  The sweeps of one direction are therefore cut into G time segments and run as
+      // a software pipeline over internal streams: segment g of a consumer starts as soon as segment g of its producer is done.
+      //   t up  : kf_fwd (x1) -> cov_fwd (x2) -> trial_fwd (st)        [after lqr_fwd, which runs t down and feeds cov_fwd]
+      //   t down: trial_rev (st) -> cov_seq_rev (x1) -> contraction (x2) -> kf_rev (x3);  lqr_rev (t up) follows on x2
+      // Carries between segments: P_t, C_t and the checkpoints of c_t are stored per step anyway (adjoint linearisation points);
+      // the adjoint carries (cb, Cb, Pnb) go through three small buffers.
+      const bool warp_cov_p = d.S <= g_warp_cov_max_samples;
+      const int wblk_p = (npad + BW_WARPS - 1) / BW_WARPS;
+      const int RTp = tgm.RT;
+      std::vector<int> kb(G + 1), tb(G + 1);
+      for (int g = 0; g <= G; ++g) { kb[g] = (int)((long long)g * tgm.nseg / G); tb[g] = std::min(Tn, kb[g] * tgm.CK); }
+      dep(st, x1);                                 // pack done -> kf_fwd on x1 beside lqr_fwd on st
+      {
+        size_t smem = sizeof(double) * 32 * LqrC<DM>::n;
+        ProfScope ps_(PK_LQR_FWD, st);
+        k_lqr_fwd<DM, false><<<nblk, 32, smem, st>>>(D(p.cst), Sc, tstride, Tn, c.eps, D(p.L), 1, D(p.Sric), nullptr, nullptr);
+        LQGK_LAUNCH_CHECK();
+      }
+      dep(st, x2);                                 // L complete -> covariance pass
+      size_t xcs = 0;
+      if ((rc = launch_repack_obs(st, d, 32 * RTp, c.x_tm, (int)s0, n, F(p.xc), &xcs))) return rc;
+      const size_t sm_kf = sizeof(double) * 32 * KfC<DM>::n;
+      const size_t sm_cov = warp_cov_p ? BigW<DM>::smem_fwd() : smem_cov_fwd<DM>();
+      if (warp_cov_p) { if ((rc = set_smem<DM>((const void*)kw_cov_fwd<DM, true>, sm_cov))) return rc; }
+      else { if ((rc = set_smem<DM>((const void*)k_cov_fwd<DM>, sm_cov))) return rc; }
+      for (int g = 0; g < G; ++g) {
+        {
+          ProfScope ps_(PK_KF_FWD, x1);
+          k_kf_fwd<DM><<<nblk, 32, sm_kf, x1>>>(D(p.cst), Sc, tstride, Tn, D(p.K), 1, D(p.Pkf), tb[g], tb[g + 1]);
+          LQGK_LAUNCH_CHECK();
+        }
+        dep(x1, x2);
+        {
+          ProfScope ps_(PK_COV_FWD, x2);
+          if (warp_cov_p)
+            kw_cov_fwd<DM, true><<<wblk_p, 32 * BW_WARPS, sm_cov, x2>>>(D(p.cst), Sc, npad, Tn, D(p.L), D(p.K), 1, D(p.Cs), D(p.FU), D(p.JS), D(p.J0),
+                                                                        F(p.rec), tb[g], tb[g + 1]);
+          else
+            k_cov_fwd<DM><<<nblk, 32, sm_cov, x2>>>(D(p.cst), Sc, tstride, Tn, D(p.L), D(p.K), 1, D(p.Cs), D(p.FU), D(p.JS), D(p.J0), F(p.rec),
+                                                    tb[g], tb[g + 1]);
+          LQGK_LAUNCH_CHECK();
+        }
+        dep(x2, st);
+        rc = LQGK_E_UNSUPPORTED;
+        static_for<1, trial_rt_max<DM>() + 1>([&](auto RTC) {
+          if (RTp == decltype(RTC)::value)
+            rc = launch_trial_fwd<DM, decltype(RTC)::value>(st, F(p.rec), F(p.xc), xcs, n, N, Tn, D(p.ll), F(p.hist), kb[g], kb[g + 1]);
+        });
+        if (rc) return rc;
+      }
+      {
+        size_t total = (size_t)n * N;
+        ProfScope ps_(PK_MISC, st);
+        k_store_ll<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(D(p.ll), total, (T*)c.ll_out + s0 * N);
+        LQGK_LAUNCH_CHECK();
+        size_t totalp = (size_t)npad * N;
+        const T* lb = c.ll_bar ? (const T*)c.ll_bar + s0 * N : nullptr;
+        k_load_w<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(lb, total, F(p.w));
+        LQGK_LAUNCH_CHECK();
+        if (totalp > total) {
+          k_load_w<T><<<(unsigned)((totalp - total + 255) / 256), 256, 0, st>>>(nullptr, totalp - total, F(p.w) + total);
+          LQGK_LAUNCH_CHECK();
+        }
+      }
+      if (cudaMemsetAsync(D(p.acc), 0, sizeof(double) * cl.total * Sc, st) != cudaSuccess) return LQGK_E_CUDA;
+      if (npad > n) {
+        if (cudaMemsetAsync(F(p.sums) + (size_t)n * Tn * DM::SUMP, 0, sizeof(float) * (size_t)(npad - n) * Tn * DM::SUMP, st) != cudaSuccess)
+          return LQGK_E_CUDA;
+      }
+      const size_t sm_seq = warp_cov_p ? BigW<DM>::smem_seq() : smem_cov_seq_rev<DM>();
+      const size_t sm_con = warp_cov_p ? BigW<DM>::smem_con() : 0;
+      if (warp_cov_p) {
+        if ((rc = set_smem<DM>((const void*)kw_cov_seq_rev<DM>, sm_seq))) return rc;
+        if ((rc = set_smem<DM>((const void*)kw_cov_contrib<DM, true>, sm_con))) return rc;
+      } else {
+        if ((rc = set_smem<DM>((const void*)k_cov_seq_rev<DM>, sm_seq))) return rc;
+      }
+      const size_t sm_kfr = smem_kf_rev<DM>();
+      if ((rc = set_smem<DM>((const void*)k_kf_rev<DM>, sm_kfr))) return rc;
+      for (int g = G - 1; g >= 0; --g) {
+        rc = LQGK_E_UNSUPPORTED;
+        static_for<1, trial_rt_max<DM>() + 1>([&](auto RTC) {
+          if (RTp == decltype(RTC)::value)
+            rc = launch_trial_rev<DM, decltype(RTC)::value>(st, F(p.rec), F(p.xc), xcs, F(p.hist), F(p.w), n, N, Tn, F(p.sums), F(p.carcb), kb[g],
+                                                            kb[g + 1]);
+        });
+        if (rc) return rc;
+        dep(st, x1);
+        {
+          ProfScope ps_(PK_COV_REV, x1);
+          if (warp_cov_p)
+            kw_cov_seq_rev<DM><<<wblk_p, 32 * BW_WARPS, sm_seq, x1>>>(npad, Tn, N, F(p.w), D(p.FU), D(p.JS), D(p.J0), F(p.sums), D(p.SGB), D(p.SGBI),
+                                                                     D(p.SFW), tb[g], tb[g + 1], D(p.carC));
+          else
+            k_cov_seq_rev<DM><<<nblk, 32, sm_seq, x1>>>(Sc, Tn, N, F(p.w), D(p.FU), D(p.JS), D(p.J0), F(p.sums), D(p.SGB), D(p.SGBI), D(p.SFW), tb[g],
+                                                        tb[g + 1], D(p.carC));
+          LQGK_LAUNCH_CHECK();
+        }
+        dep(x1, x2);
+        {
+          const int len = tb[g + 1] - tb[g];
+          ProfScope ps_(PK_COV_CONTRIB, x2);
+          if (warp_cov_p) {
+            int chunks = std::max(1, std::min((len + 3) / 4, (sm_count() * 12 + npad - 1) / npad));   // (segments run one after the other)
+            kw_cov_contrib<DM, true><<<dim3(wblk_p, chunks), 32 * BW_WARPS, sm_con, x2>>>(D(p.cst), Sc, npad, Tn, D(p.L), D(p.K), D(p.Cs), D(p.SGB),
+                                                                                       D(p.SGBI), D(p.SFW), F(p.sums), D(p.acc), D(p.Lbar),
+                                                                                       D(p.Kbar), D(p.KbarF), tb[g], tb[g + 1]);
+            LQGK_LAUNCH_CHECK();
+          } else {
+            const int cwarps = g_contrib_warps > 0 ? g_contrib_warps : sm_count() * 30;
+            int chunks = std::max(1, std::min((len + 7) / 8, (cwarps + nblk - 1) / nblk));
+            dim3 grid(nblk, chunks);
+            if constexpr (contrib_merged<DM>()) {
+              size_t smem = smem_cov_contrib<DM, 2>();
+              if ((rc = set_smem<DM>((const void*)k_cov_contrib<DM, 2>, smem))) return rc;
+              k_cov_contrib<DM, 2><<<grid, 32, smem, x2>>>(D(p.cst), Sc, Tn, D(p.L), D(p.K), D(p.Cs), D(p.SGB), D(p.SGBI), D(p.SFW), F(p.sums),
+                                                          D(p.acc), D(p.Lbar), D(p.Kbar), D(p.KbarF), tb[g], tb[g + 1]);
+              LQGK_LAUNCH_CHECK();
+            } else {
+              size_t smem0 = smem_cov_contrib<DM, 0>(), smem1 = smem_cov_contrib<DM, 1>();
+              if ((rc = set_smem<DM>((const void*)k_cov_contrib<DM, 0>, smem0))) return rc;
+              if ((rc = set_smem<DM>((const void*)k_cov_contrib<DM, 1>, smem1))) return rc;
+              k_cov_contrib<DM, 0><<<grid, 32, smem0, x2>>>(D(p.cst), Sc, Tn, D(p.L), D(p.K), D(p.Cs), D(p.SGB), D(p.SGBI), D(p.SFW), F(p.sums),
+                                                           D(p.acc), D(p.Lbar), D(p.Kbar), D(p.KbarF), tb[g], tb[g + 1]);
+              LQGK_LAUNCH_CHECK();
+              k_cov_contrib<DM, 1><<<grid, 32, smem1, x2>>>(D(p.cst), Sc, Tn, D(p.L), D(p.K), D(p.Cs), D(p.SGB), D(p.SGBI), D(p.SFW), F(p.sums),
+                                                           D(p.acc), D(p.Lbar), D(p.Kbar), D(p.KbarF), tb[g], tb[g + 1]);
+              LQGK_LAUNCH_CHECK();
+            }
+          }
+        }
+        dep(x2, x3);
+        {
+          ProfScope ps_(PK_KF_REV, x3);
+          k_kf_rev<DM><<<nblk, 32, sm_kfr, x3>>>(D(p.cst), Sc, Tn, D(p.Pkf), D(p.Kbar), D(p.KbarF), D(p.acc), tb[g], tb[g + 1], D(p.carP));
+          LQGK_LAUNCH_CHECK();
+        }
+      }
+      {
+        size_t smem = smem_lqr_rev<DM>();
+        if ((rc = set_smem<DM>((const void*)k_lqr_rev<DM>, smem))) return rc;
+        ProfScope ps_(PK_LQR_REV, x2);            // after every contraction segment (Lbar complete), in order on x2
+        k_lqr_rev<DM><<<nblk, 32, smem, x2>>>(D(p.cst), Sc, Tn, c.eps, D(p.L), D(p.Sric), D(p.Lbar), D(p.acc));
+        LQGK_LAUNCH_CHECK();
+      }
+      dep(x2, st);
+      dep(x3, st);
+      {
+        UnpackArgs<T> ua{};
+        ua.act = *c.act; ua.dyn = *c.dyn; ua.sigma0 = pa.sigma0;
+        if (c.gact) ua.gact = *c.gact;
+        if (c.gdyn) ua.gdyn = *c.gdyn;
+        if (c.gsig0) ua.gsigma0 = *c.gsig0;
+        ua.x = DM::X; ua.b = DM::B; ua.u = DM::U; ua.y = DM::Y;
+        ProfScope ps_(PK_UNPACK, st);
+        k_unpack<T><<<(n + 63) / 64, 64, 0, st>>>(ua, (int)s0, n, D(p.acc), D(p.cst), Sc);
+        LQGK_LAUNCH_CHECK();
+      }
+      continue;
+    }
     dep(st, a1);                                   // pack done -> kf_fwd (a1) may run beside lqr_fwd (st)
     {
       size_t smem = sizeof(double) * 32 * LqrC<DM>::n;
@@ -424,7 +607,7 @@ int run(const Call& c) {
     {
       size_t smem = sizeof(double) * 32 * KfC<DM>::n;
       ProfScope ps_(PK_KF_FWD, a1);
-      k_kf_fwd<DM><<<nblk, 32, smem, a1>>>(D(p.cst), Sc, tstride, Tn, D(p.K), vjp, vjp ? D(p.Pkf) : nullptr);
+      k_kf_fwd<DM><<<nblk, 32, smem, a1>>>(D(p.cst), Sc, tstride, Tn, D(p.K), vjp, vjp ? D(p.Pkf) : nullptr, 0, Tn);
       LQGK_LAUNCH_CHECK();
     }
     dep(a1, st);
@@ -465,7 +648,7 @@ int run(const Call& c) {
       if ((rc = set_smem<DM>((const void*)k_cov_fwd<DM>, smem))) return rc;
       ProfScope ps_(PK_COV_FWD, st);
       k_cov_fwd<DM><<<nblk, 32, smem, st>>>(D(p.cst), Sc, tstride, Tn, D(p.L), D(p.K), vjp, vjp ? D(p.Cs) : nullptr, vjp ? D(p.FU) : nullptr,
-                                            vjp ? D(p.JS) : nullptr, vjp ? D(p.J0) : nullptr, F(p.rec));
+                                            vjp ? D(p.JS) : nullptr, vjp ? D(p.J0) : nullptr, F(p.rec), 0, Tn);
       LQGK_LAUNCH_CHECK();
     }
     const int RT = std::min((N + 31) / 32, trial_rt_max<DM>());
@@ -498,7 +681,7 @@ int run(const Call& c) {
     rc = LQGK_E_UNSUPPORTED;
     static_for<1, trial_rt_max<DM>() + 1>([&](auto RTC) {
       if (RT == decltype(RTC)::value)
-        rc = launch_trial_rev<DM, decltype(RTC)::value>(st, F(p.rec), F(p.xc), xcs, hist, F(p.w), n, N, Tn, F(p.sums));
+        rc = launch_trial_rev<DM, decltype(RTC)::value>(st, F(p.rec), F(p.xc), xcs, hist, F(p.w), n, N, Tn, F(p.sums), F(p.carcb));
     });
     if (rc) return rc;
     if (cudaMemsetAsync(D(p.acc), 0, sizeof(double) * cl.total * Sc, st) != cudaSuccess) return LQGK_E_CUDA;
@@ -529,7 +712,8 @@ int run(const Call& c) {
       size_t smem = smem_cov_seq_rev<DM>();
       if ((rc = set_smem<DM>((const void*)k_cov_seq_rev<DM>, smem))) return rc;
       ProfScope ps_(PK_COV_REV, st);
-      k_cov_seq_rev<DM><<<nblk, 32, smem, st>>>(Sc, Tn, N, F(p.w), D(p.FU), D(p.JS), D(p.J0), F(p.sums), D(p.SGB), D(p.SGBI), D(p.SFW));
+      k_cov_seq_rev<DM><<<nblk, 32, smem, st>>>(Sc, Tn, N, F(p.w), D(p.FU), D(p.JS), D(p.J0), F(p.sums), D(p.SGB), D(p.SGBI), D(p.SFW), 0, Tn,
+                                                D(p.carC));
       LQGK_LAUNCH_CHECK();
     }
     {
@@ -542,7 +726,7 @@ int run(const Call& c) {
         if ((rc = set_smem<DM>((const void*)k_cov_contrib<DM, 2>, smem))) return rc;
         ProfScope ps_(PK_COV_CONTRIB, st);
         k_cov_contrib<DM, 2><<<grid, 32, smem, st>>>(D(p.cst), Sc, Tn, D(p.L), D(p.K), D(p.Cs), D(p.SGB), D(p.SGBI), D(p.SFW), F(p.sums),
-                                                    D(p.acc), D(p.Lbar), D(p.Kbar), D(p.KbarF));
+                                                    D(p.acc), D(p.Lbar), D(p.Kbar), D(p.KbarF), 0, Tn);
         LQGK_LAUNCH_CHECK();
       } else {
         size_t smem0 = smem_cov_contrib<DM, 0>(), smem1 = smem_cov_contrib<DM, 1>();
@@ -553,13 +737,13 @@ int run(const Call& c) {
         {
           ProfScope ps_(PK_COV_CONTRIB, st);
           k_cov_contrib<DM, 0><<<grid, 32, smem0, st>>>(D(p.cst), Sc, Tn, D(p.L), D(p.K), D(p.Cs), D(p.SGB), D(p.SGBI), D(p.SFW),
-                                                       F(p.sums), D(p.acc), D(p.Lbar), D(p.Kbar), D(p.KbarF));
+                                                       F(p.sums), D(p.acc), D(p.Lbar), D(p.Kbar), D(p.KbarF), 0, Tn);
           LQGK_LAUNCH_CHECK();
         }
         {
           ProfScope ps_(PK_COV_CONTRIB, a1);
           k_cov_contrib<DM, 1><<<grid, 32, smem1, a1>>>(D(p.cst), Sc, Tn, D(p.L), D(p.K), D(p.Cs), D(p.SGB), D(p.SGBI), D(p.SFW),
-                                                       F(p.sums), D(p.acc), D(p.Lbar), D(p.Kbar), D(p.KbarF));
+                                                       F(p.sums), D(p.acc), D(p.Lbar), D(p.Kbar), D(p.KbarF), 0, Tn);
           LQGK_LAUNCH_CHECK();
         }
       }
@@ -591,7 +775,7 @@ int run(const Call& c) {
       size_t smem = smem_kf_rev<DM>();
       if ((rc = set_smem<DM>((const void*)k_kf_rev<DM>, smem))) return rc;
       ProfScope ps_(PK_KF_REV, st);
-      k_kf_rev<DM><<<nblk, 32, smem, st>>>(D(p.cst), Sc, Tn, D(p.Pkf), D(p.Kbar), D(p.KbarF), D(p.acc));
+      k_kf_rev<DM><<<nblk, 32, smem, st>>>(D(p.cst), Sc, Tn, D(p.Pkf), D(p.Kbar), D(p.KbarF), D(p.acc), 0, Tn, D(p.carP));
       LQGK_LAUNCH_CHECK();
     }
     dep(a1, st);

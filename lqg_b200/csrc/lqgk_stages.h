@@ -98,21 +98,26 @@ LQGK_HD void lqr_fwd_body(const GCst& g, WView lc, int T, double eps, WView Lw, 
 }
 
 // ---------------------------------------------------------------------------------------------- KF fwd
+// [t0, t1): time range of this call (t1 < 0: up to T).  A sweep that starts at t0 > 0 continues from the P_{t0} an earlier
+// call saved (save_P must have been on): that is how the pipelined launch sequence cuts the sweep into segments.
 template <class DM>
-LQGK_HD void kf_fwd_body(const GCst& g, WView lc, int T, WView Kw, bool save_P, WView Pw) {
+LQGK_HD void kf_fwd_body(const GCst& g, WView lc, int T, WView Kw, bool save_P, WView Pw, int t0 = 0, int t1 = -1) {
   constexpr int B = DM::B, Y = DM::Y;
   using C = KfC<DM>;
-  load_consts<C>(g.at(0), lc, C::NSEG);
+  if (t1 < 0) t1 = T;
+  load_consts<C>(g.at(g.tstride ? t0 : 0), lc, C::NSEG);
   double P[B * B];
-  load_sym<B>(lc, C::Sig0, P);
+  if (t0 == 0) load_sym<B>(lc, C::Sig0, P);
+  else load_sym_ws<B>(Pw, (size_t)t0 * DM::EP, P);
   auto sweep = [&](const auto& cv, bool reload) {
-    for (int t = 0; t < T; ++t) {
-      if (reload && t != 0) load_consts<C>(g.at(t), lc, C::NSEG);
+    for (int t = t0; t < t1; ++t) {
+      if (reload && t != t0) load_consts<C>(g.at(t), lc, C::NSEG);
       if (save_P) store_sym<B>(Pw, (size_t)t * DM::EP, P);
       double K[B * Y];
       KfFwd<DM>::step(cv, P, K);
       LQGK_UNROLL64 for (int i = 0; i < B * Y; ++i) Kw((size_t)t * DM::EK + i) = K[i];
     }
+    if (save_P && t1 < T) store_sym<B>(Pw, (size_t)t1 * DM::EP, P);   // where the next time segment continues from
   };
   bool done = false;
   if constexpr (C::n <= LQGK_REG_CONSTS_MAX) {

@@ -114,3 +114,33 @@ def test_config_c2_horizon(lib, dev):
     """BASELINE config 2 shape: SubjectiveActor 2-D, T=1200, 20 trials, 6 conditions (sigma_target varies)."""
     case = H.Case("subjective2", S=6, T=1200, N=20, seed=5)
     H.check_vjp(lib, dev, case, torch.float32)
+
+
+@pytest.mark.parametrize("name,d,N,T,reps", [("subjective", 2, 33, 205, 1), ("subjective", 2, 33, 205, 400), ("subjective2", 4, 40, 131, 1),
+                                             ("bounded", 2, 301, 97, 200), ("delay2", 2, 20, 150, 1)])
+def test_pipelined_and_plain_launch_sequences_agree(lib, dev, name, d, N, T, reps):
+    """The pipelined launch sequence (time segments over internal streams; the default, so
+    every other test in this file runs it) and the plain one (what large sweeps use) are the same arithmetic: both match the
+    oracle, and each other to FP64-summation-order accuracy.  T is not a multiple of the checkpoint interval or the segment
+    count; reps > 1 tiles the samples beyond 512 to reach the thread-per-sample covariance kernels."""
+    case = H.Case(name, S=3, T=T, N=N, d=d, weights=True)
+    outs = []
+    for max_samples, segments in ((0, 6), (1 << 20, 6), (1 << 20, 11), (1 << 20, 1000)):
+        lib.set_pipeline(max_samples, min(segments, 64))
+        try:
+            if reps == 1:
+                H.check_vjp(lib, dev, case, torch.float32)
+            else:
+                H.check_vjp_tiled(lib, dev, case, reps, torch.float32)
+            dims = case.lqgk_dims()
+            act, dyn = case.tensors(dev, torch.float64)
+            x_tm = lib.pack_obs(torch.tensor(case.X, device=dev))
+            ws = H.workspace(lib, dims, abi.MODE_VJP, dev)
+            ll, ga, gd, _ = lib.loglik_vjp(dims, act, dyn, x_tm, ws=ws, stream=H.stream_of(dev))
+            torch.cuda.synchronize()
+            outs.append([ll] + list(ga.values()) + list(gd.values()))
+        finally:
+            lib.set_pipeline(1 << 30, 6)
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert torch.allclose(a, b, rtol=1e-9, atol=1e-9 * float(a.abs().max()) + 1e-300)
