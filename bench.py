@@ -216,7 +216,31 @@ def bench_c2(dev, barrier, reps=10):
 
     ms, (ll, g) = timed(lambda: parallel.trial_sharded_value_and_grad(local, cond), reps, 3, barrier)
     assert torch.isfinite(ll) and torch.isfinite(g).all()
-    return ms
+    # the same evaluation replayed from a CUDA graph (lqg_b200.graphs): the local part is captured, the all-reduce stays outside
+    from lqg_b200.graphs import GraphedValueAndGrad
+    lo, hi = parallel.shard_range(len(sig), *parallel.world())
+    ms_graph = None
+    if hi > lo:
+        idx = cond[lo:hi]
+
+        def fn(theta):   # theta = [5 shared | 6 sigma_target]
+            m = SubjectiveActor(dim=2, T=T, device=dev, action_cost=theta[0], action_variability=theta[1], subj_noise=theta[2],
+                                subj_vel_noise=theta[3], sigma_cursor=theta[4], sigma_target=theta[5:][idx])
+            return m.log_likelihood(x[idx])
+
+        th = torch.tensor([1.0, 0.5, 1.0, 0.5, 6.0] + sig, device=dev)
+        gv = GraphedValueAndGrad(fn, th)
+
+        def graphed():
+            out, grad = gv(th)
+            packed = torch.cat([out.sum().reshape(1), grad])
+            return parallel.allreduce_sum(packed)
+
+        ms_graph, packed = timed(graphed, reps, 3, barrier)
+        assert torch.allclose(packed[0], ll, rtol=1e-5) and torch.allclose(packed[1:], g, rtol=1e-3, atol=1e-4 * g.abs().max().item())
+    else:
+        barrier(); barrier()
+    return ms, ms_graph
 
 
 def bench_c5(dev, barrier, chains=4096, N=100, T=1200, reps=5):
@@ -237,7 +261,18 @@ def bench_c5(dev, barrier, chains=4096, N=100, T=1200, reps=5):
 
     ms, (ll, g) = timed(lambda: parallel.sharded_value_and_grad(local, theta, gather=False), reps, 2, barrier)
     assert torch.isfinite(ll).all() and torch.isfinite(g).all()
-    return ms
+    # the same evaluation replayed from a CUDA graph (what jax.jit of the potential energy is in the reference's numpyro loop)
+    from lqg_b200.graphs import GraphedValueAndGrad
+    lo, hi = parallel.shard_range(chains, *parallel.world())
+
+    def fn(th):
+        m = SubjectiveActor(dim=2, T=T, device=dev, **{n: th[:, i] for i, n in enumerate(PARAM_NAMES)})
+        return m.log_likelihood(x).sum(-1)
+
+    gv = GraphedValueAndGrad(fn, theta[lo:hi])
+    ms_graph, (ll2, g2) = timed(lambda: gv(theta[lo:hi]), reps, 2, barrier)
+    assert torch.allclose(ll2, ll, rtol=1e-5) and torch.allclose(g2, g, rtol=1e-3, atol=1e-4 * g.abs().max().item())
+    return ms, ms_graph
 
 
 def bench_c4(dev, S=4096, N=50, T=600, reps=2):
@@ -445,19 +480,21 @@ def run_ours(args):
     # ---------------- secondary workloads (every rank takes part: they shard over the ranks)
     secondary = []
     if not args.no_secondary:
-        c2_ms = bench_c2(dev, barrier)
-        c5_ms = bench_c5(dev, barrier)
-        t2 = torch.tensor([c2_ms, c5_ms], device=dev, dtype=torch.float64)
+        c2_ms, c2_g = bench_c2(dev, barrier)
+        c5_ms, c5_g = bench_c5(dev, barrier)
+        t2 = torch.tensor([c2_ms, c5_ms, c2_g or 0.0, c5_g or 0.0], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        c2_ms, c5_ms = [float(v) for v in t2.tolist()]
+        c2_ms, c5_ms, c2_g, c5_g = [float(v) for v in t2.tolist()]
         secondary.append({"workload": "c2: SubjectiveActor dim=2, 6 conditions x 20 trials x T=1200, grad wrt 5 shared + 6 per-condition "
                                       "parameters, public API; conditions sharded over the GPUs + one all-reduce of [ll, grad] (latency-bound)",
-                          "value": 6 * 20 / (c2_ms * 1e-3), "unit": "trial-evals/s", "ms_per_eval": c2_ms})
+                          "value": 6 * 20 / (c2_g * 1e-3), "unit": "trial-evals/s", "ms_per_eval": c2_g, "ms_per_eval_eager": c2_ms,
+                          "note": "ms_per_eval = the evaluation replayed from a CUDA graph (lqg_b200.graphs); eager = launched op by op"})
         secondary.append({"workload": "c5: one leapfrog of 4,096 lock-step chains = one fused log-lik+gradient of 4,096 parameter vectors x 100 "
                                       "trials x T=1200, chains sharded over the GPUs, public API (numpyro/NUTS itself is not installable here)",
-                          "value": 1e3 / c5_ms, "unit": "leapfrog-equivalents/s", "ms_per_eval": c5_ms,
-                          "chains_per_gpu": 4096 // world})
+                          "value": 1e3 / c5_g, "unit": "leapfrog-equivalents/s", "ms_per_eval": c5_g, "ms_per_eval_eager": c5_ms,
+                          "chains_per_gpu": 4096 // world,
+                          "note": "ms_per_eval = the evaluation replayed from a CUDA graph (lqg_b200.graphs); eager = launched op by op"})
 
     if rank == 0:
         # ---------------- roofline of the dominant kernel + whole step

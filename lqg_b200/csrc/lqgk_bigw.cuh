@@ -16,11 +16,57 @@ namespace lqgk {
 
 constexpr int BW_WARPS = 2;   // samples (warps) per CTA: small CTAs pack the 227 KB of shared memory better (18-23 KB per warp)
 
-// C[M,N] (op)= A B with A addressed as a(i,k), B as b(k,j); out(i, j, value) consumes each element once.  Every lane
-// owns 2 x 2 tiles of the output: 4 shared-memory loads feed 4 FMAs (the kernels are shared-memory-bandwidth bound; an
-// element-per-lane product needs 2 loads per FMA).
+// FP64 tensor-core tile: D(8x8) = A(8x4) B(4x8) + C, one warp (SASS: DMMA).  Fragments (PTX m8n8k4, A row / B col): lane
+// holds A[lane/4][lane%4], B[lane%4][lane/4] and C[lane/4][2*(lane%4) + {0,1}].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+// Products with a large enough output (see wmm_use_dmma) go to the FP64 tensor cores: the warp walks the 8 x 8 output tiles, every lane
+// feeds ONE element of A and of B per 8x8x4 block (2 shared-memory loads per DMMA = 256 FMAs, against 4 loads per 4 FMAs in
+// the scalar scheme below, which is shared-memory-latency bound at the 8 warps per SM these kernels reach).  Rows / columns /
+// k beyond the matrix are fed as zeros, results outside it are dropped, so any M, N, K works (n = 24, r = 22 at config c4).
+#ifndef LQGK_BW_DMMA
+#define LQGK_BW_DMMA 1
+#endif
+template <int M, int N, int K>
+__host__ __device__ constexpr bool wmm_use_dmma() {
+  return LQGK_BW_DMMA && ((M >= 6 && N >= 6) || ((M >= 6 || N >= 6) && M >= 2 && N >= 2 && K >= 6));
+}
+template <int M, int N, int K, class FA, class FB, class Out>
+__device__ __forceinline__ void wmm_dmma(int lane, FA&& a, FB&& b, Out&& out) {
+  constexpr int MT = (M + 7) / 8, NT = (N + 7) / 8, KT = (K + 3) / 4;
+  const int g = lane >> 2, q = lane & 3;
+  for (int it = 0; it < MT; ++it) {
+    const int i = it * 8 + g;
+    const int ic = i < M ? i : M - 1;
+    for (int jt = 0; jt < NT; ++jt) {
+      const int j = jt * 8 + g;                    // B fragment column (the C fragment's columns are jt*8 + 2q, +1)
+      const int jc = j < N ? j : N - 1;
+      double c0 = 0.0, c1 = 0.0;
+#pragma unroll 2
+      for (int kt = 0; kt < KT; ++kt) {
+        const int k = kt * 4 + q;
+        const int kc = k < K ? k : K - 1;
+        const double av = a(ic, kc), bv = b(kc, jc);
+        dmma884(c0, c1, (i < M && k < K) ? av : 0.0, (j < N && k < K) ? bv : 0.0);
+      }
+      const int j0 = jt * 8 + 2 * q;
+      if (i < M) {
+        if (j0 < N) out(i, j0, c0);
+        if (j0 + 1 < N) out(i, j0 + 1, c1);
+      }
+    }
+  }
+}
+
+// C[M,N] (op)= A B with A addressed as a(i,k), B as b(k,j); out(i, j, value) consumes each element once.  Small outputs: every
+// lane owns 2 x 2 tiles of the output: 4 shared-memory loads feed 4 FMAs (an element-per-lane product needs 2 loads per FMA).
 template <int M, int N, int K, class FA, class FB, class Out>
 __device__ __forceinline__ void wmm(int lane, FA&& a, FB&& b, Out&& out) {
+  if constexpr (wmm_use_dmma<M, N, K>()) {
+    wmm_dmma<M, N, K>(lane, a, b, out);
+    return;
+  }
   constexpr int MT = (M + 1) / 2, NT = (N + 1) / 2;
   for (int e = lane; e < MT * NT; e += 32) {
     const int it = e / NT;
@@ -61,6 +107,34 @@ __device__ __forceinline__ void bw_flush_acc(int lane, double* g, size_t Sc, con
 // C[M,M] = base(i,j) + sum_k a(i,k) b(k,j), result known symmetric: lower triangle computed (2 x 2 tiles), mirrored.
 template <int M, int K, class Base, class FA, class FB>
 __device__ __forceinline__ void wmm_sym(int lane, Base&& base, FA&& a, FB&& b, double* Cm) {
+  if constexpr (wmm_use_dmma<M, M, K>()) {
+    // tensor-core version: the 8 x 8 tiles on and below the diagonal, mirrored (diagonal tiles write both halves: same values
+    // up to the rounding of two summation orders are avoided by writing only j <= i there)
+    constexpr int MT8 = (M + 7) / 8, KT = (K + 3) / 4;
+    const int g = lane >> 2, q = lane & 3;
+    for (int it = 0; it < MT8; ++it) {
+      const int i = it * 8 + g;
+      const int ic = i < M ? i : M - 1;
+      for (int jt = 0; jt <= it; ++jt) {
+        const int j = jt * 8 + g;
+        const int jc = j < M ? j : M - 1;
+        const int j0 = jt * 8 + 2 * q;
+        double c0 = (i < M && j0 < M) ? base(i, j0) : 0.0, c1 = (i < M && j0 + 1 < M) ? base(i, j0 + 1) : 0.0;
+#pragma unroll 2
+        for (int kt = 0; kt < KT; ++kt) {
+          const int k = kt * 4 + q;
+          const int kc = k < K ? k : K - 1;
+          const double av = a(ic, kc), bv = b(kc, jc);
+          dmma884(c0, c1, (i < M && k < K) ? av : 0.0, (j < M && k < K) ? bv : 0.0);
+        }
+        if (i < M) {
+          if (j0 < M && j0 <= i) { Cm[i * M + j0] = c0; Cm[j0 * M + i] = c0; }
+          if (j0 + 1 < M && j0 + 1 <= i) { Cm[i * M + j0 + 1] = c1; Cm[(j0 + 1) * M + i] = c1; }
+        }
+      }
+    }
+    return;
+  }
   constexpr int MT = (M + 1) / 2;
   for (int e = lane; e < MT * MT; e += 32) {
     const int it = e / MT, jt = e - it * MT;

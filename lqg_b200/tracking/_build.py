@@ -1,4 +1,5 @@
 """Small helpers for building model matrices from (possibly batched) parameter tensors."""
+import functools
 from itertools import chain
 
 import torch
@@ -15,7 +16,9 @@ def canon(params, dtype=None, device=None):
         device = tens[0].device if tens else default_device()
     if dtype is None:
         dtype = next((p.dtype for p in tens if p.is_floating_point()), torch.float32)
-    vals = [p.to(device=device, dtype=dtype) if torch.is_tensor(p) else torch.tensor(float(p), dtype=dtype, device=device)
+    # Python scalars become device scalars with a fill kernel (torch.full), not a host-to-device copy: model construction
+    # stays legal inside a CUDA-graph capture (lqg_b200.graphs)
+    vals = [p.to(device=device, dtype=dtype) if torch.is_tensor(p) else torch.full((), float(p), dtype=dtype, device=device)
             for p in params]
     vals = list(torch.broadcast_tensors(*vals))
     batch = vals[0].shape
@@ -24,8 +27,29 @@ def canon(params, dtype=None, device=None):
     return vals, batch, dtype, device
 
 
+def _freeze(M):
+    return tuple(_freeze(r) for r in M) if isinstance(M, (list, tuple)) else float(M)
+
+
+@functools.lru_cache(maxsize=256)
+def _const_cached(frozen, dtype, device):
+    return torch.tensor(frozen, dtype=dtype, device=device)
+
+
 def const(M, dtype, device):
-    return torch.tensor(M, dtype=dtype, device=device)
+    """Constant matrix on `device`; cached per (values, dtype, device) so that repeated model construction does no
+    host-to-device copy (and is legal inside a CUDA-graph capture once warmed up).  Callers must not modify the result."""
+    return _const_cached(_freeze(M), dtype, torch.device(device))
+
+
+@functools.lru_cache(maxsize=64)
+def _index_cached(idx, device):
+    return torch.tensor(idx, dtype=torch.long, device=device)
+
+
+def index(idx, device):
+    """Index list as a cached device tensor (see `const`)."""
+    return _index_cached(tuple(int(i) for i in idx), torch.device(device))
 
 
 def diag(vals):
@@ -33,8 +57,14 @@ def diag(vals):
     return torch.diag_embed(torch.stack(vals, -1))
 
 
+@functools.lru_cache(maxsize=256)
+def _block_diag_cached(frozen, dim, dtype, device):
+    return torch.block_diag(*[torch.tensor(frozen, dtype=dtype)] * dim).to(device)
+
+
 def block_diag_const(block, dim, dtype, device):
-    return torch.block_diag(*[torch.tensor(block, dtype=dtype, device=device)] * dim)
+    """dim copies of a constant block on the diagonal (cached like `const`; do not modify the result)."""
+    return _block_diag_cached(_freeze(block), dim, dtype, torch.device(device))
 
 
 def swap_dims(d, dim):

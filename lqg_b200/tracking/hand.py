@@ -33,7 +33,7 @@ class HandMotionModelTrackingTask(System):
         V = B.diag([pn, pz, z, z, av])
         W = B.diag([st, sc])
         Q = torch.zeros(5, 5, dtype=dtype, device=device)
-        Q[:2, :2] = torch.tensor([[1.0, -1.0], [-1.0, 1.0]], dtype=dtype, device=device)
+        Q[:2, :2] = B.const([[1.0, -1.0], [-1.0, 1.0]], dtype, device)
         R = torch.eye(1, dtype=dtype, device=device) * ac[..., None, None]
         spec = Actor(A=A, B=Bm, F=F, V=V, W=W, Q=Q, R=R, T=T)
         super().__init__(actor=spec, dynamics=spec)

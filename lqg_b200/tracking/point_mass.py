@@ -64,7 +64,7 @@ class PointMassBoundedActor(System):
         F = torch.eye(3, 4, dtype=dtype, device=device)
         W = B.diag([st, sc, sc])
         Q = torch.zeros(4, 4, dtype=dtype, device=device)
-        Q[:2, :2] = torch.tensor([[1.0, -1.0], [-1.0, 1.0]], dtype=dtype, device=device)
+        Q[:2, :2] = B.const([[1.0, -1.0], [-1.0, 1.0]], dtype, device)
         R = torch.eye(1, dtype=dtype, device=device) * (ac * dt)[..., None, None]
         spec = Actor(A=A, B=Bm, F=F, V=V, W=W, Q=Q, R=R, T=T)
         super().__init__(actor=spec, dynamics=spec)

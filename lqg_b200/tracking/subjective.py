@@ -28,12 +28,12 @@ class SubjectiveActor(System):
         Q = B.block_diag_const([[1.0, -1.0, 0.0], [-1.0, 1.0, 0.0], [0.0, 0.0, 0.0]], dim, dtype, device)
         R = torch.eye(dim, dtype=dtype, device=device) * ac[..., None, None]
 
-        dims = swap_dims(A.shape[0], dim)
-        A = A[dims, :][:, dims]
-        Bm = Bm[dims, :]
-        V = V[..., dims, :]
-        F = F[:, dims]
-        Q = Q[dims, :][:, dims]
+        dims = B.index(swap_dims(A.shape[0], dim), device)     # cached device index (no host-to-device copy per construction)
+        A = A.index_select(0, dims).index_select(1, dims)
+        Bm = Bm.index_select(0, dims)
+        V = V.index_select(-2, dims)
+        F = F.index_select(1, dims)
+        Q = Q.index_select(0, dims).index_select(1, dims)
         act = Actor(A=A, B=Bm, F=F, V=V, W=W, Q=Q, R=R, T=T)
         super().__init__(actor=act, dynamics=dyn)
         if dim > 1:   # identical independent axes: the likelihood factorises (System.log_likelihood)

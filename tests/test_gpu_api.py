@@ -256,3 +256,27 @@ def test_vjp_call_is_capturable_into_a_cuda_graph_and_replays_identically():
         assert torch.equal(outs[0], ref[0])                                     # log-likelihoods: bit-identical
         for o, r in zip(outs[1:], ref[1:]):                                     # gradients: FP64 atomics order may differ in the last bit
             assert torch.allclose(o, r, rtol=1e-6, atol=1e-7 * r.abs().max().item())
+
+
+def test_cuda_graph_replay_of_value_and_grad_through_the_public_api():
+    """Model construction + fused likelihood + backward captured once (lqg_b200.graphs) and replayed with new parameters."""
+    from lqg_b200.graphs import GraphedValueAndGrad
+    T, N, S = 90, 8, 5
+    X = torch.tensor(_sim(O.subjective_actor_mats(dim=2), T, N, seed=12).astype(np.float32), device=DEV)
+    names = ["action_cost", "action_variability", "subj_noise", "subj_vel_noise", "sigma_target", "sigma_cursor"]
+
+    def fn(th):
+        m = tracking.SubjectiveActor(dim=2, T=T, **{n: th[:, i] for i, n in enumerate(names)})
+        return m.log_likelihood(X).sum(-1)
+
+    th0 = torch.tensor([[1.0, 0.5, 1.0, 0.5, 6.0, 6.0]], device=DEV).repeat(S, 1)
+    gv = GraphedValueAndGrad(fn, th0)
+    for seed in (1, 2):
+        th = th0 * torch.exp(0.2 * torch.randn(S, 6, device=DEV, generator=torch.Generator(device=DEV).manual_seed(seed)))
+        ll_g, g_g = gv(th)
+        ll_g, g_g = ll_g.clone(), g_g.clone()
+        th_e = th.clone().requires_grad_()
+        ll_e = fn(th_e)
+        ll_e.sum().backward()
+        assert torch.allclose(ll_g, ll_e.detach(), rtol=1e-6)
+        assert torch.allclose(g_g, th_e.grad, rtol=1e-5, atol=1e-6 * th_e.grad.abs().max().item())
