@@ -165,9 +165,11 @@ struct BigW {
   static constexpr int NC = C::n;
 
   // ------------------------------------------------------------------------------------------ forward
-  static constexpr int FWD_DOUBLES = NC + U * B + B * Y + B * U + B * Y + 2 * N * N + R * R + N * R + R * D + 3 * D * D + 8;
+  static constexpr int FWD_DOUBLES = NC + 2 * (U * B + B * Y) + B * U + B * Y + 2 * N * N + R * R + N * R + R * D + 3 * D * D + 8;
   static size_t smem_fwd() { return sizeof(double) * FWD_DOUBLES * BW_WARPS; }
-  static constexpr int SEQ_DOUBLES = 2 * R * R + 2 * N * R + 5 * R * D + 2 * D * D + N * N + 8;
+  // + two staging buffers for the step inputs (Fu_t, (J_t, S'^-1_t), the float sums tail) filled by cp.async one step ahead
+  static constexpr int SEQ_STAGE = N * R + R * D + D * (D + 1) / 2 + (DM::SUMP - DM::SUM_J + 1) / 2;
+  static constexpr int SEQ_DOUBLES = 2 * R * R + 2 * N * R + 5 * R * D + 2 * D * D + N * N + 8 + 2 * ((SEQ_STAGE + 1) & ~1);
   static size_t smem_seq() { return sizeof(double) * SEQ_DOUBLES * BW_WARPS; }
   static constexpr int CON_DOUBLES = 2 * NC + U * B + B * Y + R * R + N * R + 2 * N * N + 2 * B * Y + 2 * B * U + U * B + 8;
   static size_t smem_con() { return sizeof(double) * CON_DOUBLES * BW_WARPS; }
@@ -252,7 +254,9 @@ __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_fwd(const double* cst, s
   double* c = smw + (size_t)warp * W::FWD_DOUBLES;
   double* Lt = c + NC;
   double* Kt = Lt + U * B;
-  double* KD = Kt + B * Y;
+  double* LtN = Kt + B * Y;         // next step's gains, in flight (cp.async) while this step is computed
+  double* KtN = LtN + U * B;
+  double* KD = KtN + B * Y;
   double* KO = KD + B * U;
   double* Fj = KO + B * Y;
   double* Nj = Fj + N * N;
@@ -280,9 +284,19 @@ __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_fwd(const double* cst, s
     __syncwarp();
   }
   float* recs = rec + s * (size_t)Tn * DM::REC;
+  // gains of step t arrive by per-lane 8-byte cp.async one step ahead (an unprefetched global round trip per step was a third of
+  // this latency-bound kernel's step time)
+  auto fetch_gains = [&](int t, double* Ld, double* Kd) {
+    for (int e = lane; e < U * B; e += 32) cp_async<8>(Ld + e, L + gi(t, DM::EL, e));
+    for (int e = lane; e < B * Y; e += 32) cp_async<8>(Kd + e, K + gi(t, DM::EK, e));
+    cp_async_commit();
+  };
+  __syncwarp();                                    // (Kt was read by the initialisation above)
+  if (t0 < t1) fetch_gains(t0, Lt, Kt);
   for (int t = t0; t < t1; ++t) {
-    for (int e = lane; e < U * B; e += 32) Lt[e] = L[gi(t, DM::EL, e)];
-    for (int e = lane; e < B * Y; e += 32) Kt[e] = K[gi(t, DM::EK, e)];
+    cp_async_wait<0>();
+    __syncwarp();                                  // gains of step t visible to all lanes; the other buffer is free
+    if (t + 1 < t1) fetch_gains(t + 1, LtN, KtN);
     if (save_adj) {
       double* cs = Cs + (s * Tn + t) * (size_t)DM::EC;
       for (int e = lane; e < R * R; e += 32) {
@@ -338,6 +352,7 @@ __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_fwd(const double* cst, s
     }
     if (lane == 0) rt[DM::REC_LOGDET] = (float)*ld;
     __syncwarp();
+    { double* tp = Lt; Lt = LtN; LtN = tp; tp = Kt; Kt = KtN; KtN = tp; }
   }
   if (save_adj && t1 < Tn) {   // where the next time segment continues from
     double* cs = Cs + (s * Tn + t1) * (size_t)DM::EC;
@@ -373,22 +388,42 @@ __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_seq_rev(int npad, int Tn
   double* Sinv = CJ + R * D;
   double* Ss = Sinv + D * D;
   double* Sg = Ss + D * D;          // full symmetric joint cotangent Sgb_t (N x N)
+  double* stg0 = Sg + N * N;        // two staging buffers: [Fu (N R) | js (NJS) | float sums tail]
+  double* stg1 = stg0 + ((W::SEQ_STAGE + 1) & ~1);
+  constexpr int NFT = DM::SUMP - DM::SUM_J;   // floats of the sums row this kernel reads (Jb, Wv)
+  auto fetch_step = [&](int t, double* stg) {
+    const double* fu = FU + (s * Tn + t) * (size_t)SR::NSF;
+    const double* js = JS + (s * Tn + t) * (size_t)SR::NJS;
+    const float* sm = sums + (s * Tn + t) * (size_t)DM::SUMP + DM::SUM_J;
+    for (int e = lane; e < N * R; e += 32) cp_async<8>(stg + e, fu + e);
+    for (int e = lane; e < SR::NJS; e += 32) cp_async<8>(stg + N * R + e, js + e);
+    float* sf = reinterpret_cast<float*>(stg + N * R + SR::NJS);
+    for (int e = lane; e < NFT; e += 32) cp_async<4>(sf + e, sm + e);
+    cp_async_commit();
+  };
   double sw = 0.0;
   for (int i = lane; i < Ntr; i += 32) sw += (double)w[s * Ntr + i];
   for (int m = 16; m >= 1; m >>= 1) sw += __shfl_xor_sync(FULL, sw, m);
   if (t1 < 0) t1 = Tn;
   for (int e = lane; e < R * R; e += 32) Cb[e] = t1 == Tn ? 0.0 : carry[s * (R * R) + e];
   __syncwarp();
+  if (t1 > t0) fetch_step(t1 - 1, stg0);
   for (int t = t1 - 1; t >= t0; --t) {
-    const double* fu = FU + (s * Tn + t) * (size_t)SR::NSF;
-    const double* js = JS + (s * Tn + t) * (size_t)SR::NJS;
-    const float* sm = sums + (s * Tn + t) * (size_t)DM::SUMP;
-    for (int e = lane; e < N * R; e += 32) Fu[e] = fu[e];
-    for (int e = lane; e < R * D; e += 32) { J[e] = js[e]; Jb[e] = (double)sm[DM::SUM_J + e]; }
-    for (int e = lane; e < D * D; e += 32) {
-      const int i = e / D, j = e - i * D;
-      Sinv[e] = js[R * D + sidx(i, j)];
+    cp_async_wait<0>();
+    __syncwarp();                                  // inputs of step t staged; the other staging buffer is free
+    if (t > t0) fetch_step(t - 1, stg1);
+    {
+      const double* fu = stg0;
+      const double* js = stg0 + N * R;
+      const float* smt = reinterpret_cast<const float*>(stg0 + N * R + SR::NJS);   // sums[SUM_J ..]
+      for (int e = lane; e < N * R; e += 32) Fu[e] = fu[e];
+      for (int e = lane; e < R * D; e += 32) { J[e] = js[e]; Jb[e] = (double)smt[e]; }
+      for (int e = lane; e < D * D; e += 32) {
+        const int i = e / D, j = e - i * D;
+        Sinv[e] = js[R * D + sidx(i, j)];
+      }
     }
+    const float* sm = reinterpret_cast<const float*>(stg0 + N * R + SR::NJS) - DM::SUM_J;   // so that sm[SUM_W + ..] below reads the staged tail
     __syncwarp();
     for (int e = lane; e < R * D; e += 32) {
       const int i = e / D, j = e - i * D;
@@ -426,6 +461,7 @@ __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_seq_rev(int npad, int Tn
                   [&](int m, int b) { return SF[m * R + b]; }, Cn);        // Cb <- Fu^T SF (lower, mirrored)
     __syncwarp();
     double* tmp = Cb; Cb = Cn; Cn = tmp;
+    tmp = stg0; stg0 = stg1; stg1 = tmp;
   }
   if (t0 > 0) {
     for (int e = lane; e < R * R; e += 32) carry[s * (R * R) + e] = Cb[e];
