@@ -438,6 +438,18 @@ def run_ours(args):
     prof = lib.profile_read()
     lib.profile_enable(False)
     clocks = sampler.stop()
+    # The pipelined launch sequence overlaps kernels of different streams, so the per-kernel event times above include the
+    # time a kernel shares the SMs with others.  Two extra steps (outside the timed region) with the plain sequence give
+    # every kernel's time when it runs alone -- reported next to the live numbers.
+    lib.set_pipeline(0, args.pipe_segments)
+    step_resident()
+    lib.profile_enable(True)
+    for _ in range(2):
+        step_resident()
+    torch.cuda.synchronize()
+    prof_alone = {k: (v[0] / 2, v[1] / 2) for k, v in lib.profile_read().items()}
+    lib.profile_enable(False)
+    lib.set_pipeline(args.pipe_max if args.pipe_max >= 0 else (1 << 30), args.pipe_segments)
     assert res.shape[0] == S_total and torch.isfinite(res).all(), "non-finite sweep result in the timed region"
     del res
     t_ms = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -515,7 +527,8 @@ def run_ours(args):
             g_cnt = sum(prof[m][1] for m in members if m in prof) / args.steps
             if g_cnt == 0:
                 continue
-            entry = {"ms_per_step": g_ms, "launches_per_step": g_cnt, "share": g_ms / ms_per_step,
+            entry = {"ms_per_step": g_ms, "ms_per_step_alone": sum(prof_alone[m][0] for m in members if m in prof_alone),
+                     "launches_per_step": g_cnt, "share": g_ms / ms_per_step,
                      "kernels": {"k_" + m: prof[m][0] / args.steps for m in members if m in prof and prof[m][1] > 0}}
             if g in kind_flops:
                 entry["algorithmic_tflops"] = kind_flops[g] * S / (g_ms * 1e-3) / 1e12
@@ -523,9 +536,12 @@ def run_ours(args):
         dom = max((k for k in kernels if k in kind_flops), key=lambda k: kernels[k]["ms_per_step"])
         dom_kernel = max(kernels[dom]["kernels"], key=lambda k: kernels[dom]["kernels"][k])
         dom_ms = kernels[dom]["kernels"][dom_kernel]                  # live CUDA-event time of that kernel per step
-        dom_launches = max(1.0, kernels[dom]["launches_per_step"] if len(kernels[dom]["kernels"]) == 1 else 1.0)
+        # launches of that kernel per step: sample chunks x time segments of the pipelined sequence.  Flops / bytes per launch =
+        # per-step total / launches, so achieved (per launch / launch duration) = per-step total / per-step kernel time
+        dom_launches = max(1.0, float(prof[dom_kernel[2:]][1]) / args.steps)
         launch_ms = dom_ms / dom_launches
-        samples_per_launch = S / dom_launches
+        samples_per_launch = S                                         # every launch covers all samples of the chunk (one time segment)
+        dom_ms_alone = prof_alone[dom_kernel[2:]][0]
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         # instruction counts / DRAM bytes of THIS build from the committed ncu capture (tools/ncu_counters.py)
@@ -547,13 +563,15 @@ def run_ours(args):
         if ck:
             # per sample of one launch; the capture used fewer samples per launch than this run (ncu replays every kernel ~40x):
             # both quantities are per-sample constants of the kernel (no cross-sample reuse), so they scale with the samples
-            flops = ck["fp32_flops_per_sample"] * samples_per_launch
+            flops = ck["fp32_flops_per_sample"] * S / dom_launches
             executed = {"tflops": flops / (launch_ms * 1e-3) / 1e12, "frac": flops / (launch_ms * 1e-3) / 1e12 / fp32_peak,
+                        "frac_when_running_alone": ck["fp32_flops_per_sample"] * S / (dom_ms_alone * 1e-3) / 1e12 / fp32_peak,
+                        "ms_per_step_live_overlapped": dom_ms, "ms_per_step_alone": dom_ms_alone,
                         "fp32_flops_per_launch": flops, "warp_instructions_per_sample_step": ck["inst_per_sample_step"],
                         "fp32_share_of_instructions": ck["fp32_inst_share"],
                         "ncu_fma_pipe_cycles_active_pct": ck["fma_pipe_cycles_active_pct"], "ncu_issue_active_pct": ck["issue_active_pct"],
                         "source": f"profiles/r02_counters.json (ncu --set full of this build, {cj['samples_per_launch']} samples per launch, scaled per sample)"}
-            traffic = ck["dram_bytes_per_sample"] * samples_per_launch
+            traffic = ck["dram_bytes_per_sample"] * S / dom_launches
         achieved_alg = kernels[dom]["algorithmic_tflops"]
         # floors of the whole step (this rank's share)
         step_exec_flops = step_bytes = fp32_floor = fp64_floor = hbm_floor = None
@@ -575,6 +593,7 @@ def run_ours(args):
         roofline = {"bound": bound, "kernel": dom_kernel, "achieved": r_ach, "peak": r_peak, "unit": r_unit,
                     "frac": (r_ach / r_peak) if r_ach is not None else None, "traffic": traffic,
                     "launch_ms": launch_ms, "launches_per_step": dom_launches, "samples_per_launch": samples_per_launch,
+                    "time_steps_per_launch": T / dom_launches,
                     "peak_source": "FFMA micro-kernel measured in this run (lqgk_peak_fma); MEASURED_PEAKS.json has no FP32 figure; nominal 74.5",
                     "note": "achieved = FP32 operations the kernel executes (FFMA2 = 2 FMAs per lane, all 32 lanes counted; counts from the ncu "
                             "capture of this build) / live CUDA-event time.  algorithmic_* = SURVEY 8(d) dense count of the reference recursion the "
@@ -582,7 +601,7 @@ def run_ours(args):
                             "saving, not pipe utilisation",
                     "executed": executed, "counters_note": counters_note,
                     "algorithmic_achieved_tflops": achieved_alg, "algorithmic_frac": achieved_alg / fp32_peak,
-                    "algorithmic_flops_per_launch": kind_flops[dom] * samples_per_launch,
+                    "algorithmic_flops_per_launch": kind_flops[dom] * S / dom_launches,
                     "fp64_peak_tflops_measured": fp64_peak,
                     "step": {"ms": ms_per_step, "fp32_floor_ms": fp32_floor, "fp64_floor_ms": fp64_floor, "hbm_floor_ms": hbm_floor,
                              "executed_fp32_flops": step_exec_flops, "dram_bytes": step_bytes,
