@@ -98,8 +98,8 @@ int run_big(const Call& c) {
       size_t smem = BigW<DM>::smem_fwd();
       if ((rc = set_smem<DM>((const void*)kw_cov_fwd<DM>, smem))) return rc;
       ProfScope ps_(PK_COV_FWD, st);
-      kw_cov_fwd<DM><<<wblk, wthr, smem, st>>>(D(p.cst), Sc, npad, Tn, D(p.L), D(p.K), vjp, vjp ? D(p.Cs) : nullptr, vjp ? D(p.FU) : nullptr,
-                                               vjp ? D(p.JS) : nullptr, vjp ? D(p.J0) : nullptr, F(p.rec));
+      kw_cov_fwd<DM><<<wblk, wthr, smem, st>>>(D(p.cst), Sc, npad, Tn, D(p.L), D(p.K), vjp, vjp ? D(p.Cs) : nullptr, vjp ? F(p.FU) : nullptr,
+                                               vjp ? F(p.JS) : nullptr, vjp ? D(p.J0) : nullptr, F(p.rec));
       LQGK_LAUNCH_CHECK();
     }
     const int RT = std::min((N + 31) / 32, trial_rt_max<DM>());
@@ -144,8 +144,8 @@ int run_big(const Call& c) {
       size_t smem = BigW<DM>::smem_seq();
       if ((rc = set_smem<DM>((const void*)kw_cov_seq_rev<DM>, smem))) return rc;
       ProfScope ps_(PK_COV_REV, st);
-      kw_cov_seq_rev<DM><<<wblk, 32 * BW_WARPS, smem, st>>>(npad, Tn, N, F(p.w), D(p.FU), D(p.JS), D(p.J0), F(p.sums), D(p.SGB), D(p.SGBI),
-                                                           D(p.SFW));
+      kw_cov_seq_rev<DM><<<wblk, 32 * BW_WARPS, smem, st>>>(npad, Tn, N, F(p.w), F(p.FU), F(p.JS), D(p.J0), F(p.sums), F(p.SGB), D(p.SGBI),
+                                                           F(p.SFW));
       LQGK_LAUNCH_CHECK();
     }
     {
@@ -154,8 +154,8 @@ int run_big(const Call& c) {
       ProfScope ps_(PK_COV_CONTRIB, st);
       // time ranges: enough (sample x range) warps to put ~12 on every SM when there are few samples
       int chunks = std::max(1, std::min((Tn + 3) / 4, (sm_count() * 12 + npad - 1) / npad));
-      kw_cov_contrib<DM><<<dim3(wblk, chunks), wthr, smem, st>>>(D(p.cst), Sc, npad, Tn, D(p.L), D(p.K), D(p.Cs), D(p.SGB), D(p.SGBI),
-                                                                D(p.SFW), F(p.sums), D(p.acc), D(p.Lbar), D(p.Kbar), nullptr);
+      kw_cov_contrib<DM><<<dim3(wblk, chunks), wthr, smem, st>>>(D(p.cst), Sc, npad, Tn, D(p.L), D(p.K), D(p.Cs), F(p.SGB), D(p.SGBI),
+                                                                F(p.SFW), F(p.sums), D(p.acc), D(p.Lbar), D(p.Kbar), nullptr);
       LQGK_LAUNCH_CHECK();
     }
     {

@@ -168,7 +168,7 @@ struct BigW {
   static constexpr int FWD_DOUBLES = NC + 2 * (U * B + B * Y) + B * U + B * Y + 2 * N * N + R * R + N * R + R * D + 3 * D * D + 8;
   static size_t smem_fwd() { return sizeof(double) * FWD_DOUBLES * BW_WARPS; }
   // + two staging buffers for the step inputs (Fu_t, (J_t, S'^-1_t), the float sums tail) filled by cp.async one step ahead
-  static constexpr int SEQ_STAGE = N * R + R * D + D * (D + 1) / 2 + (DM::SUMP - DM::SUM_J + 1) / 2;
+  static constexpr int SEQ_STAGE = (N * R + R * D + D * (D + 1) / 2 + (DM::SUMP - DM::SUM_J) + 1) / 2;   // floats, counted in doubles
   static constexpr int SEQ_DOUBLES = 2 * R * R + 2 * N * R + 5 * R * D + 2 * D * D + N * N + 8 + 2 * ((SEQ_STAGE + 1) & ~1);
   static size_t smem_seq() { return sizeof(double) * SEQ_DOUBLES * BW_WARPS; }
   static constexpr int CON_DOUBLES = 2 * NC + U * B + B * Y + R * R + N * R + 2 * N * N + 2 * B * Y + 2 * B * U + U * B + 8;
@@ -240,7 +240,7 @@ __device__ __forceinline__ void bw_condition(int lane, const double* Sig, double
 // GAINS_MINOR: L, K are sample-minor [t][e][Sc] (written by the thread-per-sample Riccati / Kalman kernels of the small systems).
 template <class DM, bool GAINS_MINOR = false>
 __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_fwd(const double* cst, size_t Sc, int npad, int Tn, const double* L, const double* K,
-                                                            int save_adj, double* Cs, double* FU, double* JS, double* J0, float* rec,
+                                                            int save_adj, double* Cs, lin_t* FU, lin_t* JS, double* J0, float* rec,
                                                             int t0 = 0, int t1 = -1) {
   // [t0, t1): time range of this launch (t1 < 0: up to Tn); t0 > 0 continues from the C_{t0} saved in Cs (save_adj on)
   using W = BigW<DM>;
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_fwd(const double* cst, s
                  [&](int i, int j, double v) { KD[i * U + j] = v; });
     __syncwarp();
     float* rt = recs + (size_t)t * DM::REC;
-    double* fu = FU + (s * Tn + t) * (size_t)SR::NSF;
+    lin_t* fu = FU + (s * Tn + t) * (size_t)SR::NSF;
     for (int e = lane; e < N * N; e += 32) {                               // joint transition F_t  (system.py:167-187)
       const int i = e / N, j = e - i * N;
       double a;
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_fwd(const double* cst, s
     wmm_sym<N, R>(lane, [&](int i, int j) { return Nj[i * N + j]; }, [&](int i, int k) { return T1[i * R + k]; },
                   [&](int k, int j) { return Fj[j * N + D + k]; }, Sig);   // Sig' = Fu C Fu^T + N (lower, mirrored)
     __syncwarp();
-    double* js = JS + (s * Tn + t) * (size_t)SR::NJS;
+    lin_t* js = JS + (s * Tn + t) * (size_t)SR::NJS;
     bw_condition<DM>(lane, Sig, Linv, Z, ld, [&](int e, double v) { rt[DM::REC_J + e] = (float)v; if (save_adj) js[e] = v; }, Cm);
     for (int e = lane; e < D * D; e += 32) {
       const int i = e / D, j = e - i * D;
@@ -365,8 +365,8 @@ __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_fwd(const double* cst, s
 
 // Sequential covariance adjoint (CovSeqRev), warp per sample, t descending.
 template <class DM>
-__global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_seq_rev(int npad, int Tn, int Ntr, const float* w, const double* FU, const double* JS,
-                                                                const double* J0, const float* sums, double* SGB, double* SGBI, double* SFW,
+__global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_seq_rev(int npad, int Tn, int Ntr, const float* w, const lin_t* FU, const lin_t* JS,
+                                                                const double* J0, const float* sums, lin_t* SGB, double* SGBI, lin_t* SFW,
                                                                 int t0 = 0, int t1 = -1, double* carry = nullptr) {
   // [t0, t1) walked downwards (t1 < 0: from Tn); `carry` ([s][R*R]) hands Cb from one launch to the next (pipelined sequence)
   using W = BigW<DM>;
@@ -392,13 +392,13 @@ __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_seq_rev(int npad, int Tn
   double* stg1 = stg0 + ((W::SEQ_STAGE + 1) & ~1);
   constexpr int NFT = DM::SUMP - DM::SUM_J;   // floats of the sums row this kernel reads (Jb, Wv)
   auto fetch_step = [&](int t, double* stg) {
-    const double* fu = FU + (s * Tn + t) * (size_t)SR::NSF;
-    const double* js = JS + (s * Tn + t) * (size_t)SR::NJS;
+    const lin_t* fu = FU + (s * Tn + t) * (size_t)SR::NSF;
+    const lin_t* js = JS + (s * Tn + t) * (size_t)SR::NJS;
     const float* sm = sums + (s * Tn + t) * (size_t)DM::SUMP + DM::SUM_J;
-    for (int e = lane; e < N * R; e += 32) cp_async<8>(stg + e, fu + e);
-    for (int e = lane; e < SR::NJS; e += 32) cp_async<8>(stg + N * R + e, js + e);
-    float* sf = reinterpret_cast<float*>(stg + N * R + SR::NJS);
-    for (int e = lane; e < NFT; e += 32) cp_async<4>(sf + e, sm + e);
+    float* sf = reinterpret_cast<float*>(stg);              // staging layout (floats): [Fu (N R) | js (NJS) | sums tail (NFT)]
+    for (int e = lane; e < N * R; e += 32) cp_async<4>(sf + e, fu + e);
+    for (int e = lane; e < SR::NJS; e += 32) cp_async<4>(sf + N * R + e, js + e);
+    for (int e = lane; e < NFT; e += 32) cp_async<4>(sf + N * R + SR::NJS + e, sm + e);
     cp_async_commit();
   };
   double sw = 0.0;
@@ -413,17 +413,17 @@ __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_seq_rev(int npad, int Tn
     __syncwarp();                                  // inputs of step t staged; the other staging buffer is free
     if (t > t0) fetch_step(t - 1, stg1);
     {
-      const double* fu = stg0;
-      const double* js = stg0 + N * R;
-      const float* smt = reinterpret_cast<const float*>(stg0 + N * R + SR::NJS);   // sums[SUM_J ..]
-      for (int e = lane; e < N * R; e += 32) Fu[e] = fu[e];
-      for (int e = lane; e < R * D; e += 32) { J[e] = js[e]; Jb[e] = (double)smt[e]; }
+      const float* fu = reinterpret_cast<const float*>(stg0);
+      const float* js = fu + N * R;
+      const float* smt = js + SR::NJS;                                              // sums[SUM_J ..]
+      for (int e = lane; e < N * R; e += 32) Fu[e] = (double)fu[e];
+      for (int e = lane; e < R * D; e += 32) { J[e] = (double)js[e]; Jb[e] = (double)smt[e]; }
       for (int e = lane; e < D * D; e += 32) {
         const int i = e / D, j = e - i * D;
-        Sinv[e] = js[R * D + sidx(i, j)];
+        Sinv[e] = (double)js[R * D + sidx(i, j)];
       }
     }
-    const float* sm = reinterpret_cast<const float*>(stg0 + N * R + SR::NJS) - DM::SUM_J;   // so that sm[SUM_W + ..] below reads the staged tail
+    const float* sm = reinterpret_cast<const float*>(stg0) + N * R + SR::NJS - DM::SUM_J;   // so that sm[SUM_W + ..] below reads the staged tail
     __syncwarp();
     for (int e = lane; e < R * D; e += 32) {
       const int i = e / D, j = e - i * D;
@@ -443,19 +443,19 @@ __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_seq_rev(int npad, int Tn
       Ss[b * D + a] = v;
     }
     __syncwarp();
-    double* sgb = SGB + (s * Tn + t) * (size_t)SR::NSGB;
+    lin_t* sgb = SGB + (s * Tn + t) * (size_t)SR::NSGB;
     for (int e = lane; e < N * N; e += 32) {                               // Sgb_t: full symmetric in shared memory, packed lower out
       const int i = e / N, j = e - i * N;
       if (j > i) continue;
       const double v = i < D ? Ss[i * D + j] : (j < D ? Bh[(i - D) * D + j] : Cb[(i - D) * R + (j - D)]);
-      sgb[i * (i + 1) / 2 + j] = v;
+      sgb[i * (i + 1) / 2 + j] = (lin_t)v;
       Sg[i * N + j] = v;
       Sg[j * N + i] = v;
     }
     __syncwarp();
-    double* sfw = SFW + (s * Tn + t) * (size_t)SR::NSF;
+    lin_t* sfw = SFW + (s * Tn + t) * (size_t)SR::NSF;
     wmm<N, R, N>(lane, [&](int m, int k) { return Sg[m * N + k]; }, [&](int k, int cc) { return Fu[k * R + cc]; },
-                 [&](int m, int cc, double v) { SF[m * R + cc] = v; sfw[m * R + cc] = v; });   // SF_t = Sgb_t Fu_t
+                 [&](int m, int cc, double v) { SF[m * R + cc] = v; sfw[m * R + cc] = (lin_t)v; });   // SF_t = Sgb_t Fu_t
     __syncwarp();
     wmm_sym<R, N>(lane, [&](int, int) { return 0.0; }, [&](int a, int m) { return Fu[m * R + a]; },
                   [&](int m, int b) { return SF[m * R + b]; }, Cn);        // Cb <- Fu^T SF (lower, mirrored)
@@ -494,7 +494,7 @@ __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_seq_rev(int npad, int Tn
 // GAINS_MINOR: L, K, Lbar, Kbar sample-minor (small systems); KbarF (their second Kalman-cotangent part) is then zeroed.
 template <class DM, bool GAINS_MINOR = false>
 __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_contrib(const double* cst, size_t Sc, int npad, int Tn, const double* L, const double* K,
-                                                                const double* Cs, const double* SGB, const double* SGBI, const double* SFW,
+                                                                const double* Cs, const lin_t* SGB, const double* SGBI, const lin_t* SFW,
                                                                 const float* sums, double* gacc, double* Lbar, double* Kbar, double* KbarF,
                                                                 int ta = 0, int tb = -1) {
   using W = BigW<DM>;
@@ -554,23 +554,23 @@ __global__ void __launch_bounds__(32 * BW_WARPS) kw_cov_contrib(const double* cs
     }
     __syncwarp();
   };
-  auto load_sym_packed = [&](const double* src) {
+  auto load_sym_packed = [&](const auto* src) {
     for (int e = lane; e < N * N; e += 32) {
       const int i = e / N, j = e - i * N;
-      Nb[e] = src[sidx(i, j)];
+      Nb[e] = (double)src[sidx(i, j)];
     }
   };
   for (int t = t0; t < t1; ++t) {
     const float* sm = sums + (s * Tn + t) * (size_t)DM::SUMP;
     const double* cs = Cs + (s * Tn + t) * (size_t)DM::EC;
-    const double* sfw = SFW + (s * Tn + t) * (size_t)SR::NSF;
+    const lin_t* sfw = SFW + (s * Tn + t) * (size_t)SR::NSF;
     for (int e = lane; e < U * B; e += 32) Lt[e] = L[gi(t, DM::EL, e)];
     for (int e = lane; e < B * Y; e += 32) Kt[e] = K[gi(t, DM::EK, e)];
     for (int e = lane; e < R * R; e += 32) {
       const int i = e / R, j = e - i * R;
       Cm[e] = cs[sidx(i, j)];
     }
-    for (int e = lane; e < N * R; e += 32) SF[e] = sfw[e];
+    for (int e = lane; e < N * R; e += 32) SF[e] = (double)sfw[e];
     load_sym_packed(SGB + (s * Tn + t) * (size_t)SR::NSGB);
     __syncwarp();
     noise(true);

@@ -180,10 +180,20 @@ __device__ __forceinline__ void flush_acc_atomic(double* g, size_t stride, const
 // step t of a sample-minor array is one contiguous 256-byte line, copied with one cp.async.bulk issued by lane
 // (e mod 32); an optional float source copies one [CNTF]-float row per sample (lane = sample) from the
 // sample-major sums array.  The stage layout is [row][32 lanes] doubles (lane-strided, bank-conflict free).
+// Adjoint linearisation points that are written once and read once (Fu_t, (J_t, S'^-1_t), Sgb_t, SF_t) are stored in FP32: they
+// enter every adjoint step linearly (no accumulation of their rounding over time; measured: no change of any gradient error, see
+// DESIGN.md) and were 56 % of the FP64 workspace traffic of the per-sample kernels, two of which run at 70-90 % of HBM bandwidth.
+using lin_t = float;
 struct RingSrc {
-  const double* base;   // array base + first sample of the warp
+  const void* base;     // array base + first sample of the warp
   int rows;             // rows (elements) per time step
+  int f32;              // 0: rows of 32 doubles (256 B), 1: rows of 32 floats (128 B)
 };
+struct FView {
+  const float* p;
+  __device__ __forceinline__ double operator()(int e) const { return (double)p[(size_t)e * 32]; }
+};
+// Offsets inside a stage are counted in 128-byte units: a double row takes 2, a float row 1.
 template <int NSRC, int NST>
 struct StepRing {
   RingSrc src[NSRC];
@@ -194,10 +204,10 @@ struct StepRing {
   int fcnt;             // floats per row copy (multiple of 4)
   double* buf;          // [NST][stage_doubles]
   uint64_t* bars;       // [NST]
-  int lane, total_rows, stage_doubles;
+  int lane, total_units, stage_doubles;
   uint32_t phase_bits;
 
-  __host__ __device__ __forceinline__ static constexpr int stage_size(int total_rows, int fcnt) { return total_rows * 32 + (32 * fcnt + 1) / 2; }
+  __host__ __device__ __forceinline__ static constexpr int stage_size(int total_units, int fcnt) { return total_units * 16 + (32 * fcnt + 1) / 2; }
   __device__ __forceinline__ void init() {
     if (lane == 0) {
       for (int i = 0; i < NST; ++i) mbar_init(&bars[i], 1);
@@ -208,17 +218,19 @@ struct StepRing {
   }
   // Caller guarantees (by __syncwarp) that no lane still reads stage `st`.
   __device__ __forceinline__ void issue(int t, int st) {
-    double* dst = buf + (size_t)st * stage_doubles;
+    char* dst = reinterpret_cast<char*>(buf + (size_t)st * stage_doubles);
     fence_proxy_async();
-    if (lane == 0) mbar_expect_tx(&bars[st], (uint32_t)(total_rows * 256 + (fsrc ? 32 * fcnt * 4 : 0)));
-    int row = 0;
+    if (lane == 0) mbar_expect_tx(&bars[st], (uint32_t)(total_units * 128 + (fsrc ? 32 * fcnt * 4 : 0)));
+    int unit = 0;
     LQGK_UNROLL for (int i = 0; i < NSRC; ++i) {
+      const int u = src[i].f32 ? 1 : 2;
       for (int r = lane; r < src[i].rows; r += 32)
-        bulk_g2s(dst + (size_t)(row + r) * 32, src[i].base + ((size_t)t * src[i].rows + r) * Sc, 256, &bars[st]);
-      row += src[i].rows;
+        bulk_g2s(dst + (size_t)(unit + r * u) * 128, reinterpret_cast<const char*>(src[i].base) + ((size_t)t * src[i].rows + r) * Sc * (u * 4),
+                 (uint32_t)u * 128, &bars[st]);
+      unit += src[i].rows * u;
     }
     if (fsrc) {
-      float* fdst = reinterpret_cast<float*>(dst + (size_t)total_rows * 32);
+      float* fdst = reinterpret_cast<float*>(dst + (size_t)total_units * 128);
       bulk_g2s(fdst + lane * fcnt, fsrc + (size_t)lane * frow_stride + (size_t)t * fstep_stride, (uint32_t)fcnt * 4, &bars[st]);
     }
   }
@@ -227,12 +239,16 @@ struct StepRing {
     phase_bits ^= (1u << st);
     return buf + (size_t)st * stage_doubles;
   }
-  // view of source-row offset `row_off` for this lane
-  __device__ __forceinline__ WView view(const double* stage, int row_off) const {
-    return WView{const_cast<double*>(stage) + (size_t)row_off * 32 + lane, 32};
+  // this lane's view of a double source that starts `unit_off` units into the stage
+  __device__ __forceinline__ WView view(const double* stage, int unit_off) const {
+    return WView{const_cast<double*>(stage) + (size_t)unit_off * 16 + lane, 32};
+  }
+  // ... and of a float source
+  __device__ __forceinline__ FView fview(const double* stage, int unit_off) const {
+    return FView{reinterpret_cast<const float*>(stage + (size_t)unit_off * 16) + lane};
   }
   __device__ __forceinline__ const float* frow(const double* stage) const {
-    return reinterpret_cast<const float*>(stage + (size_t)total_rows * 32) + lane * fcnt;
+    return reinterpret_cast<const float*>(stage + (size_t)total_units * 16) + lane * fcnt;
   }
 };
 
@@ -263,7 +279,7 @@ constexpr int SEQ_NST = 3;   // ring depth of the sequential kernels
 // [t0, t1): time range of this launch; t0 > 0 continues from the C_{t0} an earlier launch saved in Cs (save_adj on).
 template <class DM>
 __global__ void __launch_bounds__(32) k_cov_fwd(const double* cst, size_t Sc, size_t tstride, int Tn, const double* L,
-                                                const double* K, int save_adj, double* Cs, double* FU, double* JS, double* J0,
+                                                const double* K, int save_adj, double* Cs, lin_t* FU, lin_t* JS, double* J0,
                                                 float* rec, int t0, int t1) {
   extern __shared__ __align__(128) double sm[];
   constexpr int B = DM::B, U = DM::U, Y = DM::Y, R = DM::R, D = DM::D;
@@ -279,7 +295,7 @@ __global__ void __launch_bounds__(32) k_cov_fwd(const double* cst, size_t Sc, si
   uint64_t* bars = reinterpret_cast<uint64_t*>(stage + SmemRecSink<DM>::FLOATS);
   for (int i = lane; i < SmemRecSink<DM>::FLOATS; i += 32) stage[i] = 0.f;
   __syncwarp();
-  Ring ring{{{L + s0, DM::EL}, {K + s0, DM::EK}}, Sc, nullptr, 0, 0, 0, ring_buf, bars, lane, ROWS, ROWS * 32, 0};
+  Ring ring{{{L + s0, DM::EL, 0}, {K + s0, DM::EK, 0}}, Sc, nullptr, 0, 0, 0, ring_buf, bars, lane, 2 * ROWS, ROWS * 32, 0};
   ring.init();
   for (int k = 0; k < SEQ_NST && t0 + k < t1; ++k) ring.issue(t0 + k, k);
   WView lc{lcp + lane, 32};
@@ -302,7 +318,7 @@ __global__ void __launch_bounds__(32) k_cov_fwd(const double* cst, size_t Sc, si
     if (tstride && t != t0) load_consts<C>(g.at(t), lc, C::NSEG);
     double Lt[U * B], Kt[B * Y];
     {
-      WView lv = ring.view(stg, 0), kv = ring.view(stg, DM::EL);
+      WView lv = ring.view(stg, 0), kv = ring.view(stg, 2 * DM::EL);
       LQGK_UNROLL for (int i = 0; i < U * B; ++i) Lt[i] = lv(i);
       LQGK_UNROLL for (int i = 0; i < B * Y; ++i) Kt[i] = kv(i);
     }
@@ -312,8 +328,8 @@ __global__ void __launch_bounds__(32) k_cov_fwd(const double* cst, size_t Sc, si
     CovFwd<DM>::step(lc, Lt, Kt, Cm, [&](int idx, float v) { sink.put(idx, v); },
                      [&](int which, int e, double v) {
                        if (save_adj) {
-                         if (which == 0) FU[((size_t)t * SR::NSF + e) * Sc + s] = v;
-                         else JS[((size_t)t * SR::NJS + e) * Sc + s] = v;
+                         if (which == 0) FU[((size_t)t * SR::NSF + e) * Sc + s] = (lin_t)v;
+                         else JS[((size_t)t * SR::NJS + e) * Sc + s] = (lin_t)v;
                        }
                      });
     sink.commit(t);
@@ -372,21 +388,21 @@ __global__ void k_trial_moments(const float* __restrict__ rec, const float* __re
 // [t0, t1): time range of this launch (walked downwards).  t1 < Tn starts from the cotangent an earlier launch left in
 // `carry` ([R*R][Sc]); t0 > 0 leaves its own there instead of finishing with the initial-condition term.
 template <class DM>
-__global__ void __launch_bounds__(32) k_cov_seq_rev(size_t Sc, int Tn, int N, const float* w, const double* FU, const double* JS,
-                                                    const double* J0, const float* sums, double* SGB, double* SGBI, double* SFW,
+__global__ void __launch_bounds__(32) k_cov_seq_rev(size_t Sc, int Tn, int N, const float* w, const lin_t* FU, const lin_t* JS,
+                                                    const double* J0, const float* sums, lin_t* SGB, double* SGBI, lin_t* SFW,
                                                     int t0, int t1, double* carry) {
   extern __shared__ __align__(128) double sm[];
   using SR = CovSeqRev<DM>;
   using Ring = StepRing<2, SEQ_NST>;
   constexpr int R = DM::R;
-  constexpr int ROWS = SR::NSF + SR::NJS, FCNT = DM::SUMP - DM::SUM_J;
-  constexpr int STAGE = Ring::stage_size(ROWS, FCNT);
+  constexpr int UNITS = SR::NSF + SR::NJS, FCNT = DM::SUMP - DM::SUM_J;      // float rows: one 128-byte unit each
+  constexpr int STAGE = Ring::stage_size(UNITS, FCNT);
   const int lane = threadIdx.x;
   const size_t s0 = (size_t)blockIdx.x * 32, s = s0 + lane;
   double* scp = sm + (size_t)SEQ_NST * STAGE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(scp + SR::SC_N * 32);
-  Ring ring{{{FU + s0, SR::NSF}, {JS + s0, SR::NJS}}, Sc, sums + s0 * Tn * DM::SUMP + DM::SUM_J, Tn * DM::SUMP, DM::SUMP, FCNT,
-            sm, bars, lane, ROWS, STAGE, 0};
+  Ring ring{{{FU + s0, SR::NSF, 1}, {JS + s0, SR::NJS, 1}}, Sc, sums + s0 * Tn * DM::SUMP + DM::SUM_J, Tn * DM::SUMP, DM::SUMP, FCNT,
+            sm, bars, lane, UNITS, STAGE, 0};
   ring.init();
   const int nsteps = t1 - t0;
   for (int k = 0; k < SEQ_NST && k < nsteps; ++k) ring.issue(t1 - 1 - k, k);
@@ -399,11 +415,11 @@ __global__ void __launch_bounds__(32) k_cov_seq_rev(size_t Sc, int Tn, int N, co
   for (int kk = 0; kk < nsteps; ++kk) {
     const int t = t1 - 1 - kk, st = kk % SEQ_NST;
     const double* stg = ring.wait(st);
-    WView fuv = ring.view(stg, 0), jsv = ring.view(stg, SR::NSF);
+    FView fuv = ring.fview(stg, 0), jsv = ring.fview(stg, SR::NSF);
     const float* fr = ring.frow(stg);
     SR::step([&](int e) { return fuv(e); }, [&](int e) { return jsv(e); }, [&](int idx) { return fr[idx - DM::SUM_J]; }, sw, sc, Cb,
-             [&](int e, double v) { SGB[((size_t)t * SR::NSGB + e) * Sc + s] = v; },
-             [&](int e, double v) { SFW[((size_t)t * SR::NSF + e) * Sc + s] = v; });
+             [&](int e, double v) { SGB[((size_t)t * SR::NSGB + e) * Sc + s] = (lin_t)v; },
+             [&](int e, double v) { SFW[((size_t)t * SR::NSF + e) * Sc + s] = (lin_t)v; });
     __syncwarp();
     if (kk + SEQ_NST < nsteps) ring.issue(t1 - 1 - (kk + SEQ_NST), st);
   }
@@ -422,13 +438,13 @@ __host__ __device__ constexpr bool contrib_merged() { return DM::N <= 6; }
 template <class DM, int PASS>
 __host__ __device__ constexpr int contrib_nst() {
   using SR = CovSeqRev<DM>;
-  constexpr int ROWS = DM::EL + DM::EK + DM::EC + SR::NSF + (PASS != 1 ? SR::NSGB : 0);
-  constexpr size_t two = sizeof(double) * ((size_t)2 * (ROWS * 32 + 16 * DM::SUM_J) + 2 * CovC<DM>::n * 32);
+  constexpr int UNITS = 2 * (DM::EL + DM::EK + DM::EC) + SR::NSF + (PASS != 1 ? SR::NSGB : 0);
+  constexpr size_t two = sizeof(double) * ((size_t)2 * (UNITS * 16 + 16 * DM::SUM_J) + 2 * CovC<DM>::n * 32);
   return two <= 200 * 1024 ? 2 : 1;
 }
 template <class DM, int PASS>
 __global__ void __launch_bounds__(32) k_cov_contrib(const double* cst, size_t Sc, int Tn, const double* L, const double* K,
-                                                    const double* Cs, const double* SGB, const double* SGBI, const double* SFW,
+                                                    const double* Cs, const lin_t* SGB, const double* SGBI, const lin_t* SFW,
                                                     const float* sums, double* acc, double* Lbar, double* Kbar, double* KbarF,
                                                     int ta, int tb) {
   extern __shared__ __align__(128) double sm[];
@@ -440,9 +456,9 @@ __global__ void __launch_bounds__(32) k_cov_contrib(const double* cst, size_t Sc
   constexpr int NSRC = P0 ? 5 : 4;
   constexpr int PAR_NST = contrib_nst<DM, PASS>();
   using Ring = StepRing<NSRC, PAR_NST>;
-  constexpr int ROWS = DM::EL + DM::EK + DM::EC + SR::NSF + (P0 ? SR::NSGB : 0);
+  constexpr int UNITS = 2 * (DM::EL + DM::EK + DM::EC) + SR::NSF + (P0 ? SR::NSGB : 0);   // 128-byte units (double rows: 2, float rows: 1)
   constexpr int FCNT = DM::SUM_J;   // = round4(N*N)
-  constexpr int STAGE = Ring::stage_size(ROWS, FCNT);
+  constexpr int STAGE = Ring::stage_size(UNITS, FCNT);
   const int lane = threadIdx.x;
   const size_t s0 = (size_t)blockIdx.x * 32, s = s0 + lane;
   double* lcp = sm + (size_t)PAR_NST * STAGE;
@@ -453,13 +469,13 @@ __global__ void __launch_bounds__(32) k_cov_contrib(const double* cst, size_t Sc
   const int t0 = min(tb, ta + q * per), t1 = min(tb, t0 + per);
   if (t0 >= t1) return;
   Ring ring;
-  ring.src[0] = {L + s0, DM::EL};
-  ring.src[1] = {K + s0, DM::EK};
-  ring.src[2] = {Cs + s0, DM::EC};
-  ring.src[3] = {SFW + s0, SR::NSF};
-  if constexpr (P0) ring.src[4] = {SGB + s0, SR::NSGB};
+  ring.src[0] = {L + s0, DM::EL, 0};
+  ring.src[1] = {K + s0, DM::EK, 0};
+  ring.src[2] = {Cs + s0, DM::EC, 0};
+  ring.src[3] = {SFW + s0, SR::NSF, 1};
+  if constexpr (P0) ring.src[4] = {SGB + s0, SR::NSGB, 1};
   ring.Sc = Sc; ring.fsrc = sums + s0 * Tn * DM::SUMP; ring.frow_stride = Tn * DM::SUMP; ring.fstep_stride = DM::SUMP;
-  ring.fcnt = FCNT; ring.buf = sm; ring.bars = bars; ring.lane = lane; ring.total_rows = ROWS; ring.stage_doubles = STAGE;
+  ring.fcnt = FCNT; ring.buf = sm; ring.bars = bars; ring.lane = lane; ring.total_units = UNITS; ring.stage_doubles = STAGE;
   ring.init();
   for (int k = 0; k < PAR_NST && t0 + k < t1; ++k) ring.issue(t0 + k, k);
   WView lc{lcp + lane, 32}, la{lap + lane, 32};
@@ -468,8 +484,8 @@ __global__ void __launch_bounds__(32) k_cov_contrib(const double* cst, size_t Sc
   for (int t = t0; t < t1; ++t) {
     const int st = (t - t0) % PAR_NST;
     const double* stg = ring.wait(st);
-    WView lv = ring.view(stg, 0), kv = ring.view(stg, DM::EL), cvw = ring.view(stg, DM::EL + DM::EK),
-          sfv = ring.view(stg, DM::EL + DM::EK + DM::EC), sgv = ring.view(stg, DM::EL + DM::EK + DM::EC + SR::NSF);
+    WView lv = ring.view(stg, 0), kv = ring.view(stg, 2 * DM::EL), cvw = ring.view(stg, 2 * (DM::EL + DM::EK));
+    FView sfv = ring.fview(stg, 2 * (DM::EL + DM::EK + DM::EC)), sgv = ring.fview(stg, 2 * (DM::EL + DM::EK + DM::EC) + SR::NSF);
     const float* fr = ring.frow(stg);
     double Cm[R * R], Lt[U * B], Kt[B * Y];
     LQGK_UNROLL for (int i = 0; i < U * B; ++i) Lt[i] = lv(i);
@@ -516,7 +532,7 @@ __global__ void __launch_bounds__(32) k_kf_rev(const double* cst, size_t Sc, int
   double* lcp = sm + (size_t)SEQ_NST * ROWS * 32;
   double* lap = lcp + C::n * 32;
   uint64_t* bars = reinterpret_cast<uint64_t*>(lap + C::n * 32);
-  Ring ring{{{Pkf + s0, DM::EP}, {Kbar + s0, DM::EK}, {KbarF + s0, DM::EK}}, Sc, nullptr, 0, 0, 0, sm, bars, lane, ROWS, ROWS * 32, 0};
+  Ring ring{{{Pkf + s0, DM::EP, 0}, {Kbar + s0, DM::EK, 0}, {KbarF + s0, DM::EK, 0}}, Sc, nullptr, 0, 0, 0, sm, bars, lane, 2 * ROWS, ROWS * 32, 0};
   ring.init();
   const int nsteps = t1 - t0;
   for (int k = 0; k < SEQ_NST && k < nsteps; ++k) ring.issue(t1 - 1 - k, k);
@@ -534,7 +550,7 @@ __global__ void __launch_bounds__(32) k_kf_rev(const double* cst, size_t Sc, int
       double P[B * B], Kb[B * Y];
       load_sym_ws<B>(ring.view(stg, 0), 0, P);
       {
-        WView kv = ring.view(stg, DM::EP), kv2 = ring.view(stg, DM::EP + DM::EK);
+        WView kv = ring.view(stg, 2 * DM::EP), kv2 = ring.view(stg, 2 * (DM::EP + DM::EK));
         LQGK_UNROLL for (int i = 0; i < B * Y; ++i) Kb[i] = kv(i) + kv2(i);
       }
       __syncwarp();
@@ -568,7 +584,7 @@ __global__ void __launch_bounds__(32) k_lqr_rev(const double* cst, size_t Sc, in
   double* lcp = sm + (size_t)SEQ_NST * ROWS * 32;
   double* lap = lcp + C::n * 32;
   uint64_t* bars = reinterpret_cast<uint64_t*>(lap + C::n * 32);
-  Ring ring{{{Sric + s0, DM::ES}, {L + s0, DM::EL}, {Lbar + s0, DM::EL}}, Sc, nullptr, 0, 0, 0, sm, bars, lane, ROWS, ROWS * 32, 0};
+  Ring ring{{{Sric + s0, DM::ES, 0}, {L + s0, DM::EL, 0}, {Lbar + s0, DM::EL, 0}}, Sc, nullptr, 0, 0, 0, sm, bars, lane, 2 * ROWS, ROWS * 32, 0};
   ring.init();
   for (int k = 0; k < SEQ_NST && k < Tn; ++k) ring.issue(k, k);
   WView lc{lcp + lane, 32}, la{lap + lane, 32};
@@ -584,7 +600,7 @@ __global__ void __launch_bounds__(32) k_lqr_rev(const double* cst, size_t Sc, in
       double S[B * B], Lt[U * B], Lb[U * B];
       load_sym_ws<B>(ring.view(stg, 0), 0, S);
       {
-        WView lv = ring.view(stg, DM::ES), bv = ring.view(stg, DM::ES + DM::EL);
+        WView lv = ring.view(stg, 2 * DM::ES), bv = ring.view(stg, 2 * (DM::ES + DM::EL));
         LQGK_UNROLL for (int i = 0; i < U * B; ++i) { Lt[i] = lv(i); Lb[i] = bv(i); }
       }
       __syncwarp();
@@ -620,14 +636,14 @@ template <class DM> constexpr size_t smem_cov_fwd() {
 }
 template <class DM> constexpr size_t smem_cov_seq_rev() {
   using SR = CovSeqRev<DM>;
-  return sizeof(double) * ((size_t)SEQ_NST * StepRing<2, SEQ_NST>::stage_size(SR::NSF + SR::NJS, DM::SUMP - DM::SUM_J) + SR::SC_N * 32) +
+  return sizeof(double) * ((size_t)SEQ_NST * StepRing<2, SEQ_NST>::stage_size(SR::NSF + SR::NJS, DM::SUMP - DM::SUM_J) + SR::SC_N * 32) +   // float rows
          sizeof(uint64_t) * SEQ_NST;
 }
 template <class DM, int PASS> constexpr size_t smem_cov_contrib() {
   using SR = CovSeqRev<DM>;
-  constexpr int ROWS = DM::EL + DM::EK + DM::EC + SR::NSF + (PASS != 1 ? SR::NSGB : 0);
+  constexpr int UNITS = 2 * (DM::EL + DM::EK + DM::EC) + SR::NSF + (PASS != 1 ? SR::NSGB : 0);
   constexpr int PAR_NST = contrib_nst<DM, PASS>();
-  return sizeof(double) * ((size_t)PAR_NST * StepRing<5, PAR_NST>::stage_size(ROWS, DM::SUM_J) + 2 * CovC<DM>::n * 32) +
+  return sizeof(double) * ((size_t)PAR_NST * StepRing<5, PAR_NST>::stage_size(UNITS, DM::SUM_J) + 2 * CovC<DM>::n * 32) +
          sizeof(uint64_t) * PAR_NST;
 }
 template <class DM> constexpr size_t smem_kf_rev() {

@@ -203,12 +203,12 @@ Plan make_plan(const LqgkDims& d, int mode, bool tv, size_t Sc) {
     }
     p.w = take(sizeof(float) * Sc * N);
     using SR = CovSeqRev<DM>;
-    p.FU = take(sizeof(double) * T * SR::NSF * Sc);
-    p.JS = take(sizeof(double) * T * SR::NJS * Sc);
+    p.FU = take(sizeof(lin_t) * T * SR::NSF * Sc);      // FP32 linearisation points (see lin_t)
+    p.JS = take(sizeof(lin_t) * T * SR::NJS * Sc);
     p.J0 = take(sizeof(double) * DM::R * DM::D * Sc);
-    p.SGB = take(sizeof(double) * T * SR::NSGB * Sc);
+    p.SGB = take(sizeof(lin_t) * T * SR::NSGB * Sc);
     p.SGBI = take(sizeof(double) * SR::NSGB * Sc);
-    p.SFW = take(sizeof(double) * T * SR::NSF * Sc);
+    p.SFW = take(sizeof(lin_t) * T * SR::NSF * Sc);
   }
   p.bytes = off;
   return p;
@@ -472,10 +472,10 @@ int run(const Call& c) {
         {
           ProfScope ps_(PK_COV_FWD, x2);
           if (warp_cov_p)
-            kw_cov_fwd<DM, true><<<wblk_p, 32 * BW_WARPS, sm_cov, x2>>>(D(p.cst), Sc, npad, Tn, D(p.L), D(p.K), 1, D(p.Cs), D(p.FU), D(p.JS), D(p.J0),
+            kw_cov_fwd<DM, true><<<wblk_p, 32 * BW_WARPS, sm_cov, x2>>>(D(p.cst), Sc, npad, Tn, D(p.L), D(p.K), 1, D(p.Cs), F(p.FU), F(p.JS), D(p.J0),
                                                                         F(p.rec), tb[g], tb[g + 1]);
           else
-            k_cov_fwd<DM><<<nblk, 32, sm_cov, x2>>>(D(p.cst), Sc, tstride, Tn, D(p.L), D(p.K), 1, D(p.Cs), D(p.FU), D(p.JS), D(p.J0), F(p.rec),
+            k_cov_fwd<DM><<<nblk, 32, sm_cov, x2>>>(D(p.cst), Sc, tstride, Tn, D(p.L), D(p.K), 1, D(p.Cs), F(p.FU), F(p.JS), D(p.J0), F(p.rec),
                                                     tb[g], tb[g + 1]);
           LQGK_LAUNCH_CHECK();
         }
@@ -528,10 +528,10 @@ int run(const Call& c) {
         {
           ProfScope ps_(PK_COV_REV, x1);
           if (warp_cov_p)
-            kw_cov_seq_rev<DM><<<wblk_p, 32 * BW_WARPS, sm_seq, x1>>>(npad, Tn, N, F(p.w), D(p.FU), D(p.JS), D(p.J0), F(p.sums), D(p.SGB), D(p.SGBI),
-                                                                     D(p.SFW), tb[g], tb[g + 1], D(p.carC));
+            kw_cov_seq_rev<DM><<<wblk_p, 32 * BW_WARPS, sm_seq, x1>>>(npad, Tn, N, F(p.w), F(p.FU), F(p.JS), D(p.J0), F(p.sums), F(p.SGB), D(p.SGBI),
+                                                                     F(p.SFW), tb[g], tb[g + 1], D(p.carC));
           else
-            k_cov_seq_rev<DM><<<nblk, 32, sm_seq, x1>>>(Sc, Tn, N, F(p.w), D(p.FU), D(p.JS), D(p.J0), F(p.sums), D(p.SGB), D(p.SGBI), D(p.SFW), tb[g],
+            k_cov_seq_rev<DM><<<nblk, 32, sm_seq, x1>>>(Sc, Tn, N, F(p.w), F(p.FU), F(p.JS), D(p.J0), F(p.sums), F(p.SGB), D(p.SGBI), F(p.SFW), tb[g],
                                                         tb[g + 1], D(p.carC));
           LQGK_LAUNCH_CHECK();
         }
@@ -541,8 +541,8 @@ int run(const Call& c) {
           ProfScope ps_(PK_COV_CONTRIB, x2);
           if (warp_cov_p) {
             int chunks = std::max(1, std::min((len + 3) / 4, (sm_count() * 12 + npad - 1) / npad));   // (segments run one after the other)
-            kw_cov_contrib<DM, true><<<dim3(wblk_p, chunks), 32 * BW_WARPS, sm_con, x2>>>(D(p.cst), Sc, npad, Tn, D(p.L), D(p.K), D(p.Cs), D(p.SGB),
-                                                                                       D(p.SGBI), D(p.SFW), F(p.sums), D(p.acc), D(p.Lbar),
+            kw_cov_contrib<DM, true><<<dim3(wblk_p, chunks), 32 * BW_WARPS, sm_con, x2>>>(D(p.cst), Sc, npad, Tn, D(p.L), D(p.K), D(p.Cs), F(p.SGB),
+                                                                                       D(p.SGBI), F(p.SFW), F(p.sums), D(p.acc), D(p.Lbar),
                                                                                        D(p.Kbar), D(p.KbarF), tb[g], tb[g + 1]);
             LQGK_LAUNCH_CHECK();
           } else {
@@ -552,17 +552,17 @@ int run(const Call& c) {
             if constexpr (contrib_merged<DM>()) {
               size_t smem = smem_cov_contrib<DM, 2>();
               if ((rc = set_smem<DM>((const void*)k_cov_contrib<DM, 2>, smem))) return rc;
-              k_cov_contrib<DM, 2><<<grid, 32, smem, x2>>>(D(p.cst), Sc, Tn, D(p.L), D(p.K), D(p.Cs), D(p.SGB), D(p.SGBI), D(p.SFW), F(p.sums),
+              k_cov_contrib<DM, 2><<<grid, 32, smem, x2>>>(D(p.cst), Sc, Tn, D(p.L), D(p.K), D(p.Cs), F(p.SGB), D(p.SGBI), F(p.SFW), F(p.sums),
                                                           D(p.acc), D(p.Lbar), D(p.Kbar), D(p.KbarF), tb[g], tb[g + 1]);
               LQGK_LAUNCH_CHECK();
             } else {
               size_t smem0 = smem_cov_contrib<DM, 0>(), smem1 = smem_cov_contrib<DM, 1>();
               if ((rc = set_smem<DM>((const void*)k_cov_contrib<DM, 0>, smem0))) return rc;
               if ((rc = set_smem<DM>((const void*)k_cov_contrib<DM, 1>, smem1))) return rc;
-              k_cov_contrib<DM, 0><<<grid, 32, smem0, x2>>>(D(p.cst), Sc, Tn, D(p.L), D(p.K), D(p.Cs), D(p.SGB), D(p.SGBI), D(p.SFW), F(p.sums),
+              k_cov_contrib<DM, 0><<<grid, 32, smem0, x2>>>(D(p.cst), Sc, Tn, D(p.L), D(p.K), D(p.Cs), F(p.SGB), D(p.SGBI), F(p.SFW), F(p.sums),
                                                            D(p.acc), D(p.Lbar), D(p.Kbar), D(p.KbarF), tb[g], tb[g + 1]);
               LQGK_LAUNCH_CHECK();
-              k_cov_contrib<DM, 1><<<grid, 32, smem1, x2>>>(D(p.cst), Sc, Tn, D(p.L), D(p.K), D(p.Cs), D(p.SGB), D(p.SGBI), D(p.SFW), F(p.sums),
+              k_cov_contrib<DM, 1><<<grid, 32, smem1, x2>>>(D(p.cst), Sc, Tn, D(p.L), D(p.K), D(p.Cs), F(p.SGB), D(p.SGBI), F(p.SFW), F(p.sums),
                                                            D(p.acc), D(p.Lbar), D(p.Kbar), D(p.KbarF), tb[g], tb[g + 1]);
               LQGK_LAUNCH_CHECK();
             }
@@ -641,14 +641,14 @@ int run(const Call& c) {
       if ((rc = set_smem<DM>((const void*)kw_cov_fwd<DM, true>, smem))) return rc;
       ProfScope ps_(PK_COV_FWD, st);
       kw_cov_fwd<DM, true><<<wblk, 32 * BW_WARPS, smem, st>>>(D(p.cst), Sc, npad, Tn, D(p.L), D(p.K), vjp, vjp ? D(p.Cs) : nullptr,
-                                                              vjp ? D(p.FU) : nullptr, vjp ? D(p.JS) : nullptr, vjp ? D(p.J0) : nullptr, F(p.rec));
+                                                              vjp ? F(p.FU) : nullptr, vjp ? F(p.JS) : nullptr, vjp ? D(p.J0) : nullptr, F(p.rec));
       LQGK_LAUNCH_CHECK();
     } else {
       size_t smem = smem_cov_fwd<DM>();
       if ((rc = set_smem<DM>((const void*)k_cov_fwd<DM>, smem))) return rc;
       ProfScope ps_(PK_COV_FWD, st);
-      k_cov_fwd<DM><<<nblk, 32, smem, st>>>(D(p.cst), Sc, tstride, Tn, D(p.L), D(p.K), vjp, vjp ? D(p.Cs) : nullptr, vjp ? D(p.FU) : nullptr,
-                                            vjp ? D(p.JS) : nullptr, vjp ? D(p.J0) : nullptr, F(p.rec), 0, Tn);
+      k_cov_fwd<DM><<<nblk, 32, smem, st>>>(D(p.cst), Sc, tstride, Tn, D(p.L), D(p.K), vjp, vjp ? D(p.Cs) : nullptr, vjp ? F(p.FU) : nullptr,
+                                            vjp ? F(p.JS) : nullptr, vjp ? D(p.J0) : nullptr, F(p.rec), 0, Tn);
       LQGK_LAUNCH_CHECK();
     }
     const int RT = std::min((N + 31) / 32, trial_rt_max<DM>());
@@ -695,15 +695,15 @@ int run(const Call& c) {
       if ((rc = set_smem<DM>((const void*)kw_cov_contrib<DM, true>, smemc))) return rc;
       {
         ProfScope ps_(PK_COV_REV, st);
-        kw_cov_seq_rev<DM><<<wblk, 32 * BW_WARPS, smem, st>>>(npad, Tn, N, F(p.w), D(p.FU), D(p.JS), D(p.J0), F(p.sums), D(p.SGB), D(p.SGBI),
-                                                             D(p.SFW));
+        kw_cov_seq_rev<DM><<<wblk, 32 * BW_WARPS, smem, st>>>(npad, Tn, N, F(p.w), F(p.FU), F(p.JS), D(p.J0), F(p.sums), F(p.SGB), D(p.SGBI),
+                                                             F(p.SFW));
         LQGK_LAUNCH_CHECK();
       }
       {
         int chunks = std::max(1, std::min((Tn + 3) / 4, (sm_count() * 12 + npad - 1) / npad));
         ProfScope ps_(PK_COV_CONTRIB, st);
-        kw_cov_contrib<DM, true><<<dim3(wblk, chunks), 32 * BW_WARPS, smemc, st>>>(D(p.cst), Sc, npad, Tn, D(p.L), D(p.K), D(p.Cs), D(p.SGB),
-                                                                                  D(p.SGBI), D(p.SFW), F(p.sums), D(p.acc), D(p.Lbar), D(p.Kbar),
+        kw_cov_contrib<DM, true><<<dim3(wblk, chunks), 32 * BW_WARPS, smemc, st>>>(D(p.cst), Sc, npad, Tn, D(p.L), D(p.K), D(p.Cs), F(p.SGB),
+                                                                                  D(p.SGBI), F(p.SFW), F(p.sums), D(p.acc), D(p.Lbar), D(p.Kbar),
                                                                                   D(p.KbarF));
         LQGK_LAUNCH_CHECK();
       }
@@ -712,7 +712,7 @@ int run(const Call& c) {
       size_t smem = smem_cov_seq_rev<DM>();
       if ((rc = set_smem<DM>((const void*)k_cov_seq_rev<DM>, smem))) return rc;
       ProfScope ps_(PK_COV_REV, st);
-      k_cov_seq_rev<DM><<<nblk, 32, smem, st>>>(Sc, Tn, N, F(p.w), D(p.FU), D(p.JS), D(p.J0), F(p.sums), D(p.SGB), D(p.SGBI), D(p.SFW), 0, Tn,
+      k_cov_seq_rev<DM><<<nblk, 32, smem, st>>>(Sc, Tn, N, F(p.w), F(p.FU), F(p.JS), D(p.J0), F(p.sums), F(p.SGB), D(p.SGBI), F(p.SFW), 0, Tn,
                                                 D(p.carC));
       LQGK_LAUNCH_CHECK();
     }
@@ -725,7 +725,7 @@ int run(const Call& c) {
         size_t smem = smem_cov_contrib<DM, 2>();
         if ((rc = set_smem<DM>((const void*)k_cov_contrib<DM, 2>, smem))) return rc;
         ProfScope ps_(PK_COV_CONTRIB, st);
-        k_cov_contrib<DM, 2><<<grid, 32, smem, st>>>(D(p.cst), Sc, Tn, D(p.L), D(p.K), D(p.Cs), D(p.SGB), D(p.SGBI), D(p.SFW), F(p.sums),
+        k_cov_contrib<DM, 2><<<grid, 32, smem, st>>>(D(p.cst), Sc, Tn, D(p.L), D(p.K), D(p.Cs), F(p.SGB), D(p.SGBI), F(p.SFW), F(p.sums),
                                                     D(p.acc), D(p.Lbar), D(p.Kbar), D(p.KbarF), 0, Tn);
         LQGK_LAUNCH_CHECK();
       } else {
@@ -736,13 +736,13 @@ int run(const Call& c) {
         dep(st, a1);                               // cov_seq_rev done -> the two contraction passes run side by side
         {
           ProfScope ps_(PK_COV_CONTRIB, st);
-          k_cov_contrib<DM, 0><<<grid, 32, smem0, st>>>(D(p.cst), Sc, Tn, D(p.L), D(p.K), D(p.Cs), D(p.SGB), D(p.SGBI), D(p.SFW),
+          k_cov_contrib<DM, 0><<<grid, 32, smem0, st>>>(D(p.cst), Sc, Tn, D(p.L), D(p.K), D(p.Cs), F(p.SGB), D(p.SGBI), F(p.SFW),
                                                        F(p.sums), D(p.acc), D(p.Lbar), D(p.Kbar), D(p.KbarF), 0, Tn);
           LQGK_LAUNCH_CHECK();
         }
         {
           ProfScope ps_(PK_COV_CONTRIB, a1);
-          k_cov_contrib<DM, 1><<<grid, 32, smem1, a1>>>(D(p.cst), Sc, Tn, D(p.L), D(p.K), D(p.Cs), D(p.SGB), D(p.SGBI), D(p.SFW),
+          k_cov_contrib<DM, 1><<<grid, 32, smem1, a1>>>(D(p.cst), Sc, Tn, D(p.L), D(p.K), D(p.Cs), F(p.SGB), D(p.SGBI), F(p.SFW),
                                                        F(p.sums), D(p.acc), D(p.Lbar), D(p.Kbar), D(p.KbarF), 0, Tn);
           LQGK_LAUNCH_CHECK();
         }

@@ -2,6 +2,7 @@
 // lqgk_stages.h, lqgk_pack.h) sequentially on the CPU, exporting the same C ABI as liblqgk.so but on HOST
 // pointers.  Lets `pytest -m "not gpu"` check the kernel mathematics (forward and adjoint) against the oracle
 // without a GPU.  It is never loaded by the product path (lqg_b200 refuses anything but the CUDA library).
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -98,6 +99,9 @@ int run(const LqgkDims& d, const LqgkSpec* act, const LqgkSpec* dyn, const LqgkM
     RecSink sink{rec.data() + (size_t)s * Tn * DM::REC, DM::REC, rec.data() + (size_t)s * Tn * DM::REC};
     cov_fwd_body<DM>(g, WView{lc.data(), 1}, Tn, V(Lw, s), V(Kw, s), want_grad, V(Cw, s), V(FUw, s), V(JSw, s), V(J0w, s), sink);
   }
+  // the library stores these adjoint linearisation points in FP32 (lin_t in lqgk_kernels.cuh): mirror the rounding
+  for (auto& v : FUw) v = (double)(float)v;
+  for (auto& v : JSw) v = (double)(float)v;
   using TR = Trial<DM>;
   constexpr int D = DM::D, R = DM::R;
   const float* x_all = x_tm;
@@ -141,6 +145,8 @@ int run(const LqgkDims& d, const LqgkSpec* act, const LqgkSpec* dyn, const LqgkM
     {
       std::vector<double> sc(SR::SC_N + 8);
       cov_seq_rev_body<DM>(Tn, sw, V(FUw, s), V(JSw, s), V(J0w, s), src, WView{sc.data(), 1}, V(SGBw, s), V(SGBIw, s), V(SFw, s));
+      for (size_t e = s; e < SGBw.size(); e += Sc) SGBw[e] = (double)(float)SGBw[e];   // (FP32 storage, as in the library)
+      for (size_t e = s; e < SFw.size(); e += Sc) SFw[e] = (double)(float)SFw[e];
       load_consts<CovC<DM>>(g.at(0), WView{lc.data(), 1}, CovC<DM>::NSEG);
       auto ct = [&](int t, int e, double v) { CTw[((size_t)t * NC + e) * Sc + s] = v; };
       cov_contrib_body<DM, 0>(WView{lc.data(), 1}, 0, Tn, V(Lw, s), V(Kw, s), V(Cw, s), V(SGBw, s), V(SGBIw, s), V(SFw, s), src,
