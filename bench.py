@@ -243,6 +243,35 @@ def bench_c2(dev, barrier, reps=10):
     return ms, ms_graph
 
 
+def bench_c2_sdn(dev, reps=5):
+    """Config c2 as BASELINE.json words it ("... with signal-dependent noise"): the c2 model with per-channel control- and
+    state-dependent noise (System.log_likelihood_sdn; an EXTENSION -- the reference has no signal-dependent noise, parity is
+    unpinned).  The covariance pass is per (condition x trial) here, FP64, one thread per system; the gradient
+    w.r.t. 5 shared + 6 per-condition + 2 noise parameters is a batched central difference (27 parameter vectors x 6 conditions
+    in one launch set).  Rank 0 only (no sharding: 240 systems).  Returns ms per value+gradient evaluation and per value."""
+    from lqg_b200.control import sdn
+    from lqg_b200.tracking import SubjectiveActor
+    sig = [8.5, 9.7, 11.8, 19.9, 28.5, 51.6]
+    T, N = 1200, 20
+    x = torch.stack([make_data_gpu(N, T, dev, seed=c, sigma_target=s_t, action_cost=1.0, sigma_cursor=6.0) for c, s_t in enumerate(sig)])
+    nc = len(sig)
+
+    def total(Th):   # Th[P', 13] = [5 shared | 6 sigma_target | signal_dep_noise, obs_dep_noise] -> summed ll per parameter vector
+        Pn = Th.shape[0]
+        rep = lambda v: v.repeat_interleave(nc)                           # (parameter vector, condition) pairs as the sample axis
+        m = SubjectiveActor(dim=2, T=T, device=dev, dtype=torch.float64, action_cost=rep(Th[:, 0]), action_variability=rep(Th[:, 1]),
+                            subj_noise=rep(Th[:, 2]), subj_vel_noise=rep(Th[:, 3]), sigma_cursor=rep(Th[:, 4]),
+                            sigma_target=Th[:, 5:5 + nc].reshape(-1))
+        ll = m.log_likelihood_sdn(x.repeat(Pn, 1, 1, 1), signal_dep_noise=rep(Th[:, 11]), obs_dep_noise=rep(Th[:, 12]))
+        return ll.reshape(Pn, nc, N).sum((1, 2))
+
+    th = torch.tensor([1.0, 0.5, 1.0, 0.5, 6.0] + sig + [20.0, 0.2], device=dev, dtype=torch.float64)
+    ms_grad, (v, g) = timed(lambda: sdn.value_and_grad_fd(total, th), reps, 2, lambda: torch.cuda.synchronize())
+    ms_val, v1 = timed(lambda: total(th[None]), reps, 2, lambda: torch.cuda.synchronize())
+    assert torch.isfinite(v) and torch.isfinite(g).all() and torch.allclose(v1[0], v)
+    return ms_grad, ms_val
+
+
 def bench_c5(dev, barrier, chains=4096, N=100, T=1200, reps=5):
     """Config c5 of BASELINE.json without numpyro (not installable): the work of ONE leapfrog step of 4,096 lock-step chains =
     one fused log-likelihood + gradient evaluation of 4,096 parameter vectors on the c3 data, chains sharded over the ranks
@@ -507,6 +536,17 @@ def run_ours(args):
                           "value": 1e3 / c5_g, "unit": "leapfrog-equivalents/s", "ms_per_eval": c5_g, "ms_per_eval_eager": c5_ms,
                           "chains_per_gpu": 4096 // world,
                           "note": "ms_per_eval = the evaluation replayed from a CUDA graph (lqg_b200.graphs); eager = launched op by op"})
+
+        if rank == 0:
+            sdn_grad_ms, sdn_val_ms = bench_c2_sdn(dev)
+            secondary.append({"workload": "c2 with signal-dependent noise (EXTENSION, parity unpinned by the reference): SubjectiveActor dim=2 "
+                                          "+ per-channel control-/state-dependent noise, 6 conditions x 20 trials x T=1200, per-trial FP64 "
+                                          "covariance pass (k_sdn_loglik), value + central-difference gradient w.r.t. 13 parameters "
+                                          "(27 x 6 systems batched), public API, one GPU",
+                              "value": 6 * 20 / (sdn_grad_ms * 1e-3), "unit": "trial-evals/s", "ms_per_eval": sdn_grad_ms,
+                              "ms_per_value_only": sdn_val_ms})
+        if world > 1:
+            dist.barrier()
 
     if rank == 0:
         # ---------------- roofline of the dominant kernel + whole step

@@ -151,6 +151,24 @@ typedef struct {
 int lqgk_sdn_gains_f64(const LqgkSdnDims* dims, const LqgkSdnSpec* spec, double* L_out, double* K_out, double* cost_out,
                        void* stream);
 
+/* lqgk_sdn_loglik_*: log-likelihood under signal-dependent noise -- the reference's experimenter-side filter
+ *   (lqg/system.py:142-248, same filter-form conventions as lqg/system.py:110-124) extended by multiplicative noise
+ *     x_{t+1} = A x_t + B u_t + V eps + sum_i eps'_i C_i u_t ,    y_t = F x_{t+1} + W eta + sum_j eta'_j D_j x_{t+1}
+ *   with moment-matched Gaussian predictive distributions (oracle/sdn_np.py: sdn_log_likelihood).  EXTENSION: the reference
+ *   has no such code, parity is pinned by Monte Carlo and by the exact reduction to lqgk_loglik_fwd_* when nc = nd = 0.
+ *   The gains L[S][T][u][b], K[S][T][b][y] are inputs (lqgk_lqr_backward_* / lqgk_kf_forward_* of the actor's model, or any
+ *   other solver).  noise->C: [nc][x][u], noise->D: [nd][y][x] per sample (sample_stride 0 = shared), nc, nd <= 4.  The
+ *   covariance recursion is per (sample x trial) here -- one FP64 system per thread.  Time-invariant specs, joint dim <= 12.
+ *   Output ll[S][N].                                                                                                      */
+typedef struct {
+  LqgkMat C, D;
+  int32_t nc, nd;
+} LqgkSdnNoise;
+int lqgk_sdn_loglik_f32(const LqgkDims* dims, const LqgkSpec* actor, const LqgkSpec* dynamics, const LqgkSdnNoise* noise,
+                        const float* L, const float* K, const float* x_tm, float* ll_out, void* stream);
+int lqgk_sdn_loglik_f64(const LqgkDims* dims, const LqgkSpec* actor, const LqgkSpec* dynamics, const LqgkSdnNoise* noise,
+                        const double* L, const double* K, const float* x_tm, double* ll_out, void* stream);
+
 /* ---- helpers ------------------------------------------------------------------------------------------ */
 /* x[N][T+1][d] (f32 or f64, trial-major as in the reference) -> x_tm[T+1][N][d] float. */
 int lqgk_pack_obs_f32(int32_t N, int32_t T1, int32_t d, const float* x, float* x_tm, void* stream);

@@ -82,6 +82,10 @@ class LqgkSdnSpec(C.Structure):
     _fields_ = [(k, LqgkMat) for k in ("A", "B", "H", "C", "D", "Q", "R", "Qf", "Om_xi", "Om_omega", "Sigma1", "xhat1")]
 
 
+class LqgkSdnNoise(C.Structure):
+    _fields_ = [("C", LqgkMat), ("D", LqgkMat), ("nc", C.c_int32), ("nd", C.c_int32)]
+
+
 class Library:
     """One loaded implementation of the C ABI."""
 
@@ -313,6 +317,35 @@ class Library:
                                          C.c_void_p(cost.data_ptr()), C.c_void_p(stream))
         self._check(rc, "lqgk_sdn_gains_f64")
         return L, K, cost
+
+    def sdn_loglik(self, dims, actor, dyn, L, K, x_tm, C_noise=None, D_noise=None, stream=0):
+        """Log-likelihood under signal-dependent noise (extension, include/lqgk.h: lqgk_sdn_loglik_*).  actor / dyn: base
+        matrices as for loglik_fwd (time-invariant), L[S,T,u,b], K[S,T,b,y]: gains, C_noise[S?,nc,x,u], D_noise[S?,nd,y,x]:
+        multiplicative-noise matrices (None = none; a leading sample axis is optional).  Returns ll[S,N]."""
+        dt, dev = actor["A"].dtype, actor["A"].device
+        S, T = dims.S, dims.T
+        self._check_obs(dims, x_tm)
+        sa, sd = self._spec(actor, S, T, ACTOR_KEYS), self._spec(dyn, S, T, DYN_KEYS)
+        keep = [L.to(dt).contiguous(), K.to(dt).contiguous()]
+        assert tuple(keep[0].shape) == (S, T, dims.u, dims.b) and tuple(keep[1].shape) == (S, T, dims.b, dims.y)
+        nz = LqgkSdnNoise()
+        for name, v, shp in (("C", C_noise, (dims.x, dims.u)), ("D", D_noise, (dims.y, dims.x))):
+            if v is None or v.numel() == 0:
+                setattr(nz, name, LqgkMat(None, 0, 0))
+                setattr(nz, "n" + name.lower(), 0)
+                continue
+            v = v.to(dt).contiguous()
+            keep.append(v)
+            assert tuple(v.shape[-2:]) == shp and v.dim() in (3, 4), (name, tuple(v.shape))
+            ss = v.stride(0) if v.dim() == 4 and v.shape[0] == S and S > 1 else 0
+            setattr(nz, name, LqgkMat(v.data_ptr(), ss, 0))
+            setattr(nz, "n" + name.lower(), v.shape[-3])
+        ll = torch.empty((S, dims.N), dtype=dt, device=dev)
+        fn = getattr(self.lib, "lqgk_sdn_loglik_" + self._suffix(dt))
+        self._check(fn(C.byref(dims), C.byref(sa), C.byref(sd), C.byref(nz), C.c_void_p(keep[0].data_ptr()),
+                       C.c_void_p(keep[1].data_ptr()), C.c_void_p(x_tm.data_ptr()), C.c_void_p(ll.data_ptr()),
+                       C.c_void_p(stream)), "lqgk_sdn_loglik")
+        return ll
 
     def init(self, max_sample_slices: int = 1):
         """Pre-create the library's internal streams / events (needed before capturing calls into a CUDA graph)."""

@@ -31,3 +31,47 @@ def solve(A, B, H, Q, R, Om_xi, Om_omega, Sigma1, xhat1, T: int, C: Optional[Seq
                 D=None if D is None else f(D if torch.is_tensor(D) else torch.stack(list(D))))
     L, K, cost = abi.load_library().sdn_gains(mats, T, sweeps, stream=torch.cuda.current_stream(dev).cuda_stream)
     return SDNGains(L, K, cost)
+
+
+# ------------------------------------------------------------------------------------------------ likelihood side
+def channel_noise(system, scale, kind: str) -> torch.Tensor:
+    """Per-channel proportional noise matrices for ``System.log_likelihood_sdn`` in the reference's filter-form model
+    (lqg/system.py:110-124 plus the multiplicative terms, oracle/sdn_np.py):
+
+    * ``kind="control"``: ``C_i = scale * B_d[:, i] e_i^T`` (one per control dimension): the process noise injected through
+      control channel i is proportional to ``u_i`` -- the motor noise of Todorov (2005) along the plant's own input map;
+    * ``kind="observation"``: ``D_j = scale * e_j e_j^T F_d`` (one per observation channel): the noise of observation j is
+      proportional to the observed signal ``(F_d x)_j`` itself.
+
+    ``scale``: scalar or batched like the model parameters ([S]).  Returns [(S,) nc, x, u] / [(S,) nd, y, x]."""
+    dyn = system.dynamics
+    Bd, Fd = dyn.B[..., 0, :, :], dyn.F[..., 0, :, :]
+    scale = torch.as_tensor(scale, dtype=Bd.dtype, device=Bd.device)
+    if kind == "control":
+        u = Bd.shape[-1]
+        mats = [Bd * torch.nn.functional.one_hot(torch.tensor(i), u).to(Bd) for i in range(u)]            # B_d[:, i] e_i^T
+    elif kind == "observation":
+        y = Fd.shape[-2]
+        mats = [Fd * torch.nn.functional.one_hot(torch.tensor(j), y).to(Fd)[:, None] for j in range(y)]   # e_j e_j^T F_d
+    else:
+        raise ValueError(kind)
+    M = torch.stack(mats, -3)
+    if scale.dim() == 1 and M.dim() == 3:
+        M = M.unsqueeze(0)
+    return M * scale.reshape(scale.shape + (1, 1, 1)) if scale.dim() else M * scale
+
+
+def value_and_grad_fd(fn, theta: torch.Tensor, rel_step: float = 1e-5, abs_step: float = 1e-7):
+    """Value and gradient of ``fn`` at ``theta[P]`` by central differences evaluated as ONE batched call:
+    ``fn(Theta[2P+1, P]) -> [2P+1]`` (e.g. the summed log-likelihood of a model built from batched parameters).  The
+    signal-dependent-noise likelihood has no adjoint kernel; its evaluations are latency-bound and the parameter-sample axis
+    of the kernels is free, so the 2P+1 evaluations cost about as much as one.  FP64 recommended."""
+    theta = theta.detach()
+    P = theta.numel()
+    h = (theta.abs() * rel_step).clamp_min(abs_step)
+    Theta = theta.repeat(2 * P + 1, 1)
+    idx = torch.arange(P, device=theta.device)
+    Theta[1 + idx, idx] += h
+    Theta[1 + P + idx, idx] -= h
+    f = fn(Theta)
+    return f[0], (f[1:1 + P] - f[1 + P:]) / (2 * h)

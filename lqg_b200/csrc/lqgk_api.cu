@@ -172,6 +172,33 @@ int simulate(const LqgkDims* d, const LqgkSpec* act, const LqgkSpec* dyn, const 
 }
 }  // namespace
 
+namespace {
+int sdn_loglik(const LqgkDims* d, const LqgkSpec* act, const LqgkSpec* dyn, const LqgkSdnNoise* nz, const void* L, const void* K,
+               const float* x_tm, void* ll_out, bool f64, void* stream) {
+  g_launches = 0;
+  if (!d || !act || !dyn || !L || !K || !x_tm || !ll_out) return LQGK_E_INVALID;
+  if (d->S <= 0 || d->N <= 0 || d->T <= 0 || d->d <= 0 || d->d > d->x || d->x_sample_stride < 0) return LQGK_E_INVALID;
+  const LqgkMat* need[] = {&act->A, &act->B, &act->F, &dyn->A, &dyn->B, &dyn->F, &dyn->V, &dyn->W};
+  for (auto m : need) {
+    if (!m->ptr) return LQGK_E_INVALID;
+    if (m->time_stride != 0) return LQGK_E_UNSUPPORTED;
+  }
+  SdnLikArgs a{};
+  a.act = *act; a.dyn = *dyn; a.L = L; a.K = K; a.x_tm = x_tm; a.x_sample_stride = d->x_sample_stride; a.ll_out = ll_out;
+  a.S = d->S; a.N = d->N; a.T = d->T;
+  if (nz) {
+    if (nz->nc < 0 || nz->nd < 0 || nz->nc > SDN_MAX_TERMS || nz->nd > SDN_MAX_TERMS) return LQGK_E_INVALID;
+    if ((nz->nc > 0 && !nz->C.ptr) || (nz->nd > 0 && !nz->D.ptr)) return LQGK_E_INVALID;
+    a.C = nz->C; a.D = nz->D; a.nc = nz->nc; a.nd = nz->nd;
+  }
+#define LQGK_CASE(X, B, U, Y, DD) \
+  if (d->x == X && d->b == B && d->u == U && d->y == Y && d->d == DD) return Runner<X, B, U, Y, DD>::run_sdn_loglik(a, f64, (cudaStream_t)stream);
+  LQGK_FOR_EACH_DIMS(LQGK_CASE)
+#undef LQGK_CASE
+  return LQGK_E_UNSUPPORTED;
+}
+}  // namespace
+
 // FMA-saturating micro-kernels: the measured FP32 / FP64 CUDA-core peaks used as roofline denominators.
 template <class T>
 __global__ void k_peak_fma(int iters, T* sink) {
@@ -221,6 +248,15 @@ int lqgk_sdn_gains_f64(const LqgkSdnDims* d, const LqgkSdnSpec* sp, double* L_ou
   LQGK_FOR_EACH_DIMS(LQGK_CASE)
 #undef LQGK_CASE
   return LQGK_E_UNSUPPORTED;
+}
+
+int lqgk_sdn_loglik_f32(const LqgkDims* dims, const LqgkSpec* actor, const LqgkSpec* dynamics, const LqgkSdnNoise* noise, const float* L,
+                        const float* K, const float* x_tm, float* ll_out, void* stream) {
+  return sdn_loglik(dims, actor, dynamics, noise, L, K, x_tm, ll_out, false, stream);
+}
+int lqgk_sdn_loglik_f64(const LqgkDims* dims, const LqgkSpec* actor, const LqgkSpec* dynamics, const LqgkSdnNoise* noise, const double* L,
+                        const double* K, const float* x_tm, double* ll_out, void* stream) {
+  return sdn_loglik(dims, actor, dynamics, noise, L, K, x_tm, ll_out, true, stream);
 }
 
 int lqgk_lqr_backward_f32(const LqgkDims* dims, const LqgkSpec* actor, double eps, float* L_out, float* l_out, float* H_out,

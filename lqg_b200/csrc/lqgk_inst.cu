@@ -35,4 +35,18 @@ int Runner<LQGK_INST_X, LQGK_INST_B, LQGK_INST_U, LQGK_INST_Y, LQGK_INST_D>::run
   return LQGK_OK;
 #endif
 }
+template <>
+int Runner<LQGK_INST_X, LQGK_INST_B, LQGK_INST_U, LQGK_INST_Y, LQGK_INST_D>::run_sdn_loglik(const SdnLikArgs& a, bool f64, cudaStream_t st) {
+#if defined(LQGK_BIG)
+  (void)a; (void)f64; (void)st;
+  return LQGK_E_UNSUPPORTED;
+#else
+  const size_t total = (size_t)a.S * a.N;
+  const unsigned blocks = (unsigned)((total + 63) / 64);
+  if (f64) k_sdn_loglik<DMI, double><<<blocks, 64, 0, st>>>(a);
+  else k_sdn_loglik<DMI, float><<<blocks, 64, 0, st>>>(a);
+  LQGK_LAUNCH_CHECK();
+  return LQGK_OK;
+#endif
+}
 }  // namespace lqgk

@@ -803,6 +803,7 @@ struct Runner {
   static int run_f64(const Call& c);
   static size_t plan_bytes(const LqgkDims& d, int mode, int32_t max_chunk);
   static int run_sdn(const SdnArgs& a, cudaStream_t st);   // signal-dependent-noise gains (b, u, y of this tuple)
+  static int run_sdn_loglik(const SdnLikArgs& a, bool f64, cudaStream_t st);   // likelihood under signal-dependent noise
 };
 
 }  // namespace lqgk

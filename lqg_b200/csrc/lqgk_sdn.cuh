@@ -10,7 +10,9 @@
 // sequences are the only O(T) state: the backward pass reads K_t and writes L_t, the forward pass reads L_t and writes K_t,
 // both directly in the caller's output arrays L[S][T][u][b], K[S][T][b][y] (FP64).
 #pragma once
+#include "../../include/lqgk.h"
 #include "lqgk_core.h"
+#include "lqgk_pack.h"
 
 namespace lqgk {
 
@@ -180,6 +182,177 @@ struct Sdn {
   }
 };
 
+// ================================================================================================
+// Likelihood under signal-dependent noise (EXTENSION, parity unpinned by the reference; spec: oracle/sdn_np.py
+// `sdn_conditional_moments` / `sdn_log_likelihood`).  The reference's experimenter-side filter (lqg/system.py:142-248) in
+// the reference's own filter-form conventions plus the multiplicative terms
+//     x_{t+1} = A x_t + B u_t + V eps + sum_i eps'_i C_i u_t ,   y_t = F x_{t+1} + W eta + sum_j eta'_j D_j x_{t+1} ,
+// with the gains (L_t, K_t) given.  The predictive covariance now depends on the second moment of the conditioned state,
+// i.e. on the running mean of the TRIAL: one dense system per (parameter sample x trial), carried in the reduced
+// condition-then-predict form of the main path (c = E[unobserved | x_0..t], C = its covariance), all FP64:
+//     Z2 = C + c c^T ;  U2 = L Z2[xhat,xhat] L^T ;  g_i = [C_i ; K F_d C_i] ;  h_j = K D_j
+//     mu' = F [x_t ; c] ;  Sig' = F[:,u] C F[:,u]^T + N + sum_i g_i U2 g_i^T ;  Sig'[xhat,xhat] += sum_j h_j (Sig'[x,x] + mu'_x mu'_x^T) h_j^T
+//     e = x_{t+1} - mu'[o] ;  ll += log N(e; 0, Sig'[o,o]) ;  J = Sig'[u,o] Sig'[o,o]^-1 ;  c = mu'[u] + J e ;  C = Sig'[u,u] - J Sig'[o,o] J^T
+// With nc = nd = 0 this is the main path's recursion (same joint_F / joint_N / predict / condition code) with the per-trial
+// part in FP64 instead of FP32.
+constexpr int SDN_MAX_TERMS = 4;   // multiplicative-noise matrices per kind
+
+struct SdnLikArgs {
+  LqgkSpec act, dyn;          // time-invariant; A, B, F of the actor and A, B, F, V, W of the dynamics are read
+  const void *L, *K;          // gains [S][T][u][b], [S][T][b][y] in the I/O type
+  LqgkMat C, D;               // C[nc][x][u], D[nd][y][x] per sample (sample_stride 0 = shared; time_stride ignored)
+  const float* x_tm;          // observations [T+1][N][d] (per sample when x_sample_stride != 0)
+  long long x_sample_stride;
+  void* ll_out;               // [S][N]
+  int S, N, T, nc, nd;
+};
+
+template <class DM>
+struct SdnLik {
+  static constexpr int X = DM::X, B = DM::B, U = DM::U, Y = DM::Y, D = DM::D, N = DM::N, R = DM::R, XU = DM::XU;
+  using CF = CovFwd<DM>;
+  using C = CovC<DM>;
+  // The constants the joint system needs, in the CovC layout the main path's k_pack produces (lqgk_pack.h), straight from
+  // the base matrices of sample s; Fd (Y x X) separately (the multiplicative control noise reaches xhat through K F_d C_i).
+  template <class T>
+  LQGK_HD static void load_consts(const LqgkSpec& act, const LqgkSpec& dyn, int s, double* lc, double* Fd) {
+    double Ad[X * X], Bd[X * U], Vd[X * X], Wd[Y * Y], Aa[B * B], Ba[B * U], Fa[Y * B];
+    for (int i = 0; i < X * X; ++i) { Ad[i] = mat_at<T>(dyn.A, s, 0, i); Vd[i] = mat_at<T>(dyn.V, s, 0, i); }
+    for (int i = 0; i < X * U; ++i) Bd[i] = mat_at<T>(dyn.B, s, 0, i);
+    for (int i = 0; i < Y * X; ++i) Fd[i] = mat_at<T>(dyn.F, s, 0, i);
+    for (int i = 0; i < Y * Y; ++i) Wd[i] = mat_at<T>(dyn.W, s, 0, i);
+    for (int i = 0; i < B * B; ++i) Aa[i] = mat_at<T>(act.A, s, 0, i);
+    for (int i = 0; i < B * U; ++i) Ba[i] = mat_at<T>(act.B, s, 0, i);
+    for (int i = 0; i < Y * B; ++i) Fa[i] = mat_at<T>(act.F, s, 0, i);
+    for (int i = 0; i < X * X; ++i) lc[C::Ad + i] = Ad[i];
+    for (int i = 0; i < X * U; ++i) lc[C::Bd + i] = Bd[i];
+    for (int i = 0; i < B * B; ++i) lc[C::Aa + i] = Aa[i];
+    for (int i = 0; i < B * U; ++i) lc[C::Ba + i] = Ba[i];
+    mm<Y, X, X>(Fd, Ad, lc + C::FAd);
+    mm<Y, B, B>(Fa, Aa, lc + C::FAa);
+    for (int i = 0; i < Y; ++i) for (int j = 0; j < U; ++j) {          // Dm = F_d B_d - F_a B_a
+      double a = 0.0;
+      for (int k = 0; k < X; ++k) a += Fd[i * X + k] * Bd[k * U + j];
+      for (int k = 0; k < B; ++k) a -= Fa[i * B + k] * Ba[k * U + j];
+      lc[C::Dm + i * U + j] = a;
+    }
+    double N11[X * X], FN[Y * X];
+    mm_nt<X, X, X>(Vd, Vd, N11);
+    for (int i = 0; i < X; ++i) for (int j = 0; j <= i; ++j) lc[C::N11 + i * (i + 1) / 2 + j] = N11[i * X + j];
+    mm<Y, X, X>(Fd, N11, FN);
+    for (int i = 0; i < Y * X; ++i) lc[C::FN + i] = FN[i];
+    for (int i = 0; i < Y; ++i) for (int j = 0; j <= i; ++j) {          // Om = F_d N11 F_d^T + W_d W_d^T
+      double a = 0.0;
+      for (int k = 0; k < X; ++k) a += FN[i * X + k] * Fd[j * X + k];
+      for (int k = 0; k < Y; ++k) a += Wd[i * Y + k] * Wd[j * Y + k];
+      lc[C::Om + i * (i + 1) / 2 + j] = a;
+    }
+  }
+  // c_0 = 0, C_0 = cov(unobserved | x_0) under Sig_0 = G_0 G_0^T                         system.py:211-212
+  template <class V>
+  LQGK_HD static void init(const V& lc, const double* K0, double* c, double* Cm) {
+    double J0[R * D];
+    CF::init(lc, K0, Cm, J0);
+    for (int i = 0; i < R; ++i) c[i] = 0.0;
+  }
+  // one step; returns the log-density of x1 = x_{t+1}[o]
+  template <class V>
+  LQGK_HD static double step(const V& lc, const double* Fd, int nc, const double* Cs, int nd, const double* Ds, const double* L,
+                             const double* K, const double* x0, const double* x1, double* c, double* Cm) {
+    double Fj[N * N], Nj[N * N], Sig[N * N], mu[N];
+    CF::joint_F(lc, L, K, Fj);
+    CF::joint_N(lc, K, Nj);
+    CF::predict(Fj, Cm, Nj, Sig);
+    for (int i = 0; i < N; ++i) {
+      double a = 0.0;
+      for (int j = 0; j < D; ++j) a += Fj[i * N + j] * x0[j];
+      for (int j = 0; j < R; ++j) a += Fj[i * N + D + j] * c[j];
+      mu[i] = a;
+    }
+    if (nc > 0) {
+      double LZ[U * B], U2[U * U], KF[B * X];
+      for (int i = 0; i < U; ++i) for (int j = 0; j < B; ++j) {         // L Z2[xhat,xhat]
+        double a = 0.0;
+        for (int k = 0; k < B; ++k) a += L[i * B + k] * (Cm[(XU + k) * R + XU + j] + c[XU + k] * c[XU + j]);
+        LZ[i * B + j] = a;
+      }
+      mm_nt<U, B, U>(LZ, L, U2);
+      mm<B, Y, X>(K, Fd, KF);
+      for (int q = 0; q < nc; ++q) {
+        const double* Cq = Cs + q * (X * U);
+        double g[N * U], gU[N * U];
+        for (int i = 0; i < X * U; ++i) g[i] = Cq[i];
+        mm<B, X, U>(KF, Cq, g + X * U);
+        mm<N, U, U>(g, U2, gU);
+        for (int i = 0; i < N; ++i) for (int j = 0; j <= i; ++j) {
+          double a = 0.0;
+          for (int k = 0; k < U; ++k) a += gU[i * U + k] * g[j * U + k];
+          Sig[i * N + j] += a;
+          if (j != i) Sig[j * N + i] += a;
+        }
+      }
+    }
+    if (nd > 0) {
+      double X2[X * X];
+      for (int i = 0; i < X; ++i) for (int j = 0; j < X; ++j) X2[i * X + j] = Sig[i * N + j] + mu[i] * mu[j];
+      for (int q = 0; q < nd; ++q) {
+        double h[B * X], hX[B * X];
+        mm<B, Y, X>(K, Ds + q * (Y * X), h);
+        mm<B, X, X>(h, X2, hX);
+        for (int i = 0; i < B; ++i) for (int j = 0; j <= i; ++j) {
+          double a = 0.0;
+          for (int k = 0; k < X; ++k) a += hX[i * X + k] * h[j * X + k];
+          Sig[(X + i) * N + X + j] += a;
+          if (j != i) Sig[(X + j) * N + X + i] += a;
+        }
+      }
+    }
+    double Linv[D * D], ld, J[R * D], Cn[R * R], e[D], z[D];
+    CF::condition(Sig, Linv, ld, [&](int i, double v) { J[i] = v; }, Cn);
+    for (int i = 0; i < D; ++i) e[i] = x1[i] - mu[i];
+    double qf = 0.0;
+    for (int i = 0; i < D; ++i) {
+      double a = 0.0;
+      for (int j = 0; j <= i; ++j) a += Linv[i * D + j] * e[j];
+      z[i] = a;
+      qf += a * a;
+    }
+    for (int i = 0; i < R; ++i) {
+      double a = mu[D + i];
+      for (int j = 0; j < D; ++j) a += J[i * D + j] * e[j];
+      c[i] = a;
+    }
+    for (int i = 0; i < R * R; ++i) Cm[i] = Cn[i];
+    return -0.5 * qf - ld - 0.91893853320467274178 * D;
+  }
+  // the whole trial `i` of sample `s` (shared by the kernel and the CPU test harness)
+  template <class T>
+  LQGK_HD static double trial(const SdnLikArgs& a, int s, int i) {
+    double lc[C::n], Fd[Y * X], Cs[SDN_MAX_TERMS * X * U], Ds[SDN_MAX_TERMS * Y * X];
+    load_consts<T>(a.act, a.dyn, s, lc, Fd);
+    for (int q = 0; q < a.nc * X * U; ++q) Cs[q] = mat_at<T>(a.C, s, 0, q);
+    for (int q = 0; q < a.nd * Y * X; ++q) Ds[q] = mat_at<T>(a.D, s, 0, q);
+    const T* Lp = (const T*)a.L + (size_t)s * a.T * (U * B);
+    const T* Kp = (const T*)a.K + (size_t)s * a.T * (B * Y);
+    const float* xp = a.x_tm + (size_t)s * a.x_sample_stride + (size_t)i * D;
+    const size_t xrow = (size_t)a.N * D;
+    double Lt[U * B], Kt[B * Y], c[R], Cm[R * R], x0[D], x1[D];
+    for (int k = 0; k < B * Y; ++k) Kt[k] = (double)Kp[k];
+    WView lv{lc, 1};
+    init(lv, Kt, c, Cm);
+    for (int k = 0; k < D; ++k) x0[k] = (double)xp[k];
+    double ll = 0.0;
+    for (int t = 0; t < a.T; ++t) {
+      for (int k = 0; k < U * B; ++k) Lt[k] = (double)Lp[(size_t)t * (U * B) + k];
+      for (int k = 0; k < B * Y; ++k) Kt[k] = (double)Kp[(size_t)t * (B * Y) + k];
+      for (int k = 0; k < D; ++k) x1[k] = (double)xp[(size_t)(t + 1) * xrow + k];
+      ll += step(lv, Fd, a.nc, Cs, a.nd, Ds, Lt, Kt, x0, x1, c, Cm);
+      for (int k = 0; k < D; ++k) x0[k] = x1[k];
+    }
+    return ll;
+  }
+};
+
 #if defined(__CUDACC__)
 template <class DM>
 __global__ void __launch_bounds__(32) k_sdn_gains(SdnArgs a) {
@@ -198,6 +371,15 @@ __global__ void __launch_bounds__(32) k_sdn_gains(SdnArgs a) {
   const double cost = Sdn<DM>::backward(a, s, A, Bm, H, Q, R, Qf, Omxi, Omom, Sig1, xh1, a.sweeps == 0);
   if (a.cost) a.cost[s] = cost;
 }
+// one thread per (parameter sample, trial) system
+template <class DM, class T>
+__global__ void __launch_bounds__(64) k_sdn_loglik(SdnLikArgs a) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)a.S * a.N) return;
+  const int s = (int)(idx / a.N), i = (int)(idx - (size_t)s * a.N);
+  ((T*)a.ll_out)[idx] = (T)SdnLik<DM>::template trial<T>(a, s, i);
+}
 #endif
+
 
 }  // namespace lqgk

@@ -367,3 +367,38 @@ def simulate(actor: LQGSpec, dynamics: LQGSpec, L, l, K, n: int, seed: int, x0=N
     if actor.A.dim() == 3 and dynamics.A.dim() == 3:
         return tuple(o[0] for o in out) if return_all else out[0]
     return out
+
+
+def sdn_log_likelihood(actor: LQGSpec, dynamics: LQGSpec, x: torch.Tensor, L: torch.Tensor, K: torch.Tensor,
+                       C: Optional[torch.Tensor] = None, D: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Per-trial log-likelihood under signal-dependent noise (EXTENSION, no reference counterpart; include/lqgk.h:
+    lqgk_sdn_loglik_*, spec oracle/sdn_np.py).  ``L[(S,) T, u, b]``, ``K[(S,) T, b, y]``: the gains; ``C[(S,) nc, x, u]``:
+    control-dependent process-noise matrices; ``D[(S,) nd, y, x]``: state-dependent observation-noise matrices.
+    x as in :func:`log_likelihood`.  Forward only (gradients: lqg_b200.control.sdn.value_and_grad_fd)."""
+    _require_cuda(actor.A, "actor spec")
+    _require_cuda(x, "observations")
+    lib = abi.load_library()
+    per_sample = x.dim() == 4
+    n, T1, d = x.shape[-3:]
+    dims = dims_of(actor, dynamics, n, d)
+    if dims.T != T1 - 1:
+        raise ValueError(f"need T+1 = {dims.T + 1} observations per trial, got {T1}")
+    if per_sample and x.shape[0] != dims.S:
+        raise ValueError(f"per-sample observations need a leading axis of {dims.S} samples, got {x.shape[0]}")
+    check_supported(dims)
+    if dims.x + dims.b > 12:
+        raise NotImplementedError("lqg_b200: the signal-dependent-noise likelihood is compiled for joint dims <= 12")
+    dt, dev = actor.A.dtype, actor.A.device
+    act, dyn = _base_mats(actor, dynamics, dt)
+    for M in list(act.values()) + list(dyn.values()):
+        if M.dim() == 4:
+            raise NotImplementedError("lqg_b200: the signal-dependent-noise likelihood needs time-invariant specs")
+    x_tm = x.detach().permute(0, 2, 1, 3).to(torch.float32).contiguous() if per_sample else lib.pack_obs(x.detach(), stream=_stream(dev))
+    S = dims.S
+
+    def per_s(t, nd):
+        t = t if t.dim() == nd + 1 else t.unsqueeze(0)
+        return t.expand(S, *t.shape[1:]).to(dt).contiguous()
+
+    ll = lib.sdn_loglik(dims, act, dyn, per_s(L, 3), per_s(K, 3), x_tm, C_noise=C, D_noise=D, stream=_stream(dev))
+    return ll[0] if (actor.A.dim() == 3 and dynamics.A.dim() == 3) else ll

@@ -160,6 +160,36 @@ class System:
     def conditional_distribution(self, x: torch.Tensor, Sigma0=None) -> ConditionalDistribution:
         return ConditionalDistribution(self, x, Sigma0)
 
+    def log_likelihood_sdn(self, x: torch.Tensor, signal_dep_noise=None, obs_dep_noise=None, C=None, D=None, gains=None,
+                           Sigma0=None) -> torch.Tensor:
+        """log p(x | theta) under signal-dependent noise -- an EXTENSION of the reference (docs/README.md:60-62 names it as
+        future work; lqg/infer/prior.py:11 only reserves the parameter name ``signal_dep_noise``), see
+        lqg_b200.control.sdn and oracle/sdn_np.py.  The plant gets control-dependent process noise and state-dependent
+        observation noise on top of V, W; the experimenter's filter (system.py:142-248) matches the first two moments of
+        every predictive distribution.  Noise model: either the scalars ``signal_dep_noise`` / ``obs_dep_noise`` (per-channel
+        proportional noise, lqg_b200.control.sdn.channel_noise; parameters may be batched like the model's own) or explicit
+        matrices ``C[(S,) nc, x, u]``, ``D[(S,) nd, y, x]``.  ``gains``: (L, K) to use instead of the actor model's own
+        lqr.backward / kf.forward (e.g. from lqg_b200.control.sdn.solve)."""
+        from lqg_b200.control import sdn
+        axis = getattr(self, "_axis_system", None)
+        if axis is not None and C is None and D is None and gains is None and Sigma0 is None and x.shape[-1] == self.xdim:
+            # per-channel noise keeps the axes of a dim > 1 tracking model independent: same factorisation as log_likelihood
+            lead, (n, T1, d) = x.shape[:-3], x.shape[-3:]
+            dim = self.dim
+            xa = x.reshape(*lead, n, T1, dim, d // dim).movedim(-2, -4).reshape(*lead, dim * n, T1, d // dim)
+            ll = axis.log_likelihood_sdn(xa, signal_dep_noise=signal_dep_noise, obs_dep_noise=obs_dep_noise)
+            return ll.reshape(*ll.shape[:-1], dim, n).sum(-2)
+        if C is None and signal_dep_noise is not None:
+            C = sdn.channel_noise(self, signal_dep_noise, "control")
+        if D is None and obs_dep_noise is not None:
+            D = sdn.channel_noise(self, obs_dep_noise, "observation")
+        if gains is None:
+            g, K = self._gains(Sigma0)
+            L = g.L
+        else:
+            L, K = gains
+        return runtime.sdn_log_likelihood(self.actor, self.dynamics, x.to(self.device), L, K, C=C, D=D)
+
     # -- slow paths ----------------------------------------------------------------------------------------
     def _joint(self, gains_L, K):
         """Joint (x, xhat) transition F[...,T,n,n] and noise factor G[...,T,n,x+y] (system.py:163-207)."""

@@ -108,3 +108,105 @@ def tracking_example(dt=1.0 / 60.0, sigma_u=0.5, sigma_target=6.0, sigma_cursor=
     Sigma1 = np.diag([1.0, 1.0])
     xhat1 = np.array([0.5, -0.5])
     return dict(A=A, B=B, H=H, C=C, D=D, Q=Q, R=R, Qf=Q, Om_xi=Om_xi, Om_om=Om_om, Sigma1=Sigma1, xhat1=xhat1)
+
+
+# =========================================================================================== likelihood under signal-dependent noise
+# Extension of the reference's experimenter-side filter (lqg/system.py:142-248) -- NOT in the reference, PARITY UNPINNED.
+# Written in the reference's own FILTER-form conventions (lqg/system.py:110-124, lqg/belief/kf.py:10-14) so that with C = D = []
+# every function below reproduces oracle/lqg_np.py (= the reference) exactly:
+#     u_t      = L_t xhat_t (+ l_t)
+#     x_{t+1}  = A x_t + B u_t + V eps_t          + sum_i eps'_{i,t} C_i u_t          C_i [x, u]   control-dependent noise
+#     y_t      = F x_{t+1} + W eta_t              + sum_j eta'_{j,t} D_j x_{t+1}      D_j [y, x]   state-dependent observation noise
+#     xp       = A_a xhat_t + B_a u_t ;  xhat_{t+1} = xp + K_t (y_t - F_a xp)
+# The gains (L, K) are INPUTS (any source: the actor's lqr.backward / kf.forward as in the reference, or an SDN-aware solver).
+# With multiplicative noise the joint (x, xhat) process is no longer Gaussian; its first two moments still obey a closed
+# recursion (the noise covariance depends on the second moment of the state), which `sdn_moments` propagates exactly.  The
+# likelihood conditions on the observed part of x step by step like system.py:214-235 and treats each predictive distribution as
+# Gaussian with those moments (moment matching) -- the approximation of Schultheis et al. (NeurIPS 2021) the reference's README
+# (docs/README.md:60-62) points to.  The covariance now depends on the running mean, so it is per TRIAL, not per parameter set.
+from oracle import lqg_np as _O  # noqa: E402
+
+
+def sdn_joint_terms(dyn, K, C, D, t):
+    """g_i = [C_i ; K_t F_d C_i]  (n x u)  and  h_j = K_t D_j  (b x x)."""
+    Kt, Fd = K[t], dyn["F"][t]
+    return [np.vstack([Ci, Kt @ Fd @ Ci]) for Ci in C], [Kt @ Dj for Dj in D]
+
+
+def sdn_predict(F, N, L, gs, hs, mu_c, Sig_c, x):
+    """One prediction step from the (conditioned or not) moments (mu_c, Sig_c) of z_t = (x, xhat)_t."""
+    Z2 = Sig_c + np.outer(mu_c, mu_c)                              # E[z z^T]
+    U2 = L @ Z2[x:, x:] @ L.T                                      # E[u u^T]
+    mu = F @ mu_c
+    Sig = F @ Sig_c @ F.T + N + sum(g @ U2 @ g.T for g in gs)
+    X2 = Sig[:x, :x] + np.outer(mu[:x], mu[:x])                    # E[x' x'^T] given the same information
+    if hs:
+        Sig = Sig.copy()
+        Sig[x:, x:] += sum(h @ X2 @ h.T for h in hs)
+    return mu, 0.5 * (Sig + Sig.T)
+
+
+def sdn_moments(actor, dyn, L, K, C, D, x0=None, xhat0=None):
+    """EXACT unconditional mean[T+1,n] / covariance[T+1,n,n] of z_t = (x_t, xhat_t) under the generative model above."""
+    Fj, Gj = _O.joint_system(actor, dyn, L, K)
+    T, x, b = Fj.shape[0], dyn["A"].shape[1], actor["A"].shape[1]
+    mu = np.concatenate([np.zeros(x) if x0 is None else x0, np.zeros(b) if xhat0 is None else xhat0])
+    Sig = np.zeros((x + b, x + b))
+    mus, Sigs = [mu], [Sig]
+    for t in range(T):
+        gs, hs = sdn_joint_terms(dyn, K, C, D, t)
+        mu, Sig = sdn_predict(Fj[t], Gj[t] @ Gj[t].T, L[t], gs, hs, mu, Sig, x)
+        mus.append(mu); Sigs.append(Sig)
+    return np.stack(mus), np.stack(Sigs)
+
+
+def sdn_conditional_moments(actor, dyn, L, K, C, D, xs):
+    """system.py:142-235 with the signal-dependent terms: predictive moments mu[T,n], Sigma[T,n,n] of one trial xs[T+1,d]."""
+    xs = np.asarray(xs, dtype=np.float64)
+    d, x, b = xs.shape[1], dyn["A"].shape[1], actor["A"].shape[1]
+    Fj, Gj = _O.joint_system(actor, dyn, L, K)
+    T = Fj.shape[0]
+    mu = np.concatenate([xs[0], np.zeros(x - d + b)])                             # system.py:211
+    Sig = Gj[0] @ Gj[0].T                                                          # system.py:212
+    mus, Sigs = np.zeros((T, x + b)), np.zeros((T, x + b, x + b))
+    for t in range(T):
+        Soo = Sig[:d, :d]
+        mu_c = mu + Sig[:, :d] @ np.linalg.solve(Soo, xs[t] - mu[:d])              # condition on x_t ...
+        Sig_c = Sig - Sig[:, :d] @ np.linalg.solve(Soo, Sig[:d, :])
+        gs, hs = sdn_joint_terms(dyn, K, C, D, t)
+        mu, Sig = sdn_predict(Fj[t], Gj[t] @ Gj[t].T, L[t], gs, hs, mu_c, Sig_c, x)   # ... then predict (system.py:219-230)
+        mus[t], Sigs[t] = mu, Sig
+    return mus, Sigs
+
+
+def sdn_log_likelihood(actor, dyn, L, K, C, D, X):
+    """Per-trial log-likelihood of X[N,T+1,d] (sum over time), system.py:237-248 with moment-matched Gaussians."""
+    X = np.asarray(X, dtype=np.float64)
+    N, _, d = X.shape
+    out = np.zeros(N)
+    for i in range(N):
+        mus, Sigs = sdn_conditional_moments(actor, dyn, L, K, C, D, X[i])
+        out[i] = sum(_O.mvn_logpdf(X[i, t + 1], mus[t, :d], Sigs[t, :d, :d]) for t in range(mus.shape[0]))
+    return out
+
+
+def sdn_simulate(actor, dyn, L, K, C, D, n, rng, x0=None, xhat0=None, l=None):
+    """The generative model above (system.py:62-140 plus the multiplicative terms).  Returns x[n,T+1,x], xhat[n,T+1,b]."""
+    T, xd, bd, yd = dyn["A"].shape[0], dyn["A"].shape[1], actor["A"].shape[1], dyn["F"].shape[1]
+    xs = np.zeros((n, T + 1, xd)); xh = np.zeros((n, T + 1, bd))
+    if x0 is not None:
+        xs[:, 0] = x0
+    if xhat0 is not None:
+        xh[:, 0] = xhat0
+    for t in range(T):
+        u = xh[:, t] @ L[t].T + (0.0 if l is None else l[t])
+        xn = xs[:, t] @ dyn["A"][t].T + u @ dyn["B"][t].T + rng.standard_normal((n, xd)) @ dyn["V"][t].T
+        for Ci in C:
+            xn = xn + rng.standard_normal((n, 1)) * (u @ Ci.T)
+        yv = xn @ dyn["F"][t].T + rng.standard_normal((n, yd)) @ dyn["W"][t].T
+        for Dj in D:
+            yv = yv + rng.standard_normal((n, 1)) * (xn @ Dj.T)
+        xp = xh[:, t] @ actor["A"][t].T + u @ actor["B"][t].T
+        xh[:, t + 1] = xp + (yv - xp @ actor["F"][t].T) @ K[t].T
+        xs[:, t + 1] = xn
+    return xs, xh

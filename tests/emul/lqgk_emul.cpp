@@ -11,6 +11,7 @@
 #include "../../lqg_b200/csrc/lqgk_dims.h"
 #include "../../lqg_b200/csrc/lqgk_pack.h"
 #include "../../lqg_b200/csrc/lqgk_stages.h"
+#include "../../lqg_b200/csrc/lqgk_sdn.cuh"
 
 using namespace lqgk;
 
@@ -194,7 +195,29 @@ static int pack_obs_host(int32_t N, int32_t T1, int32_t d, const T* x, float* x_
       for (int k = 0; k < d; ++k) x_tm[((size_t)t * N + i) * d + k] = (float)x[((size_t)i * T1 + t) * d + k];
   return LQGK_OK;
 }
+template <class T>
+static int sdn_loglik_host(const LqgkDims* d, const LqgkSpec* act, const LqgkSpec* dyn, const LqgkSdnNoise* nz, const T* L, const T* K,
+                           const float* x_tm, T* ll_out) {
+  if (!d || !act || !dyn || !L || !K || !x_tm || !ll_out) return LQGK_E_INVALID;
+  SdnLikArgs a{};
+  a.act = *act; a.dyn = *dyn; a.L = L; a.K = K; a.x_tm = x_tm; a.x_sample_stride = d->x_sample_stride; a.ll_out = ll_out;
+  a.S = d->S; a.N = d->N; a.T = d->T;
+  if (nz) { a.C = nz->C; a.D = nz->D; a.nc = nz->nc; a.nd = nz->nd; }
+#define LQGK_CASE(X, B, U, Y, DD)                                                                          \
+  if (X + B <= 12 && d->x == X && d->b == B && d->u == U && d->y == Y && d->d == DD) {                     \
+    for (int s = 0; s < a.S; ++s)                                                                          \
+      for (int i = 0; i < a.N; ++i) ll_out[(size_t)s * a.N + i] = (T)SdnLik<Dims<X, B, U, Y, DD>>::template trial<T>(a, s, i); \
+    return LQGK_OK;                                                                                        \
+  }
+  LQGK_FOR_EACH_DIMS(LQGK_CASE)
+#undef LQGK_CASE
+  return LQGK_E_UNSUPPORTED;
+}
 extern "C" {
+int lqgk_sdn_loglik_f64(const LqgkDims* dims, const LqgkSpec* actor, const LqgkSpec* dynamics, const LqgkSdnNoise* noise, const double* L,
+                        const double* K, const float* x_tm, double* ll_out, void*) {
+  return sdn_loglik_host<double>(dims, actor, dynamics, noise, L, K, x_tm, ll_out);
+}
 int lqgk_lqr_backward_f64(const LqgkDims* dims, const LqgkSpec* actor, double eps, double* L_out, double* l_out,
                           double* H_out, void*, size_t, void*) {
   return dispatch<double>(dims, actor, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, false,
