@@ -195,6 +195,17 @@ int sdn_loglik(const LqgkDims* d, const LqgkSpec* act, const LqgkSpec* dyn, cons
   if (d->x == X && d->b == B && d->u == U && d->y == Y && d->d == DD) return Runner<X, B, U, Y, DD>::run_sdn_loglik(a, f64, (cudaStream_t)stream);
   LQGK_FOR_EACH_DIMS(LQGK_CASE)
 #undef LQGK_CASE
+  // tuples compiled for this all-FP64 path only (lqgk_dims.h)
+#define LQGK_CASE(X, B, U, Y, DD)                                                                        \
+  if (d->x == X && d->b == B && d->u == U && d->y == Y && d->d == DD) {                                  \
+    const unsigned blocks = (unsigned)(((size_t)a.S * a.N + 63) / 64);                                   \
+    if (f64) k_sdn_loglik<Dims<X, B, U, Y, DD>, double><<<blocks, 64, 0, (cudaStream_t)stream>>>(a);      \
+    else k_sdn_loglik<Dims<X, B, U, Y, DD>, float><<<blocks, 64, 0, (cudaStream_t)stream>>>(a);           \
+    LQGK_LAUNCH_CHECK();                                                                                 \
+    return LQGK_OK;                                                                                      \
+  }
+  LQGK_FOR_EACH_FP64_ONLY_DIMS(LQGK_CASE)
+#undef LQGK_CASE
   return LQGK_E_UNSUPPORTED;
 }
 }  // namespace

@@ -657,9 +657,12 @@ template <class DM> constexpr size_t smem_lqr_rev() {
 // Resident CTAs per SM the forward per-trial kernel is compiled for: the small systems are latency-bound at 2 CTAs (8 warps)
 // per SM, so the register budget is capped at 65536 / (3 * 128) = 170 to fit 3.
 // The adjoint kernel needs ~240 registers; capped at 170 it spills and runs 1.6x slower (measured), so it stays at 2 CTAs.
+#ifndef LQGK_FWD_WARPS
+#define LQGK_FWD_WARPS 4
+#endif
+constexpr int TRIAL_WARPS = LQGK_FWD_WARPS;   // warps (= samples) per CTA of the forward kernel
 template <class DM>
-__host__ __device__ constexpr int trial_min_ctas() { return DM::N <= 6 ? 3 : 1; }
-constexpr int TRIAL_WARPS = 4;   // warps (= samples) per CTA of the forward kernel
+__host__ __device__ constexpr int trial_min_ctas() { return DM::N <= 6 ? 12 / TRIAL_WARPS : 1; }
 #ifndef LQGK_REV_WARPS
 #define LQGK_REV_WARPS 4
 #endif

@@ -5,9 +5,11 @@ import re
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _parse():
+def _parse(macro):
     txt = open(os.path.join(_HERE, "csrc", "lqgk_dims.h")).read()
-    return [tuple(int(v) for v in m) for m in re.findall(r"M\((\d+), (\d+), (\d+), (\d+), (\d+)\)", txt)]
+    body = txt.split("#define " + macro + "(M)", 1)[1].split("#define", 1)[0].split("// clang-format on", 1)[0]
+    return [tuple(int(v) for v in m) for m in re.findall(r"M\((\d+), (\d+), (\d+), (\d+), (\d+)\)", body)]
 
 
-SUPPORTED_DIMS = _parse()
+SUPPORTED_DIMS = _parse("LQGK_FOR_EACH_DIMS")
+FP64_ONLY_DIMS = _parse("LQGK_FOR_EACH_FP64_ONLY_DIMS")   # all-FP64 per-trial likelihood only (System.log_likelihood_fp64)

@@ -16,7 +16,7 @@ from typing import Dict, Optional, Tuple
 import torch
 
 from lqg_b200 import abi
-from lqg_b200.dims import SUPPORTED_DIMS
+from lqg_b200.dims import FP64_ONLY_DIMS, SUPPORTED_DIMS
 from lqg_b200.spec import LQGSpec
 
 WORKSPACE_FRACTION = 0.85         # of currently free device memory, upper bound for the cached workspace
@@ -385,9 +385,10 @@ def sdn_log_likelihood(actor: LQGSpec, dynamics: LQGSpec, x: torch.Tensor, L: to
         raise ValueError(f"need T+1 = {dims.T + 1} observations per trial, got {T1}")
     if per_sample and x.shape[0] != dims.S:
         raise ValueError(f"per-sample observations need a leading axis of {dims.S} samples, got {x.shape[0]}")
-    check_supported(dims)
+    if (dims.x, dims.b, dims.u, dims.y, dims.d) not in FP64_ONLY_DIMS:
+        check_supported(dims)
     if dims.x + dims.b > 12:
-        raise NotImplementedError("lqg_b200: the signal-dependent-noise likelihood is compiled for joint dims <= 12")
+        raise NotImplementedError("lqg_b200: the signal-dependent-noise / all-FP64 likelihood is compiled for joint dims <= 12")
     dt, dev = actor.A.dtype, actor.A.device
     act, dyn = _base_mats(actor, dynamics, dt)
     for M in list(act.values()) + list(dyn.values()):

@@ -160,6 +160,14 @@ class System:
     def conditional_distribution(self, x: torch.Tensor, Sigma0=None) -> ConditionalDistribution:
         return ConditionalDistribution(self, x, Sigma0)
 
+    def log_likelihood_fp64(self, x: torch.Tensor, Sigma0=None) -> torch.Tensor:
+        """``log_likelihood`` with the per-trial recursion in FP64 as well (the all-FP64 kernel k_sdn_loglik without
+        multiplicative noise): for models whose innovation covariance is too ill-conditioned for the FP32 per-trial
+        arithmetic of the main path, e.g. ``PointMassBoundedActor`` with all four states observed
+        (lqg/tracking/point_mass.py:7-47).  Forward only; gradients: lqg_b200.control.sdn.value_and_grad_fd."""
+        g, K = self._gains(Sigma0)
+        return runtime.sdn_log_likelihood(self.actor, self.dynamics, x.to(self.device), g.L, K)
+
     def log_likelihood_sdn(self, x: torch.Tensor, signal_dep_noise=None, obs_dep_noise=None, C=None, D=None, gains=None,
                            Sigma0=None) -> torch.Tensor:
         """log p(x | theta) under signal-dependent noise -- an EXTENSION of the reference (docs/README.md:60-62 names it as

@@ -16,6 +16,10 @@ def _base(M):
 
 def delay_system(spec: LQGSpec, delay: int) -> LQGSpec:
     T = spec.A.shape[-3]
+    for M in (spec.A, spec.B, spec.F, spec.V, spec.W, spec.Q, spec.R):
+        if M.shape[-3] > 1 and M.stride(-3) != 0 and not bool((M[..., :1, :, :] == M).all()):
+            raise NotImplementedError("delay_system: time-varying specs are not supported (the reference augments every time "
+                                      "step, lqg/tracking/delay.py:9-41; here the time axis is a stride-0 view of one matrix)")
     A, Bm, F, V, W, Q, R = map(_base, (spec.A, spec.B, spec.F, spec.V, spec.W, spec.Q, spec.R))
     d = A.shape[-1]
     kw = dict(dtype=A.dtype, device=A.device)
@@ -26,8 +30,8 @@ def delay_system(spec: LQGSpec, delay: int) -> LQGSpec:
     A2 = A2 + torch.diag(torch.ones(d * delay, **kw), diagonal=-d)
     B2 = torch.cat([Bm] + [torch.zeros_like(Bm)] * delay, -2)
     F2 = torch.cat([torch.zeros(F.shape[:-1] + (F.shape[-1] * delay,), **kw), F], -1)
-    V2 = torch.zeros(V.shape[:-2] + (n, n), **kw)
-    V2[..., :d, :d] = V
+    V2 = torch.zeros(V.shape[:-2] + (n, n - d + V.shape[-1]), **kw)      # noise enters the current state only
+    V2[..., :d, :V.shape[-1]] = V
     Q2 = torch.zeros(Q.shape[:-2] + (n, n), **kw)
     Q2[..., :d, :d] = Q
     return time_stack_spec(A=A2, B=B2, F=F2, V=V2, W=W, Q=Q2, R=R, T=T)

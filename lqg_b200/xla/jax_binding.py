@@ -9,7 +9,12 @@ UNTESTED IN THIS ENVIRONMENT (no jax / jaxlib in the image or wheelhouse, no net
         def log_likelihood(self, x, Sigma0=None):                # lqg/system.py:246-248
             return log_likelihood(self.actor, self.dynamics, x)
 
-``vmap`` over parameters maps onto the kernels' leading sample axis via ``vmap_method="broadcast_all"``.
+Batching over parameters: pass specs with a leading sample axis ``[S, T, r, c]`` (the kernels' own sample axis).  ``jax.vmap``
+of this function is only supported as a sequential loop over the mapped axis (``vmap_method="sequential"``): the C++ handlers
+read (S, T, N, d) from fixed operand positions, so a batch axis prepended by vmap cannot be folded into S there.
+Limits (not checkable under tracing, so stated here): time-invariant specs only -- ``_base`` takes the t = 0 slice of every
+stacked array, like the reference models build them (lqg/utils.py:6-35) --, and the default ``Sigma0`` (= V_a[0] V_a[0]^T,
+lqg/system.py:158-161); anything else must go through the C ABI directly (include/lqgk.h).
 """
 import ctypes
 import os
@@ -64,7 +69,7 @@ def _fwd_call(mats, x_tm):
     S, N, T, x, b, u, y, d = _shapes(mats, x_tm)
     out = (jax.ShapeDtypeStruct((S, N), jnp.float32),
            jax.ShapeDtypeStruct((_workspace_bytes(S, N, T, x, b, u, y, d, 1),), jnp.uint8))
-    ll, _ = jax.ffi.ffi_call("lqg_loglik_fwd", out, vmap_method="broadcast_all")(*mats, x_tm)
+    ll, _ = jax.ffi.ffi_call("lqg_loglik_fwd", out, vmap_method="sequential")(*mats, x_tm)
     return ll
 
 
@@ -78,7 +83,7 @@ def _vjp_bwd(res, ll_bar):
     outs = ([jax.ShapeDtypeStruct((S, N), jnp.float32)]
             + [jax.ShapeDtypeStruct((S,) + m.shape[1:], jnp.float32) for m in mats]
             + [jax.ShapeDtypeStruct((_workspace_bytes(S, N, T, x, b, u, y, d, 2),), jnp.uint8)])
-    res = jax.ffi.ffi_call("lqg_loglik_vjp", tuple(outs), vmap_method="broadcast_all")(*mats, x_tm, ll_bar.astype(jnp.float32))
+    res = jax.ffi.ffi_call("lqg_loglik_vjp", tuple(outs), vmap_method="sequential")(*mats, x_tm, ll_bar.astype(jnp.float32))
     grads = [g if m.shape[0] > 1 else g.sum(0, keepdims=True) for g, m in zip(res[1:13], mats)]
     return grads, None
 

@@ -210,6 +210,7 @@ static int sdn_loglik_host(const LqgkDims* d, const LqgkSpec* act, const LqgkSpe
     return LQGK_OK;                                                                                        \
   }
   LQGK_FOR_EACH_DIMS(LQGK_CASE)
+  LQGK_FOR_EACH_FP64_ONLY_DIMS(LQGK_CASE)
 #undef LQGK_CASE
   return LQGK_E_UNSUPPORTED;
 }

@@ -63,7 +63,7 @@ def test_true_noise_model_explains_sdn_data_better():
     assert ll_true.mean() > ll_plain.mean()
 
 
-def _run_library(lib, dev, name, S_, N, c_mults, d_mults, dtype, T_=T, seed=0, shared_noise=False):
+def _run_library(lib, dev, name, S_, N, c_mults, d_mults, dtype, T_=T, seed=0, shared_noise=False, d=None):
     x, b, u, y = H.MODEL_DIMS[name]
     params = H.jittered_params(name, S_, seed)
     mats = [H.model_mats(name, **kw) for kw in params]
@@ -71,7 +71,7 @@ def _run_library(lib, dev, name, S_, N, c_mults, d_mults, dtype, T_=T, seed=0, s
     gains = [(O.lqr_backward(sa)[0], O.kf_forward(sa, sa["V"][0] @ sa["V"][0].T)) for sa, _ in sys]
     noise = [_noise(sd, c_mults[0 if shared_noise else s], d_mults[0 if shared_noise else s]) for s, (_, sd) in enumerate(sys)]
     rng = np.random.default_rng(seed + 1)
-    d = {"hand": 2, "pointmass": 2}.get(name, x)                  # observed dims of the compiled tuple
+    d = d if d is not None else {"hand": 2, "pointmass": 2}.get(name, x)   # observed dims of the compiled tuple
     X = S.sdn_simulate(sys[0][0], sys[0][1], *gains[0], *noise[0], N, rng)[0][..., :d].astype(np.float32)
     ref = np.stack([S.sdn_log_likelihood(sa, sd, Lk[0], Lk[1], nz[0] if c_mults[0] else [], nz[1] if d_mults[0] else [],
                                          X.astype(np.float64)) for (sa, sd), Lk, nz in zip(sys, gains, noise)])
@@ -222,3 +222,28 @@ def test_public_api_sdn_likelihood_and_fd_gradient():
         e = np.zeros_like(th); e[p] = h
         g_ref = (total_np(th + e) - total_np(th - e)) / (2 * h)
         assert abs(float(g[p]) - g_ref) <= 1e-4 * abs(g_ref) + 1e-7, (names[p], float(g[p]), g_ref)
+
+
+def test_all_fp64_path_point_mass_with_four_observed_states_on_host():
+    """Tuple (4,4,1,3,4) is compiled for the all-FP64 per-trial kernel only (lqgk_dims.h: LQGK_FOR_EACH_FP64_ONLY_DIMS)."""
+    lib = abi.Library(H.EMUL_PATH)
+    ll, ref, _ = _run_library(lib, torch.device("cpu"), "pointmass", 2, 3, [0.0] * 2, [0.0] * 2, torch.float64, T_=60, d=4)
+    assert np.allclose(ll, ref, rtol=1e-8), np.abs(ll / ref - 1).max()
+
+
+@pytest.mark.gpu
+def test_log_likelihood_fp64_point_mass_all_states_observed():
+    """PointMassBoundedActor with all four states observed (lqg/tracking/point_mass.py:7-47): innovation covariance with condition
+    number ~1e9, out of reach of the FP32 per-trial arithmetic of the main path -> System.log_likelihood_fp64."""
+    from lqg_b200.tracking import PointMassBoundedActor
+    dev = torch.device("cuda:0")
+    T_ = 200
+    mats = O.point_mass_mats()
+    sa, sd = O.make_system(mats, T_)
+    X = O.simulate(sa, sd, 5, np.random.default_rng(11))
+    ref = O.log_likelihood(sa, sd, X)
+    model = PointMassBoundedActor(T=T_, dtype=torch.float64, device=dev)
+    ll = model.log_likelihood_fp64(torch.tensor(X, device=dev))
+    # observations are FP32 at the C ABI: evaluate the oracle on the same rounded data
+    ref32 = O.log_likelihood(sa, sd, X.astype(np.float32).astype(np.float64))
+    assert np.allclose(ll.cpu().numpy(), ref32, rtol=1e-6), (ll.cpu().numpy(), ref32, ref)
