@@ -219,27 +219,28 @@ def bench_c2(dev, barrier, reps=10):
     # the same evaluation replayed from a CUDA graph (lqg_b200.graphs): the local part is captured, the all-reduce stays outside
     from lqg_b200.graphs import GraphedValueAndGrad
     lo, hi = parallel.shard_range(len(sig), *parallel.world())
-    ms_graph = None
+    # EVERY rank runs the same sequence of collectives below, also the ranks that own no condition (more GPUs than conditions:
+    # 8 ranks, 6 conditions) -- they contribute zeros.  (A rank-dependent number of all-reduces deadlocks NCCL.)
+    gv, idx = None, cond[lo:hi]
+    th = torch.tensor([1.0, 0.5, 1.0, 0.5, 6.0] + sig, device=dev)
     if hi > lo:
-        idx = cond[lo:hi]
-
         def fn(theta):   # theta = [5 shared | 6 sigma_target]
             m = SubjectiveActor(dim=2, T=T, device=dev, action_cost=theta[0], action_variability=theta[1], subj_noise=theta[2],
                                 subj_vel_noise=theta[3], sigma_cursor=theta[4], sigma_target=theta[5:][idx])
             return m.log_likelihood(x[idx])
 
-        th = torch.tensor([1.0, 0.5, 1.0, 0.5, 6.0] + sig, device=dev)
         gv = GraphedValueAndGrad(fn, th)
 
-        def graphed():
+    def graphed():
+        if gv is not None:
             out, grad = gv(th)
             packed = torch.cat([out.sum().reshape(1), grad])
-            return parallel.allreduce_sum(packed)
+        else:
+            packed = torch.zeros(1 + th.numel(), device=dev)
+        return parallel.allreduce_sum(packed)
 
-        ms_graph, packed = timed(graphed, reps, 3, barrier)
-        assert torch.allclose(packed[0], ll, rtol=1e-5) and torch.allclose(packed[1:], g, rtol=1e-3, atol=1e-4 * g.abs().max().item())
-    else:
-        barrier(); barrier()
+    ms_graph, packed = timed(graphed, reps, 3, barrier)
+    assert torch.allclose(packed[0], ll, rtol=1e-5) and torch.allclose(packed[1:], g, rtol=1e-3, atol=1e-4 * g.abs().max().item())
     return ms, ms_graph
 
 
@@ -411,7 +412,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a collective mismatch must fail within minutes, not after NCCL's default 10-minute watchdog
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     lib = abi.load_library()
     if args.streams > 0:
         lib.set_streams(args.streams)

@@ -64,3 +64,36 @@ def test_single_process_is_a_noop():
     t = torch.ones(3)
     assert parallel.allreduce_sum(t) is t
     assert parallel.world() == (0, 1)
+
+
+def _worker_more_ranks_than_units(rank, world_size, port, out_dir):
+    """3 ranks, 2 conditions (bench.py's c2 at 8 GPUs has 6 conditions): the rank without work contributes zeros and runs the
+    SAME collectives as the others -- a rank-dependent number of all-reduces deadlocks NCCL (seen once at N=8)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        cond = torch.arange(2)
+        w = torch.tensor([2.0, 5.0], dtype=torch.float64)
+
+        def local(idx):
+            if idx.numel() == 0:
+                return torch.zeros((), dtype=torch.float64), torch.zeros(2, dtype=torch.float64)
+            g = torch.zeros(2, dtype=torch.float64)
+            g[idx] = w[idx]
+            return w[idx].sum(), g
+
+        for _ in range(3):                                            # same count of collectives on every rank
+            tot, g = parallel.trial_sharded_value_and_grad(local, cond)
+            assert tot.item() == 7.0 and torch.equal(g, w)
+        lo, hi = parallel.shard_range(2, rank, world_size)
+        packed = torch.cat([w[lo:hi].sum().reshape(1), torch.zeros(2, dtype=torch.float64)]) if hi > lo else torch.zeros(3, dtype=torch.float64)
+        assert parallel.allreduce_sum(packed)[0].item() == 7.0
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_more_ranks_than_work_units(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker_more_ranks_than_units, args=(3, port, str(tmp_path)), nprocs=3, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(3))

@@ -247,3 +247,21 @@ def test_log_likelihood_fp64_point_mass_all_states_observed():
     # observations are FP32 at the C ABI: evaluate the oracle on the same rounded data
     ref32 = O.log_likelihood(sa, sd, X.astype(np.float32).astype(np.float64))
     assert np.allclose(ll.cpu().numpy(), ref32, rtol=1e-6), (ll.cpu().numpy(), ref32, ref)
+
+
+@pytest.mark.gpu
+def test_per_condition_data_sets():
+    """x_sample_stride != 0: every parameter sample (experimental condition) has its own trials (config c2's layout)."""
+    from lqg_b200.tracking import SubjectiveActor
+    dev = torch.device("cuda:0")
+    T_, N, sig = 50, 4, [8.5, 19.9, 51.6]
+    ref, xs = [], []
+    for c, st in enumerate(sig):
+        _, sa, sd, L, K = _system("subjective", T=T_, sigma_target=st)
+        C, D = _channel_noise_np(sd, 40.0, 0.4)
+        X = S.sdn_simulate(sa, sd, L, K, C, D, N, np.random.default_rng(20 + c))[0].astype(np.float32)
+        xs.append(X)
+        ref.append(S.sdn_log_likelihood(sa, sd, L, K, C, D, X.astype(np.float64)))
+    model = SubjectiveActor(dim=1, T=T_, dtype=torch.float64, device=dev, sigma_target=torch.tensor(sig, dtype=torch.float64, device=dev))
+    ll = model.log_likelihood_sdn(torch.tensor(np.stack(xs), device=dev), signal_dep_noise=40.0, obs_dep_noise=0.4)
+    assert tuple(ll.shape) == (3, N) and np.allclose(ll.cpu().numpy(), np.stack(ref), rtol=1e-8)
