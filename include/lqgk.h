@@ -150,6 +150,14 @@ typedef struct {
 } LqgkSdnSpec;
 int lqgk_sdn_gains_f64(const LqgkSdnDims* dims, const LqgkSdnSpec* spec, double* L_out, double* K_out, double* cost_out,
                        void* stream);
+/* lqgk_sdn_gains_filter_f64: the same alternating iterations in the REFERENCE's conventions (filter form):
+ *     u = L xhat,   xp = A xhat + B u,   xhat' = xp + K (y' - H xp),   y' = H x' + om + sum_i eta_i D_i x'   (y' observes x_{t+1}),
+ *   i.e. lqg/system.py:110-124 with the multiplicative terms; Sigma1 / xhat1 are the prior covariance / mean of x_0.  With
+ *   nc = nd = 0 ONE sweep reproduces lqr.backward (lqg/control/lqr.py:16-42; same sign) and kf.forward (lqg/belief/kf.py:6-21)
+ *   exactly; the gains plug into lqgk_sdn_loglik_* / lqgk_simulate_*.  Derivation and validation: oracle/sdn_np.py
+ *   (filter_backward_pass / filter_forward_pass: Monte Carlo cost, exact policy evaluation, coordinate-wise optimality).   */
+int lqgk_sdn_gains_filter_f64(const LqgkSdnDims* dims, const LqgkSdnSpec* spec, double* L_out, double* K_out, double* cost_out,
+                              void* stream);
 
 /* lqgk_sdn_loglik_*: log-likelihood under signal-dependent noise -- the reference's experimenter-side filter
  *   (lqg/system.py:142-248, same filter-form conventions as lqg/system.py:110-124) extended by multiplicative noise

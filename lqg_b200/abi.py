@@ -282,7 +282,7 @@ class Library:
     PROFILE_KINDS = ("pack", "lqr_fwd", "kf_fwd", "cov_fwd", "trial_fwd", "misc", "trial_rev", "cov_rev", "kf_rev",
                      "lqr_rev", "unpack", "cov_contrib", "reduce")
 
-    def sdn_gains(self, mats: Dict[str, torch.Tensor], T: int, sweeps: int = 10, stream=0):
+    def sdn_gains(self, mats: Dict[str, torch.Tensor], T: int, sweeps: int = 10, stream=0, filter_form: bool = False):
         """Signal-dependent-noise gains (extension, include/lqgk.h).  mats: float64 CUDA tensors A[S?,b,b], B[S?,b,u],
         H[S?,y,b], C[S?,nc,b,u], D[S?,nd,y,b], Q, R, (Qf), Om_xi, Om_omega, Sigma1, xhat1[S?,b]; a leading sample axis is
         optional per tensor (absent / size 1 = shared).  Returns L[S,T,u,b], K[S,T,b,y], cost[S]."""
@@ -300,7 +300,7 @@ class Library:
             if v is None or v.numel() == 0:
                 setattr(sp, k, LqgkMat(None, 0, 0))
                 continue
-            assert v.dtype == torch.float64 and v.is_cuda, k
+            assert v.dtype == torch.float64 and (v.is_cuda or not hasattr(self.lib, "lqgk_init")), k   # (host tensors: test harness only)
             v = v.contiguous()
             keep.append(v)
             lead = v.dim() - base_nd[k]
@@ -311,11 +311,12 @@ class Library:
         dims = LqgkSdnDims(S, T, b, u, y, nc, nd, sweeps)
         dev = A.device
         L = torch.empty((S, T, u, b), dtype=torch.float64, device=dev)
-        K = torch.empty((S, T, b, y), dtype=torch.float64, device=dev)
+        K = torch.zeros((S, T, b, y), dtype=torch.float64, device=dev)   # sweeps = 0 leaves K = 0 (the iterations' starting point)
         cost = torch.empty((S,), dtype=torch.float64, device=dev)
-        rc = self.lib.lqgk_sdn_gains_f64(C.byref(dims), C.byref(sp), C.c_void_p(L.data_ptr()), C.c_void_p(K.data_ptr()),
-                                         C.c_void_p(cost.data_ptr()), C.c_void_p(stream))
-        self._check(rc, "lqgk_sdn_gains_f64")
+        fn = self.lib.lqgk_sdn_gains_filter_f64 if filter_form else self.lib.lqgk_sdn_gains_f64
+        rc = fn(C.byref(dims), C.byref(sp), C.c_void_p(L.data_ptr()), C.c_void_p(K.data_ptr()), C.c_void_p(cost.data_ptr()),
+                C.c_void_p(stream))
+        self._check(rc, "lqgk_sdn_gains" + ("_filter" if filter_form else "") + "_f64")
         return L, K, cost
 
     def sdn_loglik(self, dims, actor, dyn, L, K, x_tm, C_noise=None, D_noise=None, stream=0):

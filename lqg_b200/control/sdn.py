@@ -19,9 +19,12 @@ class SDNGains(NamedTuple):
 
 
 def solve(A, B, H, Q, R, Om_xi, Om_omega, Sigma1, xhat1, T: int, C: Optional[Sequence] = None, D: Optional[Sequence] = None,
-          Qf=None, sweeps: int = 10) -> SDNGains:
+          Qf=None, sweeps: int = 10, form: str = "predictor") -> SDNGains:
     """All arguments CUDA tensors (cast to float64); any of them may carry a leading parameter-sample axis S.
-    ``C``: control-dependent noise matrices [nc, b, u] (or [S, nc, b, u]); ``D``: state-dependent observation noise [nd, y, b]."""
+    ``C``: control-dependent noise matrices [nc, b, u] (or [S, nc, b, u]); ``D``: state-dependent observation noise [nd, y, b].
+    ``form``: "predictor" = the paper's convention (u = -L xhat, xhat' = A xhat + B u + K (y - H xhat)); "filter" = the
+    reference's (u = L xhat, xhat' = xp + K (y' - H xp), lqg/system.py:110-124): without multiplicative noise exactly
+    lqr.backward / kf.forward, and the gains plug into ``System.log_likelihood_sdn(gains=(L, K))``."""
     dev = A.device
     if dev.type != "cuda":
         raise RuntimeError("lqg_b200 has no CPU fallback: tensors must live on a CUDA device")
@@ -29,11 +32,49 @@ def solve(A, B, H, Q, R, Om_xi, Om_omega, Sigma1, xhat1, T: int, C: Optional[Seq
     mats = dict(A=f(A), B=f(B), H=f(H), Q=f(Q), R=f(R), Qf=f(Qf), Om_xi=f(Om_xi), Om_omega=f(Om_omega), Sigma1=f(Sigma1), xhat1=f(xhat1),
                 C=None if C is None else f(C if torch.is_tensor(C) else torch.stack(list(C))),
                 D=None if D is None else f(D if torch.is_tensor(D) else torch.stack(list(D))))
-    L, K, cost = abi.load_library().sdn_gains(mats, T, sweeps, stream=torch.cuda.current_stream(dev).cuda_stream)
+    if form not in ("predictor", "filter"):
+        raise ValueError(form)
+    L, K, cost = abi.load_library().sdn_gains(mats, T, sweeps, stream=torch.cuda.current_stream(dev).cuda_stream,
+                                              filter_form=form == "filter")
     return SDNGains(L, K, cost)
 
 
+def solve_for_actor(system, signal_dep_noise=None, obs_dep_noise=None, C=None, D=None, Sigma0=None, xhat0=None, sweeps: int = 6) -> SDNGains:
+    """Filter-form gains of ``system``'s ACTOR model under signal-dependent noise (what replaces ``lqr.backward(actor)`` /
+    ``kf.forward(actor)`` of lqg/system.py:157-161 when the actor plans and filters knowing about the multiplicative noise).
+    Noise either as per-channel scales on the actor's own B / F (``channel_noise`` on the actor spec) or as explicit
+    ``C[(S,) nc, b, u]``, ``D[(S,) nd, y, b]``.  Time-invariant specs."""
+    a = system.actor
+    base = lambda M: M[..., 0, :, :]
+    A, Bm, F, V, W, Q, R = (base(getattr(a, k)) for k in ("A", "B", "F", "V", "W", "Q", "R"))
+    if C is None and signal_dep_noise is not None:
+        C = _channel(Bm, signal_dep_noise, control=True)
+    if D is None and obs_dep_noise is not None:
+        D = _channel(F, obs_dep_noise, control=False)
+    mT = lambda M: M.transpose(-1, -2)
+    Om_xi, Om_om = V @ mT(V), W @ mT(W)
+    S0 = Om_xi if Sigma0 is None else torch.as_tensor(Sigma0, dtype=A.dtype, device=A.device)     # system.py:158-161 default
+    xh = torch.zeros(A.shape[-1], dtype=A.dtype, device=A.device) if xhat0 is None else torch.as_tensor(xhat0, dtype=A.dtype, device=A.device)
+    Qf = a.Qf if a.Qf.dim() == Q.dim() else a.Qf[..., 0, :, :] if a.Qf.dim() > Q.dim() else a.Qf
+    return solve(A, Bm, F, Q, R, Om_xi, Om_om, S0, xh, a.A.shape[-3], C=C, D=D, Qf=Qf, sweeps=sweeps, form="filter")
+
+
 # ------------------------------------------------------------------------------------------------ likelihood side
+def _channel(M: torch.Tensor, scale, control: bool) -> torch.Tensor:
+    """control: [B[:, i] e_i^T]_i from the input map M = B[(S,) x, u]; else [e_j e_j^T F]_j from the observation map M = F[(S,) y, x]."""
+    scale = torch.as_tensor(scale, dtype=M.dtype, device=M.device)
+    if control:
+        u = M.shape[-1]
+        mats = [M * torch.nn.functional.one_hot(torch.tensor(i), u).to(M) for i in range(u)]
+    else:
+        y = M.shape[-2]
+        mats = [M * torch.nn.functional.one_hot(torch.tensor(j), y).to(M)[:, None] for j in range(y)]
+    out = torch.stack(mats, -3)
+    if scale.dim() == 1 and out.dim() == 3:
+        out = out.unsqueeze(0)
+    return out * scale.reshape(scale.shape + (1, 1, 1)) if scale.dim() else out * scale
+
+
 def channel_noise(system, scale, kind: str) -> torch.Tensor:
     """Per-channel proportional noise matrices for ``System.log_likelihood_sdn`` in the reference's filter-form model
     (lqg/system.py:110-124 plus the multiplicative terms, oracle/sdn_np.py):
@@ -45,20 +86,11 @@ def channel_noise(system, scale, kind: str) -> torch.Tensor:
 
     ``scale``: scalar or batched like the model parameters ([S]).  Returns [(S,) nc, x, u] / [(S,) nd, y, x]."""
     dyn = system.dynamics
-    Bd, Fd = dyn.B[..., 0, :, :], dyn.F[..., 0, :, :]
-    scale = torch.as_tensor(scale, dtype=Bd.dtype, device=Bd.device)
     if kind == "control":
-        u = Bd.shape[-1]
-        mats = [Bd * torch.nn.functional.one_hot(torch.tensor(i), u).to(Bd) for i in range(u)]            # B_d[:, i] e_i^T
-    elif kind == "observation":
-        y = Fd.shape[-2]
-        mats = [Fd * torch.nn.functional.one_hot(torch.tensor(j), y).to(Fd)[:, None] for j in range(y)]   # e_j e_j^T F_d
-    else:
-        raise ValueError(kind)
-    M = torch.stack(mats, -3)
-    if scale.dim() == 1 and M.dim() == 3:
-        M = M.unsqueeze(0)
-    return M * scale.reshape(scale.shape + (1, 1, 1)) if scale.dim() else M * scale
+        return _channel(dyn.B[..., 0, :, :], scale, control=True)
+    if kind == "observation":
+        return _channel(dyn.F[..., 0, :, :], scale, control=False)
+    raise ValueError(kind)
 
 
 def value_and_grad_fd(fn, theta: torch.Tensor, rel_step: float = 1e-5, abs_step: float = 1e-7):

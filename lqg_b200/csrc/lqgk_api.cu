@@ -229,7 +229,7 @@ __global__ void k_peak_fma(int iters, T* sink) {
 }
 extern "C" {
 
-int lqgk_sdn_gains_f64(const LqgkSdnDims* d, const LqgkSdnSpec* sp, double* L_out, double* K_out, double* cost_out, void* stream) {
+static int sdn_gains_impl(const LqgkSdnDims* d, const LqgkSdnSpec* sp, double* L_out, double* K_out, double* cost_out, void* stream, int filter_form) {
   g_launches = 0;
   if (!d || !sp || !L_out || !K_out) return LQGK_E_INVALID;
   if (d->S <= 0 || d->T <= 0 || d->b <= 0 || d->u <= 0 || d->y <= 0 || d->nc < 0 || d->nd < 0 || d->sweeps < 0) return LQGK_E_INVALID;
@@ -253,12 +253,19 @@ int lqgk_sdn_gains_f64(const LqgkSdnDims* d, const LqgkSdnSpec* sp, double* L_ou
   if (!sp->xhat1.ptr) return LQGK_E_INVALID;
   a.xh1 = P(sp->xhat1); a.sxh1 = sp->xhat1.sample_stride;
   a.S = d->S; a.T = d->T; a.nc = d->nc; a.nd = d->nd; a.sweeps = d->sweeps;
-  a.L = L_out; a.K = K_out; a.cost = cost_out;
+  a.L = L_out; a.K = K_out; a.cost = cost_out; a.filter_form = filter_form;
 #define LQGK_CASE(X, B, U, Y, DD) \
   if (X + B <= 12 && d->b == B && d->u == U && d->y == Y) return Runner<X, B, U, Y, DD>::run_sdn(a, (cudaStream_t)stream);
   LQGK_FOR_EACH_DIMS(LQGK_CASE)
 #undef LQGK_CASE
   return LQGK_E_UNSUPPORTED;
+}
+
+int lqgk_sdn_gains_f64(const LqgkSdnDims* d, const LqgkSdnSpec* sp, double* L_out, double* K_out, double* cost_out, void* stream) {
+  return sdn_gains_impl(d, sp, L_out, K_out, cost_out, stream, 0);
+}
+int lqgk_sdn_gains_filter_f64(const LqgkSdnDims* d, const LqgkSdnSpec* sp, double* L_out, double* K_out, double* cost_out, void* stream) {
+  return sdn_gains_impl(d, sp, L_out, K_out, cost_out, stream, 1);
 }
 
 int lqgk_sdn_loglik_f32(const LqgkDims* dims, const LqgkSpec* actor, const LqgkSpec* dynamics, const LqgkSdnNoise* noise, const float* L,

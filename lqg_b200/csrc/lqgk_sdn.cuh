@@ -21,6 +21,7 @@ struct SdnArgs {
   long long sA, sB, sH, sC, sD, sQ, sR, sQf, sOmxi, sOmom, sSig1, sxh1;   // elements between samples (0 = shared)
   int S, T, nc, nd, sweeps;
   double *L, *K, *cost;
+  int filter_form;   // 0: Todorov's predictor form (u = -L xhat); 1: the reference's filter form (u = L xhat, lqr.py / kf.py conventions)
 };
 
 template <class DM>
@@ -179,6 +180,198 @@ struct Sdn {
       symmetrize<B>(Sxn);
       LQGK_UNROLL64 for (int i = 0; i < B * B; ++i) { Se[i] = Sen[i]; Sx[i] = Sxn[i]; Sxe[i] = Sxen[i]; }
     }
+  }
+  // ------------------------------------------------------------------------------------------------ FILTER form
+  // The same alternating iterations in the reference's own conventions (spec and derivation: oracle/sdn_np.py,
+  // filter_backward_pass / filter_forward_pass):  u = L xhat;  xp = A xhat + B u;  xhat' = xp + K (y' - H xp) with y' observing
+  // x_{t+1}.  Without multiplicative noise the backward pass IS lqr.backward (lqg/control/lqr.py:16-42, P = 0, no affine
+  // terms) and the forward pass IS kf.forward (lqg/belief/kf.py:6-21).
+  LQGK_HD static double backward_filter(const SdnArgs& a, int s, const double* A, const double* Bm, const double* H, const double* Q,
+                                        const double* R, const double* Qf, const double* Omxi, const double* Omom, const double* Sig1,
+                                        const double* xh1, bool k_is_zero) {
+    double Sx[B * B], Se[B * B], sc = 0.0;
+    LQGK_UNROLL64 for (int i = 0; i < B * B; ++i) { Sx[i] = Qf[i]; Se[i] = 0.0; }
+    for (int t = a.T - 1; t >= 0; --t) {
+      double Kt[B * Y], IKF[B * B], St[B * B], Wm[B * B], T1[B * B];
+      const double* kp = a.K + ((size_t)s * a.T + t) * (B * Y);
+      LQGK_UNROLL64 for (int i = 0; i < B * Y; ++i) Kt[i] = k_is_zero ? 0.0 : kp[i];
+      LQGK_UNROLL64 for (int i = 0; i < B; ++i) LQGK_UNROLL64 for (int j = 0; j < B; ++j) {
+        double w = i == j ? 1.0 : 0.0;
+        LQGK_UNROLL64 for (int k = 0; k < Y; ++k) w -= Kt[i * Y + k] * H[k * B + j];
+        IKF[i * B + j] = w;                                  // I - K H
+      }
+      LQGK_UNROLL64 for (int i = 0; i < B * B; ++i) St[i] = Sx[i];
+      for (int c = 0; c < a.nd; ++c) {                       // St = Sx + sum_j D_j' K' Se K D_j
+        const double* Di = a.D + (size_t)s * a.sD + (size_t)c * (Y * B);
+        double KDm[B * B], Dl[Y * B], SKD[B * B];
+        LQGK_UNROLL64 for (int i = 0; i < Y * B; ++i) Dl[i] = Di[i];
+        mm<B, Y, B>(Kt, Dl, KDm);
+        mm<B, B, B>(Se, KDm, SKD);
+        mm_tn<B, B, B, true>(KDm, SKD, St);
+      }
+      mm<B, B, B>(Se, IKF, T1);
+      LQGK_UNROLL64 for (int i = 0; i < B * B; ++i) Wm[i] = St[i];
+      mm_tn<B, B, B, true>(IKF, T1, Wm);                     // Wm = St + (I-KH)' Se (I-KH)
+      double SB[B * U], SA[B * B], M[U * U], G[U * B];
+      mm<B, B, U>(St, Bm, SB);
+      mm<B, B, B>(St, A, SA);
+      LQGK_UNROLL64 for (int i = 0; i < U * U; ++i) M[i] = R[i];
+      mm_tn<U, B, U, true>(Bm, SB, M);                       // R + B' St B
+      for (int c = 0; c < a.nc; ++c) {                       // + sum_i C_i' Wm C_i
+        const double* Ci = a.C + (size_t)s * a.sC + (size_t)c * (B * U);
+        double SC[B * U], Cl[B * U];
+        LQGK_UNROLL64 for (int i = 0; i < B * U; ++i) Cl[i] = Ci[i];
+        mm<B, B, U>(Wm, Cl, SC);
+        mm_tn<U, B, U, true>(Cl, SC, M);
+      }
+      mm_tn<U, B, B>(Bm, SA, G);                             // B' St A
+      double Mi[U * U], Li[U * U], Lt[U * B];
+      symmetrize<U>(M);
+      chol_and_inverse<U>(M, Li);
+      mm_tn<U, U, U>(Li, Li, Mi);
+      mm<U, U, B>(Mi, G, Lt);
+      LQGK_UNROLL64 for (int i = 0; i < U * B; ++i) Lt[i] = -Lt[i];   // L_t = -H^-1 B' St A
+      double* lp = a.L + ((size_t)s * a.T + t) * (U * B);
+      LQGK_UNROLL64 for (int i = 0; i < U * B; ++i) lp[i] = Lt[i];
+      // s += tr(St Om_xi) + tr(Se ((I-KH) Om_xi (I-KH)' + K Om_om K'))
+      double KO[B * Y], KOK[B * B], IO[B * B];
+      mm<B, Y, Y>(Kt, Omom, KO);
+      mm_nt<B, Y, B>(KO, Kt, KOK);
+      mm<B, B, B>(IKF, Omxi, IO);
+      mm_nt<B, B, B, true>(IO, IKF, KOK);
+      LQGK_UNROLL64 for (int i = 0; i < B; ++i) LQGK_UNROLL64 for (int j = 0; j < B; ++j)
+        sc += St[i * B + j] * Omxi[j * B + i] + Se[i * B + j] * KOK[j * B + i];
+      // Sx' = Q + A' St (A + B L) ;  Se' = -A' St B L + ((I-KH)A)' Se (I-KH)A
+      double ABL[B * B], Ab[B * B], Sxn[B * B], Sen[B * B];
+      LQGK_UNROLL64 for (int i = 0; i < B * B; ++i) ABL[i] = A[i];
+      mm<B, U, B, true>(Bm, Lt, ABL);
+      mm<B, B, B>(IKF, A, Ab);
+      LQGK_UNROLL64 for (int i = 0; i < B * B; ++i) Sxn[i] = Q[i];
+      mm_tn<B, B, B, true>(SA, ABL, Sxn);                    // (St A)' (A + B L)
+      mm<B, B, B>(Se, Ab, T1);
+      mm_tn<B, B, B>(Ab, T1, Sen);
+      LQGK_UNROLL64 for (int i = 0; i < B; ++i) LQGK_UNROLL64 for (int j = 0; j < B; ++j) {
+        double v = 0.0;                                      // A' St B L = (St A)' (B L) ; B L = ABL - A
+        LQGK_UNROLL64 for (int k = 0; k < B; ++k) v += SA[k * B + i] * (ABL[k * B + j] - A[k * B + j]);
+        Sen[i * B + j] -= v;
+      }
+      symmetrize<B>(Sxn);
+      symmetrize<B>(Sen);
+      LQGK_UNROLL64 for (int i = 0; i < B * B; ++i) { Sx[i] = Sxn[i]; Se[i] = Sen[i]; }
+    }
+    double cost = sc;
+    LQGK_UNROLL64 for (int i = 0; i < B; ++i) LQGK_UNROLL64 for (int j = 0; j < B; ++j)
+      cost += xh1[i] * Sx[i * B + j] * xh1[j] + (Sx[i * B + j] + Se[i * B + j]) * Sig1[j * B + i];
+    return cost;
+  }
+
+  LQGK_HD static void forward_filter(const SdnArgs& a, int s, const double* A, const double* Bm, const double* H, const double* Omxi,
+                                     const double* Omom, const double* Sig1, const double* xh1) {
+    double Se[B * B], Sx[B * B], Sxe[B * B];
+    LQGK_UNROLL64 for (int i = 0; i < B; ++i) LQGK_UNROLL64 for (int j = 0; j < B; ++j) {
+      Se[i * B + j] = Sig1[i * B + j];
+      Sx[i * B + j] = xh1[i] * xh1[j];
+      Sxe[i * B + j] = 0.0;
+    }
+    for (int t = 0; t < a.T; ++t) {
+      double Lt[U * B], ABL[B * B];
+      const double* lp = a.L + ((size_t)s * a.T + t) * (U * B);
+      LQGK_UNROLL64 for (int i = 0; i < U * B; ++i) Lt[i] = lp[i];
+      LQGK_UNROLL64 for (int i = 0; i < B * B; ++i) ABL[i] = A[i];
+      mm<B, U, B, true>(Bm, Lt, ABL);                        // A + B L
+      // P- = A Se A' + Om_xi + sum_i C_i L Sx L' C_i'
+      double T1[B * B], Pm[B * B], ASA[B * B];
+      mm<B, B, B>(A, Se, T1);
+      mm_nt<B, B, B>(T1, A, ASA);
+      LQGK_UNROLL64 for (int i = 0; i < B * B; ++i) Pm[i] = ASA[i] + Omxi[i];
+      if (a.nc > 0) {
+        double LS[U * B], U2[U * U];
+        mm<U, B, B>(Lt, Sx, LS);
+        mm_nt<U, B, U>(LS, Lt, U2);                          // L Sx L'
+        for (int c = 0; c < a.nc; ++c) {
+          const double* Ci = a.C + (size_t)s * a.sC + (size_t)c * (B * U);
+          double Cl[B * U], CU[B * U];
+          LQGK_UNROLL64 for (int i = 0; i < B * U; ++i) Cl[i] = Ci[i];
+          mm<B, U, U>(Cl, U2, CU);
+          mm_nt<B, U, B, true>(CU, Cl, Pm);
+        }
+      }
+      symmetrize<B>(Pm);
+      // Reff = Om_om + sum_j D_j E[x'x''] D_j' ,  E[x'x''] = (A+BL) Sx (A+BL)' + (A+BL) Sxe A' + A Sxe' (A+BL)' + P-
+      double Reff[Y * Y], xa[B * B];
+      mm_nt<B, B, B>(Sxe, A, xa);                            // E[xhat a'] = Sxe A'
+      LQGK_UNROLL64 for (int i = 0; i < Y * Y; ++i) Reff[i] = Omom[i];
+      if (a.nd > 0) {
+        double X2[B * B], T2[B * B];
+        mm<B, B, B>(ABL, Sx, T2);
+        LQGK_UNROLL64 for (int i = 0; i < B * B; ++i) X2[i] = Pm[i];
+        mm_nt<B, B, B, true>(T2, ABL, X2);
+        mm<B, B, B>(ABL, xa, T2);                            // (A+BL) Sxe A'
+        LQGK_UNROLL64 for (int i = 0; i < B; ++i) LQGK_UNROLL64 for (int j = 0; j < B; ++j) X2[i * B + j] += T2[i * B + j] + T2[j * B + i];
+        for (int c = 0; c < a.nd; ++c) {
+          const double* Di = a.D + (size_t)s * a.sD + (size_t)c * (Y * B);
+          double Dl[Y * B], DT[Y * B];
+          LQGK_UNROLL64 for (int i = 0; i < Y * B; ++i) Dl[i] = Di[i];
+          mm<Y, B, B>(Dl, X2, DT);
+          mm_nt<Y, B, Y, true>(DT, Dl, Reff);
+        }
+      }
+      // K = P- H' (H P- H' + Reff)^-1
+      double HP[Y * B], G[Y * Y], Li[Y * Y], Gi[Y * Y], Kt[B * Y];
+      mm<Y, B, B>(H, Pm, HP);
+      LQGK_UNROLL64 for (int i = 0; i < Y * Y; ++i) G[i] = Reff[i];
+      mm_nt<Y, B, Y, true>(HP, H, G);
+      symmetrize<Y>(G);
+      chol_and_inverse<Y>(G, Li);
+      mm_tn<Y, Y, Y>(Li, Li, Gi);
+      mm_tn<B, Y, Y>(HP, Gi, Kt);                            // (H P-)' G^-1
+      double* kp = a.K + ((size_t)s * a.T + t) * (B * Y);
+      LQGK_UNROLL64 for (int i = 0; i < B * Y; ++i) kp[i] = Kt[i];
+      // moments of (xhat', e'):  IKF = I - K H
+      double IKF[B * B], KH[B * B], KRK[B * B], KR[B * Y];
+      mm<B, Y, B>(Kt, H, KH);
+      LQGK_UNROLL64 for (int i = 0; i < B; ++i) LQGK_UNROLL64 for (int j = 0; j < B; ++j) IKF[i * B + j] = (i == j ? 1.0 : 0.0) - KH[i * B + j];
+      mm<B, Y, Y>(Kt, Reff, KR);
+      mm_nt<B, Y, B>(KR, Kt, KRK);                           // K Reff K'
+      double Sen[B * B], Sxn[B * B], Sxen[B * B], T3[B * B], T4[B * B];
+      mm<B, B, B>(IKF, Pm, T3);                              // (I-KH) P-
+      LQGK_UNROLL64 for (int i = 0; i < B * B; ++i) Sen[i] = KRK[i];
+      mm_nt<B, B, B, true>(T3, IKF, Sen);                    // Se' = (I-KH) P- (I-KH)' + K Reff K'
+      mm<B, B, B>(ABL, Sx, T4);
+      LQGK_UNROLL64 for (int i = 0; i < B * B; ++i) Sxn[i] = KRK[i];
+      mm_nt<B, B, B, true>(T4, ABL, Sxn);                    // (A+BL) Sx (A+BL)' + K Reff K'
+      double KHP[B * B], AX[B * B];
+      mm<B, B, B>(KH, Pm, KHP);                              // K H P-
+      mm_nt<B, B, B, true>(KHP, KH, Sxn);                    // + K H P- H' K'
+      mm<B, B, B>(ABL, xa, AX);                              // (A+BL) E[xhat a']
+      mm_nt<B, B, B>(AX, KH, T4);                            // (A+BL) xa H' K'
+      LQGK_UNROLL64 for (int i = 0; i < B; ++i) LQGK_UNROLL64 for (int j = 0; j < B; ++j) Sxn[i * B + j] += T4[i * B + j] + T4[j * B + i];
+      mm_nt<B, B, B>(AX, IKF, Sxen);                         // Sxe' = (A+BL) xa (I-KH)' + K H P- (I-KH)' - K Reff K'
+      mm_nt<B, B, B, true>(KHP, IKF, Sxen);
+      LQGK_UNROLL64 for (int i = 0; i < B * B; ++i) Sxen[i] -= KRK[i];
+      symmetrize<B>(Sen);
+      symmetrize<B>(Sxn);
+      LQGK_UNROLL64 for (int i = 0; i < B * B; ++i) { Se[i] = Sen[i]; Sx[i] = Sxn[i]; Sxe[i] = Sxen[i]; }
+    }
+  }
+  // all sweeps of one parameter sample (shared by the kernel and the CPU test harness); returns the expected cost
+  LQGK_HD static double solve(const SdnArgs& a, int s) {
+    double A[B * B], Bm[B * U], H[Y * B], Q[B * B], R[U * U], Qf[B * B], Omxi[B * B], Omom[Y * Y], Sig1[B * B], xh1[B];
+    auto ld = [&](const double* p, long long stride, double* out, int n) { for (int i = 0; i < n; ++i) out[i] = p[(size_t)s * stride + i]; };
+    ld(a.A, a.sA, A, B * B); ld(a.B, a.sB, Bm, B * U); ld(a.H, a.sH, H, Y * B); ld(a.Q, a.sQ, Q, B * B); ld(a.R, a.sR, R, U * U);
+    ld(a.Qf, a.sQf, Qf, B * B); ld(a.Omxi, a.sOmxi, Omxi, B * B); ld(a.Omom, a.sOmom, Omom, Y * Y); ld(a.Sig1, a.sSig1, Sig1, B * B);
+    ld(a.xh1, a.sxh1, xh1, B);
+    for (int sw = 0; sw < a.sweeps; ++sw) {
+      if (a.filter_form) {
+        backward_filter(a, s, A, Bm, H, Q, R, Qf, Omxi, Omom, Sig1, xh1, sw == 0);
+        forward_filter(a, s, A, Bm, H, Omxi, Omom, Sig1, xh1);
+      } else {
+        backward(a, s, A, Bm, H, Q, R, Qf, Omxi, Omom, Sig1, xh1, sw == 0);
+        forward(a, s, A, Bm, H, Omxi, Omom, Sig1, xh1);
+      }
+    }
+    return a.filter_form ? backward_filter(a, s, A, Bm, H, Q, R, Qf, Omxi, Omom, Sig1, xh1, a.sweeps == 0)
+                         : backward(a, s, A, Bm, H, Q, R, Qf, Omxi, Omom, Sig1, xh1, a.sweeps == 0);
   }
 };
 
@@ -356,19 +549,9 @@ struct SdnLik {
 #if defined(__CUDACC__)
 template <class DM>
 __global__ void __launch_bounds__(32) k_sdn_gains(SdnArgs a) {
-  constexpr int B = DM::B, U = DM::U, Y = DM::Y;
   const int s = blockIdx.x * 32 + threadIdx.x;
   if (s >= a.S) return;
-  double A[B * B], Bm[B * U], H[Y * B], Q[B * B], R[U * U], Qf[B * B], Omxi[B * B], Omom[Y * Y], Sig1[B * B], xh1[B];
-  auto ld = [&](const double* p, long long stride, double* out, int n) { for (int i = 0; i < n; ++i) out[i] = p[(size_t)s * stride + i]; };
-  ld(a.A, a.sA, A, B * B); ld(a.B, a.sB, Bm, B * U); ld(a.H, a.sH, H, Y * B); ld(a.Q, a.sQ, Q, B * B); ld(a.R, a.sR, R, U * U);
-  ld(a.Qf, a.sQf, Qf, B * B); ld(a.Omxi, a.sOmxi, Omxi, B * B); ld(a.Omom, a.sOmom, Omom, Y * Y); ld(a.Sig1, a.sSig1, Sig1, B * B);
-  ld(a.xh1, a.sxh1, xh1, B);
-  for (int sw = 0; sw < a.sweeps; ++sw) {
-    Sdn<DM>::backward(a, s, A, Bm, H, Q, R, Qf, Omxi, Omom, Sig1, xh1, sw == 0);
-    Sdn<DM>::forward(a, s, A, Bm, H, Omxi, Omom, Sig1, xh1);
-  }
-  const double cost = Sdn<DM>::backward(a, s, A, Bm, H, Q, R, Qf, Omxi, Omom, Sig1, xh1, a.sweeps == 0);
+  const double cost = Sdn<DM>::solve(a, s);
   if (a.cost) a.cost[s] = cost;
 }
 // one thread per (parameter sample, trial) system

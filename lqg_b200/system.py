@@ -176,16 +176,17 @@ class System:
         observation noise on top of V, W; the experimenter's filter (system.py:142-248) matches the first two moments of
         every predictive distribution.  Noise model: either the scalars ``signal_dep_noise`` / ``obs_dep_noise`` (per-channel
         proportional noise, lqg_b200.control.sdn.channel_noise; parameters may be batched like the model's own) or explicit
-        matrices ``C[(S,) nc, x, u]``, ``D[(S,) nd, y, x]``.  ``gains``: (L, K) to use instead of the actor model's own
-        lqr.backward / kf.forward (e.g. from lqg_b200.control.sdn.solve)."""
+        matrices ``C[(S,) nc, x, u]``, ``D[(S,) nd, y, x]``.  ``gains``: None = the actor model's own lqr.backward / kf.forward
+        (an actor unaware of the multiplicative noise), ``"sdn"`` = the filter-form Todorov iterations on the actor's model with
+        the same per-channel scales (lqg_b200.control.sdn.solve_for_actor), or an explicit pair (L, K)."""
         from lqg_b200.control import sdn
         axis = getattr(self, "_axis_system", None)
-        if axis is not None and C is None and D is None and gains is None and Sigma0 is None and x.shape[-1] == self.xdim:
+        if axis is not None and C is None and D is None and (gains is None or gains == "sdn") and Sigma0 is None and x.shape[-1] == self.xdim:
             # per-channel noise keeps the axes of a dim > 1 tracking model independent: same factorisation as log_likelihood
             lead, (n, T1, d) = x.shape[:-3], x.shape[-3:]
             dim = self.dim
             xa = x.reshape(*lead, n, T1, dim, d // dim).movedim(-2, -4).reshape(*lead, dim * n, T1, d // dim)
-            ll = axis.log_likelihood_sdn(xa, signal_dep_noise=signal_dep_noise, obs_dep_noise=obs_dep_noise)
+            ll = axis.log_likelihood_sdn(xa, signal_dep_noise=signal_dep_noise, obs_dep_noise=obs_dep_noise, gains=gains)
             return ll.reshape(*ll.shape[:-1], dim, n).sum(-2)
         if C is None and signal_dep_noise is not None:
             C = sdn.channel_noise(self, signal_dep_noise, "control")
@@ -194,6 +195,12 @@ class System:
         if gains is None:
             g, K = self._gains(Sigma0)
             L = g.L
+        elif isinstance(gains, str):
+            if gains != "sdn":
+                raise ValueError("gains must be None, 'sdn' or a pair (L, K)")
+            # the actor plans and filters knowing about the multiplicative noise: filter-form Todorov iterations on its own model
+            sg = sdn.solve_for_actor(self, signal_dep_noise=signal_dep_noise, obs_dep_noise=obs_dep_noise, Sigma0=Sigma0)
+            L, K = (sg.L, sg.K) if self.actor.A.dim() == 4 else (sg.L[0], sg.K[0])
         else:
             L, K = gains
         return runtime.sdn_log_likelihood(self.actor, self.dynamics, x.to(self.device), L, K, C=C, D=D)

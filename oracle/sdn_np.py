@@ -210,3 +210,118 @@ def sdn_simulate(actor, dyn, L, K, C, D, n, rng, x0=None, xhat0=None, l=None):
         xh[:, t + 1] = xp + (yv - xp @ actor["F"][t].T) @ K[t].T
         xs[:, t + 1] = xn
     return xs, xh
+
+
+# =========================================================================================== gains under signal-dependent noise, FILTER form
+# The alternating iterations of Todorov (2005) re-derived for the reference's own conventions (lqg/system.py:110-124,
+# lqg/control/lqr.py:16-42, lqg/belief/kf.py:6-21), so that without multiplicative noise they ARE lqr.backward / kf.forward:
+#     u_t = L_t xhat_t ;  x_{t+1} = A x_t + B u_t + xi + sum_i eps_i C_i u_t ;  y_{t+1} = F x_{t+1} + om + sum_j eta_j D_j x_{t+1}
+#     xp = A xhat_t + B u_t ;  xhat_{t+1} = xp + K_t (y_{t+1} - F xp) ;  cost = sum_{t<T} (x'Qx + u'Ru) + x_T' Qf x_T
+# (one model: the actor plans and filters with its own A, B, F, V, W, as lqr.backward(actor) / kf.forward(actor) do).
+# With e = x - xhat, a = A e + xi + sum_i eps_i C_i u (prior error of x_{t+1}) and b = om + sum_j eta_j D_j x_{t+1}:
+#     e_{t+1} = (I - K F) a - K b ,   cost-to-go  v_t(x, e) = x' Sx_t x + e' Se_t e + s_t   (exact for the given later gains):
+#     St = Sx + sum_j D_j' K' Se K D_j ;  H = R + B' St B + sum_i C_i' (St + (I-KF)' Se (I-KF)) C_i ;  L = -H^-1 B' St A
+#     Sx <- Q + A' St (A + B L) ;  Se <- A' St B H^-1 B' St A + ((I-KF)A)' Se (I-KF)A ;  s <- s + tr(St Om_xi) + tr(Se ((I-KF) Om_xi (I-KF)' + K Om_om K'))
+#     forward:  P- = A Sig_e A' + Om_xi + sum_i C_i L Sig_xh L' C_i' ;  Reff = Om_om + sum_j D_j E[x'x''] D_j' ;  K = P- F' (F P- F' + Reff)^-1
+def filter_backward_pass(A, B, F, C, D, Q, R, Qf, Om_xi, Om_om, K):
+    """K[T,b,y] -> L[T,u,b] (reference sign: u = L xhat) and (Sx_0, Se_0, s_0)."""
+    T = K.shape[0]
+    b, u = B.shape
+    L = np.zeros((T, u, b))
+    Sx, Se, s = Qf.copy(), np.zeros((b, b)), 0.0
+    I = np.eye(b)
+    for t in range(T - 1, -1, -1):
+        Kt = K[t]
+        IKF = I - Kt @ F
+        St = Sx + sum(Dj.T @ Kt.T @ Se @ Kt @ Dj for Dj in D)
+        H = R + B.T @ St @ B + sum(Ci.T @ (St + IKF.T @ Se @ IKF) @ Ci for Ci in C)
+        L[t] = -np.linalg.solve(H, B.T @ St @ A)
+        s = s + np.trace(St @ Om_xi) + np.trace(Se @ (IKF @ Om_xi @ IKF.T + Kt @ Om_om @ Kt.T))
+        Abar = IKF @ A
+        Se_new = -A.T @ St @ B @ L[t] + Abar.T @ Se @ Abar
+        Sx_new = Q + A.T @ St @ (A + B @ L[t])
+        Sx, Se = 0.5 * (Sx_new + Sx_new.T), 0.5 * (Se_new + Se_new.T)
+    return L, (Sx, Se, s)
+
+
+def _filter_step_moments(A, B, F, C, D, Om_xi, Om_om, Lt, Se, Sx, Sxe):
+    """Prior error covariance P-, effective observation-noise covariance Reff and E[x_{t+1} x_{t+1}'] from the moments of
+    (xhat_t, e_t): Se = E[e e'], Sx = E[xhat xhat'], Sxe = E[xhat e']."""
+    ABL = A + B @ Lt
+    ctrl = sum(Ci @ Lt @ Sx @ Lt.T @ Ci.T for Ci in C) if C else 0.0
+    Pm = A @ Se @ A.T + Om_xi + ctrl
+    X2 = ABL @ Sx @ ABL.T + A @ Se @ A.T + ABL @ Sxe @ A.T + A @ Sxe.T @ ABL.T + Om_xi + ctrl
+    Reff = Om_om + (sum(Dj @ X2 @ Dj.T for Dj in D) if D else 0.0)
+    return ABL, Pm, Reff, X2
+
+
+def _filter_advance_moments(A, F, ABL, Pm, Reff, Kt, Sx, Sxe):
+    IKF = np.eye(A.shape[0]) - Kt @ F
+    xa = Sxe @ A.T                                                   # E[xhat a']
+    Se_n = IKF @ Pm @ IKF.T + Kt @ Reff @ Kt.T
+    Sx_n = ABL @ Sx @ ABL.T + Kt @ F @ Pm @ F.T @ Kt.T + Kt @ Reff @ Kt.T + ABL @ xa @ F.T @ Kt.T + Kt @ F @ xa.T @ ABL.T
+    Sxe_n = ABL @ xa @ IKF.T + Kt @ F @ Pm @ IKF.T - Kt @ Reff @ Kt.T
+    return 0.5 * (Se_n + Se_n.T), 0.5 * (Sx_n + Sx_n.T), Sxe_n
+
+
+def filter_forward_pass(A, B, F, C, D, Om_xi, Om_om, Sigma0, xhat0, L):
+    """L[T,u,b] -> K[T,b,y] (filter form, kf.py:10-14 with the signal-dependent terms)."""
+    T = L.shape[0]
+    b, y = A.shape[0], F.shape[0]
+    K = np.zeros((T, b, y))
+    Se, Sx, Sxe = Sigma0.copy(), np.outer(xhat0, xhat0), np.zeros((b, b))
+    for t in range(T):
+        ABL, Pm, Reff, _ = _filter_step_moments(A, B, F, C, D, Om_xi, Om_om, L[t], Se, Sx, Sxe)
+        K[t] = Pm @ F.T @ np.linalg.inv(F @ Pm @ F.T + Reff)
+        Se, Sx, Sxe = _filter_advance_moments(A, F, ABL, Pm, Reff, K[t], Sx, Sxe)
+    return K
+
+
+def filter_solve(A, B, F, C, D, Q, R, Qf, Om_xi, Om_om, Sigma0, xhat0, T, sweeps=10):
+    """Alternating iterations starting from K = 0.  Returns L[T,u,b], K[T,b,y], expected cost."""
+    b, y = A.shape[0], F.shape[0]
+    K = np.zeros((T, b, y))
+    for _ in range(sweeps):
+        L, _ = filter_backward_pass(A, B, F, C, D, Q, R, Qf, Om_xi, Om_om, K)
+        K = filter_forward_pass(A, B, F, C, D, Om_xi, Om_om, Sigma0, xhat0, L)
+    L, (Sx, Se, s) = filter_backward_pass(A, B, F, C, D, Q, R, Qf, Om_xi, Om_om, K)
+    cost = float(xhat0 @ Sx @ xhat0 + np.trace((Sx + Se) @ Sigma0) + s)
+    return L, K, cost
+
+
+def filter_expected_cost(A, B, F, C, D, Q, R, Qf, Om_xi, Om_om, Sigma0, xhat0, L, K):
+    """EXACT expected total cost of ARBITRARY gains (L, K) by propagating the second moments of (xhat, e)."""
+    T = L.shape[0]
+    Se, Sx, Sxe = Sigma0.copy(), np.outer(xhat0, xhat0), np.zeros_like(Sigma0)
+    cost = 0.0
+    for t in range(T):
+        Exx = Sx + Se + Sxe + Sxe.T                                   # E[x x'], x = xhat + e
+        cost += np.trace(Q @ Exx) + np.trace(L[t].T @ R @ L[t] @ Sx)
+        ABL, Pm, Reff, _ = _filter_step_moments(A, B, F, C, D, Om_xi, Om_om, L[t], Se, Sx, Sxe)
+        Se, Sx, Sxe = _filter_advance_moments(A, F, ABL, Pm, Reff, K[t], Sx, Sxe)
+    return float(cost + np.trace(Qf @ (Sx + Se + Sxe + Sxe.T)))
+
+
+def filter_simulate_cost(A, B, F, C, D, Q, R, Qf, Om_xi, Om_om, Sigma0, xhat0, L, K, n, rng):
+    """Monte Carlo estimate (mean, standard error) of the total cost of the filter-form closed loop with gains L, K."""
+    T = L.shape[0]
+    b, y = A.shape[0], F.shape[0]
+    chol = lambda M: np.linalg.cholesky(M + 1e-300 * np.eye(M.shape[0])) if np.any(M) else np.zeros_like(M)
+    cxi, com, c0 = chol(Om_xi), chol(Om_om), chol(Sigma0)
+    xh = np.tile(xhat0, (n, 1))
+    x = xh + rng.standard_normal((n, b)) @ c0.T
+    cost = np.zeros(n)
+    for t in range(T):
+        u = xh @ L[t].T
+        cost += np.einsum("ni,ij,nj->n", x, Q, x) + np.einsum("ni,ij,nj->n", u, R, u)
+        xn = x @ A.T + u @ B.T + rng.standard_normal((n, b)) @ cxi.T
+        for Ci in C:
+            xn = xn + rng.standard_normal((n, 1)) * (u @ Ci.T)
+        yv = xn @ F.T + rng.standard_normal((n, y)) @ com.T
+        for Dj in D:
+            yv = yv + rng.standard_normal((n, 1)) * (xn @ Dj.T)
+        xp = xh @ A.T + u @ B.T
+        xh = xp + (yv - xp @ F.T) @ K[t].T
+        x = xn
+    cost += np.einsum("ni,ij,nj->n", x, Qf, x)
+    return float(cost.mean()), float(cost.std() / np.sqrt(n))

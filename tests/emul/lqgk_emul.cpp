@@ -214,7 +214,43 @@ static int sdn_loglik_host(const LqgkDims* d, const LqgkSpec* act, const LqgkSpe
 #undef LQGK_CASE
   return LQGK_E_UNSUPPORTED;
 }
+static int sdn_gains_host(const LqgkSdnDims* d, const LqgkSdnSpec* sp, double* L_out, double* K_out, double* cost_out, int filter_form) {
+  if (!d || !sp || !L_out || !K_out) return LQGK_E_INVALID;
+  SdnArgs a{};
+  auto P = [](const LqgkMat& m) { return (const double*)m.ptr; };
+  a.A = P(sp->A); a.sA = sp->A.sample_stride;
+  a.B = P(sp->B); a.sB = sp->B.sample_stride;
+  a.H = P(sp->H); a.sH = sp->H.sample_stride;
+  a.C = P(sp->C); a.sC = sp->C.sample_stride;
+  a.D = P(sp->D); a.sD = sp->D.sample_stride;
+  a.Q = P(sp->Q); a.sQ = sp->Q.sample_stride;
+  a.R = P(sp->R); a.sR = sp->R.sample_stride;
+  a.Qf = sp->Qf.ptr ? P(sp->Qf) : P(sp->Q); a.sQf = sp->Qf.ptr ? sp->Qf.sample_stride : sp->Q.sample_stride;
+  a.Omxi = P(sp->Om_xi); a.sOmxi = sp->Om_xi.sample_stride;
+  a.Omom = P(sp->Om_omega); a.sOmom = sp->Om_omega.sample_stride;
+  a.Sig1 = P(sp->Sigma1); a.sSig1 = sp->Sigma1.sample_stride;
+  a.xh1 = P(sp->xhat1); a.sxh1 = sp->xhat1.sample_stride;
+  a.S = d->S; a.T = d->T; a.nc = d->nc; a.nd = d->nd; a.sweeps = d->sweeps;
+  a.L = L_out; a.K = K_out; a.cost = cost_out; a.filter_form = filter_form;
+#define LQGK_CASE(X, B, U, Y, DD)                                             \
+  if (X + B <= 12 && d->b == B && d->u == U && d->y == Y) {                   \
+    for (int s = 0; s < a.S; ++s) {                                           \
+      const double c = Sdn<Dims<X, B, U, Y, DD>>::solve(a, s);                \
+      if (cost_out) cost_out[s] = c;                                          \
+    }                                                                         \
+    return LQGK_OK;                                                           \
+  }
+  LQGK_FOR_EACH_DIMS(LQGK_CASE)
+#undef LQGK_CASE
+  return LQGK_E_UNSUPPORTED;
+}
 extern "C" {
+int lqgk_sdn_gains_f64(const LqgkSdnDims* d, const LqgkSdnSpec* sp, double* L_out, double* K_out, double* cost_out, void*) {
+  return sdn_gains_host(d, sp, L_out, K_out, cost_out, 0);
+}
+int lqgk_sdn_gains_filter_f64(const LqgkSdnDims* d, const LqgkSdnSpec* sp, double* L_out, double* K_out, double* cost_out, void*) {
+  return sdn_gains_host(d, sp, L_out, K_out, cost_out, 1);
+}
 int lqgk_sdn_loglik_f64(const LqgkDims* dims, const LqgkSpec* actor, const LqgkSpec* dynamics, const LqgkSdnNoise* noise, const double* L,
                         const double* K, const float* x_tm, double* ll_out, void*) {
   return sdn_loglik_host<double>(dims, actor, dynamics, noise, L, K, x_tm, ll_out);

@@ -82,3 +82,93 @@ def test_cuda_kernel_two_dimensional_system():
     Kr = O.kf_forward(spec, Om_xi)
     assert np.allclose(g.L[0].cpu().numpy(), -Lr, rtol=1e-9, atol=1e-12)
     assert np.allclose(g.K[0].cpu().numpy(), a["A"] @ Kr, rtol=1e-8, atol=1e-11)
+
+
+# ------------------------------------------------------------------------------------------------ filter form (the reference's conventions)
+def _filter_kw(p):
+    return dict(A=p["A"], B=p["B"], F=p["H"], Q=p["Q"], R=p["R"], Qf=p["Qf"], Om_xi=p["Om_xi"], Om_om=p["Om_om"])
+
+
+def test_filter_form_without_multiplicative_noise_is_exactly_the_reference():
+    """C = D = 0: ONE sweep gives lqr.backward's L (same sign, lqg/control/lqr.py:16-42) and kf.forward's K (lqg/belief/kf.py:6-21)."""
+    p = S.tracking_example()
+    V, W = np.linalg.cholesky(p["Om_xi"]), np.linalg.cholesky(p["Om_om"])
+    spec = O.time_stack_spec(p["A"], p["B"], p["H"], V, W, p["Q"], p["R"], T)
+    Sigma0 = V @ V.T
+    L, K, _ = S.filter_solve(C=[], D=[], Sigma0=Sigma0, xhat0=p["xhat1"], T=T, sweeps=1, **_filter_kw(p))
+    Lr, _, _ = O.lqr_backward(spec)
+    Kr = O.kf_forward(spec, Sigma0)
+    assert np.allclose(L, Lr, rtol=1e-12, atol=1e-14) and np.allclose(K, Kr, rtol=1e-12, atol=1e-14)
+
+
+def test_filter_form_cost_monte_carlo_exact_evaluation_and_optimality():
+    p = S.tracking_example(c_mult=20.0, d_mult=0.5)
+    kw = dict(C=p["C"], D=p["D"], Sigma0=p["Sigma1"], xhat0=p["xhat1"], **_filter_kw(p))
+    c1 = S.filter_solve(T=T, sweeps=1, **kw)[2]
+    L8, K8, c8 = S.filter_solve(T=T, sweeps=8, **kw)
+    L9, K9, c9 = S.filter_solve(T=T, sweeps=9, **kw)
+    assert c8 <= c1 + 1e-9 and abs(c9 - c8) < 1e-9 * abs(c8) and np.abs(L9 - L8).max() < 1e-8 and np.abs(K9 - K8).max() < 1e-8
+    # the value-function cost equals the exact second-moment evaluation of the same gains ...
+    ce = S.filter_expected_cost(L=L9, K=K9, **kw)
+    assert abs(ce - c9) < 1e-9 * abs(c9)
+    # ... and the Monte Carlo cost of the simulated closed loop
+    m, se = S.filter_simulate_cost(L=L9, K=K9, n=200000, rng=np.random.default_rng(0), **kw)
+    assert abs(m - c9) < 4 * se, (m, se, c9)
+    # coordinate-wise optimality: perturbing any single L_t or K_t raises the exactly evaluated cost
+    rng = np.random.default_rng(1)
+    for t in (0, 7, 31, T - 1):
+        L2, K2 = L9.copy(), K9.copy()
+        L2[t] += 1e-2 * np.abs(L9[t]).max() * rng.standard_normal(L9[t].shape)
+        K2[t] += 1e-2 * max(np.abs(K9[t]).max(), 1e-3) * rng.standard_normal(K9[t].shape)
+        assert S.filter_expected_cost(L=L2, K=K9, **kw) > ce and S.filter_expected_cost(L=L9, K=K2, **kw) >= ce
+    # knowing about the multiplicative noise pays: the plain LQG gains cost more under it
+    Lp, Kp, _ = S.filter_solve(T=T, sweeps=1, **dict(kw, C=[], D=[]))
+    assert S.filter_expected_cost(L=Lp, K=Kp, **kw) > 1.05 * ce
+
+
+def _filter_library_vs_oracle(lib, dev, sweeps, n=9):
+    rng = np.random.default_rng(3)
+    ps = [S.tracking_example(c_mult=20.0 * np.exp(0.3 * rng.standard_normal()), d_mult=0.5 * np.exp(0.3 * rng.standard_normal()),
+                             action_cost=float(np.exp(0.3 * rng.standard_normal())), sigma_target=6.0 * np.exp(0.2 * rng.standard_normal()))
+          for _ in range(n)]
+    t = lambda k: torch.tensor(np.stack([np.stack(p[k]) if isinstance(p[k], list) else p[k] for p in ps]), device=dev)
+    mats = dict(A=t("A")[0], B=t("B")[0], H=t("H")[0], Q=t("Q")[0], R=t("R"), Qf=None, Om_xi=t("Om_xi")[0], Om_omega=t("Om_om"),
+                Sigma1=t("Sigma1")[0], xhat1=t("xhat1")[0], C=t("C"), D=t("D"))
+    L, K, cost = lib.sdn_gains(mats, T, sweeps, filter_form=True)
+    if dev.type == "cuda":
+        torch.cuda.synchronize()
+    for i, p in enumerate(ps):
+        Lr, Kr, cr = S.filter_solve(C=p["C"], D=p["D"], Sigma0=p["Sigma1"], xhat0=p["xhat1"], T=T, sweeps=sweeps, **_filter_kw(p))
+        assert np.allclose(L[i].cpu().numpy(), Lr, rtol=1e-9, atol=1e-11), (i, np.abs(L[i].cpu().numpy() - Lr).max())
+        assert np.allclose(K[i].cpu().numpy(), Kr, rtol=1e-9, atol=1e-11)
+        assert abs(cost[i].item() - cr) < 1e-9 * abs(cr)
+
+
+@pytest.mark.parametrize("sweeps", [0, 1, 5])
+def test_filter_form_step_functions_match_oracle_on_host(sweeps):
+    from lqg_b200 import abi
+    from tests import helpers as H
+    _filter_library_vs_oracle(abi.Library(H.EMUL_PATH), torch.device("cpu"), sweeps)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sweeps", [0, 1, 6])
+def test_filter_form_cuda_kernel_matches_oracle(sweeps):
+    from lqg_b200 import abi
+    _filter_library_vs_oracle(abi.load_library(), torch.device("cuda:0"), sweeps, n=37)
+
+
+@pytest.mark.gpu
+def test_solve_for_actor_reproduces_reference_gains_and_feeds_the_sdn_likelihood():
+    from lqg_b200.control import sdn
+    from lqg_b200.tracking import SubjectiveActor
+    dev = torch.device("cuda:0")
+    model = SubjectiveActor(dim=1, T=80, dtype=torch.float64, device=dev)
+    g0 = sdn.solve_for_actor(model, sweeps=1)                                  # no multiplicative noise
+    gains, K = model._gains()
+    assert torch.allclose(g0.L[0], gains.L, rtol=1e-9, atol=1e-12) and torch.allclose(g0.K[0], K, rtol=1e-9, atol=1e-12)
+    g = sdn.solve_for_actor(model, signal_dep_noise=40.0, obs_dep_noise=0.4)
+    x = model.simulate(3, n=5)[..., :2].to(torch.float32)
+    ll_plain = model.log_likelihood_sdn(x, signal_dep_noise=40.0, obs_dep_noise=0.4)
+    ll_sdn = model.log_likelihood_sdn(x, signal_dep_noise=40.0, obs_dep_noise=0.4, gains=(g.L[0], g.K[0]))
+    assert torch.isfinite(ll_sdn).all() and not torch.allclose(ll_sdn, ll_plain)

@@ -265,3 +265,51 @@ def test_per_condition_data_sets():
     model = SubjectiveActor(dim=1, T=T_, dtype=torch.float64, device=dev, sigma_target=torch.tensor(sig, dtype=torch.float64, device=dev))
     ll = model.log_likelihood_sdn(torch.tensor(np.stack(xs), device=dev), signal_dep_noise=40.0, obs_dep_noise=0.4)
     assert tuple(ll.shape) == (3, N) and np.allclose(ll.cpu().numpy(), np.stack(ref), rtol=1e-8)
+
+
+def _route_python_api_to_host_harness(monkeypatch):
+    """Runs the torch-facing API (lqg_b200.system / runtime / control.sdn) on HOST tensors against the CPU build of the kernels'
+    step functions (tests/emul), so that `-m "not gpu"` covers the Python plumbing above the C ABI.  Test-only: the product path
+    refuses CPU tensors and any library but the CUDA one."""
+    from lqg_b200 import runtime
+    from lqg_b200.control import sdn
+    lib = abi.Library(H.EMUL_PATH)
+
+    def solve(A, B, Hm, Q, R, Om_xi, Om_omega, Sigma1, xhat1, T, C=None, D=None, Qf=None, sweeps=10, form="predictor"):
+        f = lambda v: None if v is None else torch.as_tensor(v).to(torch.float64)
+        mats = dict(A=f(A), B=f(B), H=f(Hm), Q=f(Q), R=f(R), Qf=f(Qf), Om_xi=f(Om_xi), Om_omega=f(Om_omega), Sigma1=f(Sigma1),
+                    xhat1=f(xhat1), C=f(C), D=f(D))
+        return sdn.SDNGains(*lib.sdn_gains(mats, T, sweeps, filter_form=form == "filter"))
+
+    monkeypatch.setattr(sdn, "solve", solve)
+    monkeypatch.setattr(runtime, "_require_cuda", lambda *a, **k: None)
+    monkeypatch.setattr(runtime, "_stream", lambda dev: 0)
+    monkeypatch.setattr(abi, "load_library", lambda: lib)
+    monkeypatch.setattr(lib, "pack_obs", lambda x, stream=0: x.permute(1, 0, 2).to(torch.float32).contiguous(), raising=False)
+    return lib
+
+
+def test_python_api_with_sdn_aware_actor_on_host(monkeypatch):
+    """System.log_likelihood_sdn(gains="sdn") of a 2-axis model: per-axis factorisation -> filter-form gain iterations on the
+    actor's model -> per-trial likelihood, against the oracle evaluated on the full 2-axis system."""
+    from lqg_b200.tracking import SubjectiveActor
+    _route_python_api_to_host_harness(monkeypatch)
+    T_ = 40
+    model = SubjectiveActor(dim=2, T=T_, dtype=torch.float64)
+    _, sa, sd, _, _ = _system("subjective2", T=T_)
+    Ca, Da = _channel_noise_np(sa, 40.0, 0.4)                       # the actor's own input / observation maps
+    A0 = {k: sa[k][0] for k in "ABFVWQR"}
+    Lo, Ko, _ = S.filter_solve(A=A0["A"], B=A0["B"], F=A0["F"], C=Ca, D=Da, Q=A0["Q"], R=A0["R"], Qf=A0["Q"], Om_xi=A0["V"] @ A0["V"].T,
+                               Om_om=A0["W"] @ A0["W"].T, Sigma0=A0["V"] @ A0["V"].T, xhat0=np.zeros(6), T=T_, sweeps=6)
+    C, D = _channel_noise_np(sd, 40.0, 0.4)
+    X = S.sdn_simulate(sa, sd, Lo, Ko, C, D, 3, np.random.default_rng(0))[0].astype(np.float32)
+    ref = S.sdn_log_likelihood(sa, sd, Lo, Ko, C, D, X.astype(np.float64))
+    ll = model.log_likelihood_sdn(torch.tensor(X), signal_dep_noise=40.0, obs_dep_noise=0.4, gains="sdn")
+    assert np.allclose(ll.numpy(), ref, rtol=1e-9), np.abs(ll.numpy() - ref).max()
+    # an actor unaware of the multiplicative noise (the reference's own gains) gives a different likelihood
+    # (explicit gains: the unfactorised 2-axis kernel; lqr.backward / kf.forward themselves need the GPU)
+    L0, _, _ = O.lqr_backward(sa)
+    K0 = O.kf_forward(sa, sa["V"][0] @ sa["V"][0].T)
+    ll_plain = model.log_likelihood_sdn(torch.tensor(X), signal_dep_noise=40.0, obs_dep_noise=0.4, gains=(torch.tensor(L0), torch.tensor(K0)))
+    assert np.allclose(ll_plain.numpy(), S.sdn_log_likelihood(sa, sd, L0, K0, C, D, X.astype(np.float64)), rtol=1e-9)
+    assert np.abs(ll_plain.numpy() - ll.numpy()).max() > 1e-3
