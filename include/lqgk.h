@@ -176,6 +176,14 @@ int lqgk_sdn_loglik_f32(const LqgkDims* dims, const LqgkSpec* actor, const LqgkS
                         const float* L, const float* K, const float* x_tm, float* ll_out, void* stream);
 int lqgk_sdn_loglik_f64(const LqgkDims* dims, const LqgkSpec* actor, const LqgkSpec* dynamics, const LqgkSdnNoise* noise,
                         const double* L, const double* K, const float* x_tm, double* ll_out, void* stream);
+/* lqgk_sdn_simulate_*: lqgk_simulate_* for the generative model of lqgk_sdn_loglik_* (lqg/system.py:62-140 plus the multiplicative
+ *   terms; oracle/sdn_np.py: sdn_simulate); noise == NULL or nc = nd = 0 draws exactly the trajectories of lqgk_simulate_*.      */
+int lqgk_sdn_simulate_f32(const LqgkDims* dims, const LqgkSpec* actor, const LqgkSpec* dynamics, const LqgkSdnNoise* noise,
+                          const float* L, const float* l, const float* K, const float* x0, const float* xhat0, uint64_t seed,
+                          float* x_out, float* xhat_out, float* y_out, float* u_out, void* stream);
+int lqgk_sdn_simulate_f64(const LqgkDims* dims, const LqgkSpec* actor, const LqgkSpec* dynamics, const LqgkSdnNoise* noise,
+                          const double* L, const double* l, const double* K, const double* x0, const double* xhat0, uint64_t seed,
+                          double* x_out, double* xhat_out, double* y_out, double* u_out, void* stream);
 
 /* ---- helpers ------------------------------------------------------------------------------------------ */
 /* x[N][T+1][d] (f32 or f64, trial-major as in the reference) -> x_tm[T+1][N][d] float. */

@@ -250,8 +250,25 @@ class Library:
                     "lqgk_moments")
         return mu, Sig
 
-    def simulate(self, dims, actor, dyn, L, l, K, seed, x0=None, xhat0=None, return_all=False, stream=0):
-        """Batched System.simulate: x[S, N, T+1, x] (and xhat, y, u when return_all) for the given gains."""
+    def _noise(self, dims, dt, C_noise, D_noise, keep):
+        """LqgkSdnNoise from C_noise[S?, nc, x, u], D_noise[S?, nd, y, x] (None = none); tensors kept alive in `keep`."""
+        nz = LqgkSdnNoise()
+        for name, v, shp in (("C", C_noise, (dims.x, dims.u)), ("D", D_noise, (dims.y, dims.x))):
+            if v is None or v.numel() == 0:
+                setattr(nz, name, LqgkMat(None, 0, 0))
+                setattr(nz, "n" + name.lower(), 0)
+                continue
+            v = v.to(dt).contiguous()
+            keep.append(v)
+            assert tuple(v.shape[-2:]) == shp and v.dim() in (3, 4), (name, tuple(v.shape))
+            ss = v.stride(0) if v.dim() == 4 and v.shape[0] == dims.S and dims.S > 1 else 0
+            setattr(nz, name, LqgkMat(v.data_ptr(), ss, 0))
+            setattr(nz, "n" + name.lower(), v.shape[-3])
+        return nz
+
+    def simulate(self, dims, actor, dyn, L, l, K, seed, x0=None, xhat0=None, return_all=False, stream=0, C_noise=None, D_noise=None):
+        """Batched System.simulate: x[S, N, T+1, x] (and xhat, y, u when return_all) for the given gains.  C_noise / D_noise:
+        multiplicative-noise matrices of the signal-dependent-noise extension (lqgk_sdn_simulate_*)."""
         dt, dev = actor["A"].dtype, actor["A"].device
         S, T, N = dims.S, dims.T, dims.N
         x = torch.empty((S, N, T + 1, dims.x), dtype=dt, device=dev)
@@ -261,9 +278,15 @@ class Library:
         sa, sd = self._spec(actor, S, T, ACTOR_KEYS), self._spec(dyn, S, T, DYN_KEYS)
         keep = [t.to(dt).contiguous() if t is not None else None for t in (L, l, K, x0, xhat0)]
         ptr = lambda t: C.c_void_p(t.data_ptr() if t is not None else None)
-        fn = getattr(self.lib, "lqgk_simulate_" + self._suffix(dt))
-        self._check(fn(C.byref(dims), C.byref(sa), C.byref(sd), ptr(keep[0]), ptr(keep[1]), ptr(keep[2]), ptr(keep[3]), ptr(keep[4]),
-                       C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF), ptr(x), ptr(xh), ptr(y), ptr(u), C.c_void_p(stream)), "lqgk_simulate")
+        tail = (ptr(keep[0]), ptr(keep[1]), ptr(keep[2]), ptr(keep[3]), ptr(keep[4]), C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF),
+                ptr(x), ptr(xh), ptr(y), ptr(u), C.c_void_p(stream))
+        if C_noise is None and D_noise is None:
+            fn = getattr(self.lib, "lqgk_simulate_" + self._suffix(dt))
+            self._check(fn(C.byref(dims), C.byref(sa), C.byref(sd), *tail), "lqgk_simulate")
+        else:
+            nz = self._noise(dims, dt, C_noise, D_noise, keep)
+            fn = getattr(self.lib, "lqgk_sdn_simulate_" + self._suffix(dt))
+            self._check(fn(C.byref(dims), C.byref(sa), C.byref(sd), C.byref(nz), *tail), "lqgk_sdn_simulate")
         return (x, xh, y, u) if return_all else x
 
     def pack_obs(self, x: torch.Tensor, stream=0) -> torch.Tensor:
@@ -329,18 +352,7 @@ class Library:
         sa, sd = self._spec(actor, S, T, ACTOR_KEYS), self._spec(dyn, S, T, DYN_KEYS)
         keep = [L.to(dt).contiguous(), K.to(dt).contiguous()]
         assert tuple(keep[0].shape) == (S, T, dims.u, dims.b) and tuple(keep[1].shape) == (S, T, dims.b, dims.y)
-        nz = LqgkSdnNoise()
-        for name, v, shp in (("C", C_noise, (dims.x, dims.u)), ("D", D_noise, (dims.y, dims.x))):
-            if v is None or v.numel() == 0:
-                setattr(nz, name, LqgkMat(None, 0, 0))
-                setattr(nz, "n" + name.lower(), 0)
-                continue
-            v = v.to(dt).contiguous()
-            keep.append(v)
-            assert tuple(v.shape[-2:]) == shp and v.dim() in (3, 4), (name, tuple(v.shape))
-            ss = v.stride(0) if v.dim() == 4 and v.shape[0] == S and S > 1 else 0
-            setattr(nz, name, LqgkMat(v.data_ptr(), ss, 0))
-            setattr(nz, "n" + name.lower(), v.shape[-3])
+        nz = self._noise(dims, dt, C_noise, D_noise, keep)
         ll = torch.empty((S, dims.N), dtype=dt, device=dev)
         fn = getattr(self.lib, "lqgk_sdn_loglik_" + self._suffix(dt))
         self._check(fn(C.byref(dims), C.byref(sa), C.byref(sd), C.byref(nz), C.c_void_p(keep[0].data_ptr()),

@@ -88,6 +88,9 @@ struct SimArgs {
   T *x_out, *xhat_out, *y_out, *u_out;
   int S, N, Tn, x, b, u, y;
   unsigned long long seed;
+  // signal-dependent noise (extension, oracle/sdn_np.py: sdn_simulate): x += sum_i eps'_i C_i u,  y += sum_j eta'_j D_j x_new
+  LqgkMat Cn, Dn;   // C[nc][x][u], D[nd][y][x] per sample (sample_stride 0 = shared)
+  int nc, nd;
 };
 template <class T>
 __global__ void k_simulate(SimArgs<T> a) {
@@ -97,7 +100,7 @@ __global__ void k_simulate(SimArgs<T> a) {
   const int x = a.x, b = a.b, u = a.u, y = a.y, Tn = a.Tn;
   curandStatePhilox4_32_10_t rng;
   curand_init(a.seed, idx, 0, &rng);
-  double xv[SIM_MAX], xh[SIM_MAX], xn[SIM_MAX], xp[SIM_MAX], yv[SIM_MAX], uv[SIM_MAX], nz[2 * SIM_MAX + 4];
+  double xv[SIM_MAX], xh[SIM_MAX], xn[SIM_MAX], xp[SIM_MAX], yv[SIM_MAX], uv[SIM_MAX], nz[2 * SIM_MAX + 2 * SDN_MAX_TERMS + 4];
   for (int i = 0; i < x; ++i) xv[i] = a.x0 ? (double)a.x0[i] : 0.0;
   for (int i = 0; i < b; ++i) xh[i] = a.xhat0 ? (double)a.xhat0[i] : 0.0;
   T* xo = a.x_out + idx * (size_t)(Tn + 1) * x;
@@ -107,7 +110,7 @@ __global__ void k_simulate(SimArgs<T> a) {
   for (int i = 0; i < x; ++i) xo[i] = (T)xv[i];
   if (ho) for (int i = 0; i < b; ++i) ho[i] = (T)xh[i];
   for (int t = 0; t < Tn; ++t) {
-    for (int k = 0; k < x + y; k += 4) {
+    for (int k = 0; k < x + y + a.nc + a.nd; k += 4) {   // (nc = nd = 0: the same stream as without the extension)
       float4 g = curand_normal4(&rng);
       nz[k] = g.x; nz[k + 1] = g.y; nz[k + 2] = g.z; nz[k + 3] = g.w;
     }
@@ -124,6 +127,12 @@ __global__ void k_simulate(SimArgs<T> a) {
       for (int j = 0; j < u; ++j) v += mat_at<T>(a.dyn.B, s, t, i * u + j) * uv[j];
       xn[i] = v;
     }
+    for (int q = 0; q < a.nc; ++q)                                  // control-dependent noise: + eps'_q C_q u
+      for (int i = 0; i < x; ++i) {
+        double v = 0.0;
+        for (int j = 0; j < u; ++j) v += mat_at<T>(a.Cn, s, 0, (q * x + i) * u + j) * uv[j];
+        xn[i] += nz[x + y + q] * v;
+      }
     for (int i = 0; i < x; ++i) xv[i] = xn[i];
     for (int i = 0; i < y; ++i) {                                   // y = F x + W eta
       double v = 0.0;
@@ -131,6 +140,12 @@ __global__ void k_simulate(SimArgs<T> a) {
       for (int j = 0; j < y; ++j) v += mat_at<T>(a.dyn.W, s, t, i * y + j) * nz[x + j];
       yv[i] = v;
     }
+    for (int q = 0; q < a.nd; ++q)                                  // state-dependent observation noise: + eta'_q D_q x
+      for (int i = 0; i < y; ++i) {
+        double v = 0.0;
+        for (int j = 0; j < x; ++j) v += mat_at<T>(a.Dn, s, 0, (q * y + i) * x + j) * xv[j];
+        yv[i] += nz[x + y + a.nc + q] * v;
+      }
     for (int i = 0; i < b; ++i) {                                   // xp = A_a xhat + B_a u
       double v = 0.0;
       for (int j = 0; j < b; ++j) v += mat_at<T>(a.act.A, s, t, i * b + j) * xh[j];
@@ -156,7 +171,7 @@ __global__ void k_simulate(SimArgs<T> a) {
 namespace {
 template <class T>
 int simulate(const LqgkDims* d, const LqgkSpec* act, const LqgkSpec* dyn, const T* L, const T* l, const T* K, const T* x0, const T* xhat0,
-             uint64_t seed, T* x_out, T* xhat_out, T* y_out, T* u_out, void* stream) {
+             uint64_t seed, T* x_out, T* xhat_out, T* y_out, T* u_out, void* stream, const LqgkSdnNoise* nz = nullptr) {
   g_launches = 0;
   if (!d || !act || !dyn || !L || !K || !x_out) return LQGK_E_INVALID;
   if (d->S <= 0 || d->N <= 0 || d->T <= 0 || d->x <= 0 || d->b <= 0 || d->u <= 0 || d->y <= 0) return LQGK_E_INVALID;
@@ -165,6 +180,12 @@ int simulate(const LqgkDims* d, const LqgkSpec* act, const LqgkSpec* dyn, const 
   for (auto m : need)
     if (!m->ptr) return LQGK_E_INVALID;
   SimArgs<T> a{*act, *dyn, L, l, K, x0, xhat0, x_out, xhat_out, y_out, u_out, d->S, d->N, d->T, d->x, d->b, d->u, d->y, seed};
+  a.Cn = LqgkMat{nullptr, 0, 0}; a.Dn = LqgkMat{nullptr, 0, 0}; a.nc = 0; a.nd = 0;
+  if (nz) {
+    if (nz->nc < 0 || nz->nd < 0 || nz->nc > SDN_MAX_TERMS || nz->nd > SDN_MAX_TERMS) return LQGK_E_INVALID;
+    if ((nz->nc > 0 && !nz->C.ptr) || (nz->nd > 0 && !nz->D.ptr)) return LQGK_E_INVALID;
+    a.Cn = nz->C; a.Dn = nz->D; a.nc = nz->nc; a.nd = nz->nd;
+  }
   const size_t total = (size_t)d->S * d->N;
   k_simulate<T><<<(unsigned)((total + 63) / 64), 64, 0, (cudaStream_t)stream>>>(a);
   LQGK_LAUNCH_CHECK();
@@ -345,6 +366,17 @@ int lqgk_simulate_f64(const LqgkDims* dims, const LqgkSpec* actor, const LqgkSpe
                       const double* x0, const double* xhat0, uint64_t seed, double* x_out, double* xhat_out, double* y_out, double* u_out,
                       void* stream) {
   return simulate<double>(dims, actor, dynamics, L, l, K, x0, xhat0, seed, x_out, xhat_out, y_out, u_out, stream);
+}
+
+int lqgk_sdn_simulate_f32(const LqgkDims* dims, const LqgkSpec* actor, const LqgkSpec* dynamics, const LqgkSdnNoise* noise, const float* L,
+                          const float* l, const float* K, const float* x0, const float* xhat0, uint64_t seed, float* x_out, float* xhat_out,
+                          float* y_out, float* u_out, void* stream) {
+  return simulate<float>(dims, actor, dynamics, L, l, K, x0, xhat0, seed, x_out, xhat_out, y_out, u_out, stream, noise);
+}
+int lqgk_sdn_simulate_f64(const LqgkDims* dims, const LqgkSpec* actor, const LqgkSpec* dynamics, const LqgkSdnNoise* noise, const double* L,
+                          const double* l, const double* K, const double* x0, const double* xhat0, uint64_t seed, double* x_out,
+                          double* xhat_out, double* y_out, double* u_out, void* stream) {
+  return simulate<double>(dims, actor, dynamics, L, l, K, x0, xhat0, seed, x_out, xhat_out, y_out, u_out, stream, noise);
 }
 
 int lqgk_pack_obs_f32(int32_t N, int32_t T1, int32_t d, const float* x, float* x_tm, void* stream) {

@@ -341,7 +341,7 @@ def moments(actor: LQGSpec, dynamics: LQGSpec, x: torch.Tensor, Sigma0: Optional
     return mu, Sig
 
 
-def simulate(actor: LQGSpec, dynamics: LQGSpec, L, l, K, n: int, seed: int, x0=None, xhat0=None, return_all=False):
+def simulate(actor: LQGSpec, dynamics: LQGSpec, L, l, K, n: int, seed: int, x0=None, xhat0=None, return_all=False, C=None, D=None):
     """CUDA batched simulator (reference ``System.simulate``, lqg/system.py:62-140) for given gains ``L[(S,) T, u, b]``,
     ``l[(S,) T, u]``, ``K[(S,) T, b, y]``; returns ``x[(S,) n, T+1, xdim]`` (and xhat, y, u).  None if a dimension exceeds the
     kernel's limit (callers then use the torch slow path)."""
@@ -363,7 +363,7 @@ def simulate(actor: LQGSpec, dynamics: LQGSpec, L, l, K, n: int, seed: int, x0=N
 
     vec = lambda v: None if v is None else torch.as_tensor(v, dtype=dt, device=dev).reshape(-1).contiguous()
     out = lib.simulate(dims, act, dyn, per_sample(L, 3), per_sample(l, 2), per_sample(K, 3), seed, x0=vec(x0), xhat0=vec(xhat0),
-                       return_all=return_all, stream=_stream(dev))
+                       return_all=return_all, stream=_stream(dev), C_noise=C, D_noise=D)   # C, D: signal-dependent-noise extension
     if actor.A.dim() == 3 and dynamics.A.dim() == 3:
         return tuple(o[0] for o in out) if return_all else out[0]
     return out

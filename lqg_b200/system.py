@@ -160,6 +160,32 @@ class System:
     def conditional_distribution(self, x: torch.Tensor, Sigma0=None) -> ConditionalDistribution:
         return ConditionalDistribution(self, x, Sigma0)
 
+    def simulate_sdn(self, rng_key=0, n=1, signal_dep_noise=None, obs_dep_noise=None, C=None, D=None, gains=None, x0=None, xhat0=None,
+                     Sigma0=None, return_all=False):
+        """``simulate`` (system.py:62-140) under signal-dependent noise -- the generative model of ``log_likelihood_sdn``
+        (EXTENSION, oracle/sdn_np.py: sdn_simulate): control-dependent process noise ``sum_i eps'_i C_i u_t`` and state-dependent
+        observation noise ``sum_j eta'_j D_j x_{t+1}`` on top of V, W.  Arguments as in ``log_likelihood_sdn``; CUDA only."""
+        from lqg_b200.control import sdn
+        if C is None and signal_dep_noise is not None:
+            C = sdn.channel_noise(self, signal_dep_noise, "control")
+        if D is None and obs_dep_noise is not None:
+            D = sdn.channel_noise(self, obs_dep_noise, "observation")
+        if gains is None:
+            g, K = self._gains(Sigma0)
+            L, l = g.L, g.l
+        elif isinstance(gains, str):
+            if gains != "sdn":
+                raise ValueError("gains must be None, 'sdn' or a pair (L, K)")
+            sg = sdn.solve_for_actor(self, signal_dep_noise=signal_dep_noise, obs_dep_noise=obs_dep_noise, Sigma0=Sigma0)
+            L, K = (sg.L, sg.K) if self.actor.A.dim() == 4 else (sg.L[0], sg.K[0])
+            l = None
+        else:
+            (L, K), l = gains, None
+        out = runtime.simulate(self.actor, self.dynamics, L, l, K, n, int(rng_key), x0=x0, xhat0=xhat0, return_all=return_all, C=C, D=D)
+        if out is None:
+            raise NotImplementedError("simulate_sdn: a dimension exceeds the simulator kernel's limit (40)")
+        return out
+
     def log_likelihood_fp64(self, x: torch.Tensor, Sigma0=None) -> torch.Tensor:
         """``log_likelihood`` with the per-trial recursion in FP64 as well (the all-FP64 kernel k_sdn_loglik without
         multiplicative noise): for models whose innovation covariance is too ill-conditioned for the FP32 per-trial

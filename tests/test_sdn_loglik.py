@@ -313,3 +313,28 @@ def test_python_api_with_sdn_aware_actor_on_host(monkeypatch):
     ll_plain = model.log_likelihood_sdn(torch.tensor(X), signal_dep_noise=40.0, obs_dep_noise=0.4, gains=(torch.tensor(L0), torch.tensor(K0)))
     assert np.allclose(ll_plain.numpy(), S.sdn_log_likelihood(sa, sd, L0, K0, C, D, X.astype(np.float64)), rtol=1e-9)
     assert np.abs(ll_plain.numpy() - ll.numpy()).max() > 1e-3
+
+
+@pytest.mark.gpu
+def test_sdn_simulator_matches_the_exact_moment_recursion():
+    """lqgk_sdn_simulate (System.simulate_sdn): mean and covariance of the simulated (x, xhat)_t equal the oracle's EXACT
+    unconditional moments (sdn_moments) where the multiplicative terms change the covariance by > 20 %."""
+    from lqg_b200.tracking import SubjectiveActor
+    dev = torch.device("cuda:0")
+    T_, n, x0 = 30, 200000, [2.0, -1.0]
+    model = SubjectiveActor(dim=1, T=T_, dtype=torch.float64, device=dev)
+    x, xh, y, u = model.simulate_sdn(5, n=n, signal_dep_noise=60.0, obs_dep_noise=0.6, x0=x0, return_all=True)
+    assert tuple(x.shape) == (n, T_ + 1, 2) and tuple(xh.shape) == (n, T_ + 1, 3)
+    _, sa, sd, L, K = _system("subjective", T=T_)
+    C, D = _channel_noise_np(sd, 60.0, 0.6)
+    mus, Sigs = S.sdn_moments(sa, sd, L, K, C, D, x0=np.array(x0))
+    _, S0 = S.sdn_moments(sa, sd, L, K, [], [], x0=np.array(x0))
+    assert np.abs(Sigs[-1] - S0[-1]).max() > 0.2 * np.abs(S0[-1]).max()
+    for t in (10, T_):
+        z = torch.cat([x[:, t], xh[:, t]], 1).cpu().numpy()
+        assert np.abs(z.mean(0) - mus[t]).max() < 5 * np.sqrt(np.diag(Sigs[t])).max() / np.sqrt(n)
+        emp = np.cov(z.T)
+        assert np.abs(emp - Sigs[t]).max() < 0.02 * np.abs(Sigs[t]).max(), (t, np.abs(emp - Sigs[t]).max() / np.abs(Sigs[t]).max())
+    # the simulated data are plausible under the matching likelihood model: higher mean log-likelihood than without the noise terms
+    xs = x[:512].to(torch.float32)
+    assert model.log_likelihood_sdn(xs, signal_dep_noise=60.0, obs_dep_noise=0.6).mean() > model.log_likelihood_sdn(xs).mean()
