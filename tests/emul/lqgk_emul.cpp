@@ -42,7 +42,7 @@ static bool time_varying(const LqgkSpec& s) {
 template <class DM, class T>
 int run(const LqgkDims& d, const LqgkSpec* act, const LqgkSpec* dyn, const LqgkMat* sigma0, const float* x_tm,
         const T* ll_bar, T* ll_out, const LqgkSpecGrad* gact, const LqgkSpecGrad* gdyn, const LqgkMatGrad* gsig0,
-        bool want_grad, T* L_out, T* l_out, T* H_out, T* K_out, double eps, int mode) {
+        bool want_grad, T* L_out, T* l_out, T* H_out, T* K_out, double eps, int mode, T* mu_out = nullptr, T* Sig_out = nullptr) {
   const int S = d.S, N = d.N, Tn = d.T;
   constexpr CLayout cl = DM::CL;
   const bool has_dyn = dyn != nullptr;
@@ -98,7 +98,25 @@ int run(const LqgkDims& d, const LqgkSpec* act, const LqgkSpec* dyn, const LqgkM
   for (int s = 0; s < S; ++s) {
     GCst g{cst.data() + s, Sc, tstride};
     RecSink sink{rec.data() + (size_t)s * Tn * DM::REC, DM::REC, rec.data() + (size_t)s * Tn * DM::REC};
-    cov_fwd_body<DM>(g, WView{lc.data(), 1}, Tn, V(Lw, s), V(Kw, s), want_grad, V(Cw, s), V(FUw, s), V(JSw, s), V(J0w, s), sink);
+    if (mode == LQGK_MODE_MOMENTS)   // (what k_cov_moments does: the record plus the full predictive joint covariance of every step)
+      cov_fwd_body<DM>(g, WView{lc.data(), 1}, Tn, V(Lw, s), V(Kw, s), false, V(Cw, s), V(FUw, s), V(JSw, s), V(J0w, s), sink,
+                       [&](int t, int e, double v) { if (Sig_out) Sig_out[((size_t)s * Tn + t) * (DM::N * DM::N) + e] = (T)v; });
+    else
+      cov_fwd_body<DM>(g, WView{lc.data(), 1}, Tn, V(Lw, s), V(Kw, s), want_grad, V(Cw, s), V(FUw, s), V(JSw, s), V(J0w, s), sink);
+  }
+  if (mode == LQGK_MODE_MOMENTS) {   // (k_trial_moments)
+    if (mu_out)
+      for (int s = 0; s < S; ++s)
+        for (int i = 0; i < N; ++i) {
+          const float* xs = x_tm + (size_t)s * d.x_sample_stride;
+          float c[DM::R] = {0}, mu[DM::N];
+          for (int t = 0; t < Tn; ++t) {
+            Trial<DM>::template moments<float>(rec.data() + ((size_t)s * Tn + t) * DM::REC, xs + ((size_t)t * N + i) * DM::D,
+                                               xs + ((size_t)(t + 1) * N + i) * DM::D, c, mu);
+            for (int k = 0; k < DM::N; ++k) mu_out[(((size_t)s * N + i) * Tn + t) * DM::N + k] = (T)mu[k];
+          }
+        }
+    return LQGK_OK;
   }
   // the library stores these adjoint linearisation points in FP32 (lin_t in lqgk_kernels.cuh): mirror the rounding
   for (auto& v : FUw) v = (double)(float)v;
@@ -176,12 +194,12 @@ int run(const LqgkDims& d, const LqgkSpec* act, const LqgkSpec* dyn, const LqgkM
 template <class T>
 int dispatch(const LqgkDims* d, const LqgkSpec* act, const LqgkSpec* dyn, const LqgkMat* sigma0, const float* x_tm,
              const T* ll_bar, T* ll_out, const LqgkSpecGrad* gact, const LqgkSpecGrad* gdyn, const LqgkMatGrad* gsig0,
-             bool want_grad, T* L_out, T* l_out, T* H_out, T* K_out, double eps, int mode) {
+             bool want_grad, T* L_out, T* l_out, T* H_out, T* K_out, double eps, int mode, T* mu_out = nullptr, T* Sig_out = nullptr) {
   if (!d || !act) return LQGK_E_INVALID;
 #define LQGK_CASE(X, B, U, Y, D)                                                                              \
   if (d->x == X && d->b == B && d->u == U && d->y == Y && (d->d == D || mode == LQGK_MODE_GAINS))             \
     return run<Dims<X, B, U, Y, D>, T>(*d, act, dyn, sigma0, x_tm, ll_bar, ll_out, gact, gdyn, gsig0, want_grad, \
-                                       L_out, l_out, H_out, K_out, eps, mode);
+                                       L_out, l_out, H_out, K_out, eps, mode, mu_out, Sig_out);
   LQGK_FOR_EACH_DIMS(LQGK_CASE)
 #undef LQGK_CASE
   return LQGK_E_UNSUPPORTED;
@@ -286,6 +304,18 @@ int lqgk_loglik_vjp_f32(const LqgkDims* dims, const LqgkSpec* actor, const LqgkS
                         const LqgkSpecGrad* gd, const LqgkMatGrad* gs, void*, size_t, void*) {
   return dispatch<float>(dims, actor, dynamics, sigma0, x_tm, ll_bar, ll_out, ga, gd, gs, true, nullptr, nullptr,
                          nullptr, nullptr, 1e-8, LQGK_MODE_VJP);
+}
+int lqgk_moments_f64(const LqgkDims* dims, const LqgkSpec* actor, const LqgkSpec* dynamics, const LqgkMat* sigma0, const float* x_tm,
+                     double* mu_out, double* Sigma_out, void*, size_t, void*) {
+  if (dims && dims->x + dims->b > 12) return LQGK_E_UNSUPPORTED;
+  return dispatch<double>(dims, actor, dynamics, sigma0, x_tm, nullptr, nullptr, nullptr, nullptr, nullptr, false, nullptr, nullptr,
+                          nullptr, nullptr, 1e-8, LQGK_MODE_MOMENTS, mu_out, Sigma_out);
+}
+int lqgk_moments_f32(const LqgkDims* dims, const LqgkSpec* actor, const LqgkSpec* dynamics, const LqgkMat* sigma0, const float* x_tm,
+                     float* mu_out, float* Sigma_out, void*, size_t, void*) {
+  if (dims && dims->x + dims->b > 12) return LQGK_E_UNSUPPORTED;
+  return dispatch<float>(dims, actor, dynamics, sigma0, x_tm, nullptr, nullptr, nullptr, nullptr, nullptr, false, nullptr, nullptr,
+                         nullptr, nullptr, 1e-8, LQGK_MODE_MOMENTS, mu_out, Sigma_out);
 }
 int lqgk_pack_obs_f32(int32_t N, int32_t T1, int32_t d, const float* x, float* x_tm, void*) { return pack_obs_host(N, T1, d, x, x_tm); }
 int lqgk_pack_obs_f64(int32_t N, int32_t T1, int32_t d, const double* x, float* x_tm, void*) { return pack_obs_host(N, T1, d, x, x_tm); }

@@ -84,3 +84,19 @@ def test_per_condition_data_in_one_call(host):
     ll.sum().backward()
     assert np.allclose(ll.detach().numpy(), np.stack(lls), rtol=1e-5)
     assert np.allclose(st.grad.numpy(), np.array(grads), rtol=1e-3)
+
+
+@pytest.mark.parametrize("name,cls,kw", [("subjective", tracking.SubjectiveActor, {}), ("bounded2", tracking.BoundedActor, {"dim": 2})])
+def test_predictive_moments(host, name, cls, kw):
+    """runtime.moments (what System.conditional_moments / belief_tracking_distribution call on the GPU, lqg/system.py:142-235,
+    250-257): mu[n, T, nj], Sigma[T, nj, nj] against the oracle's literal restatement of the reference scan."""
+    T, N = 40, 3
+    mats = H.model_mats(name)
+    X = _sim(mats, T, N, seed=3).astype(np.float32)
+    model = cls(T=T, dtype=torch.float64, **kw)
+    mu, Sig = runtime.moments(model.actor, model.dynamics, torch.tensor(X))
+    sa, sd = O.make_system(mats, T)
+    for i in range(N):
+        mo, So = O.conditional_moments(sa, sd, X[i].astype(np.float64))
+        assert np.allclose(mu[i].numpy(), mo, rtol=1e-4, atol=1e-4 * np.abs(mo).max()), (i, np.abs(mu[i].numpy() - mo).max())
+        assert np.allclose(Sig.numpy(), So, rtol=1e-9, atol=1e-12)
