@@ -139,3 +139,57 @@ def subjective_actor(dim=1, process_noise=1.0, action_cost=1.0, action_variabili
                V=Vfull[..., p, :],
                R=_t(action_cost).to(torch.float64)[..., None, None] * torch.eye(dim, dtype=torch.float64))
     return act, dyn
+
+
+# --------------------------------------------------------------------------- signal-dependent noise (extension, oracle/sdn_np.py)
+def sdn_log_likelihood(act, dyn, X, c_scale, d_scale, T=None):
+    """Differentiable twin of oracle/sdn_np.py: sdn_log_likelihood for ONE (un-batched) parameter vector with the per-channel
+    noise model of lqg_b200.control.sdn.channel_noise (C_i = c_scale B_d[:, i] e_i^T, D_j = d_scale e_j e_j^T F_d) and the actor's
+    own lqr.backward / kf.forward gains.  The autograd gradient of this function is the independent check of the batched
+    central differences the product uses for the signal-dependent-noise likelihood.  X[N, T+1, d] -> ll[N]."""
+    X = X.to(torch.float64)
+    N, T1, d = X.shape
+    T = T1 - 1 if T is None else T
+    Aa, Ba, Fa, Va, Wa, Q, R = (act[k] for k in ("A", "B", "F", "V", "W", "Q", "R"))
+    Ad, Bd, Fd, Vd, Wd = (dyn[k] for k in ("A", "B", "F", "V", "W"))
+    x, b, u, y = Ad.shape[-1], Aa.shape[-1], Bd.shape[-1], Wd.shape[-1]
+    L = lqr_backward(Aa, Ba, Q, R, T)
+    K = kf_forward(Aa, Fa, Va, Wa, Va @ mT(Va), T)
+    eye_u, eye_y = torch.eye(u, dtype=X.dtype), torch.eye(y, dtype=X.dtype)
+    Cs = [c_scale * Bd[:, i:i + 1] @ eye_u[i:i + 1] for i in range(u)]
+    Ds = [d_scale * eye_y[:, j:j + 1] @ Fd[j:j + 1] for j in range(y)]
+    Dm = Fd @ Bd - Fa @ Ba
+    n = x + b
+    ll = torch.zeros(N, dtype=X.dtype)
+
+    def joint(t):
+        Lt, Kt = L[t], K[t]
+        Fj = torch.cat([torch.cat([Ad, Bd @ Lt], -1), torch.cat([Kt @ Fd @ Ad, Aa + Ba @ Lt - Kt @ Fa @ Aa + Kt @ Dm @ Lt], -1)], -2)
+        Gj = torch.cat([torch.cat([Vd, torch.zeros(x, y, dtype=X.dtype)], -1), torch.cat([Kt @ Fd @ Vd, Kt @ Wd], -1)], -2)
+        return Fj, Gj @ mT(Gj)
+
+    _, N0 = joint(0)
+    for i in range(N):                                                   # the covariance is per trial here
+        mu = torch.cat([X[i, 0], torch.zeros(n - d, dtype=X.dtype)])
+        Sig = N0
+        for t in range(T):
+            Fj, Nj = joint(t)
+            Soo = Sig[:d, :d]
+            g = torch.linalg.solve(Soo, X[i, t] - mu[:d])
+            mu_c = mu + Sig[:, :d] @ g
+            Sig_c = Sig - Sig[:, :d] @ torch.linalg.solve(Soo, Sig[:d, :])
+            Z2 = Sig_c + torch.outer(mu_c, mu_c)
+            U2 = L[t] @ Z2[x:, x:] @ mT(L[t])
+            mu = Fj @ mu_c
+            Sig = Fj @ Sig_c @ mT(Fj) + Nj
+            for Ci in Cs:
+                gi = torch.cat([Ci, K[t] @ Fd @ Ci], 0)
+                Sig = Sig + gi @ U2 @ mT(gi)
+            X2 = Sig[:x, :x] + torch.outer(mu[:x], mu[:x])
+            add = sum((K[t] @ Dj) @ X2 @ mT(K[t] @ Dj) for Dj in Ds)
+            Sig = Sig + torch.nn.functional.pad(add, (x, 0, x, 0))
+            Sig = 0.5 * (Sig + mT(Sig))
+            Lc = torch.linalg.cholesky(Sig[:d, :d])
+            z = torch.linalg.solve_triangular(Lc, (X[i, t + 1] - mu[:d])[:, None], upper=False)[:, 0]
+            ll[i] = ll[i] - 0.5 * d * LOG2PI - torch.log(torch.diagonal(Lc)).sum() - 0.5 * (z * z).sum()
+    return ll

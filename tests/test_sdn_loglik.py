@@ -338,3 +338,32 @@ def test_sdn_simulator_matches_the_exact_moment_recursion():
     # the simulated data are plausible under the matching likelihood model: higher mean log-likelihood than without the noise terms
     xs = x[:512].to(torch.float32)
     assert model.log_likelihood_sdn(xs, signal_dep_noise=60.0, obs_dep_noise=0.6).mean() > model.log_likelihood_sdn(xs).mean()
+
+
+def test_oracle_gradient_by_autograd_equals_central_differences():
+    """The reference gradient of the signal-dependent-noise likelihood in the GPU tests is a central difference of the NumPy
+    oracle; an independent torch-autograd twin of the same recursion (oracle/lqg_torch.py) gives the same value and gradient."""
+    from oracle import lqg_torch as OT
+    T_ = 25
+    th0 = np.array([1.0, 6.0, 40.0, 0.4])                              # action_cost, sigma_target, signal_dep_noise, obs_dep_noise
+
+    def total_np(th):
+        mats = O.subjective_actor_mats(dim=1, action_cost=th[0], sigma_target=th[1])
+        sa, sd = O.make_system(mats, T_)
+        L, _, _ = O.lqr_backward(sa)
+        K = O.kf_forward(sa, sa["V"][0] @ sa["V"][0].T)
+        C, D = _channel_noise_np(sd, th[2], th[3])
+        return S.sdn_log_likelihood(sa, sd, L, K, C, D, X).sum()
+
+    _, sa, sd, L, K = _system("subjective", T=T_)
+    X = S.sdn_simulate(sa, sd, L, K, *_channel_noise_np(sd, 40.0, 0.4), 3, np.random.default_rng(9))[0]
+    th = torch.tensor(th0, dtype=torch.float64, requires_grad=True)
+    a, d = OT.subjective_actor(dim=1, action_cost=th[0], sigma_target=th[1])
+    ll = OT.sdn_log_likelihood(a, d, torch.tensor(X), th[2], th[3])
+    ll.sum().backward()
+    assert abs(ll.sum().item() - total_np(th0)) < 1e-9 * abs(total_np(th0))
+    for p in range(4):
+        h = 1e-5 * th0[p]
+        e = np.zeros(4); e[p] = h
+        fd = (total_np(th0 + e) - total_np(th0 - e)) / (2 * h)
+        assert abs(th.grad[p].item() - fd) <= 1e-5 * abs(fd) + 1e-8, (p, th.grad[p].item(), fd)
