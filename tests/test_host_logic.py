@@ -25,3 +25,11 @@ def test_default_terminal_cost_and_zero_cross_cost_are_recognised_without_readin
     spb = time_stack_spec(I.expand(S, 2, 2), I[:, :1], I, I, I, I, I[:1, :1] * torch.arange(1.0, 4.0)[:, None, None], T=5)
     assert runtime._qf_is_default(spb) and is_known_zero(spb.P)
     assert not is_known_zero(spb.P.clone())
+
+
+def test_dimension_tuple_lists_are_parsed_from_the_header():
+    """lqg_b200.dims reads csrc/lqgk_dims.h (one source of truth): the tuples of the main path and the ones compiled for the
+    all-FP64 per-trial likelihood only."""
+    from lqg_b200 import dims
+    assert (2, 3, 1, 2, 2) in dims.SUPPORTED_DIMS and (12, 12, 1, 3, 2) in dims.SUPPORTED_DIMS and len(dims.SUPPORTED_DIMS) == 10
+    assert dims.FP64_ONLY_DIMS == [(4, 4, 1, 3, 4)] and not set(dims.FP64_ONLY_DIMS) & set(dims.SUPPORTED_DIMS)
